@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the VQ-NeRF decomp shading path on B200.
+
+A "step" is one pass of the hot path over one batch of synthetic input: the full-image relighting call
+`Model.fast_render(batch, mode='test', relight_probes=True)` (reference: nerfactor/test.py:254-266 ->
+models/vq_nfr.py:262-398) on an 800x800 NeRF-Blender-shaped view = 640 000 surface points, 16x32 (512-light)
+probe, P novel probes, random-init weights (BASELINE.json configs[1]).  At N GPUs the job is N such views per
+step, pixel rows sharded contiguously over the ranks (weak scaling, 640 000 points per GPU), with the single
+NCCL all-gather of the shaded pixels inside the timed step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--probes P] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  `value` = shaded points/s with inputs resident in HBM; `e2e` = the same call
+with HOST (pinned) input buffers, H2D copies and the D2H read of the shaded image inside the timed region.
+`--impl reference` times the CPU restatement of the reference (oracle/decomp_oracle.py, kind "port": the
+TensorFlow reference cannot run in this image) on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H = W = 800
+N_POINTS = H * W
+# algorithmic work per point (BASELINE.md section 4 / SURVEY.md 8d)
+MLP_ENC_FLOP = 2 * 179968
+MLP_HEADS_FLOP = 2 * 296832
+SHADE_FLOP_PER_LIGHT = 110.0
+CPU_SAMPLE_POINTS = 4096
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--probes', type=int, default=8, help='novel relight probes P (plus the model light)')
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--points', type=int, default=N_POINTS, help='points per GPU per step (default 800x800)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--precision', default='fp32', choices=['fp32', 'bf16', 'tf32x3'])
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+def synth_view(n, seed, probes):
+    """Synthetic view of SURVEY.md 8d config #2 (all foreground = worst case)."""
+    rng = np.random.default_rng(seed)
+    xyz = rng.uniform(-1, 1, size=(n, 3)).astype(np.float32)
+    rayo = rng.normal(size=(n, 3)).astype(np.float32)
+    rayo = 4.0 * rayo / np.linalg.norm(rayo, axis=1, keepdims=True)
+    normal = rng.normal(size=(n, 3)).astype(np.float32)
+    normal /= np.linalg.norm(normal, axis=1, keepdims=True)
+    lvis = rng.random(size=(n, 512), dtype=np.float32)
+    alpha = np.ones((n, 1), np.float32)
+    rgb = rng.random(size=(n, 3), dtype=np.float32)
+    return {'xyz': xyz, 'rayo': rayo.astype(np.float32), 'rayd': (-rayo / 4.0).astype(np.float32),
+            'normal': normal.astype(np.float32), 'lvis': lvis, 'alpha': alpha, 'pred_alpha': alpha.copy(), 'rgb': rgb}
+
+
+def synth_probes(p, seed=123):
+    rng = np.random.default_rng(seed)
+    return {'probe%02d' % i: (np.abs(rng.normal(size=(16, 32, 3))) * 0.5).astype(np.float32) for i in range(p)}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': float(max(mx)) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('hbm_gbs', 6650.0), d.get('bf16_tflops', 1590.0), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 1590.0, 'fallback (B200_PROFILING.md)'
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(probes, sample=CPU_SAMPLE_POINTS, steps=1):
+    """The reference's CPU path: the op-for-op PyTorch-CPU restatement (incl. the [N,512,3] intermediates) on all
+    host cores, on a bounded sample of the same workload."""
+    import torch
+    from oracle import decomp_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    scene = O.synth_scene(0, n_probes=probes)
+    batch = O.synth_batch(sample, 0)
+    O.fast_render(scene, O.synth_batch(256, 1), torch.float32, relight_probes=probes > 0)   # warm-up
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        O.fast_render(scene, batch, torch.float32, relight_probes=probes > 0)
+        times.append(time.perf_counter() - t0)
+    dt = float(np.mean(times))
+    return {'value': sample / dt, 'unit': 'points/s', 'cores': cores, 'kind': 'port',
+            'sample': '%d of %d points of the 800x800 view, %d relight probes, fp32 torch-CPU restatement of '
+                      'vq_nfr.fast_render incl. [N,512,3] intermediates; %.2f s per pass' % (sample, N_POINTS, probes, dt)}, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cb, _ = cpu_baseline(args.probes, CPU_SAMPLE_POINTS, steps=1)      # warm-up pass (untimed result discarded)
+    times = []
+    for _ in range(max(1, min(args.steps, 3))):
+        r, dt = cpu_baseline(args.probes, CPU_SAMPLE_POINTS, steps=1)
+        times.append(dt)
+    dt = float(np.mean(times))
+    val = CPU_SAMPLE_POINTS / dt
+    cb['value'] = val
+    line = {'metric': 'shaded surface points/sec', 'value': val, 'unit': 'points/s', 'n_gpus': args.gpus,
+            'steps': len(times), 'warmup': 1, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
+            'config': {'workload': 'vq_nfr.fast_render relight, %d-point sample of an 800x800 view, 512 lights, '
+                                   'P=%d probes, CPU restatement of the reference' % (CPU_SAMPLE_POINTS, args.probes)},
+            'cpu_baseline': cb,
+            'e2e': {'value': val, 'unit': 'points/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- the product path has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    from vqnerf_release_b200 import _lib, abi, dist as vdist
+    from vqnerf_release_b200.nerfactor.models.vq_nfr import Model
+
+    n = args.points
+    P = args.probes
+    model = Model({'data_type': 'nerf', 'random_seed': 2, 'precision': args.precision},
+                  light=(np.abs(np.random.default_rng(5).normal(size=(16, 32, 3))) * 0.5).astype(np.float32),
+                  novel_probes=synth_probes(P), device=dev)
+    host = synth_view(n, 1000 + rank, P)
+    keys = ('rayo', 'rayd', 'rgb', 'alpha', 'pred_alpha', 'xyz', 'normal', 'lvis')
+    pinned = {k: torch.from_numpy(host[k]).pin_memory() for k in keys}
+    devt = {k: pinned[k].to(dev, non_blocking=True) for k in keys}
+    hw = torch.zeros((n, 2), dtype=torch.int32, device=dev)
+    id_ = 'synthetic'
+
+    def batch_of(d):
+        return (id_, hw, d['rayo'], d['rayd'], d['rgb'], d['alpha'], d['pred_alpha'], d['xyz'], d['normal'], d['lvis'])
+
+    ctx = _lib.Context.get(dev)
+    n_global = n * world
+
+    def step(d):
+        pred, _, _, _ = model.fast_render(batch_of(d), mode='test', relight_probes=True)
+        img = pred['rgb_probes'] if P > 0 else pred['albedo']
+        if world > 1:
+            img = vdist.gather_rows(img, n_global)       # the single collective of a pixel-sharded render
+        return img, pred
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing -------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step(devt)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    model.stage_events = []
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(devt)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - l0
+    events = model.stage_events
+    model.stage_events = None
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = n_global / (ms_step * 1e-3)
+
+    # per-stage device time (same timed region, CUDA events on the launching stream)
+    stage_ms = {}
+    per = len(events) // args.steps if args.steps else 0
+    for s in range(args.steps):
+        chunk = events[s * per:(s + 1) * per]
+        for (na, ea), (nb, eb) in zip(chunk[:-1], chunk[1:]):
+            stage_ms.setdefault(nb, []).append(ea.elapsed_time(eb))
+    stage_ms = {k: float(np.mean(v)) for k, v in stage_ms.items()}
+
+    # ---- end-to-end: host buffers in, shaded image out ------------------------------------------
+    out_host = None
+    h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in keys)
+
+    def e2e_step():
+        nonlocal out_host
+        d = {k: pinned[k].to(dev, non_blocking=True) for k in keys}
+        img, _ = step(d)
+        if out_host is None:
+            out_host = torch.empty(img.shape, dtype=img.dtype).pin_memory()
+        out_host.copy_(img, non_blocking=True)
+        return img
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    k_e2e = max(2, min(args.steps, 5))
+    e0.record()
+    for _ in range(k_e2e):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / k_e2e
+    d2h = out_host.numel() * out_host.element_size()
+
+    if rank == 0:
+        hbm_peak, bf16_peak, peak_src = measured_peaks()
+        # FP32-FMA peak of this GPU, measured live (not in MEASURED_PEAKS.json)
+        import ctypes as C
+        tf = C.c_double()
+        _lib.check(ctx.lib.vqn_microbench_fma(ctx.handle, 0, 2000, C.byref(tf)))
+        fp32_peak = float(tf.value)
+        tf2 = C.c_double()
+        _lib.check(ctx.lib.vqn_microbench_fma(ctx.handle, 1, 2000, C.byref(tf2)))
+        heads_ms = stage_ms.get('mlp_heads', float('nan'))
+        enc_ms = stage_ms.get('mlp_enc', float('nan'))
+        shade_ms = stage_ms.get('shade', float('nan'))
+        if args.precision == 'fp32':
+            # dominant kernel: mlp_simt_kernel (heads launch); FFMA-bound, so the roofline is the fp32-FMA peak
+            ach = MLP_HEADS_FLOP * n / (heads_ms * 1e-3) / 1e12
+            roof = {'bound': 'fp32_fma', 'kernel': 'mlp_simt_kernel (3 main heads, %d points/launch)' % n,
+                    'achieved': ach, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': ach / fp32_peak,
+                    'peak_source': 'FFMA peak measured live by vqn_microbench_fma on this GPU '
+                                   '(FFMA2 packed: %.1f TFLOP/s); tensor peak for reference: %.0f bf16 TFLOP/s %s'
+                                   % (float(tf2.value), bf16_peak, peak_src),
+                    'traffic': None}
+        else:
+            peak = bf16_peak if args.precision == 'bf16' else bf16_peak / 2 / 3
+            ach = MLP_HEADS_FLOP * n / (heads_ms * 1e-3) / 1e12
+            roof = {'bound': 'tensor', 'kernel': 'mlp_tc_kernel (3 main heads)', 'achieved': ach, 'peak': peak,
+                    'unit': 'TFLOP/s', 'frac': ach / peak, 'peak_source': peak_src, 'traffic': None}
+        shade_bytes = n * (2048 + 36 + 28 + 12 * (1 + P))
+        kernels = {
+            'mlp_enc': {'ms': enc_ms, 'tflops': MLP_ENC_FLOP * n / (enc_ms * 1e-3) / 1e12},
+            'mlp_heads': {'ms': heads_ms, 'tflops': MLP_HEADS_FLOP * n / (heads_ms * 1e-3) / 1e12},
+            'shade': {'ms': shade_ms, 'gbs': shade_bytes / (shade_ms * 1e-3) / 1e9,
+                      'tflops': n * 512 * (SHADE_FLOP_PER_LIGHT + 6 * (1 + P)) / (shade_ms * 1e-3) / 1e12,
+                      'hbm_frac': shade_bytes / (shade_ms * 1e-3) / 1e9 / hbm_peak},
+            'other_ms': {k: v for k, v in stage_ms.items() if k not in ('mlp_enc', 'mlp_heads', 'shade')},
+        }
+        cb = None
+        if not args.no_cpu_baseline:
+            cb, _ = cpu_baseline(P)
+        line = {
+            'metric': 'shaded surface points/sec', 'value': value, 'unit': 'points/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': {'fp32': 'f32', 'bf16': 'bf16', 'tf32x3': 'tf32x3'}[args.precision],
+            'data': 'synthetic',
+            'config': {'workload': 'vq_nfr.fast_render full-image relight: %d points/GPU (800x800 view, all foreground), '
+                                   '512-light probe + P=%d novel probes, random-init MLPs, K=15 codebook' % (n, P),
+                       'points_per_gpu': n, 'probes': P, 'precision': args.precision,
+                       'parallelism': 'pixel rows sharded x%d, one NCCL all-gather' % world if world > 1 else 'single GPU',
+                       'l2': 'inputs (%.2f GB lvis per step) larger than the 126 MB L2, no flush needed' % (n * 2048 / 1e9)},
+            'e2e': {'value': n_global / (e2e_ms * 1e-3), 'unit': 'points/s', 'ms_per_step': e2e_ms,
+                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+            'gpu_launches': int(launches),
+            'clocks': clocks,
+            'roofline': roof,
+            'kernels': kernels,
+            'cpu_baseline': cb,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,258 @@
+/*
+ * vqnerf_b200.h -- C ABI of libvqnerf_b200.so
+ *
+ * Drop-in boundary for the VQ-NeRF decomposition-stage per-surface-point shading path
+ * (reference: decomp/nerfvq_nfr3, NeRFactor-derived) and the NeuS geo-stage per-ray scan
+ * (reference: geo/NeuS-ours2/models/renderer.py), implemented as hand-written sm_100a CUDA.
+ *
+ * The reference has no FFI layer: its "operator API" is the Python method surface of
+ * nerfactor/models/vq_nfr.py::Model and nerfactor/networks/*.  Every entry point below
+ * cites the reference method (file:line, relative to /root/reference/) it replaces; the
+ * Python mirror in vqnerf_release_b200/nerfactor/ binds them with ctypes (INTEGRATION.md
+ * shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C types only; all tensor pointers are DEVICE pointers to row-major contiguous
+ *     fp32 unless stated; indices are int64 (TF argmax default);
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous w.r.t. the host
+ *     and never synchronises (the reference's .numpy() sync at vq_layers.py:318 is NOT
+ *     reproduced);
+ *   - every function returns a vqn_status; nothing aborts; vqn_status_str() names a code and
+ *     vqn_last_error() returns the thread-local detail string of the last failure;
+ *   - no hidden global state: learned state (weights, EMA hidden/average/counter, codebook)
+ *     lives in caller-owned buffers so the caller's checkpointing keeps working.
+ */
+#ifndef VQNERF_B200_H_
+#define VQNERF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQN_ABI_VERSION 1
+#define VQN_MAX_LAYERS 8
+#define VQN_NUM_LIGHTS 512 /* 16 x 32 probe, vq_nfr.ini:51 */
+
+typedef enum vqn_status {
+  VQN_OK = 0,
+  VQN_ERR_INVALID_ARG = 1,   /* bad shape / null pointer / unsupported size  (Python: ValueError)         */
+  VQN_ERR_CUDA = 2,          /* CUDA runtime error (detail in vqn_last_error)  (Python: RuntimeError)      */
+  VQN_ERR_NONFINITE = 3,     /* check_numerics failure (vq_nfr.py:783,802,815,827,731) (InvalidArgument)  */
+  VQN_ERR_UNSUPPORTED = 4,   /* feature not built / wrong GPU architecture                                */
+  VQN_ERR_ZERO_NORM = 5      /* assert_greater on direction norms (shape.py:107-109,116-118)              */
+} vqn_status;
+
+typedef enum vqn_act { VQN_ACT_NONE = 0, VQN_ACT_RELU = 1, VQN_ACT_SIGMOID = 2 } vqn_act;
+
+/* arithmetic mode of the MLP kernels */
+typedef enum vqn_precision {
+  VQN_PREC_FP32 = 0,   /* fp32 FFMA on CUDA cores; parity mode (1e-4 rel)                     */
+  VQN_PREC_BF16 = 1,   /* tcgen05 kind::f16 bf16 operands, fp32 accumulate in TMEM (1e-2 rel) */
+  VQN_PREC_TF32X3 = 2  /* tcgen05 kind::tf32 hi/lo split, fp32 accumulate (1e-4 rel)          */
+} vqn_precision;
+
+typedef struct vqn_ctx vqn_ctx; /* one per device; re-entrant across streams */
+typedef struct vqn_net vqn_net; /* device-side packed copy of one mlp.Network */
+typedef void* vqn_stream;       /* cudaStream_t */
+
+int vqn_abi_version(void);
+const char* vqn_status_str(int status);
+const char* vqn_last_error(void);
+
+int vqn_ctx_create(int device, vqn_ctx** out);
+int vqn_ctx_destroy(vqn_ctx* ctx);
+/* number of kernels this library has launched on this ctx since creation (bench.py gpu_launches) */
+int64_t vqn_ctx_launch_count(const vqn_ctx* ctx);
+/* check_numerics flag: device-side sticky flag set by kernels that saw NaN/Inf in an output that the
+ * reference guards with tf.debugging.check_numerics; read (with a sync of `stream`) and cleared here. */
+int vqn_ctx_check_numerics(vqn_ctx* ctx, vqn_stream stream);
+
+/* ---- light probe geometry: brdf/renderer.py:184-219 gen_light_xyz (host, float64) ------------- */
+int vqn_gen_light_xyz(int envmap_h, int envmap_w, double envmap_radius, double* xyz_out /*[h,w,3]*/,
+                      double* areas_out /*[h,w]*/);
+
+/* ---- networks -------------------------------------------------------------------------------- */
+/* nerfactor/networks/mlp.py:24-50 Network(widths, act, skip_at): Keras Dense kernels [in,out], bias
+ * [out]; after layer `skip_at` the activation becomes concat(y, x_input).  skip_at = -1: none. */
+typedef struct vqn_net_desc {
+  int32_t n_layers;
+  int32_t in_dim;
+  int32_t skip_at;
+  int32_t reserved;
+  int32_t widths[VQN_MAX_LAYERS];
+  int32_t acts[VQN_MAX_LAYERS];
+  const float* w[VQN_MAX_LAYERS]; /* device, [in_i, widths[i]] */
+  const float* b[VQN_MAX_LAYERS]; /* device, [widths[i]]       */
+} vqn_net_desc;
+
+/* Pack (pad / transpose / split for the tensor-core modes) the weights into library-owned device
+ * memory.  vqn_net_repack re-reads the caller's weight buffers after an optimizer step. */
+int vqn_net_create(vqn_ctx* ctx, const vqn_net_desc* desc, vqn_net** out, vqn_stream stream);
+int vqn_net_repack(vqn_net* net, const vqn_net_desc* desc, vqn_stream stream);
+int vqn_net_destroy(vqn_net* net);
+int vqn_net_out_dim(const vqn_net* net);
+
+/* mlp.Network.__call__ (mlp.py:39-50): y[n,out] = net(x[n,in]) */
+int vqn_net_forward(vqn_net* net, const float* x, int64_t n, float* y, int precision, vqn_stream stream);
+
+/* Embedder.__call__ (networks/embedder.py:23-47, kwargs of models/shape.py:82-89):
+ * out[n, 3 + 6*n_freqs] = [x, sin(x 2^0), cos(x 2^0), ..., sin(x 2^(F-1)), cos(x 2^(F-1))] */
+int vqn_embed(vqn_ctx* ctx, const float* x, int64_t n, int n_freqs, float* out, vqn_stream stream);
+
+/* Model._pred_enc_at (models/vq_nfr.py:771-784): z[n,256] = bottleneck(fine_enc(embed(pts))).
+ * row_idx (optional, int32 [n]) gathers pts rows (mask compaction, vq_nfr.py:283-291); z is compact.
+ * n_dev (optional device int32 scalar) overrides n (<= n) so that no host sync follows the compaction. */
+int vqn_pred_enc_at(vqn_ctx* ctx, vqn_net* fine_enc, vqn_net* bottleneck, int n_freqs, const float* pts,
+                    const int32_t* row_idx, const int32_t* n_dev, int64_t n, float* z_out, int precision,
+                    vqn_stream stream);
+
+/* Model._pred_diff_at / _pred_spec_at / _pred_rough_at (models/vq_nfr.py:786-828) fused over one read
+ * of z[n,256]; any head may be NULL.  diff_out = slope*sigmoid(.)+bias (albedo_slope/bias). */
+int vqn_pred_heads(vqn_ctx* ctx, vqn_net* diff, vqn_net* spec, vqn_net* rough, const float* z,
+                   const int32_t* n_dev, int64_t n, float albedo_slope, float albedo_bias, float* diff_out /*[n,3]*/,
+                   float* spec_out /*[n,out_dim(spec)]*/, float* rough_out /*[n,1]*/, int precision,
+                   vqn_stream stream);
+
+/* ---- vector quantiser ------------------------------------------------------------------------ */
+/* Model.get_codebook (models/vq_nfr.py:761-769): out[Z,K] = l2_normalize(clip(raw,0,1), axis=0) */
+int vqn_get_codebook(vqn_ctx* ctx, const float* raw, int z_dim, int k, float* out, vqn_stream stream);
+
+/* mathutil.safe_l2_normalize(x, axis=1) (util/math.py:63-64) on rows of x[n,d] */
+int vqn_l2_normalize_rows(vqn_ctx* ctx, const float* x, int64_t n, int d, float* out, vqn_stream stream);
+
+/* VectorQuantizerEMA.__call__ forward half (networks/vq_layers.py:277-302,327-330).
+ *   inputs   [n,Z] (Z == 256)   codebook [Z,K] (already normalised, 1 <= K <= 1024)
+ *   sel_mask [K] or NULL: 1 = codeword selectable, 0 = dropped (the `roll >= thres` mask, :284-290);
+ *   normalize_inputs != 0 fuses the caller's l2_normalize(z_enc, axis=1) (vq_nfr.py:575).
+ * Outputs (each may be NULL): indices int64 [n] (0-based; callers add 1, vq_nfr.py:578), quantize [n,Z]
+ * (= x + (q - x), the STE forward value, :327), distances [n,K], z_norm_out [n,Z],
+ * stats (float64 [K+2+Z*K]): [0,K) one-hot counts, [K] sum((q-x)^2), [K+1] rows seen,
+ * [K+2,..) dw[Z,K] = x^T one_hot (:308); stats are ACCUMULATED (zero them first) so that the
+ * multi-GPU path can all-reduce them before vqn_vq_ema_update. */
+int vqn_vq_assign(vqn_ctx* ctx, const float* inputs, int64_t n, int z_dim, const float* codebook, int k,
+                  const float* sel_mask, int normalize_inputs, int64_t* indices, float* quantize,
+                  float* distances, float* z_norm_out, double* stats, int want_dw, vqn_stream stream);
+
+/* EMA half (vq_layers.py:304-321 + dm-sonnet 2.0.0 moving_averages.ExponentialMovingAverage).
+ * state layout (caller-owned, float32 unless noted):
+ *   cs_hidden[K], cs_average[K], dw_hidden[Z,K], dw_average[Z,K], counter (int64[2]: cs, dw)
+ * Reads `stats` as written by vqn_vq_assign (after any cross-GPU all-reduce), writes
+ * update[Z,K] (= 'update' of the returned dict), loss[1] = commitment*e_latent, perplexity[1]. */
+int vqn_vq_ema_update(vqn_ctx* ctx, const double* stats, int z_dim, int k, const float* codebook,
+                      float decay, float epsilon, float commitment_cost, int is_training,
+                      float* cs_hidden, float* cs_average, float* dw_hidden, float* dw_average,
+                      int64_t* counters, float* update, float* loss, float* perplexity,
+                      vqn_stream stream);
+
+/* ---- shading ---------------------------------------------------------------------------------- */
+typedef struct vqn_shade_args {
+  /* per point, compacted rows i in [0,n); when row_idx != NULL the geometry inputs and outputs are
+   * full-length arrays addressed through row_idx[i] (mask compaction/expansion, vq_nfr.py:283-291,
+   * 347-370) while albedo/spec/rough are compact [n,*]. */
+  const float* xyz;     /* [*,3] surface points                                   */
+  const float* rayo;    /* [*,3] camera locations (_calc_vdir, shape.py:112-119)  */
+  const float* normal;  /* [*,3] (un-corrected; _normal_correct is fused)         */
+  const float* lvis;    /* [*,512] or NULL (non-'nerf' data, vq_nfr.py:707)       */
+  const float* albedo;  /* [n,3] */
+  const float* spec;    /* [n,3] (f0) */
+  const float* rough;   /* [n,1] */
+  const int32_t* row_idx; /* [n] or NULL */
+  const int32_t* n_dev;   /* optional device scalar overriding n (no host sync after compaction) */
+  int64_t n;
+  /* probes */
+  const float* lxyz;    /* [512,3] fp32 light positions (gen_light_xyz)           */
+  const float* lareas;  /* [512]                                                  */
+  const float* lights;  /* [1+P,512,3]: probe 0 = model light (or novel_probes[dst_env])         */
+  int32_t n_probes;     /* 1 + P                                                  */
+  int32_t clip_light0;  /* apply clip(.,0,inf) to probe 0 (the `light` property, vq_nfr.py:759) */
+  int32_t to_srgb;      /* data_type == 'nerf': linear2srgb on outputs (vq_nfr.py:350-356) */
+  int32_t use_gamma;    /* data_type != 'nerf': rgb = (rgb*gamma_bias)^gamma_index (:715-716) */
+  float gamma_bias, gamma_index;
+  /* outputs (may be NULL) */
+  float* rgb;           /* [*, n_probes, 3]  clip(.,0,1) (+sRGB)                  */
+  float* rgb_diff;      /* [*,3] probe 0 only, diffuse lobe (vq_nfr.py:605-610)   */
+  float* rgb_spec;      /* [*,3] probe 0 only, glossy lobe                        */
+  float* normal_out;    /* [*,3] corrected normal                                 */
+} vqn_shade_args;
+
+/* _calc_ldir + _calc_vdir + _normal_correct + _eval_brdf_at (util/microfacet.py:9-89) + _render
+ * (models/vq_nfr.py:694-733) fused; nothing of shape [N,512,3] is materialised. */
+int vqn_shade(vqn_ctx* ctx, const vqn_shade_args* args, vqn_stream stream);
+
+/* Fine-grained, materialising variants kept for API parity (debug sizes only):
+ * _eval_brdf_at -> brdf, brdf_glossy, brdf_diffuse [n,512,3] from explicit directions. */
+int vqn_eval_brdf(vqn_ctx* ctx, const float* pts2l /*[n,512,3]*/, const float* pts2c /*[n,3]*/,
+                  const float* normal, const float* albedo, const float* spec, const float* rough,
+                  int64_t n, float* brdf, float* brdf_glossy, float* brdf_diffuse, vqn_stream stream);
+/* _render(brdf, l, n, light_vis) for one probe: rgb[n,3] (linear, clipped) */
+int vqn_render(vqn_ctx* ctx, const float* brdf, const float* l, const float* normal, const float* lvis,
+               const float* lareas, const float* light /*[512,3]*/, int64_t n, int use_gamma,
+               float gamma_bias, float gamma_index, float* rgb, vqn_stream stream);
+
+/* spec = ks*basecolor, albedo = (1-ks)*basecolor (models/vq_nfr.py:330-331,590-591) and fast_render's
+ * opt_scale (:333-336, opt_scale[3] device or NULL); all [n,3] compact, ks [n,1]; outputs may be NULL. */
+int vqn_material_combine(vqn_ctx* ctx, const float* basecolor, const float* ks, const float* opt_scale,
+                         const int32_t* n_dev, int64_t n, float* albedo, float* spec, float* albedo_scaled,
+                         float* spec_scaled, vqn_stream stream);
+
+/* util/img.py:142-186 */
+int vqn_linear2srgb(vqn_ctx* ctx, const float* x, int64_t count, float* out, vqn_stream stream);
+int vqn_srgb2linear(vqn_ctx* ctx, const float* x, int64_t count, float* out, vqn_stream stream);
+
+/* mask = alpha[:,0] > 0 ; ind = where(mask) (vq_nfr.py:283,345): row_idx[int32, n_total] and the
+ * device count n_active[1]; no host synchronisation. */
+int vqn_compact_mask(vqn_ctx* ctx, const float* alpha, int64_t n_total, int32_t* row_idx,
+                     int32_t* n_active, vqn_stream stream);
+
+/* scatter_nd(ind, value, (n_total,c)) (vq_nfr.py:347-370): out must be pre-zeroed full length */
+int vqn_scatter_rows(vqn_ctx* ctx, const float* compact, const int32_t* row_idx, const int32_t* n_dev,
+                     int64_t n_max, int c, float* out, vqn_stream stream);
+
+/* ---- NeuS geo stage (secondary path) -------------------------------------------------------- */
+/* NeuSRenderer.up_sample (geo/NeuS-ours2/models/renderer.py:131-175) incl. sample_pdf(det=True)
+ * (:39-69): z_samples[B,n_importance] from z_vals[B,S], sdf[B,S]. One warp per ray. */
+int vqn_neus_up_sample(vqn_ctx* ctx, const float* rays_o, const float* rays_d, const float* z_vals,
+                       const float* sdf, int64_t n_rays, int n_samples, float r_limit,
+                       int n_importance, float inv_s, float* z_samples, vqn_stream stream);
+
+/* NeuSRenderer.cat_z_vals sort/merge half (:177-191): merges new_z[B,I] into z_vals[B,S] (sorted),
+ * carrying sdf along (new_sdf may be NULL when last=True): z_out[B,S+I], sdf_out[B,S+I]. */
+int vqn_neus_cat_z_vals(vqn_ctx* ctx, const float* z_vals, const float* new_z, const float* sdf,
+                        const float* new_sdf, int64_t n_rays, int n_samples, int n_importance,
+                        float* z_out, float* sdf_out, vqn_stream stream);
+
+/* NeuSRenderer.render_core compositing half (:229-282), n_outside == 0:
+ *   inputs per sample: sdf[B,S], gradients[B,S,3], sampled_color[B,S,3], z_vals[B,S]; per ray rays_o,
+ *   rays_d; scalars inv_s (already clipped to [1e-6,1e6]), cos_anneal_ratio, sample_dist, radius,
+ *   background_rgb (3 floats or NULL).
+ *   outputs (may be NULL): color[B,3], weights[B,S], surf[B,3], depth[B,1], cdf[B,S] (= prev_cdf),
+ *   inside_sphere[B,S], mid_z_vals[B,S], dists[B,S], weight_sum[B,1], weight_max[B,1],
+ *   grad_err_sums[2] (float64: sum(relax*err), sum(relax)) accumulated for gradient_error. */
+typedef struct vqn_neus_composite_args {
+  const float* rays_o; const float* rays_d; const float* z_vals; const float* sdf;
+  const float* gradients; const float* sampled_color;
+  int64_t n_rays; int32_t n_samples; int32_t reserved;
+  float inv_s, cos_anneal_ratio, sample_dist, radius;
+  const float* background_rgb;
+  float* color; float* weights; float* surf; float* depth; float* cdf; float* inside_sphere;
+  float* mid_z_vals; float* dists; float* weight_sum; float* weight_max; double* grad_err_sums;
+} vqn_neus_composite_args;
+int vqn_neus_composite(vqn_ctx* ctx, const vqn_neus_composite_args* args, vqn_stream stream);
+
+/* mid-point sample positions of render_core (:205-216): mid_z = z + dists/2 with the last dist =
+ * sample_dist; pts[B,S,3] = o + d*mid_z, dirs[B,S,3] = d.  (inputs of the SDF / colour networks) */
+int vqn_neus_mid_points(vqn_ctx* ctx, const float* rays_o, const float* rays_d, const float* z_vals,
+                        int64_t n_rays, int n_samples, float sample_dist, float* pts, float* dirs,
+                        vqn_stream stream);
+
+/* ---- measurement helper (not a reference interface) -------------------------------------------- */
+/* FP32-FMA peak of this GPU in TFLOP/s (mode 0: FFMA, mode 1: packed fma.rn.f32x2); synchronises. */
+int vqn_microbench_fma(vqn_ctx* ctx, int mode, int iters, double* tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQNERF_B200_H_ */

@@ -1,0 +1,519 @@
+"""CPU oracle for the VQ-NeRF decomposition-stage shading path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product (`vqnerf_release_b200/`) may
+import this module; only `tests/`, `__graft_entry__.smoke()` and the
+`cpu_baseline` / `--impl reference` legs of `bench.py` do, and only as the
+checker / the CPU baseline.
+
+PARITY UNPINNED: the reference's decomp stage is TensorFlow 2.4.1 + dm-sonnet
+2.0.0 + tensorflow-probability 0.12.1, none of which is installed in this image
+(no network), and the reference ships no tests, fixtures or golden vectors for
+this path.  This file is therefore an op-for-op restatement
+of the reference's arithmetic in PyTorch-CPU (float64 = "truth", float32 =
+emulation of the TF fp32 op sequence, including the [N,512,3] intermediates the
+reference materialises).  Each function cites the reference file:line it follows
+(paths relative to /root/reference/decomp/nerfvq_nfr3/).
+
+Third-party arithmetic restated from published sources (not vendored in the
+reference): dm-sonnet 2.0.0 `moving_averages.ExponentialMovingAverage`
+(zero-debiased EMA), tfp 0.12.1 `clip_by_value_preserve_gradient` (forward ==
+clip, gradient == identity), TF `l2_normalize` (epsilon on the squared norm),
+TF `divide_no_nan`, Keras Dense / glorot_uniform.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+# ----------------------------------------------------------------------------
+# constants of the shipped config (nerfactor/config/vq_nfr.ini)
+# ----------------------------------------------------------------------------
+MLP_WIDTH = 128        # vq_nfr.ini:97
+Z_DIM = 256            # vq_nfr.ini:100 (conv_width)
+N_FREQS_XYZ = 10       # vq_nfr.ini:104
+LIGHT_H = 16           # vq_nfr.ini:51
+NUM_EMBED = 15         # vq_nfr.ini:113
+COMMITMENT_COST = 0.1  # vq_nfr.ini:114
+
+ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+
+
+# ----------------------------------------------------------------------------
+# TF primitive restatements
+# ----------------------------------------------------------------------------
+def safe_l2_normalize(x: torch.Tensor, axis: int, eps: float = 1e-6) -> torch.Tensor:
+    """nerfactor/util/math.py:63-64 -> tf.linalg.l2_normalize(x, axis, epsilon):
+    x * rsqrt(max(sum(x^2, axis), epsilon)) -- epsilon bounds the SQUARED norm."""
+    sq = torch.sum(x * x, dim=axis, keepdim=True)
+    return x * torch.rsqrt(torch.clamp(sq, min=eps))
+
+
+def divide_no_nan(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """tf.math.divide_no_nan: 0 where the denominator is exactly 0."""
+    b_safe = torch.where(b == 0, torch.ones_like(b), b)
+    out = a / b_safe
+    return torch.where(b == 0, torch.zeros_like(out), out)
+
+
+def clip_preserve_grad(x: torch.Tensor, lo: float, hi: float) -> torch.Tensor:
+    """tfp.math.clip_by_value_preserve_gradient: forward = clip, backward = identity."""
+    return x + (torch.clamp(x, lo, hi) - x).detach()
+
+
+# ----------------------------------------------------------------------------
+# light probe geometry
+# ----------------------------------------------------------------------------
+def gen_light_xyz(envmap_h: int, envmap_w: int, envmap_radius: float = 1e2):
+    """brdf/renderer.py:184-219 + third_party/xiuminglib/xiuminglib/geometry/sph.py:184-190.
+    float64 NumPy, as the reference; the model casts to fp32 (vq_nfr.py:73-75)."""
+    lat_step = np.pi / (envmap_h + 2)
+    lng_step = 2 * np.pi / (envmap_w + 2)
+    lats = np.linspace(np.pi / 2 - lat_step, -np.pi / 2 + lat_step, envmap_h)
+    lngs = np.linspace(np.pi - lng_step, -np.pi + lng_step, envmap_w)
+    lngs, lats = np.meshgrid(lngs, lats)
+    r = envmap_radius * np.ones_like(lats)
+    z = r * np.sin(lats)
+    x = r * np.cos(lats) * np.cos(lngs)
+    y = r * np.cos(lats) * np.sin(lngs)
+    xyz = np.stack((x, y, z), axis=-1)
+    sin_colat = np.sin(np.pi / 2 - lats)
+    areas = 4 * np.pi * sin_colat / np.sum(sin_colat)
+    return xyz, areas
+
+
+# ----------------------------------------------------------------------------
+# networks
+# ----------------------------------------------------------------------------
+def embed(x: torch.Tensor, n_freqs: int = N_FREQS_XYZ) -> torch.Tensor:
+    """nerfactor/networks/embedder.py:23-47 with the kwargs of models/shape.py:82-89:
+    [x, sin(x f0), cos(x f0), sin(x f1), ...], f_k = 2**linspace(0, n-1, n)."""
+    outs = [x]
+    for k in range(n_freqs):
+        f = float(2.0 ** k)
+        outs.append(torch.sin(x * f))
+        outs.append(torch.cos(x * f))
+    return torch.cat(outs, dim=-1)
+
+
+@dataclass
+class Net:
+    """nerfactor/networks/mlp.py:24-50 -- Keras Dense stack, kernel [in,out], bias [out];
+    after layer i in skip_at the output becomes concat(y, x_input) (y first)."""
+    weights: List[np.ndarray]
+    biases: List[np.ndarray]
+    acts: List[int]
+    skip_at: Optional[int] = None
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        dt = x.dtype
+        x_ = x
+        y = x
+        for i, (w, b, a) in enumerate(zip(self.weights, self.biases, self.acts)):
+            y = x_ @ torch.as_tensor(w, dtype=dt) + torch.as_tensor(b, dtype=dt)
+            if a == ACT_RELU:
+                y = torch.relu(y)
+            elif a == ACT_SIGMOID:
+                y = torch.sigmoid(y)
+            if self.skip_at is not None and i == self.skip_at:
+                y = torch.cat((y, x), dim=-1)
+            x_ = y
+        return y
+
+
+def glorot_uniform(rng: np.random.RandomState, fan_in: int, fan_out: int) -> np.ndarray:
+    """Keras Dense default kernel init: U(-l, l), l = sqrt(6/(fan_in+fan_out)); bias zeros."""
+    limit = math.sqrt(6.0 / (fan_in + fan_out))
+    return rng.uniform(-limit, limit, size=(fan_in, fan_out)).astype(np.float32)
+
+
+def make_net(rng, in_dim: int, widths: Sequence[int], acts: Sequence[int],
+             skip_at: Optional[int] = None, bias_scale: float = 0.0) -> Net:
+    ws, bs = [], []
+    d = in_dim
+    for i, w in enumerate(widths):
+        ws.append(glorot_uniform(rng, d, w))
+        if bias_scale > 0:
+            bs.append((rng.uniform(-1, 1, size=(w,)) * bias_scale).astype(np.float32))
+        else:
+            bs.append(np.zeros((w,), np.float32))
+        d = w
+        if skip_at is not None and i == skip_at:
+            d = w + in_dim
+    return Net(ws, bs, list(acts), skip_at)
+
+
+def make_vq_nfr_nets(seed: int = 0, bias_scale: float = 0.0) -> Dict[str, Net]:
+    """The 8 nets of models/vq_nfr.py:135-164 (VQ twins) + models/nfr_unit.py:110-129."""
+    rng = np.random.RandomState(seed)
+    R, S, N_ = ACT_RELU, ACT_SIGMOID, ACT_NONE
+    emb = 3 + 3 * 2 * N_FREQS_XYZ
+    nets = {}
+    nets['fine_enc'] = make_net(rng, emb, [MLP_WIDTH] * 4, [R] * 4, skip_at=2, bias_scale=bias_scale)
+    nets['bottleneck'] = make_net(rng, MLP_WIDTH, [MLP_WIDTH, Z_DIM, Z_DIM], [N_, R, S], bias_scale=bias_scale)
+    for name, out in (('diff_main', 3), ('spec_main', 1), ('rough_main', 1),
+                      ('diff_vq', 3), ('spec_vq', 3), ('rough_vq', 1)):
+        nets[name] = make_net(rng, Z_DIM, [Z_DIM, Z_DIM // 2, out], [R, R, S], skip_at=1,
+                              bias_scale=bias_scale)
+    return nets
+
+
+# ----------------------------------------------------------------------------
+# model pieces
+# ----------------------------------------------------------------------------
+def calc_ldir(lxyz: torch.Tensor, pts: torch.Tensor) -> torch.Tensor:
+    """models/shape.py:103-110"""
+    surf2l = lxyz.reshape(1, -1, 3) - pts[:, None, :]
+    return safe_l2_normalize(surf2l, axis=2)
+
+
+def calc_vdir(cam_loc: torch.Tensor, pts: torch.Tensor) -> torch.Tensor:
+    """models/shape.py:112-119"""
+    return safe_l2_normalize(cam_loc - pts, axis=1)
+
+
+def normal_correct(normal: torch.Tensor, surf2c: torch.Tensor) -> torch.Tensor:
+    """models/vq_nfr.py:830-833"""
+    cos = torch.sum(normal * surf2c, dim=-1, keepdim=True)
+    return torch.where(cos >= 0, normal, -normal)
+
+
+def pred_enc_at(nets: Dict[str, Net], pts: torch.Tensor) -> torch.Tensor:
+    """models/vq_nfr.py:771-784 (chunking is arithmetic-neutral)."""
+    return nets['bottleneck'](nets['fine_enc'](embed(pts)))
+
+
+def pred_head(nets, name: str, z: torch.Tensor, slope: float = 1.0, bias: float = 0.0):
+    """models/vq_nfr.py:786-828; slope/bias only for the diffuse heads (albedo_slope/bias)."""
+    y = nets[name](z)
+    if name.startswith('diff'):
+        y = slope * y + bias
+    return y
+
+
+def get_codebook(raw_codebook: torch.Tensor) -> torch.Tensor:
+    """models/vq_nfr.py:761-769: clip to [0,1] then l2-normalise each column ([Z,K])."""
+    c = clip_preserve_grad(raw_codebook, 0.0, 1.0)
+    return safe_l2_normalize(c, axis=0)
+
+
+# ---- microfacet BRDF ---------------------------------------------------------
+def _get_gsub(cos_theta, alpha):
+    """util/microfacet.py:49-69 (_get_gl and _get_gv share this form)."""
+    cos_theta = clip_preserve_grad(cos_theta, 0.0, 1.0)
+    cos_theta_sq = cos_theta * cos_theta
+    denom_a = torch.abs(alpha ** 2 + (1 - alpha ** 2) * cos_theta_sq)
+    denom = cos_theta + torch.sqrt(denom_a)
+    return divide_no_nan(2 * cos_theta, denom)
+
+
+def get_brdf(pts2l, pts2c, normal, albedo, rough, f0):
+    """util/microfacet.py:9-39 and helpers :41-89.  Returns (brdf, glossy, diffuse), each [N,L,3]."""
+    pts2l = safe_l2_normalize(pts2l, axis=2)
+    pts2c = safe_l2_normalize(pts2c, axis=1)
+    normal = safe_l2_normalize(normal, axis=1)
+    h = pts2l + pts2c[:, None, :]
+    h = safe_l2_normalize(h, axis=2)
+    # _get_f :82-89
+    cos_hv = torch.einsum('ijk,ik->ij', h, pts2c)[:, :, None]
+    cos_hv = clip_preserve_grad(cos_hv, 0.0, 1.0)
+    f0_ = f0[:, None, :]
+    f = f0_ + (1 - f0_) * (1 - cos_hv) ** 5
+    alpha = rough ** 2                              # :25
+    # _get_d :71-80
+    a_ = alpha[:, None, :]
+    cos_m = torch.einsum('ijk,ik->ij', h, normal)
+    cos_m = clip_preserve_grad(cos_m, 0.0, 1.0)
+    cos_m_sq = cos_m * cos_m
+    denom_d = math.pi * (cos_m_sq[:, :, None] * (a_ ** 2 - 1) + 1) ** 2
+    d = divide_no_nan(a_ ** 2, denom_d)
+    # _get_g :41-69
+    g_l = _get_gsub(torch.einsum('ijk,ik->ij', pts2l, normal)[:, :, None], a_)
+    g_v = _get_gsub(torch.einsum('ij,ij->i', normal, pts2c)[:, None, None], a_)
+    g = g_l * g_v
+    l_dot_n = torch.einsum('ijk,ik->ij', pts2l, normal)[:, :, None]
+    v_dot_n = torch.einsum('ij,ij->i', pts2c, normal)[:, None, None]
+    denom = 4 * torch.abs(l_dot_n) * torch.abs(v_dot_n)
+    glossy = divide_no_nan(f * g * d, denom)
+    diffuse = (albedo / math.pi)[:, None, :].expand_as(glossy)
+    return glossy + diffuse, glossy, diffuse
+
+
+def linear2srgb(t: torch.Tensor) -> torch.Tensor:
+    """util/img.py:142-165 (clip to [0,1] first, :62-75)."""
+    t = torch.clamp(t, 0.0, 1.0)
+    lin = t * 12.92
+    nonlin = 1.055 * torch.pow(t, 1 / 2.4) - 0.055
+    return torch.where(t <= 0.0031308, lin, nonlin)
+
+
+def srgb2linear(t: torch.Tensor) -> torch.Tensor:
+    """util/img.py:167-186"""
+    lin = t / 12.92
+    nonlin = torch.pow((t + 0.055) / 1.055, 2.4)
+    return torch.where(t <= 0.04045, lin, nonlin)
+
+
+def render(brdf, l, n, lareas, light, light_vis=None, probes: Optional[torch.Tensor] = None,
+           gamma: Optional[Tuple[float, float]] = None):
+    """models/vq_nfr.py:694-733 (_render / integrate).  `light` [16,32,3] is already
+    clip(_light, 0, inf) (:759); `probes` [P,16,32,3] are the novel probes in dict order.
+    gamma=(bias, index) only for data_type != 'nerf' (:715-716)."""
+    cos = torch.einsum('ijk,ik->ij', l, n)
+    areas = lareas.reshape(1, -1, 1)
+    front_lit = (cos > 0).to(cos.dtype)
+    lvis = front_lit if light_vis is None else front_lit * light_vis
+
+    def integrate(lt):
+        light_flat = lt.reshape(-1, 3)
+        lgt = lvis[:, :, None] * light_flat[None, :, :]
+        contrib = brdf * lgt * cos[:, :, None] * areas
+        rgb = torch.sum(contrib, dim=1)
+        if gamma is not None:
+            rgb = (rgb * gamma[0]) ** gamma[1]
+        return clip_preserve_grad(rgb, 0.0, 1.0)
+
+    rgb = integrate(light)
+    rgb_probes = None
+    if probes is not None:
+        rgb_probes = torch.stack([integrate(p) for p in probes], dim=1)
+    return rgb, rgb_probes
+
+
+# ---- vector quantiser ----------------------------------------------------------
+class SonnetEMA:
+    """dm-sonnet 2.0.0 sonnet/src/moving_averages.py ExponentialMovingAverage (not vendored;
+    restated): update(v): counter += 1; hidden -= (hidden - v) * (1 - decay);
+    average = hidden / (1 - decay**counter).  initialize() zero-fills hidden/average."""
+
+    def __init__(self, shape, decay: float, dtype=torch.float32):
+        self.decay = decay
+        self.hidden = torch.zeros(shape, dtype=dtype)
+        self.average = torch.zeros(shape, dtype=dtype)
+        self.counter = 0
+
+    def __call__(self, value: torch.Tensor) -> torch.Tensor:
+        self.counter += 1
+        self.hidden = self.hidden - (self.hidden - value) * (1.0 - self.decay)
+        self.average = self.hidden / (1.0 - self.decay ** self.counter)
+        return self.average
+
+
+class VectorQuantizerEMA:
+    """nerfactor/networks/vq_layers.py:208-349."""
+
+    def __init__(self, embedding_dim, num_embeddings, commitment_cost, decay=0.999,
+                 epsilon=1e-5, dtype=torch.float32):
+        self.embedding_dim = embedding_dim
+        self.num_embeddings = num_embeddings
+        self.commitment_cost = commitment_cost
+        self.decay = decay
+        self.epsilon = epsilon
+        self.ema_cluster_size = SonnetEMA([num_embeddings], decay, dtype)          # :249-251
+        self.ema_dw = SonnetEMA([embedding_dim, num_embeddings], decay, dtype)     # :253-255
+
+    def __call__(self, inputs, codebook, is_training, thres=None, roll=None):
+        """`roll` replaces tf.random.uniform (:286-288) so the test can inject it."""
+        dt = inputs.dtype
+        flat = inputs.reshape(-1, self.embedding_dim)
+        distances = (torch.sum(flat ** 2, 1, keepdim=True)
+                     - 2 * (flat @ codebook)
+                     + torch.sum(codebook ** 2, 0, keepdim=True))                  # :279-282
+        if thres is not None:
+            mask_value = torch.max(distances)
+            sel_mask = (roll >= thres).to(dt)
+            distances = distances * sel_mask + mask_value * (1.0 - sel_mask)       # :284-290
+        idx = torch.argmax(-distances, 1)       # first max of -d == first min of d (:292)
+        # torch.argmax does not guarantee first-index ties on all builds: enforce it.
+        dmin = distances.min(dim=1, keepdim=True).values
+        idx = torch.argmax((distances == dmin).to(torch.int8), dim=1)
+        encodings = torch.nn.functional.one_hot(idx, self.num_embeddings).to(dt)   # :293
+        quantized = codebook.t()[idx]                                              # :346-349
+        e_latent = torch.mean((quantized.detach() - inputs) ** 2)                  # :302
+        ret = {}
+        if is_training:
+            cnt = torch.sum(encodings, dim=0)
+            cs = self.ema_cluster_size(cnt)                                        # :305-306
+            dw = flat.t() @ encodings                                              # :308
+            ema_dw = self.ema_dw(dw)                                               # :309
+            n = torch.sum(cs)
+            cs = (cs + self.epsilon) / (n + self.num_embeddings * self.epsilon) * n  # :311-313
+            w = ema_dw / cs.reshape(1, -1)                                         # :315-316
+            used = (cnt > 0).to(dt)                                                # :318
+            ret['update'] = w * used[None, :] + codebook * (1.0 - used[None, :])   # :319
+        loss = self.commitment_cost * e_latent                                     # :321,324
+        quantized_ste = inputs + (quantized - inputs).detach()                     # :327
+        avg_probs = torch.mean(encodings, 0)
+        perplexity = torch.exp(-torch.sum(avg_probs * torch.log(avg_probs + 1e-10)))  # :328-330
+        ret.update({'quantize': quantized_ste, 'loss': loss, 'perplexity': perplexity,
+                    'encodings': encodings, 'encoding_indices': idx, 'distances': distances})
+        return ret
+
+
+def top2_gap_rel(distances: torch.Tensor) -> torch.Tensor:
+    """Relative gap between the two smallest distances of each row -- the tolerance clause
+    of BASELINE.json (indices bit-exact unless this gap < 1e-6)."""
+    if distances.shape[1] < 2:
+        return torch.full((distances.shape[0],), float('inf'), dtype=distances.dtype)
+    v, _ = torch.topk(distances, 2, dim=1, largest=False)
+    return (v[:, 1] - v[:, 0]) / torch.clamp(torch.abs(v[:, 0]), min=1e-30)
+
+
+# ----------------------------------------------------------------------------
+# whole-path entry points (forward only)
+# ----------------------------------------------------------------------------
+@dataclass
+class Scene:
+    """Replicated state of models/vq_nfr.py Model that the path reads."""
+    nets: Dict[str, Net]
+    light: np.ndarray                 # [16,32,3]  raw _light variable
+    codebook: np.ndarray              # [Z,K]      raw _codebook variable
+    probes: Optional[np.ndarray] = None   # [P,16,32,3]
+    albedo_slope: float = 1.0
+    albedo_bias: float = 0.0
+    data_type: str = 'nerf'
+    gamma: Tuple[float, float] = (1.0, 1.0)
+    lxyz: np.ndarray = field(default_factory=lambda: gen_light_xyz(LIGHT_H, 2 * LIGHT_H)[0])
+    lareas: np.ndarray = field(default_factory=lambda: gen_light_xyz(LIGHT_H, 2 * LIGHT_H)[1])
+
+
+def _t(a, dt):
+    return torch.as_tensor(np.asarray(a), dtype=dt)
+
+
+def fast_render(scene: Scene, batch: Dict[str, np.ndarray], dtype=torch.float64,
+                relight_probes: bool = False, opt_scale=None, gen_embed: bool = False,
+                return_brdf: bool = False) -> Dict[str, torch.Tensor]:
+    """models/vq_nfr.py:262-398.  Returns the `pred` dict entries (full length, zeros at
+    background rows) plus the compacted intermediates under '_'-prefixed keys."""
+    dt = dtype
+    alpha = _t(batch['alpha'], dt)
+    mask = alpha[:, 0] > 0
+    rayo, xyz, normal = (_t(batch[k], dt)[mask] for k in ('rayo', 'xyz', 'normal'))
+    lvis = _t(batch['lvis'], dt)[mask] if batch.get('lvis') is not None else None
+    lxyz, lareas = _t(scene.lxyz, torch.float32).to(dt), _t(scene.lareas, torch.float32).to(dt)
+    surf2l = calc_ldir(lxyz, xyz)
+    surf2c = calc_vdir(rayo, xyz)
+    normal_pred = normal_correct(normal, surf2c)
+    z_enc = pred_enc_at(scene.nets, xyz)
+    out = {}
+    if gen_embed:
+        z_norm = safe_l2_normalize(z_enc, axis=1)
+        cb = get_codebook(_t(scene.codebook, dt))
+        vq = VectorQuantizerEMA(Z_DIM, cb.shape[1], COMMITMENT_COST, dtype=dt)(z_norm, cb, False)
+        out['_embed_ind'] = vq['encoding_indices'] + 1
+        out['_vq_distances'] = vq['distances']
+    rough = pred_head(scene.nets, 'rough_main', z_enc)
+    basecolor = pred_head(scene.nets, 'diff_main', z_enc, scene.albedo_slope, scene.albedo_bias)
+    ks = pred_head(scene.nets, 'spec_main', z_enc)
+    spec = ks * basecolor
+    albedo = (1 - ks) * basecolor
+    if opt_scale is not None:
+        s = _t(opt_scale, dt)
+        s_albedo, s_spec = albedo * s, spec * s
+    else:
+        s_albedo, s_spec = albedo, spec
+    brdf, _, _ = get_brdf(surf2l, surf2c, normal_pred, s_albedo, rough, s_spec)
+    light = torch.clamp(_t(scene.light, dt), min=0.0)
+    probes = _t(scene.probes, dt) if (relight_probes and scene.probes is not None) else None
+    gamma = None if scene.data_type == 'nerf' else scene.gamma
+    rgb_pred, rgb_probes = render(brdf, surf2l, normal_pred, lareas, light, lvis, probes, gamma)
+    n = alpha.shape[0]
+
+    def scatter(v):
+        full = torch.zeros((n,) + tuple(v.shape[1:]), dtype=v.dtype)
+        full[mask] = v
+        return full
+
+    out.update({'basecolor': scatter(basecolor), 'albedo': scatter(albedo), 'spec': scatter(spec),
+                'rough': scatter(rough), '_rgb_linear': scatter(rgb_pred), '_z_enc': z_enc,
+                '_ks': ks})
+    rgb_s = linear2srgb(rgb_pred) if scene.data_type == 'nerf' else rgb_pred
+    out['rgb'] = scatter(rgb_s)
+    if rgb_probes is not None:
+        rp = linear2srgb(rgb_probes) if scene.data_type == 'nerf' else rgb_probes
+        out['rgb_probes'] = scatter(rp)
+    if gen_embed:
+        out['embed'] = scatter(out['_embed_ind'][:, None])
+    if return_brdf:
+        out['_brdf'] = brdf
+    return out
+
+
+def call_forward(scene: Scene, batch: Dict[str, np.ndarray], vq: VectorQuantizerEMA,
+                 mode: str = 'train', thres=None, roll=None, dtype=torch.float64):
+    """models/vq_nfr.py:534-692 forward (no loss).  Mutates `vq` EMA state and returns the
+    codebook update when mode == 'train'."""
+    dt = dtype
+    alpha = _t(batch['alpha'], dt)
+    mask = alpha[:, 0] > 0
+    rayo, xyz, normal = (_t(batch[k], dt)[mask] for k in ('rayo', 'xyz', 'normal'))
+    lvis = _t(batch['lvis'], dt)[mask] if batch.get('lvis') is not None else None
+    lxyz, lareas = _t(scene.lxyz, torch.float32).to(dt), _t(scene.lareas, torch.float32).to(dt)
+    surf2l = calc_ldir(lxyz, xyz)
+    surf2c = calc_vdir(rayo, xyz)
+    normal_pred = normal_correct(normal, surf2c)
+    z_enc = pred_enc_at(scene.nets, xyz)
+    z_norm = safe_l2_normalize(z_enc, axis=1)
+    cb = get_codebook(_t(scene.codebook, dt))
+    th = None if thres is None else _t(thres, dt).reshape(1, -1)
+    rl = None if roll is None else _t(roll, dt).reshape(1, -1)
+    vq_outs = vq(z_norm, cb, is_training=(mode == 'train'), thres=th, roll=rl)
+    z_vq = vq_outs['quantize']
+    rough = pred_head(scene.nets, 'rough_main', z_enc)
+    basecolor = pred_head(scene.nets, 'diff_main', z_enc, scene.albedo_slope, scene.albedo_bias)
+    ks = pred_head(scene.nets, 'spec_main', z_enc)
+    spec, albedo = ks * basecolor, (1 - ks) * basecolor
+    light = torch.clamp(_t(scene.light, dt), min=0.0)
+    gamma = None if scene.data_type == 'nerf' else scene.gamma
+    brdf, brdf_spec, brdf_diff = get_brdf(surf2l, surf2c, normal_pred, albedo, rough, spec)
+    rgb_pred, _ = render(brdf, surf2l, normal_pred, lareas, light, lvis, None, gamma)
+    out = {'rgb_linear': rgb_pred, 'albedo': albedo, 'spec': spec, 'rough': rough, 'ks': ks,
+           'z_enc': z_enc, 'z_vq': z_vq, 'embed_ind': vq_outs['encoding_indices'] + 1,
+           'vq_loss': vq_outs['loss'], 'perplexity': vq_outs['perplexity'],
+           'distances': vq_outs['distances'], 'normal': normal_pred}
+    if mode != 'train':
+        out['rgb_diff'], _ = render(brdf_diff, surf2l, normal_pred, lareas, light, lvis, None, gamma)
+        out['rgb_spec'], _ = render(brdf_spec, surf2l, normal_pred, lareas, light, lvis, None, gamma)
+    else:
+        out['update'] = vq_outs['update']
+    vq_rough = pred_head(scene.nets, 'rough_vq', z_vq)
+    vq_albedo = pred_head(scene.nets, 'diff_vq', z_vq, scene.albedo_slope, scene.albedo_bias)
+    vq_spec = pred_head(scene.nets, 'spec_vq', z_vq)
+    vq_brdf, _, _ = get_brdf(surf2l, surf2c, normal_pred, vq_albedo, vq_rough, vq_spec)
+    vq_rgb, _ = render(vq_brdf, surf2l, normal_pred, lareas, light, lvis, None, gamma)
+    out.update({'vq_rgb_linear': vq_rgb, 'vq_albedo': vq_albedo, 'vq_spec': vq_spec,
+                'vq_rough': vq_rough, 'mask': mask})
+    return out
+
+
+# ----------------------------------------------------------------------------
+# synthetic inputs -- oracle-side copy, independent of the product
+# ----------------------------------------------------------------------------
+def synth_batch(n: int, seed: int = 0, fg_frac: float = 1.0, with_lvis: bool = True):
+    rng = np.random.RandomState(seed)
+    xyz = rng.uniform(-1, 1, size=(n, 3)).astype(np.float32)
+    rayo = rng.normal(size=(n, 3))
+    rayo = (4.0 * rayo / np.linalg.norm(rayo, axis=1, keepdims=True)).astype(np.float32)
+    normal = rng.normal(size=(n, 3))
+    normal = (normal / np.linalg.norm(normal, axis=1, keepdims=True)).astype(np.float32)
+    lvis = rng.uniform(0, 1, size=(n, 512)).astype(np.float32) if with_lvis else None
+    alpha = (rng.uniform(0, 1, size=(n, 1)) < fg_frac).astype(np.float32)
+    rgb = rng.uniform(0, 1, size=(n, 3)).astype(np.float32)
+    return {'xyz': xyz, 'rayo': rayo, 'rayd': -rayo / 4.0, 'normal': normal, 'lvis': lvis,
+            'alpha': alpha, 'pred_alpha': alpha.copy(), 'rgb': rgb}
+
+
+def synth_scene(seed: int = 0, k: int = NUM_EMBED, n_probes: int = 0, bias_scale: float = 0.0,
+                data_type: str = 'nerf') -> Scene:
+    rng = np.random.RandomState(seed + 1000)
+    light = (np.abs(rng.normal(size=(LIGHT_H, 2 * LIGHT_H, 3))) * 0.5).astype(np.float32)
+    cb = rng.uniform(0, 1, size=(Z_DIM, k)).astype(np.float32)
+    probes = None
+    if n_probes > 0:
+        probes = (np.abs(rng.normal(size=(n_probes, LIGHT_H, 2 * LIGHT_H, 3))) * 0.5).astype(np.float32)
+    return Scene(nets=make_vq_nfr_nets(seed, bias_scale), light=light, codebook=cb, probes=probes,
+                 data_type=data_type, gamma=(1.1, 0.9))

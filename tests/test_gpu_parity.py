@@ -1,0 +1,363 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs,
+against the committed golden vectors, and through size-independent properties at larger sizes.
+
+Tolerances (BASELINE.json north_star): VQ indices bit-exact except rows whose oracle top-2 distance gap is
+< 1e-6 relative; radiance / albedo / BRDF within 1e-4 relative (fp32 mode).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import decomp_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+RTOL = 1e-4          # fp32 parity tolerance of the north star
+ATOL = 2e-6          # absolute floor for values near zero (outputs live in [0,1])
+
+
+def _model_from_scene(scene, dev, **cfg):
+    from vqnerf_release_b200.nerfactor.models.vq_nfr import Model
+    nets = {k: (n.weights, n.biases) for k, n in scene.nets.items()}
+    probes = None
+    if scene.probes is not None:
+        probes = {'probe%02d' % i: p for i, p in enumerate(scene.probes)}
+    conf = {'data_type': scene.data_type, 'num_embed': scene.codebook.shape[1],
+            'albedo_slope': scene.albedo_slope, 'albedo_bias': scene.albedo_bias}
+    conf.update(cfg)
+    m = Model(conf, nets=nets, light=scene.light, codebook=scene.codebook.T.copy(), novel_probes=probes, device=dev)
+    if scene.data_type != 'nerf':
+        m._gamma_bias[0], m._gamma_index[0] = scene.gamma
+    return m
+
+
+def _batch_tuple(batch, dev, data_type='nerf', ref_batch=False):
+    t = lambda a: torch.as_tensor(a).to(dev)
+    n = batch['xyz'].shape[0]
+    id_ = ['synthetic'] * n
+    hw = t(np.tile(np.array([[1, n]], np.int32), (n, 1)))
+    items = [id_, hw, t(batch['rayo']), t(batch['rayd']), t(batch['rgb']), t(batch['alpha']), t(batch['pred_alpha']),
+             t(batch['xyz']), t(batch['normal'])]
+    if ref_batch:
+        items.append(t(batch['rgb']))
+    if data_type == 'nerf':
+        items.append(t(batch['lvis']))
+    return tuple(items)
+
+
+def _close(a, b, name, rtol=RTOL, atol=ATOL):
+    a = a.detach().cpu().double().numpy() if torch.is_tensor(a) else np.asarray(a, np.float64)
+    b = b.detach().cpu().double().numpy() if torch.is_tensor(b) else np.asarray(b, np.float64)
+    assert a.shape == b.shape, (name, a.shape, b.shape)
+    err = np.abs(a - b)
+    bad = err > atol + rtol * np.abs(b)
+    assert not bad.any(), '%s: %d/%d out of tolerance, max abs err %.3e (|ref| there %.3e)' % (
+        name, bad.sum(), bad.size, err.max(), np.abs(b).reshape(-1)[err.argmax()])
+
+
+# ------------------------------------------------------------------------------------------- MLP pieces
+def test_embedder_and_net_forward(cuda_dev):
+    from vqnerf_release_b200 import abi
+    from vqnerf_release_b200.nerfactor.networks.embedder import Embedder
+    from vqnerf_release_b200.nerfactor.networks.mlp import Network
+    rng = np.random.RandomState(0)
+    x = rng.uniform(-1, 1, size=(777, 3)).astype(np.float32)
+    e = Embedder(n_freqs=10, log2_max_freq=9)(torch.as_tensor(x).to(cuda_dev))
+    _close(e, O.embed(torch.as_tensor(x, dtype=torch.float64), 10), 'embed', rtol=0, atol=2e-6)
+    assert Embedder(n_freqs=10, log2_max_freq=9).out_dims == 63
+    nets = O.make_vq_nfr_nets(3, bias_scale=0.1)
+    for name, inp in (('fine_enc', e.cpu().numpy()), ('bottleneck', rng.normal(size=(130, 128)).astype(np.float32)),
+                      ('diff_main', rng.uniform(0, 1, size=(65, 256)).astype(np.float32)),
+                      ('spec_main', rng.uniform(0, 1, size=(1, 256)).astype(np.float32))):
+        on = nets[name]
+        act = [{0: None, 1: 'relu', 2: 'sigmoid'}[a] for a in on.acts]
+        net = Network.from_arrays(on.weights, on.biases, act, skip_at=None if on.skip_at is None else [on.skip_at],
+                                  device=cuda_dev)
+        y = net(torch.as_tensor(inp).to(cuda_dev))
+        _close(y, on(torch.as_tensor(inp, dtype=torch.float64)), name)
+
+
+def test_pred_enc_and_heads_match_oracle(cuda_dev):
+    scene = O.synth_scene(1, bias_scale=0.05)
+    m = _model_from_scene(scene, cuda_dev)
+    rng = np.random.RandomState(5)
+    for n in (1, 63, 64, 65, 1000):
+        pts = rng.uniform(-1, 1, size=(n, 3)).astype(np.float32)
+        z = m._pred_enc_at(torch.as_tensor(pts).to(cuda_dev))
+        zo = O.pred_enc_at(scene.nets, torch.as_tensor(pts, dtype=torch.float64))
+        _close(z, zo, 'z_enc n=%d' % n)
+        for vq in (False, True):
+            sfx = '_vq' if vq else '_main'
+            _close(m._pred_diff_at(z, vq), O.pred_head(scene.nets, 'diff' + sfx, zo), 'diff' + sfx)
+            _close(m._pred_spec_at(z, vq), O.pred_head(scene.nets, 'spec' + sfx, zo), 'spec' + sfx)
+            _close(m._pred_rough_at(z, vq), O.pred_head(scene.nets, 'rough' + sfx, zo), 'rough' + sfx)
+
+
+# ------------------------------------------------------------------------------------------- VQ
+def _latents(n, k, seed):
+    rng = np.random.RandomState(seed)
+    x = rng.uniform(0, 1, size=(n, 256)).astype(np.float32)
+    x /= np.sqrt((x.astype(np.float64) ** 2).sum(1, keepdims=True)).astype(np.float32)
+    cb = rng.uniform(0, 1, size=(256, k)).astype(np.float32)
+    cb /= np.sqrt((cb.astype(np.float64) ** 2).sum(0, keepdims=True)).astype(np.float32)
+    return x, cb
+
+
+@pytest.mark.parametrize('k', [1, 8, 15, 16, 17, 32, 64, 128, 256, 1024])
+def test_vq_indices_bit_exact(cuda_dev, k):
+    from vqnerf_release_b200 import abi
+    n = 20001 if k <= 64 else 4097
+    x, cb = _latents(n, k, 10 + k)
+    out = abi.vq_assign(torch.as_tensor(x).to(cuda_dev), torch.as_tensor(cb).to(cuda_dev), want_distances=True)
+    vq = O.VectorQuantizerEMA(256, k, 0.1, dtype=torch.float64)
+    o = vq(torch.as_tensor(x, dtype=torch.float64), torch.as_tensor(cb, dtype=torch.float64), False)
+    gap = O.top2_gap_rel(o['distances']).numpy()
+    idx = out['indices'].cpu().numpy()
+    ref = o['encoding_indices'].numpy()
+    mism = idx != ref
+    assert not (mism & (gap >= 1e-6)).any(), 'K=%d: %d index mismatches outside the 1e-6 tie tolerance' % (
+        k, int((mism & (gap >= 1e-6)).sum()))
+    assert out['indices'].dtype == torch.int64
+    _close(out['distances'], o['distances'], 'distances K=%d' % k, rtol=1e-5, atol=2e-6)
+    _close(out['quantize'], o['quantize'], 'quantize K=%d' % k, rtol=0, atol=1e-6)
+
+
+def test_vq_duplicate_codewords_pick_first(cuda_dev):
+    from vqnerf_release_b200 import abi
+    x, cb = _latents(512, 15, 3)
+    cb[:, 9] = cb[:, 4]                     # exact duplicate: argmax(-d) must return the lower index
+    out = abi.vq_assign(torch.as_tensor(x).to(cuda_dev), torch.as_tensor(cb).to(cuda_dev))
+    assert not (out['indices'] == 9).any()
+    # empty input
+    out = abi.vq_assign(torch.zeros((0, 256), device=cuda_dev), torch.as_tensor(cb).to(cuda_dev))
+    assert out['indices'].shape == (0,)
+    with pytest.raises(ValueError):
+        abi.vq_assign(torch.zeros((4, 128), device=cuda_dev), torch.zeros((128, 15), device=cuda_dev))
+
+
+def test_vq_layer_training_matches_oracle(cuda_dev):
+    """EMA state, update, loss, perplexity, thres mask over three training steps + one eval step."""
+    from vqnerf_release_b200.nerfactor.networks.vq_layers import VectorQuantizerEMA
+    k = 15
+    x, cb = _latents(3000, k, 21)
+    layer = VectorQuantizerEMA(256, k, 0.1, seed=2, device=cuda_dev)
+    ovq = O.VectorQuantizerEMA(256, k, 0.1, dtype=torch.float64)
+    cbt, cbo = torch.as_tensor(cb).to(cuda_dev), torch.as_tensor(cb, dtype=torch.float64)
+    xo = torch.as_tensor(x, dtype=torch.float64)
+    thres = np.array([0.0] * 3 + [0.5] * 12)
+    for step in range(3):
+        roll = np.random.RandomState(step).uniform(0, 1, size=(1, k))
+        r = layer(torch.as_tensor(x).to(cuda_dev), cbt, True, thres=thres, roll=roll)
+        o = ovq(xo, cbo, True, thres=torch.as_tensor(thres).reshape(1, -1), roll=torch.as_tensor(roll))
+        assert set(r) == {'quantize', 'loss', 'perplexity', 'encodings', 'encoding_indices', 'distances', 'update'}
+        gap = O.top2_gap_rel(o['distances']).numpy()
+        mism = r['encoding_indices'].cpu().numpy() != o['encoding_indices'].numpy()
+        assert not (mism & (gap >= 1e-6)).any()
+        _close(r['distances'], o['distances'], 'masked distances', rtol=1e-5, atol=2e-6)
+        _close(r['update'], o['update'], 'update step %d' % step, rtol=2e-5, atol=1e-6)
+        _close(r['loss'], o['loss'], 'loss', rtol=1e-5)
+        _close(r['perplexity'], o['perplexity'], 'perplexity', rtol=1e-5)
+        _close(r['encodings'].sum(0), o['encodings'].sum(0), 'one-hot counts', rtol=0, atol=0)
+        cbt, cbo = r['update'].contiguous(), o['update']
+    assert layer.state['counters'].tolist() == [3, 3]
+    _close(layer.state['cs_hidden'], ovq.ema_cluster_size.hidden, 'cs_hidden', rtol=1e-5)
+    _close(layer.state['dw_average'], ovq.ema_dw.average, 'dw_average', rtol=2e-5, atol=1e-6)
+    r = layer(torch.as_tensor(x).to(cuda_dev), cbt, False)
+    assert 'update' not in r and layer.state['counters'].tolist() == [3, 3]
+    sd = layer.state_dict()
+    layer.load_state_dict(sd)
+
+
+def test_get_codebook_and_normalize(cuda_dev):
+    from vqnerf_release_b200 import abi
+    rng = np.random.RandomState(0)
+    raw = rng.uniform(-0.3, 1.3, size=(256, 15)).astype(np.float32)
+    _close(abi.get_codebook(torch.as_tensor(raw).to(cuda_dev)), O.get_codebook(torch.as_tensor(raw, dtype=torch.float64)),
+           'get_codebook', rtol=1e-6)
+    x = rng.normal(size=(333, 256)).astype(np.float32)
+    x[5] = 1e-5        # squared norm below the 1e-6 epsilon
+    _close(abi.l2_normalize_rows(torch.as_tensor(x).to(cuda_dev)),
+           O.safe_l2_normalize(torch.as_tensor(x, dtype=torch.float64), 1), 'l2_normalize_rows', rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------- shading
+def test_eval_brdf_and_render_fine_grained(cuda_dev):
+    scene = O.synth_scene(4)
+    m = _model_from_scene(scene, cuda_dev)
+    b = O.synth_batch(40, 4)
+    dt = torch.float64
+    xyz, rayo, normal = (torch.as_tensor(b[k], dtype=dt) for k in ('xyz', 'rayo', 'normal'))
+    lxyz = torch.as_tensor(scene.lxyz, dtype=torch.float32).to(dt)
+    l, v = O.calc_ldir(lxyz, xyz), O.calc_vdir(rayo, xyz)
+    nrm = O.normal_correct(normal, v)
+    rng = np.random.RandomState(0)
+    albedo, spec = rng.uniform(0, 1, (40, 3)).astype(np.float32), rng.uniform(0, 1, (40, 3)).astype(np.float32)
+    rough = rng.uniform(0.05, 1, (40, 1)).astype(np.float32)
+    ob = O.get_brdf(l, v, nrm, torch.as_tensor(albedo, dtype=dt), torch.as_tensor(rough, dtype=dt),
+                    torch.as_tensor(spec, dtype=dt))
+    g = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32).to(cuda_dev)
+    gl = m._calc_ldir(g(b['xyz']))
+    _close(gl, l, '_calc_ldir', rtol=0, atol=1e-6)
+    gv = m._calc_vdir(g(b['rayo']), g(b['xyz']))
+    _close(gv, v, '_calc_vdir', rtol=0, atol=1e-6)
+    gb = m._eval_brdf_at(gl, gv, g(nrm.numpy()), g(albedo), g(spec), g(rough))
+    for got, ref, nm in zip(gb, ob, ('brdf', 'glossy', 'diffuse')):
+        _close(got, ref, nm, rtol=2e-4, atol=1e-6)
+    rgb, _, probes = m._render(gb[0], gl, g(nrm.numpy()), g(b['lvis']))
+    lareas = torch.as_tensor(scene.lareas, dtype=torch.float32).to(dt)
+    orgb, _ = O.render(ob[0], l, nrm, lareas, torch.clamp(torch.as_tensor(scene.light, dtype=dt), min=0),
+                       torch.as_tensor(b['lvis'], dtype=dt))
+    _close(rgb, orgb, '_render')
+    assert probes is None
+
+
+@pytest.mark.parametrize('n_probes,fg,data_type', [(0, 1.0, 'nerf'), (2, 0.7, 'nerf'), (9, 0.5, 'nerf'), (1, 0.8, 'dtu')])
+def test_fast_render_matches_oracle(cuda_dev, n_probes, fg, data_type):
+    n = 4096 if n_probes == 2 else 1500
+    scene = O.synth_scene(11, n_probes=n_probes, bias_scale=0.05, data_type=data_type)
+    batch = O.synth_batch(n, 11, fg_frac=fg, with_lvis=(data_type == 'nerf'))
+    m = _model_from_scene(scene, cuda_dev)
+    pred, gt, loss_kwargs, to_vis = m.fast_render(_batch_tuple(batch, cuda_dev, data_type), mode='test',
+                                                  relight_probes=True, gen_embed=True, opt_scale=[0.9, 1.1, 1.05])
+    o = O.fast_render(scene, batch, torch.float64, relight_probes=True, gen_embed=True, opt_scale=[0.9, 1.1, 1.05])
+    for k in ('basecolor', 'albedo', 'spec', 'rough'):
+        _close(pred[k], o[k], k)
+    if n_probes > 0:
+        _close(pred['rgb_probes'], o['rgb_probes'], 'rgb_probes', rtol=RTOL, atol=5e-6)
+        assert pred['rgb_probes'].shape == (n, n_probes, 3)
+    else:
+        assert 'rgb_probes' not in pred
+    gap = O.top2_gap_rel(o['_vq_distances']).numpy()
+    mask = batch['alpha'][:, 0] > 0
+    emb = pred['embed'].cpu().numpy()[:, 0]
+    assert (emb[~mask] == 0).all()
+    mism = emb[mask] != o['_embed_ind'].numpy()
+    assert not (mism & (gap >= 1e-6)).any()
+    bg = ~mask
+    for k in ('basecolor', 'albedo', 'spec', 'rough'):
+        assert float(pred[k][torch.as_tensor(bg).to(cuda_dev)].abs().max()) == 0.0 if bg.any() else True
+    assert set(to_vis) >= {'id', 'hw', 'pred_albedo', 'gt_rgb', 'gt_alpha'}
+    assert loss_kwargs['mode'] == 'test'
+    # dst_env path: main render under a novel probe, returned as pred['rgb']
+    if n_probes > 0:
+        pred2, _, _, _ = m.fast_render(_batch_tuple(batch, cuda_dev, data_type), mode='test', dst_env='probe00')
+        sc2 = O.Scene(**{**scene.__dict__, 'light': scene.probes[0]})
+        o2 = O.fast_render(sc2, batch, torch.float64)
+        _close(pred2['rgb'], o2['rgb'], 'rgb under dst_env', rtol=RTOL, atol=5e-6)
+    with pytest.raises(ValueError):
+        m.fast_render(_batch_tuple(batch, cuda_dev, data_type), mode='bogus')
+
+
+def test_fast_render_golden_vectors(cuda_dev):
+    g = np.load(os.path.join(GOLD, 'decomp_oracle.npz'))
+    scene = O.synth_scene(int(g['seed']), n_probes=int(g['n_probes']), bias_scale=float(g['bias_scale']))
+    batch = O.synth_batch(int(g['n']), int(g['seed']), fg_frac=float(g['fg_frac']))
+    m = _model_from_scene(scene, cuda_dev)
+    pred, _, _, _ = m.fast_render(_batch_tuple(batch, cuda_dev), mode='test', relight_probes=True, gen_embed=True)
+    for k in ('basecolor', 'albedo', 'spec', 'rough', 'rgb_probes'):
+        _close(pred[k], g['fr_' + k], 'golden ' + k, rtol=RTOL, atol=5e-6)
+    # training-mode call: two EMA steps against the committed float64 vectors
+    for step in range(2):
+        pred, gt, lk, _ = m(_batch_tuple(batch, cuda_dev), mode='train', thres=g['thres'], roll=g['roll'])
+        _close(lk['rgb'], g['call%d_rgb_linear' % step], 'call rgb', rtol=RTOL, atol=5e-6)
+        _close(lk['vqrgb'], g['call%d_vq_rgb_linear' % step], 'call vq_rgb', rtol=2e-4, atol=5e-6)
+        _close(lk['vqloss'], g['call%d_vq_loss' % step], 'vq loss', rtol=1e-4)
+        _close(m._codebook, g['call%d_update' % step], 'codebook after EMA', rtol=1e-4, atol=1e-6)
+
+
+def test_call_vali_mode_outputs(cuda_dev):
+    scene = O.synth_scene(5, bias_scale=0.05)
+    batch = O.synth_batch(700, 5, fg_frac=0.6)
+    m = _model_from_scene(scene, cuda_dev)
+    cb_before = m._codebook.clone()
+    pred, gt, lk, to_vis = m.call(_batch_tuple(batch, cuda_dev), mode='vali', full_vis=True)
+    assert torch.equal(cb_before, m._codebook)              # no EMA write-back outside training
+    vq = O.VectorQuantizerEMA(256, 15, 0.1, dtype=torch.float64)
+    o = O.call_forward(scene, batch, vq, 'vali', dtype=torch.float64)
+    mask = torch.as_tensor(batch['alpha'][:, 0] > 0)
+    _close(pred['rgb_diff'][mask.to(cuda_dev)], o['rgb_diff'], 'rgb_diff', rtol=RTOL, atol=5e-6)
+    _close(pred['rgb_spec'][mask.to(cuda_dev)], o['rgb_spec'], 'rgb_spec', rtol=2e-4, atol=5e-6)
+    _close(pred['rgb'][mask.to(cuda_dev)], O.linear2srgb(o['rgb_linear']), 'rgb srgb', rtol=RTOL, atol=1e-5)
+    _close(pred['normal'][mask.to(cuda_dev)], o['normal'], 'normal', rtol=0, atol=0)
+    _close(pred['vq_albedo'][mask.to(cuda_dev)], o['vq_albedo'], 'vq_albedo')
+    _close(pred['ks'][mask.to(cuda_dev)], o['ks'], 'ks')
+    assert to_vis['enc_z'].shape == (700, 256)
+    for k in ('vq_rgb', 'vq_spec', 'vq_rough', 'embed'):
+        assert k in pred
+
+
+def test_shade_properties_full_size(cuda_dev):
+    """Size-independent properties at a full 800x800 view (BASELINE config #2, P=1): linearity in the light
+    probe, zero radiance for zero visibility, diffuse+specular == total before clipping."""
+    from vqnerf_release_b200 import abi
+    n = 640000
+    g = torch.Generator(device='cpu').manual_seed(0)
+    dev = cuda_dev
+    xyz = (torch.rand((n, 3), generator=g) * 2 - 1).to(dev)
+    rayo = torch.nn.functional.normalize(torch.randn((n, 3), generator=g), dim=1).mul(4).to(dev)
+    normal = torch.nn.functional.normalize(torch.randn((n, 3), generator=g), dim=1).to(dev)
+    lvis = torch.rand((n, 512), generator=g).to(dev)
+    albedo = (torch.rand((n, 3), generator=g) * 0.2).to(dev)
+    spec = (torch.rand((n, 3), generator=g) * 0.2).to(dev)
+    rough = (torch.rand((n, 1), generator=g) * 0.5 + 0.5).to(dev)
+    lxyz, lareas = abi.gen_light_xyz(16, 32)
+    lxyz, lareas = torch.as_tensor(lxyz, dtype=torch.float32).to(dev), torch.as_tensor(lareas, dtype=torch.float32).to(dev)
+    la = torch.rand((512, 3), generator=g).mul(0.05).to(dev)
+    lb = torch.rand((512, 3), generator=g).mul(0.05).to(dev)
+    lights = torch.stack([la, lb, la + lb])
+    out = abi.shade(xyz, rayo, normal, lvis, albedo, spec, rough, lxyz, lareas, lights, want_split=True)
+    rgb = out['rgb']
+    assert float(rgb.max()) < 1.0, 'test radiance must stay below the clip for the linearity check'
+    err = (rgb[:, 0] + rgb[:, 1] - rgb[:, 2]).abs().max()
+    assert float(err) < 2e-6, 'shade is not linear in the probe: %g' % float(err)
+    err = (out['rgb_diff'] + out['rgb_spec'] - rgb[:, 0]).abs().max()
+    assert float(err) < 2e-6
+    dark = abi.shade(xyz, rayo, normal, torch.zeros_like(lvis), albedo, spec, rough, lxyz, lareas, lights)
+    assert float(dark['rgb'].abs().max()) == 0.0
+    assert torch.isfinite(rgb).all()
+
+
+def test_compaction_and_scatter(cuda_dev):
+    from vqnerf_release_b200 import abi
+    for n in (0, 1, 1023, 1024, 1025, 100003):
+        rng = np.random.RandomState(n)
+        alpha = (rng.uniform(size=(n, 1)) < 0.4).astype(np.float32) * rng.uniform(0.1, 1, size=(n, 1)).astype(np.float32)
+        row_idx, n_act = abi.compact_mask(torch.as_tensor(alpha).to(cuda_dev))
+        ref = np.nonzero(alpha[:, 0] > 0)[0]
+        assert int(n_act.item()) == len(ref)
+        assert np.array_equal(row_idx.cpu().numpy()[:len(ref)], ref.astype(np.int32))
+        if n > 0:
+            vals = torch.arange(len(ref) * 3, dtype=torch.float32, device=cuda_dev).reshape(-1, 3) + 1
+            full = abi.scatter_rows(vals, row_idx, n, n_dev=n_act, n=len(ref))
+            exp = np.zeros((n, 3), np.float32)
+            exp[ref] = vals.cpu().numpy()
+            assert np.array_equal(full.cpu().numpy(), exp)
+
+
+def test_srgb_kernels(cuda_dev):
+    from vqnerf_release_b200 import abi
+    t = torch.linspace(-0.2, 1.2, 1001)
+    _close(abi.linear2srgb(t.to(cuda_dev)), O.linear2srgb(t.double()), 'linear2srgb', rtol=1e-6, atol=1e-6)
+    t = torch.linspace(0, 1, 1001)
+    _close(abi.srgb2linear(t.to(cuda_dev)), O.srgb2linear(t.double()), 'srgb2linear', rtol=1e-5, atol=1e-7)
+
+
+def test_check_numerics_raises(cuda_dev):
+    """A NaN in a weight must surface as the reference's check_numerics error, not as a silent NaN."""
+    from vqnerf_release_b200 import _lib
+    scene = O.synth_scene(2)
+    scene.nets['bottleneck'].biases[2][0] = np.nan
+    m = _model_from_scene(scene, cuda_dev)
+    m.debug = True
+    with pytest.raises(_lib.NonFiniteError):
+        m._pred_enc_at(torch.zeros((10, 3), device=cuda_dev))
+
+
+def test_native_library_is_what_ran(cuda_dev):
+    from vqnerf_release_b200 import _lib
+    ctx = _lib.Context.get(cuda_dev)
+    assert ctx.launch_count() > 0
+    maps = open('/proc/self/maps').read()
+    assert 'libvqnerf_b200.so' in maps

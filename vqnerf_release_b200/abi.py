@@ -1,0 +1,395 @@
+"""Torch-tensor wrappers, one per C-ABI entry point (include/vqnerf_b200.h).
+
+Each wrapper validates device/dtype/contiguity, allocates outputs with torch (device memory only)
+and launches on torch's current stream.  Nothing here computes on the host or in PyTorch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+F32 = torch.float32
+
+
+def _ctx(t: torch.Tensor) -> L.Context:
+    return L.Context.get(t.device)
+
+
+def _f(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != F32:
+        t = t.to(F32)
+    return t.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+def gen_light_xyz(envmap_h: int, envmap_w: int, envmap_radius: float = 1e2) -> Tuple[np.ndarray, np.ndarray]:
+    """brdf/renderer.py:184-219 (float64 host arrays)."""
+    lib = L.load()
+    xyz = np.zeros((envmap_h, envmap_w, 3), np.float64)
+    areas = np.zeros((envmap_h, envmap_w), np.float64)
+    L.check(lib.vqn_gen_light_xyz(envmap_h, envmap_w, float(envmap_radius),
+                                  xyz.ctypes.data_as(C.POINTER(C.c_double)),
+                                  areas.ctypes.data_as(C.POINTER(C.c_double))))
+    return xyz, areas
+
+
+class PackedNet:
+    """vqn_net handle for one mlp.Network; holds references to the caller's weight tensors."""
+
+    def __init__(self, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor], acts: Sequence,
+                 skip_at: Optional[int] = None):
+        assert len(weights) == len(biases) == len(acts)
+        self.weights = [_f(w) for w in weights]
+        self.biases = [_f(b) for b in biases]
+        self.acts = [L.act_code(a) for a in acts]
+        self.skip_at = -1 if skip_at is None else int(skip_at)
+        self.ctx = _ctx(self.weights[0])
+        self.in_dim = int(self.weights[0].shape[0])
+        self.out_dim = int(self.weights[-1].shape[1])
+        self.handle = C.c_void_p()
+        d = self._desc()
+        L.check(self.ctx.lib.vqn_net_create(self.ctx.handle, C.byref(d), C.byref(self.handle),
+                                            L.stream_ptr(self.weights[0].device)))
+
+    def _desc(self) -> L.NetDesc:
+        d = L.NetDesc()
+        n = len(self.weights)
+        if n > L.VQN_MAX_LAYERS:
+            raise ValueError('at most %d layers' % L.VQN_MAX_LAYERS)
+        d.n_layers, d.in_dim, d.skip_at = n, self.in_dim, self.skip_at
+        prev = self.in_dim
+        for i, (w, b) in enumerate(zip(self.weights, self.biases)):
+            exp_in = prev + (self.in_dim if (self.skip_at >= 0 and i == self.skip_at + 1) else 0)
+            if w.dim() != 2 or w.shape[0] != exp_in or b.shape != (w.shape[1],):
+                raise ValueError('layer %d: kernel %s / bias %s do not chain (expected in=%d)'
+                                 % (i, tuple(w.shape), tuple(b.shape), exp_in))
+            d.widths[i], d.acts[i] = int(w.shape[1]), self.acts[i]
+            d.w[i], d.b[i] = w.data_ptr(), b.data_ptr()
+            prev = int(w.shape[1])
+        return d
+
+    def repack(self):
+        d = self._desc()
+        L.check(self.ctx.lib.vqn_net_repack(self.handle, C.byref(d), L.stream_ptr(self.weights[0].device)))
+
+    def forward(self, x: torch.Tensor, precision='fp32') -> torch.Tensor:
+        x = _f(x)
+        if x.dim() != 2 or x.shape[1] != self.in_dim:
+            raise ValueError('expected input [n,%d], got %s' % (self.in_dim, tuple(x.shape)))
+        y = torch.empty((x.shape[0], self.out_dim), dtype=F32, device=x.device)
+        L.check(self.ctx.lib.vqn_net_forward(self.handle, L.ptr(x), x.shape[0], L.ptr(y),
+                                             L.precision_code(precision), L.stream_ptr(x.device)))
+        return y
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None) and self.handle.value:
+                self.ctx.lib.vqn_net_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+
+def embed(x: torch.Tensor, n_freqs: int) -> torch.Tensor:
+    x = _f(x)
+    out = torch.empty((x.shape[0], 3 + 6 * n_freqs), dtype=F32, device=x.device)
+    c = _ctx(x)
+    L.check(c.lib.vqn_embed(c.handle, L.ptr(x), x.shape[0], n_freqs, L.ptr(out), L.stream_ptr(x.device)))
+    return out
+
+
+def pred_enc_at(fine_enc: PackedNet, bottleneck: PackedNet, n_freqs: int, pts: torch.Tensor,
+                row_idx: Optional[torch.Tensor] = None, n: Optional[int] = None, precision='fp32',
+                out: Optional[torch.Tensor] = None, n_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    pts = _f(pts)
+    n = pts.shape[0] if n is None else n
+    z = out if out is not None else torch.empty((n, bottleneck.out_dim), dtype=F32, device=pts.device)
+    c = _ctx(pts)
+    L.check(c.lib.vqn_pred_enc_at(c.handle, fine_enc.handle, bottleneck.handle, n_freqs, L.ptr(pts),
+                                  L.ptr(row_idx, torch.int32), L.ptr(n_dev, torch.int32), n, L.ptr(z),
+                                  L.precision_code(precision),
+                                  L.stream_ptr(pts.device)))
+    return z
+
+
+def pred_heads(diff: Optional[PackedNet], spec: Optional[PackedNet], rough: Optional[PackedNet],
+               z: torch.Tensor, slope: float = 1.0, bias: float = 0.0, precision='fp32',
+               n_dev: Optional[torch.Tensor] = None):
+    z = _f(z)
+    n = z.shape[0]
+    outs = [torch.empty((n, h.out_dim), dtype=F32, device=z.device) if h is not None else None
+            for h in (diff, spec, rough)]
+    c = _ctx(z)
+    L.check(c.lib.vqn_pred_heads(c.handle, *(h.handle if h is not None else None for h in (diff, spec, rough)),
+                                 L.ptr(z), L.ptr(n_dev, torch.int32), n, float(slope), float(bias),
+                                 *(L.ptr(o) for o in outs),
+                                 L.precision_code(precision), L.stream_ptr(z.device)))
+    return tuple(outs)
+
+
+def get_codebook(raw: torch.Tensor) -> torch.Tensor:
+    raw = _f(raw)
+    out = torch.empty_like(raw)
+    c = _ctx(raw)
+    L.check(c.lib.vqn_get_codebook(c.handle, L.ptr(raw), raw.shape[0], raw.shape[1], L.ptr(out),
+                                   L.stream_ptr(raw.device)))
+    return out
+
+
+def l2_normalize_rows(x: torch.Tensor) -> torch.Tensor:
+    x = _f(x)
+    out = torch.empty_like(x)
+    c = _ctx(x)
+    L.check(c.lib.vqn_l2_normalize_rows(c.handle, L.ptr(x), x.shape[0], x.shape[1], L.ptr(out),
+                                        L.stream_ptr(x.device)))
+    return out
+
+
+def vq_stats_size(z_dim: int, k: int) -> int:
+    return k + 2 + z_dim * k
+
+
+def vq_assign(inputs: torch.Tensor, codebook: torch.Tensor, sel_mask: Optional[torch.Tensor] = None,
+              normalize_inputs: bool = False, want_quantize: bool = True, want_distances: bool = False,
+              want_znorm: bool = False, stats: Optional[torch.Tensor] = None, want_dw: bool = False):
+    """Returns dict(indices int64 [n], quantize, distances, z_norm) -- absent outputs are None."""
+    inputs, codebook = _f(inputs), _f(codebook)
+    n, zd = inputs.shape
+    k = codebook.shape[1]
+    if codebook.shape[0] != zd:
+        raise ValueError('codebook must be [%d,K]' % zd)
+    dev = inputs.device
+    idx = torch.empty((n,), dtype=torch.int64, device=dev)
+    quant = torch.empty_like(inputs) if want_quantize else None
+    dist = torch.empty((n, k), dtype=F32, device=dev) if want_distances else None
+    zn = torch.empty_like(inputs) if want_znorm else None
+    if sel_mask is not None:
+        sel_mask = _f(sel_mask).reshape(-1)
+        if sel_mask.numel() != k:
+            raise ValueError('sel_mask must have K entries')
+    if stats is not None and (stats.dtype != torch.float64 or stats.numel() != vq_stats_size(zd, k)):
+        raise ValueError('stats must be float64 [K+2+Z*K]')
+    c = _ctx(inputs)
+    L.check(c.lib.vqn_vq_assign(c.handle, L.ptr(inputs), n, zd, L.ptr(codebook), k, L.ptr(sel_mask),
+                                int(normalize_inputs), L.ptr(idx), L.ptr(quant), L.ptr(dist), L.ptr(zn),
+                                L.ptr(stats), int(want_dw), L.stream_ptr(dev)))
+    return {'indices': idx, 'quantize': quant, 'distances': dist, 'z_norm': zn}
+
+
+def vq_ema_update(stats: torch.Tensor, codebook: torch.Tensor, decay: float, epsilon: float,
+                  commitment_cost: float, is_training: bool, state: Optional[dict]):
+    """state: dict(cs_hidden, cs_average, dw_hidden, dw_average, counters) caller-owned tensors."""
+    codebook = _f(codebook)
+    zd, k = codebook.shape
+    dev = codebook.device
+    loss = torch.empty((1,), dtype=F32, device=dev)
+    perp = torch.empty((1,), dtype=F32, device=dev)
+    update = torch.empty_like(codebook) if is_training else None
+    c = _ctx(codebook)
+    st = state or {}
+    L.check(c.lib.vqn_vq_ema_update(
+        c.handle, L.ptr(stats, torch.float64), zd, k, L.ptr(codebook), float(decay), float(epsilon),
+        float(commitment_cost), int(is_training), L.ptr(st.get('cs_hidden')), L.ptr(st.get('cs_average')),
+        L.ptr(st.get('dw_hidden')), L.ptr(st.get('dw_average')), L.ptr(st.get('counters'), torch.int64),
+        L.ptr(update), L.ptr(loss), L.ptr(perp), L.stream_ptr(dev)))
+    return update, loss, perp
+
+
+def shade(xyz, rayo, normal, lvis, albedo, spec, rough, lxyz, lareas, lights, *, row_idx=None, n_dev=None,
+          n: Optional[int] = None, n_total: Optional[int] = None, to_srgb=False, gamma=None, clip_light0=True,
+          want_split=False, want_normal=False, out_rgb: Optional[torch.Tensor] = None):
+    """Fused _calc_ldir/_calc_vdir/_normal_correct/_eval_brdf_at/_render.  lights [1+P,512,3].
+    Returns dict(rgb [n_total,1+P,3], rgb_diff, rgb_spec, normal) (full-length when row_idx is given)."""
+    xyz, rayo, normal = _f(xyz), _f(rayo), _f(normal)
+    albedo, spec, rough = _f(albedo), _f(spec), _f(rough)
+    lights = _f(lights)
+    if lights.dim() == 2:
+        lights = lights[None]
+    npb = lights.shape[0]
+    dev = xyz.device
+    n = albedo.shape[0] if n is None else n
+    n_total = xyz.shape[0] if n_total is None else n_total
+    alloc = torch.zeros if row_idx is not None else torch.empty
+    rgb = out_rgb if out_rgb is not None else alloc((n_total, npb, 3), dtype=F32, device=dev)
+    a = L.ShadeArgs()
+    a.xyz, a.rayo, a.normal = xyz.data_ptr(), rayo.data_ptr(), normal.data_ptr()
+    if lvis is not None:
+        lvis = _f(lvis)
+        a.lvis = lvis.data_ptr()
+    a.albedo, a.spec, a.rough = albedo.data_ptr(), spec.data_ptr(), rough.data_ptr()
+    if row_idx is not None:
+        a.row_idx = L.ptr(row_idx, torch.int32).value
+    if n_dev is not None:
+        a.n_dev = L.ptr(n_dev, torch.int32).value
+    a.n = n
+    lxyz, lareas = _f(lxyz).reshape(-1, 3), _f(lareas).reshape(-1)
+    a.lxyz, a.lareas, a.lights = lxyz.data_ptr(), lareas.data_ptr(), lights.data_ptr()
+    a.n_probes, a.to_srgb, a.clip_light0 = npb, int(to_srgb), int(clip_light0)
+    if gamma is not None:
+        a.use_gamma, a.gamma_bias, a.gamma_index = 1, float(gamma[0]), float(gamma[1])
+    a.rgb = rgb.data_ptr()
+    out = {'rgb': rgb, 'rgb_diff': None, 'rgb_spec': None, 'normal': None}
+    if want_split:
+        out['rgb_diff'] = alloc((n_total, 3), dtype=F32, device=dev)
+        out['rgb_spec'] = alloc((n_total, 3), dtype=F32, device=dev)
+        a.rgb_diff, a.rgb_spec = out['rgb_diff'].data_ptr(), out['rgb_spec'].data_ptr()
+    if want_normal:
+        out['normal'] = alloc((n_total, 3), dtype=F32, device=dev)
+        a.normal_out = out['normal'].data_ptr()
+    c = _ctx(xyz)
+    L.check(c.lib.vqn_shade(c.handle, C.byref(a), L.stream_ptr(dev)))
+    return out
+
+
+def eval_brdf(pts2l, pts2c, normal, albedo, spec, rough):
+    pts2l, pts2c, normal, albedo, spec, rough = map(_f, (pts2l, pts2c, normal, albedo, spec, rough))
+    n = pts2c.shape[0]
+    outs = [torch.empty((n, 512, 3), dtype=F32, device=pts2c.device) for _ in range(3)]
+    c = _ctx(pts2c)
+    L.check(c.lib.vqn_eval_brdf(c.handle, L.ptr(pts2l), L.ptr(pts2c), L.ptr(normal), L.ptr(albedo), L.ptr(spec),
+                                L.ptr(rough), n, *(L.ptr(o) for o in outs), L.stream_ptr(pts2c.device)))
+    return tuple(outs)
+
+
+def render(brdf, l, normal, lvis, lareas, light, gamma=None):
+    brdf, l, normal, lareas, light = map(_f, (brdf, l, normal, lareas, light))
+    lvis = _f(lvis) if lvis is not None else None
+    n = normal.shape[0]
+    rgb = torch.empty((n, 3), dtype=F32, device=normal.device)
+    c = _ctx(normal)
+    g = gamma or (1.0, 1.0)
+    L.check(c.lib.vqn_render(c.handle, L.ptr(brdf), L.ptr(l), L.ptr(normal), L.ptr(lvis), L.ptr(lareas.reshape(-1)),
+                             L.ptr(light.reshape(-1, 3)), n, int(gamma is not None), float(g[0]), float(g[1]),
+                             L.ptr(rgb), L.stream_ptr(normal.device)))
+    return rgb
+
+
+def material_combine(basecolor, ks, opt_scale=None, n_dev=None, want_scaled=True):
+    basecolor, ks = _f(basecolor), _f(ks)
+    n = basecolor.shape[0]
+    albedo, spec = torch.empty_like(basecolor), torch.empty_like(basecolor)
+    a_s = torch.empty_like(basecolor) if (want_scaled and opt_scale is not None) else None
+    s_s = torch.empty_like(basecolor) if (want_scaled and opt_scale is not None) else None
+    if opt_scale is not None:
+        opt_scale = _f(opt_scale).reshape(-1)
+    c = _ctx(basecolor)
+    L.check(c.lib.vqn_material_combine(c.handle, L.ptr(basecolor), L.ptr(ks), L.ptr(opt_scale),
+                                       L.ptr(n_dev, torch.int32), n, L.ptr(albedo), L.ptr(spec), L.ptr(a_s),
+                                       L.ptr(s_s), L.stream_ptr(basecolor.device)))
+    return albedo, spec, (a_s if a_s is not None else albedo), (s_s if s_s is not None else spec)
+
+
+def linear2srgb(x):
+    x = _f(x)
+    out = torch.empty_like(x)
+    c = _ctx(x)
+    L.check(c.lib.vqn_linear2srgb(c.handle, L.ptr(x), x.numel(), L.ptr(out), L.stream_ptr(x.device)))
+    return out
+
+
+def srgb2linear(x):
+    x = _f(x)
+    out = torch.empty_like(x)
+    c = _ctx(x)
+    L.check(c.lib.vqn_srgb2linear(c.handle, L.ptr(x), x.numel(), L.ptr(out), L.stream_ptr(x.device)))
+    return out
+
+
+def compact_mask(alpha: torch.Tensor):
+    """ind = where(alpha[:,0] > 0): returns (row_idx int32 [n_total], n_active int32 [1]) on device."""
+    a = _f(alpha).reshape(-1)
+    n = a.shape[0]
+    row_idx = torch.empty((max(n, 1),), dtype=torch.int32, device=a.device)
+    n_active = torch.zeros((1,), dtype=torch.int32, device=a.device)
+    c = _ctx(a)
+    L.check(c.lib.vqn_compact_mask(c.handle, L.ptr(a), n, L.ptr(row_idx), L.ptr(n_active), L.stream_ptr(a.device)))
+    return row_idx, n_active
+
+
+def scatter_rows(compact: torch.Tensor, row_idx: torch.Tensor, n_total: int, n_dev=None,
+                 n: Optional[int] = None) -> torch.Tensor:
+    compact = _f(compact)
+    c_ = int(np.prod(compact.shape[1:])) if compact.dim() > 1 else 1
+    n = compact.shape[0] if n is None else n
+    out = torch.zeros((n_total,) + tuple(compact.shape[1:]), dtype=F32, device=compact.device)
+    c = _ctx(compact)
+    L.check(c.lib.vqn_scatter_rows(c.handle, L.ptr(compact), L.ptr(row_idx, torch.int32), L.ptr(n_dev, torch.int32),
+                                   n, c_, L.ptr(out), L.stream_ptr(compact.device)))
+    return out
+
+
+# ---- NeuS -------------------------------------------------------------------------------------
+def neus_up_sample(rays_o, rays_d, z_vals, sdf, r_limit, n_importance, inv_s):
+    rays_o, rays_d, z_vals, sdf = map(_f, (rays_o, rays_d, z_vals, sdf))
+    b, s = z_vals.shape
+    sdf = sdf.reshape(b, s)
+    out = torch.empty((b, n_importance), dtype=F32, device=z_vals.device)
+    c = _ctx(z_vals)
+    L.check(c.lib.vqn_neus_up_sample(c.handle, L.ptr(rays_o), L.ptr(rays_d), L.ptr(z_vals), L.ptr(sdf), b, s,
+                                     float(r_limit), int(n_importance), float(inv_s), L.ptr(out),
+                                     L.stream_ptr(z_vals.device)))
+    return out
+
+
+def neus_cat_z_vals(z_vals, new_z, sdf=None, new_sdf=None):
+    z_vals, new_z = _f(z_vals), _f(new_z)
+    b, s = z_vals.shape
+    i = new_z.shape[1]
+    sdf = _f(sdf).reshape(b, s) if sdf is not None else None
+    new_sdf = _f(new_sdf).reshape(b, i) if new_sdf is not None else None
+    z_out = torch.empty((b, s + i), dtype=F32, device=z_vals.device)
+    sdf_out = torch.empty((b, s + i), dtype=F32, device=z_vals.device) if (sdf is not None and new_sdf is not None) \
+        else None
+    c = _ctx(z_vals)
+    L.check(c.lib.vqn_neus_cat_z_vals(c.handle, L.ptr(z_vals), L.ptr(new_z), L.ptr(sdf), L.ptr(new_sdf), b, s, i,
+                                      L.ptr(z_out), L.ptr(sdf_out), L.stream_ptr(z_vals.device)))
+    return z_out, sdf_out
+
+
+def neus_mid_points(rays_o, rays_d, z_vals, sample_dist):
+    rays_o, rays_d, z_vals = map(_f, (rays_o, rays_d, z_vals))
+    b, s = z_vals.shape
+    pts = torch.empty((b, s, 3), dtype=F32, device=z_vals.device)
+    dirs = torch.empty((b, s, 3), dtype=F32, device=z_vals.device)
+    c = _ctx(z_vals)
+    L.check(c.lib.vqn_neus_mid_points(c.handle, L.ptr(rays_o), L.ptr(rays_d), L.ptr(z_vals), b, s,
+                                      float(sample_dist), L.ptr(pts), L.ptr(dirs), L.stream_ptr(z_vals.device)))
+    return pts, dirs
+
+
+def neus_composite(rays_o, rays_d, z_vals, sdf, gradients, sampled_color, inv_s, cos_anneal_ratio, sample_dist,
+                   radius, background_rgb=None, want_grad_err=True):
+    rays_o, rays_d, z_vals = map(_f, (rays_o, rays_d, z_vals))
+    b, s = z_vals.shape
+    dev = z_vals.device
+    sdf = _f(sdf).reshape(b, s)
+    gradients = _f(gradients).reshape(b, s, 3)
+    sampled_color = _f(sampled_color).reshape(b, s, 3)
+    a = L.NeusCompositeArgs()
+    a.rays_o, a.rays_d, a.z_vals = rays_o.data_ptr(), rays_d.data_ptr(), z_vals.data_ptr()
+    a.sdf, a.gradients, a.sampled_color = sdf.data_ptr(), gradients.data_ptr(), sampled_color.data_ptr()
+    a.n_rays, a.n_samples = b, s
+    a.inv_s, a.cos_anneal_ratio, a.sample_dist, a.radius = float(inv_s), float(cos_anneal_ratio), \
+        float(sample_dist), float(radius)
+    bg = None
+    if background_rgb is not None:
+        bg = _f(background_rgb).reshape(-1)
+        a.background_rgb = bg.data_ptr()
+    o = {k: torch.empty(shape, dtype=F32, device=dev) for k, shape in (
+        ('color', (b, 3)), ('weights', (b, s)), ('surf', (b, 3)), ('depth', (b, 1)), ('cdf', (b, s)),
+        ('inside_sphere', (b, s)), ('mid_z_vals', (b, s)), ('dists', (b, s)), ('weight_sum', (b, 1)),
+        ('weight_max', (b, 1)))}
+    for k, v in o.items():
+        setattr(a, k, v.data_ptr())
+    ge = torch.zeros((2,), dtype=torch.float64, device=dev) if want_grad_err else None
+    if ge is not None:
+        a.grad_err_sums = ge.data_ptr()
+    c = _ctx(z_vals)
+    L.check(c.lib.vqn_neus_composite(c.handle, C.byref(a), L.stream_ptr(dev)))
+    o['grad_err_sums'] = ge
+    return o

@@ -1,0 +1,353 @@
+// NeuS geo-stage per-ray warp-scan kernels (secondary path).
+//
+// Reference: geo/NeuS-ours2/models/renderer.py  sample_pdf :39-69, up_sample :131-175,
+// cat_z_vals :177-191, render_core :193-297.  One warp owns one ray; lane l owns samples
+// [4l, 4l+4) (n_samples <= 128), so every cumulative product / sum is a 4-element serial scan followed
+// by a 5-step warp shuffle scan, and neighbour samples come from lane l+1 by shuffle.  All per-ray state
+// stays in registers; HBM traffic is exactly the rows read and written once (memory-bound kernels).
+#include "common.cuh"
+
+#define NS_MAXS 128
+#define NS_PER 4
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// exclusive product scan over 128 blocked elements; v[j] in: factors, out: exclusive prefix products
+__device__ __forceinline__ void warp_excl_cumprod4(float (&v)[NS_PER], int lane) {
+  float loc[NS_PER];
+  float run = 1.f;
+#pragma unroll
+  for (int j = 0; j < NS_PER; ++j) { loc[j] = run; run *= v[j]; }
+  float incl = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl *= y;
+  }
+  float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0) excl = 1.f;
+#pragma unroll
+  for (int j = 0; j < NS_PER; ++j) v[j] = excl * loc[j];
+}
+
+// inclusive sum scan over 128 blocked elements
+__device__ __forceinline__ void warp_incl_cumsum4(float (&v)[NS_PER], int lane) {
+  float run = 0.f;
+#pragma unroll
+  for (int j = 0; j < NS_PER; ++j) { run += v[j]; v[j] = run; }
+  float incl = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0) excl = 0.f;
+#pragma unroll
+  for (int j = 0; j < NS_PER; ++j) v[j] += excl;
+}
+
+// ---------------------------------------------------------------------------------------------
+// up_sample + sample_pdf(det=True)
+// ---------------------------------------------------------------------------------------------
+__global__ void neus_up_sample_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                      const float* __restrict__ z_vals, const float* __restrict__ sdf,
+                                      long long n_rays, int S, float r_limit, int n_imp, float inv_s,
+                                      float* __restrict__ z_samples) {
+  __shared__ float s_cdf[8][NS_MAXS + 1];
+  __shared__ float s_z[8][NS_MAXS];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long ray = warp; ray < n_rays; ray += nw) {
+    const float ox = rays_o[ray * 3], oy = rays_o[ray * 3 + 1], oz = rays_o[ray * 3 + 2];
+    const float dx = rays_d[ray * 3], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
+    float z[NS_PER + 1], sd[NS_PER + 1], rad[NS_PER + 1];
+#pragma unroll
+    for (int j = 0; j < NS_PER; ++j) {
+      int i = NS_PER * lane + j;
+      z[j] = i < S ? z_vals[ray * S + i] : 0.f;
+      sd[j] = i < S ? sdf[ray * S + i] : 0.f;
+      float px = ox + dx * z[j], py = oy + dy * z[j], pz = oz + dz * z[j];
+      rad[j] = sqrtf(px * px + py * py + pz * pz);     // torch.linalg.norm(pts, ord=2)
+    }
+    // element NS_PER = first element of the next lane
+    z[NS_PER] = __shfl_down_sync(0xffffffffu, z[0], 1);
+    sd[NS_PER] = __shfl_down_sync(0xffffffffu, sd[0], 1);
+    rad[NS_PER] = __shfl_down_sync(0xffffffffu, rad[0], 1);
+    // cos_val per interval i (valid for i < S-1)
+    float cosv[NS_PER];
+#pragma unroll
+    for (int j = 0; j < NS_PER; ++j) cosv[j] = (sd[j + 1] - sd[j]) / (z[j + 1] - z[j] + 1e-5f);
+    float prev_last = __shfl_up_sync(0xffffffffu, cosv[NS_PER - 1], 1);
+    if (lane == 0) prev_last = 0.f;                     // prev_cos_val[:,0] = 0
+    float om[NS_PER], alpha[NS_PER];
+#pragma unroll
+    for (int j = 0; j < NS_PER; ++j) {
+      int i = NS_PER * lane + j;
+      float pc = j == 0 ? prev_last : cosv[j - 1];
+      float c = fminf(pc, cosv[j]);
+      c = fminf(fmaxf(c, -1e3f), 0.f);
+      bool inside = (rad[j] < r_limit) || (rad[j + 1] < r_limit);
+      c = inside ? c : 0.f;
+      float mid = (sd[j] + sd[j + 1]) * 0.5f;
+      float dist = z[j + 1] - z[j];
+      float pe = mid - c * dist * 0.5f, ne = mid + c * dist * 0.5f;
+      float pcdf = sigmoidf_(pe * inv_s), ncdf = sigmoidf_(ne * inv_s);
+      float a = (pcdf - ncdf + 1e-5f) / (pcdf + 1e-5f);
+      bool valid = i < S - 1;
+      alpha[j] = valid ? a : 0.f;
+      om[j] = valid ? (1.f - a + 1e-7f) : 1.f;
+    }
+    warp_excl_cumprod4(om, lane);                        // transmittance
+    float w[NS_PER];
+    float wsum = 0.f;
+#pragma unroll
+    for (int j = 0; j < NS_PER; ++j) {
+      int i = NS_PER * lane + j;
+      w[j] = i < S - 1 ? alpha[j] * om[j] + 1e-5f : 0.f;  // sample_pdf: weights + 1e-5
+      wsum += w[j];
+    }
+    wsum = warp_sum(wsum);
+#pragma unroll
+    for (int j = 0; j < NS_PER; ++j) w[j] = w[j] / wsum;  // pdf
+    warp_incl_cumsum4(w, lane);                          // cdf[1..S-1]
+    __syncwarp();
+    if (lane == 0) s_cdf[wib][0] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NS_PER; ++j) {
+      int i = NS_PER * lane + j;
+      if (i < S - 1) s_cdf[wib][i + 1] = w[j];
+      if (i < S) s_z[wib][i] = z[j];
+    }
+    __syncwarp();
+    // inverse CDF at u = linspace(0.5/n, 1-0.5/n, n)
+    for (int q = lane; q < n_imp; q += 32) {
+      float lo = 0.5f / n_imp, hi = 1.0f - 0.5f / n_imp;
+      float u = n_imp > 1 ? lo + (hi - lo) * ((float)q / (float)(n_imp - 1)) : lo;
+      if (q == n_imp - 1 && n_imp > 1) u = hi;
+      // searchsorted(cdf, u, right=True): first idx with cdf[idx] > u, in [0, S]
+      int a0 = 0, b0 = S;
+      while (a0 < b0) { int m = (a0 + b0) >> 1; if (s_cdf[wib][m] > u) b0 = m; else a0 = m + 1; }
+      int below = max(0, a0 - 1), above = min(S - 1, a0);
+      float cb = s_cdf[wib][below], ca = s_cdf[wib][above];
+      float bb = s_z[wib][below], ba = s_z[wib][above];
+      float den = ca - cb;
+      if (den < 1e-5f) den = 1.f;
+      float t = (u - cb) / den;
+      z_samples[ray * n_imp + q] = bb + t * (ba - bb);
+    }
+    __syncwarp();
+  }
+}
+
+extern "C" int vqn_neus_up_sample(vqn_ctx* ctx, const float* rays_o, const float* rays_d, const float* z_vals,
+                                  const float* sdf, int64_t n_rays, int n_samples, float r_limit, int n_importance,
+                                  float inv_s, float* z_samples, vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && rays_o && rays_d && z_vals && sdf && z_samples, "up_sample: null");
+  VQN_CHECK_ARG(n_samples >= 2 && n_samples <= NS_MAXS, "up_sample: 2 <= n_samples <= 128");
+  VQN_CHECK_ARG(n_importance >= 1 && n_rays >= 0, "up_sample: n_importance >= 1");
+  if (n_rays == 0) return VQN_OK;
+  long long want = (n_rays + 7) / 8;
+  int blocks = (int)(want < (long long)ctx->sm_count * 8 ? want : (long long)ctx->sm_count * 8);
+  neus_up_sample_kernel<<<blocks, 256, 0, vqn_cs(stream)>>>(rays_o, rays_d, z_vals, sdf, n_rays, n_samples,
+                                                            r_limit, n_importance, inv_s, z_samples);
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cat_z_vals: stable rank sort of [z_vals ; new_z] carrying sdf
+// ---------------------------------------------------------------------------------------------
+__global__ void neus_cat_kernel(const float* __restrict__ z_vals, const float* __restrict__ new_z,
+                                const float* __restrict__ sdf, const float* __restrict__ new_sdf, long long n_rays,
+                                int S, int I, float* __restrict__ z_out, float* __restrict__ sdf_out) {
+  __shared__ float s_z[8][2 * NS_MAXS];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int T = S + I;
+  long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long ray = warp; ray < n_rays; ray += nw) {
+    for (int i = lane; i < T; i += 32) s_z[wib][i] = i < S ? z_vals[ray * S + i] : new_z[ray * I + (i - S)];
+    __syncwarp();
+    for (int i = lane; i < T; i += 32) {
+      float v = s_z[wib][i];
+      int rank = 0;
+      for (int k = 0; k < T; ++k) {
+        float u = s_z[wib][k];
+        rank += (u < v) || (u == v && k < i);
+      }
+      z_out[ray * T + rank] = v;
+      if (sdf_out) {
+        float sv = i < S ? sdf[ray * S + i] : (new_sdf ? new_sdf[ray * I + (i - S)] : 0.f);
+        sdf_out[ray * T + rank] = sv;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+extern "C" int vqn_neus_cat_z_vals(vqn_ctx* ctx, const float* z_vals, const float* new_z, const float* sdf,
+                                   const float* new_sdf, int64_t n_rays, int n_samples, int n_importance,
+                                   float* z_out, float* sdf_out, vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && z_vals && new_z && z_out, "cat_z_vals: null");
+  VQN_CHECK_ARG(n_samples >= 1 && n_importance >= 1 && n_samples + n_importance <= 2 * NS_MAXS,
+                "cat_z_vals: n_samples + n_importance <= 256");
+  VQN_CHECK_ARG(!sdf_out || sdf, "cat_z_vals: sdf_out needs sdf");
+  if (n_rays == 0) return VQN_OK;
+  long long want = (n_rays + 7) / 8;
+  int blocks = (int)(want < (long long)ctx->sm_count * 8 ? want : (long long)ctx->sm_count * 8);
+  neus_cat_kernel<<<blocks, 256, 0, vqn_cs(stream)>>>(z_vals, new_z, sdf, new_sdf, n_rays, n_samples,
+                                                      n_importance, z_out, sdf_out);
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mid-point sample positions for the SDF / colour networks
+// ---------------------------------------------------------------------------------------------
+__global__ void neus_mid_points_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                       const float* __restrict__ z_vals, long long n_rays, int S, float sample_dist,
+                                       float* __restrict__ pts, float* __restrict__ dirs) {
+  long long total = n_rays * S;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long ray = idx / S;
+    int i = (int)(idx - ray * S);
+    float z = z_vals[idx];
+    float dist = i + 1 < S ? z_vals[idx + 1] - z : sample_dist;
+    float mz = z + dist * 0.5f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float d = rays_d[ray * 3 + c];
+      pts[idx * 3 + c] = rays_o[ray * 3 + c] + d * mz;
+      if (dirs) dirs[idx * 3 + c] = d;
+    }
+  }
+}
+
+extern "C" int vqn_neus_mid_points(vqn_ctx* ctx, const float* rays_o, const float* rays_d, const float* z_vals,
+                                   int64_t n_rays, int n_samples, float sample_dist, float* pts, float* dirs,
+                                   vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && rays_o && rays_d && z_vals && pts && n_samples >= 1 && n_rays >= 0, "mid_points args");
+  if (n_rays == 0) return VQN_OK;
+  long long want = (n_rays * n_samples + 255) / 256;
+  int blocks = (int)(want < (long long)ctx->sm_count * 8 ? want : (long long)ctx->sm_count * 8);
+  neus_mid_points_kernel<<<blocks, 256, 0, vqn_cs(stream)>>>(rays_o, rays_d, z_vals, n_rays, n_samples, sample_dist,
+                                                             pts, dirs);
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// render_core compositing
+// ---------------------------------------------------------------------------------------------
+__global__ void neus_composite_kernel(vqn_neus_composite_args a) {
+  const int lane = threadIdx.x & 31;
+  const int S = a.n_samples;
+  long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  double ge_num = 0.0, ge_den = 0.0;
+  for (long long ray = warp; ray < a.n_rays; ray += nw) {
+    const float ox = a.rays_o[ray * 3], oy = a.rays_o[ray * 3 + 1], oz = a.rays_o[ray * 3 + 2];
+    const float dx = a.rays_d[ray * 3], dy = a.rays_d[ray * 3 + 1], dz = a.rays_d[ray * 3 + 2];
+    float z[NS_PER];
+#pragma unroll
+    for (int j = 0; j < NS_PER; ++j) { int i = NS_PER * lane + j; z[j] = i < S ? a.z_vals[ray * S + i] : 0.f; }
+    float znext0 = __shfl_down_sync(0xffffffffu, z[0], 1);
+    float alpha[NS_PER], om[NS_PER], px[NS_PER], py[NS_PER], pz[NS_PER];
+#pragma unroll
+    for (int j = 0; j < NS_PER; ++j) {
+      const int i = NS_PER * lane + j;
+      const bool valid = i < S;
+      const long long si = ray * S + (valid ? i : 0);
+      float zn = j + 1 < NS_PER ? z[j + 1] : znext0;
+      float dist = (i + 1 < S) ? zn - z[j] : a.sample_dist;          // :203-204
+      float mz = z[j] + dist * 0.5f;
+      px[j] = ox + dx * mz; py[j] = oy + dy * mz; pz[j] = oz + dz * mz;
+      float sdfv = a.sdf[si];
+      float gx = a.gradients[si * 3], gy = a.gradients[si * 3 + 1], gz = a.gradients[si * 3 + 2];
+      float true_cos = dx * gx + dy * gy + dz * gz;
+      float iter_cos = -(fmaxf(-true_cos * 0.5f + 0.5f, 0.f) * (1.0f - a.cos_anneal_ratio) +
+                         fmaxf(-true_cos, 0.f) * a.cos_anneal_ratio);  // :235-236
+      float en = sdfv + iter_cos * dist * 0.5f, ep = sdfv - iter_cos * dist * 0.5f;
+      float pcdf = sigmoidf_(ep * a.inv_s), ncdf = sigmoidf_(en * a.inv_s);
+      float al = (pcdf - ncdf + 1e-5f) / (pcdf + 1e-5f);
+      al = fminf(fmaxf(al, 0.f), 1.f);
+      alpha[j] = valid ? al : 0.f;
+      om[j] = valid ? 1.f - al + 1e-7f : 1.f;
+      float radius = sqrtf(px[j] * px[j] + py[j] * py[j] + pz[j] * pz[j]);
+      if (valid) {
+        if (a.cdf) a.cdf[si] = pcdf;
+        if (a.inside_sphere) a.inside_sphere[si] = radius < a.radius ? 1.f : 0.f;
+        if (a.mid_z_vals) a.mid_z_vals[si] = mz;
+        if (a.dists) a.dists[si] = dist;
+        if (a.grad_err_sums) {
+          float relax = radius < a.radius * 1.1f ? 1.f : 0.f;
+          float gn = sqrtf(gx * gx + gy * gy + gz * gz) - 1.0f;
+          ge_num += (double)(relax * gn * gn);
+          ge_den += (double)relax;
+        }
+      }
+    }
+    warp_excl_cumprod4(om, lane);
+    float wsum = 0.f, wmax = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NS_PER; ++j) {
+      const int i = NS_PER * lane + j;
+      if (i < S) {
+        const long long si = ray * S + i;
+        float w = alpha[j] * om[j];
+        if (a.weights) a.weights[si] = w;
+        wsum += w; wmax = fmaxf(wmax, w);
+        c0 = fmaf(a.sampled_color[si * 3], w, c0);
+        c1 = fmaf(a.sampled_color[si * 3 + 1], w, c1);
+        c2 = fmaf(a.sampled_color[si * 3 + 2], w, c2);
+        s0 = fmaf(px[j], w, s0); s1 = fmaf(py[j], w, s1); s2 = fmaf(pz[j], w, s2);
+      }
+    }
+    wsum = warp_sum(wsum);
+    c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2);
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if (lane == 0) {
+      if (a.background_rgb) {
+        c0 += a.background_rgb[0] * (1.f - wsum); c1 += a.background_rgb[1] * (1.f - wsum);
+        c2 += a.background_rgb[2] * (1.f - wsum);
+      }
+      if (a.color) { a.color[ray * 3] = c0; a.color[ray * 3 + 1] = c1; a.color[ray * 3 + 2] = c2; }
+      if (a.surf) { a.surf[ray * 3] = s0; a.surf[ray * 3 + 1] = s1; a.surf[ray * 3 + 2] = s2; }
+      if (a.depth) {
+        float ex = s0 - ox, ey = s1 - oy, ez = s2 - oz;
+        a.depth[ray] = sqrtf(ex * ex + ey * ey + ez * ez);
+      }
+      if (a.weight_sum) a.weight_sum[ray] = wsum;
+      if (a.weight_max) a.weight_max[ray] = wmax;
+    }
+  }
+  if (a.grad_err_sums) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ge_num += __shfl_xor_sync(0xffffffffu, ge_num, o);
+      ge_den += __shfl_xor_sync(0xffffffffu, ge_den, o);
+    }
+    if (lane == 0 && (ge_num != 0.0 || ge_den != 0.0)) {
+      atomicAdd(&a.grad_err_sums[0], ge_num);
+      atomicAdd(&a.grad_err_sums[1], ge_den);
+    }
+  }
+}
+
+extern "C" int vqn_neus_composite(vqn_ctx* ctx, const vqn_neus_composite_args* args, vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && args, "composite: null");
+  const vqn_neus_composite_args& a = *args;
+  VQN_CHECK_ARG(a.rays_o && a.rays_d && a.z_vals && a.sdf && a.gradients && a.sampled_color, "composite: null input");
+  VQN_CHECK_ARG(a.n_samples >= 1 && a.n_samples <= NS_MAXS && a.n_rays >= 0, "composite: 1 <= n_samples <= 128");
+  if (a.n_rays == 0) return VQN_OK;
+  long long want = (a.n_rays + 7) / 8;
+  int blocks = (int)(want < (long long)ctx->sm_count * 8 ? want : (long long)ctx->sm_count * 8);
+  neus_composite_kernel<<<blocks, 256, 0, vqn_cs(stream)>>>(a);
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}

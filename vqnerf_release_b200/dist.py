@@ -1,0 +1,85 @@
+"""Multi-GPU plumbing for the shading path: one process per GPU, torch.distributed (NCCL over NVLink on
+the GPU box, gloo in the CPU tests).
+
+The path shards by surface point: every point is independent given replicated weights,
+codebook and probes, so rendering needs exactly ONE collective -- a gather of the per-pixel outputs --
+and a training step needs exactly one all-reduce of [gradients | VQ EMA statistics].  Nothing else crosses
+GPUs.  The reference's only collective call site is tf.distribute.MirroredStrategy
+(decomp/nerfvq_nfr3/nerfactor/trainvali.py:436-446,471,520); its geo stage shards views across independent
+processes (geo/NeuS-ours2/gen_geo.py:141-146).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_rows(n_total: int, rank: int, world_size: int, align: int = 1) -> Tuple[int, int]:
+    """Contiguous pixel-row block [start, stop) of rank `rank` (keeps lvis reads contiguous).  Blocks differ
+    by at most `align` rows; `align` = 2 keeps the (pixel, neighbour) pairs of a training batch
+    (train_nfr.py:447-448, vq_nfr.py:945-954) on one GPU."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError('bad rank/world_size')
+    units = (n_total + align - 1) // align
+    base, rem = divmod(units, world_size)
+    start_u = rank * base + min(rank, rem)
+    stop_u = start_u + base + (1 if rank < rem else 0)
+    return min(start_u * align, n_total), min(stop_u * align, n_total)
+
+
+def shard_sizes(n_total: int, world_size: int, align: int = 1) -> List[int]:
+    return [b - a for a, b in (shard_rows(n_total, r, world_size, align) for r in range(world_size))]
+
+
+def gather_rows(local: torch.Tensor, n_total: int, group=None, align: int = 1,
+                dst: Optional[int] = None) -> Optional[torch.Tensor]:
+    """The single collective of a pixel-sharded render: concatenates every rank's [n_r, ...] block in rank
+    order into [n_total, ...].  dst=None -> all ranks get the image (all_gather); dst=r -> only rank r."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = shard_sizes(n_total, world, align)
+    if local.shape[0] != sizes[rank]:
+        raise ValueError('rank %d holds %d rows, expected %d' % (rank, local.shape[0], sizes[rank]))
+    tail = tuple(local.shape[1:])
+    if len(set(sizes)) == 1:
+        out = torch.empty((n_total,) + tail, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out if (dst is None or dst == rank) else None
+    # ragged blocks: pad to the largest block, one all_gather, then trim
+    mx = max(sizes)
+    padded = torch.zeros((mx,) + tail, dtype=local.dtype, device=local.device)
+    padded[:local.shape[0]] = local
+    buf = torch.empty((world * mx,) + tail, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(buf, padded, group=group)
+    if dst is not None and dst != rank:
+        return None
+    return torch.cat([buf[r * mx:r * mx + sizes[r]] for r in range(world)], dim=0)
+
+
+def allreduce_flat_(tensors: List[torch.Tensor], group=None) -> None:
+    """ONE all-reduce(sum) for a training step: packs [MLP grads | light grad | codebook grad | VQ counts | dw |
+    e_latent partial sums] into a flat buffer per dtype, reduces, and scatters back in place."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    by_dtype = {}
+    for t in tensors:
+        by_dtype.setdefault(t.dtype, []).append(t)
+    for dt, ts in by_dtype.items():
+        flat = torch.cat([t.reshape(-1) for t in ts])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        off = 0
+        for t in ts:
+            t.copy_(flat[off:off + t.numel()].reshape(t.shape))
+            off += t.numel()
+
+
+def make_stats_allreduce(group=None):
+    """Hook for VectorQuantizerEMA.stats_allreduce: global-batch one-hot counts / dw / e_latent sums so that the
+    EMA, the `used` mask and the commitment mean equal the single-device global batch."""
+    def hook(stats: torch.Tensor) -> None:
+        allreduce_flat_([stats], group=group)
+    return hook

@@ -1,0 +1,112 @@
+"""Mirror of geo/NeuS-ours2/models/renderer.py::NeuSRenderer (secondary path, n_outside == 0).
+
+The per-ray work -- up_sample (+sample_pdf det=True), the sort/merge of cat_z_vals and the SDF-to-alpha
+compositing of render_core -- runs in the warp-per-ray kernels of csrc/neus.cu.  The SDF / colour /
+variance networks stay caller-supplied callables (torch modules), exactly as the reference passes them in.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import abi
+
+
+class NeuSRenderer:
+    def __init__(self, nerf, sdf_network, deviation_network, color_network, n_samples, n_importance, n_outside,
+                 up_sample_steps, perturb):
+        if n_outside != 0:
+            raise NotImplementedError('n_outside > 0 (render_core_outside) is not on the path: every shipped conf '
+                                      'uses n_outside = 0 (confs/nerf.conf:85)')
+        self.nerf = nerf
+        self.sdf_network = sdf_network
+        self.deviation_network = deviation_network
+        self.color_network = color_network
+        self.n_samples = n_samples
+        self.n_importance = n_importance
+        self.n_outside = n_outside
+        self.up_sample_steps = up_sample_steps
+        self.perturb = perturb
+
+    # renderer.py:131-175
+    def up_sample(self, rays_o, rays_d, z_vals, sdf, r_limit, n_importance, inv_s):
+        return abi.neus_up_sample(rays_o, rays_d, z_vals, sdf, r_limit, n_importance, inv_s)
+
+    # renderer.py:177-191
+    def cat_z_vals(self, rays_o, rays_d, z_vals, new_z_vals, sdf, last=False):
+        batch_size, n_samples = z_vals.shape
+        _, n_importance = new_z_vals.shape
+        if last:
+            z_out, _ = abi.neus_cat_z_vals(z_vals, new_z_vals)
+            return z_out, sdf
+        pts = rays_o[:, None, :] + rays_d[:, None, :] * new_z_vals[..., :, None]
+        new_sdf = self.sdf_network.sdf(pts.reshape(-1, 3)).reshape(batch_size, n_importance)
+        return abi.neus_cat_z_vals(z_vals, new_z_vals, sdf.reshape(batch_size, n_samples), new_sdf)
+
+    # renderer.py:193-297
+    def render_core(self, rays_o, rays_d, z_vals, sample_dist, radius, sdf_network, deviation_network,
+                    color_network, background_alpha=None, background_sampled_color=None, background_rgb=None,
+                    cos_anneal_ratio=0.0, to_light=False):
+        if background_alpha is not None or to_light:
+            raise NotImplementedError('background model / to_light marching are outside the path (n_outside = 0)')
+        batch_size, n_samples = z_vals.shape
+        pts, dirs = abi.neus_mid_points(rays_o, rays_d, z_vals, float(sample_dist))
+        pts = pts.reshape(-1, 3)
+        dirs = dirs.reshape(-1, 3)
+        sdf_nn_output = sdf_network(pts)
+        sdf = sdf_nn_output[:, :1]
+        feature_vector = sdf_nn_output[:, 1:]
+        gradients = sdf_network.gradient(pts).squeeze()
+        sampled_color = color_network(pts, gradients, dirs, feature_vector).reshape(batch_size, n_samples, 3)
+        inv_s = deviation_network(torch.zeros([1, 3], device=pts.device))[:, :1].clip(1e-6, 1e6)
+        o = abi.neus_composite(rays_o, rays_d, z_vals, sdf.detach(), gradients.detach(), sampled_color.detach(),
+                               float(inv_s.reshape(-1)[0]), cos_anneal_ratio, float(sample_dist), float(radius),
+                               background_rgb)
+        ge = o['grad_err_sums']
+        gradient_error = (ge[0] / (ge[1] + 1e-5)).to(torch.float32)
+        return {
+            'color': o['color'], 'sdf': sdf, 'dists': o['dists'],
+            'gradients': gradients.reshape(batch_size, n_samples, 3),
+            's_val': 1.0 / inv_s.expand(batch_size * n_samples, 1), 'mid_z_vals': o['mid_z_vals'],
+            'weights': o['weights'], 'cdf': o['cdf'], 'gradient_error': gradient_error,
+            'inside_sphere': o['inside_sphere'], 'surf': o['surf'], 'depth': o['depth'],
+            'weight_sum': o['weight_sum'], 'weight_max': o['weight_max'],
+        }
+
+    # renderer.py:299-401
+    def render(self, rays_o, rays_d, near, far, radius, perturb_overwrite=-1, background_rgb=None,
+               cos_anneal_ratio=0.0, to_light=False):
+        if to_light:
+            raise NotImplementedError('to_light marching (gen_geo.compute_vis) is a "next" row (SURVEY 8f N1)')
+        batch_size = len(rays_o)
+        dev = rays_o.device
+        sample_dist = 2 * radius / self.n_samples
+        z_vals = torch.linspace(0.0, 1.0, self.n_samples, device=dev)
+        z_vals = (near + (far - near) * z_vals[None, :]).expand(batch_size, self.n_samples).contiguous()
+        n_samples = self.n_samples
+        perturb = self.perturb
+        if perturb_overwrite >= 0:
+            perturb = perturb_overwrite
+        if perturb > 0:
+            t_rand = torch.rand([batch_size, 1], device=dev) - 0.5
+            z_vals = z_vals + t_rand * 2. * radius / self.n_samples
+        if self.n_importance > 0:
+            with torch.no_grad():
+                pts = rays_o[:, None, :] + rays_d[:, None, :] * z_vals[..., :, None]
+                sdf = self.sdf_network.sdf(pts.reshape(-1, 3)).reshape(batch_size, self.n_samples)
+                for i in range(self.up_sample_steps):
+                    new_z_vals = self.up_sample(rays_o, rays_d, z_vals, sdf, radius,
+                                                self.n_importance // self.up_sample_steps, 64 * 2 ** i)
+                    z_vals, sdf = self.cat_z_vals(rays_o, rays_d, z_vals, new_z_vals, sdf,
+                                                  last=(i + 1 == self.up_sample_steps))
+            n_samples = self.n_samples + self.n_importance
+        ret_fine = self.render_core(rays_o, rays_d, z_vals, sample_dist, radius, self.sdf_network,
+                                    self.deviation_network, self.color_network, background_rgb=background_rgb,
+                                    cos_anneal_ratio=cos_anneal_ratio)
+        s_val = ret_fine['s_val'].reshape(batch_size, n_samples).mean(dim=-1, keepdim=True)
+        return {
+            'color_fine': ret_fine['color'], 's_val': s_val, 'cdf_fine': ret_fine['cdf'],
+            'weight_sum': ret_fine['weight_sum'], 'weight_max': ret_fine['weight_max'],
+            'gradients': ret_fine['gradients'], 'weights': ret_fine['weights'],
+            'gradient_error': ret_fine['gradient_error'], 'inside_sphere': ret_fine['inside_sphere'],
+            'surf': ret_fine['surf'], 'depth': ret_fine['depth'],
+        }
