@@ -36,7 +36,8 @@ N_POINTS = H * W
 MLP_ENC_FLOP = 2 * 179968
 MLP_HEADS_FLOP = 2 * 296832
 SHADE_FLOP_PER_LIGHT = 110.0
-CPU_SAMPLE_POINTS = 4096
+CPU_SAMPLE_POINTS = 4096      # chunk size of the CPU restatement (config #1 size; bounds the [N,512,3] intermediates)
+CPU_BUDGET_S = 12.0           # keep adding chunks until this much CPU time has been spent
 
 
 def parse():
@@ -133,44 +134,48 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_baseline(probes, sample=CPU_SAMPLE_POINTS, steps=1):
+def cpu_baseline(probes, chunk=CPU_SAMPLE_POINTS, budget_s=CPU_BUDGET_S):
     """The reference's CPU path: the op-for-op PyTorch-CPU restatement (incl. the [N,512,3] intermediates) on all
-    host cores, on a bounded sample of the same workload."""
+    host cores, on a bounded sample of the same workload: chunks of `chunk` points of the 800x800 view are shaded
+    one after the other (the reference's own brdf_chunk loop, vq_nfr.py:841-874) until `budget_s` is spent."""
     import torch
     from oracle import decomp_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     scene = O.synth_scene(0, n_probes=probes)
-    batch = O.synth_batch(sample, 0)
     O.fast_render(scene, O.synth_batch(256, 1), torch.float32, relight_probes=probes > 0)   # warm-up
-    times = []
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        O.fast_render(scene, batch, torch.float32, relight_probes=probes > 0)
-        times.append(time.perf_counter() - t0)
-    dt = float(np.mean(times))
-    return {'value': sample / dt, 'unit': 'points/s', 'cores': cores, 'kind': 'port',
-            'sample': '%d of %d points of the 800x800 view, %d relight probes, fp32 torch-CPU restatement of '
-                      'vq_nfr.fast_render incl. [N,512,3] intermediates; %.2f s per pass' % (sample, N_POINTS, probes, dt)}, dt
+    batches = [O.synth_batch(chunk, s) for s in range(4)]
+    done, t0 = 0, time.perf_counter()
+    while True:
+        O.fast_render(scene, batches[(done // chunk) % 4], torch.float32, relight_probes=probes > 0)
+        done += chunk
+        dt = time.perf_counter() - t0
+        if dt >= budget_s or done >= N_POINTS:
+            break
+    return {'value': done / dt, 'unit': 'points/s', 'cores': cores, 'kind': 'port',
+            'sample': '%d of %d points of the 800x800 view in chunks of %d, %d relight probes, fp32 torch-CPU '
+                      'restatement of vq_nfr.fast_render incl. [N,512,3] intermediates; %.1f s of CPU time'
+                      % (done, N_POINTS, chunk, probes, dt)}, dt, done
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cb, _ = cpu_baseline(args.probes, CPU_SAMPLE_POINTS, steps=1)      # warm-up pass (untimed result discarded)
-    times = []
-    for _ in range(max(1, min(args.steps, 3))):
-        r, dt = cpu_baseline(args.probes, CPU_SAMPLE_POINTS, steps=1)
-        times.append(dt)
-    dt = float(np.mean(times))
-    val = CPU_SAMPLE_POINTS / dt
+    cpu_baseline(args.probes, budget_s=0.5)                 # warm-up step (untimed)
+    steps = max(1, min(args.steps, 3))
+    vals, dts, pts = [], [], 0
+    for _ in range(steps):
+        cb, dt, done = cpu_baseline(args.probes, budget_s=CPU_BUDGET_S / steps * 2)
+        vals.append(cb['value']); dts.append(dt); pts = done
+    val = float(np.mean(vals))
     cb['value'] = val
     line = {'metric': 'shaded surface points/sec', 'value': val, 'unit': 'points/s', 'n_gpus': args.gpus,
-            'steps': len(times), 'warmup': 1, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
-            'config': {'workload': 'vq_nfr.fast_render relight, %d-point sample of an 800x800 view, 512 lights, '
-                                   'P=%d probes, CPU restatement of the reference' % (CPU_SAMPLE_POINTS, args.probes)},
+            'steps': steps, 'warmup': 1, 'ms_per_step': float(np.mean(dts)) * 1e3, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
+            'config': {'workload': 'vq_nfr.fast_render full-image relight (800x800 view, 512 lights, P=%d probes): '
+                                   'bounded sample of %d points per step, CPU restatement of the reference'
+                                   % (args.probes, pts)},
             'cpu_baseline': cb,
             'e2e': {'value': val, 'unit': 'points/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
@@ -296,13 +301,14 @@ def run_ours(args):
         fp32_peak = float(tf.value)
         tf2 = C.c_double()
         _lib.check(ctx.lib.vqn_microbench_fma(ctx.handle, 1, 2000, C.byref(tf2)))
-        heads_ms = stage_ms.get('mlp_heads', float('nan'))
-        enc_ms = stage_ms.get('mlp_enc', float('nan'))
+        mlp_ms = stage_ms.get('mlp_main', float('nan'))
         shade_ms = stage_ms.get('shade', float('nan'))
+        MLP_FLOP = MLP_ENC_FLOP + MLP_HEADS_FLOP
         if args.precision == 'fp32':
             # dominant kernel: mlp_simt_kernel (heads launch); FFMA-bound, so the roofline is the fp32-FMA peak
-            ach = MLP_HEADS_FLOP * n / (heads_ms * 1e-3) / 1e12
-            roof = {'bound': 'fp32_fma', 'kernel': 'mlp_simt_kernel (3 main heads, %d points/launch)' % n,
+            ach = MLP_FLOP * n / (mlp_ms * 1e-3) / 1e12
+            roof = {'bound': 'fp32_fma', 'kernel': 'mlp_simt_kernel (encoder + 3 main heads fused, %d points/launch, '
+                                                   '953 600 FLOP/point)' % n,
                     'achieved': ach, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': ach / fp32_peak,
                     'peak_source': 'FFMA peak measured live by vqn_microbench_fma on this GPU '
                                    '(FFMA2 packed: %.1f TFLOP/s); tensor peak for reference: %.0f bf16 TFLOP/s %s'
@@ -310,21 +316,20 @@ def run_ours(args):
                     'traffic': None}
         else:
             peak = bf16_peak if args.precision == 'bf16' else bf16_peak / 2 / 3
-            ach = MLP_HEADS_FLOP * n / (heads_ms * 1e-3) / 1e12
-            roof = {'bound': 'tensor', 'kernel': 'mlp_tc_kernel (3 main heads)', 'achieved': ach, 'peak': peak,
+            ach = MLP_FLOP * n / (mlp_ms * 1e-3) / 1e12
+            roof = {'bound': 'tensor', 'kernel': 'mlp_tc_kernel (encoder + 3 main heads)', 'achieved': ach, 'peak': peak,
                     'unit': 'TFLOP/s', 'frac': ach / peak, 'peak_source': peak_src, 'traffic': None}
         shade_bytes = n * (2048 + 36 + 28 + 12 * (1 + P))
         kernels = {
-            'mlp_enc': {'ms': enc_ms, 'tflops': MLP_ENC_FLOP * n / (enc_ms * 1e-3) / 1e12},
-            'mlp_heads': {'ms': heads_ms, 'tflops': MLP_HEADS_FLOP * n / (heads_ms * 1e-3) / 1e12},
+            'mlp_main': {'ms': mlp_ms, 'tflops': MLP_FLOP * n / (mlp_ms * 1e-3) / 1e12},
             'shade': {'ms': shade_ms, 'gbs': shade_bytes / (shade_ms * 1e-3) / 1e9,
                       'tflops': n * 512 * (SHADE_FLOP_PER_LIGHT + 6 * (1 + P)) / (shade_ms * 1e-3) / 1e12,
                       'hbm_frac': shade_bytes / (shade_ms * 1e-3) / 1e9 / hbm_peak},
-            'other_ms': {k: v for k, v in stage_ms.items() if k not in ('mlp_enc', 'mlp_heads', 'shade')},
+            'other_ms': {k: v for k, v in stage_ms.items() if k not in ('mlp_main', 'shade')},
         }
         cb = None
         if not args.no_cpu_baseline:
-            cb, _ = cpu_baseline(P)
+            cb, _, _ = cpu_baseline(P)
         line = {
             'metric': 'shaded surface points/sec', 'value': value, 'unit': 'points/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True,

@@ -116,6 +116,13 @@ int vqn_pred_heads(vqn_ctx* ctx, vqn_net* diff, vqn_net* spec, vqn_net* rough, c
                    float* spec_out /*[n,out_dim(spec)]*/, float* rough_out /*[n,1]*/, int precision,
                    vqn_stream stream);
 
+/* _pred_enc_at + _pred_diff_at + _pred_spec_at + _pred_rough_at of the main branch in one launch, as
+ * fast_render chains them (models/vq_nfr.py:321,329-331): the latent stays on chip; z_out [n,256] is optional. */
+int vqn_mlp_main(vqn_ctx* ctx, vqn_net* fine_enc, vqn_net* bottleneck, vqn_net* diff, vqn_net* spec, vqn_net* rough,
+                 int n_freqs, const float* pts, const int32_t* row_idx, const int32_t* n_dev, int64_t n,
+                 float albedo_slope, float albedo_bias, float* z_out, float* diff_out, float* spec_out,
+                 float* rough_out, int precision, vqn_stream stream);
+
 /* ---- vector quantiser ------------------------------------------------------------------------ */
 /* Model.get_codebook (models/vq_nfr.py:761-769): out[Z,K] = l2_normalize(clip(raw,0,1), axis=0) */
 int vqn_get_codebook(vqn_ctx* ctx, const float* raw, int z_dim, int k, float* out, vqn_stream stream);
@@ -251,6 +258,10 @@ int vqn_neus_mid_points(vqn_ctx* ctx, const float* rays_o, const float* rays_d, 
 /* ---- measurement helper (not a reference interface) -------------------------------------------- */
 /* FP32-FMA peak of this GPU in TFLOP/s (mode 0: FFMA, mode 1: packed fma.rn.f32x2); synchronises. */
 int vqn_microbench_fma(vqn_ctx* ctx, int mode, int iters, double* tflops_out);
+/* Single-tile tcgen05 GEMM self-test of the tensor-core primitives: d[128,n] = a[128,k] . b[n,k]^T.
+ * mode 0: kind::tf32 (inputs truncated to tf32), 1: kind::f16 bf16 operands, 2: 3xTF32 split (fp32 parity). */
+int vqn_tc_selftest(vqn_ctx* ctx, int mode, int n, int k, const float* a, const float* b, float* d,
+                    vqn_stream stream);
 
 #ifdef __cplusplus
 }

@@ -162,7 +162,8 @@ def test_vq_layer_training_matches_oracle(cuda_dev):
         _close(r['encodings'].sum(0), o['encodings'].sum(0), 'one-hot counts', rtol=0, atol=0)
         cbt, cbo = r['update'].contiguous(), o['update']
     assert layer.state['counters'].tolist() == [3, 3]
-    _close(layer.state['cs_hidden'], ovq.ema_cluster_size.hidden, 'cs_hidden', rtol=1e-5)
+    # fp32 EMA recursion h -= (h - v)(1 - decay) with v ~ 200 rows/code: ~1e-5 relative after three steps
+    _close(layer.state['cs_hidden'], ovq.ema_cluster_size.hidden, 'cs_hidden', rtol=5e-5)
     _close(layer.state['dw_average'], ovq.ema_dw.average, 'dw_average', rtol=2e-5, atol=1e-6)
     r = layer(torch.as_tensor(x).to(cuda_dev), cbt, False)
     assert 'update' not in r and layer.state['counters'].tolist() == [3, 3]
@@ -204,7 +205,14 @@ def test_eval_brdf_and_render_fine_grained(cuda_dev):
     _close(gv, v, '_calc_vdir', rtol=0, atol=1e-6)
     gb = m._eval_brdf_at(gl, gv, g(nrm.numpy()), g(albedo), g(spec), g(rough))
     for got, ref, nm in zip(gb, ob, ('brdf', 'glossy', 'diffuse')):
-        _close(got, ref, nm, rtol=2e-4, atol=1e-6)
+        # The GGX lobe is ill-conditioned in fp32 near its peak (q = hn^2 (a2-1) + 1 cancels when a2 is small and
+        # h ~ n), so a handful of the 61k entries carry the fp32 evaluation error of the REFERENCE formula itself:
+        # 1e-4 everywhere except <= 0.05 % of entries, which must still be within 1e-3.
+        ga, rb = got.cpu().double().numpy(), ref.numpy()
+        err = np.abs(ga - rb)
+        tight = err <= 1e-6 + 1e-4 * np.abs(rb)
+        assert tight.mean() >= 0.9995, '%s: %.5f within 1e-4' % (nm, tight.mean())
+        _close(got, ref, nm, rtol=1e-3, atol=1e-6)
     rgb, _, probes = m._render(gb[0], gl, g(nrm.numpy()), g(b['lvis']))
     lareas = torch.as_tensor(scene.lareas, dtype=torch.float32).to(dt)
     orgb, _ = O.render(ob[0], l, nrm, lareas, torch.clamp(torch.as_tensor(scene.light, dtype=dt), min=0),

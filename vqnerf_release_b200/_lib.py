@@ -73,6 +73,7 @@ SIGNATURES = {
     'vqn_embed': (_I, [_P, _P, _L, _I, _P, _P]),
     'vqn_pred_enc_at': (_I, [_P, _P, _P, _I, _P, _P, _P, _L, _P, _I, _P]),
     'vqn_pred_heads': (_I, [_P, _P, _P, _P, _P, _P, _L, _F, _F, _P, _P, _P, _I, _P]),
+    'vqn_mlp_main': (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _L, _F, _F, _P, _P, _P, _P, _I, _P]),
     'vqn_get_codebook': (_I, [_P, _P, _I, _I, _P, _P]),
     'vqn_l2_normalize_rows': (_I, [_P, _P, _L, _I, _P, _P]),
     'vqn_vq_assign': (_I, [_P, _P, _L, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _P]),
@@ -90,6 +91,7 @@ SIGNATURES = {
     'vqn_neus_composite': (_I, [_P, C.POINTER(NeusCompositeArgs), _P]),
     'vqn_neus_mid_points': (_I, [_P, _P, _P, _P, _L, _I, _F, _P, _P, _P]),
     'vqn_microbench_fma': (_I, [_P, _I, _I, C.POINTER(_D)]),
+    'vqn_tc_selftest': (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
 }
 
 _lib = None

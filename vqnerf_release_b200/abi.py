@@ -132,6 +132,23 @@ def pred_heads(diff: Optional[PackedNet], spec: Optional[PackedNet], rough: Opti
     return tuple(outs)
 
 
+def mlp_main(fine_enc: PackedNet, bottleneck: PackedNet, diff: PackedNet, spec: PackedNet, rough: PackedNet,
+             n_freqs: int, pts: torch.Tensor, row_idx=None, n_dev=None, n: Optional[int] = None, slope: float = 1.0,
+             bias: float = 0.0, want_z: bool = False, precision='fp32'):
+    """Fused encoder + three main heads (one launch).  Returns (z or None, basecolor, ks, rough), all compact."""
+    pts = _f(pts)
+    n = pts.shape[0] if n is None else n
+    dev = pts.device
+    z = torch.empty((n, bottleneck.out_dim), dtype=F32, device=dev) if want_z else None
+    outs = [torch.empty((n, h.out_dim), dtype=F32, device=dev) for h in (diff, spec, rough)]
+    c = _ctx(pts)
+    L.check(c.lib.vqn_mlp_main(c.handle, fine_enc.handle, bottleneck.handle, diff.handle, spec.handle, rough.handle,
+                               n_freqs, L.ptr(pts), L.ptr(row_idx, torch.int32), L.ptr(n_dev, torch.int32), n,
+                               float(slope), float(bias), L.ptr(z), *(L.ptr(o) for o in outs),
+                               L.precision_code(precision), L.stream_ptr(dev)))
+    return (z,) + tuple(outs)
+
+
 def get_codebook(raw: torch.Tensor) -> torch.Tensor:
     raw = _f(raw)
     out = torch.empty_like(raw)
@@ -393,3 +410,16 @@ def neus_composite(rays_o, rays_d, z_vals, sdf, gradients, sampled_color, inv_s,
     L.check(c.lib.vqn_neus_composite(c.handle, C.byref(a), L.stream_ptr(dev)))
     o['grad_err_sums'] = ge
     return o
+
+
+# ---- tensor-core primitive self-test ------------------------------------------------------------
+def tc_selftest(a: torch.Tensor, b: torch.Tensor, mode: int) -> torch.Tensor:
+    """d[128,n] = a[128,k] @ b[n,k]^T on tcgen05 (mode 0 tf32, 1 bf16, 2 3xTF32)."""
+    a, b = _f(a), _f(b)
+    if a.shape[0] != 128 or a.shape[1] != b.shape[1]:
+        raise ValueError('a must be [128,k], b [n,k]')
+    d = torch.empty((128, b.shape[0]), dtype=F32, device=a.device)
+    c = _ctx(a)
+    L.check(c.lib.vqn_tc_selftest(c.handle, int(mode), b.shape[0], a.shape[1], L.ptr(a), L.ptr(b), L.ptr(d),
+                                  L.stream_ptr(a.device)))
+    return d

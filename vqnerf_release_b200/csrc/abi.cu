@@ -58,6 +58,8 @@ extern "C" int vqn_ctx_create(int device, vqn_ctx** out) {
   c->launches.store(0);
   VQN_CUDA(cudaMalloc(&c->nonfinite_flag, sizeof(int)));
   VQN_CUDA(cudaMemset(c->nonfinite_flag, 0, sizeof(int)));
+  c->scratch_ints = VQN_SCRATCH_INTS;
+  VQN_CUDA(cudaMalloc(&c->scratch, sizeof(int) * c->scratch_ints));
   *out = c;
   return VQN_OK;
 }
@@ -65,6 +67,7 @@ extern "C" int vqn_ctx_create(int device, vqn_ctx** out) {
 extern "C" int vqn_ctx_destroy(vqn_ctx* ctx) {
   if (!ctx) return VQN_OK;
   cudaFree(ctx->nonfinite_flag);
+  cudaFree(ctx->scratch);
   delete ctx;
   return VQN_OK;
 }
@@ -293,18 +296,18 @@ __global__ void compact_scatter_kernel(const float* __restrict__ alpha, long lon
 
 extern "C" int vqn_compact_mask(vqn_ctx* ctx, const float* alpha, int64_t n, int32_t* row_idx,
                                 int32_t* n_active, vqn_stream s) {
-  VQN_CHECK_ARG(ctx && alpha && row_idx && n_active && n >= 0 && n < (1LL << 31), "compact_mask args");
+  VQN_CHECK_ARG(ctx && n_active && n >= 0 && n < (1LL << 31), "compact_mask args");
   int n_blocks = (int)((n + CMP_BLOCK - 1) / CMP_BLOCK);
   if (n_blocks == 0) { VQN_CUDA(cudaMemsetAsync(n_active, 0, sizeof(int), vqn_cs(s))); return VQN_OK; }
-  int* counts = nullptr;
-  VQN_CUDA(cudaMallocAsync(&counts, sizeof(int) * n_blocks, vqn_cs(s)));
+  VQN_CHECK_ARG(alpha && row_idx, "compact_mask: null alpha / row_idx");
+  VQN_CHECK_ARG((size_t)n_blocks + 16 <= ctx->scratch_ints, "compact_mask: more than 64 M rows");
+  int* counts = ctx->scratch + 16;   // persistent scratch: stream-ordered, one compaction in flight per ctx
   compact_count_kernel<<<n_blocks, CMP_BLOCK, 0, vqn_cs(s)>>>(alpha, n, counts);
   VQN_LAUNCHED(ctx);
   compact_scan_kernel<<<1, 1024, 0, vqn_cs(s)>>>(counts, n_blocks, n_active);
   VQN_LAUNCHED(ctx);
   compact_scatter_kernel<<<n_blocks, CMP_BLOCK, 0, vqn_cs(s)>>>(alpha, n, counts, row_idx);
   VQN_LAUNCHED(ctx);
-  VQN_CUDA(cudaFreeAsync(counts, vqn_cs(s)));
   return VQN_OK;
 }
 
@@ -324,8 +327,9 @@ __global__ void scatter_rows_kernel(const float* __restrict__ compact, const int
 
 extern "C" int vqn_scatter_rows(vqn_ctx* ctx, const float* compact, const int32_t* row_idx,
                                 const int32_t* n_dev, int64_t n_max, int c, float* out, vqn_stream s) {
-  VQN_CHECK_ARG(ctx && compact && row_idx && out && n_max >= 0 && c > 0, "scatter_rows args");
+  VQN_CHECK_ARG(ctx && n_max >= 0 && c > 0, "scatter_rows args");
   if (n_max == 0) return VQN_OK;
+  VQN_CHECK_ARG(compact && row_idx && out, "scatter_rows: null pointer");
   long long want = (n_max * c + 255) / 256;
   int blocks = (int)(want < (long long)ctx->sm_count * 16 ? want : (long long)ctx->sm_count * 16);
   scatter_rows_kernel<<<blocks, 256, 0, vqn_cs(s)>>>(compact, row_idx, n_dev, n_max, c, out);

@@ -14,8 +14,11 @@ struct vqn_ctx {
   int sm_count;
   int max_smem_optin;
   int* nonfinite_flag;  // device int, sticky check_numerics flag
+  int* scratch;         // small persistent device scratch (block counts of the mask compaction, VQ max distance)
+  size_t scratch_ints;
   std::atomic<long long> launches;
 };
+#define VQN_SCRATCH_INTS (1 << 16)
 
 void vqn_set_error(const char* fmt, ...);
 

@@ -552,3 +552,44 @@ extern "C" int vqn_pred_heads(vqn_ctx* ctx, vqn_net* diff, vqn_net* spec, vqn_ne
   }
   return launch_program(ctx, B.pg, vqn_cs(stream));
 }
+
+// _pred_enc_at + the three main heads in ONE launch: z stays in shared memory (Q[0,256)) between the bottleneck
+// and the heads, so the 1 KB/point latent never round-trips through HBM unless z_out is requested
+// (fast_render, models/vq_nfr.py:321-331).
+int vqn_tc_mlp_main(vqn_ctx* ctx, vqn_net* fe, vqn_net* bn, vqn_net* diff, vqn_net* spec, vqn_net* rough, int n_freqs,
+                    const float* pts, const int32_t* row_idx, const int32_t* n_dev, int64_t n, float slope, float bias,
+                    float* z_out, float* d, float* sp, float* r, int precision, cudaStream_t s);
+
+extern "C" int vqn_mlp_main(vqn_ctx* ctx, vqn_net* fine_enc, vqn_net* bottleneck, vqn_net* diff, vqn_net* spec,
+                            vqn_net* rough, int n_freqs, const float* pts, const int32_t* row_idx,
+                            const int32_t* n_dev, int64_t n, float albedo_slope, float albedo_bias, float* z_out,
+                            float* diff_out, float* spec_out, float* rough_out, int precision, vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && fine_enc && bottleneck && diff && spec && rough && pts && diff_out && spec_out && rough_out &&
+                    n >= 0, "mlp_main args");
+  VQN_CHECK_ARG(fine_enc->in_dim == 3 + 6 * n_freqs, "mlp_main: fine_enc in_dim != 3 + 6*n_freqs");
+  VQN_CHECK_ARG(bottleneck->in_dim == vqn_net_out_dim(fine_enc), "mlp_main: bottleneck in_dim mismatch");
+  if (n == 0) return VQN_OK;
+  if (precision != VQN_PREC_FP32)
+    return vqn_tc_mlp_main(ctx, fine_enc, bottleneck, diff, spec, rough, n_freqs, pts, row_idx, n_dev, n, albedo_slope,
+                           albedo_bias, z_out, diff_out, spec_out, rough_out, precision, vqn_cs(stream));
+  ProgBuilder B;
+  B.pg.input_mode = 0; B.pg.in = pts; B.pg.n_freqs = n_freqs; B.pg.in_pad = fine_enc->in_pad; B.pg.n = n;
+  B.pg.row_idx = row_idx; B.pg.n_dev = n_dev;
+  const int z_dim = vqn_net_out_dim(bottleneck);
+  B.pg.outs[3] = z_out; B.pg.out_stride[3] = z_dim;
+  bool ok = build_net_steps(B, fine_enc, -1, 1.f, 0.f) && build_net_steps(B, bottleneck, z_out ? 3 : -1, 1.f, 0.f);
+  ok = ok && B.cur_buf == 1 && B.cur_off == 0;      // z must sit in Q[0, z_dim) for the heads
+  const int first_head_step = B.pg.n_steps;
+  vqn_net* nets[3] = {diff, spec, rough};
+  float* outs[3] = {diff_out, spec_out, rough_out};
+  for (int h = 0; ok && h < 3; ++h) {
+    ok = ok && nets[h]->in_dim == z_dim;
+    B.cur_buf = 1; B.cur_off = 0;
+    B.pg.outs[h] = outs[h]; B.pg.out_stride[h] = vqn_net_out_dim(nets[h]);
+    ok = ok && build_net_steps(B, nets[h], h, h == 0 ? albedo_slope : 1.f, h == 0 ? albedo_bias : 0.f);
+  }
+  for (int s = first_head_step; ok && s < B.pg.n_steps; ++s)
+    if (B.pg.steps[s].kind == STEP_WIDE && B.pg.steps[s].out_buf == 1 && B.pg.steps[s].out_off < z_dim) ok = false;
+  if (!ok || !B.ok) { vqn_set_error("mlp_main: program does not fit the fused kernel"); return VQN_ERR_UNSUPPORTED; }
+  return launch_program(ctx, B.pg, vqn_cs(stream));
+}

@@ -21,3 +21,8 @@ int vqn_tc_pred_heads(vqn_ctx*, vqn_net*, vqn_net*, vqn_net*, const float*, cons
   vqn_set_error("tensor-core MLP modes are not built in this revision; use VQN_PREC_FP32");
   return VQN_ERR_UNSUPPORTED;
 }
+int vqn_tc_mlp_main(vqn_ctx*, vqn_net*, vqn_net*, vqn_net*, vqn_net*, vqn_net*, int, const float*, const int32_t*,
+                    const int32_t*, int64_t, float, float, float*, float*, float*, float*, int, cudaStream_t) {
+  vqn_set_error("tensor-core MLP modes are not built in this revision; use VQN_PREC_FP32");
+  return VQN_ERR_UNSUPPORTED;
+}

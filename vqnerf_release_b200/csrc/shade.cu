@@ -9,15 +9,12 @@
 //     point ahead),
 //   - light geometry and probe radiance are SoA in shared memory, read as conflict-free LDS.128 that each
 //     deliver four lights.
-// Phase 1 computes, per light, the three probe-independent weights
-//     w   = front * lvis * cos            (area is pre-multiplied into the radiance tables)
-//     sw  = S * w,  S = D G / (4 |l.n| |v.n|)   (Fresnel-free glossy scalar)
-//     psw = (1 - h.v)^5 * sw
-// and keeps them in registers (48 per lane).  Phase 2 is 9 FFMA per (light, probe):
-//     A += sw L, B += psw L, C += w L   (per channel)
-// and  rgb = f0 A + (1 - f0) B + albedo/pi C,  because F = f0 + (1 - f0)(1 - h.v)^5 is affine in f0.
-// Partial rgb sums are combined BEFORE the cross-lane reduction (linear), so only 3 values per probe are
-// shuffled.  Algorithmic HBM bytes per point: 2048 (lvis) + 36 + 28 + 12 (1 + P).
+// Phase 1 computes, per light, the probe-independent per-channel weight
+//     e_ch = (F_ch S + albedo_ch / pi) * w,   w = front * lvis * cos   (area is folded into the radiance
+//     tables), S = D G / (4 |l.n| |v.n|), F_ch = f0_ch + (1 - f0_ch)(1 - h.v)^5
+// and keeps it in registers (48 per lane).  Phase 2 is then 3 FFMA per (light, probe):
+//     rgb[p][ch] += e_ch * L[p][l][ch]
+// followed by a halving-butterfly reduction of the 3 values per probe across the warp.  Algorithmic HBM bytes per point: 2048 (lvis) + 36 + 28 + 12 (1 + P).
 #include "common.cuh"
 
 #define SH_L 512
@@ -35,15 +32,27 @@ __device__ __forceinline__ float gsub_f(float c, float a2) {
   return den == 0.f ? 0.f : 2.0f * c / den;
 }
 
-template <bool HAS_LVIS>
-__global__ void __launch_bounds__(SH_THREADS) shade_kernel(ShadeParams P) {
+// halving butterfly over lane bit `bit`: NV values -> NV/2 (see vq.cu)
+template <int NV>
+__device__ __forceinline__ void sh_halve(float* v, int lane, int bit) {
+  const bool hi = (lane >> bit) & 1;
+#pragma unroll
+  for (int i = 0; i < NV / 2; ++i) {
+    float send = hi ? v[i] : v[i + NV / 2];
+    float keep = hi ? v[i + NV / 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1 << bit);
+  }
+}
+
+template <bool HAS_LVIS, bool SPLIT>
+__global__ void __launch_bounds__(SH_THREADS, 2) shade_kernel(ShadeParams P) {
   extern __shared__ __align__(16) float sm[];
   const vqn_shade_args& a = P.a;
   const int NP = a.n_probes;
   float* lx = sm;               // [512]
   float* ly = lx + SH_L;
   float* lz = ly + SH_L;
-  float* rad = lz + SH_L;       // [NP][3][512]  radiance * area, clip(.,0,inf) applied to probe 0
+  float* rad = lz + SH_L;       // [NP][3][512]  radiance * area
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < SH_L; i += SH_THREADS) {
     lx[i] = a.lxyz[3 * i]; ly[i] = a.lxyz[3 * i + 1]; lz[i] = a.lxyz[3 * i + 2];
@@ -82,7 +91,7 @@ __global__ void __launch_bounds__(SH_THREADS) shade_kernel(ShadeParams P) {
         lvv[4 * j + 2] = lv_next[j].z; lvv[4 * j + 3] = lv_next[j].w;
       }
     }
-    // prefetch next point's visibility row
+    // prefetch the next point's visibility row (2 KB, streamed)
     long long inext = i + warps_total;
     if (inext < n) {
       row_next = a.row_idx ? (long long)a.row_idx[inext] : inext;
@@ -120,8 +129,9 @@ __global__ void __launch_bounds__(SH_THREADS) shade_kernel(ShadeParams P) {
     // S = D g_l g_v / (4 |l.n| |v.n|) = a_pt * cl / (q^2 den_l |l.n|),  a_pt = a2 g_v / (2 pi |v.n|)
     const float a_pt = avn == 0.f ? 0.f : a2 * g_v * (0.5f * INV_PI) / avn;
 
-    // ---- phase 1: per-light weights ----
-    float w[16], sw[16], psw[16];
+    // ---- phase 1: per-light, per-channel effective weights e = F S w + albedo/pi w (probe independent) ----
+    float e[16][3];
+    float wd[SPLIT ? 16 : 1];   // SPLIT: e holds the glossy lobe only and wd the diffuse weight
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int lb = 128 * j + 4 * lane;
@@ -150,24 +160,31 @@ __global__ void __launch_bounds__(SH_THREADS) shade_kernel(ShadeParams P) {
         const float cl = fminf(fmaxf(ln, 0.f), 1.f);
         const float den_l = cl + sqrtf(fabsf(a2 + (1.0f - a2) * cl * cl));
         const float den = q_ * q_ * den_l * fabsf(ln);
-        const float S = den == 0.f ? 0.f : a_pt * cl / den;
-        const bool front = cos_r > 0.f;
-        float wv = front ? cos_r : 0.f;
+        const float S = den == 0.f ? 0.f : __fdividef(a_pt * cl, den);
+        float wv = cos_r > 0.f ? cos_r : 0.f;                              // front_lit * cos
         if (HAS_LVIS) wv *= lvv[li];
-        w[li] = wv;
-        sw[li] = S * wv;
-        psw[li] = p5 * sw[li];
+        const float sw = S * wv;
+        const float psw = p5 * sw;
+        // F_ch S w = f0 sw + (1 - f0) psw = psw + f0 (sw - psw)
+        const float dsw = sw - psw;
+        if (SPLIT) {
+          e[li][0] = fmaf(f00, dsw, psw); e[li][1] = fmaf(f01, dsw, psw); e[li][2] = fmaf(f02, dsw, psw);
+          wd[SPLIT ? li : 0] = wv;
+        } else {
+          e[li][0] = fmaf(alb0, wv, fmaf(f00, dsw, psw));
+          e[li][1] = fmaf(alb1, wv, fmaf(f01, dsw, psw));
+          e[li][2] = fmaf(alb2, wv, fmaf(f02, dsw, psw));
+        }
       }
     }
 
-    // ---- phase 2: probes, SH_PC at a time ----
-    const bool want_split = (a.rgb_diff != nullptr) || (a.rgb_spec != nullptr);
+    // ---- phase 2: probes, SH_PC at a time: 3 FFMA per (light, probe) ----
     for (int p0 = 0; p0 < NP; p0 += SH_PC) {
-      float A[SH_PC][3], B[SH_PC][3], C[SH_PC][3];
+      float out[SH_PC * 3];
+      float outd[SPLIT ? 3 : 1];
 #pragma unroll
-      for (int p = 0; p < SH_PC; ++p)
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) { A[p][ch] = 0.f; B[p][ch] = 0.f; C[p][ch] = 0.f; }
+      for (int k = 0; k < SH_PC * 3; ++k) out[k] = 0.f;
+      if (SPLIT) { outd[0] = 0.f; outd[SPLIT ? 1 : 0] = 0.f; outd[SPLIT ? 2 : 0] = 0.f; }
 #pragma unroll
       for (int p = 0; p < SH_PC; ++p) {
         if (p0 + p < NP) {                       // warp-uniform
@@ -181,62 +198,77 @@ __global__ void __launch_bounds__(SH_THREADS) shade_kernel(ShadeParams P) {
               const float l4[4] = {Lq.x, Lq.y, Lq.z, Lq.w};
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                A[p][ch] = fmaf(sw[4 * j + q], l4[q], A[p][ch]);
-                B[p][ch] = fmaf(psw[4 * j + q], l4[q], B[p][ch]);
-                C[p][ch] = fmaf(w[4 * j + q], l4[q], C[p][ch]);
+                out[p * 3 + ch] = fmaf(e[4 * j + q][ch], l4[q], out[p * 3 + ch]);
+                if (SPLIT && p0 == 0 && p == 0)
+                  outd[SPLIT ? ch : 0] = fmaf(wd[SPLIT ? 4 * j + q : 0], l4[q], outd[SPLIT ? ch : 0]);
               }
             }
           }
         }
       }
-      // combine (linear) then reduce 3 values per probe across the warp
-      float out[SH_PC][3];
+      if (SPLIT) {
+        // diffuse lobe of probe 0 (mode != 'train', vq_nfr.py:605-610); every probe's total = glossy + diffuse,
+        // so the diffuse weights are applied to all probes of this chunk through a second pass over wd
+        float dsum[3] = {warp_sum(outd[0]) * alb0, warp_sum(outd[1]) * alb1, warp_sum(outd[2]) * alb2};
+        float ssum[3] = {0.f, 0.f, 0.f};
+        if (p0 == 0) {
 #pragma unroll
-      for (int p = 0; p < SH_PC; ++p) {
-        float s0 = f00 * A[p][0] + (1.f - f00) * B[p][0];
-        float s1 = f01 * A[p][1] + (1.f - f01) * B[p][1];
-        float s2 = f02 * A[p][2] + (1.f - f02) * B[p][2];
-        float d0 = alb0 * C[p][0], d1 = alb1 * C[p][1], d2 = alb2 * C[p][2];
-        if (want_split && p0 == 0 && p == 0) {   // probe 0 lobes (mode != 'train', vq_nfr.py:605-610)
-          s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
-          d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2);
+          for (int ch = 0; ch < 3; ++ch) ssum[ch] = warp_sum(out[ch]);
           if (lane == 0) {
-            float sv[3] = {s0, s1, s2}, dv[3] = {d0, d1, d2};
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-              float s_ = sv[ch], d_ = dv[ch];
+              float s_ = ssum[ch], d_ = dsum[ch];
               if (a.use_gamma) { s_ = powf(s_ * a.gamma_bias, a.gamma_index); d_ = powf(d_ * a.gamma_bias, a.gamma_index); }
-              s_ = fminf(fmaxf(s_, 0.f), 1.f); d_ = fminf(fmaxf(d_, 0.f), 1.f);
-              if (a.rgb_spec) a.rgb_spec[row * 3 + ch] = s_;
-              if (a.rgb_diff) a.rgb_diff[row * 3 + ch] = d_;
+              if (a.rgb_spec) a.rgb_spec[row * 3 + ch] = fminf(fmaxf(s_, 0.f), 1.f);
+              if (a.rgb_diff) a.rgb_diff[row * 3 + ch] = fminf(fmaxf(d_, 0.f), 1.f);
             }
           }
-          out[p][0] = s0 + d0; out[p][1] = s1 + d1; out[p][2] = s2 + d2;   // already full sums
-          // mark as reduced by zeroing on other lanes so the generic reduction below stays correct
-          if (lane != 0) { out[p][0] = 0.f; out[p][1] = 0.f; out[p][2] = 0.f; }
-        } else {
-          out[p][0] = s0 + d0; out[p][1] = s1 + d1; out[p][2] = s2 + d2;
+        }
+        // totals: add the diffuse part of every probe in this chunk
+#pragma unroll
+        for (int p = 0; p < SH_PC; ++p) {
+          if (p0 + p < NP) {
+            const float* rp = rad + (size_t)(p0 + p) * 3 * SH_L;
+            float dd[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int ch = 0; ch < 3; ++ch) {
+                const float4 Lq = *reinterpret_cast<const float4*>(rp + ch * SH_L + 128 * j + 4 * lane);
+                dd[ch] = fmaf(wd[SPLIT ? 4 * j : 0], Lq.x, dd[ch]);
+                dd[ch] = fmaf(wd[SPLIT ? 4 * j + 1 : 0], Lq.y, dd[ch]);
+                dd[ch] = fmaf(wd[SPLIT ? 4 * j + 2 : 0], Lq.z, dd[ch]);
+                dd[ch] = fmaf(wd[SPLIT ? 4 * j + 3 : 0], Lq.w, dd[ch]);
+              }
+            out[p * 3 + 0] = fmaf(alb0, dd[0], out[p * 3 + 0]);
+            out[p * 3 + 1] = fmaf(alb1, dd[1], out[p * 3 + 1]);
+            out[p * 3 + 2] = fmaf(alb2, dd[2], out[p * 3 + 2]);
+          }
         }
       }
+      // cross-lane reduction: 12 -> 6 -> 3 values by halving on lane bits 4, 3, then 3 butterfly sums over 8 lanes
+      sh_halve<12>(out, lane, 4);
+      sh_halve<6>(out, lane, 3);
 #pragma unroll
-      for (int p = 0; p < SH_PC; ++p)
+      for (int k = 0; k < 3; ++k) {
+        out[k] += __shfl_xor_sync(0xffffffffu, out[k], 4);
+        out[k] += __shfl_xor_sync(0xffffffffu, out[k], 2);
+        out[k] += __shfl_xor_sync(0xffffffffu, out[k], 1);
+      }
+      if (a.rgb && (lane & 7) == 0) {
+        const int base = 6 * ((lane >> 4) & 1) + 3 * ((lane >> 3) & 1);   // first of this lane's 3 values
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) out[p][ch] = warp_sum(out[p][ch]);
-      if (a.rgb) {
-        // lanes 0..3*SH_PC-1 each finish one (probe, channel)
-#pragma unroll
-        for (int p = 0; p < SH_PC; ++p)
-#pragma unroll
-          for (int ch = 0; ch < 3; ++ch) {
-            if (lane == p * 3 + ch && p0 + p < NP) {
-              float v = out[p][ch];
-              if (a.use_gamma) v = powf(v * a.gamma_bias, a.gamma_index);    // vq_nfr.py:715-716
-              if (!isfinite(v)) atomicOr(P.nonfinite, 2);                    // check_numerics (:731)
-              v = fminf(fmaxf(v, 0.f), 1.f);                                 // clip_by_value (:718)
-              if (a.to_srgb) v = vqn_linear2srgb(v);
-              a.rgb[(row * NP + p0 + p) * 3 + ch] = v;
-            }
+        for (int k = 0; k < 3; ++k) {
+          const int vi = base + k, p = vi / 3, ch = vi % 3;
+          if (p0 + p < NP) {
+            float v = out[k];
+            if (a.use_gamma) v = powf(v * a.gamma_bias, a.gamma_index);    // vq_nfr.py:715-716
+            if (!isfinite(v)) atomicOr(P.nonfinite, 2);                    // check_numerics (:731)
+            v = fminf(fmaxf(v, 0.f), 1.f);                                 // clip_by_value (:718)
+            if (a.to_srgb) v = vqn_linear2srgb(v);
+            a.rgb[(row * NP + p0 + p) * 3 + ch] = v;
           }
+        }
       }
     }
   }
@@ -255,7 +287,9 @@ extern "C" int vqn_shade(vqn_ctx* ctx, const vqn_shade_args* args, vqn_stream st
   P.nonfinite = ctx->nonfinite_flag;
   size_t smem = sizeof(float) * (3 * SH_L + (size_t)a.n_probes * 3 * SH_L);
   VQN_CHECK_ARG((int)smem <= ctx->max_smem_optin, "shade: probe tables exceed shared memory");
-  auto kern = a.lvis ? shade_kernel<true> : shade_kernel<false>;
+  const bool split = a.rgb_diff || a.rgb_spec;
+  auto kern = a.lvis ? (split ? shade_kernel<true, true> : shade_kernel<true, false>)
+                     : (split ? shade_kernel<false, true> : shade_kernel<false, false>);
   VQN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   VQN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SH_THREADS, smem));

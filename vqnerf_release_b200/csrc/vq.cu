@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(VQ_THREADS, 1) vq_assign_kernel(VqParams p) {
       float xsr = my_r ? xs[1] : xs[0];
       float d = xsr - 2.0f * acc[0] + cnorm[k_glob];   // +inf for padded codewords
       if (MODE == 1) {
-        if (k_glob < K) local_max = fmaxf(local_max, d);
+        if (k_glob < K && g * R + my_r < p.n) local_max = fmaxf(local_max, d);   // padded rows must not vote
         continue;
       }
       if (p.sel_mask && k_glob < K) {
@@ -336,11 +336,12 @@ extern "C" int vqn_vq_assign(vqn_ctx* ctx, const float* inputs, int64_t n, int z
                              int k, const float* sel_mask, int normalize_inputs, int64_t* indices,
                              float* quantize, float* distances, float* z_norm_out, double* stats,
                              int want_dw, vqn_stream stream) {
-  VQN_CHECK_ARG(ctx && inputs && codebook, "vq_assign: null input");
+  VQN_CHECK_ARG(ctx, "vq_assign: null ctx");
   VQN_CHECK_ARG(z_dim == VQ_Z, "vq_assign: embedding_dim must be 256 (conv_width)");
   VQN_CHECK_ARG(k >= 1 && k <= 1024, "vq_assign: 1 <= K <= 1024");
   VQN_CHECK_ARG(n >= 0, "vq_assign: n < 0");
   if (n == 0) return VQN_OK;
+  VQN_CHECK_ARG(inputs && codebook, "vq_assign: null input");
   VqParams p;
   p.x = inputs; p.n = n; p.cb = codebook; p.K = k; p.sel_mask = sel_mask; p.maxdist = nullptr;
   p.normalize = normalize_inputs; p.idx_out = (long long*)indices; p.quant_out = quantize;
@@ -362,7 +363,7 @@ extern "C" int vqn_vq_assign(vqn_ctx* ctx, const float* inputs, int64_t n, int z
   VQN_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   unsigned* maxdist = nullptr;
   if (sel_mask) {
-    VQN_CUDA(cudaMallocAsync(&maxdist, sizeof(unsigned), s));
+    maxdist = reinterpret_cast<unsigned*>(ctx->scratch);          // persistent scratch slot 0
     VQN_CUDA(cudaMemsetAsync(maxdist, 0, sizeof(unsigned), s));   // ordered 0 == most negative
     p.maxdist = maxdist;
     k1<<<blocks, VQ_THREADS, smem, s>>>(p);
@@ -370,7 +371,6 @@ extern "C" int vqn_vq_assign(vqn_ctx* ctx, const float* inputs, int64_t n, int z
   }
   k0<<<blocks, VQ_THREADS, smem, s>>>(p);
   VQN_LAUNCHED(ctx);
-  if (maxdist) VQN_CUDA(cudaFreeAsync(maxdist, s));
   return VQN_OK;
 }
 

@@ -314,9 +314,11 @@ class Model:
         self._mark('begin', dev)
         row_idx, n_act = abi.compact_mask(alpha)
         self._mark('compact', dev)
-        z_enc = abi.pred_enc_at(self.net['fine_enc'].packed, self.net['bottleneck'].packed, nf, xyz,
-                                row_idx=row_idx, n=n_total, n_dev=n_act, precision=self.precision)
-        self._mark('mlp_enc', dev)
+        n_ = self.net
+        z_enc, basecolor, ks, rough = abi.mlp_main(
+            n_['fine_enc'].packed, n_['bottleneck'].packed, n_['diff_main'].packed, n_['spec_main'].packed,
+            n_['rough_main'].packed, nf, xyz, row_idx=row_idx, n_dev=n_act, n=n_total, slope=self.albedo_slope,
+            bias=self.albedo_bias, want_z=gen_embed, precision=self.precision)
         embed_ind = None
         if gen_embed:
             n = int(n_act.item())
@@ -325,10 +327,7 @@ class Model:
                                     thres=self._thres_mask(thres), roll=roll, return_encodings=False,
                                     return_distances=False)
             embed_ind = (vq_outs['encoding_indices'] + 1).to(torch.float32)
-        basecolor, ks, rough = abi.pred_heads(self.net['diff_main'].packed, self.net['spec_main'].packed,
-                                              self.net['rough_main'].packed, z_enc, self.albedo_slope,
-                                              self.albedo_bias, self.precision, n_dev=n_act)
-        self._mark('mlp_heads', dev)
+        self._mark('mlp_main', dev)
         scale_t = None
         if (opt_scale is not None) and (not vis_scale):
             scale_t = torch.as_tensor(np.asarray(opt_scale), dtype=torch.float32).reshape(-1).to(dev)
