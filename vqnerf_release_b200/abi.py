@@ -139,7 +139,9 @@ def mlp_main(fine_enc: PackedNet, bottleneck: PackedNet, diff: PackedNet, spec: 
     pts = _f(pts)
     n = pts.shape[0] if n is None else n
     dev = pts.device
-    z = torch.empty((n, bottleneck.out_dim), dtype=F32, device=dev) if want_z else None
+    # the tensor-core modes stage the latent in z (two launches: encoder, heads); fp32 keeps it on chip
+    stage_z = want_z or L.precision_code(precision) != L.PREC_FP32
+    z = torch.empty((n, bottleneck.out_dim), dtype=F32, device=dev) if stage_z else None
     outs = [torch.empty((n, h.out_dim), dtype=F32, device=dev) for h in (diff, spec, rough)]
     c = _ctx(pts)
     L.check(c.lib.vqn_mlp_main(c.handle, fine_enc.handle, bottleneck.handle, diff.handle, spec.handle, rough.handle,

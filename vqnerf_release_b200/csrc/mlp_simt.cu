@@ -16,7 +16,7 @@
 // Narrow output layers (N <= 8: the 3/1-wide sigmoid heads) run as a per-(point,output) dot product.
 #include <string.h>
 
-#include "common.cuh"
+#include "net.cuh"
 
 #define MLP_TM 64
 #define MLP_LD 68
@@ -57,18 +57,7 @@ struct MlpProgram {
   MlpStep steps[MLP_MAX_STEPS];
 };
 
-struct vqn_net {
-  vqn_ctx* ctx;
-  vqn_net_desc desc;       // host copy (device weight pointers are the caller's)
-  int n_layers;
-  int in_dim, in_pad;
-  int K[VQN_MAX_LAYERS], N[VQN_MAX_LAYERS], Npad[VQN_MAX_LAYERS];
-  float* packed_w[VQN_MAX_LAYERS];
-  float* packed_b[VQN_MAX_LAYERS];
-  void* tc_pack;           // tensor-core packing (mlp_tc.cu), owned there
-};
-
-static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline int round_up(int x, int m) { return vqn_round_up(x, m); }
 
 // ---------------------------------------------------------------------------------------------
 // weight packing: Keras [in,out] -> [K][Npad], K = rows in the kernel's smem order ([x_pad ; y] after a skip)
@@ -152,7 +141,7 @@ extern "C" int vqn_net_create(vqn_ctx* ctx, const vqn_net_desc* desc, vqn_net** 
   vqn_net* net = new vqn_net();
   net->ctx = ctx;
   net->desc = *desc;
-  net->tc_pack = nullptr;
+  net->tc_pack[0] = nullptr; net->tc_pack[1] = nullptr;
   net_layout(net);
   cudaStream_t s = vqn_cs(stream);
   for (int i = 0; i < desc->n_layers; ++i) {

@@ -1,28 +1,541 @@
-// Tensor-core (tcgen05 / TMEM) MLP modes: VQN_PREC_BF16 and VQN_PREC_TF32X3.
-// Round-1 status: packing hooks only; the entry points report VQN_ERR_UNSUPPORTED so that callers fail
-// loudly instead of silently falling back to another precision.
-#include "common.cuh"
+// Fused small-MLP kernel on the 5th-gen tensor cores (tcgen05 + TMEM):  VQN_PREC_TF32X3 and VQN_PREC_BF16.
+//
+// Reference: networks/mlp.py:24-50, networks/embedder.py:23-47, models/vq_nfr.py:771-828.
+//
+// One persistent CTA per SM walks tiles of 128 surface points through a chain of Dense layers without the
+// activations ever leaving the SM:
+//
+//   * accumulators live in TMEM (128 lanes = 128 points, up to 256 fp32 columns = layer width); two 256-column
+//     regions ping-pong between consecutive layers (512 columns = the whole TMEM of the SM);
+//   * the A operand of layer L+1 is produced CHUNK BY CHUNK (128 bytes of K per row: 32 tf32 / 64 bf16 values) by
+//     the four epilogue warps, which drain layer L's accumulator with tcgen05.ld, add the bias, apply the
+//     activation, convert (tf32 hi + lo planes, or bf16) and store the chunk in the 128-B-swizzled K-major layout
+//     the UMMA descriptors expect; positional-encoding chunks (Embedder) and latent chunks (z rows from global)
+//     enter the same ring, which is how the skip connections concat(y, x) are realised without copies;
+//   * the B operand (weights) is streamed from L2 by one producer thread with 1-D bulk copies (TMA engine,
+//     cp.async.bulk + mbarrier complete_tx) of host-pre-swizzled chunk images, through its own ring;
+//   * one thread issues tcgen05.mma (M = 128, N = layer width, K = 8 tf32 / 16 bf16 per instruction) and
+//     tcgen05.commit's the ring slots back to their producers and the accumulator to the epilogue warps.
+//
+// VQN_PREC_TF32X3 evaluates every product as a_hi w_hi + a_lo w_hi + a_hi w_lo with hi = rna_tf32(x),
+// lo = rna_tf32(x - hi) (three kind::tf32 MMAs, fp32 accumulation in TMEM): ~2^-21 relative per product, i.e.
+// fp32-level parity (1e-4 budget of the north star) at tensor-core speed.  VQN_PREC_BF16 is a single kind::f16 MMA
+// on bf16 operands (1e-2 budget).
+#include <string.h>
 
-struct vqn_net;
-int vqn_tc_pack_create(vqn_net*, cudaStream_t) { return VQN_OK; }
-void vqn_tc_pack_destroy(vqn_net*) {}
+#include "net.cuh"
+#include "tc_common.cuh"
 
-int vqn_tc_net_forward(vqn_net*, const float*, int64_t, float*, int, cudaStream_t) {
-  vqn_set_error("tensor-core MLP modes are not built in this revision; use VQN_PREC_FP32");
-  return VQN_ERR_UNSUPPORTED;
+#define TC_M 128               // points per tile (= TMEM lanes)
+#define TC_THREADS 192         // warps 0-3: epilogue / A producers, warp 4: MMA issuer, warp 5: weight producer
+#define TC_MAX_LAYERS 16
+#define TC_NPAD_MAX 256
+
+enum { SRC_DRAIN = 0, SRC_EMBED = 1, SRC_GLOBAL = 2 };
+
+struct TcLayer {
+  const uint8_t* w;       // packed chunk images, chunk c at w + c * chunk_bytes
+  const float* bias;      // [Npad]
+  int N, Npad, act;
+  int nseg, seg_type[2], seg_chunks[2], seg_first_chunk[2];   // seg_first_chunk: index inside the source
+  int out_slot;           // >= 0: accumulator is written to global outs[out_slot] (row-major [point][N])
+  float post_scale, post_bias;
+};
+
+struct TcProgram {
+  int n_layers;
+  int n_freqs;
+  int g_dim;               // row length of the GLOBAL source (z_dim)
+  const float* pts;        // [*,3] (EMBED source)
+  const float* gsrc;       // [n,g_dim] (GLOBAL source)
+  const int* row_idx;
+  const int* n_dev;
+  long long n;
+  float* outs[4];
+  int out_stride[4];
+  int* nonfinite;
+  TcLayer layers[TC_MAX_LAYERS];
+};
+
+struct TcPack {
+  int n_layers;
+  int Npad[VQN_MAX_LAYERS];
+  int n_chunks[VQN_MAX_LAYERS];
+  uint8_t* w[VQN_MAX_LAYERS];
+  float* bias[VQN_MAX_LAYERS];
+};
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: Keras kernel [in,out] -> per K-chunk swizzled images [Npad x 128 B] (tf32: hi image then lo image)
+// K order = Keras row order (after a skip: y rows, then the x rows), each segment padded to whole chunks.
+// ---------------------------------------------------------------------------------------------
+template <bool BF16>
+__global__ void tc_pack_kernel(const float* __restrict__ w, const float* __restrict__ b, int n_out, int Npad,
+                               int seg0_rows, int seg0_chunks, int seg1_rows, int seg1_chunks,
+                               uint8_t* __restrict__ pw, float* __restrict__ pb) {
+  constexpr int E = BF16 ? 64 : 32;
+  const int n_chunks = seg0_chunks + seg1_chunks;
+  const size_t plane = (size_t)Npad * 128;
+  const size_t chunk_bytes = BF16 ? plane : 2 * plane;
+  const long long total = (long long)n_chunks * Npad * E;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int kk = (int)(i % E);
+    int n = (int)((i / E) % Npad);
+    int c = (int)(i / ((long long)E * Npad));
+    int src;
+    if (c < seg0_chunks) { int r = c * E + kk; src = r < seg0_rows ? r : -1; }
+    else { int r = (c - seg0_chunks) * E + kk; src = r < seg1_rows ? seg0_rows + r : -1; }
+    float v = (src >= 0 && n < n_out) ? w[(size_t)src * n_out + n] : 0.f;
+    uint8_t* base = pw + (size_t)c * chunk_bytes;
+    if (BF16) {
+      uint32_t off = tc::sw128_off(n, kk / 8) + (kk % 8) * 2;
+      *reinterpret_cast<__nv_bfloat16*>(base + off) = __float2bfloat16_rn(v);
+    } else {
+      uint32_t off = tc::sw128_off(n, kk / 4) + (kk % 4) * 4;
+      float hi = tc::tf32_rna(v);
+      *reinterpret_cast<float*>(base + off) = hi;
+      *reinterpret_cast<float*>(base + plane + off) = tc::tf32_rna(v - hi);
+    }
+  }
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < Npad; c += gridDim.x * blockDim.x)
+    pb[c] = c < n_out ? b[c] : 0.f;
 }
-int vqn_tc_pred_enc_at(vqn_ctx*, vqn_net*, vqn_net*, int, const float*, const int32_t*, const int32_t*, int64_t, float*, int,
-                       cudaStream_t) {
-  vqn_set_error("tensor-core MLP modes are not built in this revision; use VQN_PREC_FP32");
-  return VQN_ERR_UNSUPPORTED;
+
+static int tc_pack_fill(vqn_net* net, int p, cudaStream_t s) {
+  TcPack* tp = net->tc_pack[p];
+  const vqn_net_desc& d = net->desc;
+  const bool bf16 = (p == 1);
+  const int E = bf16 ? 64 : 32;
+  for (int i = 0; i < d.n_layers; ++i) {
+    bool after_skip = (d.skip_at >= 0 && i == d.skip_at + 1);
+    int seg0_rows = (i == 0) ? d.in_dim : d.widths[i - 1];
+    int seg1_rows = after_skip ? d.in_dim : 0;
+    int c0 = vqn_round_up(seg0_rows, E) / E, c1 = vqn_round_up(seg1_rows, E) / E;
+    if (bf16) tc_pack_kernel<true><<<128, 256, 0, s>>>(d.w[i], d.b[i], d.widths[i], tp->Npad[i], seg0_rows, c0,
+                                                      seg1_rows, c1, tp->w[i], tp->bias[i]);
+    else tc_pack_kernel<false><<<128, 256, 0, s>>>(d.w[i], d.b[i], d.widths[i], tp->Npad[i], seg0_rows, c0,
+                                                   seg1_rows, c1, tp->w[i], tp->bias[i]);
+    net->ctx->launches.fetch_add(1);
+    VQN_CUDA(cudaGetLastError());
+  }
+  return VQN_OK;
 }
-int vqn_tc_pred_heads(vqn_ctx*, vqn_net*, vqn_net*, vqn_net*, const float*, const int32_t*, int64_t, float, float, float*, float*,
-                      float*, int, cudaStream_t) {
-  vqn_set_error("tensor-core MLP modes are not built in this revision; use VQN_PREC_FP32");
-  return VQN_ERR_UNSUPPORTED;
+
+static int tc_pack_get(vqn_net* net, int precision, cudaStream_t s, TcPack** out) {
+  const int p = precision == VQN_PREC_BF16 ? 1 : 0;
+  if (net->tc_pack[p]) { *out = net->tc_pack[p]; return VQN_OK; }
+  const vqn_net_desc& d = net->desc;
+  const int E = p == 1 ? 64 : 32;
+  for (int i = 0; i + 1 < d.n_layers; ++i)
+    if (d.widths[i] % 64 != 0) {
+      vqn_set_error("tensor-core MLP modes need hidden widths that are multiples of 64 (layer %d has %d)", i,
+                    d.widths[i]);
+      return VQN_ERR_UNSUPPORTED;
+    }
+  TcPack* tp = new TcPack();
+  memset(tp, 0, sizeof(*tp));
+  tp->n_layers = d.n_layers;
+  for (int i = 0; i < d.n_layers; ++i) {
+    bool after_skip = (d.skip_at >= 0 && i == d.skip_at + 1);
+    int seg0_rows = (i == 0) ? d.in_dim : d.widths[i - 1];
+    int seg1_rows = after_skip ? d.in_dim : 0;
+    tp->Npad[i] = vqn_round_up(d.widths[i], 16);
+    tp->n_chunks[i] = vqn_round_up(seg0_rows, E) / E + vqn_round_up(seg1_rows, E) / E;
+    size_t chunk_bytes = (size_t)tp->Npad[i] * 128 * (p == 1 ? 1 : 2);
+    VQN_CUDA(cudaMalloc(&tp->w[i], chunk_bytes * tp->n_chunks[i]));
+    VQN_CUDA(cudaMalloc(&tp->bias[i], sizeof(float) * tp->Npad[i]));
+  }
+  net->tc_pack[p] = tp;
+  int rc = tc_pack_fill(net, p, s);
+  if (rc != VQN_OK) return rc;
+  *out = tp;
+  return VQN_OK;
 }
-int vqn_tc_mlp_main(vqn_ctx*, vqn_net*, vqn_net*, vqn_net*, vqn_net*, vqn_net*, int, const float*, const int32_t*,
-                    const int32_t*, int64_t, float, float, float*, float*, float*, float*, int, cudaStream_t) {
-  vqn_set_error("tensor-core MLP modes are not built in this revision; use VQN_PREC_FP32");
-  return VQN_ERR_UNSUPPORTED;
+
+// called from vqn_net_create (nothing to do: packs are lazy) and vqn_net_repack (refresh existing images)
+int vqn_tc_pack_create(vqn_net* net, cudaStream_t s) {
+  for (int p = 0; p < 2; ++p)
+    if (net->tc_pack[p]) { int rc = tc_pack_fill(net, p, s); if (rc != VQN_OK) return rc; }
+  return VQN_OK;
+}
+
+void vqn_tc_pack_destroy(vqn_net* net) {
+  for (int p = 0; p < 2; ++p) {
+    TcPack* tp = net->tc_pack[p];
+    if (!tp) continue;
+    for (int i = 0; i < tp->n_layers; ++i) { cudaFree(tp->w[i]); cudaFree(tp->bias[i]); }
+    delete tp;
+    net->tc_pack[p] = nullptr;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float embed_val(const float (&x)[3], int col, int n_freqs) {
+  // Embedder.__call__ (embedder.py:35-47): [x, sin(x f0), cos(x f0), sin(x f1), ...], f_k = 2^k
+  if (col < 3) return x[col];
+  int q = col - 3;
+  if (q >= 6 * n_freqs) return 0.f;
+  int f = q / 6, w = q - 6 * f;
+  int ax = w < 3 ? w : w - 3;
+  float xv = ax == 0 ? x[0] : (ax == 1 ? x[1] : x[2]);   // selects, not dynamic indexing (keeps x in registers)
+  float a = xv * exp2f((float)f);
+  return w < 3 ? sinf(a) : cosf(a);
+}
+
+template <bool BF16>
+struct TcCfg {
+  static constexpr int E = BF16 ? 64 : 32;                 // K elements per chunk
+  static constexpr int PLANES = BF16 ? 1 : 2;
+  static constexpr int SA = BF16 ? 4 : 2;                  // A ring stages
+  static constexpr int SW = BF16 ? 4 : 2;                  // W ring stages
+  static constexpr uint32_t A_PLANE = TC_M * 128;          // 16 KB
+  static constexpr uint32_t A_SLOT = A_PLANE * PLANES;
+  static constexpr uint32_t W_SLOT = (uint32_t)TC_NPAD_MAX * 128 * PLANES;
+  static constexpr size_t SMEM = (size_t)SA * A_SLOT + (size_t)SW * W_SLOT + 1024;
+};
+
+// store 32 consecutive K values (columns j0 .. j0+31 of the chunk) of row r into the chunk slot
+template <bool BF16>
+__device__ __forceinline__ void store_chunk32(uint8_t* slot, int r, int j0, const float (&v)[32]) {
+  if (BF16) {
+    // 32 values = 64 bytes = four 16-byte chunks starting at c16 = j0 / 8
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]);
+      __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
+      __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
+      uint4 u;
+      u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+      u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+      *reinterpret_cast<uint4*>(slot + tc::sw128_off(r, j0 / 8 + q)) = u;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float h[4], l[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { h[i] = tc::tf32_rna(v[4 * q + i]); l[i] = tc::tf32_rna(v[4 * q + i] - h[i]); }
+      const uint32_t off = tc::sw128_off(r, j0 / 4 + q);
+      *reinterpret_cast<float4*>(slot + off) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(slot + TC_M * 128 + off) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+  }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcProgram pg) {
+  using C = TcCfg<BF16>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[4], a_empty[4], w_full[4], w_empty[4], acc_full;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_ring = smem;
+  uint8_t* w_ring = smem + (size_t)C::SA * C::A_SLOT;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (warp == 4) tc::tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) {
+      tc::mbar_init(&a_full[i], 128); tc::mbar_init(&a_empty[i], 1);
+      tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1);
+    }
+    tc::mbar_init(&acc_full, 1);
+    tc::mbar_fence_init();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+
+  long long n = pg.n_dev ? (long long)*pg.n_dev : pg.n;
+  if (n > pg.n) n = pg.n;
+  const long long n_tiles = (n + TC_M - 1) / TC_M;
+  const int L = pg.n_layers;
+
+  if (warp < 4) {
+    // =========================== epilogue warps: A-chunk producers + accumulator drain ===========================
+    const int r = tid;                                   // TMEM lane == point row of the tile
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * warp) << 16);
+    uint32_t ga = 0;                                     // global A-chunk counter
+    uint32_t gl = 0;                                     // global layer counter (acc_full phase)
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long pi = tile * TC_M + r;              // compact point index
+      const bool valid = pi < n;
+      float x[3] = {0.f, 0.f, 0.f};
+      if (pg.pts && valid) {
+        long long row = pg.row_idx ? (long long)pg.row_idx[pi] : pi;
+        x[0] = pg.pts[row * 3]; x[1] = pg.pts[row * 3 + 1]; x[2] = pg.pts[row * 3 + 2];
+      }
+      for (int l = 0; l < L; ++l) {
+        const TcLayer& ly = pg.layers[l];
+        for (int sg = 0; sg < ly.nseg; ++sg) {
+          const int st = ly.seg_type[sg];
+          if (st == SRC_DRAIN) {
+            // the previous layer's accumulator must be complete
+            tc::mbar_wait(&acc_full, (gl - 1) & 1);
+            tc::fence_after_sync();
+          }
+          for (int c = 0; c < ly.seg_chunks[sg]; ++c, ++ga) {
+            const int slot = ga % C::SA;
+            tc::mbar_wait(&a_empty[slot], ((ga / C::SA) & 1) ^ 1);
+            uint8_t* dst = a_ring + (size_t)slot * C::A_SLOT;
+            const int sc = ly.seg_first_chunk[sg] + c;   // chunk index inside the source
+#pragma unroll
+            for (int h = 0; h < C::E / 32; ++h) {
+              float v[32];
+              const int col0 = sc * C::E + 32 * h;       // first source column of this 32-wide piece
+              if (st == SRC_DRAIN) {
+                const TcLayer& pl = pg.layers[l - 1];
+                tc::tmem_ld32(lane_addr + (uint32_t)(((l - 1) & 1) * 256 + col0), v);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(pl.bias + col0 + j));
+                  v[j] = vqn_apply_act(v[j] + b4.x, pl.act); v[j + 1] = vqn_apply_act(v[j + 1] + b4.y, pl.act);
+                  v[j + 2] = vqn_apply_act(v[j + 2] + b4.z, pl.act); v[j + 3] = vqn_apply_act(v[j + 3] + b4.w, pl.act);
+                }
+              } else if (st == SRC_EMBED) {
+#pragma unroll 4
+                for (int j = 0; j < 32; ++j) v[j] = embed_val(x, col0 + j, pg.n_freqs);
+              } else {  // SRC_GLOBAL: this thread's own latent row
+                if (valid && col0 < pg.g_dim) {
+                  const float4* src = reinterpret_cast<const float4*>(pg.gsrc + pi * pg.g_dim + col0);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    float4 t = src[j];
+                    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                }
+              }
+              store_chunk32<BF16>(dst, r, 32 * h, v);
+            }
+            tc::fence_proxy_async();       // generic-proxy stores -> visible to the UMMA (async proxy)
+            tc::fence_before_sync();       // order the tcgen05.ld's above before the hand-off
+            tc::mbar_arrive(&a_full[slot]);
+          }
+        }
+        ++gl;                               // layer l's chunks are all queued
+        if (ly.out_slot >= 0) {
+          // final layer of a network: drain its accumulator to global memory
+          tc::mbar_wait(&acc_full, (gl - 1) & 1);
+          tc::fence_after_sync();
+          float* go = pg.outs[ly.out_slot];
+          const int gs = pg.out_stride[ly.out_slot];
+          for (int cb = 0; cb * 32 < ly.N; ++cb) {
+            float v[32];
+            tc::tmem_ld32(lane_addr + (uint32_t)((l & 1) * 256 + cb * 32), v);
+            bool bad = false;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float b = (cb * 32 + j < ly.Npad) ? __ldg(ly.bias + cb * 32 + j) : 0.f;
+              v[j] = vqn_apply_act(v[j] + b, ly.act) * ly.post_scale + ly.post_bias;
+              bad |= (cb * 32 + j < ly.N) && !isfinite(v[j]);
+            }
+            if (valid) {
+              if (bad) atomicOr(pg.nonfinite, 1);
+              if (cb * 32 + 32 <= ly.N && (gs & 3) == 0) {
+                float4* o = reinterpret_cast<float4*>(go + pi * gs + cb * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (cb * 32 + j < ly.N) go[pi * gs + cb * 32 + j] = v[j];
+              }
+            }
+          }
+          tc::fence_before_sync();
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // =========================== MMA issuer (one thread) ===========================
+    if (lane == 0) {
+      uint32_t ga = 0, gw = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int l = 0; l < L; ++l) {
+          const TcLayer& ly = pg.layers[l];
+          const uint32_t idesc = tc::make_idesc(BF16 ? tc::FMT_BF16 : tc::FMT_TF32, TC_M, ly.Npad);
+          const uint32_t d_tmem = tmem_base + (uint32_t)((l & 1) * 256);
+          const int nch = ly.seg_chunks[0] + (ly.nseg > 1 ? ly.seg_chunks[1] : 0);
+          uint32_t acc = 0;
+          for (int c = 0; c < nch; ++c, ++ga, ++gw) {
+            const int sa = ga % C::SA, sw = gw % C::SW;
+            tc::mbar_wait(&a_full[sa], (ga / C::SA) & 1);
+            tc::mbar_wait(&w_full[sw], (gw / C::SW) & 1);
+            tc::fence_after_sync();
+            const uint32_t a_addr = tc::smem_u32(a_ring + (size_t)sa * C::A_SLOT);
+            const uint32_t w_addr = tc::smem_u32(w_ring + (size_t)sw * C::W_SLOT);
+            const uint32_t w_plane = (uint32_t)ly.Npad * 128;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+              const uint64_t a_hi = tc::make_desc_sw128(a_addr + 32 * s);
+              const uint64_t b_hi = tc::make_desc_sw128(w_addr + 32 * s);
+              tc::mma_ss<!BF16>(d_tmem, a_hi, b_hi, idesc, acc);
+              acc = 1;
+              if (!BF16) {
+                const uint64_t a_lo = tc::make_desc_sw128(a_addr + C::A_PLANE + 32 * s);
+                const uint64_t b_lo = tc::make_desc_sw128(w_addr + w_plane + 32 * s);
+                tc::mma_ss<true>(d_tmem, a_lo, b_hi, idesc, 1);
+                tc::mma_ss<true>(d_tmem, a_hi, b_lo, idesc, 1);
+              }
+            }
+            tc::mma_commit(&a_empty[sa]);       // slots are free once these MMAs have read them
+            tc::mma_commit(&w_empty[sw]);
+          }
+          tc::mma_commit(&acc_full);            // layer complete -> epilogue warps may drain it
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================== weight producer (one thread, bulk copies) ===========================
+    if (lane == 0) {
+      uint32_t gw = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int l = 0; l < L; ++l) {
+          const TcLayer& ly = pg.layers[l];
+          const int nch = ly.seg_chunks[0] + (ly.nseg > 1 ? ly.seg_chunks[1] : 0);
+          const uint32_t bytes = (uint32_t)ly.Npad * 128 * C::PLANES;
+          for (int c = 0; c < nch; ++c, ++gw) {
+            const int sw = gw % C::SW;
+            tc::mbar_wait(&w_empty[sw], ((gw / C::SW) & 1) ^ 1);
+            tc::mbar_expect_tx(&w_full[sw], bytes);
+            tc::bulk_g2s(w_ring + (size_t)sw * C::W_SLOT, ly.w + (size_t)c * bytes, bytes, &w_full[sw]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side program assembly
+// ---------------------------------------------------------------------------------------------
+struct TcBuilder {
+  TcProgram pg;
+  bool ok;
+  int E;
+  TcBuilder(int precision) { memset(&pg, 0, sizeof(pg)); ok = true; E = precision == VQN_PREC_BF16 ? 64 : 32; }
+};
+
+// Append one network.  first_src: where its input x comes from (SRC_EMBED / SRC_GLOBAL / SRC_DRAIN = output of the
+// previous appended layer).  out_slot: global output slot of the last layer (-1: it feeds the next network).
+static bool tc_append_net(TcBuilder& B, vqn_net* net, TcPack* tp, int first_src, int out_slot, float post_scale,
+                          float post_bias) {
+  const vqn_net_desc& d = net->desc;
+  for (int i = 0; i < d.n_layers; ++i) {
+    if (B.pg.n_layers >= TC_MAX_LAYERS) return false;
+    TcLayer& ly = B.pg.layers[B.pg.n_layers];
+    memset(&ly, 0, sizeof(ly));
+    ly.w = tp->w[i]; ly.bias = tp->bias[i];
+    ly.N = d.widths[i]; ly.Npad = tp->Npad[i]; ly.act = d.acts[i];
+    ly.out_slot = -1; ly.post_scale = 1.f; ly.post_bias = 0.f;
+    const bool after_skip = (d.skip_at >= 0 && i == d.skip_at + 1);
+    const int seg0_rows = (i == 0) ? d.in_dim : d.widths[i - 1];
+    ly.nseg = 1;
+    ly.seg_type[0] = (i == 0) ? first_src : SRC_DRAIN;
+    ly.seg_chunks[0] = vqn_round_up(seg0_rows, B.E) / B.E;
+    ly.seg_first_chunk[0] = 0;
+    if (ly.seg_type[0] == SRC_DRAIN && B.pg.n_layers == 0) return false;
+    if (after_skip) {
+      if (first_src == SRC_DRAIN) return false;   // x must be regenerable (embedding / global rows)
+      ly.nseg = 2;
+      ly.seg_type[1] = first_src;
+      ly.seg_chunks[1] = vqn_round_up(d.in_dim, B.E) / B.E;
+      ly.seg_first_chunk[1] = 0;
+    }
+    if (i == d.n_layers - 1) { ly.out_slot = out_slot; ly.post_scale = post_scale; ly.post_bias = post_bias; }
+    if (ly.Npad > TC_NPAD_MAX) return false;
+    B.pg.n_layers++;
+  }
+  return true;
+}
+
+static int tc_launch(vqn_ctx* ctx, TcProgram& pg, int precision, cudaStream_t s) {
+  pg.nonfinite = ctx->nonfinite_flag;
+  long long tiles = (pg.n + TC_M - 1) / TC_M;
+  int blocks = (int)(tiles < (long long)ctx->sm_count ? tiles : (long long)ctx->sm_count);
+  if (precision == VQN_PREC_BF16) {
+    size_t smem = TcCfg<true>::SMEM;
+    VQN_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_tc_kernel<true><<<blocks, TC_THREADS, smem, s>>>(pg);
+  } else {
+    size_t smem = TcCfg<false>::SMEM;
+    VQN_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_tc_kernel<false><<<blocks, TC_THREADS, smem, s>>>(pg);
+  }
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}
+
+#define TC_UNSUPPORTED(msg) do { vqn_set_error(msg); return VQN_ERR_UNSUPPORTED; } while (0)
+
+int vqn_tc_net_forward(vqn_net* net, const float* x, int64_t n, float* y, int precision, cudaStream_t s) {
+  if (net->in_dim % 4 != 0) TC_UNSUPPORTED("tensor-core net_forward needs in_dim % 4 == 0 (16-byte row loads)");
+  TcPack* tp;
+  int rc = tc_pack_get(net, precision, s, &tp);
+  if (rc != VQN_OK) return rc;
+  TcBuilder B(precision);
+  B.pg.gsrc = x; B.pg.g_dim = net->in_dim; B.pg.n = n;
+  B.pg.outs[0] = y; B.pg.out_stride[0] = net->desc.widths[net->n_layers - 1];
+  if (!tc_append_net(B, net, tp, SRC_GLOBAL, 0, 1.f, 0.f)) TC_UNSUPPORTED("net_forward: network does not fit");
+  return tc_launch(net->ctx, B.pg, precision, s);
+}
+
+int vqn_tc_pred_enc_at(vqn_ctx* ctx, vqn_net* fe, vqn_net* bn, int n_freqs, const float* pts, const int32_t* row_idx,
+                       const int32_t* n_dev, int64_t n, float* z, int precision, cudaStream_t s) {
+  TcPack *t0, *t1;
+  int rc = tc_pack_get(fe, precision, s, &t0);
+  if (rc != VQN_OK) return rc;
+  rc = tc_pack_get(bn, precision, s, &t1);
+  if (rc != VQN_OK) return rc;
+  TcBuilder B(precision);
+  B.pg.pts = pts; B.pg.row_idx = row_idx; B.pg.n_dev = n_dev; B.pg.n = n; B.pg.n_freqs = n_freqs;
+  B.pg.outs[0] = z; B.pg.out_stride[0] = bn->desc.widths[bn->n_layers - 1];
+  bool ok = tc_append_net(B, fe, t0, SRC_EMBED, -1, 1.f, 0.f) && tc_append_net(B, bn, t1, SRC_DRAIN, 0, 1.f, 0.f);
+  if (!ok) TC_UNSUPPORTED("pred_enc_at: program does not fit the tensor-core kernel");
+  return tc_launch(ctx, B.pg, precision, s);
+}
+
+int vqn_tc_pred_heads(vqn_ctx* ctx, vqn_net* diff, vqn_net* spec, vqn_net* rough, const float* z,
+                      const int32_t* n_dev, int64_t n, float slope, float bias, float* d, float* sp, float* r,
+                      int precision, cudaStream_t s) {
+  vqn_net* nets[3] = {diff, spec, rough};
+  float* outs[3] = {d, sp, r};
+  TcBuilder B(precision);
+  B.pg.gsrc = z; B.pg.n_dev = n_dev; B.pg.n = n;
+  for (int h = 0; h < 3; ++h) {
+    if (!nets[h]) continue;
+    if (B.pg.g_dim && B.pg.g_dim != nets[h]->in_dim) TC_UNSUPPORTED("pred_heads: heads disagree on z_dim");
+    B.pg.g_dim = nets[h]->in_dim;
+    TcPack* tp;
+    int rc = tc_pack_get(nets[h], precision, s, &tp);
+    if (rc != VQN_OK) return rc;
+    B.pg.outs[h] = outs[h]; B.pg.out_stride[h] = nets[h]->desc.widths[nets[h]->n_layers - 1];
+    if (!tc_append_net(B, nets[h], tp, SRC_GLOBAL, h, h == 0 ? slope : 1.f, h == 0 ? bias : 0.f))
+      TC_UNSUPPORTED("pred_heads: program does not fit the tensor-core kernel");
+  }
+  if (B.pg.g_dim % 4 != 0) TC_UNSUPPORTED("pred_heads: z_dim % 4 != 0");
+  return tc_launch(ctx, B.pg, precision, s);
+}
+
+// encoder then heads: two launches of the same kernel; the latent round-trips through z_out (L2-resident per tile)
+int vqn_tc_mlp_main(vqn_ctx* ctx, vqn_net* fe, vqn_net* bn, vqn_net* diff, vqn_net* spec, vqn_net* rough, int n_freqs,
+                    const float* pts, const int32_t* row_idx, const int32_t* n_dev, int64_t n, float slope, float bias,
+                    float* z_out, float* d, float* sp, float* r, int precision, cudaStream_t s) {
+  if (!z_out) TC_UNSUPPORTED("mlp_main (tensor-core modes): z_out buffer is required (the latent is staged there)");
+  int rc = vqn_tc_pred_enc_at(ctx, fe, bn, n_freqs, pts, row_idx, n_dev, n, z_out, precision, s);
+  if (rc != VQN_OK) return rc;
+  return vqn_tc_pred_heads(ctx, diff, spec, rough, z_out, n_dev, n, slope, bias, d, sp, r, precision, s);
 }

@@ -125,6 +125,11 @@ __device__ __host__ __forceinline__ uint32_t sw128_off(uint32_t r, uint32_t c16)
   return r * 128u + ((c16 ^ (r & 7u)) << 4);
 }
 
-__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// round-to-nearest tf32 (low 13 mantissa bits zero afterwards); hi = rna(x), lo = rna(x - hi) is the 3xTF32 split
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 
 }  // namespace tc

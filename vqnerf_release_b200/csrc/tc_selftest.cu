@@ -1,6 +1,6 @@
 // Single-tile tcgen05 GEMM used to validate the tensor-core primitives (descriptors, 128-B swizzle, TMEM
 // alloc/ld, tcgen05.commit -> mbarrier) on real hardware:  D[128,N] = A[128,K] . B[N,K]^T, fp32 accumulate.
-//   mode 0: kind::tf32 single pass (inputs truncated to tf32 by the kernel)
+//   mode 0: kind::tf32 single pass (inputs rounded to tf32 by the kernel)
 //   mode 1: kind::f16 with bf16 operands (round-to-nearest)
 //   mode 2: 3xTF32 split  A_hi B_hi + A_lo B_hi + A_hi B_lo  (fp32-parity arithmetic of VQN_PREC_TF32X3)
 #include "common.cuh"
@@ -34,10 +34,10 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const float* __rest
       *reinterpret_cast<__nv_bfloat16*>(a_base + (size_t)ch * a_tile + off) = __float2bfloat16_rn(v);
     } else {
       uint32_t off = tc::sw128_off(r, kk / 4) + (kk % 4) * 4;
-      float hi = tc::tf32_trunc(v);
+      float hi = tc::tf32_rna(v);
       *reinterpret_cast<float*>(a_base + (size_t)ch * a_tile + off) = hi;
       if (mode == 2)
-        *reinterpret_cast<float*>(a_base + (size_t)(nch + ch) * a_tile + off) = tc::tf32_trunc(v - hi);
+        *reinterpret_cast<float*>(a_base + (size_t)(nch + ch) * a_tile + off) = tc::tf32_rna(v - hi);
     }
   }
   for (int idx = tid; idx < N * K; idx += 128) {
@@ -48,10 +48,10 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const float* __rest
       *reinterpret_cast<__nv_bfloat16*>(b_base + (size_t)ch * b_tile + off) = __float2bfloat16_rn(v);
     } else {
       uint32_t off = tc::sw128_off(r, kk / 4) + (kk % 4) * 4;
-      float hi = tc::tf32_trunc(v);
+      float hi = tc::tf32_rna(v);
       *reinterpret_cast<float*>(b_base + (size_t)ch * b_tile + off) = hi;
       if (mode == 2)
-        *reinterpret_cast<float*>(b_base + (size_t)(nch + ch) * b_tile + off) = tc::tf32_trunc(v - hi);
+        *reinterpret_cast<float*>(b_base + (size_t)(nch + ch) * b_tile + off) = tc::tf32_rna(v - hi);
     }
   }
   tc::fence_proxy_async();
