@@ -49,7 +49,8 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--points', type=int, default=N_POINTS, help='points per GPU per step (default 800x800)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--precision', default='fp32', choices=['fp32', 'bf16', 'tf32x3'])
+    ap.add_argument('--precision', default='tf32x3', choices=['fp32', 'bf16', 'tf32x3'],
+                    help='MLP arithmetic: tf32x3 = tcgen05 3xTF32 split, fp32 accumulate (fp32 parity, default)')
     return ap.parse_args()
 
 
@@ -315,10 +316,14 @@ def run_ours(args):
                                    % (float(tf2.value), bf16_peak, peak_src),
                     'traffic': None}
         else:
+            # tf32 tensor rate = bf16 / 2; three MMAs per product in the 3xTF32 split
             peak = bf16_peak if args.precision == 'bf16' else bf16_peak / 2 / 3
             ach = MLP_FLOP * n / (mlp_ms * 1e-3) / 1e12
-            roof = {'bound': 'tensor', 'kernel': 'mlp_tc_kernel (encoder + 3 main heads)', 'achieved': ach, 'peak': peak,
-                    'unit': 'TFLOP/s', 'frac': ach / peak, 'peak_source': peak_src, 'traffic': None}
+            roof = {'bound': 'tensor', 'kernel': 'mlp_tc_kernel<%s> (encoder launch + heads launch, 953 600 FLOP/point)' % args.precision,
+                    'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s (fp32-equivalent algorithmic FLOPs)', 'frac': ach / peak,
+                    'peak_source': 'bf16 cuBLAS peak %.0f TFLOP/s %s%s; FFMA peak measured live: %.1f TFLOP/s' % (
+                        bf16_peak, peak_src, '' if args.precision == 'bf16' else ' / 2 (tf32 rate) / 3 (hi/lo split MMAs)', fp32_peak),
+                    'traffic': None}
         shade_bytes = n * (2048 + 36 + 28 + 12 * (1 + P))
         kernels = {
             'mlp_main': {'ms': mlp_ms, 'tflops': MLP_FLOP * n / (mlp_ms * 1e-3) / 1e12},
@@ -333,7 +338,7 @@ def run_ours(args):
         line = {
             'metric': 'shaded surface points/sec', 'value': value, 'unit': 'points/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': {'fp32': 'f32', 'bf16': 'bf16', 'tf32x3': 'tf32x3'}[args.precision],
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': {'fp32': 'f32', 'bf16': 'bf16', 'tf32x3': 'f32 (3xTF32 tensor-core split, fp32 accumulate)'}[args.precision],
             'data': 'synthetic',
             'config': {'workload': 'vq_nfr.fast_render full-image relight: %d points/GPU (800x800 view, all foreground), '
                                    '512-light probe + P=%d novel probes, random-init MLPs, K=15 codebook' % (n, P),

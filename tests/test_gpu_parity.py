@@ -79,9 +79,10 @@ def test_embedder_and_net_forward(cuda_dev):
         _close(y, on(torch.as_tensor(inp, dtype=torch.float64)), name)
 
 
-def test_pred_enc_and_heads_match_oracle(cuda_dev):
+@pytest.mark.parametrize('precision', ['fp32', 'tf32x3'])
+def test_pred_enc_and_heads_match_oracle(cuda_dev, precision):
     scene = O.synth_scene(1, bias_scale=0.05)
-    m = _model_from_scene(scene, cuda_dev)
+    m = _model_from_scene(scene, cuda_dev, precision=precision)
     rng = np.random.RandomState(5)
     for n in (1, 63, 64, 65, 1000):
         pts = rng.uniform(-1, 1, size=(n, 3)).astype(np.float32)
@@ -223,12 +224,13 @@ def test_eval_brdf_and_render_fine_grained(cuda_dev):
     assert probes is None
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'tf32x3'])
 @pytest.mark.parametrize('n_probes,fg,data_type', [(0, 1.0, 'nerf'), (2, 0.7, 'nerf'), (9, 0.5, 'nerf'), (1, 0.8, 'dtu')])
-def test_fast_render_matches_oracle(cuda_dev, n_probes, fg, data_type):
+def test_fast_render_matches_oracle(cuda_dev, n_probes, fg, data_type, precision):
     n = 4096 if n_probes == 2 else 1500
     scene = O.synth_scene(11, n_probes=n_probes, bias_scale=0.05, data_type=data_type)
     batch = O.synth_batch(n, 11, fg_frac=fg, with_lvis=(data_type == 'nerf'))
-    m = _model_from_scene(scene, cuda_dev)
+    m = _model_from_scene(scene, cuda_dev, precision=precision)
     pred, gt, loss_kwargs, to_vis = m.fast_render(_batch_tuple(batch, cuda_dev, data_type), mode='test',
                                                   relight_probes=True, gen_embed=True, opt_scale=[0.9, 1.1, 1.05])
     o = O.fast_render(scene, batch, torch.float64, relight_probes=True, gen_embed=True, opt_scale=[0.9, 1.1, 1.05])

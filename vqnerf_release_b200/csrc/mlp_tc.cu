@@ -27,7 +27,6 @@
 #include "tc_common.cuh"
 
 #define TC_M 128               // points per tile (= TMEM lanes)
-#define TC_THREADS 192         // warps 0-3: epilogue / A producers, warp 4: MMA issuer, warp 5: weight producer
 #define TC_MAX_LAYERS 16
 #define TC_NPAD_MAX 256
 
@@ -39,6 +38,7 @@ struct TcLayer {
   int N, Npad, act;
   int nseg, seg_type[2], seg_chunks[2], seg_first_chunk[2];   // seg_first_chunk: index inside the source
   int out_slot;           // >= 0: accumulator is written to global outs[out_slot] (row-major [point][N])
+  int bias_off;           // offset of this layer's bias inside the shared-memory bias table
   float post_scale, post_bias;
 };
 
@@ -173,35 +173,44 @@ void vqn_tc_pack_destroy(vqn_net* net) {
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float embed_val(const float (&x)[3], int col, int n_freqs) {
-  // Embedder.__call__ (embedder.py:35-47): [x, sin(x f0), cos(x f0), sin(x f1), ...], f_k = 2^k
-  if (col < 3) return x[col];
-  int q = col - 3;
-  if (q >= 6 * n_freqs) return 0.f;
-  int f = q / 6, w = q - 6 * f;
-  int ax = w < 3 ? w : w - 3;
-  float xv = ax == 0 ? x[0] : (ax == 1 ? x[1] : x[2]);   // selects, not dynamic indexing (keeps x in registers)
-  float a = xv * exp2f((float)f);
-  return w < 3 ? sinf(a) : cosf(a);
-}
-
 template <bool BF16>
 struct TcCfg {
   static constexpr int E = BF16 ? 64 : 32;                 // K elements per chunk
   static constexpr int PLANES = BF16 ? 1 : 2;
   static constexpr int SA = BF16 ? 4 : 2;                  // A ring stages
   static constexpr int SW = BF16 ? 4 : 2;                  // W ring stages
+  static constexpr int G = 2;                              // epilogue warp-groups (4 warps each)
+  static constexpr int THREADS = 32 * (4 * G + 2);         // + MMA warp + weight-producer warp
   static constexpr uint32_t A_PLANE = TC_M * 128;          // 16 KB
   static constexpr uint32_t A_SLOT = A_PLANE * PLANES;
   static constexpr uint32_t W_SLOT = (uint32_t)TC_NPAD_MAX * 128 * PLANES;
   static constexpr size_t SMEM = (size_t)SA * A_SLOT + (size_t)SW * W_SLOT + 1024;
 };
+#define TC_BIAS_FLOATS 2048
+
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+template <int ACT>
+__device__ __forceinline__ void bias_act32(float (&v)[32], const float* __restrict__ bias_s) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j);
+    float t0 = v[j] + b4.x, t1 = v[j + 1] + b4.y, t2 = v[j + 2] + b4.z, t3 = v[j + 3] + b4.w;
+    if (ACT == VQN_ACT_RELU) { t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f); t2 = fmaxf(t2, 0.f); t3 = fmaxf(t3, 0.f); }
+    if (ACT == VQN_ACT_SIGMOID) { t0 = fast_sigmoid(t0); t1 = fast_sigmoid(t1); t2 = fast_sigmoid(t2); t3 = fast_sigmoid(t3); }
+    v[j] = t0; v[j + 1] = t1; v[j + 2] = t2; v[j + 3] = t3;
+  }
+}
+__device__ __forceinline__ void bias_act32_dyn(float (&v)[32], const float* __restrict__ bias_s, int act) {
+  if (act == VQN_ACT_RELU) bias_act32<VQN_ACT_RELU>(v, bias_s);
+  else if (act == VQN_ACT_SIGMOID) bias_act32<VQN_ACT_SIGMOID>(v, bias_s);
+  else bias_act32<VQN_ACT_NONE>(v, bias_s);
+}
 
 // store 32 consecutive K values (columns j0 .. j0+31 of the chunk) of row r into the chunk slot
 template <bool BF16>
 __device__ __forceinline__ void store_chunk32(uint8_t* slot, int r, int j0, const float (&v)[32]) {
   if (BF16) {
-    // 32 values = 64 bytes = four 16-byte chunks starting at c16 = j0 / 8
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]);
@@ -214,38 +223,87 @@ __device__ __forceinline__ void store_chunk32(uint8_t* slot, int r, int j0, cons
       *reinterpret_cast<uint4*>(slot + tc::sw128_off(r, j0 / 8 + q)) = u;
     }
   } else {
+    uint8_t* row = slot + r * 128;
+    const uint32_t rx = (uint32_t)(r & 7);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       float h[4], l[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { h[i] = tc::tf32_rna(v[4 * q + i]); l[i] = tc::tf32_rna(v[4 * q + i] - h[i]); }
-      const uint32_t off = tc::sw128_off(r, j0 / 4 + q);
-      *reinterpret_cast<float4*>(slot + off) = make_float4(h[0], h[1], h[2], h[3]);
-      *reinterpret_cast<float4*>(slot + TC_M * 128 + off) = make_float4(l[0], l[1], l[2], l[3]);
+      const uint32_t off = (((uint32_t)(j0 / 4 + q)) ^ rx) << 4;
+      *reinterpret_cast<float4*>(row + off) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(row + TC_M * 128 + off) = make_float4(l[0], l[1], l[2], l[3]);
     }
   }
 }
 
+// one scalar K value (column `col` of the chunk) of row r
 template <bool BF16>
-__global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcProgram pg) {
+__device__ __forceinline__ void store_chunk1(uint8_t* slot, int r, int col, float v) {
+  if (BF16) {
+    *reinterpret_cast<__nv_bfloat16*>(slot + tc::sw128_off(r, col / 8) + (col % 8) * 2) = __float2bfloat16_rn(v);
+  } else {
+    const uint32_t off = tc::sw128_off(r, col / 4) + (col % 4) * 4;
+    const float h = tc::tf32_rna(v);
+    *reinterpret_cast<float*>(slot + off) = h;
+    *reinterpret_cast<float*>(slot + TC_M * 128 + off) = tc::tf32_rna(v - h);
+  }
+}
+
+// Embedder.__call__ (embedder.py:35-47) for the chunk covering embedding columns [col0, col0 + E):
+// [x, sin(x f0), cos(x f0), sin(x f1), ...], f_k = 2^k; written straight into the swizzled slot.
+template <bool BF16>
+__device__ __forceinline__ void embed_chunk(uint8_t* slot, int r, const float (&x)[3], int col0, int n_freqs) {
+  constexpr int E = BF16 ? 64 : 32;
+  const int d = 3 + 6 * n_freqs;
+  if (col0 == 0) {
+    store_chunk1<BF16>(slot, r, 0, x[0]); store_chunk1<BF16>(slot, r, 1, x[1]); store_chunk1<BF16>(slot, r, 2, x[2]);
+  }
+  int f_lo = col0 <= 3 ? 0 : (col0 - 3 - 5 + 5) / 6;       // first frequency with a column >= col0
+  if (f_lo > 0 && 3 + 6 * (f_lo - 1) + 5 >= col0) f_lo -= 1;
+  int f_hi = (col0 + E - 1 - 3) / 6;
+  if (f_hi > n_freqs - 1) f_hi = n_freqs - 1;
+  for (int f = f_lo; f <= f_hi; ++f) {
+    const float sc = exp2f((float)f);
+    float sn[3], cs[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sincosf(x[k] * sc, &sn[k], &cs[k]);
+    const int base = 3 + 6 * f - col0;                       // chunk-relative column of sin(x0 f)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (base + k >= 0 && base + k < E) store_chunk1<BF16>(slot, r, base + k, sn[k]);
+      if (base + 3 + k >= 0 && base + 3 + k < E) store_chunk1<BF16>(slot, r, base + 3 + k, cs[k]);
+    }
+  }
+  for (int col = (d > col0 ? d : col0); col < col0 + E; ++col) store_chunk1<BF16>(slot, r, col - col0, 0.f);
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcProgram pg) {
   using C = TcCfg<BF16>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t a_full[4], a_empty[4], w_full[4], w_empty[4], acc_full;
+  __shared__ __align__(8) uint64_t a_full[4], a_empty[4], w_full[4], w_empty[4], acc_full, drain_done;
   __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float bias_s[TC_BIAS_FLOATS];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_ring = smem;
   uint8_t* w_ring = smem + (size_t)C::SA * C::A_SLOT;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int MMA_WARP = 4 * C::G, W_WARP = 4 * C::G + 1;
 
-  if (warp == 4) tc::tmem_alloc(&tmem_base_s, 512);
+  if (warp == MMA_WARP) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) {
       tc::mbar_init(&a_full[i], 128); tc::mbar_init(&a_empty[i], 1);
       tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1);
     }
     tc::mbar_init(&acc_full, 1);
+    tc::mbar_init(&drain_done, 128 * C::G);
     tc::mbar_fence_init();
   }
+  // stage every layer's bias in shared memory (layer l at bias_off[l]; host guarantees the total fits)
+  for (int l = 0; l < pg.n_layers; ++l)
+    for (int i = tid; i < pg.layers[l].Npad; i += C::THREADS) bias_s[pg.layers[l].bias_off + i] = pg.layers[l].bias[i];
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -256,10 +314,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
   const long long n_tiles = (n + TC_M - 1) / TC_M;
   const int L = pg.n_layers;
 
-  if (warp < 4) {
-    // =========================== epilogue warps: A-chunk producers + accumulator drain ===========================
-    const int r = tid;                                   // TMEM lane == point row of the tile
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * warp) << 16);
+  if (warp < 4 * C::G) {
+    // ============== epilogue warp-groups: A-chunk producers + accumulator drain ==============
+    // group g produces the chunks with (global chunk index % G == g); all groups walk the same sequence
+    const int grp = warp >> 2;
+    const int r = 32 * (warp & 3) + lane;                // TMEM lane == point row of the tile
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
     uint32_t ga = 0;                                     // global A-chunk counter
     uint32_t gl = 0;                                     // global layer counter (acc_full phase)
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -271,49 +331,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         x[0] = pg.pts[row * 3]; x[1] = pg.pts[row * 3 + 1]; x[2] = pg.pts[row * 3 + 2];
       }
       for (int l = 0; l < L; ++l) {
-        const TcLayer& ly = pg.layers[l];
-        for (int sg = 0; sg < ly.nseg; ++sg) {
-          const int st = ly.seg_type[sg];
-          if (st == SRC_DRAIN) {
-            // the previous layer's accumulator must be complete
-            tc::mbar_wait(&acc_full, (gl - 1) & 1);
-            tc::fence_after_sync();
-          }
-          for (int c = 0; c < ly.seg_chunks[sg]; ++c, ++ga) {
+        const int nseg = pg.layers[l].nseg;
+        for (int sg = 0; sg < nseg; ++sg) {
+          const int st = pg.layers[l].seg_type[sg];
+          const int nch = pg.layers[l].seg_chunks[sg];
+          const int first = pg.layers[l].seg_first_chunk[sg];
+          const int pact = l > 0 ? pg.layers[l - 1].act : 0;
+          const float* pbias = bias_s + (l > 0 ? pg.layers[l - 1].bias_off : 0);
+          const uint32_t pacc = lane_addr + (uint32_t)(((l - 1) & 1) * 256);
+          bool acc_ready = false;
+          for (int c = 0; c < nch; ++c, ++ga) {
+            if ((int)(ga % C::G) != grp) continue;
+            if (st == SRC_DRAIN && !acc_ready) {
+              tc::mbar_wait(&acc_full, (gl - 1) & 1);    // previous layer's accumulator is complete
+              tc::fence_after_sync();
+              acc_ready = true;
+            }
             const int slot = ga % C::SA;
             tc::mbar_wait(&a_empty[slot], ((ga / C::SA) & 1) ^ 1);
             uint8_t* dst = a_ring + (size_t)slot * C::A_SLOT;
-            const int sc = ly.seg_first_chunk[sg] + c;   // chunk index inside the source
+            const int sc = first + c;                     // chunk index inside the source
+            if (st == SRC_EMBED) {
+              embed_chunk<BF16>(dst, r, x, sc * C::E, pg.n_freqs);
+            } else {
 #pragma unroll
-            for (int h = 0; h < C::E / 32; ++h) {
-              float v[32];
-              const int col0 = sc * C::E + 32 * h;       // first source column of this 32-wide piece
-              if (st == SRC_DRAIN) {
-                const TcLayer& pl = pg.layers[l - 1];
-                tc::tmem_ld32(lane_addr + (uint32_t)(((l - 1) & 1) * 256 + col0), v);
+              for (int h = 0; h < C::E / 32; ++h) {
+                float v[32];
+                const int col0 = sc * C::E + 32 * h;      // first source column of this 32-wide piece
+                if (st == SRC_DRAIN) {
+                  tc::tmem_ld32(pacc + (uint32_t)col0, v);
+                  bias_act32_dyn(v, pbias + col0, pact);
+                } else {                                  // SRC_GLOBAL: this thread's own latent row
+                  if (valid && col0 < pg.g_dim) {
+                    const float4* src = reinterpret_cast<const float4*>(pg.gsrc + pi * pg.g_dim + col0);
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(pl.bias + col0 + j));
-                  v[j] = vqn_apply_act(v[j] + b4.x, pl.act); v[j + 1] = vqn_apply_act(v[j + 1] + b4.y, pl.act);
-                  v[j + 2] = vqn_apply_act(v[j + 2] + b4.z, pl.act); v[j + 3] = vqn_apply_act(v[j + 3] + b4.w, pl.act);
-                }
-              } else if (st == SRC_EMBED) {
-#pragma unroll 4
-                for (int j = 0; j < 32; ++j) v[j] = embed_val(x, col0 + j, pg.n_freqs);
-              } else {  // SRC_GLOBAL: this thread's own latent row
-                if (valid && col0 < pg.g_dim) {
-                  const float4* src = reinterpret_cast<const float4*>(pg.gsrc + pi * pg.g_dim + col0);
+                    for (int j = 0; j < 8; ++j) {
+                      float4 t = src[j];
+                      v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+                    }
+                  } else {
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    float4 t = src[j];
-                    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+                    for (int j = 0; j < 32; ++j) v[j] = 0.f;
                   }
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) v[j] = 0.f;
                 }
+                store_chunk32<BF16>(dst, r, 32 * h, v);
               }
-              store_chunk32<BF16>(dst, r, 32 * h, v);
             }
             tc::fence_proxy_async();       // generic-proxy stores -> visible to the UMMA (async proxy)
             tc::fence_before_sync();       // order the tcgen05.ld's above before the hand-off
@@ -321,20 +383,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           }
         }
         ++gl;                               // layer l's chunks are all queued
-        if (ly.out_slot >= 0) {
-          // final layer of a network: drain its accumulator to global memory
+        if (pg.layers[l].out_slot >= 0) {
+          // final layer of a network: drain its accumulator to global memory (column blocks split over groups)
+          const TcLayer& ly = pg.layers[l];
           tc::mbar_wait(&acc_full, (gl - 1) & 1);
           tc::fence_after_sync();
           float* go = pg.outs[ly.out_slot];
           const int gs = pg.out_stride[ly.out_slot];
-          for (int cb = 0; cb * 32 < ly.N; ++cb) {
+          const float* lb = bias_s + ly.bias_off;
+          for (int cb = grp; cb * 32 < ly.N; cb += C::G) {
             float v[32];
             tc::tmem_ld32(lane_addr + (uint32_t)((l & 1) * 256 + cb * 32), v);
+            if (cb * 32 + 32 <= ly.Npad) bias_act32_dyn(v, lb + cb * 32, ly.act);
+            else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float b = (cb * 32 + j < ly.Npad) ? lb[cb * 32 + j] : 0.f;
+                float t = v[j] + b;
+                v[j] = ly.act == VQN_ACT_RELU ? fmaxf(t, 0.f) : (ly.act == VQN_ACT_SIGMOID ? fast_sigmoid(t) : t);
+              }
+            }
             bool bad = false;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              float b = (cb * 32 + j < ly.Npad) ? __ldg(ly.bias + cb * 32 + j) : 0.f;
-              v[j] = vqn_apply_act(v[j] + b, ly.act) * ly.post_scale + ly.post_bias;
+              v[j] = v[j] * ly.post_scale + ly.post_bias;
               bad |= (cb * 32 + j < ly.N) && !isfinite(v[j]);
             }
             if (valid) {
@@ -351,19 +423,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             }
           }
           tc::fence_before_sync();
+          tc::mbar_arrive(&drain_done);     // the MMA thread may now reuse this TMEM region
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == MMA_WARP) {
     // =========================== MMA issuer (one thread) ===========================
     if (lane == 0) {
-      uint32_t ga = 0, gw = 0;
+      uint32_t ga = 0, gw = 0, gd = 0;
+      bool pending_drain = false;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int l = 0; l < L; ++l) {
           const TcLayer& ly = pg.layers[l];
           const uint32_t idesc = tc::make_idesc(BF16 ? tc::FMT_BF16 : tc::FMT_TF32, TC_M, ly.Npad);
           const uint32_t d_tmem = tmem_base + (uint32_t)((l & 1) * 256);
           const int nch = ly.seg_chunks[0] + (ly.nseg > 1 ? ly.seg_chunks[1] : 0);
+          const uint32_t w_plane = (uint32_t)ly.Npad * 128;
+          if (pending_drain) {              // a final layer is being drained to global: wait before any overwrite
+            tc::mbar_wait(&drain_done, gd & 1);
+            tc::fence_after_sync();
+            ++gd; pending_drain = false;
+          }
           uint32_t acc = 0;
           for (int c = 0; c < nch; ++c, ++ga, ++gw) {
             const int sa = ga % C::SA, sw = gw % C::SW;
@@ -372,7 +452,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             tc::fence_after_sync();
             const uint32_t a_addr = tc::smem_u32(a_ring + (size_t)sa * C::A_SLOT);
             const uint32_t w_addr = tc::smem_u32(w_ring + (size_t)sw * C::W_SLOT);
-            const uint32_t w_plane = (uint32_t)ly.Npad * 128;
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
               const uint64_t a_hi = tc::make_desc_sw128(a_addr + 32 * s);
@@ -390,6 +469,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             tc::mma_commit(&w_empty[sw]);
           }
           tc::mma_commit(&acc_full);            // layer complete -> epilogue warps may drain it
+          if (ly.out_slot >= 0) pending_drain = true;
         }
       }
     }
@@ -416,7 +496,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 4) tc::tmem_dealloc(tmem_base, 512);
+  if (warp == MMA_WARP) tc::tmem_dealloc(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -464,16 +544,20 @@ static bool tc_append_net(TcBuilder& B, vqn_net* net, TcPack* tp, int first_src,
 
 static int tc_launch(vqn_ctx* ctx, TcProgram& pg, int precision, cudaStream_t s) {
   pg.nonfinite = ctx->nonfinite_flag;
+  int boff = 0;
+  for (int l = 0; l < pg.n_layers; ++l) { pg.layers[l].bias_off = boff; boff += vqn_round_up(pg.layers[l].Npad, 32); }
+  if (boff > TC_BIAS_FLOATS) { vqn_set_error("tensor-core MLP: bias table exceeds %d floats", TC_BIAS_FLOATS); return VQN_ERR_UNSUPPORTED; }
+  if (pg.pts && 3 + 6 * pg.n_freqs > 64) { vqn_set_error("tensor-core MLP: embedding wider than 64"); return VQN_ERR_UNSUPPORTED; }
   long long tiles = (pg.n + TC_M - 1) / TC_M;
   int blocks = (int)(tiles < (long long)ctx->sm_count ? tiles : (long long)ctx->sm_count);
   if (precision == VQN_PREC_BF16) {
     size_t smem = TcCfg<true>::SMEM;
     VQN_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_tc_kernel<true><<<blocks, TC_THREADS, smem, s>>>(pg);
+    mlp_tc_kernel<true><<<blocks, TcCfg<true>::THREADS, smem, s>>>(pg);
   } else {
     size_t smem = TcCfg<false>::SMEM;
     VQN_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_tc_kernel<false><<<blocks, TC_THREADS, smem, s>>>(pg);
+    mlp_tc_kernel<false><<<blocks, TcCfg<false>::THREADS, smem, s>>>(pg);
   }
   VQN_LAUNCHED(ctx);
   return VQN_OK;

@@ -29,7 +29,10 @@ _DEFAULTS = {
     'data_type': 'nerf', 'no_brdf_chunk': 'True', 'random_seed': '2', 'pred_brdf': 'True', 'conv_width': '256',
     'mlp_width': '128', 'mlp_chunk': '100000', 'n_freqs_xyz': '10', 'light_h': '16', 'num_embed': '15',
     'commitment_cost': '0.1', 'albedo_slope': '1', 'albedo_bias': '0', 'brdf_chunk_size': '50000',
-    'pos_enc': 'True', 'precision': 'fp32',
+    'pos_enc': 'True',
+    # MLP arithmetic: 'tf32x3' = tcgen05 3xTF32 split with fp32 accumulation (fp32 parity, default),
+    # 'fp32' = FFMA on CUDA cores, 'bf16' = tcgen05 bf16 operands (1e-2 budget)
+    'precision': 'tf32x3',
 }
 
 
