@@ -212,7 +212,8 @@ int vqn_srgb2linear(vqn_ctx* ctx, const float* x, int64_t count, float* out, vqn
 /* mask = alpha[:,0] > 0 ; ind = where(mask) (vq_nfr.py:283,345): row_idx[int32, n_total] and the
  * device count n_active[1]; no host synchronisation. */
 int vqn_compact_mask(vqn_ctx* ctx, const float* alpha, int64_t n_total, int32_t* row_idx,
-                     int32_t* n_active, vqn_stream stream);
+                     int32_t* n_active, int32_t* workspace /* >= n_total/1024 + 1 ints, or NULL: ctx scratch
+                     (then only one compaction may be in flight per ctx) */, vqn_stream stream);
 
 /* scatter_nd(ind, value, (n_total,c)) (vq_nfr.py:347-370): out must be pre-zeroed full length */
 int vqn_scatter_rows(vqn_ctx* ctx, const float* compact, const int32_t* row_idx, const int32_t* n_dev,

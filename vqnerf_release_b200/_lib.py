@@ -84,7 +84,7 @@ SIGNATURES = {
     'vqn_material_combine': (_I, [_P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P]),
     'vqn_linear2srgb': (_I, [_P, _P, _L, _P, _P]),
     'vqn_srgb2linear': (_I, [_P, _P, _L, _P, _P]),
-    'vqn_compact_mask': (_I, [_P, _P, _L, _P, _P, _P]),
+    'vqn_compact_mask': (_I, [_P, _P, _L, _P, _P, _P, _P]),
     'vqn_scatter_rows': (_I, [_P, _P, _P, _P, _L, _I, _P, _P]),
     'vqn_neus_up_sample': (_I, [_P, _P, _P, _P, _P, _L, _I, _F, _I, _F, _P, _P]),
     'vqn_neus_cat_z_vals': (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _P, _P, _P]),

@@ -325,8 +325,10 @@ def compact_mask(alpha: torch.Tensor):
     n = a.shape[0]
     row_idx = torch.empty((max(n, 1),), dtype=torch.int32, device=a.device)
     n_active = torch.zeros((1,), dtype=torch.int32, device=a.device)
+    work = torch.empty((n // 1024 + 2,), dtype=torch.int32, device=a.device)   # per-call: safe across streams
     c = _ctx(a)
-    L.check(c.lib.vqn_compact_mask(c.handle, L.ptr(a), n, L.ptr(row_idx), L.ptr(n_active), L.stream_ptr(a.device)))
+    L.check(c.lib.vqn_compact_mask(c.handle, L.ptr(a), n, L.ptr(row_idx), L.ptr(n_active), L.ptr(work),
+                                   L.stream_ptr(a.device)))
     return row_idx, n_active
 
 

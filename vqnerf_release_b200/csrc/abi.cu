@@ -295,13 +295,13 @@ __global__ void compact_scatter_kernel(const float* __restrict__ alpha, long lon
 }
 
 extern "C" int vqn_compact_mask(vqn_ctx* ctx, const float* alpha, int64_t n, int32_t* row_idx,
-                                int32_t* n_active, vqn_stream s) {
+                                int32_t* n_active, int32_t* workspace, vqn_stream s) {
   VQN_CHECK_ARG(ctx && n_active && n >= 0 && n < (1LL << 31), "compact_mask args");
   int n_blocks = (int)((n + CMP_BLOCK - 1) / CMP_BLOCK);
   if (n_blocks == 0) { VQN_CUDA(cudaMemsetAsync(n_active, 0, sizeof(int), vqn_cs(s))); return VQN_OK; }
   VQN_CHECK_ARG(alpha && row_idx, "compact_mask: null alpha / row_idx");
-  VQN_CHECK_ARG((size_t)n_blocks + 16 <= ctx->scratch_ints, "compact_mask: more than 64 M rows");
-  int* counts = ctx->scratch + 16;   // persistent scratch: stream-ordered, one compaction in flight per ctx
+  VQN_CHECK_ARG(workspace || (size_t)n_blocks + 16 <= ctx->scratch_ints, "compact_mask: more than 64 M rows");
+  int* counts = workspace ? workspace : ctx->scratch + 16;   // ctx scratch: one compaction in flight per ctx
   compact_count_kernel<<<n_blocks, CMP_BLOCK, 0, vqn_cs(s)>>>(alpha, n, counts);
   VQN_LAUNCHED(ctx);
   compact_scan_kernel<<<1, 1024, 0, vqn_cs(s)>>>(counts, n_blocks, n_active);

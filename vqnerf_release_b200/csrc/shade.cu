@@ -26,6 +26,10 @@ struct ShadeParams {
   int* nonfinite;
 };
 
+// single-MUFU approximations (<= 2 ulp): the per-light chain tolerates them within the 1e-4 budget
+__device__ __forceinline__ float fast_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 __device__ __forceinline__ float gsub_f(float c, float a2) {
   // util/microfacet.py:49-69: 2c / (c + sqrt(|a2 + (1-a2) c^2|)), divide_no_nan
   float den = c + sqrtf(fabsf(a2 + (1.0f - a2) * c * c));
@@ -128,6 +132,7 @@ __global__ void __launch_bounds__(SH_THREADS, 2) shade_kernel(ShadeParams P) {
     const float avn = fabsf(vn);
     // S = D g_l g_v / (4 |l.n| |v.n|) = a_pt * cl / (q^2 den_l |l.n|),  a_pt = a2 g_v / (2 pi |v.n|)
     const float a_pt = avn == 0.f ? 0.f : a2 * g_v * (0.5f * INV_PI) / avn;
+    const float oma2 = 1.0f - a2, a2m1 = a2 - 1.0f;
 
     // ---- phase 1: per-light, per-channel effective weights e = F S w + albedo/pi w (probe independent) ----
     float e[16][3];
@@ -143,22 +148,22 @@ __global__ void __launch_bounds__(SH_THREADS, 2) shade_kernel(ShadeParams P) {
       for (int q = 0; q < 4; ++q) {
         const int li = 4 * j + q;
         float dx = xs4[q] - px, dy = ys4[q] - py, dz = zs4[q] - pz;
-        float inv = rsqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-6f));   // _calc_ldir
+        float inv = fast_rsqrt(fmaxf(dx * dx + dy * dy + dz * dz, 1e-6f));   // _calc_ldir
         dx *= inv; dy *= inv; dz *= inv;
         const float cos_r = dx * nx + dy * ny + dz * nz;                  // _render: cos = l . n
         const float ln = cos_r * inv_n;                                   // get_brdf: l . normalize(n)
         const float lv = dx * vx + dy * vy + dz * vz;
         // h = normalize(l + v): |l + v|^2 = 2 + 2 l.v for unit l, v
         const float t = 1.0f + lv;
-        const float hinv = rsqrtf(fmaxf(2.0f * t, 1e-6f));
+        const float hinv = fast_rsqrt(fmaxf(2.0f * t, 1e-6f));
         const float hv = fminf(fmaxf(t * hinv, 0.f), 1.f);                // h . v
         const float hn = fminf(fmaxf((ln + vn) * hinv, 0.f), 1.f);        // h . n
         const float om = 1.0f - hv;
         const float om2 = om * om;
         const float p5 = om2 * om2 * om;                                  // (1 - h.v)^5
-        const float q_ = hn * hn * (a2 - 1.0f) + 1.0f;                    // _get_d denominator core
+        const float q_ = fmaf(hn * hn, a2m1, 1.0f);                       // _get_d denominator core
         const float cl = fminf(fmaxf(ln, 0.f), 1.f);
-        const float den_l = cl + sqrtf(fabsf(a2 + (1.0f - a2) * cl * cl));
+        const float den_l = cl + fast_sqrt(fabsf(fmaf(oma2, cl * cl, a2)));
         const float den = q_ * q_ * den_l * fabsf(ln);
         const float S = den == 0.f ? 0.f : __fdividef(a_pt * cl, den);
         float wv = cos_r > 0.f ? cos_r : 0.f;                              // front_lit * cos

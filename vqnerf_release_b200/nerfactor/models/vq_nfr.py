@@ -371,6 +371,53 @@ class Model:
             to_vis['gt_' + k] = v
         return pred, gt, loss_kwargs, to_vis
 
+    # ------------------------------------------------------------------ host-buffer entry point
+    def fast_render_host(self, batch, n_chunks=8, out=None, **kw):
+        """`fast_render` for a batch whose tensors live in (pinned) HOST memory, as the reference's tf.data pipeline
+        delivers them (datasets/shape_unit.py:93-110): the view is cut into `n_chunks` contiguous row blocks that are
+        copied, shaded and copied back on two alternating CUDA streams, so the H2D transfer of block i+1 overlaps the
+        kernels of block i.  Returns the `pred` dict with pinned host tensors (`out` may pass a previous result to
+        reuse its buffers).  Same keyword arguments as fast_render."""
+        ref_batch = kw.get('ref_batch', False)
+        id_, hw, rayo, rayd, rgb, alpha, pred_alpha, xyz, normal, lvis = self._unpack(batch, ref_batch)
+        n_total = alpha.shape[0]
+        dev = self.device
+        if not hasattr(self, '_host_streams'):
+            self._host_streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+        streams = self._host_streams
+        main = torch.cuda.current_stream(dev)
+        for s in streams:
+            s.wait_stream(main)
+        bounds = [(n_total * i) // n_chunks for i in range(n_chunks + 1)]
+        res = out if out is not None else {}
+        zeros2 = torch.zeros((1, 2), dtype=torch.int32, device=dev)
+        for ci in range(n_chunks):
+            a, b = bounds[ci], bounds[ci + 1]
+            if b <= a:
+                continue
+            st = streams[ci % 2]
+            with torch.cuda.stream(st):
+                up = lambda t: None if t is None else t[a:b].to(dev, non_blocking=True)
+                d_rayo, d_alpha, d_xyz, d_normal, d_lvis = up(rayo), up(alpha), up(xyz), up(normal), up(lvis)
+                # rgb / pred_alpha are pass-through ground truth: they stay on the host
+                dummy3 = d_xyz
+                sub = [id_, zeros2, d_rayo, dummy3, dummy3, d_alpha, d_alpha, d_xyz, d_normal]
+                if ref_batch:
+                    sub.append(dummy3)
+                if self.data_type == 'nerf':
+                    sub.append(d_lvis)
+                pred, _, _, _ = self.fast_render(tuple(sub), **kw)
+                for k, v in pred.items():
+                    if k == 'alpha' or not torch.is_tensor(v):
+                        continue
+                    if k not in res:
+                        res[k] = torch.empty((n_total,) + tuple(v.shape[1:]), dtype=v.dtype).pin_memory()
+                    res[k][a:b].copy_(v if v.is_contiguous() else v.contiguous(), non_blocking=True)
+        for s in streams:
+            main.wait_stream(s)
+        res['alpha'] = pred_alpha
+        return res
+
     # ------------------------------------------------------------------ vis_mat (vq_nfr.py:400-465)
     def vis_mat(self, batch, mode='train', opt_scale=None, ref_batch=False, thres=None, roll=None):
         self._validate_mode(mode)
