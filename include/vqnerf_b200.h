@@ -219,6 +219,69 @@ int vqn_compact_mask(vqn_ctx* ctx, const float* alpha, int64_t n_total, int32_t*
 int vqn_scatter_rows(vqn_ctx* ctx, const float* compact, const int32_t* row_idx, const int32_t* n_dev,
                      int64_t n_max, int c, float* out, vqn_stream stream);
 
+/* ---- training step (BASELINE config #4): Model.call(mode='train') + compute_loss under tf.GradientTape and
+ * the Adam(amsgrad) update (models/vq_nfr.py:534-692, 876-986; train_nfr.py:121-139, 562-576) -------------- */
+/* Keras Dense forward with the output kept for the backward pass (networks/mlp.py:44-46):
+ * Y[m,n] (leading dim ldy) = out_scale * act(X[m,k] (leading dim ldx) . W[k,n] + b[n]) + out_bias.  Leading
+ * dimensions let a layer read/write a column slice of the concat buffer of a skip connection (mlp.py:47-48). */
+int vqn_dense_forward(vqn_ctx* ctx, const float* x, int64_t ldx, const float* w, const float* b, float* y,
+                      int64_t ldy, int64_t m, int k, int n, int act, float out_scale, float out_bias,
+                      vqn_stream stream);
+/* dX[m,k] (+)= (dZ[m,n] . W[k,n]^T) * act_prev'(Yprev[m,k]); act_prev' is taken from the stored activation
+ * (relu: y > 0, sigmoid: y (1 - y)); accumulate != 0 adds into dX (several consumers of one tensor). */
+int vqn_dense_backward_data(vqn_ctx* ctx, const float* dz, int64_t lddz, const float* w, float* dx, int64_t lddx,
+                            const float* yprev, int64_t ldyp, int act_prev, int accumulate, int64_t m, int k, int n,
+                            vqn_stream stream);
+/* dW[k,n] += X[m,k]^T . dZ[m,n];  db[n] += colsum(dZ)  (gradient buffers are accumulated: zero them per step) */
+int vqn_dense_backward_weights(vqn_ctx* ctx, const float* x, int64_t ldx, const float* dz, int64_t lddz, float* dw,
+                               float* db, int64_t m, int k, int n, vqn_stream stream);
+/* dZ = scale * dY * act'(Y) through a net's LAST activation; Y is stored as out_scale * act(.) + out_bias */
+int vqn_act_backward(vqn_ctx* ctx, const float* dy, int64_t lddy, const float* y, int64_t ldy, int64_t m, int n,
+                     int act, float scale, float out_scale, float out_bias, float* dz, int64_t lddz,
+                     vqn_stream stream);
+/* dst[:, 0:w] (leading dim ldd) = src[:, 0:w] (leading dim lds): the x half of concat(y, x) (mlp.py:47-48) */
+int vqn_copy_cols(vqn_ctx* ctx, const float* src, int64_t lds, float* dst, int64_t ldd, int64_t m, int w,
+                  vqn_stream stream);
+/* Backward of vqn_shade for probe 0 (linear rgb; clip_by_value_preserve_gradient has identity gradient,
+ * vq_nfr.py:718,759): d_rgb [n,3] compact -> d_albedo [n,3], d_spec [n,3], d_rough [n,1] compact and
+ * d_light [512,3] (ACCUMULATED over points and calls; gradient w.r.t. the raw _light variable). */
+int vqn_shade_backward(vqn_ctx* ctx, const float* xyz, const float* rayo, const float* normal, const float* lvis,
+                       const int32_t* row_idx, int64_t n, const float* albedo, const float* spec, const float* rough,
+                       const float* lxyz, const float* lareas, const float* light, int clip_light0,
+                       const float* d_rgb, float* d_albedo, float* d_spec, float* d_rough, float* d_light,
+                       vqn_stream stream);
+/* compute_loss(mode='train') (vq_nfr.py:923-986) per example, without the two broadcast scalars (vqloss,
+ * sim_smooth), and the gradients of sum(loss) * inv_global_bs (tf.nn.compute_average_loss, train_nfr.py:571)
+ * w.r.t. rgb, vq_rgb, z_vq (pair smoothness) and spec (lambert).  Rows are (pixel, neighbour) pairs: n even.
+ * sums[6] (optional, accumulated): rgb, vqrgb, chromaticity, chr_smooth, lambert, total. */
+int vqn_loss_train(vqn_ctx* ctx, const float* gtc, const float* rgb, const float* vqrgb, const float* z_vq,
+                   const float* spec, const float* rough, int64_t n, int z_dim, int data_is_nerf,
+                   float combine_weight, float chromaticity_weight, float mat_sloss_weight, float lambert_weight,
+                   float chr_alpha, float chr_thres, float inv_global_bs, float* loss_rows, float* d_rgb,
+                   float* d_vqrgb, float* d_z, float* d_spec, float* sums, vqn_stream stream);
+/* Backward of l2_normalize + VectorQuantizerEMA (vq_nfr.py:575-577, vq_layers.py:302,321,327): straight-through
+ * d z_norm = d z_vq, plus the commitment term commit_coef * (z_norm - codebook[:,idx]) with
+ * commit_coef = vq_loss_weight * commitment_cost * 2 / (global_bs * Z), through x * rsqrt(max(|x|^2, 1e-6)). */
+int vqn_vq_backward(vqn_ctx* ctx, const float* z_enc, const int64_t* indices, const float* codebook, int k,
+                    const float* d_zvq, float commit_coef, int64_t n, int accumulate, float* d_zenc,
+                    vqn_stream stream);
+/* spec = ks*basecolor, albedo = (1-ks)*basecolor backward (vq_nfr.py:590-591); d_spec_extra (optional) is added
+ * to d_spec (the lambert term). */
+int vqn_material_combine_backward(vqn_ctx* ctx, const float* basecolor, const float* ks, const float* d_albedo,
+                                  const float* d_spec, const float* d_spec_extra, int64_t n, float* d_basecolor,
+                                  float* d_ks, vqn_stream stream);
+/* sim_smooth (vq_nfr.py:958-972) on get_codebook(raw): loss_out[1] = -log(min_{i!=j} |c_i - c_j|) (unweighted),
+ * d_raw[Z,K] (+)= grad_scale * d loss / d raw. */
+int vqn_codebook_sim_loss(vqn_ctx* ctx, const float* raw_codebook, int z_dim, int k, float grad_scale,
+                          float* loss_out, float* d_raw, int accumulate, vqn_stream stream);
+/* tf.keras.optimizers.Adam(amsgrad=True) dense update on a flat parameter buffer (train_nfr.py:121-139);
+ * lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t) is computed by the caller. */
+int vqn_adam_amsgrad(vqn_ctx* ctx, float* param, const float* grad, float* m, float* v, float* vhat, int64_t count,
+                     float lr_t, float beta1, float beta2, float epsilon, vqn_stream stream);
+/* VQ statistics (float64) <-> the fp32 tail of the flat all-reduce buffer */
+int vqn_cast_f64_f32(vqn_ctx* ctx, const double* src, float* dst, int64_t count, vqn_stream stream);
+int vqn_cast_f32_f64(vqn_ctx* ctx, const float* src, double* dst, int64_t count, vqn_stream stream);
+
 /* ---- NeuS geo stage (secondary path) -------------------------------------------------------- */
 /* NeuSRenderer.up_sample (geo/NeuS-ours2/models/renderer.py:131-175) incl. sample_pdf(det=True)
  * (:39-69): z_samples[B,n_importance] from z_vals[B,S], sdf[B,S]. One warp per ray. */

@@ -381,6 +381,8 @@ class Scene:
 
 
 def _t(a, dt):
+    if isinstance(a, torch.Tensor):       # autograd leaves of train_step() pass through
+        return a.to(dt)
     return torch.as_tensor(np.asarray(a), dtype=dt)
 
 
@@ -467,7 +469,7 @@ def call_forward(scene: Scene, batch: Dict[str, np.ndarray], vq: VectorQuantizer
     basecolor = pred_head(scene.nets, 'diff_main', z_enc, scene.albedo_slope, scene.albedo_bias)
     ks = pred_head(scene.nets, 'spec_main', z_enc)
     spec, albedo = ks * basecolor, (1 - ks) * basecolor
-    light = torch.clamp(_t(scene.light, dt), min=0.0)
+    light = clip_preserve_grad(_t(scene.light, dt), 0.0, float('inf'))             # :759
     gamma = None if scene.data_type == 'nerf' else scene.gamma
     brdf, brdf_spec, brdf_diff = get_brdf(surf2l, surf2c, normal_pred, albedo, rough, spec)
     rgb_pred, _ = render(brdf, surf2l, normal_pred, lareas, light, lvis, None, gamma)
@@ -488,6 +490,136 @@ def call_forward(scene: Scene, batch: Dict[str, np.ndarray], vq: VectorQuantizer
     out.update({'vq_rgb_linear': vq_rgb, 'vq_albedo': vq_albedo, 'vq_spec': vq_spec,
                 'vq_rough': vq_rough, 'mask': mask})
     return out
+
+
+# ----------------------------------------------------------------------------
+# training step: compute_loss (models/vq_nfr.py:876-986) + train_iter (train_nfr.py:562-576)
+# ----------------------------------------------------------------------------
+@dataclass
+class LossConfig:
+    """nerfactor/config/vq_nfr.ini:115-131"""
+    vq_loss_weight: float = 1.0
+    chr_alpha: float = 60.0
+    chr_thres: float = 0.1
+    combine_weight: float = 0.2
+    mat_sloss_weight: float = 0.05
+    chromaticity_loss_weight: float = 1.0
+    sim_loss_weight: float = 1e-4
+    lambert_weight: float = 1e-3
+
+
+def rgb2chromaticity(rgb: torch.Tensor) -> torch.Tensor:
+    """models/vq_nfr.py:1135-1137"""
+    denom = torch.sqrt(torch.sum(rgb * rgb, dim=-1, keepdim=True))
+    return divide_no_nan(rgb, denom)
+
+
+def mse(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """tf.keras.losses.MSE: mean over the last axis -> per-row [n]."""
+    return torch.mean((a - b) ** 2, dim=-1)
+
+
+def sim_loss(codebook_raw: torch.Tensor) -> torch.Tensor:
+    """models/vq_nfr.py:958-972: -log(min_{i != j} ||c_i - c_j||) on the normalised codebook.
+    DEVIATION (documented in DESIGN.md): tf.sqrt's gradient at the K diagonal zeros is 0 * 0.5/0 = NaN in
+    TF (and in torch); the masked product gives those entries zero weight, so the oracle and the product
+    define their contribution as 0 (sqrt is only taken off the diagonal)."""
+    cb = get_codebook(codebook_raw).t()                                     # [K,Z]
+    k = cb.shape[0]
+    sq = torch.sum((cb[:, None, :] - cb[None, :, :]) ** 2, dim=-1)
+    eye = torch.eye(k, dtype=cb.dtype)
+    dist = torch.sqrt(sq + eye) * (1 - eye)                                 # == sqrt(sq) off the diagonal
+    max_value = torch.max(dist)
+    masked = dist * (1 - eye) + eye * max_value
+    return -torch.log(torch.min(masked))
+
+
+def compute_loss(mode: str, gtc, rgb, vqrgb, vqloss=None, z=None, spec=None, rough=None,
+                 codebook_raw=None, cfg: LossConfig = LossConfig(), data_type: str = 'nerf'):
+    """models/vq_nfr.py:876-986.  Returns (per-example loss [n], loss_dict).  `codebook_raw` is the
+    `_codebook` variable AFTER the EMA assign of the forward pass (get_codebook() is re-evaluated here)."""
+    if data_type == 'nerf':
+        linear_gt, srgb_pred = srgb2linear(gtc), linear2srgb(rgb)
+    else:
+        linear_gt, srgb_pred = gtc, rgb
+    ld = {}
+    if mode != 'train':
+        ld['rgb'] = mse(gtc, srgb_pred)
+        ld['vqrgb'] = mse(gtc, linear2srgb(vqrgb))
+        ld['chromaticity'] = mse(rgb2chromaticity(linear_gt), rgb2chromaticity(vqrgb))
+        return ld['rgb'] + ld['vqrgb'] + ld['chromaticity'], ld
+    ld['rgb'] = cfg.combine_weight * mse(linear_gt, rgb)
+    loss = ld['rgb']
+    ld['vqrgb'] = mse(linear_gt, vqrgb)
+    loss = loss + ld['vqrgb']
+    ld['vqloss'] = cfg.vq_loss_weight * vqloss
+    loss = loss + ld['vqloss']
+    schr_gt = rgb2chromaticity(gtc)
+    if cfg.chromaticity_loss_weight > 0:
+        ld['chromaticity'] = cfg.chromaticity_loss_weight * mse(rgb2chromaticity(linear_gt),
+                                                                rgb2chromaticity(vqrgb))
+        loss = loss + ld['chromaticity']
+    if cfg.mat_sloss_weight > 0:
+        chr1, chr2 = schr_gt[::2, :], schr_gt[1::2, :]
+        chr_e = torch.sqrt(torch.sum((chr1 - chr2) ** 2, dim=-1))
+        chr_e = torch.where(chr_e > cfg.chr_thres, chr_e, torch.zeros_like(chr_e))
+        w_chr = torch.exp(-cfg.chr_alpha * chr_e)
+        mat1, mat2 = z[::2, :], z[1::2, :]
+        chr_sl = w_chr * (1.0 - torch.sum(mat1 * mat2, dim=-1))
+        chr_sl = torch.stack((chr_sl, chr_sl), dim=-1).reshape(-1)
+        ld['chr_smooth'] = cfg.mat_sloss_weight * chr_sl
+        loss = loss + ld['chr_smooth']
+    if cfg.sim_loss_weight > 0:
+        ld['sim_smooth'] = cfg.sim_loss_weight * sim_loss(codebook_raw)
+        loss = loss + ld['sim_smooth']
+    if cfg.lambert_weight > 0:
+        sg_rough = rough.detach()
+        sg_rough = torch.where(sg_rough < 0.5, torch.zeros_like(sg_rough), 2 * sg_rough - 1.0)
+        ld['lambert'] = cfg.lambert_weight * torch.max(spec, dim=-1).values * sg_rough[:, 0]
+        loss = loss + ld['lambert']
+    ld['loss'] = loss
+    return loss, ld
+
+
+def train_step(scene: Scene, batch: Dict[str, np.ndarray], vq: VectorQuantizerEMA, thres=None, roll=None,
+               cfg: LossConfig = LossConfig(), global_bs: Optional[int] = None, dtype=torch.float64):
+    """train_nfr.py:562-576 train_iter, gradients by autograd over the float64 restatement of
+    Model.call(mode='train') + compute_loss.  weighted_loss = sum(per_example_loss) / global_bs
+    (tf.nn.compute_average_loss).  Returns loss, per-variable gradients, the EMA codebook update and the
+    forward outputs.  Mutates `vq` (EMA state) like the reference's forward."""
+    dt = dtype
+    leaf = lambda a: torch.as_tensor(np.asarray(a), dtype=dt).clone().requires_grad_(True)
+    nets_t = {k: Net([leaf(w) for w in n.weights], [leaf(b) for b in n.biases], n.acts, n.skip_at)
+              for k, n in scene.nets.items()}
+    light_t = leaf(scene.light)
+    sc = Scene(nets=nets_t, light=light_t, codebook=scene.codebook, probes=None,
+               albedo_slope=scene.albedo_slope, albedo_bias=scene.albedo_bias, data_type=scene.data_type,
+               gamma=scene.gamma, lxyz=scene.lxyz, lareas=scene.lareas)
+    out = call_forward(sc, batch, vq, 'train', thres, roll, dt)
+    cb_after = leaf(out['update'].detach().numpy())                 # _codebook.assign(update) (:582-583)
+    mask = out['mask']
+    gtc = _t(batch['rgb'], dt)[mask]
+    loss, ld = compute_loss('train', gtc, out['rgb_linear'], out['vq_rgb_linear'], out['vq_loss'], out['z_vq'],
+                            out['spec'], out['rough'], cb_after, cfg, scene.data_type)
+    n_rows = loss.shape[0]
+    gbs = float(global_bs if global_bs is not None else n_rows)
+    weighted = torch.sum(loss) / gbs
+    weighted.backward()
+    grads = {k: ([w.grad for w in n.weights], [b.grad for b in n.biases]) for k, n in nets_t.items()}
+    return {'loss': weighted.detach(), 'per_example': loss.detach(), 'loss_dict': {k: v.detach() for k, v in ld.items()},
+            'grads': grads, 'dlight': light_t.grad, 'dcodebook': cb_after.grad, 'update': out['update'].detach(),
+            'out': {k: (v.detach() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}}
+
+
+def adam_amsgrad(param, grad, m, v, vhat, step: int, lr: float, beta1=0.9, beta2=0.999, eps=1e-7):
+    """tf.keras.optimizers.Adam(amsgrad=True) dense update (TF 2.4 optimizer_v2/adam.py):
+    lr_t = lr sqrt(1-b2^t)/(1-b1^t); m,v EMAs; vhat = max(vhat, v); p -= lr_t m / (sqrt(vhat) + eps).
+    `step` is the 1-based iteration count after the increment.  Returns (param, m, v, vhat)."""
+    lr_t = lr * math.sqrt(1.0 - beta2 ** step) / (1.0 - beta1 ** step)
+    m = m + (grad - m) * (1.0 - beta1)
+    v = v + (grad * grad - v) * (1.0 - beta2)
+    vhat = torch.maximum(vhat, v)
+    return param - lr_t * m / (torch.sqrt(vhat) + eps), m, v, vhat
 
 
 # ----------------------------------------------------------------------------

@@ -90,6 +90,19 @@ SIGNATURES = {
     'vqn_neus_cat_z_vals': (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _P, _P, _P]),
     'vqn_neus_composite': (_I, [_P, C.POINTER(NeusCompositeArgs), _P]),
     'vqn_neus_mid_points': (_I, [_P, _P, _P, _P, _L, _I, _F, _P, _P, _P]),
+    'vqn_dense_forward': (_I, [_P, _P, _L, _P, _P, _P, _L, _L, _I, _I, _I, _F, _F, _P]),
+    'vqn_dense_backward_data': (_I, [_P, _P, _L, _P, _P, _L, _P, _L, _I, _I, _L, _I, _I, _P]),
+    'vqn_dense_backward_weights': (_I, [_P, _P, _L, _P, _L, _P, _P, _L, _I, _I, _P]),
+    'vqn_act_backward': (_I, [_P, _P, _L, _P, _L, _L, _I, _I, _F, _F, _F, _P, _L, _P]),
+    'vqn_copy_cols': (_I, [_P, _P, _L, _P, _L, _L, _I, _P]),
+    'vqn_shade_backward': (_I, [_P] * 6 + [_L] + [_P] * 6 + [_I] + [_P] * 6),
+    'vqn_loss_train': (_I, [_P] * 7 + [_L, _I, _I] + [_F] * 7 + [_P] * 7),
+    'vqn_vq_backward': (_I, [_P, _P, _P, _P, _I, _P, _F, _L, _I, _P, _P]),
+    'vqn_material_combine_backward': (_I, [_P, _P, _P, _P, _P, _P, _L, _P, _P, _P]),
+    'vqn_codebook_sim_loss': (_I, [_P, _P, _I, _I, _F, _P, _P, _I, _P]),
+    'vqn_adam_amsgrad': (_I, [_P, _P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _P]),
+    'vqn_cast_f64_f32': (_I, [_P, _P, _P, _L, _P]),
+    'vqn_cast_f32_f64': (_I, [_P, _P, _P, _L, _P]),
     'vqn_microbench_fma': (_I, [_P, _I, _I, C.POINTER(_D)]),
     'vqn_tc_selftest': (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
 }

@@ -427,3 +427,106 @@ def tc_selftest(a: torch.Tensor, b: torch.Tensor, mode: int) -> torch.Tensor:
     L.check(c.lib.vqn_tc_selftest(c.handle, int(mode), b.shape[0], a.shape[1], L.ptr(a), L.ptr(b), L.ptr(d),
                                   L.stream_ptr(a.device)))
     return d
+
+
+# ---------------------------------------------------------------------------------------------
+# training step (include/vqnerf_b200.h "training step"): raw-pointer wrappers, no allocation --
+# the caller (nerfactor/train_nfr.py) owns every buffer so that a step can be replayed from a CUDA graph
+# ---------------------------------------------------------------------------------------------
+def _p(t, off_elems: int = 0):
+    """device pointer of tensor `t` advanced by `off_elems` elements (views into concat / flat buffers)"""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr() + off_elems * t.element_size())
+
+
+def dense_forward(x, ldx, w, b, y, ldy, m, k, n, act, out_scale=1.0, out_bias=0.0, x_off=0, y_off=0):
+    c = _ctx(w)
+    L.check(c.lib.vqn_dense_forward(c.handle, _p(x, x_off), ldx, _p(w), _p(b), _p(y, y_off), ldy, m, k, n, act,
+                                    float(out_scale), float(out_bias), L.stream_ptr(w.device)))
+
+
+def dense_backward_data(dz, lddz, w, dx, lddx, yprev, ldyp, act_prev, accumulate, m, k, n, w_row0=0, dx_off=0,
+                        yprev_off=0):
+    """dx[:, dx_off:dx_off+k] (+)= (dz . w[w_row0:w_row0+k, :]^T) * act_prev'(yprev[:, yprev_off:...])"""
+    c = _ctx(w)
+    L.check(c.lib.vqn_dense_backward_data(c.handle, _p(dz), lddz, _p(w, w_row0 * n), _p(dx, dx_off), lddx,
+                                          _p(yprev, yprev_off), ldyp, act_prev, int(accumulate), m, k, n,
+                                          L.stream_ptr(w.device)))
+
+
+def dense_backward_weights(x, ldx, dz, lddz, dw, db, m, k, n, x_off=0):
+    c = _ctx(dw)
+    L.check(c.lib.vqn_dense_backward_weights(c.handle, _p(x, x_off), ldx, _p(dz), lddz, _p(dw), _p(db), m, k, n,
+                                             L.stream_ptr(dw.device)))
+
+
+def act_backward(dy, lddy, y, ldy, m, n, act, scale, out_scale, out_bias, dz, lddz):
+    c = _ctx(dy)
+    L.check(c.lib.vqn_act_backward(c.handle, _p(dy), lddy, _p(y), ldy, m, n, act, float(scale), float(out_scale),
+                                   float(out_bias), _p(dz), lddz, L.stream_ptr(dy.device)))
+
+
+def copy_cols(src, lds, dst, ldd, m, w, dst_off=0):
+    c = _ctx(src)
+    L.check(c.lib.vqn_copy_cols(c.handle, _p(src), lds, _p(dst, dst_off), ldd, m, w, L.stream_ptr(src.device)))
+
+
+def shade_backward(xyz, rayo, normal, lvis, albedo, spec, rough, lxyz, lareas, light, d_rgb, d_albedo, d_spec,
+                   d_rough, d_light, clip_light0=True, row_idx=None):
+    c = _ctx(xyz)
+    n = albedo.shape[0]
+    L.check(c.lib.vqn_shade_backward(c.handle, _p(xyz), _p(rayo), _p(normal), _p(lvis), _p(row_idx), n, _p(albedo),
+                                     _p(spec), _p(rough), _p(lxyz), _p(lareas), _p(light), int(clip_light0),
+                                     _p(d_rgb), _p(d_albedo), _p(d_spec), _p(d_rough), _p(d_light),
+                                     L.stream_ptr(xyz.device)))
+
+
+def loss_train(gtc, rgb, vqrgb, z_vq, spec, rough, data_is_nerf, combine_weight, chromaticity_weight,
+               mat_sloss_weight, lambert_weight, chr_alpha, chr_thres, inv_global_bs, loss_rows, d_rgb, d_vqrgb,
+               d_z, d_spec, sums):
+    c = _ctx(gtc)
+    n, zd = z_vq.shape
+    L.check(c.lib.vqn_loss_train(c.handle, _p(gtc), _p(rgb), _p(vqrgb), _p(z_vq), _p(spec), _p(rough), n, zd,
+                                 int(data_is_nerf), float(combine_weight), float(chromaticity_weight),
+                                 float(mat_sloss_weight), float(lambert_weight), float(chr_alpha), float(chr_thres),
+                                 float(inv_global_bs), _p(loss_rows), _p(d_rgb), _p(d_vqrgb), _p(d_z), _p(d_spec),
+                                 _p(sums), L.stream_ptr(gtc.device)))
+
+
+def vq_backward(z_enc, indices, codebook, d_zvq, commit_coef, d_zenc, accumulate=True):
+    c = _ctx(z_enc)
+    L.check(c.lib.vqn_vq_backward(c.handle, _p(z_enc), _p(indices), _p(codebook), codebook.shape[1], _p(d_zvq),
+                                  float(commit_coef), z_enc.shape[0], int(accumulate), _p(d_zenc),
+                                  L.stream_ptr(z_enc.device)))
+
+
+def material_combine_backward(basecolor, ks, d_albedo, d_spec, d_spec_extra, d_basecolor, d_ks):
+    c = _ctx(basecolor)
+    L.check(c.lib.vqn_material_combine_backward(c.handle, _p(basecolor), _p(ks), _p(d_albedo), _p(d_spec),
+                                                _p(d_spec_extra), basecolor.shape[0], _p(d_basecolor), _p(d_ks),
+                                                L.stream_ptr(basecolor.device)))
+
+
+def codebook_sim_loss(raw_codebook, grad_scale, loss_out, d_raw, accumulate=False):
+    c = _ctx(raw_codebook)
+    zd, k = raw_codebook.shape
+    L.check(c.lib.vqn_codebook_sim_loss(c.handle, _p(raw_codebook), zd, k, float(grad_scale), _p(loss_out),
+                                        _p(d_raw), int(accumulate), L.stream_ptr(raw_codebook.device)))
+
+
+def adam_amsgrad(param, grad, m, v, vhat, lr_t, beta1, beta2, epsilon):
+    c = _ctx(param)
+    L.check(c.lib.vqn_adam_amsgrad(c.handle, _p(param), _p(grad), _p(m), _p(v), _p(vhat), param.numel(),
+                                   float(lr_t), float(beta1), float(beta2), float(epsilon),
+                                   L.stream_ptr(param.device)))
+
+
+def cast_f64_f32(src, dst):
+    c = _ctx(src)
+    L.check(c.lib.vqn_cast_f64_f32(c.handle, _p(src), _p(dst), src.numel(), L.stream_ptr(src.device)))
+
+
+def cast_f32_f64(src, dst):
+    c = _ctx(src)
+    L.check(c.lib.vqn_cast_f32_f64(c.handle, _p(src), _p(dst), src.numel(), L.stream_ptr(src.device)))

@@ -1,0 +1,288 @@
+// Dense-layer kernels of the training step (config #4): Keras Dense forward with saved activations,
+// backward-data and backward-weights (networks/mlp.py:24-50 under tf.GradientTape, train_nfr.py:562-576).
+//
+// One GEMM core, C[M,N] = A[M,K] . B[K,N], 3xTF32 on the warp-level tensor cores (mma.sync m16n8k8,
+// fp32 accumulate; hi = cvt.rna.tf32(v), lo = cvt.rna.tf32(v - hi), C = Ah.Bh + (Al.Bh + Ah.Bl)) so the
+// gradients keep fp32 parity (1e-4 rel) with the reference.  The training batch is small (8192 rays per
+// GPU, widths <= 384), so the layers are launch- and latency-bound rather than tensor-bound: the kernels are
+// built for generality (arbitrary leading dimensions so layers read and write slices of the concat buffers
+// of the skip connections, transposed operands read in place) and are meant to be replayed from a CUDA
+// graph.  Block tile 64x64x16, 4 warps (2x2) of 32x32, operands staged in padded shared memory whose
+// strides (20 for k-contiguous, 72 for m/n-contiguous tiles) make every fragment read conflict-free.
+//
+//   forward   (mlp.py:44-46)   Y  = act(X . W + b)                 A = X,    B = W
+//   bwd data                   dX = (dZ . W^T) * act'(Y_prev)      A = dZ,   B = W^T (read in place)
+//   bwd weight                 dW += X^T . dZ  (split over rows, fp32 atomics),  db += colsum(dZ)
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, THREADS = 128;
+constexpr int LDK = BK + 4;    // k-contiguous tile  [rows][k]   stride 20 floats
+constexpr int LDR = BM + 8;    // row-contiguous tile [k][rows]  stride 72 floats
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_tf32(float x, unsigned& hi, unsigned& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+
+struct GemmParams {
+  const float* A; long long lda;   // A_TRANS ? element (m,k) at A[k*lda + m] : A[m*lda + k]
+  const float* B; long long ldb;   // B_TRANS ? element (k,n) at B[n*ldb + k] : B[k*ldb + n]
+  float* C; long long ldc;
+  int M, N, K;
+  int k_split;                      // rows of K per blockIdx.z (EPI_ATOMIC only)
+  // epilogues
+  const float* bias; int act;                      // EPI_FWD
+  const float* yprev; long long ldy; int act_prev; // EPI_BWD: multiply by act'(yprev[m*ldy + n])
+  int accumulate;                                  // EPI_BWD: C += result
+  float out_scale, out_bias;                       // EPI_FWD: y = out_scale * act(.) + out_bias (albedo_slope/bias)
+};
+
+enum { EPI_FWD = 0, EPI_BWD = 1, EPI_ATOMIC = 2 };
+
+// load a 4-wide strip of a [rows x cols] operand tile; `contig` runs along the contiguous global axis
+__device__ __forceinline__ float4 load4(const float* base, long long ld, int outer, int inner, int outer_lim,
+                                        int inner_lim) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (outer >= outer_lim) return v;
+  const float* p = base + (long long)outer * ld + inner;
+  if (inner + 3 < inner_lim && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+    v = *reinterpret_cast<const float4*>(p);
+  } else {
+    if (inner < inner_lim) v.x = p[0];
+    if (inner + 1 < inner_lim) v.y = p[1];
+    if (inner + 2 < inner_lim) v.z = p[2];
+    if (inner + 3 < inner_lim) v.w = p[3];
+  }
+  return v;
+}
+
+template <bool A_TRANS, bool B_TRANS, int EPI>
+__global__ void __launch_bounds__(THREADS) dense_gemm_kernel(GemmParams p) {
+  // A tile: !A_TRANS -> As[m][k] (stride LDK), A_TRANS -> As[k][m] (stride LDR); same for B with n
+  __shared__ __align__(16) float As[A_TRANS ? BK * LDR : BM * LDK];
+  __shared__ __align__(16) float Bs[B_TRANS ? BN * LDK : BK * LDR];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  int k_begin = 0, k_end = p.K;
+  if (EPI == EPI_ATOMIC) {
+    k_begin = blockIdx.z * p.k_split;
+    k_end = min(p.K, k_begin + p.k_split);
+  }
+  float acc_m[2][4][4], acc_c[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { acc_m[i][j][e] = 0.f; acc_c[i][j][e] = 0.f; }
+
+  // global -> register staging: each operand tile is 64 x 16 = 256 float4 strips, 2 per thread
+  float4 ra[2], rb[2];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int s = tid + i * THREADS;
+      if (!A_TRANS) {           // strips along k: row = s / 4, kq = s % 4
+        const int r = s >> 2, kq = (s & 3) * 4;
+        ra[i] = load4(p.A, p.lda, m0 + r, k0 + kq, p.M, k_end);
+      } else {                  // strips along m: k = s / 16, mq = s % 16
+        const int kk = s >> 4, mq = (s & 15) * 4;
+        ra[i] = load4(p.A, p.lda, k0 + kk, m0 + mq, k_end, p.M);
+      }
+      if (B_TRANS) {            // strips along k: col = s / 4
+        const int c = s >> 2, kq = (s & 3) * 4;
+        rb[i] = load4(p.B, p.ldb, n0 + c, k0 + kq, p.N, k_end);
+      } else {                  // strips along n
+        const int kk = s >> 4, nq = (s & 15) * 4;
+        rb[i] = load4(p.B, p.ldb, k0 + kk, n0 + nq, k_end, p.N);
+      }
+    }
+  };
+  auto sstore = [&]() {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int s = tid + i * THREADS;
+      if (!A_TRANS) *reinterpret_cast<float4*>(&As[(s >> 2) * LDK + (s & 3) * 4]) = ra[i];
+      else *reinterpret_cast<float4*>(&As[(s >> 4) * LDR + (s & 15) * 4]) = ra[i];
+      if (B_TRANS) *reinterpret_cast<float4*>(&Bs[(s >> 2) * LDK + (s & 3) * 4]) = rb[i];
+      else *reinterpret_cast<float4*>(&Bs[(s >> 4) * LDR + (s & 15) * 4]) = rb[i];
+    }
+  };
+  auto a_at = [&](int m, int k) { return A_TRANS ? As[k * LDR + m] : As[m * LDK + k]; };
+  auto b_at = [&](int k, int n) { return B_TRANS ? Bs[n * LDK + k] : Bs[k * LDR + n]; };
+
+  if (k_begin < k_end) gload(k_begin);
+  for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+    __syncthreads();
+    sstore();
+    __syncthreads();
+    if (k0 + BK < k_end) gload(k0 + BK);
+#pragma unroll
+    for (int ks = 0; ks < BK; ks += 8) {
+      unsigned ah[2][4], al[2][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int m = wm + i * 16 + g;
+        split_tf32(a_at(m, ks + t), ah[i][0], al[i][0]);
+        split_tf32(a_at(m + 8, ks + t), ah[i][1], al[i][1]);
+        split_tf32(a_at(m, ks + t + 4), ah[i][2], al[i][2]);
+        split_tf32(a_at(m + 8, ks + t + 4), ah[i][3], al[i][3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = wn + j * 8 + g;
+        unsigned bh0, bl0, bh1, bl1;
+        split_tf32(b_at(ks + t, n), bh0, bl0);
+        split_tf32(b_at(ks + t + 4, n), bh1, bl1);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          mma_tf32(acc_m[i][j], ah[i], bh0, bh1);
+          mma_tf32(acc_c[i][j], al[i], bh0, bh1);
+          mma_tf32(acc_c[i][j], ah[i], bl0, bl1);
+        }
+      }
+    }
+  }
+
+  // epilogue: accumulator (i, j, e): row = wm + 16i + g + 8*(e>>1), col = wn + 8j + 2t + (e&1)
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int m = m0 + wm + i * 16 + g + 8 * (e >> 1);
+        const int n = n0 + wn + j * 8 + 2 * t + (e & 1);
+        if (m >= p.M || n >= p.N) continue;
+        float v = acc_m[i][j][e] + acc_c[i][j][e];
+        float* dst = p.C + (long long)m * p.ldc + n;
+        if (EPI == EPI_FWD) {
+          if (p.bias) v += p.bias[n];
+          v = vqn_apply_act(v, p.act);
+          *dst = p.out_scale * v + p.out_bias;
+        } else if (EPI == EPI_BWD) {
+          if (p.act_prev != VQN_ACT_NONE) {
+            const float y = p.yprev[(long long)m * p.ldy + n];
+            v *= (p.act_prev == VQN_ACT_RELU) ? (y > 0.f ? 1.f : 0.f) : y * (1.f - y);
+          }
+          if (p.accumulate) v += *dst;
+          *dst = v;
+        } else {
+          atomicAdd(dst, v);
+        }
+      }
+}
+
+// db[n] += sum_m dZ[m, n]   (Keras Dense bias gradient)
+__global__ void colsum_kernel(const float* __restrict__ dz, long long ld, int M, int N, int rows_per_block,
+                              float* __restrict__ db) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float s = 0.f;
+  for (int m = r0; m < r1; ++m) s += dz[(long long)m * ld + n];
+  atomicAdd(&db[n], s);
+}
+
+// dZ = dY * act'(Y) for the LAST layer of a net (no following GEMM epilogue to fuse into);
+// scale folds d(out_scale * act + out_bias) (albedo_slope)
+__global__ void act_grad_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ y,
+                                long long ldy, int M, int N, int act, float scale, float out_scale,
+                                float out_bias, float* __restrict__ dz, long long lddz) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)M * N) return;
+  const int m = (int)(i / N), n = (int)(i % N);
+  float v = dy[(long long)m * lddy + n] * scale;
+  if (act != VQN_ACT_NONE) {
+    // stored y = out_scale * a + out_bias  ->  a = (y - out_bias) / out_scale
+    float a = (y[(long long)m * ldy + n] - out_bias) / out_scale;
+    v *= (act == VQN_ACT_RELU) ? (a > 0.f ? 1.f : 0.f) : a * (1.f - a);
+  }
+  dz[(long long)m * lddz + n] = v;
+}
+
+}  // namespace
+
+/* mlp.py:44-46: Y[M,N] (ld ldy) = out_scale * act(X[M,K] (ld ldx) . W[K,N] + b[N]) + out_bias */
+extern "C" int vqn_dense_forward(vqn_ctx* ctx, const float* x, int64_t ldx, const float* w, const float* b, float* y,
+                                 int64_t ldy, int64_t m, int k, int n, int act, float out_scale, float out_bias,
+                                 vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && x && w && y, "dense_forward: null pointer");
+  VQN_CHECK_ARG(m >= 0 && k > 0 && n > 0 && ldx >= k && ldy >= n, "dense_forward: bad shape");
+  if (m == 0) return VQN_OK;
+  GemmParams p = {};
+  p.A = x; p.lda = ldx; p.B = w; p.ldb = n; p.C = y; p.ldc = ldy; p.M = (int)m; p.N = n; p.K = k;
+  p.bias = b; p.act = act; p.out_scale = out_scale; p.out_bias = out_bias;
+  dim3 grid((unsigned)((m + BM - 1) / BM), (unsigned)((n + BN - 1) / BN), 1);
+  dense_gemm_kernel<false, false, EPI_FWD><<<grid, THREADS, 0, vqn_cs(stream)>>>(p);
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}
+
+/* dX[M,K] (ld lddx) (+)= (dZ[M,N] (ld lddz) . W[K,N]^T) * act_prev'(Yprev[M,K] (ld ldyp)) */
+extern "C" int vqn_dense_backward_data(vqn_ctx* ctx, const float* dz, int64_t lddz, const float* w, float* dx,
+                                       int64_t lddx, const float* yprev, int64_t ldyp, int act_prev, int accumulate,
+                                       int64_t m, int k, int n, vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && dz && w && dx, "dense_backward_data: null pointer");
+  VQN_CHECK_ARG(m >= 0 && k > 0 && n > 0 && lddz >= n && lddx >= k, "dense_backward_data: bad shape");
+  VQN_CHECK_ARG(act_prev == VQN_ACT_NONE || yprev, "dense_backward_data: act_prev needs yprev");
+  if (m == 0) return VQN_OK;
+  GemmParams p = {};
+  p.A = dz; p.lda = lddz; p.B = w; p.ldb = n; p.C = dx; p.ldc = lddx; p.M = (int)m; p.N = k; p.K = n;
+  p.yprev = yprev; p.ldy = ldyp; p.act_prev = act_prev; p.accumulate = accumulate;
+  dim3 grid((unsigned)((m + BM - 1) / BM), (unsigned)((k + BN - 1) / BN), 1);
+  dense_gemm_kernel<false, true, EPI_BWD><<<grid, THREADS, 0, vqn_cs(stream)>>>(p);
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}
+
+/* dW[K,N] += X[M,K]^T . dZ[M,N];  db[N] += colsum(dZ)  (db may be NULL) */
+extern "C" int vqn_dense_backward_weights(vqn_ctx* ctx, const float* x, int64_t ldx, const float* dz, int64_t lddz,
+                                          float* dw, float* db, int64_t m, int k, int n, vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && x && dz && dw, "dense_backward_weights: null pointer");
+  VQN_CHECK_ARG(m >= 0 && k > 0 && n > 0 && ldx >= k && lddz >= n, "dense_backward_weights: bad shape");
+  if (m == 0) return VQN_OK;
+  GemmParams p = {};
+  p.A = x; p.lda = ldx; p.B = dz; p.ldb = lddz; p.C = dw; p.ldc = n; p.M = k; p.N = n; p.K = (int)m;
+  const int tiles = ((k + BM - 1) / BM) * ((n + BN - 1) / BN);
+  int splits = (2 * ctx->sm_count + tiles - 1) / tiles;           // ~2 waves of CTAs
+  int per = (int)((m + splits - 1) / splits);
+  per = ((per + BK - 1) / BK) * BK;
+  if (per < 4 * BK) per = 4 * BK;
+  splits = (int)((m + per - 1) / per);
+  p.k_split = per;
+  dim3 grid((unsigned)((k + BM - 1) / BM), (unsigned)((n + BN - 1) / BN), (unsigned)splits);
+  dense_gemm_kernel<true, false, EPI_ATOMIC><<<grid, THREADS, 0, vqn_cs(stream)>>>(p);
+  VQN_LAUNCHED(ctx);
+  if (db) {
+    const int rows = 256;
+    dim3 g2((unsigned)((n + 127) / 128), (unsigned)((m + rows - 1) / rows));
+    colsum_kernel<<<g2, 128, 0, vqn_cs(stream)>>>(dz, lddz, (int)m, n, rows, db);
+    VQN_LAUNCHED(ctx);
+  }
+  return VQN_OK;
+}
+
+/* dZ[M,N] = scale * dY * act'(Y): gradient through the last layer's activation (and albedo_slope) */
+extern "C" int vqn_act_backward(vqn_ctx* ctx, const float* dy, int64_t lddy, const float* y, int64_t ldy, int64_t m,
+                                int n, int act, float scale, float out_scale, float out_bias, float* dz, int64_t lddz,
+                                vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && dy && dz && (act == VQN_ACT_NONE || y), "act_backward: null pointer");
+  VQN_CHECK_ARG(out_scale != 0.f, "act_backward: out_scale == 0");
+  if (m == 0) return VQN_OK;
+  const long long total = (long long)m * n;
+  act_grad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, vqn_cs(stream)>>>(dy, lddy, y, ldy, (int)m, n, act, scale,
+                                                                              out_scale, out_bias, dz, lddz);
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}

@@ -1,0 +1,370 @@
+"""Mirror of the training-step half of decomp/nerfvq_nfr3/nerfactor/train_nfr.py (:121-139 optimizer,
+:562-576 train_iter): one VQ-stage training iteration = Model.call(mode='train') + compute_loss under a
+gradient tape + Adam(amsgrad) apply, here as hand-written forward / backward kernels behind the C ABI.
+
+    optimizer = Adam(learning_rate=5e-4, amsgrad=True, decay_steps=500_000, decay_rate=0.1)
+    weighted_loss, partial_to_vis, loss_dict = train_iter(model, batch, optimizer, global_bs, thres=thres)
+
+Data flow of a step (all device-side, no host synchronisation when every row is foreground):
+  embed -> fine_enc -> bottleneck -> z_enc -> {VQ assign (+ one-hot / dw statistics), main heads -> shade,
+  VQ heads(z_vq) -> shade} -> loss -> backward of each in reverse -> ONE all-reduce of
+  [all gradients | VQ statistics | loss sums] (NCCL over NVLink; single GPU: none) -> Sonnet EMA codebook update
+  with the GLOBAL statistics -> codebook separation loss on the updated codebook -> Adam on the flat buffer.
+All trainable tensors (8 MLPs, _light, _codebook) are views into ONE flat fp32 buffer, and so are their
+gradients, so the collective and the optimizer are each a single launch.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .. import _lib as L
+from .. import abi
+
+F32 = torch.float32
+NET_ORDER = ('fine_enc', 'bottleneck', 'diff_main', 'spec_main', 'rough_main', 'diff_vq', 'spec_vq', 'rough_vq')
+
+
+def _pad4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+class Adam:
+    """tf.keras.optimizers.Adam(learning_rate, amsgrad=True) (train_nfr.py:121-139) with the optional
+    ExponentialDecay schedule lr * rate ** (step / decay_steps) (:123-127)."""
+
+    def __init__(self, learning_rate: float = 5e-4, beta_1: float = 0.9, beta_2: float = 0.999,
+                 epsilon: float = 1e-7, amsgrad: bool = True, decay_steps: int = -1, decay_rate: float = 0.1):
+        if not amsgrad:
+            raise NotImplementedError('the reference trains with amsgrad=True (train_nfr.py:129)')
+        self.learning_rate, self.beta_1, self.beta_2, self.epsilon = learning_rate, beta_1, beta_2, epsilon
+        self.decay_steps, self.decay_rate = decay_steps, decay_rate
+        self.iterations = 0
+        self.m = self.v = self.vhat = None
+
+    def lr_t(self) -> float:
+        """called after `iterations` was incremented for this step"""
+        t = self.iterations
+        lr = self.learning_rate
+        if self.decay_steps > 0:
+            lr = lr * self.decay_rate ** ((t - 1) / self.decay_steps)   # schedule sees the pre-increment step
+        return lr * math.sqrt(1.0 - self.beta_2 ** t) / (1.0 - self.beta_1 ** t)
+
+    def apply_gradients(self, params: torch.Tensor, grads: torch.Tensor) -> None:
+        if self.m is None:
+            self.m, self.v, self.vhat = (torch.zeros_like(params) for _ in range(3))
+        self.iterations += 1
+        abi.adam_amsgrad(params, grads, self.m, self.v, self.vhat, self.lr_t(), self.beta_1, self.beta_2,
+                         self.epsilon)
+
+    def state_dict(self):
+        return {'iterations': self.iterations, 'm': self.m, 'v': self.v, 'vhat': self.vhat}
+
+
+class _NetTrain:
+    """Activations and gradient scratch of one mlp.Network for a fixed row count (networks/mlp.py:39-50)."""
+
+    def __init__(self, net, in_dim: int, n: int, out_scale: float = 1.0, out_bias: float = 0.0):
+        self.net, self.in_dim, self.n = net, in_dim, n
+        self.out_scale, self.out_bias = out_scale, out_bias
+        self.acts = [L.act_code(a) for a in net.act]
+        self.skip = None if net.skip_at is None else int(net.skip_at[0])
+        dev = net.kernels[0].device
+        self.widths = list(net.widths)
+        self.k_in: List[int] = []          # input width of layer i
+        self.ld: List[int] = []            # leading dim of the output buffer of layer i
+        d = in_dim
+        for i, w in enumerate(self.widths):
+            self.k_in.append(d)
+            d = w + (in_dim if self.skip == i else 0)
+            self.ld.append(_pad4(d))
+        self.y = [torch.zeros((n, ld), dtype=F32, device=dev) for ld in self.ld]
+        self.dz = [torch.empty((n, _pad4(w)), dtype=F32, device=dev) for w in self.widths]
+        self.x = None
+        self.ldx = None
+
+    @property
+    def out(self) -> torch.Tensor:
+        return self.y[-1]
+
+    def forward(self, x: torch.Tensor, ldx: int) -> torch.Tensor:
+        self.x, self.ldx = x, ldx
+        cur, ld = x, ldx
+        n_layers = len(self.widths)
+        for i, w in enumerate(self.widths):
+            last = i == n_layers - 1
+            abi.dense_forward(cur, ld, self.net.kernels[i], self.net.biases[i], self.y[i], self.ld[i], self.n,
+                              self.k_in[i], w, self.acts[i], self.out_scale if last else 1.0,
+                              self.out_bias if last else 0.0)
+            if self.skip == i:                                            # concat(y, x) (mlp.py:47-48)
+                abi.copy_cols(x, ldx, self.y[i], self.ld[i], self.n, self.in_dim, dst_off=w)
+            cur, ld = self.y[i], self.ld[i]
+        return self.y[-1]
+
+    def backward(self, dy: torch.Tensor, lddy: int, dW: List[torch.Tensor], dB: List[torch.Tensor],
+                 d_input: Optional[torch.Tensor] = None, ld_din: int = 0) -> None:
+        """dy: gradient w.r.t. the net output [n, out].  Adds weight gradients into dW/dB and (optionally)
+        ACCUMULATES the gradient w.r.t. the net input into d_input."""
+        nl = len(self.widths)
+        last = nl - 1
+        abi.act_backward(dy, lddy, self.y[last], self.ld[last], self.n, self.widths[last], self.acts[last],
+                         self.out_scale, self.out_scale, self.out_bias, self.dz[last], self.dz[last].shape[1])
+        for i in range(last, -1, -1):
+            w = self.widths[i]
+            dz, lddz = self.dz[i], self.dz[i].shape[1]
+            xin, ldin = (self.x, self.ldx) if i == 0 else (self.y[i - 1], self.ld[i - 1])
+            abi.dense_backward_weights(xin, ldin, dz, lddz, dW[i], dB[i], self.n, self.k_in[i], w)
+            if i > 0:
+                wp = self.widths[i - 1]
+                # y part of the input: through the previous layer's activation -> dz[i-1]
+                abi.dense_backward_data(dz, lddz, self.net.kernels[i], self.dz[i - 1], self.dz[i - 1].shape[1],
+                                        self.y[i - 1], self.ld[i - 1], self.acts[i - 1], False, self.n, wp, w)
+                if self.skip == i - 1 and d_input is not None:            # x part of concat(y, x)
+                    abi.dense_backward_data(dz, lddz, self.net.kernels[i], d_input, ld_din, None, 0, L.ACT_NONE,
+                                            True, self.n, self.in_dim, w, w_row0=wp)
+            elif d_input is not None:
+                abi.dense_backward_data(dz, lddz, self.net.kernels[0], d_input, ld_din, None, 0, L.ACT_NONE, True,
+                                        self.n, self.in_dim, w)
+
+
+class TrainState:
+    """Flat parameter / gradient buffers (views re-pointed into the model) + per-row-count activation sets."""
+
+    def __init__(self, model):
+        self.model = model
+        dev = model.device
+        tensors = []
+        for name in NET_ORDER:
+            net = model.net[name]
+            for k, b in zip(net.kernels, net.biases):
+                tensors += [k, b]
+        tensors += [model._light, model._codebook]
+        sizes = [_pad4(t.numel()) for t in tensors]              # 16-byte aligned views
+        self.n_param = sum(sizes)
+        z, k = model.z_dim, model.num_embed
+        self.n_stats = abi.vq_stats_size(z, k)
+        self.n_sums = 8                                           # loss sums [6] + active rows + spare
+        # flat = [params]; gflat = [grads | stats (fp32) | sums]
+        self.params = torch.zeros((self.n_param,), dtype=F32, device=dev)
+        self.gflat = torch.zeros((self.n_param + _pad4(self.n_stats) + self.n_sums,), dtype=F32, device=dev)
+        self.grads = self.gflat[:self.n_param]
+        self.stats32 = self.gflat[self.n_param:self.n_param + self.n_stats]
+        self.sums = self.gflat[self.n_param + _pad4(self.n_stats):]
+        self.stats64 = torch.zeros((self.n_stats,), dtype=torch.float64, device=dev)
+        off = 0
+        views, gviews = [], []
+        for t, sz in zip(tensors, sizes):
+            v = self.params[off:off + t.numel()].view(t.shape)
+            v.copy_(t)
+            views.append(v)
+            gviews.append(self.grads[off:off + t.numel()].view(t.shape))
+            off += sz
+        it, git = iter(views), iter(gviews)
+        self.dW: Dict[str, List[torch.Tensor]] = {}
+        self.dB: Dict[str, List[torch.Tensor]] = {}
+        for name in NET_ORDER:
+            net = model.net[name]
+            self.dW[name], self.dB[name] = [], []
+            for i in range(len(net.kernels)):
+                net.kernels[i] = next(it)
+                net.biases[i] = next(it)
+                self.dW[name].append(next(git))
+                self.dB[name].append(next(git))
+            net._pack()                                           # the inference handles follow the new storage
+        model._light = next(it)
+        model._codebook = next(it)
+        self.d_light = next(git)
+        self.d_codebook = next(git)
+        self.sim_loss = torch.zeros((1,), dtype=F32, device=dev)
+        self.acts: Dict[int, dict] = {}
+        self.dirty = False
+
+    def buffers(self, n: int) -> dict:
+        if n in self.acts:
+            return self.acts[n]
+        m = self.model
+        dev = m.device
+        z = m.z_dim
+        emb = m.embedder['xyz'].out_dims
+        e = lambda *s: torch.empty(s, dtype=F32, device=dev)
+        b = {
+            'embed': torch.zeros((n, _pad4(emb)), dtype=F32, device=dev),
+            'nets': {
+                'fine_enc': _NetTrain(m.net['fine_enc'], emb, n),
+                'bottleneck': _NetTrain(m.net['bottleneck'], m.net['fine_enc'].widths[-1], n),
+                'diff_main': _NetTrain(m.net['diff_main'], z, n, m.albedo_slope, m.albedo_bias),
+                'spec_main': _NetTrain(m.net['spec_main'], z, n),
+                'rough_main': _NetTrain(m.net['rough_main'], z, n),
+                'diff_vq': _NetTrain(m.net['diff_vq'], z, n, m.albedo_slope, m.albedo_bias),
+                'spec_vq': _NetTrain(m.net['spec_vq'], z, n),
+                'rough_vq': _NetTrain(m.net['rough_vq'], z, n),
+            },
+            'albedo': e(n, 3), 'spec': e(n, 3), 'base_c': e(n, 3), 'ks_c': e(n, 1), 'rough_c': e(n, 1),
+            'vq_albedo_c': e(n, 3), 'vq_spec_c': e(n, 3), 'vq_rough_c': e(n, 1),
+            'loss_rows': e(n), 'd_rgb': e(n, 3), 'd_vqrgb': e(n, 3), 'd_zvq': e(n, z), 'd_spec_l': e(n, 3),
+            'd_albedo': e(n, 3), 'd_spec': e(n, 3), 'd_rough': e(n, 1), 'd_base': e(n, 3), 'd_ks': e(n, 1),
+            'd_vq_albedo': e(n, 3), 'd_vq_spec': e(n, 3), 'd_vq_rough': e(n, 1),
+            'd_zenc': e(n, z), 'd_h': e(n, m.net['fine_enc'].widths[-1]),
+        }
+        self.acts[n] = b
+        return b
+
+
+def _train_state(model) -> TrainState:
+    st = getattr(model, '_train_state', None)
+    if st is None:
+        st = TrainState(model)
+        model._train_state = st
+    return st
+
+
+LOSS_DEFAULTS = dict(vq_loss_weight=1.0, chr_alpha=60.0, chr_thres=0.1, combine_weight=0.2, mat_sloss_weight=0.05,
+                     chromaticity_loss_weight=1.0, sim_loss_weight=1e-4, lambert_weight=1e-3)   # vq_nfr.ini:115-131
+
+
+def _compact_col(src: torch.Tensor, ld: int, w: int, dst: torch.Tensor):
+    abi.copy_cols(src, ld, dst, w, src.shape[0], w)
+    return dst
+
+
+def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=None, group=None,
+               apply: bool = True):
+    """train_nfr.py:562-576.  Returns (weighted_loss [device scalar], partial_to_vis, loss_dict of per-term
+    batch means).  `group`: torch.distributed process group for the data-parallel all-reduce (None: default
+    group when initialised, else single GPU).  Rows must be (pixel, neighbour) pairs (train_nfr.py:447-448)."""
+    m = model
+    if m.data_type != 'nerf':
+        raise NotImplementedError('training kernels are built for data_type == nerf (no gamma variables)')
+    st = _train_state(m)
+    cfg = m.config
+    lw = {k: (cfg.getfloat(k, fallback=v) if hasattr(cfg, 'getfloat') else v) for k, v in LOSS_DEFAULTS.items()}
+    id_, hw, rayo, rayd, rgb, alpha, pred_alpha, xyz, normal, lvis = m._unpack(batch, False)
+    n_total = alpha.shape[0]
+    row_idx, n_act = abi.compact_mask(alpha)
+    full = getattr(m, 'assume_all_foreground', False)
+    n = n_total if full else int(n_act.item())
+    if n != n_total:                     # the sampler only draws foreground pixels (train_nfr.py:380-467); rare path
+        idx = row_idx[:n].long()
+        rayo, rgb, xyz, normal = (t.index_select(0, idx) for t in (rayo, rgb, xyz, normal))
+        lvis = lvis.index_select(0, idx) if lvis is not None else None
+    if n % 2:
+        raise ValueError('training rows must come in (pixel, neighbour) pairs')
+    B = st.buffers(n)
+    nets = B['nets']
+    z = m.z_dim
+    K = m.num_embed
+    inv_gbs = 1.0 / float(global_bs)
+    st.gflat.zero_()
+    st.stats64.zero_()
+
+    # ---- forward ------------------------------------------------------------------------------------------
+    emb = m.embedder['xyz']
+    E = B['embed']
+    c = L.Context.get(m.device)
+    xyz_c = xyz.contiguous()
+    e_tmp = abi.embed(xyz_c, emb.n_freqs)
+    abi.copy_cols(e_tmp, emb.out_dims, E, E.shape[1], n, emb.out_dims)
+    h = nets['fine_enc'].forward(E, E.shape[1])
+    z_enc = nets['bottleneck'].forward(h, nets['fine_enc'].ld[-1])
+    codebook = m.get_codebook()                                                   # :576, before the EMA assign
+    sel_mask = None
+    th = m._thres_mask(thres)
+    if th is not None:
+        vq = m.vq_layer
+        if roll is None:
+            roll = torch.rand((1, K), generator=vq._gen, dtype=F32)
+        roll = torch.as_tensor(roll, dtype=F32).reshape(1, -1)
+        sel_mask = (roll >= torch.as_tensor(th, dtype=F32).reshape(1, -1)).to(F32).expand(1, K).reshape(-1).to(m.device)
+    vq_out = abi.vq_assign(z_enc, codebook, sel_mask=sel_mask, normalize_inputs=True, want_quantize=True,
+                           stats=st.stats64, want_dw=True)                        # :575-577 (l2_normalize fused)
+    z_vq, idx = vq_out['quantize'], vq_out['indices']
+    base = nets['diff_main'].forward(z_enc, z)
+    ks = nets['spec_main'].forward(z_enc, z)
+    rough = nets['rough_main'].forward(z_enc, z)
+    base_c = _compact_col(base, nets['diff_main'].ld[-1], 3, B['base_c'])
+    ks_c = _compact_col(ks, nets['spec_main'].ld[-1], 1, B['ks_c'])
+    rough_c = _compact_col(rough, nets['rough_main'].ld[-1], 1, B['rough_c'])
+    albedo, spec, _, _ = abi.material_combine(base_c, ks_c, want_scaled=False)    # :590-591
+    lights = m._light.reshape(1, 512, 3)
+    sh = abi.shade(xyz, rayo, normal, lvis, albedo, spec, rough_c, m.lxyz, m.lareas, lights, n=n, n_total=n)
+    rgb_pred = sh['rgb'].reshape(n, 3)
+    va = nets['diff_vq'].forward(z_vq, z)
+    vs = nets['spec_vq'].forward(z_vq, z)
+    vr = nets['rough_vq'].forward(z_vq, z)
+    va_c = _compact_col(va, nets['diff_vq'].ld[-1], 3, B['vq_albedo_c'])
+    vs_c = _compact_col(vs, nets['spec_vq'].ld[-1], 3, B['vq_spec_c'])
+    vr_c = _compact_col(vr, nets['rough_vq'].ld[-1], 1, B['vq_rough_c'])
+    sh_vq = abi.shade(xyz, rayo, normal, lvis, va_c, vs_c, vr_c, m.lxyz, m.lareas, lights, n=n, n_total=n)
+    vq_rgb = sh_vq['rgb'].reshape(n, 3)
+
+    # ---- loss + backward ----------------------------------------------------------------------------------
+    abi.loss_train(rgb.contiguous(), rgb_pred, vq_rgb, z_vq, spec, rough_c, True, lw['combine_weight'],
+                   lw['chromaticity_loss_weight'], lw['mat_sloss_weight'], lw['lambert_weight'], lw['chr_alpha'],
+                   lw['chr_thres'], inv_gbs, B['loss_rows'], B['d_rgb'], B['d_vqrgb'], B['d_zvq'], B['d_spec_l'],
+                   st.sums)
+    # main branch
+    abi.shade_backward(xyz, rayo, normal, lvis, albedo, spec, rough_c, m.lxyz, m.lareas, m._light, B['d_rgb'],
+                       B['d_albedo'], B['d_spec'], B['d_rough'], st.d_light)
+    abi.material_combine_backward(base_c, ks_c, B['d_albedo'], B['d_spec'], B['d_spec_l'], B['d_base'], B['d_ks'])
+    d_zenc = B['d_zenc']
+    d_zenc.zero_()
+    nets['diff_main'].backward(B['d_base'], 3, st.dW['diff_main'], st.dB['diff_main'], d_zenc, z)
+    nets['spec_main'].backward(B['d_ks'], 1, st.dW['spec_main'], st.dB['spec_main'], d_zenc, z)
+    nets['rough_main'].backward(B['d_rough'], 1, st.dW['rough_main'], st.dB['rough_main'], d_zenc, z)
+    # VQ branch (d_zvq already holds the pair-smoothness gradient)
+    abi.shade_backward(xyz, rayo, normal, lvis, va_c, vs_c, vr_c, m.lxyz, m.lareas, m._light, B['d_vqrgb'],
+                       B['d_vq_albedo'], B['d_vq_spec'], B['d_vq_rough'], st.d_light)
+    d_zvq = B['d_zvq']
+    nets['diff_vq'].backward(B['d_vq_albedo'], 3, st.dW['diff_vq'], st.dB['diff_vq'], d_zvq, z)
+    nets['spec_vq'].backward(B['d_vq_spec'], 3, st.dW['spec_vq'], st.dB['spec_vq'], d_zvq, z)
+    nets['rough_vq'].backward(B['d_vq_rough'], 1, st.dW['rough_vq'], st.dB['rough_vq'], d_zvq, z)
+    commit_coef = lw['vq_loss_weight'] * m.vq_layer.commitment_cost * 2.0 * inv_gbs / z
+    abi.vq_backward(z_enc, idx, codebook, d_zvq, commit_coef, d_zenc, accumulate=True)
+    d_h = B['d_h']
+    d_h.zero_()
+    nets['bottleneck'].backward(d_zenc, z, st.dW['bottleneck'], st.dB['bottleneck'], d_h, d_h.shape[1])
+    nets['fine_enc'].backward(d_h, d_h.shape[1], st.dW['fine_enc'], st.dB['fine_enc'])
+
+    # ---- the single collective: [gradients | VQ statistics | loss sums] --------------------------------------
+    abi.cast_f64_f32(st.stats64, st.stats32)
+    st.sums[6:7] += float(n)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(st.gflat, op=dist.ReduceOp.SUM, group=group)
+    abi.cast_f32_f64(st.stats32, st.stats64)
+
+    # ---- EMA codebook update with the global statistics (:582-583), separation loss on the updated codebook ----
+    vq = m.vq_layer
+    update, vq_loss, _ = abi.vq_ema_update(st.stats64, codebook, vq.decay, vq.epsilon, vq.commitment_cost, True,
+                                           vq.state)
+    m._codebook.copy_(update)
+    rows_scale = st.sums[6] * inv_gbs             # (global active rows) / global_bs: weight of broadcast scalars
+    sim_w = lw['sim_loss_weight']
+    if sim_w > 0:
+        # gradient scale = sim_w * rows / gbs (scalar broadcast to every row, vq_nfr.py:971-972); rows == known
+        n_glob = n * (dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1) \
+            if full else None
+        scale = sim_w * (float(n_glob) * inv_gbs if n_glob is not None else float(rows_scale.item()))
+        abi.codebook_sim_loss(m._codebook, scale, st.sim_loss, st.d_codebook, accumulate=False)
+    weighted = st.sums[5] * inv_gbs + rows_scale * (lw['vq_loss_weight'] * vq_loss[0] + sim_w * st.sim_loss[0])
+    loss_dict = {'rgb': st.sums[0], 'vqrgb': st.sums[1], 'chromaticity': st.sums[2], 'chr_smooth': st.sums[3],
+                 'lambert': st.sums[4], 'vqloss': lw['vq_loss_weight'] * vq_loss[0],
+                 'sim_smooth': sim_w * st.sim_loss[0], 'rows': st.sums[6]}
+    if apply:
+        optimizer.apply_gradients(st.params, st.grads)
+        st.dirty = True
+    partial_to_vis = {'id': id_, 'hw': hw, 'pred_rgb_linear': rgb_pred, 'pred_vq_rgb_linear': vq_rgb,
+                      'pred_albedo': albedo, 'pred_spec': spec, 'pred_rough': rough_c, 'embed_ind': idx + 1,
+                      'z_enc': z_enc, 'z_vq': z_vq, 'loss_rows': B['loss_rows']}
+    return weighted, partial_to_vis, loss_dict
+
+
+def sync_inference_weights(model) -> None:
+    """Re-pack the inference-side weight images (tensor-core swizzled copies) after optimizer steps."""
+    st = getattr(model, '_train_state', None)
+    if st is not None and st.dirty:
+        for name in NET_ORDER:
+            model.net[name].weights_updated()
+        st.dirty = False
