@@ -275,9 +275,10 @@ int vqn_material_combine_backward(vqn_ctx* ctx, const float* basecolor, const fl
 int vqn_codebook_sim_loss(vqn_ctx* ctx, const float* raw_codebook, int z_dim, int k, float grad_scale,
                           float* loss_out, float* d_raw, int accumulate, vqn_stream stream);
 /* tf.keras.optimizers.Adam(amsgrad=True) dense update on a flat parameter buffer (train_nfr.py:121-139);
- * lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t) is computed by the caller. */
+ * lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t) is computed by the caller; lr_t_dev (optional device scalar)
+ * overrides lr_t so that a CUDA-graph replay of the step can change the rate without re-capturing. */
 int vqn_adam_amsgrad(vqn_ctx* ctx, float* param, const float* grad, float* m, float* v, float* vhat, int64_t count,
-                     float lr_t, float beta1, float beta2, float epsilon, vqn_stream stream);
+                     float lr_t, const float* lr_t_dev, float beta1, float beta2, float epsilon, vqn_stream stream);
 /* VQ statistics (float64) <-> the fp32 tail of the flat all-reduce buffer */
 int vqn_cast_f64_f32(vqn_ctx* ctx, const double* src, float* dst, int64_t count, vqn_stream stream);
 int vqn_cast_f32_f64(vqn_ctx* ctx, const float* src, double* dst, int64_t count, vqn_stream stream);

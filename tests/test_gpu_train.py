@@ -186,3 +186,31 @@ def test_shade_backward_matches_autograd(cuda_dev, rough_lo, rel):
     _tensor_close(d_r, rough.grad, 'd rough', rel=rel)
     _tensor_close(d_l, light.grad.reshape(-1, 3), 'd light', rel=rel)
     _close(d_alb, alb.grad, 'd albedo (elementwise)', rtol=2e-4, atol=1e-5)
+
+
+def test_graphed_train_iter_equals_eager(cuda_dev):
+    """The CUDA-graph replay of a step must leave exactly the same parameters as the eager step sequence."""
+    from vqnerf_release_b200.nerfactor import train_nfr as T
+    n, gbs, k = 256, 128, 15
+    thres = np.array([0.0] * 3 + [0.4] * 12)
+    finals = []
+    for graphed in (False, True):
+        scene, batch, m, _ = _train_pair(cuda_dev, n, seed=4)
+        opt = T.Adam(learning_rate=5e-4, decay_steps=1000, decay_rate=0.1)
+        bt = _batch_tuple(batch, cuda_dev)
+        step = T.GraphedTrainIter(m, opt, gbs, bt) if graphed else None
+        losses = []
+        for it in range(3):
+            roll = np.random.RandomState(it).uniform(0, 1, size=(1, k))
+            if graphed:
+                loss, _, _ = step(bt, thres=thres, roll=roll)
+            else:
+                loss, _, _ = T.train_iter(m, bt, opt, gbs, thres=thres, roll=roll)
+            losses.append(float(loss))
+        torch.cuda.synchronize()
+        assert opt.iterations == 3
+        finals.append((m._train_state.params.clone(), losses, m.vq_layer.state['counters'].tolist()))
+    assert finals[0][2] == finals[1][2] == [3, 3]
+    np.testing.assert_allclose(finals[0][1], finals[1][1], rtol=1e-5)
+    # atomics reorder the weight-gradient sums, so equality is to fp32 rounding of the Adam-normalised update
+    assert (finals[0][0] - finals[1][0]).abs().max().item() < 2e-5

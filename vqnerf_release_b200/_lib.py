@@ -100,7 +100,7 @@ SIGNATURES = {
     'vqn_vq_backward': (_I, [_P, _P, _P, _P, _I, _P, _F, _L, _I, _P, _P]),
     'vqn_material_combine_backward': (_I, [_P, _P, _P, _P, _P, _P, _L, _P, _P, _P]),
     'vqn_codebook_sim_loss': (_I, [_P, _P, _I, _I, _F, _P, _P, _I, _P]),
-    'vqn_adam_amsgrad': (_I, [_P, _P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _P]),
+    'vqn_adam_amsgrad': (_I, [_P, _P, _P, _P, _P, _P, _L, _F, _P, _F, _F, _F, _P]),
     'vqn_cast_f64_f32': (_I, [_P, _P, _P, _L, _P]),
     'vqn_cast_f32_f64': (_I, [_P, _P, _P, _L, _P]),
     'vqn_microbench_fma': (_I, [_P, _I, _I, C.POINTER(_D)]),

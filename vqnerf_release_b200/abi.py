@@ -515,10 +515,10 @@ def codebook_sim_loss(raw_codebook, grad_scale, loss_out, d_raw, accumulate=Fals
                                         _p(d_raw), int(accumulate), L.stream_ptr(raw_codebook.device)))
 
 
-def adam_amsgrad(param, grad, m, v, vhat, lr_t, beta1, beta2, epsilon):
+def adam_amsgrad(param, grad, m, v, vhat, lr_t, beta1, beta2, epsilon, lr_t_dev=None):
     c = _ctx(param)
     L.check(c.lib.vqn_adam_amsgrad(c.handle, _p(param), _p(grad), _p(m), _p(v), _p(vhat), param.numel(),
-                                   float(lr_t), float(beta1), float(beta2), float(epsilon),
+                                   float(lr_t), _p(lr_t_dev), float(beta1), float(beta2), float(epsilon),
                                    L.stream_ptr(param.device)))
 
 

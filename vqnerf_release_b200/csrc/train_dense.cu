@@ -12,7 +12,7 @@
 //
 //   forward   (mlp.py:44-46)   Y  = act(X . W + b)                 A = X,    B = W
 //   bwd data                   dX = (dZ . W^T) * act'(Y_prev)      A = dZ,   B = W^T (read in place)
-//   bwd weight                 dW += X^T . dZ  (split over rows, fp32 atomics),  db += colsum(dZ)
+//   bwd weight                 dW += X^T . dZ  (split over rows, fp32 atomics),  db += colsum(dZ) (fused)
 #include "common.cuh"
 
 namespace {
@@ -43,6 +43,7 @@ struct GemmParams {
   const float* yprev; long long ldy; int act_prev; // EPI_BWD: multiply by act'(yprev[m*ldy + n])
   int accumulate;                                  // EPI_BWD: C += result
   float out_scale, out_bias;                       // EPI_FWD: y = out_scale * act(.) + out_bias (albedo_slope/bias)
+  float* colsum;                                   // EPI_ATOMIC: colsum[n] += sum_k B[k][n] (the Dense bias gradient)
 };
 
 enum { EPI_FWD = 0, EPI_BWD = 1, EPI_ATOMIC = 2 };
@@ -121,12 +122,20 @@ __global__ void __launch_bounds__(THREADS) dense_gemm_kernel(GemmParams p) {
   auto a_at = [&](int m, int k) { return A_TRANS ? As[k * LDR + m] : As[m * LDK + k]; };
   auto b_at = [&](int k, int n) { return B_TRANS ? Bs[n * LDK + k] : Bs[k * LDR + n]; };
 
+  // bias gradient fused into the weight-gradient GEMM: the CTAs of the first row-tile also sum the columns of
+  // every dZ tile they stage (thread t < 64 owns column n0 + t)
+  const bool do_colsum = EPI == EPI_ATOMIC && p.colsum != nullptr && blockIdx.x == 0 && tid < BN;
+  float csum = 0.f;
   if (k_begin < k_end) gload(k_begin);
   for (int k0 = k_begin; k0 < k_end; k0 += BK) {
     __syncthreads();
     sstore();
     __syncthreads();
     if (k0 + BK < k_end) gload(k0 + BK);
+    if (EPI == EPI_ATOMIC && do_colsum) {
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) csum += Bs[B_TRANS ? tid * LDK + kk : kk * LDR + tid];
+    }
 #pragma unroll
     for (int ks = 0; ks < BK; ks += 8) {
       unsigned ah[2][4], al[2][4];
@@ -153,6 +162,8 @@ __global__ void __launch_bounds__(THREADS) dense_gemm_kernel(GemmParams p) {
       }
     }
   }
+
+  if (EPI == EPI_ATOMIC && do_colsum && n0 + tid < p.N) atomicAdd(&p.colsum[n0 + tid], csum);
 
   // epilogue: accumulator (i, j, e): row = wm + 16i + g + 8*(e>>1), col = wn + 8j + 2t + (e&1)
 #pragma unroll
@@ -181,17 +192,6 @@ __global__ void __launch_bounds__(THREADS) dense_gemm_kernel(GemmParams p) {
           atomicAdd(dst, v);
         }
       }
-}
-
-// db[n] += sum_m dZ[m, n]   (Keras Dense bias gradient)
-__global__ void colsum_kernel(const float* __restrict__ dz, long long ld, int M, int N, int rows_per_block,
-                              float* __restrict__ db) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
-  float s = 0.f;
-  for (int m = r0; m < r1; ++m) s += dz[(long long)m * ld + n];
-  atomicAdd(&db[n], s);
 }
 
 // dZ = dY * act'(Y) for the LAST layer of a net (no following GEMM epilogue to fuse into);
@@ -261,15 +261,10 @@ extern "C" int vqn_dense_backward_weights(vqn_ctx* ctx, const float* x, int64_t 
   if (per < 4 * BK) per = 4 * BK;
   splits = (int)((m + per - 1) / per);
   p.k_split = per;
+  p.colsum = db;
   dim3 grid((unsigned)((k + BM - 1) / BM), (unsigned)((n + BN - 1) / BN), (unsigned)splits);
   dense_gemm_kernel<true, false, EPI_ATOMIC><<<grid, THREADS, 0, vqn_cs(stream)>>>(p);
   VQN_LAUNCHED(ctx);
-  if (db) {
-    const int rows = 256;
-    dim3 g2((unsigned)((n + 127) / 128), (unsigned)((m + rows - 1) / rows));
-    colsum_kernel<<<g2, 128, 0, vqn_cs(stream)>>>(dz, lddz, (int)m, n, rows, db);
-    VQN_LAUNCHED(ctx);
-  }
   return VQN_OK;
 }
 

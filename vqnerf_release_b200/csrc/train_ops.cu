@@ -422,8 +422,9 @@ __global__ void __launch_bounds__(256) sim_loss_kernel(const float* __restrict__
 // tf.keras.optimizers.Adam(amsgrad=True) (optimizer_v2/adam.py): lr_t = lr sqrt(1-b2^t)/(1-b1^t) is computed by
 // the caller; m += (g-m)(1-b1); v += (g^2-v)(1-b2); vhat = max(vhat, v); p -= lr_t m / (sqrt(vhat) + eps)
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, float* __restrict__ vhat, long long count, float lr_t, float b1,
-                            float b2, float eps) {
+                            float* __restrict__ v, float* __restrict__ vhat, long long count, float lr_t,
+                            const float* __restrict__ lr_t_dev, float b1, float b2, float eps) {
+  if (lr_t_dev) lr_t = *lr_t_dev;      // CUDA-graph replay: the step-dependent rate lives in device memory
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
        i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i];
@@ -522,12 +523,14 @@ extern "C" int vqn_codebook_sim_loss(vqn_ctx* ctx, const float* raw_codebook, in
 }
 
 extern "C" int vqn_adam_amsgrad(vqn_ctx* ctx, float* param, const float* grad, float* m, float* v, float* vhat,
-                                int64_t count, float lr_t, float beta1, float beta2, float epsilon, vqn_stream stream) {
+                                int64_t count, float lr_t, const float* lr_t_dev, float beta1, float beta2,
+                                float epsilon, vqn_stream stream) {
   VQN_CHECK_ARG(ctx && param && grad && m && v && vhat && count >= 0, "adam args");
   if (count == 0) return VQN_OK;
   long long want = (count + 255) / 256;
   int blocks = (int)(want < (long long)ctx->sm_count * 8 ? want : (long long)ctx->sm_count * 8);
-  adam_kernel<<<blocks, 256, 0, vqn_cs(stream)>>>(param, grad, m, v, vhat, (long long)count, lr_t, beta1, beta2, epsilon);
+  adam_kernel<<<blocks, 256, 0, vqn_cs(stream)>>>(param, grad, m, v, vhat, (long long)count, lr_t, lr_t_dev, beta1, beta2,
+                                                  epsilon);
   VQN_LAUNCHED(ctx);
   return VQN_OK;
 }

@@ -53,12 +53,17 @@ class Adam:
             lr = lr * self.decay_rate ** ((t - 1) / self.decay_steps)   # schedule sees the pre-increment step
         return lr * math.sqrt(1.0 - self.beta_2 ** t) / (1.0 - self.beta_1 ** t)
 
-    def apply_gradients(self, params: torch.Tensor, grads: torch.Tensor) -> None:
+    def apply_gradients(self, params: torch.Tensor, grads: torch.Tensor, lr_t_dev=None) -> None:
+        """lr_t_dev: device scalar holding lr_t (graph replay: the caller advances `iterations` and refreshes it)"""
+        self.ensure_state(params)
+        if lr_t_dev is None:
+            self.iterations += 1
+        abi.adam_amsgrad(params, grads, self.m, self.v, self.vhat, self.lr_t() if lr_t_dev is None else 0.0,
+                         self.beta_1, self.beta_2, self.epsilon, lr_t_dev=lr_t_dev)
+
+    def ensure_state(self, params: torch.Tensor) -> None:
         if self.m is None:
             self.m, self.v, self.vhat = (torch.zeros_like(params) for _ in range(3))
-        self.iterations += 1
-        abi.adam_amsgrad(params, grads, self.m, self.v, self.vhat, self.lr_t(), self.beta_1, self.beta_2,
-                         self.epsilon)
 
     def state_dict(self):
         return {'iterations': self.iterations, 'm': self.m, 'v': self.v, 'vhat': self.vhat}
@@ -231,7 +236,7 @@ def _compact_col(src: torch.Tensor, ld: int, w: int, dst: torch.Tensor):
 
 
 def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=None, group=None,
-               apply: bool = True):
+               apply: bool = True, _sel_mask_dev=None, _lr_t_dev=None):
     """train_nfr.py:562-576.  Returns (weighted_loss [device scalar], partial_to_vis, loss_dict of per-term
     batch means).  `group`: torch.distributed process group for the data-parallel all-reduce (None: default
     group when initialised, else single GPU).  Rows must be (pixel, neighbour) pairs (train_nfr.py:447-448)."""
@@ -270,8 +275,8 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
     h = nets['fine_enc'].forward(E, E.shape[1])
     z_enc = nets['bottleneck'].forward(h, nets['fine_enc'].ld[-1])
     codebook = m.get_codebook()                                                   # :576, before the EMA assign
-    sel_mask = None
-    th = m._thres_mask(thres)
+    sel_mask = _sel_mask_dev           # graph replay: a static device mask refreshed by the caller
+    th = m._thres_mask(thres) if _sel_mask_dev is None else None
     if th is not None:
         vq = m.vq_layer
         if roll is None:
@@ -353,12 +358,79 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
                  'lambert': st.sums[4], 'vqloss': lw['vq_loss_weight'] * vq_loss[0],
                  'sim_smooth': sim_w * st.sim_loss[0], 'rows': st.sums[6]}
     if apply:
-        optimizer.apply_gradients(st.params, st.grads)
+        optimizer.apply_gradients(st.params, st.grads, lr_t_dev=_lr_t_dev)
         st.dirty = True
     partial_to_vis = {'id': id_, 'hw': hw, 'pred_rgb_linear': rgb_pred, 'pred_vq_rgb_linear': vq_rgb,
                       'pred_albedo': albedo, 'pred_spec': spec, 'pred_rough': rough_c, 'embed_ind': idx + 1,
                       'z_enc': z_enc, 'z_vq': z_vq, 'loss_rows': B['loss_rows']}
     return weighted, partial_to_vis, loss_dict
+
+
+class GraphedTrainIter:
+    """train_iter captured ONCE into a CUDA graph and replayed: the ~150 kernel launches of a step (plus the NCCL
+    all-reduce) become one graph launch, which is what makes the 8192-rays-per-GPU step GPU-bound instead of
+    launch-bound.  Inputs are copied into static buffers; the codeword-dropout mask and Adam's step-dependent
+    rate live in device memory so that a replay needs no re-capture.  Requires an all-foreground batch of a fixed
+    row count (what the reference's sampler produces, train_nfr.py:380-467)."""
+
+    def __init__(self, model, optimizer: Adam, global_bs: int, example_batch, use_thres: bool = True, group=None):
+        self.model, self.opt, self.gbs, self.group = model, optimizer, int(global_bs), group
+        dev = model.device
+        model.assume_all_foreground = True
+        self.static = [t.clone() if torch.is_tensor(t) else t for t in example_batch]
+        self.K = model.num_embed
+        self.sel_mask = torch.ones((self.K,), dtype=F32, device=dev) if use_thres else None
+        self.lr_t = torch.zeros((1,), dtype=F32, device=dev)
+        self._lr_host = torch.zeros((1,), dtype=F32).pin_memory()
+        self._mask_host = torch.ones((self.K,), dtype=F32).pin_memory()
+        # warm-up on a side stream (allocates the activation set, Adam state, NCCL buffers), then capture; the
+        # learned state touched by the warm-up steps is snapshotted and restored so that construction has no effect
+        st = _train_state(model)
+        optimizer.ensure_state(st.params)
+        vq = model.vq_layer
+        snap = (st.params.clone(), {k: v.clone() for k, v in vq.state.items()}, optimizer.iterations,
+                optimizer.m.clone(), optimizer.v.clone(), optimizer.vhat.clone(), vq._gen.get_state())
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._refresh(None, None)
+                self.out = train_iter(model, tuple(self.static), optimizer, self.gbs, group=group,
+                                      _sel_mask_dev=self.sel_mask, _lr_t_dev=self.lr_t)
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        st.params.copy_(snap[0])
+        for k, v in snap[1].items():
+            vq.state[k].copy_(v)
+        optimizer.iterations = snap[2]
+        optimizer.m.copy_(snap[3]); optimizer.v.copy_(snap[4]); optimizer.vhat.copy_(snap[5])
+        vq._gen.set_state(snap[6])
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, capture_error_mode='thread_local'):
+            self.out = train_iter(model, tuple(self.static), optimizer, self.gbs, group=group,
+                                  _sel_mask_dev=self.sel_mask, _lr_t_dev=self.lr_t)
+
+    def _refresh(self, thres, roll):
+        self.opt.iterations += 1
+        self._lr_host[0] = self.opt.lr_t()
+        self.lr_t.copy_(self._lr_host, non_blocking=True)
+        if self.sel_mask is not None:
+            if thres is None:
+                self._mask_host.fill_(1.0)
+            else:
+                th = torch.as_tensor(thres, dtype=F32).reshape(-1)
+                if roll is None:
+                    roll = torch.rand((1, self.K), generator=self.model.vq_layer._gen, dtype=F32)
+                self._mask_host.copy_((torch.as_tensor(roll, dtype=F32).reshape(-1) >= th).to(F32))
+            self.sel_mask.copy_(self._mask_host, non_blocking=True)
+
+    def __call__(self, batch, thres=None, roll=None):
+        for dst, src in zip(self.static, batch):
+            if torch.is_tensor(dst) and src is not dst:
+                dst.copy_(src, non_blocking=True)
+        self._refresh(thres, roll)
+        self.graph.replay()
+        return self.out
 
 
 def sync_inference_weights(model) -> None:
