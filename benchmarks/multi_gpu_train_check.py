@@ -1,0 +1,85 @@
+"""2-rank data-parallel training step == single-device global batch.  Run on a 2-GPU box:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 \
+        benchmarks/multi_gpu_train_check.py
+
+Every rank first runs the FULL 512-row batch alone (no process group yet), then the ranks shard the same batch
+(pairs kept together, dist.shard_rows(align=2)), run the step with the single NCCL all-reduce of
+[gradients | VQ statistics | loss sums], and compare parameters, EMA state and loss with the full-batch run.
+Also checks the pixel-sharded render + one all-gather against the single-device image."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import decomp_oracle as O  # noqa: E402  (synthetic inputs only)
+
+
+def build(dev):
+    from vqnerf_release_b200.nerfactor.models.vq_nfr import Model
+    scene = O.synth_scene(0, bias_scale=0.05, n_probes=2)
+    nets = {k: (n.weights, n.biases) for k, n in scene.nets.items()}
+    m = Model({'data_type': 'nerf'}, nets=nets, light=scene.light, codebook=scene.codebook.T.copy(),
+              novel_probes={'p%d' % i: p for i, p in enumerate(scene.probes)}, device=dev)
+    m.assume_all_foreground = True
+    return m
+
+
+def batch_tuple(b, dev, lo, hi):
+    t = lambda a: torch.as_tensor(a[lo:hi]).to(dev).contiguous()
+    n = hi - lo
+    return ('s', torch.zeros((n, 2), dtype=torch.int32, device=dev), t(b['rayo']), t(b['rayd']), t(b['rgb']),
+            t(b['alpha']), t(b['pred_alpha']), t(b['xyz']), t(b['normal']), t(b['lvis']))
+
+
+def main():
+    rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+    dev = torch.device('cuda', int(os.environ['LOCAL_RANK']))
+    torch.cuda.set_device(dev)
+    from vqnerf_release_b200 import dist as vdist
+    from vqnerf_release_b200.nerfactor import train_nfr as T
+    n, gbs, k = 512, 256, 15
+    batch = O.synth_batch(n, 0)
+    thres = np.array([0.0] * 3 + [0.4] * 12)
+    # ---- full batch on one device (no process group) ----
+    m1 = build(dev)
+    o1 = T.Adam(learning_rate=5e-4)
+    img1 = m1.fast_render(batch_tuple(batch, dev, 0, n), mode='test', relight_probes=True)[0]['rgb_probes'].clone()
+    losses1 = []
+    for it in range(2):
+        roll = np.random.RandomState(it).uniform(0, 1, size=(1, k))
+        l, _, _ = T.train_iter(m1, batch_tuple(batch, dev, 0, n), o1, gbs, thres=thres, roll=roll)
+        losses1.append(float(l))
+    torch.cuda.synchronize()
+    # ---- sharded ----
+    dist.init_process_group('nccl', device_id=dev)
+    lo, hi = vdist.shard_rows(n, rank, world, align=2)
+    m2 = build(dev)
+    o2 = T.Adam(learning_rate=5e-4)
+    img_local = m2.fast_render(batch_tuple(batch, dev, lo, hi), mode='test', relight_probes=True)[0]['rgb_probes']
+    img2 = vdist.gather_rows(img_local, n)
+    assert torch.equal(img1, img2), 'sharded render + all-gather differs from the single-device image'
+    losses2 = []
+    for it in range(2):
+        roll = np.random.RandomState(it).uniform(0, 1, size=(1, k))
+        l, _, _ = T.train_iter(m2, batch_tuple(batch, dev, lo, hi), o2, gbs, thres=thres, roll=roll)
+        losses2.append(float(l))
+    torch.cuda.synchronize()
+    p1, p2 = m1._train_state.params, m2._train_state.params
+    err = (p1 - p2).abs().max().item()
+    cs = (m1.vq_layer.state['cs_hidden'] - m2.vq_layer.state['cs_hidden']).abs().max().item()
+    dw = (m1.vq_layer.state['dw_hidden'] - m2.vq_layer.state['dw_hidden']).abs().max().item()
+    ok = err < 2e-5 and cs == 0.0 and dw < 1e-5 and np.allclose(losses1, losses2, rtol=1e-5)
+    print('rank %d: rows [%d,%d) max|param diff| %.3e  cs_hidden diff %.1e  dw_hidden diff %.1e  loss %s vs %s  -> %s'
+          % (rank, lo, hi, err, cs, dw, losses1, losses2, 'OK' if ok else 'MISMATCH'), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    if not ok:
+        raise SystemExit(1)
+
+
+if __name__ == '__main__':
+    main()
