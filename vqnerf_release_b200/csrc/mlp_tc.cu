@@ -40,6 +40,15 @@ struct TcLayer {
   int out_slot;           // >= 0: accumulator is written to global outs[out_slot] (row-major [point][N])
   int bias_off;           // offset of this layer's bias inside the shared-memory bias table
   float post_scale, post_bias;
+  int tmem_col;           // first TMEM column of this layer's accumulator
+  // Folded skip connection: concat(y, x) . W = y . W_y + x . W_x.  When the layer after the skip is narrow (Npad 16)
+  // its x-half is accumulated as a SIDE product of the network's first layer, whose A chunks are the same x
+  // chunks (side_w = W_x chunk images, 16 columns at TMEM column side_col); the narrow layer then only consumes
+  // its y chunks and its epilogue adds the side accumulator (add_col).  This halves the number of times the
+  // latent has to be re-read, split and staged per head.
+  const uint8_t* side_w;
+  int side_col;
+  int add_col;            // >= 0: final epilogue adds TMEM columns [add_col, add_col + 16)
 };
 
 struct TcProgram {
@@ -183,7 +192,9 @@ struct TcCfg {
   static constexpr int THREADS = 32 * (4 * G + 2);         // + MMA warp + weight-producer warp
   static constexpr uint32_t A_PLANE = TC_M * 128;          // 16 KB
   static constexpr uint32_t A_SLOT = A_PLANE * PLANES;
-  static constexpr uint32_t W_SLOT = (uint32_t)TC_NPAD_MAX * 128 * PLANES;
+  static constexpr uint32_t W_MAIN = (uint32_t)TC_NPAD_MAX * 128 * PLANES;
+  static constexpr uint32_t W_SIDE_PLANE = 16 * 128;       // side product: 16 output columns
+  static constexpr uint32_t W_SLOT = W_MAIN + W_SIDE_PLANE * PLANES;
   static constexpr size_t SMEM = (size_t)SA * A_SLOT + (size_t)SW * W_SLOT + 1024;
 };
 #define TC_BIAS_FLOATS 2048
@@ -338,7 +349,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
           const int first = pg.layers[l].seg_first_chunk[sg];
           const int pact = l > 0 ? pg.layers[l - 1].act : 0;
           const float* pbias = bias_s + (l > 0 ? pg.layers[l - 1].bias_off : 0);
-          const uint32_t pacc = lane_addr + (uint32_t)(((l - 1) & 1) * 256);
+          const uint32_t pacc = lane_addr + (uint32_t)(l > 0 ? pg.layers[l - 1].tmem_col : 0);
           bool acc_ready = false;
           for (int c = 0; c < nch; ++c, ++ga) {
             if ((int)(ga % C::G) != grp) continue;
@@ -348,10 +359,10 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
               acc_ready = true;
             }
             const int slot = ga % C::SA;
-            tc::mbar_wait(&a_empty[slot], ((ga / C::SA) & 1) ^ 1);
             uint8_t* dst = a_ring + (size_t)slot * C::A_SLOT;
             const int sc = first + c;                     // chunk index inside the source
             if (st == SRC_EMBED) {
+              tc::mbar_wait(&a_empty[slot], ((ga / C::SA) & 1) ^ 1);
               embed_chunk<BF16>(dst, r, x, sc * C::E, pg.n_freqs);
             } else {
 #pragma unroll
@@ -374,6 +385,9 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                     for (int j = 0; j < 32; ++j) v[j] = 0.f;
                   }
                 }
+                // the values are ready in registers BEFORE the slot is claimed: the TMEM / global load latency
+                // and the activation math overlap the MMAs that are still reading the slot's previous chunk
+                if (h == 0) tc::mbar_wait(&a_empty[slot], ((ga / C::SA) & 1) ^ 1);
                 store_chunk32<BF16>(dst, r, 32 * h, v);
               }
             }
@@ -393,7 +407,13 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
           const float* lb = bias_s + ly.bias_off;
           for (int cb = grp; cb * 32 < ly.N; cb += C::G) {
             float v[32];
-            tc::tmem_ld32(lane_addr + (uint32_t)((l & 1) * 256 + cb * 32), v);
+            tc::tmem_ld32(lane_addr + (uint32_t)(ly.tmem_col + cb * 32), v);
+            if (ly.add_col >= 0 && cb == 0) {            // folded skip connection: + x . W_x (16 columns)
+              float sv[32];
+              tc::tmem_ld32(lane_addr + (uint32_t)ly.add_col, sv);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] += sv[j];
+            }
             if (cb * 32 + 32 <= ly.Npad) bias_act32_dyn(v, lb + cb * 32, ly.act);
             else {
 #pragma unroll
@@ -432,19 +452,28 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
     if (lane == 0) {
       uint32_t ga = 0, gw = 0, gd = 0;
       bool pending_drain = false;
+      int pend_lo = 0, pend_hi = 0;         // TMEM columns of the accumulator still being drained to global
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int l = 0; l < L; ++l) {
           const TcLayer& ly = pg.layers[l];
           const uint32_t idesc = tc::make_idesc(BF16 ? tc::FMT_BF16 : tc::FMT_TF32, TC_M, ly.Npad);
-          const uint32_t d_tmem = tmem_base + (uint32_t)((l & 1) * 256);
+          const uint32_t idesc_side = tc::make_idesc(BF16 ? tc::FMT_BF16 : tc::FMT_TF32, TC_M, 16);
+          const uint32_t d_tmem = tmem_base + (uint32_t)ly.tmem_col;
+          const uint32_t d_side = tmem_base + (uint32_t)ly.side_col;
+          const bool side = ly.side_w != nullptr;
           const int nch = ly.seg_chunks[0] + (ly.nseg > 1 ? ly.seg_chunks[1] : 0);
           const uint32_t w_plane = (uint32_t)ly.Npad * 128;
-          if (pending_drain) {              // a final layer is being drained to global: wait before any overwrite
-            tc::mbar_wait(&drain_done, gd & 1);
-            tc::fence_after_sync();
-            ++gd; pending_drain = false;
+          if (pending_drain) {
+            // a final layer is being drained to global: wait before overwriting ITS columns (other columns may go on)
+            const bool hit = (ly.tmem_col < pend_hi && ly.tmem_col + ly.Npad > pend_lo) ||
+                             (side && ly.side_col < pend_hi && ly.side_col + 16 > pend_lo) || ly.out_slot >= 0;
+            if (hit) {
+              tc::mbar_wait(&drain_done, gd & 1);
+              tc::fence_after_sync();
+              ++gd; pending_drain = false;
+            }
           }
-          uint32_t acc = 0;
+          uint32_t acc = 0, acc_s = 0;
           for (int c = 0; c < nch; ++c, ++ga, ++gw) {
             const int sa = ga % C::SA, sw = gw % C::SW;
             tc::mbar_wait(&a_full[sa], (ga / C::SA) & 1);
@@ -464,12 +493,23 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                 tc::mma_ss<true>(d_tmem, a_lo, b_hi, idesc, 1);
                 tc::mma_ss<true>(d_tmem, a_hi, b_lo, idesc, 1);
               }
+              if (side) {
+                const uint64_t s_hi = tc::make_desc_sw128(w_addr + C::W_MAIN + 32 * s);
+                tc::mma_ss<!BF16>(d_side, a_hi, s_hi, idesc_side, acc_s);
+                acc_s = 1;
+                if (!BF16) {
+                  const uint64_t a_lo = tc::make_desc_sw128(a_addr + C::A_PLANE + 32 * s);
+                  const uint64_t s_lo = tc::make_desc_sw128(w_addr + C::W_MAIN + C::W_SIDE_PLANE + 32 * s);
+                  tc::mma_ss<true>(d_side, a_lo, s_hi, idesc_side, 1);
+                  tc::mma_ss<true>(d_side, a_hi, s_lo, idesc_side, 1);
+                }
+              }
             }
             tc::mma_commit(&a_empty[sa]);       // slots are free once these MMAs have read them
             tc::mma_commit(&w_empty[sw]);
           }
           tc::mma_commit(&acc_full);            // layer complete -> epilogue warps may drain it
-          if (ly.out_slot >= 0) pending_drain = true;
+          if (ly.out_slot >= 0) { pending_drain = true; pend_lo = ly.tmem_col; pend_hi = ly.tmem_col + ly.Npad; }
         }
       }
     }
@@ -486,8 +526,12 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
           for (int c = 0; c < nch; ++c, ++gw) {
             const int sw = gw % C::SW;
             tc::mbar_wait(&w_empty[sw], ((gw / C::SW) & 1) ^ 1);
-            tc::mbar_expect_tx(&w_full[sw], bytes);
+            const uint32_t sbytes = ly.side_w ? C::W_SIDE_PLANE * C::PLANES : 0u;
+            tc::mbar_expect_tx(&w_full[sw], bytes + sbytes);
             tc::bulk_g2s(w_ring + (size_t)sw * C::W_SLOT, ly.w + (size_t)c * bytes, bytes, &w_full[sw]);
+            if (sbytes)
+              tc::bulk_g2s(w_ring + (size_t)sw * C::W_SLOT + C::W_MAIN, ly.side_w + (size_t)c * sbytes, sbytes,
+                           &w_full[sw]);
           }
         }
       }
@@ -512,8 +556,9 @@ struct TcBuilder {
 // Append one network.  first_src: where its input x comes from (SRC_EMBED / SRC_GLOBAL / SRC_DRAIN = output of the
 // previous appended layer).  out_slot: global output slot of the last layer (-1: it feeds the next network).
 static bool tc_append_net(TcBuilder& B, vqn_net* net, TcPack* tp, int first_src, int out_slot, float post_scale,
-                          float post_bias) {
+                          float post_bias, int fold_side_col = -1) {
   const vqn_net_desc& d = net->desc;
+  const int first_layer = B.pg.n_layers;
   for (int i = 0; i < d.n_layers; ++i) {
     if (B.pg.n_layers >= TC_MAX_LAYERS) return false;
     TcLayer& ly = B.pg.layers[B.pg.n_layers];
@@ -521,6 +566,7 @@ static bool tc_append_net(TcBuilder& B, vqn_net* net, TcPack* tp, int first_src,
     ly.w = tp->w[i]; ly.bias = tp->bias[i];
     ly.N = d.widths[i]; ly.Npad = tp->Npad[i]; ly.act = d.acts[i];
     ly.out_slot = -1; ly.post_scale = 1.f; ly.post_bias = 0.f;
+    ly.tmem_col = (B.pg.n_layers & 1) * 256; ly.side_w = nullptr; ly.side_col = 0; ly.add_col = -1;
     const bool after_skip = (d.skip_at >= 0 && i == d.skip_at + 1);
     const int seg0_rows = (i == 0) ? d.in_dim : d.widths[i - 1];
     ly.nseg = 1;
@@ -530,10 +576,20 @@ static bool tc_append_net(TcBuilder& B, vqn_net* net, TcPack* tp, int first_src,
     if (ly.seg_type[0] == SRC_DRAIN && B.pg.n_layers == 0) return false;
     if (after_skip) {
       if (first_src == SRC_DRAIN) return false;   // x must be regenerable (embedding / global rows)
-      ly.nseg = 2;
-      ly.seg_type[1] = first_src;
-      ly.seg_chunks[1] = vqn_round_up(d.in_dim, B.E) / B.E;
-      ly.seg_first_chunk[1] = 0;
+      const int xc = vqn_round_up(d.in_dim, B.E) / B.E;
+      if (fold_side_col >= 0 && tp->Npad[i] == 16 && i > 0) {
+        // fold the x-half into a side product of the first layer (same x chunks, 16 output columns)
+        TcLayer& l0 = B.pg.layers[first_layer];
+        const size_t chunk_bytes = (size_t)16 * 128 * (B.E == 64 ? 1 : 2);
+        l0.side_w = tp->w[i] + (size_t)ly.seg_chunks[0] * chunk_bytes;
+        l0.side_col = fold_side_col;
+        ly.add_col = fold_side_col;
+      } else {
+        ly.nseg = 2;
+        ly.seg_type[1] = first_src;
+        ly.seg_chunks[1] = xc;
+        ly.seg_first_chunk[1] = 0;
+      }
     }
     if (i == d.n_layers - 1) { ly.out_slot = out_slot; ly.post_scale = post_scale; ly.post_bias = post_bias; }
     if (ly.Npad > TC_NPAD_MAX) return false;
@@ -607,8 +663,16 @@ int vqn_tc_pred_heads(vqn_ctx* ctx, vqn_net* diff, vqn_net* spec, vqn_net* rough
     int rc = tc_pack_get(nets[h], precision, s, &tp);
     if (rc != VQN_OK) return rc;
     B.pg.outs[h] = outs[h]; B.pg.out_stride[h] = nets[h]->desc.widths[nets[h]->n_layers - 1];
-    if (!tc_append_net(B, nets[h], tp, SRC_GLOBAL, h, h == 0 ? slope : 1.f, h == 0 ? bias : 0.f))
+    // TMEM plan of a [256, 128, out] head: layer 0 at columns [0,256), layer 1 at [256,384), the folded skip
+    // products of the three heads at [384 + 16 h, +16), the narrow last layer at [448,464)
+    const vqn_net_desc& hd = nets[h]->desc;
+    const bool plan = hd.n_layers == 3 && hd.skip_at == 1 && hd.widths[0] <= 256 && hd.widths[1] <= 128 &&
+                      tp->Npad[2] == 16;
+    const int l0 = B.pg.n_layers;
+    if (!tc_append_net(B, nets[h], tp, SRC_GLOBAL, h, h == 0 ? slope : 1.f, h == 0 ? bias : 0.f,
+                       plan ? 384 + 16 * h : -1))
       TC_UNSUPPORTED("pred_heads: program does not fit the tensor-core kernel");
+    if (plan) { B.pg.layers[l0].tmem_col = 0; B.pg.layers[l0 + 1].tmem_col = 256; B.pg.layers[l0 + 2].tmem_col = 448; }
   }
   if (B.pg.g_dim % 4 != 0) TC_UNSUPPORTED("pred_heads: z_dim % 4 != 0");
   return tc_launch(ctx, B.pg, precision, s);
