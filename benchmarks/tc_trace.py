@@ -1,0 +1,58 @@
+"""Per-layer time stamps of the tcgen05 MLP kernel's MMA thread (CTA 0, first 4 tiles) -- diagnostic.
+
+    python benchmarks/tc_trace.py [--precision tf32x3]
+Prints, per layer: wait for the previous drain, wait for the first A/W chunk, time to issue all chunks (which
+includes waiting for A slots to be refilled), in SM clock cycles."""
+import argparse
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--precision', default='tf32x3')
+    ap.add_argument('--points', type=int, default=640000)
+    args = ap.parse_args()
+    from vqnerf_release_b200 import _lib, abi
+    from vqnerf_release_b200.nerfactor.models.vq_nfr import Model
+    dev = torch.device('cuda:0')
+    m = Model({'data_type': 'nerf', 'precision': args.precision}, device=dev)
+    ctx = _lib.Context.get(dev)
+    n = args.points
+    xyz = torch.rand((n, 3), device=dev) * 2 - 1
+    nf = m.embedder['xyz'].n_freqs
+    buf = torch.zeros((4 * 16 * 4,), dtype=torch.int64, device=dev)
+    ctx.lib.vqn_debug_tc_trace.argtypes = [C.c_void_p]
+    for which in ('encoder', 'heads'):
+        z = abi.pred_enc_at(m.net['fine_enc'].packed, m.net['bottleneck'].packed, nf, xyz, precision=args.precision)
+        torch.cuda.synchronize()
+        buf.zero_()
+        ctx.lib.vqn_debug_tc_trace(C.c_void_p(buf.data_ptr()))
+        if which == 'encoder':
+            abi.pred_enc_at(m.net['fine_enc'].packed, m.net['bottleneck'].packed, nf, xyz, precision=args.precision)
+        else:
+            abi.pred_heads(m.net['diff_main'].packed, m.net['spec_main'].packed, m.net['rough_main'].packed, z, 1.0, 0.0,
+                           args.precision)
+        torch.cuda.synchronize()
+        ctx.lib.vqn_debug_tc_trace(None)
+        t = buf.cpu().numpy().reshape(4, 16, 4)
+        print('==', which, args.precision)
+        for tile in (1, 2):
+            base = t[tile, 0, 0]
+            nl = int((t[tile, :, 3] != 0).sum())
+            print(' tile %d (starts %d cycles after tile %d started)' % (tile, base - t[tile - 1, 0, 0], tile - 1))
+            for l in range(nl):
+                a, b, c, d = t[tile, l]
+                print('   layer %2d: begin +%6d | drain-wait %5d | first-chunk wait %5d | issue %6d' % (l, a - base, b - a, c - b, d - c))
+            print('   tile total: %d cycles' % (t[tile, nl - 1, 3] - base))
+
+
+if __name__ == '__main__':
+    main()

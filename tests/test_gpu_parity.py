@@ -373,3 +373,44 @@ def test_native_library_is_what_ran(cuda_dev):
     assert ctx.launch_count() > 0
     maps = open('/proc/self/maps').read()
     assert 'libvqnerf_b200.so' in maps
+
+
+@pytest.mark.parametrize('n_probes,with_lvis', [(0, True), (2, True), (8, True), (4, False)])
+def test_shade_thread_per_point_kernel(cuda_dev, n_probes, with_lvis):
+    """Batches >= 32768 points take the thread-per-point kernel (light tables in the constant bank): it must agree
+    with the warp-per-point kernel (same batch in small pieces) and with the float64 oracle."""
+    from vqnerf_release_b200 import abi
+    n = 40000
+    scene = O.synth_scene(7, n_probes=n_probes)
+    b = O.synth_batch(n, 7, with_lvis=with_lvis)
+    rng = np.random.RandomState(1)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).to(cuda_dev)
+    alb, f0 = rng.uniform(0, 1, (n, 3)).astype(np.float32), rng.uniform(0, 1, (n, 3)).astype(np.float32)
+    rough = rng.uniform(0.3, 1, (n, 1)).astype(np.float32)
+    lights = scene.light[None] if scene.probes is None else np.concatenate([scene.light[None], scene.probes], 0)
+    lights = t(lights.reshape(lights.shape[0], 512, 3))
+    lx, la = t(scene.lxyz.reshape(-1, 3)), t(scene.lareas.reshape(-1))
+    lvis = t(b['lvis']) if with_lvis else None
+    big = abi.shade(t(b['xyz']), t(b['rayo']), t(b['normal']), lvis, t(alb), t(f0), t(rough), lx, la, lights)['rgb']
+    parts = []
+    for lo in range(0, n, 10000):
+        s = slice(lo, lo + 10000)
+        parts.append(abi.shade(t(b['xyz'][s]), t(b['rayo'][s]), t(b['normal'][s]), None if lvis is None else lvis[s].contiguous(),
+                               t(alb[s]), t(f0[s]), t(rough[s]), lx, la, lights)['rgb'])
+    small = torch.cat(parts, 0)
+    _close(big, small, 'thread-per-point vs warp-per-point', rtol=1e-5, atol=2e-6)
+    # oracle on the first 256 points
+    m = 256
+    dt = torch.float64
+    xyz, rayo, normal = (torch.as_tensor(b[k][:m], dtype=dt) for k in ('xyz', 'rayo', 'normal'))
+    lxyz = torch.as_tensor(scene.lxyz, dtype=torch.float32).to(dt)
+    lareas = torch.as_tensor(scene.lareas, dtype=torch.float32).to(dt)
+    s2l, s2c = O.calc_ldir(lxyz, xyz), O.calc_vdir(rayo, xyz)
+    nrm = O.normal_correct(normal, s2c)
+    brdf, _, _ = O.get_brdf(s2l, s2c, nrm, torch.as_tensor(alb[:m], dtype=dt), torch.as_tensor(rough[:m], dtype=dt),
+                            torch.as_tensor(f0[:m], dtype=dt))
+    lv = torch.as_tensor(b['lvis'][:m], dtype=dt) if with_lvis else None
+    probes = None if scene.probes is None else torch.as_tensor(scene.probes, dtype=dt)
+    rgb, rgbp = O.render(brdf, s2l, nrm, lareas, torch.clamp(torch.as_tensor(scene.light, dtype=dt), min=0), lv, probes)
+    ref = rgb[:, None, :] if rgbp is None else torch.cat([rgb[:, None, :], rgbp], 1)
+    _close(big[:m], ref, 'thread-per-point vs oracle', rtol=1e-4, atol=5e-6)

@@ -63,6 +63,7 @@ struct TcProgram {
   float* outs[4];
   int out_stride[4];
   int* nonfinite;
+  long long* trace;        // diagnostic (vqn_debug_tc_trace): clock64 stamps of CTA 0's MMA thread, 4 per layer
   TcLayer layers[TC_MAX_LAYERS];
 };
 
@@ -361,6 +362,11 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
             const int slot = ga % C::SA;
             uint8_t* dst = a_ring + (size_t)slot * C::A_SLOT;
             const int sc = first + c;                     // chunk index inside the source
+#ifdef TC_EXP_NO_PROD
+            if (sc >= 0) {
+              tc::mbar_wait(&a_empty[slot], ((ga / C::SA) & 1) ^ 1);
+            } else
+#endif
             if (st == SRC_EMBED) {
               tc::mbar_wait(&a_empty[slot], ((ga / C::SA) & 1) ^ 1);
               embed_chunk<BF16>(dst, r, x, sc * C::E, pg.n_freqs);
@@ -463,6 +469,9 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
           const bool side = ly.side_w != nullptr;
           const int nch = ly.seg_chunks[0] + (ly.nseg > 1 ? ly.seg_chunks[1] : 0);
           const uint32_t w_plane = (uint32_t)ly.Npad * 128;
+          long long* tr = (pg.trace && blockIdx.x == 0 && tile < 4 * (long long)gridDim.x)
+                              ? pg.trace + ((tile / gridDim.x) * TC_MAX_LAYERS + l) * 4 : nullptr;
+          if (tr) tr[0] = clock64();
           if (pending_drain) {
             // a final layer is being drained to global: wait before overwriting ITS columns (other columns may go on)
             const bool hit = (ly.tmem_col < pend_hi && ly.tmem_col + ly.Npad > pend_lo) ||
@@ -476,11 +485,16 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
           uint32_t acc = 0, acc_s = 0;
           for (int c = 0; c < nch; ++c, ++ga, ++gw) {
             const int sa = ga % C::SA, sw = gw % C::SW;
+            if (tr && c == 0) tr[1] = clock64();
             tc::mbar_wait(&a_full[sa], (ga / C::SA) & 1);
             tc::mbar_wait(&w_full[sw], (gw / C::SW) & 1);
             tc::fence_after_sync();
+            if (tr && c == 0) tr[2] = clock64();
             const uint32_t a_addr = tc::smem_u32(a_ring + (size_t)sa * C::A_SLOT);
             const uint32_t w_addr = tc::smem_u32(w_ring + (size_t)sw * C::W_SLOT);
+#ifdef TC_EXP_NO_MMA
+            if (tile >= 0) { tc::mma_commit(&a_empty[sa]); tc::mma_commit(&w_empty[sw]); continue; }
+#endif
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
               const uint64_t a_hi = tc::make_desc_sw128(a_addr + 32 * s);
@@ -509,6 +523,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
             tc::mma_commit(&w_empty[sw]);
           }
           tc::mma_commit(&acc_full);            // layer complete -> epilogue warps may drain it
+          if (tr) tr[3] = clock64();
           if (ly.out_slot >= 0) { pending_drain = true; pend_lo = ly.tmem_col; pend_hi = ly.tmem_col + ly.Npad; }
         }
       }
@@ -527,6 +542,9 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
             const int sw = gw % C::SW;
             tc::mbar_wait(&w_empty[sw], ((gw / C::SW) & 1) ^ 1);
             const uint32_t sbytes = ly.side_w ? C::W_SIDE_PLANE * C::PLANES : 0u;
+#ifdef TC_EXPERIMENT_NO_W
+            if (gw >= (uint32_t)C::SW) { tc::mbar_arrive(&w_full[sw]); continue; }
+#endif
             tc::mbar_expect_tx(&w_full[sw], bytes + sbytes);
             tc::bulk_g2s(w_ring + (size_t)sw * C::W_SLOT, ly.w + (size_t)c * bytes, bytes, &w_full[sw]);
             if (sbytes)
@@ -598,8 +616,14 @@ static bool tc_append_net(TcBuilder& B, vqn_net* net, TcPack* tp, int first_src,
   return true;
 }
 
+// diagnostic knob (not part of include/vqnerf_b200.h): device buffer of >= 4 * 16 * 4 int64 that receives the
+// MMA-thread time stamps of the next launches (NULL: off)
+static long long* g_tc_trace = nullptr;
+extern "C" void vqn_debug_tc_trace(long long* dev_buf) { g_tc_trace = dev_buf; }
+
 static int tc_launch(vqn_ctx* ctx, TcProgram& pg, int precision, cudaStream_t s) {
   pg.nonfinite = ctx->nonfinite_flag;
+  pg.trace = g_tc_trace;
   int boff = 0;
   for (int l = 0; l < pg.n_layers; ++l) { pg.layers[l].bias_off = boff; boff += vqn_round_up(pg.layers[l].Npad, 32); }
   if (boff > TC_BIAS_FLOATS) { vqn_set_error("tensor-core MLP: bias table exceeds %d floats", TC_BIAS_FLOATS); return VQN_ERR_UNSUPPORTED; }

@@ -279,6 +279,8 @@ __global__ void __launch_bounds__(SH_THREADS, 2) shade_kernel(ShadeParams P) {
   }
 }
 
+int vqn_shade_pt_launch(vqn_ctx* ctx, const vqn_shade_args& a, cudaStream_t s);   // shade_pt.cu
+
 extern "C" int vqn_shade(vqn_ctx* ctx, const vqn_shade_args* args, vqn_stream stream) {
   VQN_CHECK_ARG(ctx && args, "shade: null args");
   const vqn_shade_args& a = *args;
@@ -293,6 +295,9 @@ extern "C" int vqn_shade(vqn_ctx* ctx, const vqn_shade_args* args, vqn_stream st
   size_t smem = sizeof(float) * (3 * SH_L + (size_t)a.n_probes * 3 * SH_L);
   VQN_CHECK_ARG((int)smem <= ctx->max_smem_optin, "shade: probe tables exceed shared memory");
   const bool split = a.rgb_diff || a.rgb_spec;
+  // large un-split batches: thread-per-point kernel with the light tables in the constant bank (shade_pt.cu);
+  // small batches (training, 8192 rays) keep the warp-per-point kernel, which exposes 32x more parallelism
+  if (!split && a.n_probes <= 9 && a.n >= 32768) return vqn_shade_pt_launch(ctx, a, vqn_cs(stream));
   auto kern = a.lvis ? (split ? shade_kernel<true, true> : shade_kernel<true, false>)
                      : (split ? shade_kernel<false, true> : shade_kernel<false, false>);
   VQN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1,0 +1,201 @@
+// Light-integral kernel, thread-per-point form (large batches: full-image relighting).
+//
+// Reference: models/shape.py:103-119, models/vq_nfr.py:694-733,830-874, util/microfacet.py:9-89 -- the same
+// arithmetic as shade_kernel (shade.cu), with the roles of lanes swapped: a THREAD owns one surface point and
+// walks the 512 lights, so the per-light data (light position, probe radiance x area) is warp-UNIFORM: every
+// shared-memory read is a broadcast (one wavefront for 32 points).  Compared with the warp-per-point kernel
+// this removes (i) its shared-memory bottleneck -- there 27 LDS.128 per 4 lights serve ONE point, i.e. 4x the
+// 128 B/clk smem port at full FMA rate; here the same 27 reads serve 32 points --, (ii) the cross-lane
+// reductions and (iii) the 48 registers of per-light weights: the 3 x (1+P) sums stay in the thread's registers.
+// The point's visibility row is read as one 16-byte load per 4 lights (every 128-byte line is consumed by 8
+// consecutive loads of the same thread and stays in L1 meanwhile).  (A first version kept the tables in the
+// constant bank: 61 KB swept by 24 warps at different offsets thrashes the constant cache -- 6.7 ms vs 2.6 ms.)
+//
+// Light image (61 440 B, built on the launching stream before every launch since the model light is trainable):
+// per group of 4 lights, 3 float4 of light positions (x, y, z of the 4 lights) and 27 float4 of radiance x area
+// ((probe, channel)-major, the 4 lights in the components).  One persistent 640-thread block per SM copies it
+// into shared memory once and walks 32-point tiles, warp-strided.
+#include "common.cuh"
+
+#define SP_L 512
+#define SP_GROUPS (SP_L / 4)
+#define SP_MAXP 9
+#define SP_F4_PER_GROUP (3 + 3 * SP_MAXP)
+
+#define SP_THREADS 640
+
+namespace {
+
+__device__ __forceinline__ float fast_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// staging image in device memory (copied to c_shade with a D2D memcpy-to-symbol)
+__global__ void shade_pt_prep_kernel(const float* __restrict__ lxyz, const float* __restrict__ lareas,
+                                     const float* __restrict__ lights, int n_probes, int clip_light0,
+                                     float4* __restrict__ img) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;       // one float4 of the image
+  if (i >= SP_GROUPS * SP_F4_PER_GROUP) return;
+  const int grp = i / SP_F4_PER_GROUP, k = i % SP_F4_PER_GROUP;
+  float v[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int l = 4 * grp + q;
+    if (k < 3) {
+      v[q] = lxyz[3 * l + k];
+    } else {
+      const int p = (k - 3) / 3, ch = (k - 3) % 3;
+      float r = 0.f;
+      if (p < n_probes) {
+        r = lights[((size_t)p * SP_L + l) * 3 + ch];
+        if (p == 0 && clip_light0) r = fmaxf(r, 0.f);          // clip(_light, 0, inf), vq_nfr.py:759
+        r *= lareas[l];
+      }
+      v[q] = r;
+    }
+  }
+  img[i] = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+template <int NPC, bool HAS_LVIS>
+__global__ void __launch_bounds__(SP_THREADS, 1) shade_pt_kernel(vqn_shade_args a, const float4* __restrict__ img,
+                                                                 int* nonfinite) {
+  extern __shared__ __align__(16) float4 s_img[];
+  for (int k = threadIdx.x; k < SP_GROUPS * SP_F4_PER_GROUP; k += SP_THREADS) s_img[k] = img[k];
+  __syncthreads();
+  long long n = a.n_dev ? (long long)*a.n_dev : a.n;
+  if (n > a.n) n = a.n;
+  const int lane = threadIdx.x & 31;
+  const long long warps_total = (long long)gridDim.x * (SP_THREADS / 32);
+  const long long warp0 = (long long)blockIdx.x * (SP_THREADS / 32) + (threadIdx.x >> 5);
+  for (long long tile = warp0; tile * 32 < n; tile += warps_total) {
+  const long long i = tile * 32 + lane;
+  if (i >= n) continue;
+  const long long row = a.row_idx ? (long long)a.row_idx[i] : i;
+  const float INV_PI = 0.318309886183790671538f;
+  const float px = a.xyz[row * 3], py = a.xyz[row * 3 + 1], pz = a.xyz[row * 3 + 2];
+  float vx = a.rayo[row * 3] - px, vy = a.rayo[row * 3 + 1] - py, vz = a.rayo[row * 3 + 2] - pz;
+  {  // _calc_vdir: safe_l2_normalize (eps on the squared norm)
+    const float inv = rsqrtf(fmaxf(vx * vx + vy * vy + vz * vz, 1e-6f));
+    vx *= inv; vy *= inv; vz *= inv;
+  }
+  float nx = a.normal[row * 3], ny = a.normal[row * 3 + 1], nz = a.normal[row * 3 + 2];
+  {  // _normal_correct: where(n.v >= 0, n, -n)
+    const float c = nx * vx + ny * vy + nz * vz;
+    if (!(c >= 0.f)) { nx = -nx; ny = -ny; nz = -nz; }
+  }
+  if (a.normal_out) { a.normal_out[row * 3] = nx; a.normal_out[row * 3 + 1] = ny; a.normal_out[row * 3 + 2] = nz; }
+  const float inv_n = rsqrtf(fmaxf(nx * nx + ny * ny + nz * nz, 1e-6f));
+  const float vn = (nx * vx + ny * vy + nz * vz) * inv_n;
+  const float alb0 = a.albedo[i * 3] * INV_PI, alb1 = a.albedo[i * 3 + 1] * INV_PI, alb2 = a.albedo[i * 3 + 2] * INV_PI;
+  const float f00 = a.spec[i * 3], f01 = a.spec[i * 3 + 1], f02 = a.spec[i * 3 + 2];
+  const float rough = a.rough[i];
+  const float alpha = rough * rough, a2 = alpha * alpha;        // microfacet.py:25; helpers use alpha ** 2
+  const float oma2 = 1.0f - a2, a2m1 = a2 - 1.0f;
+  const float cv = fminf(fmaxf(vn, 0.f), 1.f);
+  const float den_v = cv + sqrtf(fabsf(a2 + oma2 * cv * cv));
+  const float g_v = den_v == 0.f ? 0.f : 2.0f * cv / den_v;
+  const float avn = fabsf(vn);
+  const float a_pt = avn == 0.f ? 0.f : a2 * g_v * (0.5f * INV_PI) / avn;
+
+  float out[NPC * 3];
+#pragma unroll
+  for (int k = 0; k < NPC * 3; ++k) out[k] = 0.f;
+  const float4* lv = reinterpret_cast<const float4*>(a.lvis + (HAS_LVIS ? row * SP_L : 0));
+  float4 lv_cur = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (HAS_LVIS) lv_cur = __ldg(lv);
+
+#pragma unroll 1
+  for (int grp = 0; grp < SP_GROUPS; ++grp) {
+    float4 lv_nxt = lv_cur;
+    if (HAS_LVIS && grp + 1 < SP_GROUPS) lv_nxt = __ldg(lv + grp + 1);
+    const float4* cg = s_img + grp * SP_F4_PER_GROUP;          // warp-uniform address: broadcast reads
+    const float4 X = cg[0], Y = cg[1], Z = cg[2];
+    const float xs4[4] = {X.x, X.y, X.z, X.w}, ys4[4] = {Y.x, Y.y, Y.z, Y.w}, zs4[4] = {Z.x, Z.y, Z.z, Z.w};
+    const float lvv[4] = {lv_cur.x, lv_cur.y, lv_cur.z, lv_cur.w};
+    float e[4][3];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float dx = xs4[q] - px, dy = ys4[q] - py, dz = zs4[q] - pz;
+      const float inv = fast_rsqrt(fmaxf(dx * dx + dy * dy + dz * dz, 1e-6f));   // _calc_ldir
+      dx *= inv; dy *= inv; dz *= inv;
+      const float cos_r = dx * nx + dy * ny + dz * nz;          // _render: cos = l . n
+      const float ln = cos_r * inv_n;                           // get_brdf: l . normalize(n)
+      const float lvd = dx * vx + dy * vy + dz * vz;
+      const float t = 1.0f + lvd;                               // |l + v|^2 = 2 + 2 l.v
+      const float hinv = fast_rsqrt(fmaxf(2.0f * t, 1e-6f));
+      const float hv = fminf(fmaxf(t * hinv, 0.f), 1.f);
+      const float hn = fminf(fmaxf((ln + vn) * hinv, 0.f), 1.f);
+      const float om = 1.0f - hv, om2 = om * om;
+      const float p5 = om2 * om2 * om;                          // (1 - h.v)^5
+      const float q_ = fmaf(hn * hn, a2m1, 1.0f);
+      const float cl = fminf(fmaxf(ln, 0.f), 1.f);
+      const float den_l = cl + fast_sqrt(fabsf(fmaf(oma2, cl * cl, a2)));
+      const float den = q_ * q_ * den_l * fabsf(ln);
+      const float S = den == 0.f ? 0.f : __fdividef(a_pt * cl, den);
+      float wv = cos_r > 0.f ? cos_r : 0.f;                     // front_lit * cos
+      if (HAS_LVIS) wv *= lvv[q];
+      const float sw = S * wv, psw = p5 * sw, dsw = sw - psw;   // F S w = psw + f0 (sw - psw)
+      e[q][0] = fmaf(alb0, wv, fmaf(f00, dsw, psw));
+      e[q][1] = fmaf(alb1, wv, fmaf(f01, dsw, psw));
+      e[q][2] = fmaf(alb2, wv, fmaf(f02, dsw, psw));
+    }
+#pragma unroll
+    for (int p = 0; p < NPC; ++p)
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        const float4 R = cg[3 + p * 3 + ch];
+        float o = out[p * 3 + ch];
+        o = fmaf(e[0][ch], R.x, o); o = fmaf(e[1][ch], R.y, o);
+        o = fmaf(e[2][ch], R.z, o); o = fmaf(e[3][ch], R.w, o);
+        out[p * 3 + ch] = o;
+      }
+    lv_cur = lv_nxt;
+  }
+  if (!a.rgb) continue;
+  const int NP = a.n_probes;
+#pragma unroll
+  for (int p = 0; p < NPC; ++p) {
+    if (p >= NP) break;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float v = out[p * 3 + ch];
+      if (a.use_gamma) v = powf(v * a.gamma_bias, a.gamma_index);     // vq_nfr.py:715-716
+      if (!isfinite(v)) atomicOr(nonfinite, 2);                        // check_numerics (:731)
+      v = fminf(fmaxf(v, 0.f), 1.f);                                   // clip_by_value (:718)
+      if (a.to_srgb) v = vqn_linear2srgb(v);
+      a.rgb[(row * NP + p) * 3 + ch] = v;
+    }
+  }
+  }   // tile loop
+}
+
+template <int NPC>
+int launch_pt(vqn_ctx* ctx, const vqn_shade_args& a, const float4* img, cudaStream_t s) {
+  const size_t smem = sizeof(float4) * SP_GROUPS * SP_F4_PER_GROUP;
+  long long want = (a.n + SP_THREADS - 1) / SP_THREADS;
+  const unsigned blocks = (unsigned)(want < (long long)ctx->sm_count ? want : (long long)ctx->sm_count);
+  if (a.lvis) {
+    VQN_CUDA(cudaFuncSetAttribute(shade_pt_kernel<NPC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    shade_pt_kernel<NPC, true><<<blocks, SP_THREADS, smem, s>>>(a, img, ctx->nonfinite_flag);
+  } else {
+    VQN_CUDA(cudaFuncSetAttribute(shade_pt_kernel<NPC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    shade_pt_kernel<NPC, false><<<blocks, SP_THREADS, smem, s>>>(a, img, ctx->nonfinite_flag);
+  }
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}
+
+}  // namespace
+
+// called by vqn_shade (shade.cu) for large un-split batches with at most SP_MAXP probes
+int vqn_shade_pt_launch(vqn_ctx* ctx, const vqn_shade_args& a, cudaStream_t s) {
+  // staging image in the upper half of the context's persistent scratch (stream-ordered: prep, then the kernel)
+  float4* img = reinterpret_cast<float4*>(ctx->scratch + 32768);
+  const int total = SP_GROUPS * SP_F4_PER_GROUP;
+  shade_pt_prep_kernel<<<(total + 127) / 128, 128, 0, s>>>(a.lxyz, a.lareas, a.lights, a.n_probes, a.clip_light0, img);
+  VQN_LAUNCHED(ctx);
+  if (a.n_probes <= 1) return launch_pt<1>(ctx, a, img, s);
+  if (a.n_probes <= 3) return launch_pt<3>(ctx, a, img, s);
+  if (a.n_probes <= 5) return launch_pt<5>(ctx, a, img, s);
+  return launch_pt<SP_MAXP>(ctx, a, img, s);
+}
