@@ -13,7 +13,7 @@
 //
 // Light image (61 440 B, built on the launching stream before every launch since the model light is trainable):
 // per group of 4 lights, 3 float4 of light positions (x, y, z of the 4 lights) and 27 float4 of radiance x area
-// ((probe, channel)-major, the 4 lights in the components).  One persistent 640-thread block per SM copies it
+// ((probe, channel)-major, the 4 lights in the components).  One persistent 512-thread block per SM copies it
 // into shared memory once and walks 32-point tiles, warp-strided.
 #include "common.cuh"
 
@@ -22,7 +22,7 @@
 #define SP_MAXP 9
 #define SP_F4_PER_GROUP (3 + 3 * SP_MAXP)
 
-#define SP_THREADS 640
+#define SP_THREADS 512
 
 namespace {
 
