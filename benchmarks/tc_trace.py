@@ -28,7 +28,7 @@ def main():
     n = args.points
     xyz = torch.rand((n, 3), device=dev) * 2 - 1
     nf = m.embedder['xyz'].n_freqs
-    buf = torch.zeros((4 * 16 * 4,), dtype=torch.int64, device=dev)
+    buf = torch.zeros((256 + 8 * 96,), dtype=torch.int64, device=dev)
     ctx.lib.vqn_debug_tc_trace.argtypes = [C.c_void_p]
     for which in ('encoder', 'heads'):
         z = abi.pred_enc_at(m.net['fine_enc'].packed, m.net['bottleneck'].packed, nf, xyz, precision=args.precision)
@@ -42,7 +42,9 @@ def main():
                            args.precision)
         torch.cuda.synchronize()
         ctx.lib.vqn_debug_tc_trace(None)
-        t = buf.cpu().numpy().reshape(4, 16, 4)
+        raw = buf.cpu().numpy()
+        t = raw[:256].reshape(4, 16, 4)
+        pt = raw[256:].reshape(96, 8)
         print('==', which, args.precision)
         for tile in (1, 2):
             base = t[tile, 0, 0]
@@ -52,6 +54,11 @@ def main():
                 a, b, c, d = t[tile, l]
                 print('   layer %2d: begin +%6d | drain-wait %5d | first-chunk wait %5d | issue %6d' % (l, a - base, b - a, c - b, d - c))
             print('   tile total: %d cycles' % (t[tile, nl - 1, 3] - base))
+        print(' producer thread 0 (group 0), tile 1: per chunk [layer*1000+seg*100+chunk]: load+math | slot wait | split+store | fences | arrive | gap to next')
+        rows = [r for r in pt if r[0] != 0]
+        for i, r in enumerate(rows):
+            gap = rows[i + 1][0] - r[5] if i + 1 < len(rows) else 0
+            print('   %5d: %6d %6d %6d %6d %6d | %6d' % (r[6], r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], gap))
 
 
 if __name__ == '__main__':

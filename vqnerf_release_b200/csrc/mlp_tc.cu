@@ -17,10 +17,13 @@
 //   * one thread issues tcgen05.mma (M = 128, N = layer width, K = 8 tf32 / 16 bf16 per instruction) and
 //     tcgen05.commit's the ring slots back to their producers and the accumulator to the epilogue warps.
 //
-// VQN_PREC_TF32X3 evaluates every product as a_hi w_hi + a_lo w_hi + a_hi w_lo with hi = rna_tf32(x),
-// lo = rna_tf32(x - hi) (three kind::tf32 MMAs, fp32 accumulation in TMEM): ~2^-21 relative per product, i.e.
-// fp32-level parity (1e-4 budget of the north star) at tensor-core speed.  VQN_PREC_BF16 is a single kind::f16 MMA
-// on bf16 operands (1e-2 budget).
+// VQN_PREC_TF32X3 evaluates every product as a_hi w_hi + a_lo w_hi + a_hi w_lo with hi = rna_tf32(x), lo = x - hi,
+// fp32 accumulation in TMEM: the leading term is a kind::tf32 MMA; the two correction terms are 2^-11 of it, so
+// their operands only need ~9 bits and are fed as bf16 through ONE kind::f16 MMA of twice the K
+// ([a_lo | a_hi] . [w_hi ; w_lo]): ~2^-20 relative per product, i.e. fp32-level parity (1e-4 budget of the north
+// star), for 2/3 of the tensor time and 2/3 of the shared-memory operand traffic of three tf32 MMAs -- and the
+// kernel is bound by exactly that traffic (the 128 B/clk smem port feeds UMMA operand reads, the A-chunk stores and
+// the weight copies).  VQN_PREC_BF16 is a single kind::f16 MMA on bf16 operands (1e-2 budget).
 #include <string.h>
 
 #include "net.cuh"
@@ -102,10 +105,14 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, const float* __restr
       uint32_t off = tc::sw128_off(n, kk / 8) + (kk % 8) * 2;
       *reinterpret_cast<__nv_bfloat16*>(base + off) = __float2bfloat16_rn(v);
     } else {
+      // plane H: tf32 hi (32 fp32 words per row); plane C: 64 bf16 per row = [bf16(w_hi) x 32 | bf16(w_lo) x 32],
+      // the operands of the two correction products a_lo.w_hi and a_hi.w_lo (see store_chunk32)
       uint32_t off = tc::sw128_off(n, kk / 4) + (kk % 4) * 4;
       float hi = tc::tf32_rna(v);
       *reinterpret_cast<float*>(base + off) = hi;
-      *reinterpret_cast<float*>(base + plane + off) = tc::tf32_rna(v - hi);
+      uint8_t* pc = base + plane;
+      *reinterpret_cast<__nv_bfloat16*>(pc + tc::sw128_off(n, kk / 8) + (kk % 8) * 2) = __float2bfloat16_rn(hi);
+      *reinterpret_cast<__nv_bfloat16*>(pc + tc::sw128_off(n, 4 + kk / 8) + (kk % 8) * 2) = __float2bfloat16_rn(v - hi);
     }
   }
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < Npad; c += gridDim.x * blockDim.x)
@@ -235,16 +242,29 @@ __device__ __forceinline__ void store_chunk32(uint8_t* slot, int r, int j0, cons
       *reinterpret_cast<uint4*>(slot + tc::sw128_off(r, j0 / 8 + q)) = u;
     }
   } else {
+    // plane H (tf32 hi) at slot, plane C at slot + 16 KB: [bf16(a_lo) x 32 | bf16(a_hi) x 32] per row.
     uint8_t* row = slot + r * 128;
     const uint32_t rx = (uint32_t)(r & 7);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      float h[4], l[4];
+    for (int qq = 0; qq < 4; ++qq) {            // 8 K values per step
+      float h[8], l[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { h[i] = tc::tf32_rna(v[4 * q + i]); l[i] = tc::tf32_rna(v[4 * q + i] - h[i]); }
-      const uint32_t off = (((uint32_t)(j0 / 4 + q)) ^ rx) << 4;
-      *reinterpret_cast<float4*>(row + off) = make_float4(h[0], h[1], h[2], h[3]);
-      *reinterpret_cast<float4*>(row + TC_M * 128 + off) = make_float4(l[0], l[1], l[2], l[3]);
+      for (int i = 0; i < 8; ++i) { h[i] = tc::tf32_rna(v[8 * qq + i]); l[i] = v[8 * qq + i] - h[i]; }
+      const uint32_t c0 = (uint32_t)(j0 / 4 + 2 * qq);
+      *reinterpret_cast<float4*>(row + (((c0) ^ rx) << 4)) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(row + (((c0 + 1) ^ rx) << 4)) = make_float4(h[4], h[5], h[6], h[7]);
+      uint4 ul, uh;
+      __nv_bfloat162 t0 = __floats2bfloat162_rn(l[0], l[1]), t1 = __floats2bfloat162_rn(l[2], l[3]);
+      __nv_bfloat162 t2 = __floats2bfloat162_rn(l[4], l[5]), t3 = __floats2bfloat162_rn(l[6], l[7]);
+      ul.x = *reinterpret_cast<uint32_t*>(&t0); ul.y = *reinterpret_cast<uint32_t*>(&t1);
+      ul.z = *reinterpret_cast<uint32_t*>(&t2); ul.w = *reinterpret_cast<uint32_t*>(&t3);
+      t0 = __floats2bfloat162_rn(h[0], h[1]); t1 = __floats2bfloat162_rn(h[2], h[3]);
+      t2 = __floats2bfloat162_rn(h[4], h[5]); t3 = __floats2bfloat162_rn(h[6], h[7]);
+      uh.x = *reinterpret_cast<uint32_t*>(&t0); uh.y = *reinterpret_cast<uint32_t*>(&t1);
+      uh.z = *reinterpret_cast<uint32_t*>(&t2); uh.w = *reinterpret_cast<uint32_t*>(&t3);
+      const uint32_t cc = (uint32_t)(j0 / 8 + qq);                 // bf16 16-byte chunk of the lo half
+      *reinterpret_cast<uint4*>(row + TC_M * 128 + ((cc ^ rx) << 4)) = ul;
+      *reinterpret_cast<uint4*>(row + TC_M * 128 + (((cc + 4) ^ rx) << 4)) = uh;
     }
   }
 }
@@ -258,7 +278,9 @@ __device__ __forceinline__ void store_chunk1(uint8_t* slot, int r, int col, floa
     const uint32_t off = tc::sw128_off(r, col / 4) + (col % 4) * 4;
     const float h = tc::tf32_rna(v);
     *reinterpret_cast<float*>(slot + off) = h;
-    *reinterpret_cast<float*>(slot + TC_M * 128 + off) = tc::tf32_rna(v - h);
+    uint8_t* pc = slot + TC_M * 128;
+    *reinterpret_cast<__nv_bfloat16*>(pc + tc::sw128_off(r, col / 8) + (col % 8) * 2) = __float2bfloat16_rn(v - h);
+    *reinterpret_cast<__nv_bfloat16*>(pc + tc::sw128_off(r, 4 + col / 8) + (col % 8) * 2) = __float2bfloat16_rn(h);
   }
 }
 
@@ -348,6 +370,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
     uint32_t ga = 0;                                     // global A-chunk counter
     uint32_t gl = 0;                                     // global layer counter (acc_full phase)
+    int ptrace_n = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long pi = tile * TC_M + r;              // compact point index
       const bool valid = pi < n;
@@ -376,6 +399,10 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
             const int slot = ga % C::SA;
             uint8_t* dst = a_ring + (size_t)slot * C::A_SLOT;
             const int sc = first + c;                     // chunk index inside the source
+            long long* ptr_ = nullptr;                    // diagnostic stamps of one producer thread (tile 1 of CTA 0)
+            if (pg.trace && blockIdx.x == 0 && tid == 0 && tile == (long long)gridDim.x && ptrace_n < 96)
+              ptr_ = pg.trace + 256 + 8 * (ptrace_n++);
+            if (ptr_) { ptr_[0] = clock64(); ptr_[6] = l * 1000 + sg * 100 + c; }
 #ifdef TC_EXP_NO_PROD
             if (sc >= 0) {
               tc::mbar_wait(&a_empty[slot], ((ga / C::SA) & 1) ^ 1);
@@ -407,13 +434,18 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                 }
                 // the values are ready in registers BEFORE the slot is claimed: the TMEM / global load latency
                 // and the activation math overlap the MMAs that are still reading the slot's previous chunk
+                if (ptr_ && h == 0) ptr_[1] = clock64();
                 if (h == 0) tc::mbar_wait(&a_empty[slot], ((ga / C::SA) & 1) ^ 1);
+                if (ptr_ && h == 0) ptr_[2] = clock64();
                 store_chunk32<BF16>(dst, r, 32 * h, v);
               }
             }
+            if (ptr_) ptr_[3] = clock64();
             tc::fence_proxy_async();       // generic-proxy stores -> visible to the UMMA (async proxy)
             tc::fence_before_sync();       // order the tcgen05.ld's above before the hand-off
+            if (ptr_) ptr_[4] = clock64();
             tc::mbar_arrive(&a_full[slot]);
+            if (ptr_) ptr_[5] = clock64();
           }
         }
         ++gl;                               // layer l's chunks are all queued
@@ -478,6 +510,8 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
           const TcLayer& ly = pg.layers[l];
           const uint32_t idesc = tc::make_idesc(BF16 ? tc::FMT_BF16 : tc::FMT_TF32, TC_M, ly.Npad);
           const uint32_t idesc_side = tc::make_idesc(BF16 ? tc::FMT_BF16 : tc::FMT_TF32, TC_M, 16);
+          const uint32_t idesc_c = tc::make_idesc(tc::FMT_BF16, TC_M, ly.Npad);        // correction plane (kind::f16)
+          const uint32_t idesc_side_c = tc::make_idesc(tc::FMT_BF16, TC_M, 16);
           const uint32_t d_tmem = tmem_base + (uint32_t)ly.tmem_col;
           const uint32_t d_side = tmem_base + (uint32_t)ly.side_col;
           const bool side = ly.side_w != nullptr;
@@ -516,20 +550,19 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
               tc::mma_ss<!BF16>(d_tmem, a_hi, b_hi, idesc, acc);
               acc = 1;
               if (!BF16) {
-                const uint64_t a_lo = tc::make_desc_sw128(a_addr + C::A_PLANE + 32 * s);
-                const uint64_t b_lo = tc::make_desc_sw128(w_addr + w_plane + 32 * s);
-                tc::mma_ss<true>(d_tmem, a_lo, b_hi, idesc, 1);
-                tc::mma_ss<true>(d_tmem, a_hi, b_lo, idesc, 1);
+                // both correction products in ONE bf16 MMA of K = 16: [a_lo | a_hi] . [w_hi ; w_lo] (plane C)
+                const uint64_t a_c = tc::make_desc_sw128(a_addr + C::A_PLANE + 32 * s);
+                const uint64_t b_c = tc::make_desc_sw128(w_addr + w_plane + 32 * s);
+                tc::mma_ss<false>(d_tmem, a_c, b_c, idesc_c, 1);
               }
               if (side) {
                 const uint64_t s_hi = tc::make_desc_sw128(w_addr + C::W_MAIN + 32 * s);
                 tc::mma_ss<!BF16>(d_side, a_hi, s_hi, idesc_side, acc_s);
                 acc_s = 1;
                 if (!BF16) {
-                  const uint64_t a_lo = tc::make_desc_sw128(a_addr + C::A_PLANE + 32 * s);
-                  const uint64_t s_lo = tc::make_desc_sw128(w_addr + C::W_MAIN + C::W_SIDE_PLANE + 32 * s);
-                  tc::mma_ss<true>(d_side, a_lo, s_hi, idesc_side, 1);
-                  tc::mma_ss<true>(d_side, a_hi, s_lo, idesc_side, 1);
+                  const uint64_t a_c = tc::make_desc_sw128(a_addr + C::A_PLANE + 32 * s);
+                  const uint64_t s_c = tc::make_desc_sw128(w_addr + C::W_MAIN + C::W_SIDE_PLANE + 32 * s);
+                  tc::mma_ss<false>(d_side, a_c, s_c, idesc_side_c, 1);
                 }
               }
             }
@@ -630,7 +663,7 @@ static bool tc_append_net(TcBuilder& B, vqn_net* net, TcPack* tp, int first_src,
   return true;
 }
 
-// diagnostic knob (not part of include/vqnerf_b200.h): device buffer of >= 4 * 16 * 4 int64 that receives the
+// diagnostic knob (not part of include/vqnerf_b200.h): device buffer of >= 256 + 8 * 96 int64 that receives the
 // MMA-thread time stamps of the next launches (NULL: off)
 static long long* g_tc_trace = nullptr;
 extern "C" void vqn_debug_tc_trace(long long* dev_buf) { g_tc_trace = dev_buf; }
