@@ -196,8 +196,8 @@ struct TcCfg {
   static constexpr int PLANES = BF16 ? 1 : 2;
   static constexpr int SA = BF16 ? 4 : 2;                  // A ring stages
   static constexpr int SW = BF16 ? 4 : 2;                  // W ring stages
-  static constexpr int G = 2;                              // epilogue warp-groups (4 warps each)
-  static constexpr int THREADS = 32 * (4 * G + 2);         // + MMA warp + weight-producer warp
+  static constexpr int G = 2;                              // epilogue warp-groups (8 warps each: a thread owns 16 columns of a row)
+  static constexpr int THREADS = 32 * (8 * G + 2);         // + MMA warp + weight-producer warp
   static constexpr uint32_t A_PLANE = TC_M * 128;          // 16 KB
   static constexpr uint32_t A_SLOT = A_PLANE * PLANES;
   static constexpr uint32_t W_MAIN = (uint32_t)TC_NPAD_MAX * 128 * PLANES;
@@ -210,9 +210,9 @@ struct TcCfg {
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 template <int ACT>
-__device__ __forceinline__ void bias_act32(float (&v)[32], const float* __restrict__ bias_s) {
+__device__ __forceinline__ void bias_act32(float (&v)[16], const float* __restrict__ bias_s) {
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
+  for (int j = 0; j < 16; j += 4) {
     const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j);
     float t0 = v[j] + b4.x, t1 = v[j + 1] + b4.y, t2 = v[j + 2] + b4.z, t3 = v[j + 3] + b4.w;
     if (ACT == VQN_ACT_RELU) { t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f); t2 = fmaxf(t2, 0.f); t3 = fmaxf(t3, 0.f); }
@@ -220,18 +220,18 @@ __device__ __forceinline__ void bias_act32(float (&v)[32], const float* __restri
     v[j] = t0; v[j + 1] = t1; v[j + 2] = t2; v[j + 3] = t3;
   }
 }
-__device__ __forceinline__ void bias_act32_dyn(float (&v)[32], const float* __restrict__ bias_s, int act) {
+__device__ __forceinline__ void bias_act32_dyn(float (&v)[16], const float* __restrict__ bias_s, int act) {
   if (act == VQN_ACT_RELU) bias_act32<VQN_ACT_RELU>(v, bias_s);
   else if (act == VQN_ACT_SIGMOID) bias_act32<VQN_ACT_SIGMOID>(v, bias_s);
   else bias_act32<VQN_ACT_NONE>(v, bias_s);
 }
 
-// store 32 consecutive K values (columns j0 .. j0+31 of the chunk) of row r into the chunk slot
+// store 16 consecutive K values (columns j0 .. j0+15 of the chunk, j0 % 16 == 0) of row r into the chunk slot
 template <bool BF16>
-__device__ __forceinline__ void store_chunk32(uint8_t* slot, int r, int j0, const float (&v)[32]) {
+__device__ __forceinline__ void store_chunk32(uint8_t* slot, int r, int j0, const float (&v)[16]) {
   if (BF16) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 2; ++q) {
       __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]);
       __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
       __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
@@ -246,7 +246,7 @@ __device__ __forceinline__ void store_chunk32(uint8_t* slot, int r, int j0, cons
     uint8_t* row = slot + r * 128;
     const uint32_t rx = (uint32_t)(r & 7);
 #pragma unroll
-    for (int qq = 0; qq < 4; ++qq) {            // 8 K values per step
+    for (int qq = 0; qq < 2; ++qq) {            // 8 K values per step
       float h[8], l[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) { h[i] = tc::tf32_rna(v[8 * qq + i]); l[i] = v[8 * qq + i] - h[i]; }
@@ -337,16 +337,16 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
   uint8_t* a_ring = smem;
   uint8_t* w_ring = smem + (size_t)C::SA * C::A_SLOT;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int MMA_WARP = 4 * C::G, W_WARP = 4 * C::G + 1;
+  constexpr int MMA_WARP = 8 * C::G, W_WARP = 8 * C::G + 1;
 
   if (warp == MMA_WARP) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) {
-      tc::mbar_init(&a_full[i], 128); tc::mbar_init(&a_empty[i], 1);
+      tc::mbar_init(&a_full[i], 256); tc::mbar_init(&a_empty[i], 1);
       tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1);
     }
     tc::mbar_init(&acc_full, 1);
-    tc::mbar_init(&drain_done, 128 * C::G);
+    tc::mbar_init(&drain_done, 256 * C::G);
     tc::mbar_fence_init();
   }
   // stage every layer's bias in shared memory (layer l at bias_off[l]; host guarantees the total fits)
@@ -362,10 +362,13 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
   const long long n_tiles = (n + TC_M - 1) / TC_M;
   const int L = pg.n_layers;
 
-  if (warp < 4 * C::G) {
+  if (warp < 8 * C::G) {
     // ============== epilogue warp-groups: A-chunk producers + accumulator drain ==============
-    // group g produces the chunks with (global chunk index % G == g); all groups walk the same sequence
-    const int grp = warp >> 2;
+    // group g (8 warps) produces the chunks with (global chunk index % G == g); all groups walk the same sequence.
+    // Warps w and w + 4 of a group share a TMEM lane quarter; `half` selects which 16 of every 32 columns a
+    // thread handles, which halves the serial latency of a chunk (load, activation, split, 8 instead of 16 stores).
+    const int grp = warp >> 3;
+    const int half = (warp >> 2) & 1;
     const int r = 32 * (warp & 3) + lane;                // TMEM lane == point row of the tile
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
     uint32_t ga = 0;                                     // global A-chunk counter
@@ -410,26 +413,26 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
 #endif
             if (st == SRC_EMBED) {
               tc::mbar_wait(&a_empty[slot], ((ga / C::SA) & 1) ^ 1);
-              embed_chunk<BF16>(dst, r, x, sc * C::E, pg.n_freqs);
+              if (half == 0) embed_chunk<BF16>(dst, r, x, sc * C::E, pg.n_freqs);
             } else {
 #pragma unroll
               for (int h = 0; h < C::E / 32; ++h) {
-                float v[32];
-                const int col0 = sc * C::E + 32 * h;      // first source column of this 32-wide piece
+                float v[16];
+                const int col0 = sc * C::E + 32 * h + 16 * half;   // first source column of this thread's 16-wide piece
                 if (st == SRC_DRAIN) {
-                  tc::tmem_ld32(pacc + (uint32_t)col0, v);
+                  tc::tmem_ld16(pacc + (uint32_t)col0, v);
                   bias_act32_dyn(v, pbias + col0, pact);
                 } else {                                  // SRC_GLOBAL: this thread's own latent row
                   if (valid && col0 < pg.g_dim) {
                     const float4* src = reinterpret_cast<const float4*>(pg.gsrc + pi * pg.g_dim + col0);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < 4; ++j) {
                       float4 t = src[j];
                       v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
                     }
                   } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                    for (int j = 0; j < 16; ++j) v[j] = 0.f;
                   }
                 }
                 // the values are ready in registers BEFORE the slot is claimed: the TMEM / global load latency
@@ -437,7 +440,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                 if (ptr_ && h == 0) ptr_[1] = clock64();
                 if (h == 0) tc::mbar_wait(&a_empty[slot], ((ga / C::SA) & 1) ^ 1);
                 if (ptr_ && h == 0) ptr_[2] = clock64();
-                store_chunk32<BF16>(dst, r, 32 * h, v);
+                store_chunk32<BF16>(dst, r, 32 * h + 16 * half, v);
               }
             }
             if (ptr_) ptr_[3] = clock64();
@@ -458,39 +461,42 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
           const int gs = pg.out_stride[ly.out_slot];
           const float* lb = bias_s + ly.bias_off;
           for (int cb = grp; cb * 32 < ly.N; cb += C::G) {
-            float v[32];
-            tc::tmem_ld32(lane_addr + (uint32_t)(ly.tmem_col + cb * 32), v);
-            if (ly.add_col >= 0 && cb == 0) {            // folded skip connection: + x . W_x (16 columns)
-              float sv[32];
-              tc::tmem_ld32(lane_addr + (uint32_t)ly.add_col, sv);
+            const int c16 = cb * 32 + 16 * half;           // this thread's 16 columns of the 32-column block
+            if (c16 < ly.N) {
+              float v[16];
+              tc::tmem_ld16(lane_addr + (uint32_t)(ly.tmem_col + c16), v);
+              if (ly.add_col >= 0 && c16 == 0) {           // folded skip connection: + x . W_x (16 columns)
+                float sv[16];
+                tc::tmem_ld16(lane_addr + (uint32_t)ly.add_col, sv);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] += sv[j];
-            }
-            if (cb * 32 + 32 <= ly.Npad) bias_act32_dyn(v, lb + cb * 32, ly.act);
-            else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                float b = (cb * 32 + j < ly.Npad) ? lb[cb * 32 + j] : 0.f;
-                float t = v[j] + b;
-                v[j] = ly.act == VQN_ACT_RELU ? fmaxf(t, 0.f) : (ly.act == VQN_ACT_SIGMOID ? fast_sigmoid(t) : t);
+                for (int j = 0; j < 16; ++j) v[j] += sv[j];
               }
-            }
-            bool bad = false;
+              if (c16 + 16 <= ly.Npad) bias_act32_dyn(v, lb + c16, ly.act);
+              else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              v[j] = v[j] * ly.post_scale + ly.post_bias;
-              bad |= (cb * 32 + j < ly.N) && !isfinite(v[j]);
-            }
-            if (valid) {
-              if (bad) atomicOr(pg.nonfinite, 1);
-              if (cb * 32 + 32 <= ly.N && (gs & 3) == 0) {
-                float4* o = reinterpret_cast<float4*>(go + pi * gs + cb * 32);
+                for (int j = 0; j < 16; ++j) {
+                  float b = (c16 + j < ly.Npad) ? lb[c16 + j] : 0.f;
+                  float t = v[j] + b;
+                  v[j] = ly.act == VQN_ACT_RELU ? fmaxf(t, 0.f) : (ly.act == VQN_ACT_SIGMOID ? fast_sigmoid(t) : t);
+                }
+              }
+              bool bad = false;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-              } else {
+              for (int j = 0; j < 16; ++j) {
+                v[j] = v[j] * ly.post_scale + ly.post_bias;
+                bad |= (c16 + j < ly.N) && !isfinite(v[j]);
+              }
+              if (valid) {
+                if (bad) atomicOr(pg.nonfinite, 1);
+                if (c16 + 16 <= ly.N && (gs & 3) == 0) {
+                  float4* o = reinterpret_cast<float4*>(go + pi * gs + c16);
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (cb * 32 + j < ly.N) go[pi * gs + cb * 32 + j] = v[j];
+                  for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    if (c16 + j < ly.N) go[pi * gs + c16 + j] = v[j];
+                }
               }
             }
           }
