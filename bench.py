@@ -126,6 +126,26 @@ class ClockSampler:
                 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
+def ncu_traffic(n, probes, precision):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r1b_ncu_traffic.json) -- only valid for the workload it was captured on, else None."""
+    p = os.path.join(ROOT, 'profiles', 'r1b_ncu_traffic.json')
+    try:
+        d = json.load(open(p))
+        w = d['workload']
+        if (w['points'], w['probes'], w['precision']) != (n, probes, precision):
+            return None
+        k = d['per_launch_dram_bytes']
+        enc, heads = k['mlp_tc_kernel<tf32x3> encoder launch'], k['mlp_tc_kernel<tf32x3> heads launch']
+        return {'bytes': enc['read'] + enc['write'] + heads['read'] + heads['write'],
+                'note': 'dram__bytes_read.sum + dram__bytes_write.sum of the encoder launch + the heads launch '
+                        '(the latent z [n,256] fp32 = 655 MB is written by the first and read by the second; '
+                        'weights stay in L2); algorithmic bytes of the fused pair: 40 B/point = 25.6 MB',
+                'source': 'profiles/r1b_ncu_traffic.json'}
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -431,6 +451,12 @@ def run_ours(args):
                     'peak_source': 'bf16 cuBLAS peak %.0f TFLOP/s %s%s; FFMA peak measured live: %.1f TFLOP/s' % (
                         bf16_peak, peak_src, '' if args.precision == 'bf16' else ' / 2 (tf32 rate) / 3 (hi/lo split MMAs)', fp32_peak),
                     'traffic': None}
+            tr = ncu_traffic(n, P, args.precision)
+            if tr is not None:
+                roof['traffic'] = tr['bytes']
+                roof['traffic_note'] = tr['note'] + ' [' + tr['source'] + ']'
+            roof['binding_resource'] = ('shared-memory port (128 B/clk/SM): UMMA operand reads + A-chunk stores + weight '
+                                        'copies; see DESIGN.md 4.1 and benchmarks/tc_trace.py')
         shade_bytes = n * (2048 + 36 + 28 + 12 * (1 + P))
         kernels = {
             'mlp_main': {'ms': mlp_ms, 'tflops': MLP_FLOP * n / (mlp_ms * 1e-3) / 1e12},
