@@ -49,6 +49,8 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--points', type=int, default=N_POINTS, help='points per GPU per step (default 800x800)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--gather', default='p2p', choices=['p2p', 'nccl'],
+                    help='multi-GPU image gather: p2p = fused into the shading kernel (peer stores), nccl = all_gather')
     ap.add_argument('--precision', default='tf32x3', choices=['fp32', 'bf16', 'tf32x3'],
                     help='MLP arithmetic: tf32x3 = tcgen05 3xTF32 split, fp32 accumulate (fp32 parity, default)')
     return ap.parse_args()
@@ -282,6 +284,55 @@ def bench_train_step(dev, rank, world, args):
                     'kernels; eager_ms_per_step = the same kernels launched one by one from Python'}
 
 
+def bench_neus_scan(dev, hbm_peak):
+    """NeuS geo stage (BASELINE configs[4], secondary path): hierarchical up_sample (4 x 16 importance samples,
+    sample_pdf + merge) and render_core compositing as warp-per-ray scan kernels; the SDF / colour networks are the
+    caller's (synthetic sdf / gradients / colours here, so this times exactly the scan kernels).  512 rays per batch
+    as in the reference (launch-bound), and 65 536 rays (one 256 x 256 tile) for the HBM fraction."""
+    import torch
+    from vqnerf_release_b200 import abi
+    out = {}
+    for b in (512, 65536):
+        g = torch.Generator(device=dev).manual_seed(b)
+        rays_o = torch.randn((b, 3), generator=g, device=dev)
+        rays_o = 4.0 * rays_o / rays_o.norm(dim=1, keepdim=True)
+        rays_d = -rays_o / 4.0 + 0.05 * torch.randn((b, 3), generator=g, device=dev)
+        rays_d = rays_d / rays_d.norm(dim=1, keepdim=True)
+        z0 = torch.linspace(2.0, 6.0, 64, device=dev)[None, :].expand(b, 64).contiguous()
+        sdf_of = lambda z: ((rays_o[:, None, :] + rays_d[:, None, :] * z[..., None]).norm(dim=-1) - 1.0).contiguous()
+        sdf0 = sdf_of(z0)
+        new_sdf = [torch.rand((b, 16), generator=g, device=dev) - 0.5 for _ in range(4)]
+        grads = torch.randn((b, 128, 3), generator=g, device=dev)
+        cols = torch.rand((b, 128, 3), generator=g, device=dev)
+        sdf_f = torch.rand((b, 128), generator=g, device=dev) - 0.5
+
+        def run():
+            z, sdf = z0, sdf0
+            for i in range(4):
+                nz = abi.neus_up_sample(rays_o, rays_d, z, sdf, 1.0, 16, 64 * 2 ** i)
+                z, sdf = abi.neus_cat_z_vals(z, nz, sdf, new_sdf[i])
+            return abi.neus_composite(rays_o, rays_d, z, sdf_f, grads, cols, 300.0, 1.0, 2.0 / 64, 1.0)
+
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize(dev)
+        reps = 20 if b == 512 else 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            run()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / reps
+        # algorithmic bytes (SURVEY 8d): composite B*S*(4+4+12+12) in + B*(3+3+1+S)*4 out; up-sample steps read z,sdf and write z,sdf
+        comp = b * 128 * 32 + b * (7 + 128) * 4
+        ups = sum(b * (s * 8 + 16 * 4 + (s + 16) * 8 + 16 * 4) for s in (64, 80, 96, 112))
+        out['rays_%d' % b] = {'ms': ms, 'rays_per_s': b / (ms * 1e-3), 'samples_per_s': b * 128 / (ms * 1e-3),
+                              'gbs': (comp + ups) / (ms * 1e-3) / 1e9, 'hbm_frac': (comp + ups) / (ms * 1e-3) / 1e9 / hbm_peak,
+                              'launches': 9}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -316,10 +367,31 @@ def run_ours(args):
     ctx = _lib.Context.get(dev)
     n_global = n * world
 
+    # multi-GPU: the single gather of the pixel-sharded render is FUSED into the shading kernel (P2P stores of every
+    # shaded row into all ranks' symmetric-memory image buffers over NVLink); --gather nccl selects the separate
+    # all_gather_into_tensor instead
+    peer_img, gather_mode = None, 'none'
+    if world > 1:
+        gather_mode = args.gather
+        if gather_mode == 'p2p':
+            try:
+                peer_img = vdist.PeerImage(n_global, (1 + P, 3), dev)
+            except Exception as e:                       # no symmetric memory on this box: fall back to NCCL
+                if rank == 0:
+                    print('bench.py: symmetric memory unavailable (%s); using the NCCL all-gather' % (e,), file=sys.stderr)
+                gather_mode = 'nccl'
+        ok = torch.tensor([1 if gather_mode == 'p2p' else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            peer_img, gather_mode = None, 'nccl'
+
     def step(d):
-        pred, _, _, _ = model.fast_render(batch_of(d), mode='test', relight_probes=True)
+        pred, _, _, _ = model.fast_render(batch_of(d), mode='test', relight_probes=True, peer_image=peer_img)
         img = pred['rgb_probes'] if P > 0 else pred['albedo']
-        if world > 1:
+        if peer_img is not None:
+            peer_img.barrier()                           # all peers' rows have landed: peer_img.tensor is the full image
+            img = peer_img.tensor
+        elif world > 1:
             img = vdist.gather_rows(img, n_global)       # the single collective of a pixel-sharded render
         return img, pred
 
@@ -476,7 +548,7 @@ def run_ours(args):
             'config': {'workload': 'vq_nfr.fast_render full-image relight: %d points/GPU (800x800 view, all foreground), '
                                    '512-light probe + P=%d novel probes, random-init MLPs, K=15 codebook' % (n, P),
                        'points_per_gpu': n, 'probes': P, 'precision': args.precision,
-                       'parallelism': 'pixel rows sharded x%d, one NCCL all-gather' % world if world > 1 else 'single GPU',
+                       'parallelism': ('pixel rows sharded x%d, image gather %s' % (world, {'p2p': 'fused into the shading kernel (P2P stores over NVLink, symmetric memory)', 'nccl': 'one NCCL all-gather'}[gather_mode])) if world > 1 else 'single GPU',
                        'l2': 'inputs (%.2f GB lvis per step) larger than the 126 MB L2, no flush needed' % (n * 2048 / 1e9)},
             'e2e': {'value': n_global / (e2e_ms * 1e-3), 'unit': 'points/s', 'ms_per_step': e2e_ms,
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
@@ -487,6 +559,7 @@ def run_ours(args):
             'cpu_baseline': cb,
             'vq_assign': dict(vq, hbm_frac=vq['gbs'] / hbm_peak, bound='hbm', algorithmic_bytes_per_latent=1032),
             'train_step': train,
+            'neus_scan': bench_neus_scan(dev, hbm_peak),
         }
         print(json.dumps(line))
     if world > 1:

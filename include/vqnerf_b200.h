@@ -183,6 +183,15 @@ typedef struct vqn_shade_args {
   float* rgb_diff;      /* [*,3] probe 0 only, diffuse lobe (vq_nfr.py:605-610)   */
   float* rgb_spec;      /* [*,3] probe 0 only, glossy lobe                        */
   float* normal_out;    /* [*,3] corrected normal                                 */
+  /* Fused image gather (multi-GPU relighting): when n_peers > 0 the kernel also stores every shaded row
+   * into the n_peers image buffers peer_rgb[p] ([n_global, n_probes, 3], P2P-mapped device pointers of ALL ranks
+   * incl. this one, e.g. torch symmetric memory) at global row peer_row0 + row, so that the single gather of the
+   * pixel-sharded render travels over NVLink from inside the shading kernel instead of a separate collective.
+   * The caller synchronises the ranks afterwards (a barrier on the stream).  Large un-split batches only. */
+  float* peer_rgb[8];
+  int32_t n_peers;
+  int32_t reserved_peers;
+  int64_t peer_row0;
 } vqn_shade_args;
 
 /* _calc_ldir + _calc_vdir + _normal_correct + _eval_brdf_at (util/microfacet.py:9-89) + _render

@@ -476,3 +476,24 @@ def test_smoke_entry_point(cuda_dev):
     """__graft_entry__.smoke() (4096 points, seed 0: contains a grazing l ~ -v point) must pass as the driver runs it."""
     import __graft_entry__ as g
     g.smoke()
+
+
+@pytest.mark.parametrize('n,k', [(16 * 1024 * 1024, 15), (4 * 1024 * 1024, 256)])
+def test_vq_full_size_known_answer(cuda_dev, n, k):
+    """BASELINE configs[2] sizes (oracle-free, size-independent property): every latent is a codeword plus small
+    noise, so the assigned index must be the generating codeword; a second assignment of the quantised output is
+    idempotent; the one-hot counts of the statistics vector sum to n."""
+    from vqnerf_release_b200 import abi
+    g = torch.Generator(device=cuda_dev).manual_seed(k)
+    cb = abi.get_codebook(torch.rand((256, k), generator=g, device=cuda_dev))
+    src = torch.randint(0, k, (n,), generator=g, device=cuda_dev)
+    x = cb.t().contiguous()[src]
+    x += 1e-3 * (torch.rand((n, 256), generator=g, device=cuda_dev) - 0.5)
+    stats = torch.zeros((abi.vq_stats_size(256, k),), dtype=torch.float64, device=cuda_dev)
+    out = abi.vq_assign(x, cb, want_quantize=True, stats=stats)
+    assert torch.equal(out['indices'], src)
+    assert float(stats[:k].sum()) == n and float(stats[k + 1]) == n
+    again = abi.vq_assign(out['quantize'], cb, want_quantize=False)
+    assert torch.equal(again['indices'], src)
+    del x, out, again
+    torch.cuda.empty_cache()

@@ -38,7 +38,9 @@ class ShadeArgs(C.Structure):
                 ('lxyz', C.c_void_p), ('lareas', C.c_void_p), ('lights', C.c_void_p),
                 ('n_probes', C.c_int32), ('clip_light0', C.c_int32), ('to_srgb', C.c_int32), ('use_gamma', C.c_int32),
                 ('gamma_bias', C.c_float), ('gamma_index', C.c_float),
-                ('rgb', C.c_void_p), ('rgb_diff', C.c_void_p), ('rgb_spec', C.c_void_p), ('normal_out', C.c_void_p)]
+                ('rgb', C.c_void_p), ('rgb_diff', C.c_void_p), ('rgb_spec', C.c_void_p), ('normal_out', C.c_void_p),
+                ('peer_rgb', C.c_void_p * 8), ('n_peers', C.c_int32), ('reserved_peers', C.c_int32),
+                ('peer_row0', C.c_int64)]
 
 
 class NeusCompositeArgs(C.Structure):

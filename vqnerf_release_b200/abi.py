@@ -221,7 +221,8 @@ def vq_ema_update(stats: torch.Tensor, codebook: torch.Tensor, decay: float, eps
 
 def shade(xyz, rayo, normal, lvis, albedo, spec, rough, lxyz, lareas, lights, *, row_idx=None, n_dev=None,
           n: Optional[int] = None, n_total: Optional[int] = None, to_srgb=False, gamma=None, clip_light0=True,
-          want_split=False, want_normal=False, out_rgb: Optional[torch.Tensor] = None):
+          want_split=False, want_normal=False, out_rgb: Optional[torch.Tensor] = None,
+          peer_ptrs: Optional[Sequence[int]] = None, peer_row0: int = 0):
     """Fused _calc_ldir/_calc_vdir/_normal_correct/_eval_brdf_at/_render.  lights [1+P,512,3].
     Returns dict(rgb [n_total,1+P,3], rgb_diff, rgb_spec, normal) (full-length when row_idx is given)."""
     xyz, rayo, normal = _f(xyz), _f(rayo), _f(normal)
@@ -252,6 +253,12 @@ def shade(xyz, rayo, normal, lvis, albedo, spec, rough, lxyz, lareas, lights, *,
     if gamma is not None:
         a.use_gamma, a.gamma_bias, a.gamma_index = 1, float(gamma[0]), float(gamma[1])
     a.rgb = rgb.data_ptr()
+    if peer_ptrs:
+        if len(peer_ptrs) > 8:
+            raise ValueError('at most 8 peers (one NVSwitch box)')
+        for q, pp in enumerate(peer_ptrs):
+            a.peer_rgb[q] = int(pp)
+        a.n_peers, a.peer_row0 = len(peer_ptrs), int(peer_row0)
     out = {'rgb': rgb, 'rgb_diff': None, 'rgb_spec': None, 'normal': None}
     if want_split:
         out['rgb_diff'] = alloc((n_total, 3), dtype=F32, device=dev)

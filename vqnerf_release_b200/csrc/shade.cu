@@ -302,7 +302,9 @@ extern "C" int vqn_shade(vqn_ctx* ctx, const vqn_shade_args* args, vqn_stream st
   const bool split = a.rgb_diff || a.rgb_spec;
   // large un-split batches: thread-per-point kernel with the light tables in the constant bank (shade_pt.cu);
   // small batches (training, 8192 rays) keep the warp-per-point kernel, which exposes 32x more parallelism
-  if (!split && a.n_probes <= 9 && a.n >= 32768) return vqn_shade_pt_launch(ctx, a, vqn_cs(stream));
+  VQN_CHECK_ARG(a.n_peers >= 0 && a.n_peers <= 8, "shade: 0 <= n_peers <= 8");
+  if (!split && a.n_probes <= 9 && (a.n >= 32768 || a.n_peers > 0)) return vqn_shade_pt_launch(ctx, a, vqn_cs(stream));
+  VQN_CHECK_ARG(a.n_peers == 0, "shade: the fused peer gather needs an un-split batch with at most 9 probes");
   auto kern = a.lvis ? (split ? shade_kernel<true, true> : shade_kernel<true, false>)
                      : (split ? shade_kernel<false, true> : shade_kernel<false, false>);
   VQN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -61,6 +61,8 @@ __global__ void __launch_bounds__(SP_THREADS, 1) shade_pt_kernel(vqn_shade_args 
                                                                  int* nonfinite) {
   extern __shared__ __align__(16) float4 s_img[];
   for (int k = threadIdx.x; k < SP_GROUPS * SP_F4_PER_GROUP; k += SP_THREADS) s_img[k] = img[k];
+  // per-warp staging of the 32 x (3 NPC) outputs of a tile for the coalesced peer stores (fused gather)
+  float* s_out = reinterpret_cast<float*>(s_img + SP_GROUPS * SP_F4_PER_GROUP) + (threadIdx.x >> 5) * (32 * (3 * NPC + 1));
   __syncthreads();
   long long n = a.n_dev ? (long long)*a.n_dev : a.n;
   if (n > a.n) n = a.n;
@@ -68,8 +70,9 @@ __global__ void __launch_bounds__(SP_THREADS, 1) shade_pt_kernel(vqn_shade_args 
   const long long warps_total = (long long)gridDim.x * (SP_THREADS / 32);
   const long long warp0 = (long long)blockIdx.x * (SP_THREADS / 32) + (threadIdx.x >> 5);
   for (long long tile = warp0; tile * 32 < n; tile += warps_total) {
-  const long long i = tile * 32 + lane;
-  if (i >= n) continue;
+  const long long i_raw = tile * 32 + lane;
+  const bool live = i_raw < n;
+  const long long i = live ? i_raw : n - 1;                     // dead lanes of the last tile recompute row n-1
   const long long row = a.row_idx ? (long long)a.row_idx[i] : i;
   const float INV_PI = 0.318309886183790671538f;
   const float px = a.xyz[row * 3], py = a.xyz[row * 3 + 1], pz = a.xyz[row * 3 + 2];
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) shade_pt_kernel(vqn_shade_args 
     const float c = nx * vx + ny * vy + nz * vz;
     if (!(c >= 0.f)) { nx = -nx; ny = -ny; nz = -nz; }
   }
-  if (a.normal_out) { a.normal_out[row * 3] = nx; a.normal_out[row * 3 + 1] = ny; a.normal_out[row * 3 + 2] = nz; }
+  if (a.normal_out && live) { a.normal_out[row * 3] = nx; a.normal_out[row * 3 + 1] = ny; a.normal_out[row * 3 + 2] = nz; }
   const float inv_n = rsqrtf(fmaxf(nx * nx + ny * ny + nz * nz, 1e-6f));
   const float vn = (nx * vx + ny * vy + nz * vz) * inv_n;
   const float alb0 = a.albedo[i * 3] * INV_PI, alb1 = a.albedo[i * 3 + 1] * INV_PI, alb2 = a.albedo[i * 3 + 2] * INV_PI;
@@ -156,19 +159,38 @@ __global__ void __launch_bounds__(SP_THREADS, 1) shade_pt_kernel(vqn_shade_args 
       }
     lv_cur = lv_nxt;
   }
-  if (!a.rgb) continue;
   const int NP = a.n_probes;
 #pragma unroll
   for (int p = 0; p < NPC; ++p) {
-    if (p >= NP) break;
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
       float v = out[p * 3 + ch];
       if (a.use_gamma) v = powf(v * a.gamma_bias, a.gamma_index);     // vq_nfr.py:715-716
-      if (!isfinite(v)) atomicOr(nonfinite, 2);                        // check_numerics (:731)
+      if (p < NP && live && !isfinite(v)) atomicOr(nonfinite, 2);      // check_numerics (:731)
       v = fminf(fmaxf(v, 0.f), 1.f);                                   // clip_by_value (:718)
       if (a.to_srgb) v = vqn_linear2srgb(v);
-      a.rgb[(row * NP + p) * 3 + ch] = v;
+      out[p * 3 + ch] = v;
+      if (a.rgb && p < NP && live) a.rgb[(row * NP + p) * 3 + ch] = v;
+    }
+  }
+  if (a.n_peers > 0) {
+    // fused gather: stage the tile's rows, then store each row (3 NP contiguous floats) coalesced into the image
+    // buffer of EVERY rank (P2P stores over NVLink; the local rank is one of the peers)
+    constexpr int ST = 3 * NPC + 1;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 3 * NPC; ++k) s_out[lane * ST + k] = out[k];
+    __syncwarp();
+    const int w = 3 * NP;
+    for (int pt = 0; pt < 32; ++pt) {
+      const long long r_pt = __shfl_sync(0xffffffffu, row, pt);
+      const bool live_pt = __shfl_sync(0xffffffffu, (int)live, pt) != 0;
+      if (!live_pt) break;                                             // warp-uniform: dead lanes are at the end
+      if (lane < w) {
+        const float v = s_out[pt * ST + lane];
+        const long long off = (a.peer_row0 + r_pt) * w + lane;
+        for (int q = 0; q < a.n_peers; ++q) a.peer_rgb[q][off] = v;
+      }
     }
   }
   }   // tile loop
@@ -176,7 +198,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) shade_pt_kernel(vqn_shade_args 
 
 template <int NPC>
 int launch_pt(vqn_ctx* ctx, const vqn_shade_args& a, const float4* img, cudaStream_t s) {
-  const size_t smem = sizeof(float4) * SP_GROUPS * SP_F4_PER_GROUP;
+  const size_t smem = sizeof(float4) * SP_GROUPS * SP_F4_PER_GROUP + sizeof(float) * (SP_THREADS / 32) * 32 * (3 * NPC + 1);
   long long want = (a.n + SP_THREADS - 1) / SP_THREADS;
   const unsigned blocks = (unsigned)(want < (long long)ctx->sm_count ? want : (long long)ctx->sm_count);
   if (a.lvis) {

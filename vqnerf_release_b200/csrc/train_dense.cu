@@ -1,9 +1,9 @@
 // Dense-layer kernels of the training step (config #4): Keras Dense forward with saved activations,
 // backward-data and backward-weights (networks/mlp.py:24-50 under tf.GradientTape, train_nfr.py:562-576).
 //
-// One GEMM core, C[M,N] = A[M,K] . B[K,N], 3xTF32 on the warp-level tensor cores (mma.sync m16n8k8,
-// fp32 accumulate; hi = cvt.rna.tf32(v), lo = cvt.rna.tf32(v - hi), C = Ah.Bh + (Al.Bh + Ah.Bl)) so the
-// gradients keep fp32 parity (1e-4 rel) with the reference.  The training batch is small (8192 rays per
+// One GEMM core, C[M,N] = A[M,K] . B[K,N], 3-term split on the warp-level tensor cores (fp32 accumulate;
+// hi = cvt.rna.tf32(v), lo = v - hi, C = Ah.Bh [mma.sync m16n8k8 tf32] + (Al.Bh + Ah.Bl) [ONE m16n8k16 bf16 MMA])
+// so the gradients keep fp32 parity (1e-4 rel) with the reference.  The training batch is small (8192 rays per
 // GPU, widths <= 384), so the layers are launch- and latency-bound rather than tensor-bound: the kernels are
 // built for generality (arbitrary leading dimensions so layers read and write slices of the concat buffers
 // of the skip connections, transposed operands read in place) and are meant to be replayed from a CUDA
@@ -26,10 +26,24 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], 
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void split_tf32(float x, unsigned& hi, unsigned& lo) {
+// x = hi + lo with hi = rna_tf32(x) (returned as tf32 bits) and lo = x - hi (exact, returned as a float)
+__device__ __forceinline__ void split_tf32(float x, unsigned& hi, float& lo) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+  lo = x - __uint_as_float(hi);
+}
+// {low half: bf16(a), high half: bf16(b)}
+__device__ __forceinline__ unsigned pack_bf16(float a, float b) {
+  unsigned r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// The two correction products a_lo.b_hi + a_hi.b_lo are 2^-11 of the leading term, so bf16 operands (2^-9) keep
+// them to 2^-20: ONE m16n8k16 bf16 MMA evaluates both, with its 16 k-slots holding [lo(k=t), lo(k=t+4)] pairs in
+// slots 0-7 and [hi(k=t), hi(k=t+4)] pairs in slots 8-15 (any k-permutation shared by A and B is valid).
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 struct GemmParams {
@@ -138,26 +152,33 @@ __global__ void __launch_bounds__(THREADS) dense_gemm_kernel(GemmParams p) {
     }
 #pragma unroll
     for (int ks = 0; ks < BK; ks += 8) {
-      unsigned ah[2][4], al[2][4];
+      unsigned ah[2][4], ac[2][4];          // tf32 hi fragment, bf16 correction fragment
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int m = wm + i * 16 + g;
-        split_tf32(a_at(m, ks + t), ah[i][0], al[i][0]);
-        split_tf32(a_at(m + 8, ks + t), ah[i][1], al[i][1]);
-        split_tf32(a_at(m, ks + t + 4), ah[i][2], al[i][2]);
-        split_tf32(a_at(m + 8, ks + t + 4), ah[i][3], al[i][3]);
+        float l0, l1, l2, l3;
+        split_tf32(a_at(m, ks + t), ah[i][0], l0);
+        split_tf32(a_at(m + 8, ks + t), ah[i][1], l1);
+        split_tf32(a_at(m, ks + t + 4), ah[i][2], l2);
+        split_tf32(a_at(m + 8, ks + t + 4), ah[i][3], l3);
+        ac[i][0] = pack_bf16(l0, l2);                                                   // row g:   lo(k=t), lo(k=t+4)
+        ac[i][1] = pack_bf16(l1, l3);                                                   // row g+8
+        ac[i][2] = pack_bf16(__uint_as_float(ah[i][0]), __uint_as_float(ah[i][2]));      // row g:   hi(k=t), hi(k=t+4)
+        ac[i][3] = pack_bf16(__uint_as_float(ah[i][1]), __uint_as_float(ah[i][3]));      // row g+8
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int n = wn + j * 8 + g;
-        unsigned bh0, bl0, bh1, bl1;
+        unsigned bh0, bh1;
+        float bl0, bl1;
         split_tf32(b_at(ks + t, n), bh0, bl0);
         split_tf32(b_at(ks + t + 4, n), bh1, bl1);
+        const unsigned bc0 = pack_bf16(__uint_as_float(bh0), __uint_as_float(bh1));     // pairs with the lo slots of A
+        const unsigned bc1 = pack_bf16(bl0, bl1);                                       // pairs with the hi slots of A
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           mma_tf32(acc_m[i][j], ah[i], bh0, bh1);
-          mma_tf32(acc_c[i][j], al[i], bh0, bh1);
-          mma_tf32(acc_c[i][j], ah[i], bl0, bl1);
+          mma_bf16(acc_c[i][j], ac[i], bc0, bc1);
         }
       }
     }

@@ -13,9 +13,10 @@
 // straight into the m16n8k8 A-fragment positions: k-step s = 2c+u uses z0 = 16c+4t+2u at column t and
 // z0+1 at column t+4; the codebook B fragments are pre-split and stored in exactly that order in shared
 // memory ({b0.hi, b1.hi, b0.lo, b1.lo} per lane -> one conflict-free LDS.128 per (k-step, n-tile)).
-// fp32 parity comes from the 3xTF32 split  x.c = xh.ch + (xl.ch + xh.cl),  hi = cvt.rna.tf32(v),
-// lo = cvt.rna.tf32(v - hi), with the large and the small products in separate fp32 accumulators; rows
-// whose best two distances are closer than 2e-5 relative are re-scored in fp64, so indices are exact
+// fp32 parity comes from the 3-term split  x.c = xh.ch + (xl.ch + xh.cl),  hi = cvt.rna.tf32(v), lo = v - hi:
+// the leading term is a tf32 MMA, the two corrections (2^-11 of it) ONE bf16 m16n8k16 MMA (4 instead of 6 MMAs
+// per k-step at K <= 16), with the large and the small products in separate fp32 accumulators; rows
+// whose best two distances are closer than 4e-5 relative are re-scored in fp64, so indices are exact
 // whenever the true top-2 gap exceeds the 1e-6 tolerance of BASELINE.json.  Loads are software-pipelined
 // in four phases per tile through two register buffers (one phase = 4 KB per warp in flight behind the
 // one being consumed; 16 warps/SM).
@@ -37,6 +38,17 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], 
   asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// {low half: bf16(a), high half: bf16(b)}
+__device__ __forceinline__ unsigned pack_bf16(float a, float b) {
+  unsigned r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
 __device__ __forceinline__ unsigned cvt_tf32(float x) {
   unsigned r;
@@ -85,15 +97,21 @@ __device__ __forceinline__ void compute_phase(const float4 (&vg)[4], const float
       const float a1 = u ? vh[cc].z : vh[cc].x, a3 = u ? vh[cc].w : vh[cc].y;
       xs_g = fmaf(a0, a0, xs_g); xs_g = fmaf(a2, a2, xs_g);
       xs_h = fmaf(a1, a1, xs_h); xs_h = fmaf(a3, a3, xs_h);
-      unsigned ah[4], al[4];
-      split_tf32(a0, ah[0], al[0]); split_tf32(a1, ah[1], al[1]);
-      split_tf32(a2, ah[2], al[2]); split_tf32(a3, ah[3], al[3]);
+      // leading term: tf32 MMA on the hi parts; both correction terms (x_lo.c_hi + x_hi.c_lo, 2^-11 of it) in ONE
+      // bf16 m16n8k16 MMA whose k-slots 0-7 hold the lo pairs [k=t, k=t+4] and slots 8-15 the hi pairs
+      unsigned ah[4], ac[4];
+      ah[0] = cvt_tf32(a0); ah[1] = cvt_tf32(a1); ah[2] = cvt_tf32(a2); ah[3] = cvt_tf32(a3);
+      const float h0 = __uint_as_float(ah[0]), h1 = __uint_as_float(ah[1]);
+      const float h2 = __uint_as_float(ah[2]), h3 = __uint_as_float(ah[3]);
+      ac[0] = pack_bf16(a0 - h0, a2 - h2);
+      ac[1] = pack_bf16(a1 - h1, a3 - h3);
+      ac[2] = pack_bf16(h0, h2);
+      ac[3] = pack_bf16(h1, h3);
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
         const float4 b = bl[(s * NT + j) * 32];
         mma_tf32(accm[j], ah, __float_as_uint(b.x), __float_as_uint(b.y));
-        mma_tf32(accc[j], al, __float_as_uint(b.x), __float_as_uint(b.y));
-        mma_tf32(accc[j], ah, __float_as_uint(b.z), __float_as_uint(b.w));
+        mma_bf16(accc[j], ac, __float_as_uint(b.z), __float_as_uint(b.w));
       }
     }
   }
@@ -146,9 +164,11 @@ __global__ void __launch_bounds__(VqmCfg<NT>::WARPS * 32, VqmCfg<NT>::BLOCKS) vq
       const int z0 = 16 * c + 4 * tt + 2 * u, k = ch * KCH + 8 * j + gg;
       float b0 = 0.f, b1 = 0.f;
       if (k < K) { b0 = p.cb[(size_t)z0 * K + k]; b1 = p.cb[(size_t)(z0 + 1) * K + k]; }
-      unsigned h0, l0, h1, l1;
-      split_tf32(b0, h0, l0); split_tf32(b1, h1, l1);
-      bsm[i] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
+      // {b0.hi, b1.hi} as tf32 and the bf16 pairs {bf16(b0.hi), bf16(b1.hi)} (meets the x_lo slots) and
+      // {bf16(b0.lo), bf16(b1.lo)} (meets the x_hi slots) of the correction MMA
+      const unsigned h0 = cvt_tf32(b0), h1 = cvt_tf32(b1);
+      const float fh0 = __uint_as_float(h0), fh1 = __uint_as_float(h1);
+      bsm[i] = make_float4(fh0, fh1, __uint_as_float(pack_bf16(fh0, fh1)), __uint_as_float(pack_bf16(b0 - fh0, b1 - fh1)));
     }
     // ||c||^2 (vq_layers.py:282); padded codewords get +inf so they never win
     for (int kk = warp; kk < KCH; kk += VQM_WARPS) {
@@ -237,11 +257,11 @@ __global__ void __launch_bounds__(VqmCfg<NT>::WARPS * 32, VqmCfg<NT>::BLOCKS) vq
         return;
       }
     }
-    // fp64 re-score of near-ties (top-2 gap below 2e-5 relative): exact ordering of the two candidates
+    // fp64 re-score of near-ties (top-2 gap below 4e-5 relative): exact ordering of the two candidates
     int best_g = tg.bi, best_h = th.bi;
     {
-      bool near_g = ok_g && K > 1 && (tg.s - tg.b) <= 2e-5f * fmaxf(fabsf(tg.b), 1e-3f);
-      bool near_h = ok_h && K > 1 && (th.s - th.b) <= 2e-5f * fmaxf(fabsf(th.b), 1e-3f);
+      bool near_g = ok_g && K > 1 && (tg.s - tg.b) <= 4e-5f * fmaxf(fabsf(tg.b), 1e-3f);
+      bool near_h = ok_h && K > 1 && (th.s - th.b) <= 4e-5f * fmaxf(fabsf(th.b), 1e-3f);
       if (p.sel_mask) {
         if (near_g && (p.sel_mask[tg.bi] == 0.f || p.sel_mask[tg.si] == 0.f)) near_g = false;
         if (near_h && (p.sel_mask[th.bi] == 0.f || p.sel_mask[th.si] == 0.f)) near_h = false;

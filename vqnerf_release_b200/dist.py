@@ -83,3 +83,27 @@ def make_stats_allreduce(group=None):
     def hook(stats: torch.Tensor) -> None:
         allreduce_flat_([stats], group=group)
     return hook
+
+
+class PeerImage:
+    """Fused gather of a pixel-sharded render: every rank owns an image buffer [n_total, c...] in torch symmetric
+    memory (P2P-mapped over NVLink / NVSwitch); the shading kernel of rank r stores its rows straight into ALL
+    ranks' buffers (vqn_shade_args.peer_rgb), so the "single gather" of SURVEY 8e overlaps the light integral tile by
+    tile instead of running as a separate NCCL collective.  `barrier()` (device-side, on the current stream) makes the
+    peers' rows visible; afterwards `tensor` holds the complete image on every rank."""
+
+    def __init__(self, n_total: int, tail, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.n_total = int(n_total)
+        self.tensor = symm_mem.empty((self.n_total,) + tuple(tail), dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.tensor, self.group)
+        self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        if len(self.peer_ptrs) != self.world:
+            raise RuntimeError('symmetric memory rendezvous returned %d peers for world %d' % (len(self.peer_ptrs), self.world))
+        self.row0 = shard_rows(self.n_total, self.rank, self.world)[0]
+
+    def barrier(self) -> None:
+        self.handle.barrier()

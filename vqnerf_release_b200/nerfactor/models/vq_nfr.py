@@ -305,7 +305,10 @@ class Model:
     # ------------------------------------------------------------------ fast_render (vq_nfr.py:262-398)
     def fast_render(self, batch, mode='train', relight_olat=False, relight_probes=False, opt_scale=None,
                     edit_mask=None, edit_material=None, ref_batch=False, dst_env=None, gen_embed=False, thres=None,
-                    vis_scale=False, roll=None):
+                    vis_scale=False, roll=None, peer_image=None):
+        """`peer_image` (vqnerf_release_b200.dist.PeerImage, multi-GPU only): the shaded rows [.., 1+P, 3] are also
+        stored into every rank's image buffer from inside the shading kernel (fused gather); call
+        `peer_image.barrier()` afterwards."""
         self._validate_mode(mode)
         if edit_mask is not None:
             raise NotImplementedError('material editing (edit.py) is outside the hot path (SURVEY 2.1)')
@@ -341,7 +344,9 @@ class Model:
         sh = abi.shade(xyz, rayo, normal, lvis, s_albedo, s_spec, rough, self.lxyz, self.lareas,
                        lights, row_idx=row_idx, n_dev=n_act, n=n_total,
                        n_total=n_total, to_srgb=(self.data_type == 'nerf'), gamma=gamma,
-                       clip_light0=(dst_env is None))
+                       clip_light0=(dst_env is None),
+                       peer_ptrs=None if peer_image is None else peer_image.peer_ptrs,
+                       peer_row0=0 if peer_image is None else peer_image.row0)
         self._mark('shade', dev)
         self._check_numerics(dev)
         loss_kwargs = {'mode': mode, 'gtc': rgb}
