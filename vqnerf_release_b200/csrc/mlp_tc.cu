@@ -326,6 +326,9 @@ __device__ __forceinline__ void embed_chunk(uint8_t* slot, int r, const float (&
   for (int col = (d > col0 ? d : col0); col < col0 + E; ++col) store_chunk1<BF16>(slot, r, col - col0, 0.f);
 }
 
+// named barrier of one 256-thread epilogue group (ids 1, 2; id 0 is __syncthreads)
+__device__ __forceinline__ void group_bar(int grp) { asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory"); }
+
 template <bool BF16>
 __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcProgram pg) {
   using C = TcCfg<BF16>;
@@ -369,6 +372,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
     // thread handles, which halves the serial latency of a chunk (load, activation, split, 8 instead of 16 stores).
     const int grp = warp >> 3;
     const int half = (warp >> 2) & 1;
+    const int tg = tid & 255;                            // thread index inside the group
     const int r = 32 * (warp & 3) + lane;                // TMEM lane == point row of the tile
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
     uint32_t ga = 0;                                     // global A-chunk counter
@@ -414,6 +418,39 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
             if (st == SRC_EMBED) {
               tc::mbar_wait(&a_empty[slot], ((ga / C::SA) & 1) ^ 1);
               if (half == 0) embed_chunk<BF16>(dst, r, x, sc * C::E, pg.n_freqs);
+            } else if (!BF16 && st == SRC_GLOBAL) {
+              // Latent chunk [128 rows x 32 columns] of the row-major source: loaded COALESCED (a warp reads 4 rows x
+              // 128 B per instruction; a thread-per-row load touches 32 lines per instruction and costs 8x the L1/smem
+              // data-pipe wavefronts, which is the port this kernel is bound by), staged through the plane-C half of the
+              // group's own slot with the 128-B swizzle (conflict-free both ways), then re-read row-wise.
+              float4 ldv[4];
+              const int col_base = sc * C::E;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int f = tg + 256 * i, rr = f >> 3, ch = f & 7;
+                const long long prow = tile * TC_M + rr;
+                ldv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (prow < n && col_base + 4 * ch < pg.g_dim)
+                  ldv[i] = __ldg(reinterpret_cast<const float4*>(pg.gsrc + prow * pg.g_dim + col_base + 4 * ch));
+              }
+              if (ptr_) ptr_[1] = clock64();
+              tc::mbar_wait(&a_empty[slot], ((ga / C::SA) & 1) ^ 1);
+              if (ptr_) ptr_[2] = clock64();
+              uint8_t* stage = dst + C::A_PLANE;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int f = tg + 256 * i, rr = f >> 3, ch = f & 7;
+                *reinterpret_cast<float4*>(stage + rr * 128 + ((ch ^ (rr & 7)) << 4)) = ldv[i];
+              }
+              group_bar(grp);
+              float v[16];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 t = *reinterpret_cast<const float4*>(stage + r * 128 + (((4 * half + q) ^ (r & 7)) << 4));
+                v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+              }
+              group_bar(grp);                    // every row has been read before plane C is overwritten
+              store_chunk32<BF16>(dst, r, 16 * half, v);
             } else {
 #pragma unroll
               for (int h = 0; h < C::E / 32; ++h) {
@@ -422,7 +459,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                 if (st == SRC_DRAIN) {
                   tc::tmem_ld16(pacc + (uint32_t)col0, v);
                   bias_act32_dyn(v, pbias + col0, pact);
-                } else {                                  // SRC_GLOBAL: this thread's own latent row
+                } else {                                  // SRC_GLOBAL (bf16 mode): this thread's own latent row
                   if (valid && col0 < pg.g_dim) {
                     const float4* src = reinterpret_cast<const float4*>(pg.gsrc + pi * pg.g_dim + col0);
 #pragma unroll
@@ -460,6 +497,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
           float* go = pg.outs[ly.out_slot];
           const int gs = pg.out_stride[ly.out_slot];
           const float* lb = bias_s + ly.bias_off;
+          const bool wide = (ly.N % 32 == 0) && (gs % 4 == 0);   // full 32-column blocks of 16-byte aligned rows
           for (int cb = grp; cb * 32 < ly.N; cb += C::G) {
             const int c16 = cb * 32 + 16 * half;           // this thread's 16 columns of the 32-column block
             if (c16 < ly.N) {
@@ -486,8 +524,16 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                 v[j] = v[j] * ly.post_scale + ly.post_bias;
                 bad |= (c16 + j < ly.N) && !isfinite(v[j]);
               }
-              if (valid) {
-                if (bad) atomicOr(pg.nonfinite, 1);
+              if (valid && bad) atomicOr(pg.nonfinite, 1);
+              if (wide) {
+                // stage the 32-column block in the group's own (free) A slot, swizzled, then store it coalesced:
+                // a warp writes 4 rows x 128 B per instruction instead of 16 B into each of 32 rows
+                uint8_t* stage = a_ring + (size_t)grp * C::A_SLOT;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  *reinterpret_cast<float4*>(stage + r * 128 + (((4 * half + q) ^ (r & 7)) << 4)) =
+                      make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              } else if (valid) {
                 if (c16 + 16 <= ly.N && (gs & 3) == 0) {
                   float4* o = reinterpret_cast<float4*>(go + pi * gs + c16);
 #pragma unroll
@@ -498,6 +544,19 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                     if (c16 + j < ly.N) go[pi * gs + c16 + j] = v[j];
                 }
               }
+            }
+            if (wide) {
+              const uint8_t* stage = a_ring + (size_t)grp * C::A_SLOT;
+              group_bar(grp);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int f = tg + 256 * i, rr = f >> 3, ch = f & 7;
+                const long long prow = tile * TC_M + rr;
+                if (prow < n)
+                  *reinterpret_cast<float4*>(go + prow * gs + cb * 32 + 4 * ch) =
+                      *reinterpret_cast<const float4*>(stage + rr * 128 + ((ch ^ (rr & 7)) << 4));
+              }
+              group_bar(grp);
             }
           }
           tc::fence_before_sync();
