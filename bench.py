@@ -375,7 +375,7 @@ def run_ours(args):
         gather_mode = args.gather
         if gather_mode == 'p2p':
             try:
-                peer_img = vdist.PeerImage(n_global, (1 + P, 3), dev)
+                peer_img = vdist.PeerImage(n_global, (1 + P, 3), dev, dst=0)   # the image is gathered on rank 0
             except Exception as e:                       # no symmetric memory on this box: fall back to NCCL
                 if rank == 0:
                     print('bench.py: symmetric memory unavailable (%s); using the NCCL all-gather' % (e,), file=sys.stderr)
@@ -548,7 +548,7 @@ def run_ours(args):
             'config': {'workload': 'vq_nfr.fast_render full-image relight: %d points/GPU (800x800 view, all foreground), '
                                    '512-light probe + P=%d novel probes, random-init MLPs, K=15 codebook' % (n, P),
                        'points_per_gpu': n, 'probes': P, 'precision': args.precision,
-                       'parallelism': ('pixel rows sharded x%d, image gather %s' % (world, {'p2p': 'fused into the shading kernel (P2P stores over NVLink, symmetric memory)', 'nccl': 'one NCCL all-gather'}[gather_mode])) if world > 1 else 'single GPU',
+                       'parallelism': ('pixel rows sharded x%d, image gather %s' % (world, {'p2p': 'to rank 0, fused into the shading kernel (P2P stores over NVLink into symmetric memory)', 'nccl': 'one NCCL all-gather'}[gather_mode])) if world > 1 else 'single GPU',
                        'l2': 'inputs (%.2f GB lvis per step) larger than the 126 MB L2, no flush needed' % (n * 2048 / 1e9)},
             'e2e': {'value': n_global / (e2e_ms * 1e-3), 'unit': 'points/s', 'ms_per_step': e2e_ms,
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},

@@ -74,6 +74,18 @@ def main():
     assert torch.allclose(peer.tensor[:, 1:, :], ref_all, rtol=5e-5, atol=2e-6), 'fused P2P gather differs from the single-device image'
     assert torch.equal(pred_p['rgb_probes'], peer.tensor[lo:hi, 1:, :]), 'local rows differ from the rows stored into the image'
     print('rank %d: fused P2P gather OK (max |diff| vs single device %.2e)' % (rank, (peer.tensor[:, 1:, :] - ref_all).abs().max().item()), flush=True)
+    # gather semantics: only rank 0's buffer receives the rows
+    peer0 = vdist.PeerImage(n, (3, 3), dev, dst=0)
+    peer0.tensor.zero_()
+    dist.barrier()
+    m2.fast_render(batch_tuple(batch, dev, lo, hi), mode='test', relight_probes=True, peer_image=peer0)
+    peer0.barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        assert torch.equal(peer0.tensor, peer.tensor), 'gather-to-rank-0 image differs from the all-gather image'
+    else:
+        assert float(peer0.tensor.abs().max()) == 0.0, 'a non-destination rank received rows'
+    print('rank %d: fused gather to rank 0 OK' % rank, flush=True)
     losses2 = []
     for it in range(2):
         roll = np.random.RandomState(it).uniform(0, 1, size=(1, k))

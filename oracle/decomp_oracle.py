@@ -649,3 +649,30 @@ def synth_scene(seed: int = 0, k: int = NUM_EMBED, n_probes: int = 0, bias_scale
         probes = (np.abs(rng.normal(size=(n_probes, LIGHT_H, 2 * LIGHT_H, 3))) * 0.5).astype(np.float32)
     return Scene(nets=make_vq_nfr_nets(seed, bias_scale), light=light, codebook=cb, probes=probes,
                  data_type=data_type, gamma=(1.1, 0.9))
+
+
+# ----------------------------------------------------------------------------
+# codebook initialisation: nerfactor/util/torch_kmeans.py:23-94 restated in float64 NumPy
+# ----------------------------------------------------------------------------
+def kmeans_oracle(x: np.ndarray, num_clusters: int, tol: float = 1e-4, seed: int = 1, max_iter: int = 10000):
+    """Lloyd iterations exactly as the reference: initial centres = rows np.random.choice(N, K, replace=False)
+    after np.random.seed(seed) (:15-19); assignment = first arg-min of the squared euclidean distance (:58-60);
+    centre = member mean (:65-70; an empty cluster keeps its centre -- the reference would produce NaN);
+    stop when (sum_k |delta c_k|)^2 < tol (:72-75,91).  Returns (ids, centres, iterations)."""
+    x = np.asarray(x, np.float64)
+    np.random.seed(seed)
+    centers = x[np.random.choice(len(x), num_clusters, replace=False)].copy()
+    ids = None
+    for it in range(1, max_iter + 1):
+        d = (x * x).sum(1, keepdims=True) - 2.0 * x @ centers.T + (centers * centers).sum(1)[None, :]
+        ids = d.argmin(1)
+        new = centers.copy()
+        for k in range(num_clusters):
+            sel = x[ids == k]
+            if len(sel):
+                new[k] = sel.mean(0)
+        shift = np.sqrt(((new - centers) ** 2).sum(1)).sum()
+        centers = new
+        if shift ** 2 < tol:
+            break
+    return ids, centers, it

@@ -497,3 +497,37 @@ def test_vq_full_size_known_answer(cuda_dev, n, k):
     assert torch.equal(again['indices'], src)
     del x, out, again
     torch.cuda.empty_cache()
+
+
+def test_kmeans_codebook_init_matches_oracle(cuda_dev):
+    """SURVEY 8f N2 (nerfactor/util/torch_kmeans.py): Lloyd's k-means on [N,256] latents through the VQ assignment
+    kernel against the float64 restatement: same seed -> same initial rows -> same ids and centres.  (a) a crisp case
+    (5 separated clusters, seed 16 draws one row from each: converges in 2 iterations, exact agreement); (b) the
+    ill-conditioned case (15 clusters, duplicated initial draws, empty clusters): Lloyd iterations amplify fp32-vs-fp64
+    rounding at cluster boundaries there -- a float32 NumPy run differs from the float64 one in 0.4 % of the
+    memberships -- so only the objective is compared."""
+    from vqnerf_release_b200.nerfactor.util import torch_kmeans as KM
+    rng = np.random.RandomState(0)
+    k, n = 5, 6000
+    true_c = rng.uniform(0, 1, (k, 256))
+    x = (true_c[rng.randint(0, k, n)] + 0.05 * rng.normal(size=(n, 256))).astype(np.float32)
+    ids, centers = KM.kmeans(torch.from_numpy(x), k, distance='euclidean', tol=1e-4, device=cuda_dev, seed=16)
+    oid, oc, iters = O.kmeans_oracle(x, k, tol=1e-4, seed=16)
+    assert iters == 2 and centers.shape == (k, 256) and ids.dtype == torch.int64
+    assert (ids.numpy() == oid).all()
+    _close(centers, oc, 'k-means centres', rtol=1e-5, atol=1e-6)
+    pred = KM.kmeans_predict(torch.from_numpy(x[:1000]), centers, device=cuda_dev)
+    assert (pred.numpy() == oid[:1000]).all()
+    d = KM.pairwise_distance(torch.from_numpy(x[:64]), centers, device=cuda_dev)
+    dref = ((x[:64, None, :].astype(np.float64) - oc[None]) ** 2).sum(-1)
+    # the kernel evaluates |x|^2 - 2 x.c + |c|^2 (the VQ layer's form): absolute accuracy ~1e-5 of |x|^2 ~ 85
+    _close(d, dref, 'pairwise_distance', rtol=1e-4, atol=1e-3)
+    # (b)
+    k, n = 15, 20000
+    true_c = rng.uniform(0, 1, (k, 256))
+    x = (true_c[rng.randint(0, k, n)] + 0.05 * rng.normal(size=(n, 256))).astype(np.float32)
+    ids, centers = KM.kmeans(torch.from_numpy(x), k, device=cuda_dev, seed=1)
+    oid, oc, _ = O.kmeans_oracle(x, k, seed=1)
+    obj = lambda c, i: float(((x.astype(np.float64) - np.asarray(c, np.float64)[i]) ** 2).sum())
+    assert abs(obj(centers.numpy(), ids.numpy()) - obj(oc, oid)) <= 2e-3 * obj(oc, oid)
+    assert torch.isfinite(centers).all()          # empty clusters keep their centre instead of the reference's NaN

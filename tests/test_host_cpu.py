@@ -85,3 +85,20 @@ def test_single_process_paths_are_identity():
     assert vdist.gather_rows(t, 4) is t
     vdist.allreduce_flat_([t])
     assert bool((t == 1).all())
+
+
+def test_adam_schedule_matches_keras(built_lib):
+    """train_nfr.Adam.lr_t == tf.keras Adam's lr_t with ExponentialDecay (host arithmetic, no GPU):
+    lr * rate ** (step / decay_steps) * sqrt(1 - b2^t) / (1 - b1^t), the schedule seeing the pre-increment step."""
+    import math
+    from vqnerf_release_b200.nerfactor import train_nfr as T
+    opt = T.Adam(learning_rate=5e-4, decay_steps=500_000, decay_rate=0.1)
+    for t in (1, 2, 10, 1000, 500_001):
+        opt.iterations = t
+        want = 5e-4 * 0.1 ** ((t - 1) / 500_000) * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
+        assert abs(opt.lr_t() - want) <= 1e-12 * want
+    assert T.Adam(learning_rate=1e-3).lr_t.__self__.decay_steps == -1
+    with pytest.raises(NotImplementedError):
+        T.Adam(amsgrad=False)
+    assert T._pad4(63) == 64 and T._pad4(64) == 64
+    assert T.NET_ORDER[0] == 'fine_enc' and len(T.NET_ORDER) == 8

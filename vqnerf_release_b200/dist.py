@@ -92,7 +92,10 @@ class PeerImage:
     tile instead of running as a separate NCCL collective.  `barrier()` (device-side, on the current stream) makes the
     peers' rows visible; afterwards `tensor` holds the complete image on every rank."""
 
-    def __init__(self, n_total: int, tail, device, group=None):
+    def __init__(self, n_total: int, tail, device, group=None, dst: Optional[int] = None):
+        """dst=None: every rank ends up with the full image (all-gather semantics, world x the NVLink traffic);
+        dst=r: only rank r does (gather semantics -- what writing an image needs: the senders push 1/world of the
+        image each and rank r's ingress overlaps its own kernels)."""
         import torch.distributed._symmetric_memory as symm_mem
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
@@ -100,9 +103,11 @@ class PeerImage:
         self.n_total = int(n_total)
         self.tensor = symm_mem.empty((self.n_total,) + tuple(tail), dtype=torch.float32, device=device)
         self.handle = symm_mem.rendezvous(self.tensor, self.group)
-        self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
-        if len(self.peer_ptrs) != self.world:
-            raise RuntimeError('symmetric memory rendezvous returned %d peers for world %d' % (len(self.peer_ptrs), self.world))
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        if len(ptrs) != self.world:
+            raise RuntimeError('symmetric memory rendezvous returned %d peers for world %d' % (len(ptrs), self.world))
+        self.dst = dst
+        self.peer_ptrs = ptrs if dst is None else [ptrs[int(dst)]]
         self.row0 = shard_rows(self.n_total, self.rank, self.world)[0]
 
     def barrier(self) -> None:
