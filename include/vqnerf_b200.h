@@ -292,6 +292,19 @@ int vqn_adam_amsgrad(vqn_ctx* ctx, float* param, const float* grad, float* m, fl
 int vqn_cast_f64_f32(vqn_ctx* ctx, const double* src, float* dst, int64_t count, vqn_stream stream);
 int vqn_cast_f32_f64(vqn_ctx* ctx, const float* src, double* dst, int64_t count, vqn_stream stream);
 
+/* ---- training-batch assembler: outer_sample, nerfactor/train_nfr.py:380-467 ------------------- */
+/* Index half (:401-448): one random 8-neighbour per interior pixel, pairs whose alphas both exceed alpha_thres,
+ * bs draws with replacement -> rows int32 [2*bs] = [p1, p1_n, p2, p2_n, ...] (linear pixel indices of the H x W view;
+ * -1 when no pair is valid), n_valid[1].  Randomness: splitmix64 counter hash of (seed, stream, index) -- TF's RNG
+ * is not reproducible outside TF.  Workspaces: flag_ws float / nb_ws, valid_ws int32 of (H-2)(W-2) entries,
+ * compact_ws int32 of (H-2)(W-2)/1024 + 2. */
+int vqn_sample_pairs(vqn_ctx* ctx, const float* alpha, int h, int w, int use_alpha_thres, float alpha_thres, int bs,
+                     uint64_t seed, float* flag_ws, int32_t* nb_ws, int32_t* valid_ws, int32_t* compact_ws,
+                     int32_t* n_valid, int32_t* rows, vqn_stream stream);
+/* tf.gather_nd(tensor, select_ind) (:450-465): out[n_out,c] = src[rows[o],:] */
+int vqn_gather_rows(vqn_ctx* ctx, const float* src, const int32_t* rows, int64_t n_out, int c, float* out,
+                    vqn_stream stream);
+
 /* ---- NeuS geo stage (secondary path) -------------------------------------------------------- */
 /* NeuSRenderer.up_sample (geo/NeuS-ours2/models/renderer.py:131-175) incl. sample_pdf(det=True)
  * (:39-69): z_samples[B,n_importance] from z_vals[B,S], sdf[B,S]. One warp per ray. */

@@ -676,3 +676,45 @@ def kmeans_oracle(x: np.ndarray, num_clusters: int, tol: float = 1e-4, seed: int
         if shift ** 2 < tol:
             break
     return ids, centers, it
+
+
+# ----------------------------------------------------------------------------
+# training-batch assembler: nerfactor/train_nfr.py:380-467 with the product's counter-hash RNG
+# ----------------------------------------------------------------------------
+_M64 = (1 << 64) - 1
+
+
+def _splitmix64(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & _M64
+    return x ^ (x >> 31)
+
+
+def _rnd_u32(seed: int, stream: int, idx: int) -> int:
+    return (_splitmix64((_splitmix64((seed ^ (stream << 56)) & _M64) + idx) & _M64) >> 32) & 0xFFFFFFFF
+
+
+def outer_sample_rows(alpha_hw: np.ndarray, bs: int, seed: int, alpha_thres: Optional[float] = 0.9) -> np.ndarray:
+    """train_nfr.py:401-448 (pure Python, small views only): the [p1, p1_n, p2, p2_n, ...] linear pixel indices.
+    tf.random.uniform is replaced by the documented splitmix64 counter hash (TF's streams are not reproducible
+    outside TF): stream 1 = the neighbour of interior pixel q, stream 2 = the s-th draw among the valid pairs."""
+    h, w = alpha_hw.shape
+    jit = [(-1, -1), (-1, 0), (-1, 1), (0, -1), (0, 1), (1, -1), (1, 0), (1, 1)]           # :401-402
+    valid, nbs = [], []
+    for i in range(1, h - 1):
+        for j in range(1, w - 1):
+            q = (i - 1) * (w - 2) + (j - 1)
+            di, dj = jit[_rnd_u32(seed, 1, q) % 8]
+            ok = True
+            if alpha_thres is not None:
+                ok = alpha_hw[i, j] > alpha_thres and alpha_hw[i + di, j + dj] > alpha_thres   # :428-431
+            if ok:
+                valid.append(i * w + j)
+                nbs.append((i + di) * w + (j + dj))
+    rows = np.full((2 * bs,), -1, np.int32)
+    if valid:
+        for s in range(bs):
+            r = _rnd_u32(seed, 2, s) % len(valid)                                              # :438-439
+            rows[2 * s], rows[2 * s + 1] = valid[r], nbs[r]
+    return rows

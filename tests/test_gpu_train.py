@@ -237,3 +237,37 @@ def test_graphed_train_iter_equals_eager(cuda_dev):
     np.testing.assert_allclose(finals[0][1], finals[1][1], rtol=1e-5)
     # atomics reorder the weight-gradient sums, so equality is to fp32 rounding of the Adam-normalised update
     assert (finals[0][0] - finals[1][0]).abs().max().item() < 2e-5
+
+
+def test_outer_sample_matches_oracle(cuda_dev):
+    """SURVEY 8f N4 (train_nfr.py:380-467): pair sampler + row gathers against the Python restatement (same
+    counter-hash RNG), plus the structural invariants of the reference (8-neighbour pairs, both above alpha_thres)."""
+    from vqnerf_release_b200.nerfactor import train_nfr as T
+    h, w, bs = 37, 53, 256
+    rng = np.random.RandomState(2)
+    n = h * w
+    alpha = rng.uniform(0, 1, (n, 1)).astype(np.float32)
+    alpha[rng.uniform(size=(n, 1)) < 0.5] = 1.0
+    mk = lambda c: rng.uniform(-1, 1, (n, c)).astype(np.float32)
+    host = {'rayo': mk(3), 'rayd': mk(3), 'rgb': mk(3), 'xyz': mk(3), 'normal': mk(3), 'lvis': mk(512)}
+    t = lambda a: torch.as_tensor(a).to(cuda_dev)
+    hw = torch.tensor([[h, w]] * n, dtype=torch.int32, device=cuda_dev)
+    batch = ('view', hw, t(host['rayo']), t(host['rayd']), t(host['rgb']), t(alpha), t(alpha), t(host['xyz']),
+             t(host['normal']), t(host['lvis']))
+    for seed in (0, 7):
+        out = T.outer_sample(batch, {'n_rays_per_step': bs}, 'nerf', alpha_thres=0.9, seed=seed)
+        rows = O.outer_sample_rows(alpha.reshape(h, w), bs, seed, 0.9)
+        assert out[2].shape == (2 * bs, 3) and out[9].shape == (2 * bs, 512) and out[5].shape == (2 * bs, 1)
+        for k, idx in (('rayo', 2), ('rayd', 3), ('rgb', 4), ('xyz', 7), ('normal', 8), ('lvis', 9)):
+            assert np.array_equal(out[idx].cpu().numpy(), host[k][rows]), k
+        assert np.array_equal(out[5].cpu().numpy(), alpha[rows])
+        pi, pj = rows[0::2] // w, rows[0::2] % w
+        ni, nj = rows[1::2] // w, rows[1::2] % w
+        assert (np.maximum(np.abs(pi - ni), np.abs(pj - nj)) == 1).all()
+        assert (alpha[rows] > 0.9).all() and pi.min() >= 1 and pi.max() <= h - 2 and pj.min() >= 1 and pj.max() <= w - 2
+    # no threshold: every interior pixel is a candidate; no valid pair: rows = -1 and zero rows
+    out = T.outer_sample(batch, {'n_rays_per_step': bs}, 'nerf', alpha_thres=None, seed=3)
+    assert np.array_equal(out[7].cpu().numpy(), host['xyz'][O.outer_sample_rows(alpha.reshape(h, w), bs, 3, None)])
+    b0 = list(batch); b0[5] = torch.zeros_like(batch[5])
+    out = T.outer_sample(tuple(b0), {'n_rays_per_step': 8}, 'nerf', alpha_thres=0.9, seed=1)
+    assert float(out[7].abs().max()) == 0.0

@@ -105,6 +105,8 @@ SIGNATURES = {
     'vqn_adam_amsgrad': (_I, [_P, _P, _P, _P, _P, _P, _L, _F, _P, _F, _F, _F, _P]),
     'vqn_cast_f64_f32': (_I, [_P, _P, _P, _L, _P]),
     'vqn_cast_f32_f64': (_I, [_P, _P, _P, _L, _P]),
+    'vqn_sample_pairs': (_I, [_P, _P, _I, _I, _I, _F, _I, C.c_uint64, _P, _P, _P, _P, _P, _P, _P]),
+    'vqn_gather_rows': (_I, [_P, _P, _P, _L, _I, _P, _P]),
     'vqn_microbench_fma': (_I, [_P, _I, _I, C.POINTER(_D)]),
     'vqn_tc_selftest': (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
 }

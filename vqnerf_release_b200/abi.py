@@ -537,3 +537,37 @@ def cast_f64_f32(src, dst):
 def cast_f32_f64(src, dst):
     c = _ctx(src)
     L.check(c.lib.vqn_cast_f32_f64(c.handle, _p(src), _p(dst), src.numel(), L.stream_ptr(src.device)))
+
+
+# ---------------------------------------------------------------------------------------------
+# training-batch assembler (outer_sample, nerfactor/train_nfr.py:380-467)
+# ---------------------------------------------------------------------------------------------
+def sample_pairs(alpha: torch.Tensor, h: int, w: int, bs: int, seed: int, alpha_thres: Optional[float] = 0.9):
+    """rows int32 [2*bs] = [p1, p1_n, p2, p2_n, ...] and n_valid int32 [1] (device)."""
+    a = _f(alpha).reshape(-1)
+    if a.numel() != h * w:
+        raise ValueError('alpha must hold one H x W view')
+    dev = a.device
+    total = (h - 2) * (w - 2)
+    flag = torch.empty((total,), dtype=F32, device=dev)
+    nb = torch.empty((total,), dtype=torch.int32, device=dev)
+    valid = torch.empty((total,), dtype=torch.int32, device=dev)
+    work = torch.empty((total // 1024 + 2,), dtype=torch.int32, device=dev)
+    n_valid = torch.zeros((1,), dtype=torch.int32, device=dev)
+    rows = torch.empty((2 * bs,), dtype=torch.int32, device=dev)
+    c = _ctx(a)
+    L.check(c.lib.vqn_sample_pairs(c.handle, L.ptr(a), h, w, int(alpha_thres is not None),
+                                   float(alpha_thres if alpha_thres is not None else 0.0), bs, int(seed) & (2 ** 64 - 1),
+                                   L.ptr(flag), L.ptr(nb), L.ptr(valid), L.ptr(work), L.ptr(n_valid), L.ptr(rows),
+                                   L.stream_ptr(dev)))
+    return rows, n_valid
+
+
+def gather_rows(src: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
+    src = _f(src)
+    flat = src.reshape(src.shape[0], -1)
+    out = torch.empty((rows.shape[0], flat.shape[1]), dtype=F32, device=src.device)
+    c = _ctx(src)
+    L.check(c.lib.vqn_gather_rows(c.handle, L.ptr(flat), L.ptr(rows, torch.int32), rows.shape[0], flat.shape[1],
+                                  L.ptr(out), L.stream_ptr(src.device)))
+    return out.reshape((rows.shape[0],) + tuple(src.shape[1:]))

@@ -433,6 +433,34 @@ class GraphedTrainIter:
         return self.out
 
 
+def outer_sample(batch, config, data_type, alpha_thres=0.9, seed=0, hw=None):
+    """train_nfr.py:380-467: n_rays_per_step (pixel, random 8-neighbour) pairs of one H x W view, both above
+    alpha_thres, as the 2*bs-row batch [p1, p1_n, p2, p2_n, ...] of every per-pixel tensor.  `hw`: (H, W) if known
+    (avoids the reference's hw[0,:].numpy() host sync); `seed`: counter-hash seed of this draw (pass the step number).
+    `id_` (strings in the reference) is passed through unchanged."""
+    cfg = config
+    bs = int(cfg.getint('DEFAULT', 'n_rays_per_step')) if hasattr(cfg, 'getint') and hasattr(cfg, 'has_option') \
+        else int(cfg.get('n_rays_per_step', 1024))
+    if data_type == 'nerf':
+        id_, hw_t, rayo, rayd, rgb, alpha, pred_alpha, xyz, normal, lvis = batch
+    else:
+        id_, hw_t, rayo, rayd, rgb, alpha, pred_alpha, xyz, normal = batch
+        lvis = None
+    if hw is None:
+        hw = tuple(int(v) for v in hw_t[0, :].tolist())
+    h, w = hw
+    rows, n_valid = abi.sample_pairs(alpha, h, w, bs, seed, alpha_thres)
+    g = lambda t: abi.gather_rows(t, rows)
+    hw_out = hw_t.index_select(0, rows.clamp_min(0).long())          # int32 metadata: index plumbing
+    out = [id_, hw_out, g(rayo), g(rayd), g(rgb), g(alpha).reshape(-1, 1), g(pred_alpha).reshape(-1, 1), g(xyz),
+           g(normal)]
+    if data_type == 'nerf':
+        if lvis is None:
+            raise ValueError('NeRF data requires lvis')
+        out.append(g(lvis))
+    return tuple(out)
+
+
 def sync_inference_weights(model) -> None:
     """Re-pack the inference-side weight images (tensor-core swizzled copies) after optimizer steps."""
     st = getattr(model, '_train_state', None)
