@@ -130,8 +130,8 @@ class ClockSampler:
 
 def ncu_traffic(n, probes, precision):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r1b_ncu_traffic.json) -- only valid for the workload it was captured on, else None."""
-    p = os.path.join(ROOT, 'profiles', 'r1b_ncu_traffic.json')
+    (profiles/r1c_ncu_traffic.json) -- only valid for the workload it was captured on, else None."""
+    p = os.path.join(ROOT, 'profiles', 'r1c_ncu_traffic.json')
     try:
         d = json.load(open(p))
         w = d['workload']
@@ -143,7 +143,7 @@ def ncu_traffic(n, probes, precision):
                 'note': 'dram__bytes_read.sum + dram__bytes_write.sum of the encoder launch + the heads launch '
                         '(the latent z [n,256] fp32 = 655 MB is written by the first and read by the second; '
                         'weights stay in L2); algorithmic bytes of the fused pair: 40 B/point = 25.6 MB',
-                'source': 'profiles/r1b_ncu_traffic.json'}
+                'source': 'profiles/r1c_ncu_traffic.json'}
     except Exception:
         return None
 
