@@ -70,6 +70,15 @@ int64_t vqn_ctx_launch_count(const vqn_ctx* ctx);
  * reference guards with tf.debugging.check_numerics; read (with a sync of `stream`) and cleared here. */
 int vqn_ctx_check_numerics(vqn_ctx* ctx, vqn_stream stream);
 
+/* ---- workspace / buffer size queries (element counts) ---------------------------------------------------------- */
+/* float64 entries of the VQ statistics vector: K counts + sum((q-x)^2) + rows + dw[Z,K] */
+int64_t vqn_vq_stats_size(int z_dim, int k);
+/* int32 entries of the compaction workspace of vqn_compact_mask for n rows */
+int64_t vqn_compact_workspace_size(int64_t n);
+/* entries of flag_ws (float) = nb_ws = valid_ws (int32) of vqn_sample_pairs for an H x W view; its compact_ws needs
+ * vqn_compact_workspace_size of that count */
+int64_t vqn_sample_pairs_workspace_size(int h, int w);
+
 /* ---- light probe geometry: brdf/renderer.py:184-219 gen_light_xyz (host, float64) ------------- */
 int vqn_gen_light_xyz(int envmap_h, int envmap_w, double envmap_radius, double* xyz_out /*[h,w,3]*/,
                       double* areas_out /*[h,w]*/);

@@ -1,7 +1,7 @@
 """2-rank data-parallel training step == single-device global batch.  Run on a 2-GPU box:
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 \
-        benchmarks/multi_gpu_train_check.py
+        tests/multi_gpu_check.py
 
 Every rank first runs the FULL 512-row batch alone (no process group yet), then the ranks shard the same batch
 (pairs kept together, dist.shard_rows(align=2)), run the step with the single NCCL all-reduce of

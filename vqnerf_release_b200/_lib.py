@@ -66,6 +66,9 @@ SIGNATURES = {
     'vqn_ctx_destroy': (_I, [_P]),
     'vqn_ctx_launch_count': (_L, [_P]),
     'vqn_ctx_check_numerics': (_I, [_P, _P]),
+    'vqn_vq_stats_size': (_L, [_I, _I]),
+    'vqn_compact_workspace_size': (_L, [_L]),
+    'vqn_sample_pairs_workspace_size': (_L, [_I, _I]),
     'vqn_gen_light_xyz': (_I, [_I, _I, _D, C.POINTER(_D), C.POINTER(_D)]),
     'vqn_net_create': (_I, [_P, C.POINTER(NetDesc), C.POINTER(_P), _P]),
     'vqn_net_repack': (_I, [_P, C.POINTER(NetDesc), _P]),

@@ -170,7 +170,7 @@ def l2_normalize_rows(x: torch.Tensor) -> torch.Tensor:
 
 
 def vq_stats_size(z_dim: int, k: int) -> int:
-    return k + 2 + z_dim * k
+    return int(L.load().vqn_vq_stats_size(int(z_dim), int(k)))
 
 
 def vq_assign(inputs: torch.Tensor, codebook: torch.Tensor, sel_mask: Optional[torch.Tensor] = None,

@@ -72,6 +72,10 @@ extern "C" int vqn_ctx_destroy(vqn_ctx* ctx) {
   return VQN_OK;
 }
 
+extern "C" int64_t vqn_vq_stats_size(int z_dim, int k) { return (int64_t)k + 2 + (int64_t)z_dim * k; }
+extern "C" int64_t vqn_compact_workspace_size(int64_t n) { return n / 1024 + 2; }
+extern "C" int64_t vqn_sample_pairs_workspace_size(int h, int w) { return (int64_t)(h - 2) * (w - 2); }
+
 extern "C" int64_t vqn_ctx_launch_count(const vqn_ctx* ctx) { return ctx ? (int64_t)ctx->launches.load() : 0; }
 
 extern "C" int vqn_ctx_check_numerics(vqn_ctx* ctx, vqn_stream stream) {
