@@ -271,3 +271,47 @@ def test_outer_sample_matches_oracle(cuda_dev):
     b0 = list(batch); b0[5] = torch.zeros_like(batch[5])
     out = T.outer_sample(tuple(b0), {'n_rays_per_step': 8}, 'nerf', alpha_thres=0.9, seed=1)
     assert float(out[7].abs().max()) == 0.0
+
+
+def test_training_abi_edge_cases(cuda_dev):
+    """Error behaviour and degenerate sizes of the training entry points (C ABI -> Python exceptions)."""
+    from vqnerf_release_b200 import abi
+    from vqnerf_release_b200.nerfactor import train_nfr as T
+    z = torch.zeros((4, 8), device=cuda_dev)
+    w = torch.zeros((8, 4), device=cuda_dev)
+    # m == 0 is a no-op, bad leading dimensions are rejected
+    abi.dense_forward(z, 8, w, None, z, 8, 0, 8, 4, 0)
+    with pytest.raises(ValueError):
+        abi.dense_forward(z, 4, w, None, z, 8, 4, 8, 4, 0)          # ldx < k
+    with pytest.raises(ValueError):
+        abi.dense_backward_data(z, 2, w, z, 8, None, 0, 0, False, 4, 8, 4)   # lddz < n
+    with pytest.raises(ValueError):
+        abi.dense_backward_data(z, 4, w, z, 8, None, 0, 1, False, 4, 8, 4)   # act_prev without yprev
+    # loss kernel needs (pixel, neighbour) pairs
+    f = lambda *s: torch.zeros(s, device=cuda_dev)
+    with pytest.raises(ValueError):
+        abi.loss_train(f(3, 3), f(3, 3), f(3, 3), f(3, 256), f(3, 3), f(3, 1), True, 0.2, 1.0, 0.05, 1e-3, 60.0, 0.1,
+                       1.0, f(3), f(3, 3), f(3, 3), f(3, 256), f(3, 3), None)
+    # odd batch through train_iter
+    scene, batch, m, _ = _train_pair(cuda_dev, 7)
+    with pytest.raises(ValueError):
+        T.train_iter(m, _batch_tuple(batch, cuda_dev), T.Adam(), 4)
+    # non-nerf data is refused (no gamma variables in the training kernels)
+    m.data_type = 'dtu'
+    with pytest.raises(NotImplementedError):
+        T.train_iter(m, _batch_tuple(batch, cuda_dev), T.Adam(), 4)
+    # sampler argument checks
+    with pytest.raises(ValueError):
+        abi.sample_pairs(torch.ones((4,), device=cuda_dev), 2, 2, 4, 0)
+    with pytest.raises(ValueError):
+        abi.sample_pairs(torch.ones((10,), device=cuda_dev), 3, 3, 4, 0)
+    # partially-foreground batch takes the compaction path and still matches the oracle's loss
+    scene, batch, m, ovq = _train_pair(cuda_dev, 256, seed=5, fg=0.75)
+    keep = batch['alpha'][:, 0] > 0
+    if keep.sum() % 2:                                  # keep (pixel, neighbour) pairing: drop one more row
+        batch['alpha'][np.where(keep)[0][-1], 0] = 0.0
+        batch['pred_alpha'] = batch['alpha'].copy()
+    ref = O.train_step(scene, batch, ovq, global_bs=64)
+    loss, vis, _ = T.train_iter(m, _batch_tuple(batch, cuda_dev), T.Adam(), 64, apply=False)
+    _close(loss, ref['loss'], 'loss with background rows', rtol=1e-4, atol=1e-7)
+    _tensor_close(m._train_state.dW['fine_enc'][0], ref['grads']['fine_enc'][0][0], 'd fine_enc.kernel[0] (masked batch)')
