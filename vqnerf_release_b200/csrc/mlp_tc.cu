@@ -52,6 +52,13 @@ struct TcLayer {
   const uint8_t* side_w;
   int side_col;
   int add_col;            // >= 0: final epilogue adds TMEM columns [add_col, add_col + 16)
+  // Narrow tail: a last layer with <= 4 outputs that follows this layer (after the fold above its K is just this
+  // layer's width) is evaluated on the CUDA cores while this layer's accumulator is drained -- 3 x width FMAs per
+  // row instead of four more A chunks (32 KB of smem stores + fences each) for an MMA with N = 16.
+  const float* tail_w;    // fp32 Keras kernel of the tail layer, rows [0, N) used, row stride tail_n
+  const float* tail_b;    // its bias
+  int tail_n, tail_act, tail_out_slot, tail_add_col, tail_woff;
+  float tail_scale, tail_bias;
 };
 
 struct TcProgram {
@@ -205,7 +212,7 @@ struct TcCfg {
   static constexpr uint32_t W_SLOT = W_MAIN + W_SIDE_PLANE * PLANES;
   static constexpr size_t SMEM = (size_t)SA * A_SLOT + (size_t)SW * W_SLOT + 1024;
 };
-#define TC_BIAS_FLOATS 2048
+#define TC_BIAS_FLOATS 4096
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
@@ -353,8 +360,14 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
     tc::mbar_fence_init();
   }
   // stage every layer's bias in shared memory (layer l at bias_off[l]; host guarantees the total fits)
-  for (int l = 0; l < pg.n_layers; ++l)
+  for (int l = 0; l < pg.n_layers; ++l) {
     for (int i = tid; i < pg.layers[l].Npad; i += C::THREADS) bias_s[pg.layers[l].bias_off + i] = pg.layers[l].bias[i];
+    if (pg.layers[l].tail_w)          // tail kernel rows as float4 {w[k][0..3]} (zero padded)
+      for (int i = tid; i < pg.layers[l].N * 4; i += C::THREADS) {
+        const int k = i >> 2, o = i & 3;
+        bias_s[pg.layers[l].tail_woff + i] = o < pg.layers[l].tail_n ? pg.layers[l].tail_w[k * pg.layers[l].tail_n + o] : 0.f;
+      }
+  }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -489,6 +502,63 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
           }
         }
         ++gl;                               // layer l's chunks are all queued
+        if (pg.layers[l].tail_w) {
+          // narrow tail layer on the CUDA cores: out[o] = act(sum_k relu(acc[k] + b[k]) W[k][o] + side[o] + bias[o])
+          const TcLayer& ly = pg.layers[l];
+          tc::mbar_wait(&acc_full, (gl - 1) & 1);
+          tc::fence_after_sync();
+          const float* lb = bias_s + ly.bias_off;
+          const float4* tw = reinterpret_cast<const float4*>(bias_s + ly.tail_woff);
+          float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+          for (int cb = grp; cb * 32 < ly.N; cb += C::G) {
+            const int c16 = cb * 32 + 16 * half;
+            if (c16 < ly.N) {
+              float v[16];
+              tc::tmem_ld16(lane_addr + (uint32_t)(ly.tmem_col + c16), v);
+              bias_act32_dyn(v, lb + c16, ly.act);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float4 w4 = tw[c16 + j];
+                p0 = fmaf(v[j], w4.x, p0); p1 = fmaf(v[j], w4.y, p1); p2 = fmaf(v[j], w4.z, p2); p3 = fmaf(v[j], w4.w, p3);
+              }
+            }
+          }
+          // the four partial sums of a row (2 groups x 2 column halves) meet in the (free) first A slot
+          float4* part = reinterpret_cast<float4*>(a_ring);
+          part[r * 4 + grp * 2 + half] = make_float4(p0, p1, p2, p3);
+          tc::fence_before_sync();
+          asm volatile("bar.sync 3, %0;" ::"r"(256 * C::G) : "memory");
+          if (grp == 0 && half == 0) {
+            float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int q = 0; q < 2 * C::G; ++q) {
+              const float4 t4 = part[r * 4 + q];
+              o[0] += t4.x; o[1] += t4.y; o[2] += t4.z; o[3] += t4.w;
+            }
+            if (ly.tail_add_col >= 0) {            // folded skip connection: + x . W_x
+              float sv[16];
+              tc::tmem_ld16(lane_addr + (uint32_t)ly.tail_add_col, sv);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) o[q] += sv[q];
+            }
+            float* go = pg.outs[ly.tail_out_slot];
+            const int gs = pg.out_stride[ly.tail_out_slot];
+            bool bad = false;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (q < ly.tail_n) {
+                float t = o[q] + ly.tail_b[q];
+                t = ly.tail_act == VQN_ACT_RELU ? fmaxf(t, 0.f) : (ly.tail_act == VQN_ACT_SIGMOID ? fast_sigmoid(t) : t);
+                t = t * ly.tail_scale + ly.tail_bias;
+                bad |= !isfinite(t);
+                if (valid) go[pi * gs + q] = t;
+              }
+            }
+            if (valid && bad) atomicOr(pg.nonfinite, 1);
+          }
+          tc::fence_before_sync();
+          asm volatile("bar.sync 3, %0;" ::"r"(256 * C::G) : "memory");   // scratch is free again
+        }
         if (pg.layers[l].out_slot >= 0) {
           // final layer of a network: drain its accumulator to global memory (column blocks split over groups)
           const TcLayer& ly = pg.layers[l];
@@ -697,6 +767,7 @@ static bool tc_append_net(TcBuilder& B, vqn_net* net, TcPack* tp, int first_src,
     ly.N = d.widths[i]; ly.Npad = tp->Npad[i]; ly.act = d.acts[i];
     ly.out_slot = -1; ly.post_scale = 1.f; ly.post_bias = 0.f;
     ly.tmem_col = (B.pg.n_layers & 1) * 256; ly.side_w = nullptr; ly.side_col = 0; ly.add_col = -1;
+    ly.tail_w = nullptr; ly.tail_b = nullptr; ly.tail_n = 0; ly.tail_out_slot = -1; ly.tail_add_col = -1;
     const bool after_skip = (d.skip_at >= 0 && i == d.skip_at + 1);
     const int seg0_rows = (i == 0) ? d.in_dim : d.widths[i - 1];
     ly.nseg = 1;
@@ -714,6 +785,15 @@ static bool tc_append_net(TcBuilder& B, vqn_net* net, TcPack* tp, int first_src,
         l0.side_w = tp->w[i] + (size_t)ly.seg_chunks[0] * chunk_bytes;
         l0.side_col = fold_side_col;
         ly.add_col = fold_side_col;
+        if (i == d.n_layers - 1 && d.widths[i] <= 4 && i - 1 > 0 && B.pg.n_layers - 1 > first_layer) {
+          // ... and what is left of this layer (K = previous width, <= 4 outputs) becomes the TAIL of the previous
+          // layer: no TcLayer is appended for it
+          TcLayer& prev = B.pg.layers[B.pg.n_layers - 1];
+          prev.tail_w = d.w[i]; prev.tail_b = d.b[i]; prev.tail_n = d.widths[i]; prev.tail_act = d.acts[i];
+          prev.tail_out_slot = out_slot; prev.tail_add_col = fold_side_col;
+          prev.tail_scale = post_scale; prev.tail_bias = post_bias;
+          continue;
+        }
       } else {
         ly.nseg = 2;
         ly.seg_type[1] = first_src;
@@ -738,6 +818,8 @@ static int tc_launch(vqn_ctx* ctx, TcProgram& pg, int precision, cudaStream_t s)
   pg.trace = g_tc_trace;
   int boff = 0;
   for (int l = 0; l < pg.n_layers; ++l) { pg.layers[l].bias_off = boff; boff += vqn_round_up(pg.layers[l].Npad, 32); }
+  for (int l = 0; l < pg.n_layers; ++l)
+    if (pg.layers[l].tail_w) { pg.layers[l].tail_woff = boff; boff += 4 * pg.layers[l].N; }
   if (boff > TC_BIAS_FLOATS) { vqn_set_error("tensor-core MLP: bias table exceeds %d floats", TC_BIAS_FLOATS); return VQN_ERR_UNSUPPORTED; }
   if (pg.pts && 3 + 6 * pg.n_freqs > 64) { vqn_set_error("tensor-core MLP: embedding wider than 64"); return VQN_ERR_UNSUPPORTED; }
   long long tiles = (pg.n + TC_M - 1) / TC_M;
@@ -800,7 +882,7 @@ int vqn_tc_pred_heads(vqn_ctx* ctx, vqn_net* diff, vqn_net* spec, vqn_net* rough
     if (rc != VQN_OK) return rc;
     B.pg.outs[h] = outs[h]; B.pg.out_stride[h] = nets[h]->desc.widths[nets[h]->n_layers - 1];
     // TMEM plan of a [256, 128, out] head: layer 0 at columns [0,256), layer 1 at [256,384), the folded skip
-    // products of the three heads at [384 + 16 h, +16), the narrow last layer at [448,464)
+    // products of the three heads at [384 + 16 h, +16), the narrow last layer at [448,464) unless it runs as a tail
     const vqn_net_desc& hd = nets[h]->desc;
     const bool plan = hd.n_layers == 3 && hd.skip_at == 1 && hd.widths[0] <= 256 && hd.widths[1] <= 128 &&
                       tp->Npad[2] == 16;
@@ -808,7 +890,10 @@ int vqn_tc_pred_heads(vqn_ctx* ctx, vqn_net* diff, vqn_net* spec, vqn_net* rough
     if (!tc_append_net(B, nets[h], tp, SRC_GLOBAL, h, h == 0 ? slope : 1.f, h == 0 ? bias : 0.f,
                        plan ? 384 + 16 * h : -1))
       TC_UNSUPPORTED("pred_heads: program does not fit the tensor-core kernel");
-    if (plan) { B.pg.layers[l0].tmem_col = 0; B.pg.layers[l0 + 1].tmem_col = 256; B.pg.layers[l0 + 2].tmem_col = 448; }
+    if (plan) {
+      B.pg.layers[l0].tmem_col = 0; B.pg.layers[l0 + 1].tmem_col = 256;
+      if (B.pg.n_layers - l0 > 2) B.pg.layers[l0 + 2].tmem_col = 448;     // absent when it became the tail of layer 1
+    }
   }
   if (B.pg.g_dim % 4 != 0) TC_UNSUPPORTED("pred_heads: z_dim % 4 != 0");
   return tc_launch(ctx, B.pg, precision, s);
