@@ -44,20 +44,18 @@ struct TcLayer {
   int bias_off;           // offset of this layer's bias inside the shared-memory bias table
   float post_scale, post_bias;
   int tmem_col;           // first TMEM column of this layer's accumulator
-  // Folded skip connection: concat(y, x) . W = y . W_y + x . W_x.  When the layer after the skip is narrow (Npad 16)
-  // its x-half is accumulated as a SIDE product of the network's first layer, whose A chunks are the same x
-  // chunks (side_w = W_x chunk images, 16 columns at TMEM column side_col); the narrow layer then only consumes
-  // its y chunks and its epilogue adds the side accumulator (add_col).  This halves the number of times the
-  // latent has to be re-read, split and staged per head.
-  const uint8_t* side_w;
-  int side_col;
-  int add_col;            // >= 0: final epilogue adds TMEM columns [add_col, add_col + 16)
+  // Folded skip connection of a narrow last layer: concat(y, x) . W = y . W_y + x . W_x with <= 4 outputs.  The x half
+  // is accumulated on the CUDA cores by the producers of the network's FIRST layer while they hold the same x
+  // values in registers (skip_w = W_x rows, skip_n outputs; 4 FMAs per value), the y half by the tail below -- the
+  // narrow layer needs no MMA, no A chunks and no second pass over x.
+  const float* skip_w;    // fp32 rows of the tail kernel that multiply x: [g_dim, skip_n]
+  int skip_n, skip_woff;
   // Narrow tail: a last layer with <= 4 outputs that follows this layer (after the fold above its K is just this
   // layer's width) is evaluated on the CUDA cores while this layer's accumulator is drained -- 3 x width FMAs per
   // row instead of four more A chunks (32 KB of smem stores + fences each) for an MMA with N = 16.
   const float* tail_w;    // fp32 Keras kernel of the tail layer, rows [0, N) used, row stride tail_n
   const float* tail_b;    // its bias
-  int tail_n, tail_act, tail_out_slot, tail_add_col, tail_woff;
+  int tail_n, tail_act, tail_out_slot, tail_add_skip, tail_woff;
   float tail_scale, tail_bias;
 };
 
@@ -207,12 +205,10 @@ struct TcCfg {
   static constexpr int THREADS = 32 * (8 * G + 2);         // + MMA warp + weight-producer warp
   static constexpr uint32_t A_PLANE = TC_M * 128;          // 16 KB
   static constexpr uint32_t A_SLOT = A_PLANE * PLANES;
-  static constexpr uint32_t W_MAIN = (uint32_t)TC_NPAD_MAX * 128 * PLANES;
-  static constexpr uint32_t W_SIDE_PLANE = 16 * 128;       // side product: 16 output columns
-  static constexpr uint32_t W_SLOT = W_MAIN + W_SIDE_PLANE * PLANES;
+  static constexpr uint32_t W_SLOT = (uint32_t)TC_NPAD_MAX * 128 * PLANES;
   static constexpr size_t SMEM = (size_t)SA * A_SLOT + (size_t)SW * W_SLOT + 1024;
 };
-#define TC_BIAS_FLOATS 4096
+#define TC_BIAS_FLOATS 6144
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
@@ -362,6 +358,11 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
   // stage every layer's bias in shared memory (layer l at bias_off[l]; host guarantees the total fits)
   for (int l = 0; l < pg.n_layers; ++l) {
     for (int i = tid; i < pg.layers[l].Npad; i += C::THREADS) bias_s[pg.layers[l].bias_off + i] = pg.layers[l].bias[i];
+    if (pg.layers[l].skip_w)          // skip kernel rows as float4 {w[k][0..3]} (zero padded)
+      for (int i = tid; i < pg.g_dim * 4; i += C::THREADS) {
+        const int k = i >> 2, o = i & 3;
+        bias_s[pg.layers[l].skip_woff + i] = o < pg.layers[l].skip_n ? pg.layers[l].skip_w[k * pg.layers[l].skip_n + o] : 0.f;
+      }
     if (pg.layers[l].tail_w)          // tail kernel rows as float4 {w[k][0..3]} (zero padded)
       for (int i = tid; i < pg.layers[l].N * 4; i += C::THREADS) {
         const int k = i >> 2, o = i & 3;
@@ -391,6 +392,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
     uint32_t ga = 0;                                     // global A-chunk counter
     uint32_t gl = 0;                                     // global layer counter (acc_full phase)
     int ptrace_n = 0;
+    float sp0 = 0.f, sp1 = 0.f, sp2 = 0.f, sp3 = 0.f;   // folded-skip partial sums of this thread (see TcLayer::skip_w)
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long pi = tile * TC_M + r;              // compact point index
       const bool valid = pi < n;
@@ -463,6 +465,14 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                 v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
               }
               group_bar(grp);                    // every row has been read before plane C is overwritten
+              if (pg.layers[l].skip_w) {         // folded skip connection: x . W_x for this thread's 16 values
+                const float4* sw = reinterpret_cast<const float4*>(bias_s + pg.layers[l].skip_woff) + col_base + 16 * half;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float4 w4 = sw[j];
+                  sp0 = fmaf(v[j], w4.x, sp0); sp1 = fmaf(v[j], w4.y, sp1); sp2 = fmaf(v[j], w4.z, sp2); sp3 = fmaf(v[j], w4.w, sp3);
+                }
+              }
               store_chunk32<BF16>(dst, r, 16 * half, v);
             } else {
 #pragma unroll
@@ -484,6 +494,14 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = 0.f;
                   }
+                  if (pg.layers[l].skip_w) {     // folded skip connection (see the tf32 path)
+                    const float4* sw = reinterpret_cast<const float4*>(bias_s + pg.layers[l].skip_woff) + col0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                      const float4 w4 = sw[j];
+                      sp0 = fmaf(v[j], w4.x, sp0); sp1 = fmaf(v[j], w4.y, sp1); sp2 = fmaf(v[j], w4.z, sp2); sp3 = fmaf(v[j], w4.w, sp3);
+                    }
+                  }
                 }
                 // the values are ready in registers BEFORE the slot is claimed: the TMEM / global load latency
                 // and the activation math overlap the MMAs that are still reading the slot's previous chunk
@@ -503,13 +521,14 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
         }
         ++gl;                               // layer l's chunks are all queued
         if (pg.layers[l].tail_w) {
-          // narrow tail layer on the CUDA cores: out[o] = act(sum_k relu(acc[k] + b[k]) W[k][o] + side[o] + bias[o])
+          // narrow tail layer on the CUDA cores: out[o] = act(sum_k relu(acc[k] + b[k]) W_y[k][o] + x . W_x[o] + bias[o])
           const TcLayer& ly = pg.layers[l];
           tc::mbar_wait(&acc_full, (gl - 1) & 1);
           tc::fence_after_sync();
           const float* lb = bias_s + ly.bias_off;
           const float4* tw = reinterpret_cast<const float4*>(bias_s + ly.tail_woff);
           float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+          if (ly.tail_add_skip) { p0 = sp0; p1 = sp1; p2 = sp2; p3 = sp3; sp0 = sp1 = sp2 = sp3 = 0.f; }
           for (int cb = grp; cb * 32 < ly.N; cb += C::G) {
             const int c16 = cb * 32 + 16 * half;
             if (c16 < ly.N) {
@@ -534,12 +553,6 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
             for (int q = 0; q < 2 * C::G; ++q) {
               const float4 t4 = part[r * 4 + q];
               o[0] += t4.x; o[1] += t4.y; o[2] += t4.z; o[3] += t4.w;
-            }
-            if (ly.tail_add_col >= 0) {            // folded skip connection: + x . W_x
-              float sv[16];
-              tc::tmem_ld16(lane_addr + (uint32_t)ly.tail_add_col, sv);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) o[q] += sv[q];
             }
             float* go = pg.outs[ly.tail_out_slot];
             const int gs = pg.out_stride[ly.tail_out_slot];
@@ -573,12 +586,6 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
             if (c16 < ly.N) {
               float v[16];
               tc::tmem_ld16(lane_addr + (uint32_t)(ly.tmem_col + c16), v);
-              if (ly.add_col >= 0 && c16 == 0) {           // folded skip connection: + x . W_x (16 columns)
-                float sv[16];
-                tc::tmem_ld16(lane_addr + (uint32_t)ly.add_col, sv);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] += sv[j];
-              }
               if (c16 + 16 <= ly.Npad) bias_act32_dyn(v, lb + c16, ly.act);
               else {
 #pragma unroll
@@ -644,12 +651,8 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
         for (int l = 0; l < L; ++l) {
           const TcLayer& ly = pg.layers[l];
           const uint32_t idesc = tc::make_idesc(BF16 ? tc::FMT_BF16 : tc::FMT_TF32, TC_M, ly.Npad);
-          const uint32_t idesc_side = tc::make_idesc(BF16 ? tc::FMT_BF16 : tc::FMT_TF32, TC_M, 16);
           const uint32_t idesc_c = tc::make_idesc(tc::FMT_BF16, TC_M, ly.Npad);        // correction plane (kind::f16)
-          const uint32_t idesc_side_c = tc::make_idesc(tc::FMT_BF16, TC_M, 16);
           const uint32_t d_tmem = tmem_base + (uint32_t)ly.tmem_col;
-          const uint32_t d_side = tmem_base + (uint32_t)ly.side_col;
-          const bool side = ly.side_w != nullptr;
           const int nch = ly.seg_chunks[0] + (ly.nseg > 1 ? ly.seg_chunks[1] : 0);
           const uint32_t w_plane = (uint32_t)ly.Npad * 128;
           long long* tr = (pg.trace && blockIdx.x == 0 && tile < 4 * (long long)gridDim.x)
@@ -657,15 +660,14 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
           if (tr) tr[0] = clock64();
           if (pending_drain) {
             // a final layer is being drained to global: wait before overwriting ITS columns (other columns may go on)
-            const bool hit = (ly.tmem_col < pend_hi && ly.tmem_col + ly.Npad > pend_lo) ||
-                             (side && ly.side_col < pend_hi && ly.side_col + 16 > pend_lo) || ly.out_slot >= 0;
+            const bool hit = (ly.tmem_col < pend_hi && ly.tmem_col + ly.Npad > pend_lo) || ly.out_slot >= 0;
             if (hit) {
               tc::mbar_wait(&drain_done, gd & 1);
               tc::fence_after_sync();
               ++gd; pending_drain = false;
             }
           }
-          uint32_t acc = 0, acc_s = 0;
+          uint32_t acc = 0;
           for (int c = 0; c < nch; ++c, ++ga, ++gw) {
             const int sa = ga % C::SA, sw = gw % C::SW;
             if (tr && c == 0) tr[1] = clock64();
@@ -690,16 +692,6 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                 const uint64_t b_c = tc::make_desc_sw128(w_addr + w_plane + 32 * s);
                 tc::mma_ss<false>(d_tmem, a_c, b_c, idesc_c, 1);
               }
-              if (side) {
-                const uint64_t s_hi = tc::make_desc_sw128(w_addr + C::W_MAIN + 32 * s);
-                tc::mma_ss<!BF16>(d_side, a_hi, s_hi, idesc_side, acc_s);
-                acc_s = 1;
-                if (!BF16) {
-                  const uint64_t a_c = tc::make_desc_sw128(a_addr + C::A_PLANE + 32 * s);
-                  const uint64_t s_c = tc::make_desc_sw128(w_addr + C::W_MAIN + C::W_SIDE_PLANE + 32 * s);
-                  tc::mma_ss<false>(d_side, a_c, s_c, idesc_side_c, 1);
-                }
-              }
             }
             tc::mma_commit(&a_empty[sa]);       // slots are free once these MMAs have read them
             tc::mma_commit(&w_empty[sw]);
@@ -723,15 +715,11 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
           for (int c = 0; c < nch; ++c, ++gw) {
             const int sw = gw % C::SW;
             tc::mbar_wait(&w_empty[sw], ((gw / C::SW) & 1) ^ 1);
-            const uint32_t sbytes = ly.side_w ? C::W_SIDE_PLANE * C::PLANES : 0u;
 #ifdef TC_EXPERIMENT_NO_W
             if (gw >= (uint32_t)C::SW) { tc::mbar_arrive(&w_full[sw]); continue; }
 #endif
-            tc::mbar_expect_tx(&w_full[sw], bytes + sbytes);
+            tc::mbar_expect_tx(&w_full[sw], bytes);
             tc::bulk_g2s(w_ring + (size_t)sw * C::W_SLOT, ly.w + (size_t)c * bytes, bytes, &w_full[sw]);
-            if (sbytes)
-              tc::bulk_g2s(w_ring + (size_t)sw * C::W_SLOT + C::W_MAIN, ly.side_w + (size_t)c * sbytes, sbytes,
-                           &w_full[sw]);
           }
         }
       }
@@ -756,7 +744,7 @@ struct TcBuilder {
 // Append one network.  first_src: where its input x comes from (SRC_EMBED / SRC_GLOBAL / SRC_DRAIN = output of the
 // previous appended layer).  out_slot: global output slot of the last layer (-1: it feeds the next network).
 static bool tc_append_net(TcBuilder& B, vqn_net* net, TcPack* tp, int first_src, int out_slot, float post_scale,
-                          float post_bias, int fold_side_col = -1) {
+                          float post_bias, bool fold_narrow_tail = false) {
   const vqn_net_desc& d = net->desc;
   const int first_layer = B.pg.n_layers;
   for (int i = 0; i < d.n_layers; ++i) {
@@ -766,8 +754,8 @@ static bool tc_append_net(TcBuilder& B, vqn_net* net, TcPack* tp, int first_src,
     ly.w = tp->w[i]; ly.bias = tp->bias[i];
     ly.N = d.widths[i]; ly.Npad = tp->Npad[i]; ly.act = d.acts[i];
     ly.out_slot = -1; ly.post_scale = 1.f; ly.post_bias = 0.f;
-    ly.tmem_col = (B.pg.n_layers & 1) * 256; ly.side_w = nullptr; ly.side_col = 0; ly.add_col = -1;
-    ly.tail_w = nullptr; ly.tail_b = nullptr; ly.tail_n = 0; ly.tail_out_slot = -1; ly.tail_add_col = -1;
+    ly.tmem_col = (B.pg.n_layers & 1) * 256; ly.skip_w = nullptr; ly.skip_n = 0;
+    ly.tail_w = nullptr; ly.tail_b = nullptr; ly.tail_n = 0; ly.tail_out_slot = -1; ly.tail_add_skip = 0;
     const bool after_skip = (d.skip_at >= 0 && i == d.skip_at + 1);
     const int seg0_rows = (i == 0) ? d.in_dim : d.widths[i - 1];
     ly.nseg = 1;
@@ -778,22 +766,17 @@ static bool tc_append_net(TcBuilder& B, vqn_net* net, TcPack* tp, int first_src,
     if (after_skip) {
       if (first_src == SRC_DRAIN) return false;   // x must be regenerable (embedding / global rows)
       const int xc = vqn_round_up(d.in_dim, B.E) / B.E;
-      if (fold_side_col >= 0 && tp->Npad[i] == 16 && i > 0) {
-        // fold the x-half into a side product of the first layer (same x chunks, 16 output columns)
+      if (fold_narrow_tail && first_src == SRC_GLOBAL && i == d.n_layers - 1 && d.widths[i] <= 4 && i >= 2) {
+        // Narrow last layer after the skip: y . W_y runs as the TAIL of the previous layer and x . W_x is accumulated
+        // by the producers of the first layer (TcLayer::skip_w); no TcLayer is appended for it.
         TcLayer& l0 = B.pg.layers[first_layer];
-        const size_t chunk_bytes = (size_t)16 * 128 * (B.E == 64 ? 1 : 2);
-        l0.side_w = tp->w[i] + (size_t)ly.seg_chunks[0] * chunk_bytes;
-        l0.side_col = fold_side_col;
-        ly.add_col = fold_side_col;
-        if (i == d.n_layers - 1 && d.widths[i] <= 4 && i - 1 > 0 && B.pg.n_layers - 1 > first_layer) {
-          // ... and what is left of this layer (K = previous width, <= 4 outputs) becomes the TAIL of the previous
-          // layer: no TcLayer is appended for it
-          TcLayer& prev = B.pg.layers[B.pg.n_layers - 1];
-          prev.tail_w = d.w[i]; prev.tail_b = d.b[i]; prev.tail_n = d.widths[i]; prev.tail_act = d.acts[i];
-          prev.tail_out_slot = out_slot; prev.tail_add_col = fold_side_col;
-          prev.tail_scale = post_scale; prev.tail_bias = post_bias;
-          continue;
-        }
+        TcLayer& prev = B.pg.layers[B.pg.n_layers - 1];
+        l0.skip_w = d.w[i] + (size_t)d.widths[i - 1] * d.widths[i];      // Keras rows: y first, then x (mlp.py:47-48)
+        l0.skip_n = d.widths[i];
+        prev.tail_w = d.w[i]; prev.tail_b = d.b[i]; prev.tail_n = d.widths[i]; prev.tail_act = d.acts[i];
+        prev.tail_out_slot = out_slot; prev.tail_add_skip = 1;
+        prev.tail_scale = post_scale; prev.tail_bias = post_bias;
+        continue;
       } else {
         ly.nseg = 2;
         ly.seg_type[1] = first_src;
@@ -818,8 +801,10 @@ static int tc_launch(vqn_ctx* ctx, TcProgram& pg, int precision, cudaStream_t s)
   pg.trace = g_tc_trace;
   int boff = 0;
   for (int l = 0; l < pg.n_layers; ++l) { pg.layers[l].bias_off = boff; boff += vqn_round_up(pg.layers[l].Npad, 32); }
-  for (int l = 0; l < pg.n_layers; ++l)
+  for (int l = 0; l < pg.n_layers; ++l) {
     if (pg.layers[l].tail_w) { pg.layers[l].tail_woff = boff; boff += 4 * pg.layers[l].N; }
+    if (pg.layers[l].skip_w) { pg.layers[l].skip_woff = boff; boff += 4 * pg.g_dim; }
+  }
   if (boff > TC_BIAS_FLOATS) { vqn_set_error("tensor-core MLP: bias table exceeds %d floats", TC_BIAS_FLOATS); return VQN_ERR_UNSUPPORTED; }
   if (pg.pts && 3 + 6 * pg.n_freqs > 64) { vqn_set_error("tensor-core MLP: embedding wider than 64"); return VQN_ERR_UNSUPPORTED; }
   long long tiles = (pg.n + TC_M - 1) / TC_M;
@@ -881,19 +866,15 @@ int vqn_tc_pred_heads(vqn_ctx* ctx, vqn_net* diff, vqn_net* spec, vqn_net* rough
     int rc = tc_pack_get(nets[h], precision, s, &tp);
     if (rc != VQN_OK) return rc;
     B.pg.outs[h] = outs[h]; B.pg.out_stride[h] = nets[h]->desc.widths[nets[h]->n_layers - 1];
-    // TMEM plan of a [256, 128, out] head: layer 0 at columns [0,256), layer 1 at [256,384), the folded skip
-    // products of the three heads at [384 + 16 h, +16), the narrow last layer at [448,464) unless it runs as a tail
+    // [256, 128, out <= 4] head: layer 0 at TMEM columns [0,256), layer 1 at [256,384); the narrow last layer is
+    // folded into the producers of layer 0 (x half) and the tail of layer 1 (y half)
     const vqn_net_desc& hd = nets[h]->desc;
     const bool plan = hd.n_layers == 3 && hd.skip_at == 1 && hd.widths[0] <= 256 && hd.widths[1] <= 128 &&
-                      tp->Npad[2] == 16;
+                      hd.widths[2] <= 4;
     const int l0 = B.pg.n_layers;
-    if (!tc_append_net(B, nets[h], tp, SRC_GLOBAL, h, h == 0 ? slope : 1.f, h == 0 ? bias : 0.f,
-                       plan ? 384 + 16 * h : -1))
+    if (!tc_append_net(B, nets[h], tp, SRC_GLOBAL, h, h == 0 ? slope : 1.f, h == 0 ? bias : 0.f, plan))
       TC_UNSUPPORTED("pred_heads: program does not fit the tensor-core kernel");
-    if (plan) {
-      B.pg.layers[l0].tmem_col = 0; B.pg.layers[l0 + 1].tmem_col = 256;
-      if (B.pg.n_layers - l0 > 2) B.pg.layers[l0 + 2].tmem_col = 448;     // absent when it became the tail of layer 1
-    }
+    if (plan && B.pg.n_layers - l0 == 2) { B.pg.layers[l0].tmem_col = 0; B.pg.layers[l0 + 1].tmem_col = 256; }
   }
   if (B.pg.g_dim % 4 != 0) TC_UNSUPPORTED("pred_heads: z_dim % 4 != 0");
   return tc_launch(ctx, B.pg, precision, s);
