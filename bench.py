@@ -36,6 +36,10 @@ N_POINTS = H * W
 MLP_ENC_FLOP = 2 * 179968
 MLP_HEADS_FLOP = 2 * 296832
 SHADE_FLOP_PER_LIGHT = 110.0
+# NeuS networks of confs/nerf.conf: MACs per sample
+SDF_TRUNK_MACS = 39 * 256 + 2 * 256 * 256 + 256 * 217 + 4 * 256 * 256      # lin0 .. lin7
+SDF_MACS = SDF_TRUNK_MACS + 256 * 257                                       # = 524 544
+COLOR_MACS = 289 * 256 + 3 * 256 * 256 + 256 * 3                            # = 271 360
 CPU_SAMPLE_POINTS = 4096      # chunk size of the CPU restatement (config #1 size; bounds the [N,512,3] intermediates)
 CPU_BUDGET_S = 12.0           # keep adding chunks until this much CPU time has been spent
 
@@ -333,6 +337,65 @@ def bench_neus_scan(dev, hbm_peak):
     return out
 
 
+def bench_neus_render(dev):
+    """BASELINE configs[4] end to end with the NATIVE networks (neus/fields.py on the fused tcgen05 kernel):
+    NeuSRenderer.render = SDF net on 64 coarse samples, 4 x (up_sample + SDF net on 16 new samples + merge),
+    render_core (SDF value + feature + gradient jets in one launch, colour net, compositing); nerf.conf network sizes
+    (SDF 39 -> 256 x 8 -> 257, colour 289 -> 256 x 4 -> 3), geometric random init.  Also the SDF kernel alone."""
+    import torch
+    from vqnerf_release_b200.neus.fields import RenderingNetwork, SDFNetwork, SingleVarianceNetwork
+    from vqnerf_release_b200.neus.renderer import NeuSRenderer
+    torch.manual_seed(0)
+    sdf_net = SDFNetwork(d_out=257, d_in=3, d_hidden=256, n_layers=8, skip_in=(4,), multires=6, bias=0.5, scale=1.0,
+                         geometric_init=True, weight_norm=True, device=dev)
+    col_net = RenderingNetwork(d_feature=256, mode='idr', d_in=9, d_out=3, d_hidden=256, n_layers=4, weight_norm=True,
+                               multires_view=4, squeeze_out=True, device=dev)
+    dev_net = SingleVarianceNetwork(0.5, device=dev)
+    r = NeuSRenderer(None, sdf_net, dev_net, col_net, 64, 64, 0, 4, 0.0)
+    out = {}
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+
+    for b in (512, 65536):
+        g = torch.Generator(device=dev).manual_seed(b)
+        rays_o = torch.randn((b, 3), generator=g, device=dev)
+        rays_o = 4.0 * rays_o / rays_o.norm(dim=1, keepdim=True)
+        rays_d = -rays_o / 4.0 + 0.05 * torch.randn((b, 3), generator=g, device=dev)
+        rays_d = rays_d / rays_d.norm(dim=1, keepdim=True)
+        near = torch.full((b, 1), 2.0, device=dev)
+        far = torch.full((b, 1), 6.0, device=dev)
+        bg = torch.ones((1, 3), device=dev)
+        ms = timed(lambda: r.render(rays_o, rays_d, near, far, 1.0, background_rgb=bg, cos_anneal_ratio=1.0),
+                   10 if b == 512 else 3)
+        # network evaluations per ray: SDF value on 64 + 3 x 16 samples, SDF jets + colour on 128 samples
+        flop = b * (112 * 2 * SDF_MACS + 128 * (4 * 2 * SDF_MACS + 2 * COLOR_MACS))
+        out['rays_%d' % b] = {'ms': ms, 'rays_per_s': b / (ms * 1e-3), 'samples_per_s': b * 128 / (ms * 1e-3),
+                              'tflops_executed': flop / (ms * 1e-3) / 1e12}
+    n = 1 << 20
+    pts = torch.rand((n, 3), device=dev) * 2 - 1
+    rows = col_net.alloc_rows(n, dev)
+    ms_jet = timed(lambda: sdf_net.forward_with_gradient(pts, feat_out=rows), 3)
+    ms_val = timed(lambda: sdf_net.sdf(pts), 3)
+    out['sdf_kernel_1M_points'] = {
+        'value_feature_gradient_ms': ms_jet, 'points_per_s': n / (ms_jet * 1e-3),
+        'tflops_executed': n * 4 * 2 * SDF_MACS / (ms_jet * 1e-3) / 1e12,
+        'tflops_algorithmic': n * 2 * (SDF_MACS + SDF_TRUNK_MACS) / (ms_jet * 1e-3) / 1e12,
+        'sdf_only_ms': ms_val, 'sdf_only_tflops': n * 2 * (SDF_TRUNK_MACS + 256) / (ms_val * 1e-3) / 1e12,
+        'note': 'jets = 4 MMA-tile rows per point (value + 3 tangents); algorithmic = forward + one reverse-mode pass '
+                'through the trunk (what autograd would execute); 3xTF32 tensor roofline 273 TFLOP/s'}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -560,6 +623,7 @@ def run_ours(args):
             'vq_assign': dict(vq, hbm_frac=vq['gbs'] / hbm_peak, bound='hbm', algorithmic_bytes_per_latent=1032),
             'train_step': train,
             'neus_scan': bench_neus_scan(dev, hbm_peak),
+            'neus_render': bench_neus_render(dev),
         }
         print(json.dumps(line))
     if world > 1:

@@ -45,7 +45,10 @@ typedef enum vqn_status {
   VQN_ERR_ZERO_NORM = 5      /* assert_greater on direction norms (shape.py:107-109,116-118)              */
 } vqn_status;
 
-typedef enum vqn_act { VQN_ACT_NONE = 0, VQN_ACT_RELU = 1, VQN_ACT_SIGMOID = 2 } vqn_act;
+typedef enum vqn_act {
+  VQN_ACT_NONE = 0, VQN_ACT_RELU = 1, VQN_ACT_SIGMOID = 2,
+  VQN_ACT_SOFTPLUS100 = 3 /* torch.nn.Softplus(beta=100), geo/NeuS-ours2/models/fields.py:72 (tensor-core modes only) */
+} vqn_act;
 
 /* arithmetic mode of the MLP kernels */
 typedef enum vqn_precision {
@@ -350,6 +353,27 @@ int vqn_neus_composite(vqn_ctx* ctx, const vqn_neus_composite_args* args, vqn_st
 int vqn_neus_mid_points(vqn_ctx* ctx, const float* rays_o, const float* rays_d, const float* z_vals,
                         int64_t n_rays, int n_samples, float sample_dist, float* pts, float* dirs,
                         vqn_stream stream);
+
+/* SDFNetwork.forward / .sdf / .gradient (geo/NeuS-ours2/models/fields.py:74-112) in ONE launch of the fused
+ * tensor-core MLP kernel.  `trunk` = lin0 .. lin{L-2} packed as one network [in_dim = 3 + 6*n_freqs, skip_at = the layer
+ * BEFORE the skip_in layer, activations VQN_ACT_SOFTPLUS100] with the effective weights: weight_norm folded
+ * (w = g v/|v|), Keras layout [in,out], and the 1/sqrt(2) of the skip concat (fields.py:82) folded into the skip_in
+ * layer.  The last Linear (d_hidden -> 1 + d_feature) is passed split: w_sdf[d_hidden] / b_sdf[1] = its output 0,
+ * `feat` = a one-layer network holding outputs 1.. [NULL when feat_out is NULL].  scale == 1 (every shipped conf).
+ *   sdf[n]  <- forward(x)[:, :1];  feat_out[n, feat_stride >= d_feature] <- forward(x)[:, 1:]  (optional)
+ *   grad_out[n,3] <- d sdf / d x (optional).  With grad_out the kernel propagates (value, d/dx, d/dy, d/dz) jets --
+ *   four rows of the 128-row MMA tile per point -- so autograd's second pass (fields.py:98-110) does not exist.
+ * precision: VQN_PREC_TF32X3 or VQN_PREC_BF16. */
+int vqn_sdf_forward(vqn_ctx* ctx, vqn_net* trunk, const float* w_sdf, const float* b_sdf, vqn_net* feat,
+                    int n_freqs, const float* pts, int64_t n, float* sdf, float* feat_out, int64_t feat_stride,
+                    float* grad_out, int precision, vqn_stream stream);
+
+/* RenderingNetwork input (fields.py:147-156, mode 'idr'): writes [points(3), embed(view_dirs)(3+6*multires_view),
+ * normals(3), zero pad] into columns [col_off, col_off + width) of rows[n, row_stride]; the feature vector is
+ * written in place by vqn_sdf_forward (feat_out = rows), so the 289-wide concat is never copied. */
+int vqn_neus_color_input(vqn_ctx* ctx, const float* pts, const float* dirs, const float* normals, int64_t n,
+                         int multires_view, float* rows, int64_t row_stride, int col_off, int width,
+                         vqn_stream stream);
 
 /* ---- measurement helper (not a reference interface) -------------------------------------------- */
 /* FP32-FMA peak of this GPU in TFLOP/s (mode 0: FFMA, mode 1: packed fma.rn.f32x2); synchronises. */

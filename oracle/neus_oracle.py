@@ -109,3 +109,123 @@ def composite(rays_o, rays_d, z_vals, sdf, gradients, sampled_color, inv_s, cos_
     return {'color': color, 'weights': weights, 'surf': surf, 'depth': depth, 'cdf': c.reshape(b, s),
             'inside_sphere': inside, 'mid_z_vals': mid_z, 'dists': dists, 'weight_sum': wsum,
             'weight_max': weights.max(-1, keepdims=True), 'gradient_error': gerr}
+
+
+# ---------------------------------------------------------------------------------------------
+# SDFNetwork / RenderingNetwork (geo/NeuS-ours2/models/fields.py:9-172, embedder.py:6-50), float64 restatement.
+# PINNED: tests/test_oracle_cpu.py compares these with tests/golden/neus_fields_ref.npz, recorded by
+# oracle/gen_golden_neus_fields.py from the reference's own modules (autograd gradient included).
+# ---------------------------------------------------------------------------------------------
+def make_neus_state(seed=0, d_hidden=256, n_layers=8, skip_in=(4,), multires=6, d_feature=256, bias=0.5,
+                    color_layers=4, multires_view=4):
+    """Random-init parameters under the reference's state_dict names (lin{l}.weight_g / .weight_v / .bias), drawn with
+    NumPy so that the golden generator (which loads them into the reference modules) and the tests build identical
+    networks without 3 MB of weights in the repository.  SDF net: the geometric initialisation of fields.py:45-61;
+    colour net: nn.Linear's default U(-1/sqrt(in), 1/sqrt(in)).  weight_g = |v| * U(0.9, 1.1) (weight_norm starts at
+    g = |v|; the factor makes the normalisation observable)."""
+    rng = np.random.RandomState(seed)
+    d0 = 3 + 6 * multires
+    dims = [d0] + [d_hidden] * n_layers + [1 + d_feature]
+    sdf = {}
+    for l in range(len(dims) - 1):
+        out_dim = dims[l + 1] - dims[0] if (l + 1) in skip_in else dims[l + 1]
+        if l == len(dims) - 2:
+            w = rng.normal(np.sqrt(np.pi) / np.sqrt(dims[l]), 1e-4, size=(out_dim, dims[l]))
+            b = np.full(out_dim, -bias)
+        elif l == 0:
+            w = np.zeros((out_dim, dims[l]))
+            w[:, :3] = rng.normal(0.0, np.sqrt(2) / np.sqrt(out_dim), size=(out_dim, 3))
+            b = np.zeros(out_dim)
+        elif l in skip_in:
+            w = rng.normal(0.0, np.sqrt(2) / np.sqrt(out_dim), size=(out_dim, dims[l]))
+            w[:, -(dims[0] - 3):] = 0.0
+            b = np.zeros(out_dim)
+        else:
+            w = rng.normal(0.0, np.sqrt(2) / np.sqrt(out_dim), size=(out_dim, dims[l]))
+            b = np.zeros(out_dim)
+        # the zeroed high-frequency columns would make the embedding a no-op: give them small weights so that the
+        # parity tests exercise every column
+        w = w + rng.normal(0.0, 0.02 / np.sqrt(out_dim), size=w.shape) * (w == 0.0)
+        g = np.linalg.norm(w, axis=1, keepdims=True) * rng.uniform(0.9, 1.1, size=(out_dim, 1))
+        sdf['lin%d.weight_v' % l] = w.astype(np.float32)
+        sdf['lin%d.weight_g' % l] = g.astype(np.float32)
+        sdf['lin%d.bias' % l] = (b + rng.normal(0.0, 0.001, size=b.shape) * (l < len(dims) - 2)).astype(np.float32)
+    cd = [9 + d_feature + 6 * multires_view] + [d_hidden] * color_layers + [3]
+    col = {}
+    for l in range(len(cd) - 1):
+        k = 1.0 / np.sqrt(cd[l])
+        w = rng.uniform(-k, k, size=(cd[l + 1], cd[l]))
+        col['lin%d.weight_v' % l] = w.astype(np.float32)
+        col['lin%d.weight_g' % l] = (np.linalg.norm(w, axis=1, keepdims=True)
+                                     * rng.uniform(0.9, 1.1, size=(cd[l + 1], 1))).astype(np.float32)
+        col['lin%d.bias' % l] = rng.uniform(-k, k, size=cd[l + 1]).astype(np.float32)
+    return {'sdf': sdf, 'color': col}
+
+
+def effective_weight(state, l):
+    """nn.utils.weight_norm (fields.py:63-64, dim=0): w = g * v / |v|, norm over the input axis of each output row."""
+    if 'lin%d.weight' % l in state:
+        return np.asarray(state['lin%d.weight' % l], np.float64)
+    v = np.asarray(state['lin%d.weight_v' % l], np.float64)
+    g = np.asarray(state['lin%d.weight_g' % l], np.float64)
+    return g * v / np.linalg.norm(v, axis=1, keepdims=True)
+
+
+def n_lin(state):
+    return len([k for k in state if k.endswith('.bias')])
+
+
+def embed_jac(x, multires):
+    """embedder.py:11-35: [x, sin(x f0), cos(x f0), ...], f_k = 2^k; also d embed / d x  [n, 3, dim]."""
+    x = np.asarray(x, np.float64)
+    n = x.shape[0]
+    cols, jac = [x], [np.broadcast_to(np.eye(3), (n, 3, 3))]
+    for k in range(multires):
+        f = 2.0 ** k
+        s, c = np.sin(x * f), np.cos(x * f)
+        cols += [s, c]
+        jac += [np.eye(3)[None] * (f * c)[:, None, :], np.eye(3)[None] * (-f * s)[:, None, :]]
+    return np.concatenate(cols, -1), np.concatenate(jac, -1)
+
+
+def _softplus100(x):
+    bt = 100.0 * x
+    return np.where(bt > 20.0, x, np.log1p(np.exp(np.minimum(bt, 20.0))) / 100.0)
+
+
+def sdf_forward(state, x, multires=6, skip_in=(4,), scale=1.0):
+    """SDFNetwork.forward + .gradient (fields.py:74-112): returns (out [n, 1 + d_feature], d sdf / d x [n, 3]).
+    The gradient is propagated forward (Jacobian-vector form), which equals the reference's autograd result."""
+    x = np.asarray(x, np.float64) * scale
+    e, de = embed_jac(x, multires)
+    de = de * scale
+    h, dh = e, de
+    L = n_lin(state)
+    for l in range(L):
+        if l in skip_in:
+            h = np.concatenate([h, e], -1) / np.sqrt(2)
+            dh = np.concatenate([dh, de], -1) / np.sqrt(2)
+        w = effective_weight(state, l)
+        b = np.asarray(state['lin%d.bias' % l], np.float64)
+        pre = h @ w.T + b
+        dpre = dh @ w.T
+        if l < L - 1:
+            h = _softplus100(pre)
+            dh = dpre * _sigmoid(100.0 * pre)[:, None, :]
+        else:
+            h, dh = pre, dpre
+    out = np.concatenate([h[:, :1] / scale, h[:, 1:]], -1)
+    return out, dh[:, :, 0] / scale
+
+
+def color_forward(state, points, normals, view_dirs, feature_vectors, multires_view=4, squeeze_out=True):
+    """RenderingNetwork.forward, mode 'idr' (fields.py:147-172)."""
+    v, _ = embed_jac(view_dirs, multires_view)
+    h = np.concatenate([np.asarray(points, np.float64), v, np.asarray(normals, np.float64),
+                        np.asarray(feature_vectors, np.float64)], -1)
+    L = n_lin(state)
+    for l in range(L):
+        h = h @ effective_weight(state, l).T + np.asarray(state['lin%d.bias' % l], np.float64)
+        if l < L - 1:
+            h = np.maximum(h, 0.0)
+    return _sigmoid(h) if squeeze_out else h

@@ -153,3 +153,22 @@ def test_decomp_oracle_matches_committed_vectors():
         scene.codebook = c['update'].numpy().astype(np.float32)
         for k in ('rgb_linear', 'vq_rgb_linear', 'embed_ind', 'update', 'vq_loss', 'perplexity'):
             np.testing.assert_allclose(c[k].numpy(), g['call%d_%s' % (step, k)], rtol=1e-9, atol=1e-12)
+
+
+def test_neus_networks_match_reference():
+    """oracle SDFNetwork / RenderingNetwork restatement vs the reference's own modules (autograd gradient included):
+    tests/golden/neus_fields_ref.npz, recorded by oracle/gen_golden_neus_fields.py (float32 torch on CPU)."""
+    g = np.load(os.path.join(GOLD, 'neus_fields_ref.npz'))
+    st = NO.make_neus_state(0)
+    out, grad = NO.sdf_forward(st['sdf'], g['pts'])
+    np.testing.assert_allclose(out[:, 0], g['sdf'], rtol=0, atol=3e-6)
+    np.testing.assert_allclose(out[:96, 1:], g['feat'], rtol=0, atol=3e-6)
+    np.testing.assert_allclose(grad, g['grad'], rtol=0, atol=2e-5)
+    col = NO.color_forward(st['color'], g['pts'], g['grad'], g['dirs'], out[:, 1:])
+    np.testing.assert_allclose(col, g['color'], rtol=0, atol=3e-6)
+    # the forward-mode gradient is the derivative of the oracle's own sdf (central differences in float64)
+    x = g['pts'][:16].astype(np.float64)
+    for k in range(3):
+        e = np.zeros(3); e[k] = 1e-6
+        fd = (NO.sdf_forward(st['sdf'], x + e)[0][:, 0] - NO.sdf_forward(st['sdf'], x - e)[0][:, 0]) / 2e-6
+        np.testing.assert_allclose(grad[:16, k], fd, rtol=0, atol=1e-6)

@@ -14,8 +14,9 @@ LIB_PATH = os.path.join(HERE, 'libvqnerf_b200.so')
 
 VQN_MAX_LAYERS = 8
 PREC_FP32, PREC_BF16, PREC_TF32X3 = 0, 1, 2
-ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
-_ACT_BY_NAME = {None: ACT_NONE, 'none': ACT_NONE, 'linear': ACT_NONE, 'relu': ACT_RELU, 'sigmoid': ACT_SIGMOID}
+ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SOFTPLUS100 = 0, 1, 2, 3
+_ACT_BY_NAME = {None: ACT_NONE, 'none': ACT_NONE, 'linear': ACT_NONE, 'relu': ACT_RELU, 'sigmoid': ACT_SIGMOID,
+                'softplus100': ACT_SOFTPLUS100}
 _PREC_BY_NAME = {'fp32': PREC_FP32, 'bf16': PREC_BF16, 'tf32x3': PREC_TF32X3}
 
 (OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NONFINITE, ERR_UNSUPPORTED, ERR_ZERO_NORM) = range(6)
@@ -95,6 +96,8 @@ SIGNATURES = {
     'vqn_neus_cat_z_vals': (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _P, _P, _P]),
     'vqn_neus_composite': (_I, [_P, C.POINTER(NeusCompositeArgs), _P]),
     'vqn_neus_mid_points': (_I, [_P, _P, _P, _P, _L, _I, _F, _P, _P, _P]),
+    'vqn_sdf_forward': (_I, [_P, _P, _P, _P, _P, _I, _P, _L, _P, _P, _L, _P, _I, _P]),
+    'vqn_neus_color_input': (_I, [_P, _P, _P, _P, _L, _I, _P, _L, _I, _I, _P]),
     'vqn_dense_forward': (_I, [_P, _P, _L, _P, _P, _P, _L, _L, _I, _I, _I, _F, _F, _P]),
     'vqn_dense_backward_data': (_I, [_P, _P, _L, _P, _P, _L, _P, _L, _I, _I, _L, _I, _I, _P]),
     'vqn_dense_backward_weights': (_I, [_P, _P, _L, _P, _L, _P, _P, _L, _I, _I, _P]),

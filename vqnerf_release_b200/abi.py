@@ -423,6 +423,46 @@ def neus_composite(rays_o, rays_d, z_vals, sdf, gradients, sampled_color, inv_s,
     return o
 
 
+def sdf_forward(trunk: PackedNet, w_sdf: torch.Tensor, b_sdf: torch.Tensor, feat: Optional[PackedNet], n_freqs: int,
+                pts: torch.Tensor, want_grad: bool = False, feat_out: Optional[torch.Tensor] = None,
+                precision='tf32x3'):
+    """vqn_sdf_forward (fields.py:74-112).  feat_out: None (sdf only) or a [n, stride >= d_feature] row buffer that
+    receives the feature vector in its first columns.  Returns (sdf [n,1], grad [n,3] or None)."""
+    pts = _f(pts)
+    n = pts.shape[0]
+    if pts.dim() != 2 or pts.shape[1] != 3:
+        raise ValueError('expected points [n,3], got %s' % (tuple(pts.shape),))
+    sdf = torch.empty((n, 1), dtype=F32, device=pts.device)
+    grad = torch.empty((n, 3), dtype=F32, device=pts.device) if want_grad else None
+    if n == 0:
+        L.precision_code(precision)
+        return sdf, grad
+    stride = 0
+    if feat_out is not None:
+        if feat is None or feat_out.dim() != 2 or feat_out.shape[0] != n or feat_out.dtype != F32 \
+                or feat_out.stride(1) != 1 or feat_out.stride(0) < feat.out_dim:
+            raise ValueError('feat_out must be a float32 [n, >= d_feature] row buffer')
+        stride = feat_out.stride(0)
+    c = _ctx(pts)
+    L.check(c.lib.vqn_sdf_forward(c.handle, trunk.handle, L.ptr(w_sdf, F32), L.ptr(b_sdf, F32),
+                                  feat.handle if feat_out is not None else None, n_freqs, L.ptr(pts), n, L.ptr(sdf),
+                                  C.c_void_p(feat_out.data_ptr()) if feat_out is not None else None, stride,
+                                  L.ptr(grad), L.precision_code(precision), L.stream_ptr(pts.device)))
+    return sdf, grad
+
+
+def neus_color_input(pts, dirs, normals, multires_view: int, rows: torch.Tensor, col_off: int, width: int):
+    """vqn_neus_color_input: columns [col_off, col_off + width) of rows <- [pts, embed(dirs), normals, 0...]."""
+    pts, dirs, normals = map(_f, (pts, dirs, normals))
+    n = pts.shape[0]
+    if rows.dtype != F32 or rows.dim() != 2 or rows.shape[0] != n or rows.stride(1) != 1:
+        raise ValueError('rows must be a float32 [n, stride] buffer')
+    c = _ctx(pts)
+    L.check(c.lib.vqn_neus_color_input(c.handle, L.ptr(pts), L.ptr(dirs), L.ptr(normals), n, int(multires_view),
+                                       C.c_void_p(rows.data_ptr()), rows.stride(0), int(col_off), int(width),
+                                       L.stream_ptr(pts.device)))
+
+
 # ---- tensor-core primitive self-test ------------------------------------------------------------
 def tc_selftest(a: torch.Tensor, b: torch.Tensor, mode: int) -> torch.Tensor:
     """d[128,n] = a[128,k] @ b[n,k]^T on tcgen05 (mode 0 tf32, 1 bf16, 2 3xTF32)."""

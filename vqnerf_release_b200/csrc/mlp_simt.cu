@@ -126,21 +126,23 @@ static int net_pack(vqn_net* net, cudaStream_t s) {
 extern "C" int vqn_net_create(vqn_ctx* ctx, const vqn_net_desc* desc, vqn_net** out, vqn_stream stream) {
   VQN_CHECK_ARG(ctx && desc && out, "net_create: null");
   VQN_CHECK_ARG(desc->n_layers >= 1 && desc->n_layers <= VQN_MAX_LAYERS, "net_create: 1..8 layers");
-  VQN_CHECK_ARG(desc->in_dim >= 1 && desc->in_dim <= 256, "net_create: in_dim must be <= 256");
+  VQN_CHECK_ARG(desc->in_dim >= 1 && desc->in_dim <= 512, "net_create: in_dim must be <= 512");
   VQN_CHECK_ARG(desc->skip_at < desc->n_layers - 1, "net_create: skip_at must precede the last layer");
+  // The FFMA kernel (VQN_PREC_FP32) handles the decomposition-stage shapes; anything else (NeuS: softplus, a 217-wide
+  // layer, the 292-wide colour input) runs in the tensor-core modes only.
+  bool simt_ok = desc->in_dim <= 256;
   for (int i = 0; i < desc->n_layers; ++i) {
     VQN_CHECK_ARG(desc->w[i] && desc->b[i], "net_create: null weight pointer");
     VQN_CHECK_ARG(desc->widths[i] >= 1 && desc->widths[i] <= 256, "net_create: widths must be <= 256");
-    VQN_CHECK_ARG(desc->acts[i] >= 0 && desc->acts[i] <= 2, "net_create: bad activation");
-    if (i < desc->n_layers - 1)
-      VQN_CHECK_ARG(desc->widths[i] % 32 == 0, "net_create: hidden widths must be multiples of 32");
+    VQN_CHECK_ARG(desc->acts[i] >= 0 && desc->acts[i] <= 3, "net_create: bad activation");
+    if (desc->acts[i] == VQN_ACT_SOFTPLUS100) simt_ok = false;
+    if (i < desc->n_layers - 1 && desc->widths[i] % 32 != 0) simt_ok = false;
   }
-  if (desc->skip_at >= 0)
-    VQN_CHECK_ARG(round_up(desc->in_dim, MLP_KC) + desc->widths[desc->skip_at] <= MLP_Q_ROWS,
-                  "net_create: skip concat wider than 384");
+  if (desc->skip_at >= 0 && round_up(desc->in_dim, MLP_KC) + desc->widths[desc->skip_at] > MLP_Q_ROWS) simt_ok = false;
   vqn_net* net = new vqn_net();
   net->ctx = ctx;
   net->desc = *desc;
+  net->simt_ok = simt_ok;
   net->tc_pack[0] = nullptr; net->tc_pack[1] = nullptr;
   net_layout(net);
   cudaStream_t s = vqn_cs(stream);
@@ -411,6 +413,7 @@ static bool build_net_steps(ProgBuilder& B, const vqn_net* net, int out_slot_las
   const vqn_net_desc& d = net->desc;
   const int L = d.n_layers;
   const int skip = d.skip_at;
+  if (!net->simt_ok) return false;     // tensor-core-only network (see vqn_net_create)
   // a net with a skip needs its input x resident in Q at offset 0 (x stays there until the concat)
   if (skip >= 0 && !(B.cur_buf == 1 && B.cur_off == 0)) {
     MlpStep* c = B.add(); if (!c) return false;

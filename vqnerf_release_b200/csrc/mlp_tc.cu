@@ -70,6 +70,11 @@ struct TcProgram {
   long long n;
   float* outs[4];
   int out_stride[4];
+  // Jet mode (vqn_sdf_forward with grad_out): a tile is 32 points x 4 rows -- row 4p is the value of point p, rows
+  // 4p+1..4p+3 its derivatives with respect to x, y, z; every layer is linear in the tangent rows and the activation
+  // multiplies them by act'(pre-activation of the value row), fetched from the neighbouring TMEM lane by a shuffle.
+  int jet;
+  float* jet_grad;         // [n,3]: tangent rows of the narrow tail (d sdf / d x)
   int* nonfinite;
   long long* trace;        // diagnostic (vqn_debug_tc_trace): clock64 stamps of CTA 0's MMA thread, 4 per layer
   TcLayer layers[TC_MAX_LAYERS];
@@ -149,12 +154,6 @@ static int tc_pack_get(vqn_net* net, int precision, cudaStream_t s, TcPack** out
   if (net->tc_pack[p]) { *out = net->tc_pack[p]; return VQN_OK; }
   const vqn_net_desc& d = net->desc;
   const int E = p == 1 ? 64 : 32;
-  for (int i = 0; i + 1 < d.n_layers; ++i)
-    if (d.widths[i] % 64 != 0) {
-      vqn_set_error("tensor-core MLP modes need hidden widths that are multiples of 64 (layer %d has %d)", i,
-                    d.widths[i]);
-      return VQN_ERR_UNSUPPORTED;
-    }
   TcPack* tp = new TcPack();
   memset(tp, 0, sizeof(*tp));
   tp->n_layers = d.n_layers;
@@ -162,7 +161,9 @@ static int tc_pack_get(vqn_net* net, int precision, cudaStream_t s, TcPack** out
     bool after_skip = (d.skip_at >= 0 && i == d.skip_at + 1);
     int seg0_rows = (i == 0) ? d.in_dim : d.widths[i - 1];
     int seg1_rows = after_skip ? d.in_dim : 0;
-    tp->Npad[i] = vqn_round_up(d.widths[i], 16);
+    // hidden layers are drained in whole K-chunks of the next layer: pad their accumulators to a chunk multiple (the
+    // pad columns have zero weights and meet zero-filled weight rows of the next layer, e.g. NeuS' 217-wide lin3)
+    tp->Npad[i] = vqn_round_up(d.widths[i], i + 1 < d.n_layers ? E : 16);
     tp->n_chunks[i] = vqn_round_up(seg0_rows, E) / E + vqn_round_up(seg1_rows, E) / E;
     size_t chunk_bytes = (size_t)tp->Npad[i] * 128 * (p == 1 ? 1 : 2);
     VQN_CUDA(cudaMalloc(&tp->w[i], chunk_bytes * tp->n_chunks[i]));
@@ -212,6 +213,40 @@ struct TcCfg {
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
+// torch.nn.Softplus(beta=100) (fields.py:72): log1p(exp(100 x)) / 100 (x itself beyond the threshold 100 x > 20, where
+// the formula below differs by < 2.1e-11).  lg2.approx is accurate to 2^-22 ABSOLUTE on (0.5, 2): 1.7e-9 after the /100.
+__device__ __forceinline__ float softplus100(float t) {
+  const float bt = 100.0f * t;
+  const float e = __expf(-fabsf(bt));
+  return (fmaxf(bt, 0.0f) + __logf(1.0f + e)) * 0.01f;
+}
+
+// Activation of a jet tile: lane 4p holds the value row of point p, lanes 4p+1..3 its tangent rows.
+//   value row:   act(v + b)          tangent rows:   v * act'(pre-activation of the value row)
+__device__ __forceinline__ void bias_act32_jet(float (&v)[16], const float* __restrict__ bias_s, int act, int lane) {
+  const int src = lane & ~3;
+  const bool is_val = (lane & 3) == 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float pre = __shfl_sync(0xffffffffu, v[j], src) + bias_s[j];
+    float val, der;
+    if (act == VQN_ACT_SOFTPLUS100) {
+      const float bt = 100.0f * pre;
+      const float e = __expf(-fabsf(bt));
+      const float s = __fdividef(1.0f, 1.0f + e);
+      val = (fmaxf(bt, 0.0f) + __logf(1.0f + e)) * 0.01f;
+      der = bt >= 0.0f ? s : e * s;
+    } else if (act == VQN_ACT_RELU) {
+      val = fmaxf(pre, 0.0f); der = pre > 0.0f ? 1.0f : 0.0f;
+    } else if (act == VQN_ACT_SIGMOID) {
+      val = __fdividef(1.0f, 1.0f + __expf(-pre)); der = val * (1.0f - val);
+    } else {
+      val = pre; der = 1.0f;
+    }
+    v[j] = is_val ? val : v[j] * der;
+  }
+}
+
 template <int ACT>
 __device__ __forceinline__ void bias_act32(float (&v)[16], const float* __restrict__ bias_s) {
 #pragma unroll
@@ -220,13 +255,19 @@ __device__ __forceinline__ void bias_act32(float (&v)[16], const float* __restri
     float t0 = v[j] + b4.x, t1 = v[j + 1] + b4.y, t2 = v[j + 2] + b4.z, t3 = v[j + 3] + b4.w;
     if (ACT == VQN_ACT_RELU) { t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f); t2 = fmaxf(t2, 0.f); t3 = fmaxf(t3, 0.f); }
     if (ACT == VQN_ACT_SIGMOID) { t0 = fast_sigmoid(t0); t1 = fast_sigmoid(t1); t2 = fast_sigmoid(t2); t3 = fast_sigmoid(t3); }
+    if (ACT == VQN_ACT_SOFTPLUS100) { t0 = softplus100(t0); t1 = softplus100(t1); t2 = softplus100(t2); t3 = softplus100(t3); }
     v[j] = t0; v[j + 1] = t1; v[j + 2] = t2; v[j + 3] = t3;
   }
 }
 __device__ __forceinline__ void bias_act32_dyn(float (&v)[16], const float* __restrict__ bias_s, int act) {
   if (act == VQN_ACT_RELU) bias_act32<VQN_ACT_RELU>(v, bias_s);
   else if (act == VQN_ACT_SIGMOID) bias_act32<VQN_ACT_SIGMOID>(v, bias_s);
+  else if (act == VQN_ACT_SOFTPLUS100) bias_act32<VQN_ACT_SOFTPLUS100>(v, bias_s);
   else bias_act32<VQN_ACT_NONE>(v, bias_s);
+}
+__device__ __forceinline__ float act1_dyn(float t, int act) {
+  return act == VQN_ACT_RELU ? fmaxf(t, 0.f)
+       : act == VQN_ACT_SIGMOID ? fast_sigmoid(t) : act == VQN_ACT_SOFTPLUS100 ? softplus100(t) : t;
 }
 
 // store 16 consecutive K values (columns j0 .. j0+15 of the chunk, j0 % 16 == 0) of row r into the chunk slot
@@ -289,12 +330,15 @@ __device__ __forceinline__ void store_chunk1(uint8_t* slot, int r, int col, floa
 
 // Embedder.__call__ (embedder.py:35-47) for the chunk covering embedding columns [col0, col0 + E):
 // [x, sin(x f0), cos(x f0), sin(x f1), ...], f_k = 2^k; written straight into the swizzled slot.
+// jc = 0: the embedding itself; jc = 1..3 (tangent rows of a jet tile): its derivative with respect to x[jc-1], i.e.
+// [e_m, f cos(x_m f) e_m, -f sin(x_m f) e_m, ...] with m = jc - 1.
 template <bool BF16>
-__device__ __forceinline__ void embed_chunk(uint8_t* slot, int r, const float (&x)[3], int col0, int n_freqs) {
+__device__ __forceinline__ void embed_chunk(uint8_t* slot, int r, const float (&x)[3], int col0, int n_freqs, int jc) {
   constexpr int E = BF16 ? 64 : 32;
   const int d = 3 + 6 * n_freqs;
   if (col0 == 0) {
-    store_chunk1<BF16>(slot, r, 0, x[0]); store_chunk1<BF16>(slot, r, 1, x[1]); store_chunk1<BF16>(slot, r, 2, x[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) store_chunk1<BF16>(slot, r, k, jc == 0 ? x[k] : (jc - 1 == k ? 1.0f : 0.0f));
   }
   int f_lo = col0 <= 3 ? 0 : (col0 - 3 - 5 + 5) / 6;       // first frequency with a column >= col0
   if (f_lo > 0 && 3 + 6 * (f_lo - 1) + 5 >= col0) f_lo -= 1;
@@ -320,10 +364,13 @@ __device__ __forceinline__ void embed_chunk(uint8_t* slot, int r, const float (&
       have_prev = true;
     }
     const int base = 3 + 6 * f - col0;                       // chunk-relative column of sin(x0 f)
+    const float fr = exp2f((float)f);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      if (base + k >= 0 && base + k < E) store_chunk1<BF16>(slot, r, base + k, sn[k]);
-      if (base + 3 + k >= 0 && base + 3 + k < E) store_chunk1<BF16>(slot, r, base + 3 + k, cs[k]);
+      const float vs = jc == 0 ? sn[k] : (jc - 1 == k ? fr * cs[k] : 0.0f);
+      const float vc = jc == 0 ? cs[k] : (jc - 1 == k ? -fr * sn[k] : 0.0f);
+      if (base + k >= 0 && base + k < E) store_chunk1<BF16>(slot, r, base + k, vs);
+      if (base + 3 + k >= 0 && base + 3 + k < E) store_chunk1<BF16>(slot, r, base + 3 + k, vc);
     }
   }
   for (int col = (d > col0 ? d : col0); col < col0 + E; ++col) store_chunk1<BF16>(slot, r, col - col0, 0.f);
@@ -332,7 +379,7 @@ __device__ __forceinline__ void embed_chunk(uint8_t* slot, int r, const float (&
 // named barrier of one 256-thread epilogue group (ids 1, 2; id 0 is __syncthreads)
 __device__ __forceinline__ void group_bar(int grp) { asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory"); }
 
-template <bool BF16>
+template <bool BF16, bool JET>
 __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcProgram pg) {
   using C = TcCfg<BF16>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -376,7 +423,9 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
 
   long long n = pg.n_dev ? (long long)*pg.n_dev : pg.n;
   if (n > pg.n) n = pg.n;
-  const long long n_tiles = (n + TC_M - 1) / TC_M;
+  constexpr bool jet = JET;                              // compile-time: the decomposition-stage kernels carry no jet code
+  constexpr int tile_pts = JET ? TC_M / 4 : TC_M;        // points per tile
+  const long long n_tiles = (n + tile_pts - 1) / tile_pts;
   const int L = pg.n_layers;
 
   if (warp < 8 * C::G) {
@@ -394,8 +443,10 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
     int ptrace_n = 0;
     float sp0 = 0.f, sp1 = 0.f, sp2 = 0.f, sp3 = 0.f;   // folded-skip partial sums of this thread (see TcLayer::skip_w)
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const long long pi = tile * TC_M + r;              // compact point index
+      const long long pi = tile * tile_pts + (jet ? (r >> 2) : r);   // compact point index
+      const int jc = jet ? (r & 3) : 0;                  // jet component of this row (0 = value)
       const bool valid = pi < n;
+      const bool valid_out = valid && jc == 0;           // rows whose network outputs are stored
       float x[3] = {0.f, 0.f, 0.f};
       if (pg.pts && valid) {
         long long row = pg.row_idx ? (long long)pg.row_idx[pi] : pi;
@@ -432,7 +483,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
 #endif
             if (st == SRC_EMBED) {
               tc::mbar_wait(&a_empty[slot], ((ga / C::SA) & 1) ^ 1);
-              if (half == 0) embed_chunk<BF16>(dst, r, x, sc * C::E, pg.n_freqs);
+              if (half == 0) embed_chunk<BF16>(dst, r, x, sc * C::E, pg.n_freqs, jc);
             } else if (!BF16 && st == SRC_GLOBAL) {
               // Latent chunk [128 rows x 32 columns] of the row-major source: loaded COALESCED (a warp reads 4 rows x
               // 128 B per instruction; a thread-per-row load touches 32 lines per instruction and costs 8x the L1/smem
@@ -481,7 +532,8 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                 const int col0 = sc * C::E + 32 * h + 16 * half;   // first source column of this thread's 16-wide piece
                 if (st == SRC_DRAIN) {
                   tc::tmem_ld16(pacc + (uint32_t)col0, v);
-                  bias_act32_dyn(v, pbias + col0, pact);
+                  if (jet) bias_act32_jet(v, pbias + col0, pact, lane);
+                  else bias_act32_dyn(v, pbias + col0, pact);
                 } else {                                  // SRC_GLOBAL (bf16 mode): this thread's own latent row
                   if (valid && col0 < pg.g_dim) {
                     const float4* src = reinterpret_cast<const float4*>(pg.gsrc + pi * pg.g_dim + col0);
@@ -534,7 +586,8 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
             if (c16 < ly.N) {
               float v[16];
               tc::tmem_ld16(lane_addr + (uint32_t)(ly.tmem_col + c16), v);
-              bias_act32_dyn(v, lb + c16, ly.act);
+              if (jet) bias_act32_jet(v, lb + c16, ly.act, lane);
+              else bias_act32_dyn(v, lb + c16, ly.act);
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const float4 w4 = tw[c16 + j];
@@ -557,14 +610,19 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
             float* go = pg.outs[ly.tail_out_slot];
             const int gs = pg.out_stride[ly.tail_out_slot];
             bool bad = false;
+            if (jc != 0) {
+              // tangent row of a jet tile (linear tail, tail_n == 1): d out / d x[jc-1]
+              bad = !isfinite(o[0]);
+              if (valid && pg.jet_grad) pg.jet_grad[pi * 3 + (jc - 1)] = o[0];
+            } else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (q < ly.tail_n) {
-                float t = o[q] + ly.tail_b[q];
-                t = ly.tail_act == VQN_ACT_RELU ? fmaxf(t, 0.f) : (ly.tail_act == VQN_ACT_SIGMOID ? fast_sigmoid(t) : t);
-                t = t * ly.tail_scale + ly.tail_bias;
-                bad |= !isfinite(t);
-                if (valid) go[pi * gs + q] = t;
+              for (int q = 0; q < 4; ++q) {
+                if (q < ly.tail_n) {
+                  float t = act1_dyn(o[q] + ly.tail_b[q], ly.tail_act);
+                  t = t * ly.tail_scale + ly.tail_bias;
+                  bad |= !isfinite(t);
+                  if (valid && go) go[pi * gs + q] = t;
+                }
               }
             }
             if (valid && bad) atomicOr(pg.nonfinite, 1);
@@ -591,8 +649,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                   float b = (c16 + j < ly.Npad) ? lb[c16 + j] : 0.f;
-                  float t = v[j] + b;
-                  v[j] = ly.act == VQN_ACT_RELU ? fmaxf(t, 0.f) : (ly.act == VQN_ACT_SIGMOID ? fast_sigmoid(t) : t);
+                  v[j] = act1_dyn(v[j] + b, ly.act);
                 }
               }
               bool bad = false;
@@ -601,7 +658,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                 v[j] = v[j] * ly.post_scale + ly.post_bias;
                 bad |= (c16 + j < ly.N) && !isfinite(v[j]);
               }
-              if (valid && bad) atomicOr(pg.nonfinite, 1);
+              if (valid_out && bad) atomicOr(pg.nonfinite, 1);
               if (wide) {
                 // stage the 32-column block in the group's own (free) A slot, swizzled, then store it coalesced:
                 // a warp writes 4 rows x 128 B per instruction instead of 16 B into each of 32 rows
@@ -610,7 +667,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                 for (int q = 0; q < 4; ++q)
                   *reinterpret_cast<float4*>(stage + r * 128 + (((4 * half + q) ^ (r & 7)) << 4)) =
                       make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-              } else if (valid) {
+              } else if (valid_out) {
                 if (c16 + 16 <= ly.N && (gs & 3) == 0) {
                   float4* o = reinterpret_cast<float4*>(go + pi * gs + c16);
 #pragma unroll
@@ -628,9 +685,9 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int f = tg + 256 * i, rr = f >> 3, ch = f & 7;
-                const long long prow = tile * TC_M + rr;
-                if (prow < n)
-                  *reinterpret_cast<float4*>(go + prow * gs + cb * 32 + 4 * ch) =
+                const long long prow = tile * tile_pts + (jet ? (rr >> 2) : rr);
+                if (prow < n && (!jet || (rr & 3) == 0))
+                  *reinterpret_cast<float4*>(go + (size_t)prow * gs + cb * 32 + 4 * ch) =
                       *reinterpret_cast<const float4*>(stage + rr * 128 + ((ch ^ (rr & 7)) << 4));
               }
               group_bar(grp);
@@ -807,17 +864,23 @@ static int tc_launch(vqn_ctx* ctx, TcProgram& pg, int precision, cudaStream_t s)
   }
   if (boff > TC_BIAS_FLOATS) { vqn_set_error("tensor-core MLP: bias table exceeds %d floats", TC_BIAS_FLOATS); return VQN_ERR_UNSUPPORTED; }
   if (pg.pts && 3 + 6 * pg.n_freqs > 64) { vqn_set_error("tensor-core MLP: embedding wider than 64"); return VQN_ERR_UNSUPPORTED; }
-  long long tiles = (pg.n + TC_M - 1) / TC_M;
-  int blocks = (int)(tiles < (long long)ctx->sm_count ? tiles : (long long)ctx->sm_count);
-  if (precision == VQN_PREC_BF16) {
-    size_t smem = TcCfg<true>::SMEM;
-    VQN_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_tc_kernel<true><<<blocks, TcCfg<true>::THREADS, smem, s>>>(pg);
-  } else {
-    size_t smem = TcCfg<false>::SMEM;
-    VQN_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_tc_kernel<false><<<blocks, TcCfg<false>::THREADS, smem, s>>>(pg);
+  if (pg.jet) {
+    for (int l = 0; l < pg.n_layers; ++l)
+      for (int sg = 0; sg < pg.layers[l].nseg; ++sg)
+        if (pg.layers[l].seg_type[sg] == SRC_GLOBAL) { vqn_set_error("tensor-core MLP: jet mode has no GLOBAL source"); return VQN_ERR_UNSUPPORTED; }
   }
+  const int tile_pts = pg.jet ? TC_M / 4 : TC_M;
+  long long tiles = (pg.n + tile_pts - 1) / tile_pts;
+  int blocks = (int)(tiles < (long long)ctx->sm_count ? tiles : (long long)ctx->sm_count);
+#define TC_LAUNCH(BF, JT)                                                                                              \
+  do {                                                                                                                 \
+    size_t smem = TcCfg<BF>::SMEM;                                                                                     \
+    VQN_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<BF, JT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    mlp_tc_kernel<BF, JT><<<blocks, TcCfg<BF>::THREADS, smem, s>>>(pg);                                                \
+  } while (0)
+  if (precision == VQN_PREC_BF16) { if (pg.jet) TC_LAUNCH(true, true); else TC_LAUNCH(true, false); }
+  else { if (pg.jet) TC_LAUNCH(false, true); else TC_LAUNCH(false, false); }
+#undef TC_LAUNCH
   VQN_LAUNCHED(ctx);
   return VQN_OK;
 }
@@ -888,4 +951,37 @@ int vqn_tc_mlp_main(vqn_ctx* ctx, vqn_net* fe, vqn_net* bn, vqn_net* diff, vqn_n
   int rc = vqn_tc_pred_enc_at(ctx, fe, bn, n_freqs, pts, row_idx, n_dev, n, z_out, precision, s);
   if (rc != VQN_OK) return rc;
   return vqn_tc_pred_heads(ctx, diff, spec, rough, z_out, n_dev, n, slope, bias, d, sp, r, precision, s);
+}
+
+// SDFNetwork (geo/NeuS-ours2/models/fields.py:74-112): trunk (lin0 .. lin{L-2}, softplus) -> narrow tail = output 0 (sdf,
+// on the CUDA cores while the last hidden accumulator is drained) [-> feature layer = outputs 1.. (one more MMA layer)].
+// With grad_out the tile carries (value, d/dx, d/dy, d/dz) jets and the tail's tangent rows are the SDF gradient.
+extern "C" int vqn_sdf_forward(vqn_ctx* ctx, vqn_net* trunk, const float* w_sdf, const float* b_sdf, vqn_net* feat,
+                               int n_freqs, const float* pts, int64_t n, float* sdf, float* feat_out,
+                               int64_t feat_stride, float* grad_out, int precision, vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && trunk && w_sdf && b_sdf && pts && sdf && n >= 0, "sdf_forward: null argument");
+  VQN_CHECK_ARG(precision == VQN_PREC_TF32X3 || precision == VQN_PREC_BF16,
+                "sdf_forward: precision must be tf32x3 or bf16 (tensor-core kernel)");
+  VQN_CHECK_ARG(trunk->in_dim == 3 + 6 * n_freqs, "sdf_forward: trunk in_dim != 3 + 6*n_freqs");
+  VQN_CHECK_ARG(!feat_out || (feat && feat->n_layers == 1 && feat->in_dim == vqn_net_out_dim(trunk) &&
+                              feat_stride >= vqn_net_out_dim(feat) && feat_stride < (1 << 30)),
+                "sdf_forward: feature layer / feat_stride mismatch");
+  if (n == 0) return VQN_OK;
+  cudaStream_t s = vqn_cs(stream);
+  TcPack *t0 = nullptr, *t1 = nullptr;
+  int rc = tc_pack_get(trunk, precision, s, &t0);
+  if (rc != VQN_OK) return rc;
+  if (feat_out) { rc = tc_pack_get(feat, precision, s, &t1); if (rc != VQN_OK) return rc; }
+  TcBuilder B(precision);
+  B.pg.pts = pts; B.pg.n = n; B.pg.n_freqs = n_freqs;
+  B.pg.jet = grad_out ? 1 : 0; B.pg.jet_grad = grad_out;
+  B.pg.outs[0] = feat_out; B.pg.out_stride[0] = (int)feat_stride;
+  B.pg.outs[1] = sdf; B.pg.out_stride[1] = 1;
+  if (!tc_append_net(B, trunk, t0, SRC_EMBED, -1, 1.f, 0.f)) TC_UNSUPPORTED("sdf_forward: trunk does not fit the tensor-core kernel");
+  TcLayer& last = B.pg.layers[B.pg.n_layers - 1];
+  last.tail_w = w_sdf; last.tail_b = b_sdf; last.tail_n = 1; last.tail_act = VQN_ACT_NONE; last.tail_out_slot = 1;
+  last.tail_add_skip = 0; last.tail_scale = 1.f; last.tail_bias = 0.f;
+  if (feat_out && !tc_append_net(B, feat, t1, SRC_DRAIN, 0, 1.f, 0.f))
+    TC_UNSUPPORTED("sdf_forward: feature layer does not fit the tensor-core kernel");
+  return tc_launch(ctx, B.pg, precision, s);
 }

@@ -13,6 +13,7 @@ struct vqn_net {
   int K[VQN_MAX_LAYERS], N[VQN_MAX_LAYERS], Npad[VQN_MAX_LAYERS];
   float* packed_w[VQN_MAX_LAYERS];
   float* packed_b[VQN_MAX_LAYERS];
+  bool simt_ok;            // false: only the tensor-core modes can run this network (NeuS widths / softplus)
   TcPack* tc_pack[2];      // [0] = tf32 hi/lo images, [1] = bf16 images; built lazily on first use
 };
 

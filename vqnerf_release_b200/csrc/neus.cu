@@ -351,3 +351,46 @@ extern "C" int vqn_neus_composite(vqn_ctx* ctx, const vqn_neus_composite_args* a
   VQN_LAUNCHED(ctx);
   return VQN_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// RenderingNetwork input columns (fields.py:147-156, mode 'idr'; embedder.py: [x, sin(x f), cos(x f), ...], f = 2^k)
+// one thread per (point, column): coalesced 4-byte stores into the strided row buffer
+// ---------------------------------------------------------------------------------------------
+__global__ void neus_color_input_kernel(const float* __restrict__ pts, const float* __restrict__ dirs,
+                                        const float* __restrict__ normals, long long n, int multires_view,
+                                        float* __restrict__ rows, long long row_stride, int col_off, int width) {
+  const int e_dim = 3 + 6 * multires_view;
+  const long long total = n * width;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / width;
+    const int c = (int)(i - p * width);
+    float v = 0.f;
+    if (c < 3) v = pts[p * 3 + c];
+    else if (c < 3 + e_dim) {
+      const int e = c - 3;
+      if (e < 3) v = dirs[p * 3 + e];
+      else {
+        const int f = (e - 3) / 6, w = (e - 3) % 6;
+        const float a = dirs[p * 3 + (w % 3)] * exp2f((float)f);
+        v = w < 3 ? sinf(a) : cosf(a);
+      }
+    } else if (c < 6 + e_dim) v = normals[p * 3 + (c - 3 - e_dim)];
+    rows[p * row_stride + col_off + c] = v;
+  }
+}
+
+extern "C" int vqn_neus_color_input(vqn_ctx* ctx, const float* pts, const float* dirs, const float* normals, int64_t n,
+                                    int multires_view, float* rows, int64_t row_stride, int col_off, int width,
+                                    vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && pts && dirs && normals && rows && n >= 0, "color_input: null argument");
+  VQN_CHECK_ARG(multires_view >= 0 && width >= 9 + 6 * multires_view && col_off >= 0 &&
+                    row_stride >= (int64_t)col_off + width, "color_input: columns do not fit the row");
+  if (n == 0) return VQN_OK;
+  long long want = (n * width + 255) / 256;
+  int blocks = (int)(want < (long long)ctx->sm_count * 16 ? want : (long long)ctx->sm_count * 16);
+  neus_color_input_kernel<<<blocks, 256, 0, vqn_cs(stream)>>>(pts, dirs, normals, n, multires_view, rows, row_stride,
+                                                               col_off, width);
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}

@@ -2,7 +2,10 @@
 
 The per-ray work -- up_sample (+sample_pdf det=True), the sort/merge of cat_z_vals and the SDF-to-alpha
 compositing of render_core -- runs in the warp-per-ray kernels of csrc/neus.cu.  The SDF / colour /
-variance networks stay caller-supplied callables (torch modules), exactly as the reference passes them in.
+variance networks are passed in exactly as the reference passes them; with the native networks of
+neus/fields.py (fused tcgen05 kernel) render_core takes the fused route: ONE launch gives sdf, feature vector and
+SDF gradient, the feature vector lands directly in the colour network's input rows.  Any other callable (a torch
+module) is called the way the reference calls it.
 """
 from __future__ import annotations
 
@@ -52,15 +55,24 @@ class NeuSRenderer:
         pts, dirs = abi.neus_mid_points(rays_o, rays_d, z_vals, float(sample_dist))
         pts = pts.reshape(-1, 3)
         dirs = dirs.reshape(-1, 3)
-        sdf_nn_output = sdf_network(pts)
-        sdf = sdf_nn_output[:, :1]
-        feature_vector = sdf_nn_output[:, 1:]
-        gradients = sdf_network.gradient(pts).squeeze()
-        sampled_color = color_network(pts, gradients, dirs, feature_vector).reshape(batch_size, n_samples, 3)
-        inv_s = deviation_network(torch.zeros([1, 3], device=pts.device))[:, :1].clip(1e-6, 1e6)
+        if hasattr(sdf_network, 'forward_with_gradient') and hasattr(color_network, 'forward_rows'):
+            rows = color_network.alloc_rows(pts.shape[0], pts.device)
+            sdf, _, gradients = sdf_network.forward_with_gradient(pts, feat_out=rows)
+            sampled_color = color_network.forward_rows(rows, pts, gradients, dirs).reshape(batch_size, n_samples, 3)
+        else:
+            sdf_nn_output = sdf_network(pts)
+            sdf = sdf_nn_output[:, :1]
+            feature_vector = sdf_nn_output[:, 1:]
+            gradients = sdf_network.gradient(pts).squeeze()
+            sampled_color = color_network(pts, gradients, dirs, feature_vector).reshape(batch_size, n_samples, 3)
+        if hasattr(deviation_network, 'inv_s'):
+            inv_s_f = min(max(deviation_network.inv_s(), 1e-6), 1e6)          # host value: no device sync
+            inv_s = torch.full((1, 1), inv_s_f, dtype=torch.float32, device=pts.device)
+        else:
+            inv_s = deviation_network(torch.zeros([1, 3], device=pts.device))[:, :1].clip(1e-6, 1e6)
+            inv_s_f = float(inv_s.reshape(-1)[0])
         o = abi.neus_composite(rays_o, rays_d, z_vals, sdf.detach(), gradients.detach(), sampled_color.detach(),
-                               float(inv_s.reshape(-1)[0]), cos_anneal_ratio, float(sample_dist), float(radius),
-                               background_rgb)
+                               inv_s_f, cos_anneal_ratio, float(sample_dist), float(radius), background_rgb)
         ge = o['grad_err_sums']
         gradient_error = (ge[0] / (ge[1] + 1e-5)).to(torch.float32)
         return {
