@@ -381,6 +381,23 @@ def bench_neus_render(dev):
         flop = b * (112 * 2 * SDF_MACS + 128 * (4 * 2 * SDF_MACS + 2 * COLOR_MACS))
         out['rays_%d' % b] = {'ms': ms, 'rays_per_s': b / (ms * 1e-3), 'samples_per_s': b * 128 / (ms * 1e-3),
                               'tflops_executed': flop / (ms * 1e-3) / 1e12}
+    # light-visibility extraction (gen_geo.compute_vis): 256 surface points x 512 lights
+    from vqnerf_release_b200 import abi
+    from vqnerf_release_b200.neus.gen_geo import compute_vis
+    g = torch.Generator(device=dev).manual_seed(3)
+    u = torch.randn((256, 3), generator=g, device=dev)
+    u = u / u.norm(dim=1, keepdim=True)
+    surf = 0.45 * u
+    lx, _ = abi.gen_light_xyz(16, 32)
+    lxyz = torch.as_tensor(lx.reshape(1, -1, 3), dtype=torch.float32).to(dev)
+    ms = timed(lambda: compute_vis(r, surf, u, lxyz, 1.0, cos_anneal_ratio=1.0), 2)
+    lv = compute_vis(r, surf, u, lxyz, 1.0, cos_anneal_ratio=1.0)
+    n_rays = int((lv != 0).sum().item())
+    out['compute_vis_256pts_x_512lights'] = {
+        'ms': ms, 'front_lit_rays': n_rays, 'rays_per_s': n_rays / (ms * 1e-3),
+        'lvis_entries_per_s': 256 * 512 / (ms * 1e-3), 'mean_lvis': float(lv.mean().item()),
+        'tflops_executed': n_rays * (112 * 2 * (SDF_TRUNK_MACS + 256) + 128 * 4 * 2 * (SDF_TRUNK_MACS + 256)) / (ms * 1e-3) / 1e12,
+        'note': 'every front-lit (point, light) pair is one NeuS render of 64 + 4 x 16 samples; colour network skipped'}
     n = 1 << 20
     pts = torch.rand((n, 3), device=dev) * 2 - 1
     rows = col_net.alloc_rows(n, dev)

@@ -375,6 +375,18 @@ int vqn_neus_color_input(vqn_ctx* ctx, const float* pts, const float* dirs, cons
                          int multires_view, float* rows, int64_t row_stride, int col_off, int width,
                          vqn_stream stream);
 
+/* Light-visibility extraction, Runner.compute_vis (geo/NeuS-ours2/gen_geo.py:182-257) + intersect_circle (:346-357):
+ * ray set-up for the pairs (surface point p, light l0 + j), pair index m = p * n_chunk + j:
+ *   rays_o[m] = surf[p]; rays_d[m] = normalize(lxyz[l] - surf[p]); front[m] = (rays_d . normal[p] > 0) as 1.0 / 0.0;
+ *   far[m] = larger root of |o + t d| = radius; near[m] = min(0.1, far / 2).
+ * The caller compacts the front-lit pairs (vqn_compact_mask on `front`), renders them (NeuSRenderer.render) and
+ * scatters 1 - weight_sum back with vqn_neus_lvis_scatter; back-lit entries of lvis[n_pts, n_lights] stay 0. */
+int vqn_neus_light_rays(vqn_ctx* ctx, const float* surf, const float* normal, const float* lxyz, int64_t n_pts,
+                        int l0, int n_chunk, float radius, float* rays_o, float* rays_d, float* near_out,
+                        float* far_out, float* front, vqn_stream stream);
+int vqn_neus_lvis_scatter(vqn_ctx* ctx, const float* weight_sum, const int32_t* row_idx, const int32_t* n_dev,
+                          int64_t n_max, int l0, int n_chunk, int n_lights, float* lvis, vqn_stream stream);
+
 /* ---- measurement helper (not a reference interface) -------------------------------------------- */
 /* FP32-FMA peak of this GPU in TFLOP/s (mode 0: FFMA, mode 1: packed fma.rn.f32x2); synchronises. */
 int vqn_microbench_fma(vqn_ctx* ctx, int mode, int iters, double* tflops_out);

@@ -193,29 +193,31 @@ def _softplus100(x):
     return np.where(bt > 20.0, x, np.log1p(np.exp(np.minimum(bt, 20.0))) / 100.0)
 
 
-def sdf_forward(state, x, multires=6, skip_in=(4,), scale=1.0):
+def sdf_forward(state, x, multires=6, skip_in=(4,), scale=1.0, want_grad=True):
     """SDFNetwork.forward + .gradient (fields.py:74-112): returns (out [n, 1 + d_feature], d sdf / d x [n, 3]).
     The gradient is propagated forward (Jacobian-vector form), which equals the reference's autograd result."""
     x = np.asarray(x, np.float64) * scale
     e, de = embed_jac(x, multires)
     de = de * scale
-    h, dh = e, de
+    h, dh = e, (de if want_grad else None)
     L = n_lin(state)
     for l in range(L):
         if l in skip_in:
             h = np.concatenate([h, e], -1) / np.sqrt(2)
-            dh = np.concatenate([dh, de], -1) / np.sqrt(2)
+            if want_grad:
+                dh = np.concatenate([dh, de], -1) / np.sqrt(2)
         w = effective_weight(state, l)
         b = np.asarray(state['lin%d.bias' % l], np.float64)
         pre = h @ w.T + b
-        dpre = dh @ w.T
+        dpre = dh @ w.T if want_grad else None
         if l < L - 1:
             h = _softplus100(pre)
-            dh = dpre * _sigmoid(100.0 * pre)[:, None, :]
+            if want_grad:
+                dh = dpre * _sigmoid(100.0 * pre)[:, None, :]
         else:
             h, dh = pre, dpre
     out = np.concatenate([h[:, :1] / scale, h[:, 1:]], -1)
-    return out, dh[:, :, 0] / scale
+    return out, (dh[:, :, 0] / scale if want_grad else None)
 
 
 def color_forward(state, points, normals, view_dirs, feature_vectors, multires_view=4, squeeze_out=True):
@@ -229,3 +231,71 @@ def color_forward(state, points, normals, view_dirs, feature_vectors, multires_v
         if l < L - 1:
             h = np.maximum(h, 0.0)
     return _sigmoid(h) if squeeze_out else h
+
+
+# ---------------------------------------------------------------------------------------------
+# NeuSRenderer.render (renderer.py:299-401, n_outside == 0, perturb == 0) and Runner.compute_vis
+# (gen_geo.py:182-257, intersect_circle :346-357) assembled from the pieces above.
+# PINNED by tests/golden/neus_vis_ref.npz (oracle/gen_golden_neus_vis.py: the reference's own renderer + networks).
+# ---------------------------------------------------------------------------------------------
+def render(state, rays_o, rays_d, near, far, radius, inv_s, cos_anneal_ratio=0.0, background_rgb=None,
+           n_samples=64, n_importance=64, up_sample_steps=4, need_color=True):
+    f32 = np.float32
+    rays_o, rays_d = np.asarray(rays_o, f32), np.asarray(rays_d, f32)
+    near, far = np.asarray(near, f32).reshape(-1, 1), np.asarray(far, f32).reshape(-1, 1)
+    b = rays_o.shape[0]
+    sample_dist = 2 * radius / n_samples
+    z = (near + (far - near) * np.linspace(0.0, 1.0, n_samples, dtype=f32)[None, :]).astype(f32)
+    sdf_of = lambda zz: sdf_forward(state['sdf'], (rays_o[:, None, :] + rays_d[:, None, :] * zz[..., None])
+                                    .reshape(-1, 3), want_grad=False)[0][:, 0].reshape(zz.shape).astype(f32)
+    if n_importance > 0:
+        sdf = sdf_of(z)
+        for i in range(up_sample_steps):
+            new_z = up_sample(rays_o, rays_d, z, sdf, radius, n_importance // up_sample_steps, 64 * 2 ** i)
+            if i + 1 == up_sample_steps:
+                z, _ = cat_z_vals(z, new_z)
+            else:
+                z, sdf = cat_z_vals(z, new_z, sdf, sdf_of(new_z))
+    s = z.shape[1]
+    dists = np.concatenate([z[:, 1:] - z[:, :-1], np.full((b, 1), sample_dist, f32)], -1)
+    mid = z + dists * f32(0.5)
+    pts = (rays_o[:, None, :] + rays_d[:, None, :] * mid[..., None]).reshape(-1, 3)
+    out, grad = sdf_forward(state['sdf'], pts)
+    if need_color:
+        dirs = np.broadcast_to(rays_d[:, None, :], (b, s, 3)).reshape(-1, 3)
+        col = color_forward(state['color'], pts, grad, dirs, out[:, 1:])
+    else:
+        col = np.zeros((b * s, 3))
+    return composite(rays_o, rays_d, z, out[:, 0], grad, col, inv_s, cos_anneal_ratio, sample_dist, radius,
+                     background_rgb)
+
+
+def light_rays(surf, normal, lxyz, radius):
+    """gen_geo.py:203-228: directions to every light, front-lit mask, near / far of the visibility rays (float32)."""
+    f32 = np.float32
+    surf, normal, lxyz = np.asarray(surf, f32), np.asarray(normal, f32), np.asarray(lxyz, f32).reshape(-1, 3)
+    d = lxyz[None, :, :] - surf[:, None, :]
+    d = d / np.linalg.norm(d, axis=-1, keepdims=True)
+    front = np.einsum('ijk,ik->ij', d, normal) > 0
+    x = np.broadcast_to(surf[:, None, :], d.shape)
+    bq = f32(2.) * np.sum(x * d, -1)
+    a = np.sum(d * d, -1)
+    c = np.sum(x * x, -1) - f32(radius) ** 2
+    denom = np.where(2 * a > 1e-7, 2 * a, f32(1e-7))
+    disc = np.sqrt(np.square(bq) - f32(4.) * a * c)
+    t1, t2 = (-bq + disc) / denom, (-bq - disc) / denom
+    far = np.where(t1 > t2, t1, t2).astype(f32)
+    near = np.minimum(f32(0.1), far / f32(2.)).astype(f32)
+    return d.astype(f32), front, near, far
+
+
+def compute_vis(state, surf, normal, lxyz, radius, inv_s, cos_anneal_ratio=1.0):
+    """gen_geo.py:182-257 without the dataset / file handling: lvis [N, n_lights] = 1 - weight_sum, 0 where back-lit."""
+    d, front, near, far = light_rays(surf, normal, lxyz, radius)
+    n, nl = front.shape
+    lvis = np.zeros((n, nl), np.float32)
+    o = np.broadcast_to(np.asarray(surf, np.float32)[:, None, :], d.shape)
+    r = render(state, o[front], d[front], near[front], far[front], radius, inv_s, cos_anneal_ratio, None,
+               need_color=False)
+    lvis[front] = 1.0 - r['weight_sum'][:, 0]
+    return lvis

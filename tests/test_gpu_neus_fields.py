@@ -117,3 +117,45 @@ def test_render_with_native_networks_vs_reference(cuda_dev):
     np.testing.assert_allclose(out['weights'].cpu().numpy(), g['render_weights'], rtol=0, atol=5e-3)
     np.testing.assert_allclose(out['s_val'].cpu().numpy(), g['render_s_val'], rtol=1e-5)
     assert abs(float(out['gradient_error']) - float(g['render_gradient_error'])) < 1e-3
+
+
+def test_light_rays_kernel_vs_oracle(cuda_dev):
+    from vqnerf_release_b200 import abi
+    g = np.load(os.path.join(os.path.dirname(GOLD), 'neus_vis_ref.npz'))
+    rng = np.random.RandomState(5)
+    n = 37
+    surf = rng.uniform(-0.7, 0.7, size=(n, 3)).astype(np.float32)
+    nrm = rng.normal(size=(n, 3)); nrm = (nrm / np.linalg.norm(nrm, axis=1, keepdims=True)).astype(np.float32)
+    d, front, near, far = NO.light_rays(surf, nrm, g['lxyz'], 1.0)
+    for l0, nc in ((0, 512), (100, 7), (511, 1)):
+        ro, rd, nr, fr, ft = abi.neus_light_rays(_t(surf, cuda_dev), _t(nrm, cuda_dev), _t(g['lxyz'], cuda_dev), l0, nc, 1.0)
+        assert ro.shape == (n * nc, 3) and ft.shape == (n * nc, 1)
+        np.testing.assert_array_equal(ro.cpu().numpy().reshape(n, nc, 3), np.broadcast_to(surf[:, None, :], (n, nc, 3)))
+        np.testing.assert_allclose(rd.cpu().numpy().reshape(n, nc, 3), d[:, l0:l0 + nc], rtol=0, atol=3e-7)
+        np.testing.assert_allclose(fr.cpu().numpy().reshape(n, nc), far[:, l0:l0 + nc], rtol=2e-5, atol=0)     # -b + sqrt(disc) cancels
+        np.testing.assert_allclose(nr.cpu().numpy().reshape(n, nc), near[:, l0:l0 + nc], rtol=2e-5, atol=0)
+        lcos = np.einsum('ijk,ik->ij', d.astype(np.float64), nrm.astype(np.float64))[:, l0:l0 + nc]
+        sure = np.abs(lcos) > 1e-6                                   # the sign of a grazing cosine may round either way
+        np.testing.assert_array_equal((ft.cpu().numpy().reshape(n, nc) > 0)[sure], front[:, l0:l0 + nc][sure])
+    with pytest.raises(ValueError):
+        abi.neus_light_rays(_t(surf, cuda_dev), _t(nrm, cuda_dev), _t(g['lxyz'], cuda_dev), 510, 3, 1.0)
+
+
+def test_compute_vis_vs_reference(cuda_dev):
+    """Light-visibility extraction with the native renderer against the reference's renderer + networks
+    driven by the loop of gen_geo.py:202-244 (tests/golden/neus_vis_ref.npz); two chunkings give the same buffer."""
+    from vqnerf_release_b200.neus.gen_geo import compute_vis
+    from vqnerf_release_b200.neus.renderer import NeuSRenderer
+    g = np.load(os.path.join(os.path.dirname(GOLD), 'neus_vis_ref.npz'))
+    _, sdf_net, col_net, dev_net = _nets(cuda_dev)
+    r = NeuSRenderer(None, sdf_net, dev_net, col_net, n_samples=64, n_importance=64, n_outside=0, up_sample_steps=4,
+                     perturb=0.0)
+    surf, nrm, lxyz = _t(g['surf'], cuda_dev), _t(g['normal'], cuda_dev), _t(g['lxyz'], cuda_dev)
+    lvis = compute_vis(r, surf, nrm, lxyz[None], float(g['max_radius']), cos_anneal_ratio=1.0)
+    assert lvis.shape == (5, 512)
+    got = lvis.cpu().numpy()
+    np.testing.assert_array_equal(got == 0.0, g['lvis'] == 0.0)                # back-lit pairs exactly zero
+    np.testing.assert_allclose(got, g['lvis'], rtol=0, atol=2e-3)
+    lvis2 = compute_vis(r, surf, nrm, lxyz[None], float(g['max_radius']), cos_anneal_ratio=1.0, batch_size=2,
+                        rays_per_render=100)
+    np.testing.assert_allclose(lvis2.cpu().numpy(), got, rtol=0, atol=1e-6)    # chunking does not change a pair's ray

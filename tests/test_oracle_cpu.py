@@ -172,3 +172,17 @@ def test_neus_networks_match_reference():
         e = np.zeros(3); e[k] = 1e-6
         fd = (NO.sdf_forward(st['sdf'], x + e)[0][:, 0] - NO.sdf_forward(st['sdf'], x - e)[0][:, 0]) / 2e-6
         np.testing.assert_allclose(grad[:16, k], fd, rtol=0, atol=1e-6)
+
+
+def test_neus_compute_vis_matches_reference():
+    """oracle light-visibility extraction (ray set-up + render + 1 - weight_sum) vs the loop of gen_geo.py:202-244
+    driven around the reference's own renderer and networks (tests/golden/neus_vis_ref.npz)."""
+    g = np.load(os.path.join(GOLD, 'neus_vis_ref.npz'))
+    st = NO.make_neus_state(0)
+    inv_s = float(np.exp(np.float32(g['variance']) * 10.0))
+    k = 1                                                     # one probe point (~260 rays) keeps the CPU suite short
+    lvis = NO.compute_vis(st, g['surf'][:k], g['normal'][:k], g['lxyz'], float(g['max_radius']), inv_s, 1.0)
+    assert lvis.shape == (k, 512)
+    np.testing.assert_array_equal(lvis == 0.0, g['lvis'][:k] == 0.0)          # back-lit pairs are exactly zero
+    np.testing.assert_allclose(lvis, g['lvis'][:k], rtol=0, atol=2e-3)
+    assert 0.05 < (g['lvis'][:k] > 0.5).mean() < 0.95                          # occluded and visible pairs both present

@@ -463,6 +463,37 @@ def neus_color_input(pts, dirs, normals, multires_view: int, rows: torch.Tensor,
                                        L.stream_ptr(pts.device)))
 
 
+def neus_light_rays(surf, normal, lxyz, l0: int, n_chunk: int, radius: float):
+    """vqn_neus_light_rays: rays from every surface point to lights [l0, l0 + n_chunk).  Returns rays_o [M,3],
+    rays_d [M,3], near [M,1], far [M,1], front [M,1] (1.0 where front-lit), M = n_pts * n_chunk."""
+    surf, normal, lxyz = map(_f, (surf, normal, lxyz))
+    lxyz = lxyz.reshape(-1, 3)
+    n = surf.shape[0]
+    if l0 < 0 or n_chunk < 1 or l0 + n_chunk > lxyz.shape[0]:
+        raise ValueError('light chunk [%d, %d) outside the %d lights' % (l0, l0 + n_chunk, lxyz.shape[0]))
+    m = n * n_chunk
+    dev = surf.device
+    rays_o = torch.empty((m, 3), dtype=F32, device=dev)
+    rays_d = torch.empty((m, 3), dtype=F32, device=dev)
+    near, far, front = (torch.empty((m, 1), dtype=F32, device=dev) for _ in range(3))
+    if m:
+        c = _ctx(surf)
+        L.check(c.lib.vqn_neus_light_rays(c.handle, L.ptr(surf), L.ptr(normal), L.ptr(lxyz), n, int(l0), int(n_chunk),
+                                          float(radius), L.ptr(rays_o), L.ptr(rays_d), L.ptr(near), L.ptr(far),
+                                          L.ptr(front), L.stream_ptr(dev)))
+    return rays_o, rays_d, near, far, front
+
+
+def neus_lvis_scatter(weight_sum, row_idx, n: int, l0: int, n_chunk: int, lvis: torch.Tensor):
+    """lvis[p, l0 + j] = 1 - weight_sum[i] for the compacted pair row_idx[i] = p * n_chunk + j (first n rows)."""
+    weight_sum = _f(weight_sum)
+    if lvis.dtype != F32 or not lvis.is_contiguous() or lvis.dim() != 2:
+        raise ValueError('lvis must be a contiguous float32 [n_pts, n_lights] tensor')
+    c = _ctx(lvis)
+    L.check(c.lib.vqn_neus_lvis_scatter(c.handle, L.ptr(weight_sum), L.ptr(row_idx, torch.int32), None, int(n), int(l0),
+                                        int(n_chunk), int(lvis.shape[1]), L.ptr(lvis), L.stream_ptr(lvis.device)))
+
+
 # ---- tensor-core primitive self-test ------------------------------------------------------------
 def tc_selftest(a: torch.Tensor, b: torch.Tensor, mode: int) -> torch.Tensor:
     """d[128,n] = a[128,k] @ b[n,k]^T on tcgen05 (mode 0 tf32, 1 bf16, 2 3xTF32)."""

@@ -394,3 +394,83 @@ extern "C" int vqn_neus_color_input(vqn_ctx* ctx, const float* pts, const float*
   VQN_LAUNCHED(ctx);
   return VQN_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Light-visibility extraction, ray set-up and result scatter (gen_geo.py:182-257 compute_vis, :346-357 intersect_circle)
+//   pair m = p * n_chunk + j  <->  surface point p, light l0 + j
+//   d = normalize(lxyz[l] - surf[p]); front = d . normal[p] > 0; far = larger root of |surf + t d| = r;
+//   near = min(0.1, far / 2)
+// ---------------------------------------------------------------------------------------------
+__global__ void neus_light_rays_kernel(const float* __restrict__ surf, const float* __restrict__ normal,
+                                       const float* __restrict__ lxyz, long long n_pts, int l0, int n_chunk, float radius,
+                                       float* __restrict__ rays_o, float* __restrict__ rays_d, float* __restrict__ near_o,
+                                       float* __restrict__ far_o, float* __restrict__ front) {
+  const long long total = n_pts * n_chunk;
+  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < total;
+       m += (long long)gridDim.x * blockDim.x) {
+    const long long p = m / n_chunk;
+    const int l = l0 + (int)(m - p * n_chunk);
+    const float sx = surf[p * 3], sy = surf[p * 3 + 1], sz = surf[p * 3 + 2];
+    float dx = lxyz[l * 3] - sx, dy = lxyz[l * 3 + 1] - sy, dz = lxyz[l * 3 + 2] - sz;
+    const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);          // torch.linalg.norm; division as in :208
+    dx = dx / nrm; dy = dy / nrm; dz = dz / nrm;
+    const float lcos = dx * normal[p * 3] + dy * normal[p * 3 + 1] + dz * normal[p * 3 + 2];
+    const float b = 2.0f * (sx * dx + sy * dy + sz * dz);
+    const float a = dx * dx + dy * dy + dz * dz;
+    const float c = sx * sx + sy * sy + sz * sz - radius * radius;
+    const float denom = 2.0f * a > 1e-7f ? 2.0f * a : 1e-7f;
+    const float sq = sqrtf(b * b - 4.0f * a * c);
+    const float t1 = (-b + sq) / denom, t2 = (-b - sq) / denom;
+    const float t = t1 > t2 ? t1 : t2;
+    const float n_far = t * 0.5f;
+    rays_o[m * 3] = sx; rays_o[m * 3 + 1] = sy; rays_o[m * 3 + 2] = sz;
+    rays_d[m * 3] = dx; rays_d[m * 3 + 1] = dy; rays_d[m * 3 + 2] = dz;
+    far_o[m] = t;
+    near_o[m] = 0.1f < n_far ? 0.1f : n_far;
+    front[m] = lcos > 0.0f ? 1.0f : 0.0f;
+  }
+}
+
+extern "C" int vqn_neus_light_rays(vqn_ctx* ctx, const float* surf, const float* normal, const float* lxyz,
+                                   int64_t n_pts, int l0, int n_chunk, float radius, float* rays_o, float* rays_d,
+                                   float* near_out, float* far_out, float* front, vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && surf && normal && lxyz && rays_o && rays_d && near_out && far_out && front,
+                "light_rays: null argument");
+  VQN_CHECK_ARG(n_pts >= 0 && l0 >= 0 && n_chunk >= 1 && radius > 0.f, "light_rays: bad sizes");
+  if (n_pts == 0) return VQN_OK;
+  long long want = (n_pts * n_chunk + 255) / 256;
+  int blocks = (int)(want < (long long)ctx->sm_count * 16 ? want : (long long)ctx->sm_count * 16);
+  neus_light_rays_kernel<<<blocks, 256, 0, vqn_cs(stream)>>>(surf, normal, lxyz, n_pts, l0, n_chunk, radius, rays_o,
+                                                              rays_d, near_out, far_out, front);
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}
+
+// lvis[p, l0 + j] = 1 - weight_sum of the compacted ray i whose pair index is row_idx[i] = p * n_chunk + j
+// (gen_geo.py:241-244: lvis_hit[front_lit_full] = 1 - occu); back-lit pairs keep the buffer's zero
+__global__ void neus_lvis_scatter_kernel(const float* __restrict__ weight_sum, const int* __restrict__ row_idx,
+                                         const int* __restrict__ n_dev, long long n_max, int l0, int n_chunk,
+                                         int n_lights, float* __restrict__ lvis) {
+  long long n = n_dev ? (long long)*n_dev : n_max;
+  if (n > n_max) n = n_max;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = row_idx[i];
+    const long long p = m / n_chunk;
+    const int j = (int)(m - p * n_chunk);
+    lvis[p * n_lights + l0 + j] = 1.0f - weight_sum[i];
+  }
+}
+
+extern "C" int vqn_neus_lvis_scatter(vqn_ctx* ctx, const float* weight_sum, const int32_t* row_idx,
+                                     const int32_t* n_dev, int64_t n_max, int l0, int n_chunk, int n_lights,
+                                     float* lvis, vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && weight_sum && row_idx && lvis && n_max >= 0, "lvis_scatter: null argument");
+  VQN_CHECK_ARG(l0 >= 0 && n_chunk >= 1 && l0 + n_chunk <= n_lights, "lvis_scatter: light chunk outside the probe");
+  if (n_max == 0) return VQN_OK;
+  long long want = (n_max + 255) / 256;
+  int blocks = (int)(want < (long long)ctx->sm_count * 16 ? want : (long long)ctx->sm_count * 16);
+  neus_lvis_scatter_kernel<<<blocks, 256, 0, vqn_cs(stream)>>>(weight_sum, row_idx, n_dev, n_max, l0, n_chunk, n_lights,
+                                                                lvis);
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}

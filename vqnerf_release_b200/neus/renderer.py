@@ -48,14 +48,19 @@ class NeuSRenderer:
     # renderer.py:193-297
     def render_core(self, rays_o, rays_d, z_vals, sample_dist, radius, sdf_network, deviation_network,
                     color_network, background_alpha=None, background_sampled_color=None, background_rgb=None,
-                    cos_anneal_ratio=0.0, to_light=False):
+                    cos_anneal_ratio=0.0, to_light=False, need_color=True):
+        # need_color=False (not a reference argument): callers that only read the weights (compute_vis) skip the
+        # colour network; every other output is unchanged and 'color' is the composited background only
         if background_alpha is not None or to_light:
             raise NotImplementedError('background model / to_light marching are outside the path (n_outside = 0)')
         batch_size, n_samples = z_vals.shape
         pts, dirs = abi.neus_mid_points(rays_o, rays_d, z_vals, float(sample_dist))
         pts = pts.reshape(-1, 3)
         dirs = dirs.reshape(-1, 3)
-        if hasattr(sdf_network, 'forward_with_gradient') and hasattr(color_network, 'forward_rows'):
+        if not need_color and hasattr(sdf_network, 'forward_with_gradient'):
+            sdf, _, gradients = sdf_network.forward_with_gradient(pts, want_feat=False)
+            sampled_color = torch.zeros((batch_size, n_samples, 3), dtype=torch.float32, device=pts.device)
+        elif hasattr(sdf_network, 'forward_with_gradient') and hasattr(color_network, 'forward_rows'):
             rows = color_network.alloc_rows(pts.shape[0], pts.device)
             sdf, _, gradients = sdf_network.forward_with_gradient(pts, feat_out=rows)
             sampled_color = color_network.forward_rows(rows, pts, gradients, dirs).reshape(batch_size, n_samples, 3)
@@ -86,7 +91,7 @@ class NeuSRenderer:
 
     # renderer.py:299-401
     def render(self, rays_o, rays_d, near, far, radius, perturb_overwrite=-1, background_rgb=None,
-               cos_anneal_ratio=0.0, to_light=False):
+               cos_anneal_ratio=0.0, to_light=False, need_color=True):
         if to_light:
             raise NotImplementedError('to_light marching (gen_geo.compute_vis) is a "next" row (SURVEY 8f N1)')
         batch_size = len(rays_o)
@@ -113,7 +118,7 @@ class NeuSRenderer:
             n_samples = self.n_samples + self.n_importance
         ret_fine = self.render_core(rays_o, rays_d, z_vals, sample_dist, radius, self.sdf_network,
                                     self.deviation_network, self.color_network, background_rgb=background_rgb,
-                                    cos_anneal_ratio=cos_anneal_ratio)
+                                    cos_anneal_ratio=cos_anneal_ratio, need_color=need_color)
         s_val = ret_fine['s_val'].reshape(batch_size, n_samples).mean(dim=-1, keepdim=True)
         return {
             'color_fine': ret_fine['color'], 's_val': s_val, 'cdf_fine': ret_fine['cdf'],
