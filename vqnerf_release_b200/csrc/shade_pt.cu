@@ -11,46 +11,62 @@
 // consecutive loads of the same thread and stays in L1 meanwhile).  (A first version kept the tables in the
 // constant bank: 61 KB swept by 24 warps at different offsets thrashes the constant cache -- 6.7 ms vs 2.6 ms.)
 //
-// Light image (61 440 B, built on the launching stream before every launch since the model light is trainable):
-// per group of 4 lights, 3 float4 of light positions (x, y, z of the 4 lights) and 27 float4 of radiance x area
-// ((probe, channel)-major, the 4 lights in the components).  One persistent 512-thread block per SM copies it
-// into shared memory once and walks 32-point tiles, warp-strided.
+// Light image (<= 63 488 B, built on the launching stream before every launch since the model light is trainable):
+// per group of 4 lights, 3 float4 of light positions (x, y, z of the 4 lights), then per light NF4 float4 of
+// radiance x area arranged as output PAIRS: pair m < NPC = (probe m: channel 0, channel 1), pair NPC + j = channel 2
+// of probes (2j, 2j+1) (zero padded).  The 3 (1+P) sums are accumulated pairwise with the packed fma.rn.f32x2
+// (FFMA2): the kernel is bound by issue slots, not by the FMA pipe, and the pairs halve the issue slots of the
+// accumulation (27 -> 14 per light for 9 probes); the per-light factor is (e0, e1) or (e2, e2); an LDS.128 delivers
+// two radiance pairs already in aligned 64-bit registers.  One persistent
+// 512-thread block per SM copies the image into shared memory once and walks 32-point tiles, warp-strided.
 #include "common.cuh"
 
 #define SP_L 512
 #define SP_GROUPS (SP_L / 4)
 #define SP_MAXP 9
-#define SP_F4_PER_GROUP (3 + 3 * SP_MAXP)
+#define SP_NPAIR(npc) ((npc) + ((npc) + 1) / 2)         // output pairs: (c0, c1) per probe + channel 2 of two probes
+#define SP_NF4(npc) ((SP_NPAIR(npc) + 1) / 2)           // float4 of radiance per light
+#define SP_F4_PER_GROUP(npc) (3 + 4 * SP_NF4(npc))
+#define SP_F4_MAX SP_F4_PER_GROUP(SP_MAXP)
 
 #define SP_THREADS 512
 
 namespace {
 
 __device__ __forceinline__ float fast_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
-// staging image in device memory (copied to c_shade with a D2D memcpy-to-symbol)
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void ffma2(u64& acc, u64 a, u64 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+
+// staging image in device memory, nf4 = SP_NF4(NPC) of the kernel instance that will read it
 __global__ void shade_pt_prep_kernel(const float* __restrict__ lxyz, const float* __restrict__ lareas,
-                                     const float* __restrict__ lights, int n_probes, int clip_light0,
-                                     float4* __restrict__ img) {
+                                     const float* __restrict__ lights, int n_probes, int clip_light0, int npc,
+                                     int nf4, float4* __restrict__ img) {
+  const int per_group = 3 + 4 * nf4;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;       // one float4 of the image
-  if (i >= SP_GROUPS * SP_F4_PER_GROUP) return;
-  const int grp = i / SP_F4_PER_GROUP, k = i % SP_F4_PER_GROUP;
+  if (i >= SP_GROUPS * per_group) return;
+  const int grp = i / per_group, k = i % per_group;
   float v[4];
+  if (k < 3) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int l = 4 * grp + q;
-    if (k < 3) {
-      v[q] = lxyz[3 * l + k];
-    } else {
-      const int p = (k - 3) / 3, ch = (k - 3) % 3;
+    for (int q = 0; q < 4; ++q) v[q] = lxyz[3 * (4 * grp + q) + k];
+  } else {
+    const int l = 4 * grp + (k - 3) / nf4, j = (k - 3) % nf4;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int m = 2 * j + (c >> 1);                          // output pair (see the header comment)
+      const int p = m < npc ? m : 2 * (m - npc) + (c & 1), ch = m < npc ? (c & 1) : 2;
       float r = 0.f;
       if (p < n_probes) {
         r = lights[((size_t)p * SP_L + l) * 3 + ch];
         if (p == 0 && clip_light0) r = fmaxf(r, 0.f);          // clip(_light, 0, inf), vq_nfr.py:759
         r *= lareas[l];
       }
-      v[q] = r;
+      v[c] = r;
     }
   }
   img[i] = make_float4(v[0], v[1], v[2], v[3]);
@@ -60,9 +76,10 @@ template <int NPC, bool HAS_LVIS>
 __global__ void __launch_bounds__(SP_THREADS, 1) shade_pt_kernel(vqn_shade_args a, const float4* __restrict__ img,
                                                                  int* nonfinite) {
   extern __shared__ __align__(16) float4 s_img[];
-  for (int k = threadIdx.x; k < SP_GROUPS * SP_F4_PER_GROUP; k += SP_THREADS) s_img[k] = img[k];
+  constexpr int NF4 = SP_NF4(NPC), PER_GROUP = SP_F4_PER_GROUP(NPC), NPAIR = 2 * NF4;   // NPAIR includes the padding pair
+  for (int k = threadIdx.x; k < SP_GROUPS * PER_GROUP; k += SP_THREADS) s_img[k] = img[k];
   // per-warp staging of the 32 x (3 NPC) outputs of a tile for the coalesced peer stores (fused gather)
-  float* s_out = reinterpret_cast<float*>(s_img + SP_GROUPS * SP_F4_PER_GROUP) + (threadIdx.x >> 5) * (32 * (3 * NPC + 1));
+  float* s_out = reinterpret_cast<float*>(s_img + SP_GROUPS * PER_GROUP) + (threadIdx.x >> 5) * (32 * (3 * NPC + 1));
   __syncthreads();
   long long n = a.n_dev ? (long long)*a.n_dev : a.n;
   if (n > a.n) n = a.n;
@@ -100,9 +117,9 @@ __global__ void __launch_bounds__(SP_THREADS, 1) shade_pt_kernel(vqn_shade_args 
   const float avn = fabsf(vn);
   const float a_pt = avn == 0.f ? 0.f : a2 * g_v * (0.5f * INV_PI) / avn;
 
-  float out[NPC * 3];
+  u64 acc[NPAIR];                                               // (out[2m], out[2m+1]) pairs, fp32 x 2
 #pragma unroll
-  for (int k = 0; k < NPC * 3; ++k) out[k] = 0.f;
+  for (int m = 0; m < NPAIR; ++m) acc[m] = 0ull;
   const float4* lv = reinterpret_cast<const float4*>(a.lvis + (HAS_LVIS ? row * SP_L : 0));
   float4 lv_cur = make_float4(1.f, 1.f, 1.f, 1.f);
   if (HAS_LVIS) lv_cur = __ldg(lv);
@@ -111,55 +128,60 @@ __global__ void __launch_bounds__(SP_THREADS, 1) shade_pt_kernel(vqn_shade_args 
   for (int grp = 0; grp < SP_GROUPS; ++grp) {
     float4 lv_nxt = lv_cur;
     if (HAS_LVIS && grp + 1 < SP_GROUPS) lv_nxt = __ldg(lv + grp + 1);
-    const float4* cg = s_img + grp * SP_F4_PER_GROUP;          // warp-uniform address: broadcast reads
+    const float4* cg = s_img + grp * PER_GROUP;                // warp-uniform address: broadcast reads
     const float4 X = cg[0], Y = cg[1], Z = cg[2];
     const float xs4[4] = {X.x, X.y, X.z, X.w}, ys4[4] = {Y.x, Y.y, Y.z, Y.w}, zs4[4] = {Z.x, Z.y, Z.z, Z.w};
     const float lvv[4] = {lv_cur.x, lv_cur.y, lv_cur.z, lv_cur.w};
-    float e[4][3];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      float dx = xs4[q] - px, dy = ys4[q] - py, dz = zs4[q] - pz;
-      const float inv = fast_rsqrt(fmaxf(dx * dx + dy * dy + dz * dz, 1e-6f));   // _calc_ldir
-      dx *= inv; dy *= inv; dz *= inv;
-      const float cos_r = dx * nx + dy * ny + dz * nz;          // _render: cos = l . n
+      const float dx = xs4[q] - px, dy = ys4[q] - py, dz = zs4[q] - pz;
+      const float inv = fast_rsqrt(fmaxf(dx * dx + dy * dy + dz * dz, 1e-6f));   // _calc_ldir: l = d * inv
+      const float cos_r = (dx * nx + dy * ny + dz * nz) * inv;  // _render: cos = l . n
       const float ln = cos_r * inv_n;                           // get_brdf: l . normalize(n)
-      const float lvd = dx * vx + dy * vy + dz * vz;
       // h = normalize(l + v), formed componentwise as the reference does (microfacet.py:21-22).  The shortcut
       // |l + v|^2 = 2 + 2 l.v is cheaper but its rounding error is amplified by 2/q in q = 1 - (h.n)^2 (1 - a^2)
       // near the highlight (h ~ n, small roughness): 2e-4 relative on the specular lobe, outside the parity budget.
-      const float hx = dx + vx, hy = dy + vy, hz = dz + vz;
+      const float hx = fmaf(dx, inv, vx), hy = fmaf(dy, inv, vy), hz = fmaf(dz, inv, vz);
       const float hi_ = fast_rsqrt(fmaxf(hx * hx + hy * hy + hz * hz, 1e-6f));
       const float hvr = (hx * vx + hy * vy + hz * vz) * hi_;
-      const float hnr = (hx * nx + hy * ny + hz * nz) * inv_n * hi_;
-      const float hv = fminf(fmaxf(hvr, 0.f), 1.f);                     // h . v
-      const float hn = fminf(fmaxf(hnr, 0.f), 1.f);                     // h . n
+      const float hnr = (hx * nx + hy * ny + hz * nz) * (inv_n * hi_);
+      const float hv = __saturatef(hvr);                        // clip(h . v, 0, 1)
+      const float hn = __saturatef(hnr);                        // clip(h . n, 0, 1)
       const float om = 1.0f - hv, om2 = om * om;
       const float p5 = om2 * om2 * om;                          // (1 - h.v)^5
       const float q_ = fmaf(hn * hn, a2m1, 1.0f);
-      const float cl = fminf(fmaxf(ln, 0.f), 1.f);
+      const float cl = __saturatef(ln);
       const float den_l = cl + fast_sqrt(fabsf(fmaf(oma2, cl * cl, a2)));
-      const float den = q_ * q_ * den_l * fabsf(ln);
-      const float S = den == 0.f ? 0.f : __fdividef(a_pt * cl, den);
-      float wv = cos_r > 0.f ? cos_r : 0.f;                     // front_lit * cos
+      // glossy = F G D / (4 |l.n| |v.n|) with g(l) = 2 cl / den_l: the factor cl / |l.n| is 1 for every front-lit
+      // light (0 < l.n <= 1) and the term is multiplied by front_lit * cos below, so the division by |l.n| and the
+      // divide_no_nan guard drop out; q_^2 den_l >= a2^2.5 > 0 (the floor only matters for rough == 0, where a_pt == 0)
+      const float S = a_pt * fast_rcp(fmaxf(q_ * q_ * den_l, 1e-30f));
+      float wv = fmaxf(cos_r, 0.f);                             // front_lit * cos
       if (HAS_LVIS) wv *= lvv[q];
       const float sw = S * wv, psw = p5 * sw, dsw = sw - psw;   // F S w = psw + f0 (sw - psw)
-      e[q][0] = fmaf(alb0, wv, fmaf(f00, dsw, psw));
-      e[q][1] = fmaf(alb1, wv, fmaf(f01, dsw, psw));
-      e[q][2] = fmaf(alb2, wv, fmaf(f02, dsw, psw));
-    }
+      const float e0 = fmaf(alb0, wv, fmaf(f00, dsw, psw));
+      const float e1 = fmaf(alb1, wv, fmaf(f01, dsw, psw));
+      const float e2 = fmaf(alb2, wv, fmaf(f02, dsw, psw));
+      const u64 e01 = pack2(e0, e1), e22 = pack2(e2, e2);
+      const ulonglong2* rq = reinterpret_cast<const ulonglong2*>(cg + 3 + q * NF4);
 #pragma unroll
-    for (int p = 0; p < NPC; ++p)
-#pragma unroll
-      for (int ch = 0; ch < 3; ++ch) {
-        const float4 R = cg[3 + p * 3 + ch];
-        float o = out[p * 3 + ch];
-        o = fmaf(e[0][ch], R.x, o); o = fmaf(e[1][ch], R.y, o);
-        o = fmaf(e[2][ch], R.z, o); o = fmaf(e[3][ch], R.w, o);
-        out[p * 3 + ch] = o;
+      for (int j = 0; j < NF4; ++j) {
+        const ulonglong2 R = rq[j];                             // radiance x area of output pairs 2j, 2j+1 for this light
+        ffma2(acc[2 * j], 2 * j < NPC ? e01 : e22, R.x);
+        ffma2(acc[2 * j + 1], 2 * j + 1 < NPC ? e01 : e22, R.y);
       }
+    }
     lv_cur = lv_nxt;
   }
   const int NP = a.n_probes;
+  float out[3 * NPC];
+#pragma unroll
+  for (int p = 0; p < NPC; ++p) {
+    unpack2(acc[p], out[3 * p], out[3 * p + 1]);
+    float lo, hi;
+    unpack2(acc[NPC + p / 2], lo, hi);
+    out[3 * p + 2] = (p & 1) ? hi : lo;
+  }
 #pragma unroll
   for (int p = 0; p < NPC; ++p) {
 #pragma unroll
@@ -198,7 +220,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) shade_pt_kernel(vqn_shade_args 
 
 template <int NPC>
 int launch_pt(vqn_ctx* ctx, const vqn_shade_args& a, const float4* img, cudaStream_t s) {
-  const size_t smem = sizeof(float4) * SP_GROUPS * SP_F4_PER_GROUP + sizeof(float) * (SP_THREADS / 32) * 32 * (3 * NPC + 1);
+  const size_t smem = sizeof(float4) * SP_GROUPS * SP_F4_PER_GROUP(NPC) + sizeof(float) * (SP_THREADS / 32) * 32 * (3 * NPC + 1);
   long long want = (a.n + SP_THREADS - 1) / SP_THREADS;
   const unsigned blocks = (unsigned)(want < (long long)ctx->sm_count ? want : (long long)ctx->sm_count);
   if (a.lvis) {
@@ -218,11 +240,13 @@ int launch_pt(vqn_ctx* ctx, const vqn_shade_args& a, const float4* img, cudaStre
 int vqn_shade_pt_launch(vqn_ctx* ctx, const vqn_shade_args& a, cudaStream_t s) {
   // staging image in the upper half of the context's persistent scratch (stream-ordered: prep, then the kernel)
   float4* img = reinterpret_cast<float4*>(ctx->scratch + 32768);
-  const int total = SP_GROUPS * SP_F4_PER_GROUP;
-  shade_pt_prep_kernel<<<(total + 127) / 128, 128, 0, s>>>(a.lxyz, a.lareas, a.lights, a.n_probes, a.clip_light0, img);
+  const int npc = a.n_probes <= 1 ? 1 : a.n_probes <= 3 ? 3 : a.n_probes <= 5 ? 5 : SP_MAXP;
+  const int total = SP_GROUPS * SP_F4_PER_GROUP(npc);
+  shade_pt_prep_kernel<<<(total + 127) / 128, 128, 0, s>>>(a.lxyz, a.lareas, a.lights, a.n_probes, a.clip_light0,
+                                                           npc, SP_NF4(npc), img);
   VQN_LAUNCHED(ctx);
-  if (a.n_probes <= 1) return launch_pt<1>(ctx, a, img, s);
-  if (a.n_probes <= 3) return launch_pt<3>(ctx, a, img, s);
-  if (a.n_probes <= 5) return launch_pt<5>(ctx, a, img, s);
+  if (npc == 1) return launch_pt<1>(ctx, a, img, s);
+  if (npc == 3) return launch_pt<3>(ctx, a, img, s);
+  if (npc == 5) return launch_pt<5>(ctx, a, img, s);
   return launch_pt<SP_MAXP>(ctx, a, img, s);
 }
