@@ -134,8 +134,8 @@ class ClockSampler:
 
 def ncu_traffic(n, probes, precision):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r1c_ncu_traffic.json) -- only valid for the workload it was captured on, else None."""
-    p = os.path.join(ROOT, 'profiles', 'r1c_ncu_traffic.json')
+    (profiles/r1e_ncu_traffic.json) -- only valid for the workload it was captured on, else None."""
+    p = os.path.join(ROOT, 'profiles', 'r1e_ncu_traffic.json')
     try:
         d = json.load(open(p))
         w = d['workload']
@@ -147,7 +147,7 @@ def ncu_traffic(n, probes, precision):
                 'note': 'dram__bytes_read.sum + dram__bytes_write.sum of the encoder launch + the heads launch '
                         '(the latent z [n,256] fp32 = 655 MB is written by the first and read by the second; '
                         'weights stay in L2); algorithmic bytes of the fused pair: 40 B/point = 25.6 MB',
-                'source': 'profiles/r1c_ncu_traffic.json'}
+                'source': 'profiles/r1e_ncu_traffic.json'}
     except Exception:
         return None
 
@@ -608,7 +608,17 @@ def run_ours(args):
                 roof['traffic'] = tr['bytes']
                 roof['traffic_note'] = tr['note'] + ' [' + tr['source'] + ']'
             roof['binding_resource'] = ('shared-memory port (128 B/clk/SM): UMMA operand reads + A-chunk stores + weight '
-                                        'copies; see DESIGN.md 4.1 and benchmarks/tc_trace.py')
+                                        'copies, and on the N = 128 layers the producers\' chunk rate; see DESIGN.md 4.1 '
+                                        'and benchmarks/tc_trace.py')
+            if args.precision == 'tf32x3':
+                # the kernel evaluates the two correction products as ONE bf16 MMA of twice the K, i.e. 4 instead of 6
+                # bf16-equivalent MMA units per fp32-equivalent product: its own instruction stream has a higher ceiling
+                roof['frac_of_executed_scheme_peak'] = ach / (bf16_peak / 4)
+                roof['executed_scheme_note'] = ('peak above = three kind::tf32 MMAs per product (the plain 3xTF32 split); the '
+                                                'kernel issues 1 tf32 + 1 bf16(K=16) MMA per 8 K-values = bf16 peak / 4 = '
+                                                '%.0f TFLOP/s fp32-equivalent; ncu sm__pipe_tensor_cycles_active: encoder '
+                                                'launch 28 %%, heads launch 34 %% (profiles/r1e_ncu_traffic.json)'
+                                                % (bf16_peak / 4))
         shade_bytes = n * (2048 + 36 + 28 + 12 * (1 + P))
         kernels = {
             'mlp_main': {'ms': mlp_ms, 'tflops': MLP_FLOP * n / (mlp_ms * 1e-3) / 1e12},

@@ -99,6 +99,36 @@ def main():
     ok = err < 2e-5 and cs == 0.0 and dw < 1e-5 and np.allclose(losses1, losses2, rtol=1e-5)
     print('rank %d: rows [%d,%d) max|param diff| %.3e  cs_hidden diff %.1e  dw_hidden diff %.1e  loss %s vs %s  -> %s'
           % (rank, lo, hi, err, cs, dw, losses1, losses2, 'OK' if ok else 'MISMATCH'), flush=True)
+    # ---- NeuS geo stage: ray-sharded render and point-sharded light visibility == single device ----
+    from oracle import neus_oracle as NO
+    from vqnerf_release_b200 import abi
+    from vqnerf_release_b200.neus.fields import RenderingNetwork, SDFNetwork, SingleVarianceNetwork
+    from vqnerf_release_b200.neus.gen_geo import compute_vis, compute_vis_sharded
+    from vqnerf_release_b200.neus.renderer import NeuSRenderer, render_sharded
+    st = NO.make_neus_state(0)
+    sdf_net = SDFNetwork(d_out=257, d_in=3, d_hidden=256, n_layers=8, skip_in=(4,), multires=6, device=dev)
+    col_net = RenderingNetwork(d_feature=256, mode='idr', d_in=9, d_out=3, d_hidden=256, n_layers=4, multires_view=4,
+                               device=dev)
+    sdf_net.load_state_dict(st['sdf']); col_net.load_state_dict(st['color'])
+    r = NeuSRenderer(None, sdf_net, SingleVarianceNetwork(0.5, device=dev), col_net, 64, 64, 0, 4, 0.0)
+    g = torch.Generator().manual_seed(5)
+    nb = 301
+    o = torch.nn.functional.normalize(torch.randn((nb, 3), generator=g), dim=1).mul(4).to(dev)
+    d = torch.nn.functional.normalize(-o + 0.3 * torch.randn((nb, 3), generator=g).to(dev), dim=1)
+    near, far = torch.full((nb, 1), 2.0, device=dev), torch.full((nb, 1), 6.0, device=dev)
+    bg = torch.ones((1, 3), device=dev)
+    one = r.render(o, d, near, far, 1.0, background_rgb=bg, cos_anneal_ratio=1.0)
+    sh = render_sharded(r, o, d, near, far, 1.0, background_rgb=bg, cos_anneal_ratio=1.0)
+    for kk in ('color_fine', 'weights', 'weight_sum', 'surf', 'depth'):
+        assert torch.equal(one[kk], sh[kk]), 'ray-sharded NeuS render differs in %s' % kk
+    surf = 0.5 * torch.nn.functional.normalize(torch.randn((9, 3), generator=g), dim=1).to(dev)
+    nrm = torch.nn.functional.normalize(surf + 0.3 * torch.randn((9, 3), generator=g).to(dev), dim=1)
+    lx, _ = abi.gen_light_xyz(16, 32)
+    lxyz = torch.as_tensor(lx.reshape(1, -1, 3), dtype=torch.float32).to(dev)
+    lv1 = compute_vis(r, surf, nrm, lxyz, 1.0)
+    lv2 = compute_vis_sharded(r, surf, nrm, lxyz, 1.0)
+    assert torch.equal(lv1, lv2), 'point-sharded light visibility differs'
+    print('rank %d: NeuS ray-sharded render and point-sharded compute_vis bit-identical to one device' % rank, flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if not ok:

@@ -49,3 +49,16 @@ def compute_vis(renderer, surf, normal, lxyz_flat, max_radius, cos_anneal_ratio=
                                   background_rgb=background_rgb, need_color=False)
             abi.neus_lvis_scatter(out['weight_sum'], rows, n, l0, nc, lv)
     return lvis
+
+
+def compute_vis_sharded(renderer, surf, normal, lxyz_flat, max_radius, group=None, dst=None, **kw):
+    """Surface points sharded over the ranks of `group` (contiguous blocks, dist.shard_rows), one gather of the
+    lvis rows at the end (the reference shards whole views over independent processes, gen_geo.py:141-146)."""
+    import torch.distributed as dist
+    from .. import dist as vdist
+    n = surf.reshape(-1, 3).shape[0]
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return compute_vis(renderer, surf, normal, lxyz_flat, max_radius, **kw)
+    lo, hi = vdist.shard_rows(n, dist.get_rank(group), dist.get_world_size(group))
+    local = compute_vis(renderer, surf.reshape(-1, 3)[lo:hi], normal.reshape(-1, 3)[lo:hi], lxyz_flat, max_radius, **kw)
+    return vdist.gather_rows(local, n, group=group, dst=dst)

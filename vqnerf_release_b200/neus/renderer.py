@@ -127,3 +127,25 @@ class NeuSRenderer:
             'gradient_error': ret_fine['gradient_error'], 'inside_sphere': ret_fine['inside_sphere'],
             'surf': ret_fine['surf'], 'depth': ret_fine['depth'],
         }
+
+
+def render_sharded(renderer: NeuSRenderer, rays_o, rays_d, near, far, radius, group=None, dst=None, **kw):
+    """Ray-sharded render (rays are independent given replicated networks): every rank renders the
+    contiguous block dist.shard_rows(n_rays, rank, world) of the SAME ray list and the per-ray outputs are gathered
+    with ONE collective per output tensor (dist.gather_rows; none at world size 1).  Returns the dict of
+    NeuSRenderer.render for all rays (None on ranks != dst when dst is given); 'gradient_error' stays the local
+    shard's scalar."""
+    import torch.distributed as dist
+    from .. import dist as vdist
+    n = rays_o.shape[0]
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return renderer.render(rays_o, rays_d, near, far, radius, **kw)
+    lo, hi = vdist.shard_rows(n, dist.get_rank(group), dist.get_world_size(group))
+    out = renderer.render(rays_o[lo:hi].contiguous(), rays_d[lo:hi].contiguous(), near[lo:hi].contiguous(),
+                          far[lo:hi].contiguous(), radius, **kw)
+    full = {}
+    for k, v in out.items():
+        full[k] = v if v.dim() == 0 else vdist.gather_rows(v.contiguous(), n, group=group, dst=dst)
+    if dst is not None and dist.get_rank(group) != dst:
+        return None
+    return full
