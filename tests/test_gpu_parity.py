@@ -125,6 +125,34 @@ def test_vq_indices_bit_exact(cuda_dev, k):
     _close(out['quantize'], o['quantize'], 'quantize K=%d' % k, rtol=0, atol=1e-6)
 
 
+@pytest.mark.parametrize('n,k', [(4097, 65), (777, 100), (4097, 128), (1, 200), (129, 256), (20000, 257), (3000, 500), (8193, 1024)])
+def test_vq_large_codebook_tensor_core_path(cuda_dev, n, k):
+    """K >= 128, indices only: the tcgen05 kernel (csrc/vq_tc.cu) against the float64 oracle AND against the
+    warp-level kernel (taken when other outputs are requested); duplicated codewords resolve to the first index."""
+    from vqnerf_release_b200 import abi
+    x, cb = _latents(n, k, 77 + k)
+    cb[:, k - 1] = cb[:, 3]                                 # exact duplicate at the far end of the last block
+    cb[:, 130 % k] = cb[:, 5] if k > 130 else cb[:, 130 % k]
+    xt, ct = torch.as_tensor(x).to(cuda_dev), torch.as_tensor(cb).to(cuda_dev)
+    out = abi.vq_assign(xt, ct, want_quantize=False)
+    vq = O.VectorQuantizerEMA(256, k, 0.1, dtype=torch.float64)
+    o = vq(torch.as_tensor(x, dtype=torch.float64), torch.as_tensor(cb, dtype=torch.float64), False)
+    gap = O.top2_gap_rel(o['distances']).numpy()
+    idx, ref = out['indices'].cpu().numpy(), o['encoding_indices'].numpy()
+    mism = idx != ref
+    # an exact duplicate pair has gap 0: the reference picks the lower index and so must the kernel
+    dup_ok = ~np.isin(idx, [k - 1]) & (~np.isin(idx, [130]) if k > 130 else True)
+    assert dup_ok.all(), 'a duplicated codeword was returned instead of its first occurrence'
+    first = np.where(np.isin(ref, [3, 5]))[0]
+    assert (idx[first] == ref[first]).all()
+    assert not (mism & (gap >= 1e-6)).any(), 'K=%d: %d index mismatches outside the 1e-6 tie tolerance' % (
+        k, int((mism & (gap >= 1e-6)).sum()))
+    other = abi.vq_assign(xt, ct, want_quantize=True)['indices'].cpu().numpy()     # vq_mma.cu path
+    d2 = idx != other
+    assert not (d2 & (gap >= 1e-6)).any()
+    assert out['indices'].dtype == torch.int64
+
+
 def test_vq_duplicate_codewords_pick_first(cuda_dev):
     from vqnerf_release_b200 import abi
     x, cb = _latents(512, 15, 3)
@@ -478,7 +506,7 @@ def test_smoke_entry_point(cuda_dev):
     g.smoke()
 
 
-@pytest.mark.parametrize('n,k', [(16 * 1024 * 1024, 15), (4 * 1024 * 1024, 256)])
+@pytest.mark.parametrize('n,k', [(16 * 1024 * 1024, 15), (4 * 1024 * 1024, 256), (4 * 1024 * 1024 + 5, 1024)])
 def test_vq_full_size_known_answer(cuda_dev, n, k):
     """BASELINE configs[2] sizes (oracle-free, size-independent property): every latent is a codeword plus small
     noise, so the assigned index must be the generating codeword; a second assignment of the quantised output is

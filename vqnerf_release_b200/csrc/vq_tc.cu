@@ -1,0 +1,375 @@
+// VQ nearest-codeword assignment for LARGE codebooks (K > 64) on the 5th-gen tensor cores (tcgen05 + TMEM).
+//
+// Reference: networks/vq_layers.py:279-292 (distances ||x||^2 - 2 x.C + ||c||^2, first-minimum arg-min).
+// BASELINE.json configs[2] sweeps K up to 1024, where the assignment is a [n,256] x [256,K] GEMM with an arg-min
+// epilogue and no longer HBM-bound (2 K FLOP against 4 B per latent value).  The warp-level kernel of vq_mma.cu
+// (operands from registers, right for the HBM-bound K <= 64) tops out at ~46 TFLOP/s there; this kernel keeps the
+// 3-term fp32-parity split of mlp_tc.cu (kind::tf32 leading term + ONE kind::f16 bf16 MMA of twice the K for the two
+// correction terms) and the same warp roles:
+//
+//   * a persistent CTA per SM walks tiles of 128 latents; a "layer" is (tile, block of <= 256 codewords);
+//   * 16 producer warps (2 groups) load the tile's K-chunks (128 rows x 32 values) COALESCED, split them into the
+//     tf32 plane + bf16 correction plane of the 128-B-swizzled A slot, and accumulate ||x||^2 on the way;
+//   * one thread streams the pre-split codebook chunk images (cp.async.bulk + mbarrier), one thread issues the MMAs;
+//   * accumulators ping-pong between two 256-column TMEM regions: while the tensor cores fill one region with the
+//     dot products of the next codeword block, the producers drain the other one -- c2 - 2 x.c per codeword, running
+//     (best, runner-up) per row in registers, first-index tie-break;
+//   * after a tile's last block the four partial (best, runner-up) pairs of a row are merged through shared memory;
+//     rows whose two best distances are closer than 4e-5 relative are re-scored in fp64 (warp-cooperative), so the
+//     index is exact whenever the true top-2 gap exceeds the 1e-6 tolerance of BASELINE.json.
+//
+// Indices only (no thres mask, no l2-normalise, no statistics): every other variant stays on vq_mma.cu.
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+#include "vq.cuh"
+
+#define VT_M 128
+#define VT_G 2                               // producer groups of 8 warps
+#define VT_THREADS (32 * (8 * VT_G + 2))
+#define VT_A_PLANE (VT_M * 128u)             // 16 KB
+#define VT_A_SLOT (2u * VT_A_PLANE)          // tf32 plane + bf16 correction plane
+#define VT_W_SLOT (256u * 128u * 2u)         // 64 KB
+#define VT_STAGES 2
+#define VT_KCHUNKS (VQ_Z / 32)               // 8 K-chunks of 32 values
+#define VT_MAXK 1024
+#define VT_SMEM (VT_STAGES * VT_A_SLOT + VT_STAGES * VT_W_SLOT + 1024)
+
+namespace {
+
+struct VtParams {
+  const float* x;          // [n,256]
+  long long n;
+  const float* cb;         // [256,K] fp32 (for the fp64 re-score)
+  int K, nb;               // nb = ceil(K / 256) codeword blocks
+  const uint8_t* wpack;    // block b at wpack + b * (VT_KCHUNKS * VT_W_SLOT): chunk images [Npad_b x 128 B] x 2 planes
+  const float* c2;         // [nb * 256] ||c||^2, +huge for the padding columns
+  long long* idx_out;
+};
+
+struct Top2 { float b, s; int bi, si; };
+
+__device__ __forceinline__ void top2_push(Top2& t, float d, int i) {
+  if (d < t.b) { t.s = t.b; t.si = t.bi; t.b = d; t.bi = i; }
+  else if (d < t.s) { t.s = d; t.si = i; }
+}
+// merge (ob, obi, os, osi) into t; ties go to the lower index (first minimum, tf.argmax(-d))
+__device__ __forceinline__ void top2_merge(Top2& t, float ob, int obi, float os, int osi) {
+  const bool other_first = (ob < t.b) || (ob == t.b && obi < t.bi);
+  float b, s, c1, c2_; int bi, si, i1, i2;
+  if (other_first) { b = ob; bi = obi; c1 = t.b; i1 = t.bi; c2_ = os; i2 = osi; }
+  else { b = t.b; bi = t.bi; c1 = ob; i1 = obi; c2_ = t.s; i2 = t.si; }
+  if ((c1 < c2_) || (c1 == c2_ && i1 < i2)) { s = c1; si = i1; } else { s = c2_; si = i2; }
+  t.b = b; t.bi = bi; t.s = s; t.si = si;
+}
+
+// codebook block -> per K-chunk swizzled images: plane H = tf32 hi [Npad x 32 fp32], plane C = [bf16(hi) x 32 | bf16(lo) x 32]
+// (the layout of mlp_tc.cu's tc_pack_kernel; the codeword is the N row, z the K index), and c2 = ||c||^2
+__global__ void vt_pack_kernel(const float* __restrict__ cb, int K, int nb, uint8_t* __restrict__ wpack,
+                               float* __restrict__ c2) {
+  const long long total = (long long)nb * VT_KCHUNKS * 256 * 32;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int kk = (int)(i % 32);
+    const int nrow = (int)((i / 32) % 256);
+    const int c = (int)((i / (32 * 256)) % VT_KCHUNKS);
+    const int b = (int)(i / (32 * 256 * VT_KCHUNKS));
+    const int nblk = min(256, K - 256 * b), npad = (nblk + 15) / 16 * 16;
+    if (nrow >= npad) continue;
+    const int z = c * 32 + kk, col = 256 * b + nrow;
+    const float v = nrow < nblk ? cb[(size_t)z * K + col] : 0.f;
+    const size_t plane = (size_t)npad * 128;
+    uint8_t* base = wpack + (size_t)b * VT_KCHUNKS * VT_W_SLOT + (size_t)c * 2 * plane;
+    const float hi = tc::tf32_rna(v);
+    *reinterpret_cast<float*>(base + tc::sw128_off(nrow, kk / 4) + (kk % 4) * 4) = hi;
+    uint8_t* pc = base + plane;
+    *reinterpret_cast<__nv_bfloat16*>(pc + tc::sw128_off(nrow, kk / 8) + (kk % 8) * 2) = __float2bfloat16_rn(hi);
+    *reinterpret_cast<__nv_bfloat16*>(pc + tc::sw128_off(nrow, 4 + kk / 8) + (kk % 8) * 2) = __float2bfloat16_rn(v - hi);
+  }
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nb * 256; j += gridDim.x * blockDim.x) {
+    float s = 3.0e38f;                                         // padding columns never win
+    if (j < K) {
+      s = 0.f;
+      for (int z = 0; z < VQ_Z; ++z) { const float v = cb[(size_t)z * K + j]; s = fmaf(v, v, s); }
+    }
+    c2[j] = s;
+  }
+}
+
+// 16 consecutive K values of row r into the A slot (tf32 hi plane + [bf16(lo) | bf16(hi)] plane), as mlp_tc.cu
+__device__ __forceinline__ void vt_store16(uint8_t* slot, int r, int j0, const float (&v)[16]) {
+  uint8_t* row = slot + r * 128;
+  const uint32_t rx = (uint32_t)(r & 7);
+#pragma unroll
+  for (int qq = 0; qq < 2; ++qq) {
+    float h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { h[i] = tc::tf32_rna(v[8 * qq + i]); l[i] = v[8 * qq + i] - h[i]; }
+    const uint32_t c0 = (uint32_t)(j0 / 4 + 2 * qq);
+    *reinterpret_cast<float4*>(row + (((c0) ^ rx) << 4)) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(row + (((c0 + 1) ^ rx) << 4)) = make_float4(h[4], h[5], h[6], h[7]);
+    uint4 ul, uh;
+    __nv_bfloat162 t0 = __floats2bfloat162_rn(l[0], l[1]), t1 = __floats2bfloat162_rn(l[2], l[3]);
+    __nv_bfloat162 t2 = __floats2bfloat162_rn(l[4], l[5]), t3 = __floats2bfloat162_rn(l[6], l[7]);
+    ul.x = *reinterpret_cast<uint32_t*>(&t0); ul.y = *reinterpret_cast<uint32_t*>(&t1);
+    ul.z = *reinterpret_cast<uint32_t*>(&t2); ul.w = *reinterpret_cast<uint32_t*>(&t3);
+    t0 = __floats2bfloat162_rn(h[0], h[1]); t1 = __floats2bfloat162_rn(h[2], h[3]);
+    t2 = __floats2bfloat162_rn(h[4], h[5]); t3 = __floats2bfloat162_rn(h[6], h[7]);
+    uh.x = *reinterpret_cast<uint32_t*>(&t0); uh.y = *reinterpret_cast<uint32_t*>(&t1);
+    uh.z = *reinterpret_cast<uint32_t*>(&t2); uh.w = *reinterpret_cast<uint32_t*>(&t3);
+    const uint32_t cc = (uint32_t)(j0 / 8 + qq);
+    *reinterpret_cast<uint4*>(row + VT_A_PLANE + ((cc ^ rx) << 4)) = ul;
+    *reinterpret_cast<uint4*>(row + VT_A_PLANE + (((cc + 4) ^ rx) << 4)) = uh;
+  }
+}
+
+__device__ __forceinline__ void vt_group_bar(int grp) { asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory"); }
+
+__global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_constant__ VtParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[VT_STAGES], a_empty[VT_STAGES], w_full[VT_STAGES], w_empty[VT_STAGES];
+  __shared__ __align__(8) uint64_t acc_full[2], drain_done[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float c2_s[VT_MAXK];
+  __shared__ __align__(16) float4 merge_s[2][VT_M * 4];      // Top2 of the 4 threads of a row, double-buffered by tile
+  __shared__ float xs_s[2][VT_M * 4];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_ring = smem;
+  uint8_t* w_ring = smem + (size_t)VT_STAGES * VT_A_SLOT;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int MMA_WARP = 8 * VT_G, W_WARP = 8 * VT_G + 1;
+
+  if (warp == MMA_WARP) tc::tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) {
+    for (int i = 0; i < VT_STAGES; ++i) {
+      tc::mbar_init(&a_full[i], 256); tc::mbar_init(&a_empty[i], 1);
+      tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&drain_done[i], 256 * VT_G); }
+    tc::mbar_fence_init();
+  }
+  for (int i = tid; i < p.nb * 256; i += VT_THREADS) c2_s[i] = p.c2[i];
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+  const long long n_tiles = (p.n + VT_M - 1) / VT_M;
+  const int nb = p.nb;
+
+  if (warp < 8 * VT_G) {
+    // ===================== producers: A chunks, accumulator drain, arg-min =====================
+    const int grp = warp >> 3, half = (warp >> 2) & 1, tg = tid & 255;
+    const int r = 32 * (warp & 3) + lane;                          // TMEM lane == latent row of the tile
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+    uint32_t ga = 0, gk = 0;                                       // global chunk / layer counters
+    Top2 t2 = {3.0e38f, 3.0e38f, 0, 0};
+    float xs = 0.f, xs_fin = 0.f;
+    long long pend_tile = -1; int pend_b = 0; uint32_t pend_k = 0; uint32_t tiles_done = 0;
+
+    auto drain = [&](long long tile, int b, uint32_t k) {
+      const int region = (int)(k & 1u);
+      tc::mbar_wait(&acc_full[region], (k >> 1) & 1u);
+      tc::fence_after_sync();
+      const int nblk = min(256, p.K - 256 * b), npad = (nblk + 15) / 16 * 16;
+      const float* c2b = c2_s + 256 * b;
+      for (int cbk = grp; cbk * 32 < npad; cbk += VT_G) {
+        const int c16 = cbk * 32 + 16 * half;
+        if (c16 < npad) {
+          float v[16];
+          tc::tmem_ld16(lane_addr + (uint32_t)(region * 256 + c16), v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) top2_push(t2, fmaf(-2.0f, v[j], c2b[c16 + j]), 256 * b + c16 + j);
+        }
+      }
+      tc::fence_before_sync();
+      tc::mbar_arrive(&drain_done[region]);
+      if (b + 1 < nb) return;
+      // ---- last block of the tile: merge the 4 partial results of each row, re-score near-ties, write the index ----
+      const int buf = (int)(tiles_done & 1u);
+      ++tiles_done;
+      merge_s[buf][r * 4 + grp * 2 + half] = make_float4(t2.b, t2.s, __int_as_float(t2.bi), __int_as_float(t2.si));
+      xs_s[buf][r * 4 + grp * 2 + half] = xs_fin;
+      t2.b = 3.0e38f; t2.s = 3.0e38f; t2.bi = 0; t2.si = 0;
+      asm volatile("bar.sync 3, %0;" ::"r"(256 * VT_G) : "memory");
+      if (grp == 0 && half == 0) {
+        Top2 m = {3.0e38f, 3.0e38f, 0x7fffffff, 0x7fffffff};
+        float xsum = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 e = merge_s[buf][r * 4 + q];
+          top2_merge(m, e.x, __float_as_int(e.z), e.y, __float_as_int(e.w));
+          xsum += xs_s[buf][r * 4 + q];
+        }
+        const long long row = tile * VT_M + r;
+        const bool ok = row < p.n;
+        int best = m.bi;
+        const float full = m.b + xsum;                            // the reference's distance of the winner
+        const bool near = ok && p.K > 1 && (m.s - m.b) <= 4e-5f * fmaxf(fabsf(full), 1e-3f);
+        unsigned need = __ballot_sync(0xffffffffu, near);
+        while (need) {                                            // warp-uniform: fp64 re-score of the two candidates
+          const int src = __ffs(need) - 1;
+          need &= need - 1;
+          const long long rrow = tile * VT_M + 32 * (warp & 3) + src;
+          const int i1 = __shfl_sync(0xffffffffu, m.bi, src), i2 = __shfl_sync(0xffffffffu, m.si, src);
+          double d1 = 0.0, d2 = 0.0;
+#pragma unroll
+          for (int mm = 0; mm < 8; ++mm) {
+            const int z = lane + 32 * mm;
+            const double xv = (double)p.x[rrow * VQ_Z + z];
+            const double c1 = (double)p.cb[(size_t)z * p.K + i1], c2v = (double)p.cb[(size_t)z * p.K + i2];
+            d1 += c1 * c1 - 2.0 * xv * c1;
+            d2 += c2v * c2v - 2.0 * xv * c2v;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+            d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+          }
+          const bool swap = (d2 < d1) || (d2 == d1 && i2 < i1);
+          if (swap && lane == src) best = i2;
+        }
+        if (ok) p.idx_out[row] = (long long)best;
+      }
+    };
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int b = 0; b < nb; ++b, ++gk) {
+        for (int c = 0; c < VT_KCHUNKS; ++c, ++ga) {
+          if ((int)(ga % VT_G) != grp) continue;
+          const int slot = (int)(ga % VT_STAGES);
+          uint8_t* dst = a_ring + (size_t)slot * VT_A_SLOT;
+          // coalesced load of the chunk (a warp reads 4 rows x 128 B per instruction), issued BEFORE the slot is claimed.
+          // (Keeping the group's next chunk in flight across the drain was measured slower: 9.6 -> 11.4 ms at K = 1024,
+          // the extra live registers spill inside the arg-min loop.)
+          float4 ldv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int f = tg + 256 * i, rr = f >> 3, ch = f & 7;
+            const long long prow = tile * VT_M + rr;
+            ldv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (prow < p.n) ldv[i] = __ldg(reinterpret_cast<const float4*>(p.x + prow * VQ_Z + c * 32 + 4 * ch));
+          }
+          tc::mbar_wait(&a_empty[slot], ((ga / VT_STAGES) & 1u) ^ 1u);
+          uint8_t* stage = dst + VT_A_PLANE;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int f = tg + 256 * i, rr = f >> 3, ch = f & 7;
+            *reinterpret_cast<float4*>(stage + rr * 128 + ((ch ^ (rr & 7)) << 4)) = ldv[i];
+          }
+          vt_group_bar(grp);
+          float v[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 t = *reinterpret_cast<const float4*>(stage + r * 128 + (((4 * half + q) ^ (r & 7)) << 4));
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+          }
+          vt_group_bar(grp);                                     // every row has been read before plane C is overwritten
+          if (b == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) xs = fmaf(v[j], v[j], xs);
+          }
+          vt_store16(dst, r, 16 * half, v);
+          tc::fence_proxy_async();
+          tc::fence_before_sync();
+          tc::mbar_arrive(&a_full[slot]);
+        }
+        // the previous layer is drained while the tensor cores work on this one
+        if (pend_tile >= 0) drain(pend_tile, pend_b, pend_k);
+        pend_tile = tile; pend_b = b; pend_k = gk;
+        if (b == nb - 1) { xs_fin = xs; xs = 0.f; }
+        else if (b == 0 && nb > 1) { /* xs complete after block 0; kept until the tile's last drain */ }
+      }
+    }
+    if (pend_tile >= 0) drain(pend_tile, pend_b, pend_k);
+  } else if (warp == MMA_WARP) {
+    if (lane == 0) {
+      uint32_t ga = 0, gk = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int b = 0; b < nb; ++b, ++gk) {
+          const int region = (int)(gk & 1u);
+          const int nblk = min(256, p.K - 256 * b), npad = (nblk + 15) / 16 * 16;
+          const uint32_t idesc = tc::make_idesc(tc::FMT_TF32, VT_M, npad);
+          const uint32_t idesc_c = tc::make_idesc(tc::FMT_BF16, VT_M, npad);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(region * 256);
+          const uint32_t w_plane = (uint32_t)npad * 128;
+          if (gk >= 2) {                                          // the drain of the layer that used this region
+            tc::mbar_wait(&drain_done[region], ((gk - 2) >> 1) & 1u);
+            tc::fence_after_sync();
+          }
+          uint32_t acc = 0;
+          for (int c = 0; c < VT_KCHUNKS; ++c, ++ga) {
+            const int s_ = (int)(ga % VT_STAGES);
+            tc::mbar_wait(&a_full[s_], (ga / VT_STAGES) & 1u);
+            tc::mbar_wait(&w_full[s_], (ga / VT_STAGES) & 1u);
+            tc::fence_after_sync();
+            const uint32_t a_addr = tc::smem_u32(a_ring + (size_t)s_ * VT_A_SLOT);
+            const uint32_t w_addr = tc::smem_u32(w_ring + (size_t)s_ * VT_W_SLOT);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+              tc::mma_ss<true>(d_tmem, tc::make_desc_sw128(a_addr + 32 * s), tc::make_desc_sw128(w_addr + 32 * s), idesc, acc);
+              acc = 1;
+              tc::mma_ss<false>(d_tmem, tc::make_desc_sw128(a_addr + VT_A_PLANE + 32 * s),
+                                tc::make_desc_sw128(w_addr + w_plane + 32 * s), idesc_c, 1);
+            }
+            tc::mma_commit(&a_empty[s_]);
+            tc::mma_commit(&w_empty[s_]);
+          }
+          tc::mma_commit(&acc_full[region]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == W_WARP) {
+    if (lane == 0) {
+      uint32_t gw = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int b = 0; b < nb; ++b) {
+          const int nblk = min(256, p.K - 256 * b), npad = (nblk + 15) / 16 * 16;
+          const uint32_t bytes = (uint32_t)npad * 128 * 2;
+          const uint8_t* wb = p.wpack + (size_t)b * VT_KCHUNKS * VT_W_SLOT;
+          for (int c = 0; c < VT_KCHUNKS; ++c, ++gw) {
+            const int s_ = (int)(gw % VT_STAGES);
+            tc::mbar_wait(&w_empty[s_], ((gw / VT_STAGES) & 1u) ^ 1u);
+            tc::mbar_expect_tx(&w_full[s_], bytes);
+            tc::bulk_g2s(w_ring + (size_t)s_ * VT_W_SLOT, wb + (size_t)c * bytes, bytes, &w_full[s_]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == MMA_WARP) tc::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+// library-owned pack buffers (one set per context would need a ctx field; the codebook images are rebuilt on every
+// call, stream-ordered, so one process-wide set per device is enough)
+int vq_tc_min_k() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VQN_VQ_TC_MIN_K"); v = e ? atoi(e) : 65; if (v < 16) v = 16; }
+  return v;
+}
+static uint8_t* g_vt_wpack[16] = {nullptr};
+static float* g_vt_c2[16] = {nullptr};
+
+int vq_tc_assign_launch(vqn_ctx* ctx, const VqParams& q, cudaStream_t s) {
+  const int dev = ctx->device & 15;
+  if (!g_vt_wpack[dev]) {
+    VQN_CUDA(cudaMalloc(&g_vt_wpack[dev], (size_t)4 * VT_KCHUNKS * VT_W_SLOT));
+    VQN_CUDA(cudaMalloc(&g_vt_c2[dev], sizeof(float) * VT_MAXK));
+  }
+  VtParams p;
+  p.x = q.x; p.n = q.n; p.cb = q.cb; p.K = q.K; p.nb = (q.K + 255) / 256;
+  p.wpack = g_vt_wpack[dev]; p.c2 = g_vt_c2[dev]; p.idx_out = q.idx_out;
+  vt_pack_kernel<<<256, 256, 0, s>>>(q.cb, q.K, p.nb, g_vt_wpack[dev], g_vt_c2[dev]);
+  VQN_LAUNCHED(ctx);
+  const long long tiles = (q.n + VT_M - 1) / VT_M;
+  const int blocks = (int)(tiles < (long long)ctx->sm_count ? tiles : (long long)ctx->sm_count);
+  VQN_CUDA(cudaFuncSetAttribute(vq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VT_SMEM));
+  vq_tc_kernel<<<blocks, VT_THREADS, VT_SMEM, s>>>(p);
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}
