@@ -142,11 +142,12 @@ def ncu_traffic(n, probes, precision):
         if (w['points'], w['probes'], w['precision']) != (n, probes, precision):
             return None
         k = d['per_launch_dram_bytes']
-        enc, heads = k['mlp_tc_kernel<tf32x3> encoder launch'], k['mlp_tc_kernel<tf32x3> heads launch']
-        return {'bytes': enc['read'] + enc['write'] + heads['read'] + heads['write'],
-                'note': 'dram__bytes_read.sum + dram__bytes_write.sum of the encoder launch + the heads launch '
-                        '(the latent z [n,256] fp32 = 655 MB is written by the first and read by the second; '
-                        'weights stay in L2); algorithmic bytes of the fused pair: 40 B/point = 25.6 MB',
+        f = k['mlp_tc_kernel<tf32x3> encoder+heads, ONE launch (r1f, per-CTA L2-resident latent scratch)']
+        return {'bytes': f['read'] + f['write'],
+                'note': 'dram__bytes_read.sum + dram__bytes_write.sum of the single encoder+heads launch: the latent z '
+                        '[128,256] tile of a CTA goes through a per-CTA scratch that stays in L2 (the two-launch form '
+                        'moved 1.28 GB per view); reads = xyz + weights, the 17.9 MB of outputs were still in L2 when '
+                        'the kernel ended; algorithmic bytes: 40 B/point = 25.6 MB',
                 'source': 'profiles/r1e_ncu_traffic.json'}
     except Exception:
         return None
@@ -598,7 +599,7 @@ def run_ours(args):
             # tf32 tensor rate = bf16 / 2; three MMAs per product in the 3xTF32 split
             peak = bf16_peak if args.precision == 'bf16' else bf16_peak / 2 / 3
             ach = MLP_FLOP * n / (mlp_ms * 1e-3) / 1e12
-            roof = {'bound': 'tensor', 'kernel': 'mlp_tc_kernel<%s> (encoder launch + heads launch, 953 600 FLOP/point)' % args.precision,
+            roof = {'bound': 'tensor', 'kernel': 'mlp_tc_kernel<%s> (encoder + bottleneck + 3 heads in one launch, 953 600 FLOP/point)' % args.precision,
                     'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s (fp32-equivalent algorithmic FLOPs)', 'frac': ach / peak,
                     'peak_source': 'bf16 cuBLAS peak %.0f TFLOP/s %s%s; FFMA peak measured live: %.1f TFLOP/s' % (
                         bf16_peak, peak_src, '' if args.precision == 'bf16' else ' / 2 (tf32 rate) / 3 (hi/lo split MMAs)', fp32_peak),
@@ -616,8 +617,8 @@ def run_ours(args):
                 roof['frac_of_executed_scheme_peak'] = ach / (bf16_peak / 4)
                 roof['executed_scheme_note'] = ('peak above = three kind::tf32 MMAs per product (the plain 3xTF32 split); the '
                                                 'kernel issues 1 tf32 + 1 bf16(K=16) MMA per 8 K-values = bf16 peak / 4 = '
-                                                '%.0f TFLOP/s fp32-equivalent; ncu sm__pipe_tensor_cycles_active: encoder '
-                                                'launch 28 %%, heads launch 34 %% (profiles/r1e_ncu_traffic.json)'
+                                                '%.0f TFLOP/s fp32-equivalent; ncu sm__pipe_tensor_cycles_active of the fused '
+                                                'launch: 31 %% (profiles/r1f_ncu_full_mlp_tc_fused.txt)'
                                                 % (bf16_peak / 4))
         shade_bytes = n * (2048 + 36 + 28 + 12 * (1 + P))
         kernels = {

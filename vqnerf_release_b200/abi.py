@@ -139,15 +139,26 @@ def mlp_main(fine_enc: PackedNet, bottleneck: PackedNet, diff: PackedNet, spec: 
     pts = _f(pts)
     n = pts.shape[0] if n is None else n
     dev = pts.device
-    # the tensor-core modes stage the latent in z (two launches: encoder, heads); fp32 keeps it on chip
-    stage_z = want_z or L.precision_code(precision) != L.PREC_FP32
-    z = torch.empty((n, bottleneck.out_dim), dtype=F32, device=dev) if stage_z else None
+    # the latent stays on chip (fp32: shared memory; tensor-core modes: a per-CTA L2-resident scratch tile) unless the
+    # caller wants it; network shapes the fused tensor-core program does not cover fall back to two launches staged in z
     outs = [torch.empty((n, h.out_dim), dtype=F32, device=dev) for h in (diff, spec, rough)]
     c = _ctx(pts)
-    L.check(c.lib.vqn_mlp_main(c.handle, fine_enc.handle, bottleneck.handle, diff.handle, spec.handle, rough.handle,
-                               n_freqs, L.ptr(pts), L.ptr(row_idx, torch.int32), L.ptr(n_dev, torch.int32), n,
-                               float(slope), float(bias), L.ptr(z), *(L.ptr(o) for o in outs),
-                               L.precision_code(precision), L.stream_ptr(dev)))
+
+    def launch(z):
+        L.check(c.lib.vqn_mlp_main(c.handle, fine_enc.handle, bottleneck.handle, diff.handle, spec.handle, rough.handle,
+                                   n_freqs, L.ptr(pts), L.ptr(row_idx, torch.int32), L.ptr(n_dev, torch.int32), n,
+                                   float(slope), float(bias), L.ptr(z), *(L.ptr(o) for o in outs),
+                                   L.precision_code(precision), L.stream_ptr(dev)))
+
+    z = torch.empty((n, bottleneck.out_dim), dtype=F32, device=dev) if want_z else None
+    try:
+        launch(z)
+    except NotImplementedError as e:
+        if z is not None or 'z_out buffer is required' not in str(e):
+            raise
+        z = torch.empty((n, bottleneck.out_dim), dtype=F32, device=dev)
+        launch(z)
+        z = None
     return (z,) + tuple(outs)
 
 

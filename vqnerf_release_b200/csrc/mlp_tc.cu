@@ -70,6 +70,12 @@ struct TcProgram {
   long long n;
   float* outs[4];
   int out_stride[4];
+  // Per-CTA latent scratch (vqn_tc_mlp_main): the GLOBAL source / output slot `local_slot` is a [128, g_dim] tile PER CTA
+  // (gsrc + blockIdx.x * 128 * g_dim), written by the final drain of the bottleneck and re-read by the heads of the
+  // SAME tile -- 148 x 128 KB stay in L2, so the latent never travels to HBM and encoder + heads are one launch.
+  // out_dup: optional [n, g_dim] global copy of that slot (callers that want z).
+  int g_local, local_slot;
+  float* out_dup;
   // Jet mode (vqn_sdf_forward with grad_out): a tile is 32 points x 4 rows -- row 4p is the value of point p, rows
   // 4p+1..4p+3 its derivatives with respect to x, y, z; every layer is linear in the tangent rows and the activation
   // multiplies them by act'(pre-activation of the value row), fetched from the neighbouring TMEM lane by a shuffle.
@@ -209,7 +215,7 @@ struct TcCfg {
   static constexpr uint32_t W_SLOT = (uint32_t)TC_NPAD_MAX * 128 * PLANES;
   static constexpr size_t SMEM = (size_t)SA * A_SLOT + (size_t)SW * W_SLOT + 1024;
 };
-#define TC_BIAS_FLOATS 6144
+#define TC_BIAS_FLOATS 7168
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
@@ -496,8 +502,11 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                 const int f = tg + 256 * i, rr = f >> 3, ch = f & 7;
                 const long long prow = tile * TC_M + rr;
                 ldv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (prow < n && col_base + 4 * ch < pg.g_dim)
-                  ldv[i] = __ldg(reinterpret_cast<const float4*>(pg.gsrc + prow * pg.g_dim + col_base + 4 * ch));
+                if (prow < n && col_base + 4 * ch < pg.g_dim) {
+                  // per-CTA scratch: written earlier in this kernel by other threads -> L2-coherent load, no L1 line
+                  if (pg.g_local) ldv[i] = __ldcg(reinterpret_cast<const float4*>(pg.gsrc + ((size_t)blockIdx.x * TC_M + rr) * pg.g_dim + col_base + 4 * ch));
+                  else ldv[i] = __ldg(reinterpret_cast<const float4*>(pg.gsrc + prow * pg.g_dim + col_base + 4 * ch));
+                }
               }
               if (ptr_) ptr_[1] = clock64();
               tc::mbar_wait(&a_empty[slot], ((ga / C::SA) & 1) ^ 1);
@@ -536,10 +545,11 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                   else bias_act32_dyn(v, pbias + col0, pact);
                 } else {                                  // SRC_GLOBAL (bf16 mode): this thread's own latent row
                   if (valid && col0 < pg.g_dim) {
-                    const float4* src = reinterpret_cast<const float4*>(pg.gsrc + pi * pg.g_dim + col0);
+                    const float4* src = reinterpret_cast<const float4*>(
+                        pg.gsrc + (pg.g_local ? (size_t)blockIdx.x * TC_M + r : (size_t)pi) * pg.g_dim + col0);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                      float4 t = src[j];
+                      float4 t = pg.g_local ? __ldcg(src + j) : src[j];
                       v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
                     }
                   } else {
@@ -635,6 +645,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
           const TcLayer& ly = pg.layers[l];
           tc::mbar_wait(&acc_full, (gl - 1) & 1);
           tc::fence_after_sync();
+          const bool local = pg.g_local && ly.out_slot == pg.local_slot;     // per-CTA scratch tile (wide path only)
           float* go = pg.outs[ly.out_slot];
           const int gs = pg.out_stride[ly.out_slot];
           const float* lb = bias_s + ly.bias_off;
@@ -686,15 +697,26 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
               for (int i = 0; i < 4; ++i) {
                 const int f = tg + 256 * i, rr = f >> 3, ch = f & 7;
                 const long long prow = tile * tile_pts + (jet ? (rr >> 2) : rr);
-                if (prow < n && (!jet || (rr & 3) == 0))
-                  *reinterpret_cast<float4*>(go + (size_t)prow * gs + cb * 32 + 4 * ch) =
-                      *reinterpret_cast<const float4*>(stage + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                if (prow < n && (!jet || (rr & 3) == 0)) {
+                  const float4 val = *reinterpret_cast<const float4*>(stage + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                  if (local) {
+                    *reinterpret_cast<float4*>(go + ((size_t)blockIdx.x * TC_M + rr) * gs + cb * 32 + 4 * ch) = val;
+                    if (pg.out_dup) *reinterpret_cast<float4*>(pg.out_dup + (size_t)prow * gs + cb * 32 + 4 * ch) = val;
+                  } else {
+                    *reinterpret_cast<float4*>(go + (size_t)prow * gs + cb * 32 + 4 * ch) = val;
+                  }
+                }
               }
               group_bar(grp);
             }
           }
           tc::fence_before_sync();
           tc::mbar_arrive(&drain_done);     // the MMA thread may now reuse this TMEM region
+          if (local) {
+            // the heads' producers (all 512 threads) re-read this tile from the scratch: CTA-wide visibility
+            __threadfence_block();
+            asm volatile("bar.sync 3, %0;" ::"r"(256 * C::G) : "memory");
+          }
         }
       }
     }
@@ -943,14 +965,53 @@ int vqn_tc_pred_heads(vqn_ctx* ctx, vqn_net* diff, vqn_net* spec, vqn_net* rough
   return tc_launch(ctx, B.pg, precision, s);
 }
 
-// encoder then heads: two launches of the same kernel; the latent round-trips through z_out (L2-resident per tile)
+// encoder + bottleneck + three heads in ONE launch.  The latent tile of a CTA ([128, z_dim] fp32) goes through a per-CTA
+// scratch (sm_count x 128 KB, L2-resident) between the bottleneck's final drain and the heads' layer-0 producers: it
+// never travels to HBM (the two-launch form wrote and re-read 1 KB per point: 1.3 GB per 800 x 800 view) unless the
+// caller asks for z (z_out != NULL: a second, streaming store).
+static float* g_tc_zscratch[16] = {nullptr};
 int vqn_tc_mlp_main(vqn_ctx* ctx, vqn_net* fe, vqn_net* bn, vqn_net* diff, vqn_net* spec, vqn_net* rough, int n_freqs,
                     const float* pts, const int32_t* row_idx, const int32_t* n_dev, int64_t n, float slope, float bias,
                     float* z_out, float* d, float* sp, float* r, int precision, cudaStream_t s) {
-  if (!z_out) TC_UNSUPPORTED("mlp_main (tensor-core modes): z_out buffer is required (the latent is staged there)");
-  int rc = vqn_tc_pred_enc_at(ctx, fe, bn, n_freqs, pts, row_idx, n_dev, n, z_out, precision, s);
+  const int z_dim = bn->desc.widths[bn->n_layers - 1];
+  vqn_net* nets[3] = {diff, spec, rough};
+  float* outs[3] = {d, sp, r};
+  bool fusable = z_dim % 32 == 0 && z_dim <= TC_NPAD_MAX && fe->n_layers + bn->n_layers + 6 <= TC_MAX_LAYERS;
+  for (int h = 0; h < 3; ++h) {
+    const vqn_net_desc& hd = nets[h]->desc;
+    fusable = fusable && nets[h]->in_dim == z_dim && hd.n_layers == 3 && hd.skip_at == 1 && hd.widths[0] <= 256 &&
+              hd.widths[1] <= 128 && hd.widths[2] <= 4;
+  }
+  if (!fusable) {                                 // generic shapes: two launches, the latent staged in z_out
+    if (!z_out) TC_UNSUPPORTED("mlp_main (tensor-core modes): z_out buffer is required for this network shape");
+    int rc = vqn_tc_pred_enc_at(ctx, fe, bn, n_freqs, pts, row_idx, n_dev, n, z_out, precision, s);
+    if (rc != VQN_OK) return rc;
+    return vqn_tc_pred_heads(ctx, diff, spec, rough, z_out, n_dev, n, slope, bias, d, sp, r, precision, s);
+  }
+  const int dev = ctx->device & 15;
+  if (!g_tc_zscratch[dev]) VQN_CUDA(cudaMalloc(&g_tc_zscratch[dev], sizeof(float) * (size_t)ctx->sm_count * TC_M * TC_NPAD_MAX));
+  TcPack *t0, *t1;
+  int rc = tc_pack_get(fe, precision, s, &t0);
   if (rc != VQN_OK) return rc;
-  return vqn_tc_pred_heads(ctx, diff, spec, rough, z_out, n_dev, n, slope, bias, d, sp, r, precision, s);
+  rc = tc_pack_get(bn, precision, s, &t1);
+  if (rc != VQN_OK) return rc;
+  TcBuilder B(precision);
+  B.pg.pts = pts; B.pg.row_idx = row_idx; B.pg.n_dev = n_dev; B.pg.n = n; B.pg.n_freqs = n_freqs;
+  B.pg.gsrc = g_tc_zscratch[dev]; B.pg.g_dim = z_dim; B.pg.g_local = 1; B.pg.local_slot = 3; B.pg.out_dup = z_out;
+  B.pg.outs[3] = g_tc_zscratch[dev]; B.pg.out_stride[3] = z_dim;
+  bool ok = tc_append_net(B, fe, t0, SRC_EMBED, -1, 1.f, 0.f) && tc_append_net(B, bn, t1, SRC_DRAIN, 3, 1.f, 0.f);
+  for (int h = 0; ok && h < 3; ++h) {
+    TcPack* tp;
+    rc = tc_pack_get(nets[h], precision, s, &tp);
+    if (rc != VQN_OK) return rc;
+    B.pg.outs[h] = outs[h]; B.pg.out_stride[h] = nets[h]->desc.widths[nets[h]->n_layers - 1];
+    const int l0 = B.pg.n_layers;
+    ok = tc_append_net(B, nets[h], tp, SRC_GLOBAL, h, h == 0 ? slope : 1.f, h == 0 ? bias : 0.f, true);
+    if (ok && B.pg.n_layers - l0 == 2) { B.pg.layers[l0].tmem_col = 0; B.pg.layers[l0 + 1].tmem_col = 256; }
+    else ok = false;
+  }
+  if (!ok) TC_UNSUPPORTED("mlp_main: program does not fit the tensor-core kernel");
+  return tc_launch(ctx, B.pg, precision, s);
 }
 
 // SDFNetwork (geo/NeuS-ours2/models/fields.py:74-112): trunk (lin0 .. lin{L-2}, softplus) -> narrow tail = output 0 (sdf,
