@@ -234,6 +234,15 @@ __global__ void act_grad_kernel(const float* __restrict__ dy, long long lddy, co
 
 }  // namespace
 
+// train_tc.cu: the same two contracts on tcgen05/TMEM (taken from vqn_dense_tc_min_m() rows upwards)
+long long vqn_dense_tc_min_m();
+int vqn_dense_tc_forward(vqn_ctx* ctx, const float* x, long long ldx, const float* w, const float* b, float* y,
+                         long long ldy, long long m, int k, int n, int act, float out_scale, float out_bias,
+                         cudaStream_t s);
+int vqn_dense_tc_backward_data(vqn_ctx* ctx, const float* dz, long long lddz, const float* w, float* dx, long long lddx,
+                               const float* yprev, long long ldyp, int act_prev, int accumulate, long long m, int k,
+                               int n, cudaStream_t s);
+
 /* mlp.py:44-46: Y[M,N] (ld ldy) = out_scale * act(X[M,K] (ld ldx) . W[K,N] + b[N]) + out_bias */
 extern "C" int vqn_dense_forward(vqn_ctx* ctx, const float* x, int64_t ldx, const float* w, const float* b, float* y,
                                  int64_t ldy, int64_t m, int k, int n, int act, float out_scale, float out_bias,
@@ -241,6 +250,12 @@ extern "C" int vqn_dense_forward(vqn_ctx* ctx, const float* x, int64_t ldx, cons
   VQN_CHECK_ARG(ctx && x && w && y, "dense_forward: null pointer");
   VQN_CHECK_ARG(m >= 0 && k > 0 && n > 0 && ldx >= k && ldy >= n, "dense_forward: bad shape");
   if (m == 0) return VQN_OK;
+  // measured per layer at 8192 rows (benchmarks/dense_micro.py, CUDA-graph replay): the tcgen05 kernel wins only on the
+  // wide layers (k = n = 256: 18 us vs 29 us); its fixed costs (132 KB smem carve-out, TMEM allocation, un-coalesced
+  // row-per-thread operand loads) lose on the narrow ones (k = 63: 12 us vs 8 us).  VQN_DENSE_TC_MIN_M=1 forces it.
+  const long long tc_min = vqn_dense_tc_min_m();
+  if (tc_min >= 0 && m >= tc_min && (tc_min <= 1 || (k >= 192 && n >= 192)))
+    return vqn_dense_tc_forward(ctx, x, ldx, w, b, y, ldy, m, k, n, act, out_scale, out_bias, vqn_cs(stream));
   GemmParams p = {};
   p.A = x; p.lda = ldx; p.B = w; p.ldb = n; p.C = y; p.ldc = ldy; p.M = (int)m; p.N = n; p.K = k;
   p.bias = b; p.act = act; p.out_scale = out_scale; p.out_bias = out_bias;
@@ -258,6 +273,9 @@ extern "C" int vqn_dense_backward_data(vqn_ctx* ctx, const float* dz, int64_t ld
   VQN_CHECK_ARG(m >= 0 && k > 0 && n > 0 && lddz >= n && lddx >= k, "dense_backward_data: bad shape");
   VQN_CHECK_ARG(act_prev == VQN_ACT_NONE || yprev, "dense_backward_data: act_prev needs yprev");
   if (m == 0) return VQN_OK;
+  if (vqn_dense_tc_min_m() == 1)      // never faster than the warp-level kernel at the training sizes (27 vs 22-32 us)
+    return vqn_dense_tc_backward_data(ctx, dz, lddz, w, dx, lddx, yprev, ldyp, act_prev, accumulate, m, k, n,
+                                      vqn_cs(stream));
   GemmParams p = {};
   p.A = dz; p.lda = lddz; p.B = w; p.ldb = n; p.C = dx; p.ldc = lddx; p.M = (int)m; p.N = k; p.K = n;
   p.yprev = yprev; p.ldy = ldyp; p.act_prev = act_prev; p.accumulate = accumulate;

@@ -1,0 +1,262 @@
+// Dense-layer forward and backward-data of the training step on the 5th-gen tensor cores (tcgen05 + TMEM).
+//
+// Reference: networks/mlp.py:44-48 under tf.GradientTape (train_nfr.py:562-576).  Same contract as the warp-level
+// kernels of train_dense.cu (vqn_dense_forward / vqn_dense_backward_data: arbitrary leading dimensions so layers read
+// and write slices of the skip-connection concat buffers, activations kept / act' taken from the stored activation),
+// same 3-term fp32-parity split (kind::tf32 leading term + ONE kind::f16 bf16 MMA of twice the K for both correction
+// terms), but the products run as M = 128 UMMAs with the accumulator in TMEM:
+//
+//   C[M, N] = epilogue( A[M, K] . B[K, N] )      forward:  A = X,  B = W          epilogue: act(. + b) * scale + bias
+//                                                 bwd data: A = dZ, B = W^T        epilogue: . * act'(Y_prev) (+= dX)
+//
+// One CTA per (128-row block, 128-column block).  Neither operand is pre-packed (the weights change every step and the
+// C ABI takes plain pointers): of each 256-thread producer group, 128 threads own an A row and 128 threads a B row of
+// the current 32-wide K chunk; they load their 32 values, split them (tf32 hi plane + bf16 correction plane) into the
+// 128-B-swizzled K-major slot and hand it to the MMA thread through mbarriers; two groups alternate chunks.
+// Measured at 8192 rows (benchmarks/dense_micro.py): 12-18 us forward, 15-32 us backward-data per layer against 8-29 /
+// 11-32 us on the mma.sync path: a win only on the 256 x 256 layers (18 vs 29 us), which is where vqn_dense_forward
+// routes to it.  The batch of a training step is too small for per-layer tensor-core kernels to pay off; the next step
+// is the fused multi-layer form of mlp_tc.cu with activation saves.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+#define DT_M 128
+#define DT_N 128
+#define DT_PLANE (128u * 128u)                 // 16 KB: 128 rows x 128 B
+#define DT_OPERAND (2u * DT_PLANE)             // tf32 plane + bf16 correction plane
+#define DT_SLOT (2u * DT_OPERAND)              // A + B
+#define DT_STAGES 2
+#define DT_THREADS (32 * 17)                   // 16 producer/epilogue warps + 1 MMA warp
+#define DT_SMEM (DT_STAGES * DT_SLOT + 1024)
+
+namespace {
+
+struct DtParams {
+  const float* A; long long lda;
+  const float* W; long long ldw;
+  float* C; long long ldc;
+  int M, N, K;                                 // GEMM sizes (bwd data: N = layer inputs, K = layer outputs)
+  int bwd;                                     // 0: B(n,k) = W[k*ldw + n];  1: B(n,k) = W[n*ldw + k]
+  const float* bias; int act; float out_scale, out_bias;
+  const float* yprev; long long ldy; int act_prev; int accumulate;
+};
+
+// 16 consecutive K values of row r -> tf32 hi plane + bf16 correction plane (layout of mlp_tc.cu).  The correction MMA
+// evaluates a_lo.b_hi + a_hi.b_lo in ONE product of K = 64, so the A operand stores [bf16(lo) x 32 | bf16(hi) x 32] and
+// the B operand the opposite order [bf16(hi) x 32 | bf16(lo) x 32].
+__device__ __forceinline__ void dt_store16(uint8_t* op, int r, int j0, const float* v, bool b_operand) {
+  uint8_t* row = op + r * 128;
+  const uint32_t rx = (uint32_t)(r & 7);
+#pragma unroll
+  for (int qq = 0; qq < 2; ++qq) {
+    float h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { h[i] = tc::tf32_rna(v[8 * qq + i]); l[i] = v[8 * qq + i] - h[i]; }
+    const uint32_t c0 = (uint32_t)(j0 / 4 + 2 * qq);
+    *reinterpret_cast<float4*>(row + (((c0) ^ rx) << 4)) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(row + (((c0 + 1) ^ rx) << 4)) = make_float4(h[4], h[5], h[6], h[7]);
+    uint4 ul, uh;
+    __nv_bfloat162 t0 = __floats2bfloat162_rn(l[0], l[1]), t1 = __floats2bfloat162_rn(l[2], l[3]);
+    __nv_bfloat162 t2 = __floats2bfloat162_rn(l[4], l[5]), t3 = __floats2bfloat162_rn(l[6], l[7]);
+    ul.x = *reinterpret_cast<uint32_t*>(&t0); ul.y = *reinterpret_cast<uint32_t*>(&t1);
+    ul.z = *reinterpret_cast<uint32_t*>(&t2); ul.w = *reinterpret_cast<uint32_t*>(&t3);
+    t0 = __floats2bfloat162_rn(h[0], h[1]); t1 = __floats2bfloat162_rn(h[2], h[3]);
+    t2 = __floats2bfloat162_rn(h[4], h[5]); t3 = __floats2bfloat162_rn(h[6], h[7]);
+    uh.x = *reinterpret_cast<uint32_t*>(&t0); uh.y = *reinterpret_cast<uint32_t*>(&t1);
+    uh.z = *reinterpret_cast<uint32_t*>(&t2); uh.w = *reinterpret_cast<uint32_t*>(&t3);
+    const uint32_t cc = (uint32_t)(j0 / 8 + qq);
+    *reinterpret_cast<uint4*>(row + DT_PLANE + ((cc ^ rx) << 4)) = b_operand ? uh : ul;
+    *reinterpret_cast<uint4*>(row + DT_PLANE + (((cc + 4) ^ rx) << 4)) = b_operand ? ul : uh;
+  }
+}
+
+// 32 consecutive floats starting at p (elements >= n_valid read as zero); vectorised when the address allows
+__device__ __forceinline__ void dt_load_row32(const float* p, int n_valid, float (&v)[32]) {
+  if (n_valid >= 32 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p) + q);
+      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = j < n_valid ? __ldg(p + j) : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(const __grid_constant__ DtParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full[DT_STAGES], empty[DT_STAGES], acc_full;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int MMA_WARP = 16;
+  const int m0 = blockIdx.x * DT_M, n0 = blockIdx.y * DT_N;
+  const int nvalid = min(DT_N, p.N - n0), npad = (nvalid + 15) / 16 * 16;
+  const int nch = (p.K + 31) / 32;
+
+  if (warp == MMA_WARP) tc::tmem_alloc(&tmem_base_s, 128);
+  if (tid == 0) {
+    for (int i = 0; i < DT_STAGES; ++i) { tc::mbar_init(&full[i], 256); tc::mbar_init(&empty[i], 1); }
+    tc::mbar_init(&acc_full, 1);
+    tc::mbar_fence_init();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < 16) {
+    const int grp = warp >> 3, i = tid & 255;
+    const bool a_role = i < 128;
+    const int r = a_role ? i : i - 128;                       // A row / B row (= output column) of this thread
+    for (int c = grp; c < nch; c += 2) {
+      const int slot = c & 1, k0 = c * 32, kv = min(32, p.K - k0);
+      float v[32];
+      if (a_role) {
+        const int m = m0 + r;
+        if (m < p.M) dt_load_row32(p.A + (long long)m * p.lda + k0, kv, v);
+        else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+      } else if (r < nvalid) {
+        if (p.bwd) dt_load_row32(p.W + (long long)(n0 + r) * p.ldw + k0, kv, v);
+        else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = j < kv ? __ldg(p.W + (long long)(k0 + j) * p.ldw + n0 + r) : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      tc::mbar_wait(&empty[slot], (((uint32_t)c / DT_STAGES) & 1u) ^ 1u);
+      uint8_t* op = smem + (size_t)slot * DT_SLOT + (a_role ? 0 : DT_OPERAND);
+      dt_store16(op, r, 0, v, !a_role);
+      dt_store16(op, r, 16, v + 16, !a_role);
+      tc::fence_proxy_async();
+      tc::mbar_arrive(&full[slot]);
+    }
+    // ---- epilogue: 4 warps share a TMEM lane quarter; each thread handles two 16-column pieces of its row ----
+    tc::mbar_wait(&acc_full, 0);
+    tc::fence_after_sync();
+    const int row = 32 * (warp & 3) + lane, m = m0 + row;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+    const int piece0 = warp >> 2;                             // 0..3
+#pragma unroll 1
+    for (int t = 0; t < 2; ++t) {
+      const int c16 = 16 * (piece0 + 4 * t);
+      if (c16 >= npad) continue;                              // warp-uniform
+      float v[16];
+      tc::tmem_ld16(lane_addr + (uint32_t)c16, v);
+      if (m < p.M) {                                          // (no early exit: the next tcgen05.ld is warp-collective)
+        float* dst = p.C + (long long)m * p.ldc + n0 + c16;
+        const int cnt = min(16, nvalid - c16);
+        if (!p.bwd) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (j < cnt) {
+              float x = v[j] + (p.bias ? __ldg(p.bias + n0 + c16 + j) : 0.f);
+              v[j] = p.out_scale * vqn_apply_act(x, p.act) + p.out_bias;
+            }
+          }
+        } else {
+          if (p.act_prev != VQN_ACT_NONE) {
+            const float* yp = p.yprev + (long long)m * p.ldy + n0 + c16;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (j < cnt) {
+                const float y = yp[j];
+                v[j] *= (p.act_prev == VQN_ACT_RELU) ? (y > 0.f ? 1.f : 0.f) : y * (1.f - y);
+              }
+            }
+          }
+          if (p.accumulate) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (j < cnt) v[j] += dst[j];
+          }
+        }
+        if (cnt == 16 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (j < cnt) dst[j] = v[j];
+        }
+      }
+      __syncwarp();
+    }
+    tc::fence_before_sync();
+  } else {
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc(tc::FMT_TF32, DT_M, npad);
+      const uint32_t idesc_c = tc::make_idesc(tc::FMT_BF16, DT_M, npad);
+      uint32_t acc = 0;
+      for (int c = 0; c < nch; ++c) {
+        const int slot = c & 1;
+        tc::mbar_wait(&full[slot], ((uint32_t)c / DT_STAGES) & 1u);
+        tc::fence_after_sync();
+        const uint32_t a_addr = tc::smem_u32(smem + (size_t)slot * DT_SLOT);
+        const uint32_t b_addr = a_addr + DT_OPERAND;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          tc::mma_ss<true>(tmem_base, tc::make_desc_sw128(a_addr + 32 * s), tc::make_desc_sw128(b_addr + 32 * s), idesc, acc);
+          acc = 1;
+          tc::mma_ss<false>(tmem_base, tc::make_desc_sw128(a_addr + DT_PLANE + 32 * s),
+                            tc::make_desc_sw128(b_addr + DT_PLANE + 32 * s), idesc_c, 1);
+        }
+        tc::mma_commit(&empty[slot]);
+      }
+      tc::mma_commit(&acc_full);
+    }
+    __syncwarp();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == MMA_WARP) tc::tmem_dealloc(tmem_base, 128);
+}
+
+int dt_launch(vqn_ctx* ctx, const DtParams& p, cudaStream_t s) {
+  static bool attr_set[16] = {false};
+  const int dev = ctx->device & 15;
+  if (!attr_set[dev]) {
+    VQN_CUDA(cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DT_SMEM));
+    attr_set[dev] = true;
+  }
+  dim3 grid((unsigned)((p.M + DT_M - 1) / DT_M), (unsigned)((p.N + DT_N - 1) / DT_N), 1);
+  dense_tc_kernel<<<grid, DT_THREADS, DT_SMEM, s>>>(p);
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}
+
+}  // namespace
+
+// rows from which the tcgen05 forward is taken for the WIDE layers (k, n >= 192); VQN_DENSE_TC_MIN_M overrides: 1 = every
+// forward and backward-data call (parity tests, measurements), a negative value = never
+long long vqn_dense_tc_min_m() {
+  static bool init = false;
+  static long long v = 1024;
+  if (!init) { const char* e = getenv("VQN_DENSE_TC_MIN_M"); if (e) v = atoll(e); init = true; }
+  return v;
+}
+
+int vqn_dense_tc_forward(vqn_ctx* ctx, const float* x, long long ldx, const float* w, const float* b, float* y,
+                         long long ldy, long long m, int k, int n, int act, float out_scale, float out_bias,
+                         cudaStream_t s) {
+  DtParams p = {};
+  p.A = x; p.lda = ldx; p.W = w; p.ldw = n; p.C = y; p.ldc = ldy; p.M = (int)m; p.N = n; p.K = k; p.bwd = 0;
+  p.bias = b; p.act = act; p.out_scale = out_scale; p.out_bias = out_bias;
+  return dt_launch(ctx, p, s);
+}
+
+int vqn_dense_tc_backward_data(vqn_ctx* ctx, const float* dz, long long lddz, const float* w, float* dx, long long lddx,
+                               const float* yprev, long long ldyp, int act_prev, int accumulate, long long m, int k,
+                               int n, cudaStream_t s) {
+  DtParams p = {};
+  p.A = dz; p.lda = lddz; p.W = w; p.ldw = n; p.C = dx; p.ldc = lddx; p.M = (int)m; p.N = k; p.K = n; p.bwd = 1;
+  p.yprev = yprev; p.ldy = ldyp; p.act_prev = act_prev; p.accumulate = accumulate;
+  return dt_launch(ctx, p, s);
+}
