@@ -642,7 +642,11 @@ def run_ours(args):
                        'parallelism': ('pixel rows sharded x%d, image gather %s' % (world, {'p2p': 'to rank 0, fused into the shading kernel (P2P stores over NVLink into symmetric memory)', 'nccl': 'one NCCL all-gather'}[gather_mode])) if world > 1 else 'single GPU',
                        'l2': 'inputs (%.2f GB lvis per step) larger than the 126 MB L2, no flush needed' % (n * 2048 / 1e9)},
             'e2e': {'value': n_global / (e2e_ms * 1e-3), 'unit': 'points/s', 'ms_per_step': e2e_ms,
-                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'h2d_gbs': h2d / (e2e_ms * 1e-3) / 1e9,
+                    'bound': 'host-to-device link: the step moves %.2f GB of fp32 light visibility per view from pinned '
+                             'host memory, overlapped with the kernels (fast_render_host); the device-resident step is '
+                             '%.1fx shorter' % (h2d / 1e9, e2e_ms / ms_step)},
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': roof,
