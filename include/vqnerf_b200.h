@@ -361,12 +361,14 @@ int vqn_neus_mid_points(vqn_ctx* ctx, const float* rays_o, const float* rays_d, 
  * layer.  The last Linear (d_hidden -> 1 + d_feature) is passed split: w_sdf[d_hidden] / b_sdf[1] = its output 0,
  * `feat` = a one-layer network holding outputs 1.. [NULL when feat_out is NULL].  scale == 1 (every shipped conf).
  *   sdf[n]  <- forward(x)[:, :1];  feat_out[n, feat_stride >= d_feature] <- forward(x)[:, 1:]  (optional)
- *   grad_out[n,3] <- d sdf / d x (optional).  With grad_out the kernel propagates (value, d/dx, d/dy, d/dz) jets --
- *   four rows of the 128-row MMA tile per point -- so autograd's second pass (fields.py:98-110) does not exist.
+ *   grad_out[n,3] <- d sdf / d x (optional), inside the same launch (autograd's second pass, fields.py:98-110, does not
+ *   exist): grad_mode 0 propagates (value, d/dx, d/dy, d/dz) jets -- four rows of the 128-row MMA tile per point, nothing
+ *   stored; grad_mode 1 runs the forward pass on value rows with act' of every hidden layer stashed in a per-CTA L2-resident
+ *   scratch, then the transposed layers back to the embedding (2 row-passes per point instead of 4).
  * precision: VQN_PREC_TF32X3 or VQN_PREC_BF16. */
 int vqn_sdf_forward(vqn_ctx* ctx, vqn_net* trunk, const float* w_sdf, const float* b_sdf, vqn_net* feat,
                     int n_freqs, const float* pts, int64_t n, float* sdf, float* feat_out, int64_t feat_stride,
-                    float* grad_out, int precision, vqn_stream stream);
+                    float* grad_out, int grad_mode, int precision, vqn_stream stream);
 
 /* RenderingNetwork input (fields.py:147-156, mode 'idr'): writes [points(3), embed(view_dirs)(3+6*multires_view),
  * normals(3), zero pad] into columns [col_off, col_off + width) of rows[n, row_stride]; the feature vector is

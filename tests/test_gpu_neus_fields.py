@@ -16,11 +16,11 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'neus_fields_ref.npz')
 
 
-def _nets(dev, precision='tf32x3'):
+def _nets(dev, precision='tf32x3', grad_mode='reverse'):
     from vqnerf_release_b200.neus.fields import RenderingNetwork, SDFNetwork, SingleVarianceNetwork
     st = NO.make_neus_state(0)
     sdf = SDFNetwork(d_out=257, d_in=3, d_hidden=256, n_layers=8, skip_in=(4,), multires=6, bias=0.5, scale=1.0,
-                     geometric_init=True, weight_norm=True, device=dev, precision=precision)
+                     geometric_init=True, weight_norm=True, device=dev, precision=precision, grad_mode=grad_mode)
     col = RenderingNetwork(d_feature=256, mode='idr', d_in=9, d_out=3, d_hidden=256, n_layers=4, weight_norm=True,
                            multires_view=4, squeeze_out=True, device=dev, precision=precision)
     sdf.load_state_dict(st['sdf'])
@@ -32,9 +32,10 @@ def _t(a, dev):
     return torch.as_tensor(np.asarray(a, np.float32)).to(dev)
 
 
-def test_sdf_network_vs_reference(cuda_dev):
+@pytest.mark.parametrize('grad_mode', ['reverse', 'jet'])
+def test_sdf_network_vs_reference(cuda_dev, grad_mode):
     g = np.load(GOLD)
-    _, sdf_net, col_net, _ = _nets(cuda_dev)
+    _, sdf_net, col_net, _ = _nets(cuda_dev, grad_mode=grad_mode)
     x = _t(g['pts'], cuda_dev)
     out = sdf_net(x).cpu().numpy()
     assert out.shape == (len(g['pts']), 257)
@@ -48,22 +49,26 @@ def test_sdf_network_vs_reference(cuda_dev):
     np.testing.assert_allclose(col.cpu().numpy(), g['color'], rtol=1e-4, atol=2e-5)
 
 
+@pytest.mark.parametrize('grad_mode', ['reverse', 'jet'])
 @pytest.mark.parametrize('n', [1, 31, 33, 127, 129, 5003, 40000])
-def test_sdf_forward_vs_oracle_ragged(cuda_dev, n):
-    st, sdf_net, col_net, _ = _nets(cuda_dev)
+def test_sdf_forward_vs_oracle_ragged(cuda_dev, n, grad_mode):
+    st, sdf_net, col_net, _ = _nets(cuda_dev, grad_mode=grad_mode)
     rng = np.random.RandomState(n)
     pts = rng.uniform(-1.2, 1.2, size=(n, 3)).astype(np.float32)
     eo, eg = NO.sdf_forward(st['sdf'], pts)
     x = _t(pts, cuda_dev)
     rows = col_net.alloc_rows(n, cuda_dev)
     rows.fill_(float('nan'))
-    sdf, feat, grad = sdf_net.forward_with_gradient(x, feat_out=rows)      # one launch: jets + features into the rows
+    sdf, feat, grad = sdf_net.forward_with_gradient(x, feat_out=rows)      # one launch: value, gradient, features into the rows
     np.testing.assert_allclose(sdf.cpu().numpy()[:, 0], eo[:, 0], rtol=1e-4, atol=2e-5)
     np.testing.assert_allclose(feat.cpu().numpy(), eo[:, 1:], rtol=1e-4, atol=2e-5)
     np.testing.assert_allclose(grad.cpu().numpy(), eg, rtol=1e-4, atol=1e-4)
     assert torch.isnan(rows[:, 256:]).all()                                  # only the feature columns were written
-    # value-only tiles (128 points per tile) agree with the jet tiles (32 points per tile)
+    # value-only launch agrees with the gradient launch (jets: 32 points per tile; reverse: 128)
     np.testing.assert_allclose(sdf_net.sdf(x).cpu().numpy(), sdf.cpu().numpy(), rtol=0, atol=2e-6)
+    # gradient without the feature layer (what compute_vis asks for)
+    g2 = sdf_net.gradient(x)[:, 0]
+    np.testing.assert_allclose(g2.cpu().numpy(), eg, rtol=1e-4, atol=1e-4)
     # colour network on the rows the SDF kernel filled
     dirs = rng.normal(size=(n, 3)); dirs = (dirs / np.linalg.norm(dirs, axis=1, keepdims=True)).astype(np.float32)
     col = col_net.forward_rows(rows, x, grad, _t(dirs, cuda_dev))

@@ -96,7 +96,7 @@ SIGNATURES = {
     'vqn_neus_cat_z_vals': (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _P, _P, _P]),
     'vqn_neus_composite': (_I, [_P, C.POINTER(NeusCompositeArgs), _P]),
     'vqn_neus_mid_points': (_I, [_P, _P, _P, _P, _L, _I, _F, _P, _P, _P]),
-    'vqn_sdf_forward': (_I, [_P, _P, _P, _P, _P, _I, _P, _L, _P, _P, _L, _P, _I, _P]),
+    'vqn_sdf_forward': (_I, [_P, _P, _P, _P, _P, _I, _P, _L, _P, _P, _L, _P, _I, _I, _P]),
     'vqn_neus_color_input': (_I, [_P, _P, _P, _P, _L, _I, _P, _L, _I, _I, _P]),
     'vqn_neus_light_rays': (_I, [_P, _P, _P, _P, _L, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
     'vqn_neus_lvis_scatter': (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _P, _P]),

@@ -436,9 +436,12 @@ def neus_composite(rays_o, rays_d, z_vals, sdf, gradients, sampled_color, inv_s,
 
 def sdf_forward(trunk: PackedNet, w_sdf: torch.Tensor, b_sdf: torch.Tensor, feat: Optional[PackedNet], n_freqs: int,
                 pts: torch.Tensor, want_grad: bool = False, feat_out: Optional[torch.Tensor] = None,
-                precision='tf32x3'):
+                precision='tf32x3', grad_mode: str = 'reverse'):
     """vqn_sdf_forward (fields.py:74-112).  feat_out: None (sdf only) or a [n, stride >= d_feature] row buffer that
-    receives the feature vector in its first columns.  Returns (sdf [n,1], grad [n,3] or None)."""
+    receives the feature vector in its first columns.  grad_mode: 'reverse' (act' stash + transposed layers) or 'jet'
+    (forward-mode tangent rows).  Returns (sdf [n,1], grad [n,3] or None)."""
+    if grad_mode not in ('reverse', 'jet'):
+        raise ValueError("grad_mode must be 'reverse' or 'jet'")
     pts = _f(pts)
     n = pts.shape[0]
     if pts.dim() != 2 or pts.shape[1] != 3:
@@ -458,7 +461,8 @@ def sdf_forward(trunk: PackedNet, w_sdf: torch.Tensor, b_sdf: torch.Tensor, feat
     L.check(c.lib.vqn_sdf_forward(c.handle, trunk.handle, L.ptr(w_sdf, F32), L.ptr(b_sdf, F32),
                                   feat.handle if feat_out is not None else None, n_freqs, L.ptr(pts), n, L.ptr(sdf),
                                   C.c_void_p(feat_out.data_ptr()) if feat_out is not None else None, stride,
-                                  L.ptr(grad), L.precision_code(precision), L.stream_ptr(pts.device)))
+                                  L.ptr(grad), 1 if grad_mode == 'reverse' else 0, L.precision_code(precision),
+                                  L.stream_ptr(pts.device)))
     return sdf, grad
 
 

@@ -30,10 +30,12 @@
 #include "tc_common.cuh"
 
 #define TC_M 128               // points per tile (= TMEM lanes)
-#define TC_MAX_LAYERS 16
+#define TC_MAX_LAYERS 20
 #define TC_NPAD_MAX 256
 
-enum { SRC_DRAIN = 0, SRC_EMBED = 1, SRC_GLOBAL = 2 };
+enum { SRC_DRAIN = 0, SRC_EMBED = 1, SRC_GLOBAL = 2,
+       SRC_GRADINIT = 3,      // reverse mode: A = w_tail (x) act'(stash)            (d out / d pre of the last hidden layer)
+       SRC_GRAD = 4 };        // reverse mode: A = drain(previous accumulator) * act'(stash)
 
 struct TcLayer {
   const uint8_t* w;       // packed chunk images, chunk c at w + c * chunk_bytes
@@ -57,6 +59,13 @@ struct TcLayer {
   const float* tail_b;    // its bias
   int tail_n, tail_act, tail_out_slot, tail_add_skip, tail_woff;
   float tail_scale, tail_bias;
+  // Reverse-mode gradient (MODE 2, vqn_sdf_forward): stash_w >= 0: whoever applies this layer's activation (the next
+  // layer's drain, or the tail) also stores act'(pre-activation) into stash slot stash_w of the CTA's scratch;
+  // grad_stash: the slot a SRC_GRADINIT / SRC_GRAD layer multiplies by; grad_tail_woff: table of the tail weights;
+  // egrad_col0 >= 0: columns [egrad_col0, egrad_col0 + 3 + 6 n_freqs) of this layer's accumulator are d out / d embedding
+  // and are contracted with the embedding Jacobian (the skip half of the skip_in layer, and the whole last layer);
+  // grad_final: this is the last backward layer -- combine the partial gradients and store d out / d x.
+  int stash_w, grad_stash, grad_tail_woff, egrad_col0, grad_final;
 };
 
 struct TcProgram {
@@ -80,7 +89,12 @@ struct TcProgram {
   // 4p+1..4p+3 its derivatives with respect to x, y, z; every layer is linear in the tangent rows and the activation
   // multiplies them by act'(pre-activation of the value row), fetched from the neighbouring TMEM lane by a shuffle.
   int jet;
-  float* jet_grad;         // [n,3]: tangent rows of the narrow tail (d sdf / d x)
+  float* jet_grad;         // [n,3]: tangent rows of the narrow tail (d sdf / d x); reverse mode: the gradient output
+  // Reverse mode (MODE 2): forward pass on value rows (128 points per tile) with act' of every hidden layer stashed in a
+  // per-CTA scratch ([slot][16-column piece][row][16] fp32, L2-resident), then the transposed layers back to the
+  // embedding and a contraction with the embedding's Jacobian: 2 row-passes per point instead of the 4 of the jets.
+  int reverse;
+  float* stash;            // sm_count x TC_STASH_FLOATS
   int* nonfinite;
   long long* trace;        // diagnostic (vqn_debug_tc_trace): clock64 stamps of CTA 0's MMA thread, 4 per layer
   TcLayer layers[TC_MAX_LAYERS];
@@ -92,6 +106,13 @@ struct TcPack {
   int n_chunks[VQN_MAX_LAYERS];
   uint8_t* w[VQN_MAX_LAYERS];
   float* bias[VQN_MAX_LAYERS];
+  // transposed images for the reverse-mode gradient (built on first use): layer i as the GEMM  d in = d out . W_i^T,
+  // i.e. N = inputs of layer i (incl. the skip concat), K = outputs of layer i; biasT = zeros
+  bool has_T;
+  int NpadT[VQN_MAX_LAYERS];
+  int n_chunksT[VQN_MAX_LAYERS];
+  uint8_t* wT[VQN_MAX_LAYERS];
+  float* biasT[VQN_MAX_LAYERS];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -101,7 +122,9 @@ struct TcPack {
 template <bool BF16>
 __global__ void tc_pack_kernel(const float* __restrict__ w, const float* __restrict__ b, int n_out, int Npad,
                                int seg0_rows, int seg0_chunks, int seg1_rows, int seg1_chunks,
-                               uint8_t* __restrict__ pw, float* __restrict__ pb) {
+                               uint8_t* __restrict__ pw, float* __restrict__ pb, int transpose_ld) {
+  // transpose_ld > 0: the GEMM's N index runs over the Keras kernel's ROWS (n_out of them) and its K index over the
+  // kernel's columns (seg0_rows of them, row length transpose_ld): the image of W^T for the backward pass
   constexpr int E = BF16 ? 64 : 32;
   const int n_chunks = seg0_chunks + seg1_chunks;
   const size_t plane = (size_t)Npad * 128;
@@ -115,7 +138,7 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, const float* __restr
     int src;
     if (c < seg0_chunks) { int r = c * E + kk; src = r < seg0_rows ? r : -1; }
     else { int r = (c - seg0_chunks) * E + kk; src = r < seg1_rows ? seg0_rows + r : -1; }
-    float v = (src >= 0 && n < n_out) ? w[(size_t)src * n_out + n] : 0.f;
+    float v = (src >= 0 && n < n_out) ? (transpose_ld > 0 ? w[(size_t)n * transpose_ld + src] : w[(size_t)src * n_out + n]) : 0.f;
     uint8_t* base = pw + (size_t)c * chunk_bytes;
     if (BF16) {
       uint32_t off = tc::sw128_off(n, kk / 8) + (kk % 8) * 2;
@@ -132,7 +155,7 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, const float* __restr
     }
   }
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < Npad; c += gridDim.x * blockDim.x)
-    pb[c] = c < n_out ? b[c] : 0.f;
+    pb[c] = (b && c < n_out) ? b[c] : 0.f;
 }
 
 static int tc_pack_fill(vqn_net* net, int p, cudaStream_t s) {
@@ -146,13 +169,44 @@ static int tc_pack_fill(vqn_net* net, int p, cudaStream_t s) {
     int seg1_rows = after_skip ? d.in_dim : 0;
     int c0 = vqn_round_up(seg0_rows, E) / E, c1 = vqn_round_up(seg1_rows, E) / E;
     if (bf16) tc_pack_kernel<true><<<128, 256, 0, s>>>(d.w[i], d.b[i], d.widths[i], tp->Npad[i], seg0_rows, c0,
-                                                      seg1_rows, c1, tp->w[i], tp->bias[i]);
+                                                      seg1_rows, c1, tp->w[i], tp->bias[i], 0);
     else tc_pack_kernel<false><<<128, 256, 0, s>>>(d.w[i], d.b[i], d.widths[i], tp->Npad[i], seg0_rows, c0,
-                                                   seg1_rows, c1, tp->w[i], tp->bias[i]);
+                                                   seg1_rows, c1, tp->w[i], tp->bias[i], 0);
     net->ctx->launches.fetch_add(1);
     VQN_CUDA(cudaGetLastError());
+    if (tp->has_T) {
+      const int in_rows = seg0_rows + seg1_rows;             // Keras kernel rows (y rows, then the x rows after a skip)
+      const int kc = vqn_round_up(d.widths[i], E) / E;
+      if (bf16) tc_pack_kernel<true><<<128, 256, 0, s>>>(d.w[i], nullptr, in_rows, tp->NpadT[i], d.widths[i], kc, 0, 0,
+                                                        tp->wT[i], tp->biasT[i], d.widths[i]);
+      else tc_pack_kernel<false><<<128, 256, 0, s>>>(d.w[i], nullptr, in_rows, tp->NpadT[i], d.widths[i], kc, 0, 0,
+                                                     tp->wT[i], tp->biasT[i], d.widths[i]);
+      net->ctx->launches.fetch_add(1);
+      VQN_CUDA(cudaGetLastError());
+    }
   }
   return VQN_OK;
+}
+
+// reverse-mode gradient: allocate + fill the transposed images of an existing pack
+static int tc_packT_ensure(vqn_net* net, int precision, cudaStream_t s) {
+  const int p = precision == VQN_PREC_BF16 ? 1 : 0;
+  TcPack* tp = net->tc_pack[p];
+  if (!tp || tp->has_T) return VQN_OK;
+  const vqn_net_desc& d = net->desc;
+  const int E = p == 1 ? 64 : 32;
+  for (int i = 0; i < d.n_layers; ++i) {
+    const bool after_skip = (d.skip_at >= 0 && i == d.skip_at + 1);
+    const int in_rows = ((i == 0) ? d.in_dim : d.widths[i - 1]) + (after_skip ? d.in_dim : 0);
+    tp->NpadT[i] = vqn_round_up(in_rows, i > 0 ? E : 16);   // layer 0's input gradient is only contracted, not chained
+    tp->n_chunksT[i] = vqn_round_up(d.widths[i], E) / E;
+    if (tp->NpadT[i] > TC_NPAD_MAX) { vqn_set_error("reverse-mode gradient: layer %d has more than 256 inputs", i); return VQN_ERR_UNSUPPORTED; }
+    const size_t chunk_bytes = (size_t)tp->NpadT[i] * 128 * (p == 1 ? 1 : 2);
+    VQN_CUDA(cudaMalloc(&tp->wT[i], chunk_bytes * tp->n_chunksT[i]));
+    VQN_CUDA(cudaMalloc(&tp->biasT[i], sizeof(float) * tp->NpadT[i]));
+  }
+  tp->has_T = true;
+  return tc_pack_fill(net, p, s);
 }
 
 static int tc_pack_get(vqn_net* net, int precision, cudaStream_t s, TcPack** out) {
@@ -193,7 +247,10 @@ void vqn_tc_pack_destroy(vqn_net* net) {
   for (int p = 0; p < 2; ++p) {
     TcPack* tp = net->tc_pack[p];
     if (!tp) continue;
-    for (int i = 0; i < tp->n_layers; ++i) { cudaFree(tp->w[i]); cudaFree(tp->bias[i]); }
+    for (int i = 0; i < tp->n_layers; ++i) {
+      cudaFree(tp->w[i]); cudaFree(tp->bias[i]);
+      if (tp->has_T) { cudaFree(tp->wT[i]); cudaFree(tp->biasT[i]); }
+    }
     delete tp;
     net->tc_pack[p] = nullptr;
   }
@@ -216,6 +273,8 @@ struct TcCfg {
   static constexpr size_t SMEM = (size_t)SA * A_SLOT + (size_t)SW * W_SLOT + 1024;
 };
 #define TC_BIAS_FLOATS 7168
+#define TC_STASH_SLOTS 8
+#define TC_STASH_FLOATS (TC_STASH_SLOTS * 16 * TC_M * 16)     // 1 MB per CTA
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
@@ -250,6 +309,61 @@ __device__ __forceinline__ void bias_act32_jet(float (&v)[16], const float* __re
       val = pre; der = 1.0f;
     }
     v[j] = is_val ? val : v[j] * der;
+  }
+}
+
+// Reverse mode: value AND act' of 16 pre-activations; act' goes to the stash (4 x 16-byte stores, a warp writes 2 KB)
+__device__ __forceinline__ void bias_act32_stash(float (&v)[16], const float* __restrict__ bias_s, int act,
+                                                 float* __restrict__ stash16) {
+  float d[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float pre = v[j] + bias_s[j];
+    if (act == VQN_ACT_SOFTPLUS100) {
+      const float bt = 100.0f * pre;
+      const float e = __expf(-fabsf(bt));
+      const float s = __fdividef(1.0f, 1.0f + e);
+      v[j] = (fmaxf(bt, 0.0f) + __logf(1.0f + e)) * 0.01f;
+      d[j] = bt >= 0.0f ? s : e * s;
+    } else if (act == VQN_ACT_RELU) {
+      v[j] = fmaxf(pre, 0.0f); d[j] = pre > 0.0f ? 1.0f : 0.0f;
+    } else if (act == VQN_ACT_SIGMOID) {
+      v[j] = __fdividef(1.0f, 1.0f + __expf(-pre)); d[j] = v[j] * (1.0f - v[j]);
+    } else {
+      v[j] = pre; d[j] = 1.0f;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    __stcg(reinterpret_cast<float4*>(stash16) + q, make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]));
+}
+__device__ __forceinline__ void stash_load16(const float* __restrict__ stash16, float (&d)[16]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 t = __ldcg(reinterpret_cast<const float4*>(stash16) + q);
+    d[4 * q] = t.x; d[4 * q + 1] = t.y; d[4 * q + 2] = t.z; d[4 * q + 3] = t.w;
+  }
+}
+// sum_k g[k] * d embed_{e0+k} / d x_j  for the 16 embedding columns e0 .. e0+15 (embedder.py: [x, sin(x f), cos(x f), ...])
+__device__ __forceinline__ void embed_jac_contract(const float (&g)[16], int e0, int n_freqs, const float (&x)[3],
+                                                   float& a0, float& a1, float& a2) {
+  const int d = 3 + 6 * n_freqs;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int k = e0 + j;
+    if (k < 0 || k >= d) continue;
+    int c; float w;
+    if (k < 3) { c = k; w = 1.0f; }
+    else {
+      const int f = (k - 3) / 6, q = (k - 3) % 6;
+      c = q % 3;
+      const float fr = exp2f((float)f);
+      float sn, cs;
+      sincosf(x[c] * fr, &sn, &cs);
+      w = q < 3 ? fr * cs : -fr * sn;
+    }
+    const float t = g[j] * w;
+    a0 += c == 0 ? t : 0.0f; a1 += c == 1 ? t : 0.0f; a2 += c == 2 ? t : 0.0f;
   }
 }
 
@@ -385,7 +499,8 @@ __device__ __forceinline__ void embed_chunk(uint8_t* slot, int r, const float (&
 // named barrier of one 256-thread epilogue group (ids 1, 2; id 0 is __syncthreads)
 __device__ __forceinline__ void group_bar(int grp) { asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory"); }
 
-template <bool BF16, bool JET>
+// MODE 0: plain chain (decomposition stage, SDF value-only); 1: jets (4 rows per point); 2: reverse-mode gradient
+template <bool BF16, int MODE>
 __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcProgram pg) {
   using C = TcCfg<BF16>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -429,8 +544,9 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
 
   long long n = pg.n_dev ? (long long)*pg.n_dev : pg.n;
   if (n > pg.n) n = pg.n;
-  constexpr bool jet = JET;                              // compile-time: the decomposition-stage kernels carry no jet code
-  constexpr int tile_pts = JET ? TC_M / 4 : TC_M;        // points per tile
+  constexpr bool jet = MODE == 1;                        // compile-time: the decomposition-stage kernels carry no jet code
+  constexpr bool rev = MODE == 2;
+  constexpr int tile_pts = jet ? TC_M / 4 : TC_M;        // points per tile
   const long long n_tiles = (n + tile_pts - 1) / tile_pts;
   const int L = pg.n_layers;
 
@@ -460,6 +576,20 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
       }
       for (int l = 0; l < L; ++l) {
         const int nseg = pg.layers[l].nseg;
+        if (rev && l > 0 && pg.layers[l - 1].egrad_col0 >= 0 && !pg.layers[l - 1].grad_final) {
+          // skip half of the skip_in layer's input gradient: d out / d embedding, contracted with the embedding Jacobian
+          // right away (3 partial sums in registers) -- the columns are not an operand of any later layer
+          const TcLayer& pl = pg.layers[l - 1];
+          tc::mbar_wait(&acc_full, (gl - 1) & 1);
+          tc::fence_after_sync();
+          const int t4 = grp * 2 + half;
+          const int c16 = (pl.egrad_col0 & ~15) + 16 * t4;
+          if (c16 < pl.Npad) {                                   // warp-uniform
+            float v[16];
+            tc::tmem_ld16(lane_addr + (uint32_t)(pl.tmem_col + c16), v);
+            embed_jac_contract(v, c16 - pl.egrad_col0, pg.n_freqs, x, sp0, sp1, sp2);
+          }
+        }
         for (int sg = 0; sg < nseg; ++sg) {
           const int st = pg.layers[l].seg_type[sg];
           const int nch = pg.layers[l].seg_chunks[sg];
@@ -470,7 +600,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
           bool acc_ready = false;
           for (int c = 0; c < nch; ++c, ++ga) {
             if ((int)(ga % C::G) != grp) continue;
-            if (st == SRC_DRAIN && !acc_ready) {
+            if ((st == SRC_DRAIN || st == SRC_GRAD) && !acc_ready) {
               tc::mbar_wait(&acc_full, (gl - 1) & 1);    // previous layer's accumulator is complete
               tc::fence_after_sync();
               acc_ready = true;
@@ -542,7 +672,24 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                 if (st == SRC_DRAIN) {
                   tc::tmem_ld16(pacc + (uint32_t)col0, v);
                   if (jet) bias_act32_jet(v, pbias + col0, pact, lane);
+                  else if (rev && pg.layers[l - 1].stash_w >= 0 && !pg.layers[l - 1].tail_w)
+                    bias_act32_stash(v, pbias + col0, pact,
+                                     pg.stash + (size_t)blockIdx.x * TC_STASH_FLOATS +
+                                         ((size_t)(pg.layers[l - 1].stash_w * 16 + (col0 >> 4)) * TC_M + r) * 16);
                   else bias_act32_dyn(v, pbias + col0, pact);
+                } else if (rev && (st == SRC_GRAD || st == SRC_GRADINIT)) {
+                  float dv[16];
+                  stash_load16(pg.stash + (size_t)blockIdx.x * TC_STASH_FLOATS +
+                                   ((size_t)(pg.layers[l].grad_stash * 16 + (col0 >> 4)) * TC_M + r) * 16, dv);
+                  if (st == SRC_GRAD) {
+                    tc::tmem_ld16(pacc + (uint32_t)col0, v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] *= dv[j];
+                  } else {
+                    const float4* tw = reinterpret_cast<const float4*>(bias_s + pg.layers[l].grad_tail_woff) + col0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = dv[j] * tw[j].x;
+                  }
                 } else {                                  // SRC_GLOBAL (bf16 mode): this thread's own latent row
                   if (valid && col0 < pg.g_dim) {
                     const float4* src = reinterpret_cast<const float4*>(
@@ -597,6 +744,9 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
               float v[16];
               tc::tmem_ld16(lane_addr + (uint32_t)(ly.tmem_col + c16), v);
               if (jet) bias_act32_jet(v, lb + c16, ly.act, lane);
+              else if (rev && ly.stash_w >= 0)
+                bias_act32_stash(v, lb + c16, ly.act, pg.stash + (size_t)blockIdx.x * TC_STASH_FLOATS +
+                                                          ((size_t)(ly.stash_w * 16 + (c16 >> 4)) * TC_M + r) * 16);
               else bias_act32_dyn(v, lb + c16, ly.act);
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
@@ -609,6 +759,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
           float4* part = reinterpret_cast<float4*>(a_ring);
           part[r * 4 + grp * 2 + half] = make_float4(p0, p1, p2, p3);
           tc::fence_before_sync();
+          if (rev) __threadfence_block();      // the stash written above (and by the forward drains) is read by other threads
           asm volatile("bar.sync 3, %0;" ::"r"(256 * C::G) : "memory");
           if (grp == 0 && half == 0) {
             float o[4] = {0.f, 0.f, 0.f, 0.f};
@@ -636,6 +787,36 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
               }
             }
             if (valid && bad) atomicOr(pg.nonfinite, 1);
+          }
+          tc::fence_before_sync();
+          asm volatile("bar.sync 3, %0;" ::"r"(256 * C::G) : "memory");   // scratch is free again
+        }
+        if (rev && pg.layers[l].grad_final) {
+          // last backward layer: its accumulator is d out / d embedding; contract with the embedding Jacobian, add the
+          // skip partials, combine the (up to) four partial gradients of a row through the free first A slot
+          const TcLayer& ly = pg.layers[l];
+          tc::mbar_wait(&acc_full, (gl - 1) & 1);
+          tc::fence_after_sync();
+          const int t4 = grp * 2 + half;
+          const int c16 = (ly.egrad_col0 & ~15) + 16 * t4;
+          if (c16 < ly.Npad) {                                   // warp-uniform
+            float v[16];
+            tc::tmem_ld16(lane_addr + (uint32_t)(ly.tmem_col + c16), v);
+            embed_jac_contract(v, c16 - ly.egrad_col0, pg.n_freqs, x, sp0, sp1, sp2);
+          }
+          float4* part = reinterpret_cast<float4*>(a_ring);
+          part[r * 4 + t4] = make_float4(sp0, sp1, sp2, 0.f);
+          sp0 = sp1 = sp2 = 0.f;
+          tc::fence_before_sync();
+          asm volatile("bar.sync 3, %0;" ::"r"(256 * C::G) : "memory");
+          if (t4 == 0) {
+            float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const float4 t = part[r * 4 + q]; g0 += t.x; g1 += t.y; g2 += t.z; }
+            if (valid) {
+              if (!isfinite(g0) || !isfinite(g1) || !isfinite(g2)) atomicOr(pg.nonfinite, 1);
+              pg.jet_grad[pi * 3] = g0; pg.jet_grad[pi * 3 + 1] = g1; pg.jet_grad[pi * 3 + 2] = g2;
+            }
           }
           tc::fence_before_sync();
           asm volatile("bar.sync 3, %0;" ::"r"(256 * C::G) : "memory");   // scratch is free again
@@ -835,6 +1016,7 @@ static bool tc_append_net(TcBuilder& B, vqn_net* net, TcPack* tp, int first_src,
     ly.out_slot = -1; ly.post_scale = 1.f; ly.post_bias = 0.f;
     ly.tmem_col = (B.pg.n_layers & 1) * 256; ly.skip_w = nullptr; ly.skip_n = 0;
     ly.tail_w = nullptr; ly.tail_b = nullptr; ly.tail_n = 0; ly.tail_out_slot = -1; ly.tail_add_skip = 0;
+    ly.stash_w = -1; ly.grad_stash = -1; ly.grad_tail_woff = 0; ly.egrad_col0 = -1; ly.grad_final = 0;
     const bool after_skip = (d.skip_at >= 0 && i == d.skip_at + 1);
     const int seg0_rows = (i == 0) ? d.in_dim : d.widths[i - 1];
     ly.nseg = 1;
@@ -885,6 +1067,15 @@ static int tc_launch(vqn_ctx* ctx, TcProgram& pg, int precision, cudaStream_t s)
     if (pg.layers[l].skip_w) { pg.layers[l].skip_woff = boff; boff += 4 * pg.g_dim; }
   }
   if (boff > TC_BIAS_FLOATS) { vqn_set_error("tensor-core MLP: bias table exceeds %d floats", TC_BIAS_FLOATS); return VQN_ERR_UNSUPPORTED; }
+  if (pg.reverse) {
+    int tw = -1;
+    for (int l = 0; l < pg.n_layers; ++l) if (pg.layers[l].tail_w) tw = pg.layers[l].tail_woff;
+    for (int l = 0; l < pg.n_layers; ++l)
+      if (pg.layers[l].seg_type[0] == SRC_GRADINIT) {
+        if (tw < 0) { vqn_set_error("tensor-core MLP: reverse mode needs a tail layer"); return VQN_ERR_UNSUPPORTED; }
+        pg.layers[l].grad_tail_woff = tw;
+      }
+  }
   if (pg.pts && 3 + 6 * pg.n_freqs > 64) { vqn_set_error("tensor-core MLP: embedding wider than 64"); return VQN_ERR_UNSUPPORTED; }
   if (pg.jet) {
     for (int l = 0; l < pg.n_layers; ++l)
@@ -900,8 +1091,12 @@ static int tc_launch(vqn_ctx* ctx, TcProgram& pg, int precision, cudaStream_t s)
     VQN_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<BF, JT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
     mlp_tc_kernel<BF, JT><<<blocks, TcCfg<BF>::THREADS, smem, s>>>(pg);                                                \
   } while (0)
-  if (precision == VQN_PREC_BF16) { if (pg.jet) TC_LAUNCH(true, true); else TC_LAUNCH(true, false); }
-  else { if (pg.jet) TC_LAUNCH(false, true); else TC_LAUNCH(false, false); }
+  const int mode = pg.jet ? 1 : (pg.reverse ? 2 : 0);
+  if (precision == VQN_PREC_BF16) {
+    if (mode == 1) TC_LAUNCH(true, 1); else if (mode == 2) TC_LAUNCH(true, 2); else TC_LAUNCH(true, 0);
+  } else {
+    if (mode == 1) TC_LAUNCH(false, 1); else if (mode == 2) TC_LAUNCH(false, 2); else TC_LAUNCH(false, 0);
+  }
 #undef TC_LAUNCH
   VQN_LAUNCHED(ctx);
   return VQN_OK;
@@ -1016,33 +1211,66 @@ int vqn_tc_mlp_main(vqn_ctx* ctx, vqn_net* fe, vqn_net* bn, vqn_net* diff, vqn_n
 
 // SDFNetwork (geo/NeuS-ours2/models/fields.py:74-112): trunk (lin0 .. lin{L-2}, softplus) -> narrow tail = output 0 (sdf,
 // on the CUDA cores while the last hidden accumulator is drained) [-> feature layer = outputs 1.. (one more MMA layer)].
-// With grad_out the tile carries (value, d/dx, d/dy, d/dz) jets and the tail's tangent rows are the SDF gradient.
+// Gradient (grad_out): grad_mode 0 = jets (value, d/dx, d/dy, d/dz rows through every layer: 4 row-passes per point,
+// nothing stored); grad_mode 1 = reverse mode (forward on value rows with act' stashed per CTA in an L2-resident scratch,
+// then the transposed layers back to the embedding and a contraction with its Jacobian: 2 row-passes per point).
+static float* g_tc_stash[16] = {nullptr};
 extern "C" int vqn_sdf_forward(vqn_ctx* ctx, vqn_net* trunk, const float* w_sdf, const float* b_sdf, vqn_net* feat,
                                int n_freqs, const float* pts, int64_t n, float* sdf, float* feat_out,
-                               int64_t feat_stride, float* grad_out, int precision, vqn_stream stream) {
+                               int64_t feat_stride, float* grad_out, int grad_mode, int precision, vqn_stream stream) {
   VQN_CHECK_ARG(ctx && trunk && w_sdf && b_sdf && pts && sdf && n >= 0, "sdf_forward: null argument");
   VQN_CHECK_ARG(precision == VQN_PREC_TF32X3 || precision == VQN_PREC_BF16,
                 "sdf_forward: precision must be tf32x3 or bf16 (tensor-core kernel)");
   VQN_CHECK_ARG(trunk->in_dim == 3 + 6 * n_freqs, "sdf_forward: trunk in_dim != 3 + 6*n_freqs");
+  VQN_CHECK_ARG(grad_mode == 0 || grad_mode == 1, "sdf_forward: grad_mode must be 0 (jets) or 1 (reverse)");
   VQN_CHECK_ARG(!feat_out || (feat && feat->n_layers == 1 && feat->in_dim == vqn_net_out_dim(trunk) &&
                               feat_stride >= vqn_net_out_dim(feat) && feat_stride < (1 << 30)),
                 "sdf_forward: feature layer / feat_stride mismatch");
   if (n == 0) return VQN_OK;
   cudaStream_t s = vqn_cs(stream);
+  const bool reverse = grad_out && grad_mode == 1;
   TcPack *t0 = nullptr, *t1 = nullptr;
   int rc = tc_pack_get(trunk, precision, s, &t0);
   if (rc != VQN_OK) return rc;
   if (feat_out) { rc = tc_pack_get(feat, precision, s, &t1); if (rc != VQN_OK) return rc; }
   TcBuilder B(precision);
   B.pg.pts = pts; B.pg.n = n; B.pg.n_freqs = n_freqs;
-  B.pg.jet = grad_out ? 1 : 0; B.pg.jet_grad = grad_out;
+  B.pg.jet = (grad_out && !reverse) ? 1 : 0; B.pg.jet_grad = grad_out;
   B.pg.outs[0] = feat_out; B.pg.out_stride[0] = (int)feat_stride;
   B.pg.outs[1] = sdf; B.pg.out_stride[1] = 1;
   if (!tc_append_net(B, trunk, t0, SRC_EMBED, -1, 1.f, 0.f)) TC_UNSUPPORTED("sdf_forward: trunk does not fit the tensor-core kernel");
+  const int nt = trunk->n_layers;
   TcLayer& last = B.pg.layers[B.pg.n_layers - 1];
   last.tail_w = w_sdf; last.tail_b = b_sdf; last.tail_n = 1; last.tail_act = VQN_ACT_NONE; last.tail_out_slot = 1;
   last.tail_add_skip = 0; last.tail_scale = 1.f; last.tail_bias = 0.f;
   if (feat_out && !tc_append_net(B, feat, t1, SRC_DRAIN, 0, 1.f, 0.f))
     TC_UNSUPPORTED("sdf_forward: feature layer does not fit the tensor-core kernel");
+  if (reverse) {
+    if (nt > TC_STASH_SLOTS || B.pg.n_layers + nt > TC_MAX_LAYERS) TC_UNSUPPORTED("sdf_forward: too many layers for the reverse-mode gradient");
+    rc = tc_packT_ensure(trunk, precision, s);
+    if (rc != VQN_OK) return rc;
+    const int dev = ctx->device & 15;
+    if (!g_tc_stash[dev]) VQN_CUDA(cudaMalloc(&g_tc_stash[dev], sizeof(float) * (size_t)ctx->sm_count * TC_STASH_FLOATS));
+    B.pg.reverse = 1; B.pg.stash = g_tc_stash[dev];
+    const vqn_net_desc& d = trunk->desc;
+    for (int i = 0; i < nt; ++i) B.pg.layers[i].stash_w = i;          // act' of every hidden layer
+    for (int i = nt - 1; i >= 0; --i) {
+      TcLayer& ly = B.pg.layers[B.pg.n_layers];
+      memset(&ly, 0, sizeof(ly));
+      const bool after_skip = (d.skip_at >= 0 && i == d.skip_at + 1);
+      ly.w = t0->wT[i]; ly.bias = t0->biasT[i];
+      ly.N = ((i == 0) ? d.in_dim : d.widths[i - 1]) + (after_skip ? d.in_dim : 0);
+      ly.Npad = t0->NpadT[i]; ly.act = VQN_ACT_NONE;
+      ly.nseg = 1; ly.seg_type[0] = (i == nt - 1) ? SRC_GRADINIT : SRC_GRAD;
+      ly.seg_chunks[0] = t0->n_chunksT[i]; ly.seg_first_chunk[0] = 0;
+      ly.out_slot = -1; ly.post_scale = 1.f; ly.post_bias = 0.f;
+      ly.tmem_col = (B.pg.n_layers & 1) * 256;
+      ly.tail_out_slot = -1;
+      ly.stash_w = -1; ly.grad_stash = i;
+      ly.egrad_col0 = after_skip ? d.widths[i - 1] : (i == 0 ? 0 : -1);
+      ly.grad_final = (i == 0);
+      B.pg.n_layers++;
+    }
+  }
   return tc_launch(ctx, B.pg, precision, s);
 }

@@ -74,7 +74,8 @@ class _LinStack:
 
 class SDFNetwork(_LinStack):
     def __init__(self, d_in, d_out, d_hidden, n_layers, skip_in=(4,), multires=0, bias=0.5, scale=1,
-                 geometric_init=True, weight_norm=True, inside_outside=False, device='cuda', precision='tf32x3'):
+                 geometric_init=True, weight_norm=True, inside_outside=False, device='cuda', precision='tf32x3',
+                 grad_mode='reverse'):
         if d_in != 3 or multires <= 0:
             raise NotImplementedError('the fused kernel embeds 3-D points in-kernel: d_in == 3 and multires > 0')
         if float(scale) != 1.0:
@@ -83,6 +84,7 @@ class SDFNetwork(_LinStack):
         if len(skip_in) > 1 or any(s < 1 or s >= n_layers for s in skip_in):
             raise NotImplementedError('at most one skip_in layer, inside the hidden stack')
         self.multires, self.skip_in, self.scale, self.precision = int(multires), skip_in, 1.0, precision
+        self.grad_mode = grad_mode          # 'reverse' (default) or 'jet': how the fused kernel evaluates grad sdf
         self.device = torch.device(device)
         d0 = 3 + 6 * self.multires
         dims = [d0] + [d_hidden] * n_layers + [d_out]
@@ -145,7 +147,8 @@ class SDFNetwork(_LinStack):
         else:
             feat_out = None
         sdf, grad = abi.sdf_forward(self._trunk, self._w_sdf, self._b_sdf, self._feat, self.multires, x,
-                                    want_grad=want_grad, feat_out=feat_out, precision=self.precision)
+                                    want_grad=want_grad, feat_out=feat_out, precision=self.precision,
+                                    grad_mode=self.grad_mode)
         feat = feat_out[:, :self.d_feature] if feat_out is not None else None
         return sdf, feat, grad
 
