@@ -378,8 +378,9 @@ def bench_neus_render(dev):
         bg = torch.ones((1, 3), device=dev)
         ms = timed(lambda: r.render(rays_o, rays_d, near, far, 1.0, background_rgb=bg, cos_anneal_ratio=1.0),
                    10 if b == 512 else 3)
-        # network evaluations per ray: SDF value on 64 + 3 x 16 samples, SDF jets + colour on 128 samples
-        flop = b * (112 * 2 * SDF_MACS + 128 * (4 * 2 * SDF_MACS + 2 * COLOR_MACS))
+        # network evaluations per ray: SDF value on 64 + 3 x 16 samples; SDF value + feature + gradient (reverse mode:
+        # forward + transposed trunk) and the colour network on 128 samples
+        flop = b * (112 * 2 * (SDF_TRUNK_MACS + 256) + 128 * (2 * (SDF_MACS + SDF_TRUNK_MACS) + 2 * COLOR_MACS))
         out['rays_%d' % b] = {'ms': ms, 'rays_per_s': b / (ms * 1e-3), 'samples_per_s': b * 128 / (ms * 1e-3),
                               'tflops_executed': flop / (ms * 1e-3) / 1e12}
     # light-visibility extraction (gen_geo.compute_vis): 256 surface points x 512 lights
@@ -397,20 +398,24 @@ def bench_neus_render(dev):
     out['compute_vis_256pts_x_512lights'] = {
         'ms': ms, 'front_lit_rays': n_rays, 'rays_per_s': n_rays / (ms * 1e-3),
         'lvis_entries_per_s': 256 * 512 / (ms * 1e-3), 'mean_lvis': float(lv.mean().item()),
-        'tflops_executed': n_rays * (112 * 2 * (SDF_TRUNK_MACS + 256) + 128 * 4 * 2 * (SDF_TRUNK_MACS + 256)) / (ms * 1e-3) / 1e12,
+        'tflops_executed': n_rays * (112 * 2 * (SDF_TRUNK_MACS + 256) + 128 * 2 * 2 * (SDF_TRUNK_MACS + 256)) / (ms * 1e-3) / 1e12,
         'note': 'every front-lit (point, light) pair is one NeuS render of 64 + 4 x 16 samples; colour network skipped'}
     n = 1 << 20
     pts = torch.rand((n, 3), device=dev) * 2 - 1
     rows = col_net.alloc_rows(n, dev)
+    ms_rev = timed(lambda: sdf_net.forward_with_gradient(pts, feat_out=rows), 3)
+    sdf_net.grad_mode = 'jet'
     ms_jet = timed(lambda: sdf_net.forward_with_gradient(pts, feat_out=rows), 3)
+    sdf_net.grad_mode = 'reverse'
     ms_val = timed(lambda: sdf_net.sdf(pts), 3)
     out['sdf_kernel_1M_points'] = {
-        'value_feature_gradient_ms': ms_jet, 'points_per_s': n / (ms_jet * 1e-3),
-        'tflops_executed': n * 4 * 2 * SDF_MACS / (ms_jet * 1e-3) / 1e12,
-        'tflops_algorithmic': n * 2 * (SDF_MACS + SDF_TRUNK_MACS) / (ms_jet * 1e-3) / 1e12,
+        'value_feature_gradient_ms': ms_rev, 'points_per_s': n / (ms_rev * 1e-3),
+        'tflops': n * 2 * (SDF_MACS + SDF_TRUNK_MACS) / (ms_rev * 1e-3) / 1e12,
+        'jet_mode_ms': ms_jet, 'jet_mode_tflops_executed': n * 4 * 2 * SDF_MACS / (ms_jet * 1e-3) / 1e12,
         'sdf_only_ms': ms_val, 'sdf_only_tflops': n * 2 * (SDF_TRUNK_MACS + 256) / (ms_val * 1e-3) / 1e12,
-        'note': 'jets = 4 MMA-tile rows per point (value + 3 tangents); algorithmic = forward + one reverse-mode pass '
-                'through the trunk (what autograd would execute); 3xTF32 tensor roofline 273 TFLOP/s'}
+        'note': 'gradient in reverse mode inside the launch: forward on value rows with act\' stashed per CTA in L2, then '
+                'the transposed trunk layers (2 row-passes per point); jet mode = 4 tile rows per point (value + 3 '
+                'tangents), nothing stored; 3xTF32 tensor roofline 273 TFLOP/s'}
     return out
 
 
