@@ -1,5 +1,5 @@
-"""One launch each of the NeuS network kernels on 1 M points (for ncu): SDF value + feature + gradient jets,
-SDF value only, colour network.  `ncu --set full -k regex:mlp_tc_kernel python benchmarks/neus_prof.py`"""
+"""One launch each of the NeuS network kernels on 1 M points (for ncu): SDF value + feature + gradient (reverse mode, then
+jets), SDF value only, colour network.  `ncu --set full -k regex:mlp_tc_kernel python benchmarks/neus_prof.py`"""
 import os
 import sys
 
@@ -21,7 +21,10 @@ def main():
     dirs = torch.nn.functional.normalize(torch.randn((n, 3), device=dev), dim=1)
     rows = col_net.alloc_rows(n, dev)
     for _ in range(2):
-        sdf, feat, grad = sdf_net.forward_with_gradient(pts, feat_out=rows)     # jets
+        sdf_net.grad_mode = 'reverse'
+        sdf, feat, grad = sdf_net.forward_with_gradient(pts, feat_out=rows)     # value + feature + gradient (reverse mode)
+        sdf_net.grad_mode = 'jet'
+        sdf_net.forward_with_gradient(pts, feat_out=rows)                       # the same by jets
         s = sdf_net.sdf(pts)                                                    # value only
         col = col_net.forward_rows(rows, pts, grad, dirs)                       # colour network
     torch.cuda.synchronize()

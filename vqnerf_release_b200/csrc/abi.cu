@@ -5,6 +5,9 @@
 
 #include <new>
 
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -32,6 +35,29 @@ extern "C" const char* vqn_status_str(int s) {
   }
 }
 
+namespace {
+struct ScratchEntry { int kind; cudaStream_t stream; void* ptr; size_t bytes; };
+struct ScratchPool { std::mutex mu; std::vector<ScratchEntry> entries; };
+}  // namespace
+
+void* vqn_stream_scratch(vqn_ctx* ctx, int kind, cudaStream_t stream, size_t bytes) {
+  ScratchPool* pool = static_cast<ScratchPool*>(ctx->pool);
+  std::lock_guard<std::mutex> lock(pool->mu);
+  for (ScratchEntry& e : pool->entries)
+    if (e.kind == kind && e.stream == stream) {
+      if (e.bytes >= bytes) return e.ptr;
+      cudaFree(e.ptr);                                   // grow (cudaFree synchronises: no kernel still uses it)
+      e.ptr = nullptr; e.bytes = 0;
+      if (cudaMalloc(&e.ptr, bytes) != cudaSuccess) { vqn_set_error("scratch allocation of %zu bytes failed", bytes); return nullptr; }
+      e.bytes = bytes;
+      return e.ptr;
+    }
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) { vqn_set_error("scratch allocation of %zu bytes failed", bytes); return nullptr; }
+  pool->entries.push_back({kind, stream, p, bytes});
+  return p;
+}
+
 extern "C" int vqn_ctx_create(int device, vqn_ctx** out) {
   VQN_CHECK_ARG(out != nullptr, "out is NULL");
   int count = 0;
@@ -53,6 +79,7 @@ extern "C" int vqn_ctx_create(int device, vqn_ctx** out) {
   vqn_ctx* c = new (std::nothrow) vqn_ctx();
   VQN_CHECK_ARG(c != nullptr, "out of host memory");
   c->device = device;
+  c->pool = new ScratchPool();
   c->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : VQN_SM_COUNT_FALLBACK;
   c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   c->launches.store(0);
@@ -68,6 +95,11 @@ extern "C" int vqn_ctx_destroy(vqn_ctx* ctx) {
   if (!ctx) return VQN_OK;
   cudaFree(ctx->nonfinite_flag);
   cudaFree(ctx->scratch);
+  if (ctx->pool) {
+    ScratchPool* pool = static_cast<ScratchPool*>(ctx->pool);
+    for (ScratchEntry& e : pool->entries) cudaFree(e.ptr);
+    delete pool;
+  }
   delete ctx;
   return VQN_OK;
 }

@@ -17,7 +17,13 @@ struct vqn_ctx {
   int* scratch;         // small persistent device scratch (block counts of the mask compaction, VQ max distance)
   size_t scratch_ints;
   std::atomic<long long> launches;
+  void* pool;           // per-(kind, stream) device buffers of the tensor-core kernels (abi.cu: vqn_stream_scratch)
 };
+
+// Library-owned work buffers that must not be shared between streams (latent scratch of mlp_main, act' stash of the SDF
+// gradient, codebook images of vq_tc): one buffer per (kind, stream), allocated on first use, freed with the context.
+enum { VQN_SCRATCH_Z = 0, VQN_SCRATCH_STASH = 1, VQN_SCRATCH_VQ_W = 2, VQN_SCRATCH_VQ_C2 = 3 };
+void* vqn_stream_scratch(vqn_ctx* ctx, int kind, cudaStream_t stream, size_t bytes);   // nullptr: allocation failed
 #define VQN_SCRATCH_INTS (1 << 16)
 
 void vqn_set_error(const char* fmt, ...);

@@ -1164,7 +1164,6 @@ int vqn_tc_pred_heads(vqn_ctx* ctx, vqn_net* diff, vqn_net* spec, vqn_net* rough
 // scratch (sm_count x 128 KB, L2-resident) between the bottleneck's final drain and the heads' layer-0 producers: it
 // never travels to HBM (the two-launch form wrote and re-read 1 KB per point: 1.3 GB per 800 x 800 view) unless the
 // caller asks for z (z_out != NULL: a second, streaming store).
-static float* g_tc_zscratch[16] = {nullptr};
 int vqn_tc_mlp_main(vqn_ctx* ctx, vqn_net* fe, vqn_net* bn, vqn_net* diff, vqn_net* spec, vqn_net* rough, int n_freqs,
                     const float* pts, const int32_t* row_idx, const int32_t* n_dev, int64_t n, float slope, float bias,
                     float* z_out, float* d, float* sp, float* r, int precision, cudaStream_t s) {
@@ -1183,8 +1182,9 @@ int vqn_tc_mlp_main(vqn_ctx* ctx, vqn_net* fe, vqn_net* bn, vqn_net* diff, vqn_n
     if (rc != VQN_OK) return rc;
     return vqn_tc_pred_heads(ctx, diff, spec, rough, z_out, n_dev, n, slope, bias, d, sp, r, precision, s);
   }
-  const int dev = ctx->device & 15;
-  if (!g_tc_zscratch[dev]) VQN_CUDA(cudaMalloc(&g_tc_zscratch[dev], sizeof(float) * (size_t)ctx->sm_count * TC_M * TC_NPAD_MAX));
+  float* zscratch = static_cast<float*>(
+      vqn_stream_scratch(ctx, VQN_SCRATCH_Z, s, sizeof(float) * (size_t)ctx->sm_count * TC_M * TC_NPAD_MAX));
+  if (!zscratch) return VQN_ERR_CUDA;
   TcPack *t0, *t1;
   int rc = tc_pack_get(fe, precision, s, &t0);
   if (rc != VQN_OK) return rc;
@@ -1192,8 +1192,8 @@ int vqn_tc_mlp_main(vqn_ctx* ctx, vqn_net* fe, vqn_net* bn, vqn_net* diff, vqn_n
   if (rc != VQN_OK) return rc;
   TcBuilder B(precision);
   B.pg.pts = pts; B.pg.row_idx = row_idx; B.pg.n_dev = n_dev; B.pg.n = n; B.pg.n_freqs = n_freqs;
-  B.pg.gsrc = g_tc_zscratch[dev]; B.pg.g_dim = z_dim; B.pg.g_local = 1; B.pg.local_slot = 3; B.pg.out_dup = z_out;
-  B.pg.outs[3] = g_tc_zscratch[dev]; B.pg.out_stride[3] = z_dim;
+  B.pg.gsrc = zscratch; B.pg.g_dim = z_dim; B.pg.g_local = 1; B.pg.local_slot = 3; B.pg.out_dup = z_out;
+  B.pg.outs[3] = zscratch; B.pg.out_stride[3] = z_dim;
   bool ok = tc_append_net(B, fe, t0, SRC_EMBED, -1, 1.f, 0.f) && tc_append_net(B, bn, t1, SRC_DRAIN, 3, 1.f, 0.f);
   for (int h = 0; ok && h < 3; ++h) {
     TcPack* tp;
@@ -1214,7 +1214,6 @@ int vqn_tc_mlp_main(vqn_ctx* ctx, vqn_net* fe, vqn_net* bn, vqn_net* diff, vqn_n
 // Gradient (grad_out): grad_mode 0 = jets (value, d/dx, d/dy, d/dz rows through every layer: 4 row-passes per point,
 // nothing stored); grad_mode 1 = reverse mode (forward on value rows with act' stashed per CTA in an L2-resident scratch,
 // then the transposed layers back to the embedding and a contraction with its Jacobian: 2 row-passes per point).
-static float* g_tc_stash[16] = {nullptr};
 extern "C" int vqn_sdf_forward(vqn_ctx* ctx, vqn_net* trunk, const float* w_sdf, const float* b_sdf, vqn_net* feat,
                                int n_freqs, const float* pts, int64_t n, float* sdf, float* feat_out,
                                int64_t feat_stride, float* grad_out, int grad_mode, int precision, vqn_stream stream) {
@@ -1249,9 +1248,10 @@ extern "C" int vqn_sdf_forward(vqn_ctx* ctx, vqn_net* trunk, const float* w_sdf,
     if (nt > TC_STASH_SLOTS || B.pg.n_layers + nt > TC_MAX_LAYERS) TC_UNSUPPORTED("sdf_forward: too many layers for the reverse-mode gradient");
     rc = tc_packT_ensure(trunk, precision, s);
     if (rc != VQN_OK) return rc;
-    const int dev = ctx->device & 15;
-    if (!g_tc_stash[dev]) VQN_CUDA(cudaMalloc(&g_tc_stash[dev], sizeof(float) * (size_t)ctx->sm_count * TC_STASH_FLOATS));
-    B.pg.reverse = 1; B.pg.stash = g_tc_stash[dev];
+    float* stash = static_cast<float*>(
+        vqn_stream_scratch(ctx, VQN_SCRATCH_STASH, s, sizeof(float) * (size_t)ctx->sm_count * TC_STASH_FLOATS));
+    if (!stash) return VQN_ERR_CUDA;
+    B.pg.reverse = 1; B.pg.stash = stash;
     const vqn_net_desc& d = trunk->desc;
     for (int i = 0; i < nt; ++i) B.pg.layers[i].stash_w = i;          // act' of every hidden layer
     for (int i = nt - 1; i >= 0; --i) {

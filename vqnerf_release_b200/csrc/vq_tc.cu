@@ -345,26 +345,21 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
 
 }  // namespace
 
-// library-owned pack buffers (one set per context would need a ctx field; the codebook images are rebuilt on every
-// call, stream-ordered, so one process-wide set per device is enough)
 int vq_tc_min_k() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("VQN_VQ_TC_MIN_K"); v = e ? atoi(e) : 65; if (v < 16) v = 16; }
   return v;
 }
-static uint8_t* g_vt_wpack[16] = {nullptr};
-static float* g_vt_c2[16] = {nullptr};
 
 int vq_tc_assign_launch(vqn_ctx* ctx, const VqParams& q, cudaStream_t s) {
-  const int dev = ctx->device & 15;
-  if (!g_vt_wpack[dev]) {
-    VQN_CUDA(cudaMalloc(&g_vt_wpack[dev], (size_t)4 * VT_KCHUNKS * VT_W_SLOT));
-    VQN_CUDA(cudaMalloc(&g_vt_c2[dev], sizeof(float) * VT_MAXK));
-  }
+  // codebook images are rebuilt on every call (the codebook is a caller tensor), stream-ordered, in per-stream buffers
+  uint8_t* wpack = static_cast<uint8_t*>(vqn_stream_scratch(ctx, VQN_SCRATCH_VQ_W, s, (size_t)4 * VT_KCHUNKS * VT_W_SLOT));
+  float* c2 = static_cast<float*>(vqn_stream_scratch(ctx, VQN_SCRATCH_VQ_C2, s, sizeof(float) * VT_MAXK));
+  if (!wpack || !c2) return VQN_ERR_CUDA;
   VtParams p;
   p.x = q.x; p.n = q.n; p.cb = q.cb; p.K = q.K; p.nb = (q.K + 255) / 256;
-  p.wpack = g_vt_wpack[dev]; p.c2 = g_vt_c2[dev]; p.idx_out = q.idx_out;
-  vt_pack_kernel<<<256, 256, 0, s>>>(q.cb, q.K, p.nb, g_vt_wpack[dev], g_vt_c2[dev]);
+  p.wpack = wpack; p.c2 = c2; p.idx_out = q.idx_out;
+  vt_pack_kernel<<<256, 256, 0, s>>>(q.cb, q.K, p.nb, wpack, c2);
   VQN_LAUNCHED(ctx);
   const long long tiles = (q.n + VT_M - 1) / VT_M;
   const int blocks = (int)(tiles < (long long)ctx->sm_count ? tiles : (long long)ctx->sm_count);
