@@ -125,9 +125,9 @@ def test_vq_indices_bit_exact(cuda_dev, k):
     _close(out['quantize'], o['quantize'], 'quantize K=%d' % k, rtol=0, atol=1e-6)
 
 
-@pytest.mark.parametrize('n,k', [(4097, 65), (777, 100), (4097, 128), (1, 200), (129, 256), (20000, 257), (3000, 500), (8193, 1024)])
+@pytest.mark.parametrize('n,k', [(5000, 33), (4097, 64), (4097, 65), (777, 100), (4097, 128), (1, 200), (129, 256), (20000, 257), (3000, 500), (8193, 1024)])
 def test_vq_large_codebook_tensor_core_path(cuda_dev, n, k):
-    """K >= 128, indices only: the tcgen05 kernel (csrc/vq_tc.cu) against the float64 oracle AND against the
+    """K > 32, indices only: the tcgen05 kernel (csrc/vq_tc.cu; K <= 128 with TMA tensor-map loads) against the float64 oracle AND against the
     warp-level kernel (taken when other outputs are requested); duplicated codewords resolve to the first index."""
     from vqnerf_release_b200 import abi
     x, cb = _latents(n, k, 77 + k)

@@ -20,7 +20,7 @@ extern "C" int vqn_vq_assign(vqn_ctx* ctx, const float* inputs, int64_t n, int z
   p.normalize = normalize_inputs; p.idx_out = (long long*)indices; p.quant_out = quantize;
   p.dist_out = distances; p.znorm_out = z_norm_out; p.stats = stats; p.want_dw = want_dw;
   cudaStream_t s = vqn_cs(stream);
-  // large codebooks (K > 64), indices only (BASELINE configs[2] sweep): GEMM-shaped -> tcgen05 kernel with an arg-min epilogue
+  // codebooks of K > 32, indices only (BASELINE configs[2] sweep): GEMM-shaped -> tcgen05 kernel with an arg-min epilogue
   if (k >= vq_tc_min_k() && indices && !sel_mask && !normalize_inputs && !quantize && !distances && !z_norm_out && !stats)
     return vq_tc_assign_launch(ctx, p, s);
   return vq_assign_mma_launch(ctx, p, s);

@@ -31,6 +31,6 @@ __device__ __forceinline__ float ord2f(unsigned u) {
 
 // vq_mma.cu: launches the (optional) max-distance pass and the assignment pass for any K
 int vq_assign_mma_launch(vqn_ctx* ctx, VqParams p, cudaStream_t s);
-// vq_tc.cu: K > 64, indices only, on tcgen05/TMEM (3xTF32 split, fp64 near-tie re-score)
+// vq_tc.cu: K > 32, indices only, on tcgen05/TMEM (3xTF32 split, fp64 near-tie re-score)
 int vq_tc_assign_launch(vqn_ctx* ctx, const VqParams& p, cudaStream_t s);
-int vq_tc_min_k();   // smallest K routed to vq_tc.cu (default 65; VQN_VQ_TC_MIN_K overrides, for measurements)
+int vq_tc_min_k();   // smallest K routed to vq_tc.cu (default 33; VQN_VQ_TC_MIN_K overrides, for measurements)

@@ -1,4 +1,4 @@
-// VQ nearest-codeword assignment for LARGE codebooks (K > 64) on the 5th-gen tensor cores (tcgen05 + TMEM).
+// VQ nearest-codeword assignment for codebooks of K > 32 on the 5th-gen tensor cores (tcgen05 + TMEM).
 //
 // Reference: networks/vq_layers.py:279-292 (distances ||x||^2 - 2 x.C + ||c||^2, first-minimum arg-min).
 // BASELINE.json configs[2] sweeps K up to 1024, where the assignment is a [n,256] x [256,K] GEMM with an arg-min
@@ -18,15 +18,22 @@
 //     rows whose two best distances are closer than 4e-5 relative are re-scored in fp64 (warp-cooperative), so the
 //     index is exact whenever the true top-2 gap exceeds the 1e-6 tolerance of BASELINE.json.
 //
+// K <= 128 (one codeword block, SMALLK): the latent chunks come through the TMA engine -- a tensor map with the 128-byte
+// swizzle, four [128 x 32] boxes in flight per SM -- and the 64 KB codebook ring is cut into 2 / 4 / 8 chunk-sized slots.
+// Measured (4 M latents): K = 64 1.62 ms (warp-level kernel: 2.13 ms, it pads K = 33..64 to 8 n-tiles), K = 128 1.84 ms
+// (register loads instead of TMA: 2.49 ms), K = 32 1.49 ms (warp-level kernel: 1.23 ms -> routing starts at K = 33).
+//
 // Indices only (no thres mask, no l2-normalise, no statistics): every other variant stays on vq_mma.cu.
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "tc_common.cuh"
 #include "vq.cuh"
 
 #define VT_M 128
 #define VT_G 2                               // producer groups of 8 warps
-#define VT_THREADS (32 * (8 * VT_G + 2))
+#define VT_THREADS (32 * (8 * VT_G + 3))      // + MMA warp, codebook-stream warp, latent-TMA warp (SMALLK)
 #define VT_A_PLANE (VT_M * 128u)             // 16 KB
 #define VT_A_SLOT (2u * VT_A_PLANE)          // tf32 plane + bf16 correction plane
 #define VT_W_SLOT (256u * 128u * 2u)         // 64 KB
@@ -34,6 +41,12 @@
 #define VT_KCHUNKS (VQ_Z / 32)               // 8 K-chunks of 32 values
 #define VT_MAXK 1024
 #define VT_SMEM (VT_STAGES * VT_A_SLOT + VT_STAGES * VT_W_SLOT + 1024)
+// SMALLK (K <= 128, one codeword block): the codebook chunk is <= 32 KB, so half of the W ring holds a 4-stage staging
+// ring that the TMA engine fills with [128 rows x 128 B] boxes of the latents (tensor map, SWIZZLE_128B)
+#define VT_W_SLOT_SMALL (128u * 128u * 2u)   // 32 KB
+#define VT_XSTAGES 4
+#define VT_WSTAGES_MAX 8                     // SMALLK: the 64 KB codebook ring holds 2 (K <= 128), 4 (K <= 64) or 8 (K <= 32) chunks
+#define VT_X_STAGE (VT_M * 128u)             // 16 KB
 
 namespace {
 
@@ -125,10 +138,23 @@ __device__ __forceinline__ void vt_store16(uint8_t* slot, int r, int j0, const f
 
 __device__ __forceinline__ void vt_group_bar(int grp) { asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory"); }
 
-__global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_constant__ VtParams p) {
+// 2-D tiled TMA load (tensor map in kernel parameter space) -> shared memory, completion counted on `bar` in bytes
+__device__ __forceinline__ void vt_tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int crd0, int crd1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(tc::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(tc::smem_u32(bar)), "r"(crd0),
+               "r"(crd1) : "memory");
+}
+
+// SMALLK: K <= 128 (one codeword block).  There the kernel is bound by the latency of the latent loads, so they go
+// through the TMA engine: one thread keeps VT_XSTAGES boxes of [128 latents x 32 values] in flight (tensor map with the
+// 128-byte swizzle = the layout the producers read conflict-free), the producer groups only split and store.
+template <bool SMALLK>
+__global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_constant__ VtParams p,
+                                                              const __grid_constant__ CUtensorMap xmap) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t a_full[VT_STAGES], a_empty[VT_STAGES], w_full[VT_STAGES], w_empty[VT_STAGES];
+  __shared__ __align__(8) uint64_t a_full[VT_STAGES], a_empty[VT_STAGES], w_full[VT_WSTAGES_MAX], w_empty[VT_WSTAGES_MAX];
   __shared__ __align__(8) uint64_t acc_full[2], drain_done[2];
+  __shared__ __align__(8) uint64_t x_full[VT_XSTAGES], x_empty[VT_XSTAGES];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float c2_s[VT_MAXK];
   __shared__ __align__(16) float4 merge_s[2][VT_M * 4];      // Top2 of the 4 threads of a row, double-buffered by tile
@@ -136,16 +162,21 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_ring = smem;
   uint8_t* w_ring = smem + (size_t)VT_STAGES * VT_A_SLOT;
+  // codebook ring: two 64 KB slots; SMALLK: 64 KB in total, cut into as many chunk-sized slots as fit (the stream of a
+  // small codebook is latency-bound with two slots: every copy waits for the MMAs two chunks back)
+  const uint32_t npad0 = (uint32_t)((min(256, p.K) + 15) / 16 * 16);
+  const uint32_t W_SLOT = SMALLK ? npad0 * 256u : VT_W_SLOT;
+  const uint32_t NWS = SMALLK ? (npad0 <= 32 ? 8u : npad0 <= 64 ? 4u : 2u) : (uint32_t)VT_STAGES;
+  uint8_t* x_ring = w_ring + (size_t)VT_STAGES * VT_W_SLOT_SMALL;       // SMALLK only: the upper half of the W ring
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int MMA_WARP = 8 * VT_G, W_WARP = 8 * VT_G + 1;
+  constexpr int MMA_WARP = 8 * VT_G, W_WARP = 8 * VT_G + 1, X_WARP = 8 * VT_G + 2;
 
   if (warp == MMA_WARP) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
-    for (int i = 0; i < VT_STAGES; ++i) {
-      tc::mbar_init(&a_full[i], 256); tc::mbar_init(&a_empty[i], 1);
-      tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1);
-    }
+    for (int i = 0; i < VT_STAGES; ++i) { tc::mbar_init(&a_full[i], 256); tc::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < VT_WSTAGES_MAX; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&drain_done[i], 256 * VT_G); }
+    for (int i = 0; i < VT_XSTAGES; ++i) { tc::mbar_init(&x_full[i], 1); tc::mbar_init(&x_empty[i], 256); }
     tc::mbar_fence_init();
   }
   for (int i = tid; i < p.nb * 256; i += VT_THREADS) c2_s[i] = p.c2[i];
@@ -238,32 +269,46 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
           if ((int)(ga % VT_G) != grp) continue;
           const int slot = (int)(ga % VT_STAGES);
           uint8_t* dst = a_ring + (size_t)slot * VT_A_SLOT;
-          // coalesced load of the chunk (a warp reads 4 rows x 128 B per instruction), issued BEFORE the slot is claimed.
-          // (Keeping the group's next chunk in flight across the drain was measured slower: 9.6 -> 11.4 ms at K = 1024,
-          // the extra live registers spill inside the arg-min loop.)
-          float4 ldv[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int f = tg + 256 * i, rr = f >> 3, ch = f & 7;
-            const long long prow = tile * VT_M + rr;
-            ldv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (prow < p.n) ldv[i] = __ldg(reinterpret_cast<const float4*>(p.x + prow * VQ_Z + c * 32 + 4 * ch));
-          }
-          tc::mbar_wait(&a_empty[slot], ((ga / VT_STAGES) & 1u) ^ 1u);
-          uint8_t* stage = dst + VT_A_PLANE;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int f = tg + 256 * i, rr = f >> 3, ch = f & 7;
-            *reinterpret_cast<float4*>(stage + rr * 128 + ((ch ^ (rr & 7)) << 4)) = ldv[i];
-          }
-          vt_group_bar(grp);
           float v[16];
+          if (SMALLK) {
+            // the chunk was put into staging buffer ga % VT_XSTAGES by the TMA engine (swizzled like the A planes)
+            const int xs_i = (int)(ga % VT_XSTAGES);
+            tc::mbar_wait(&x_full[xs_i], (ga / VT_XSTAGES) & 1u);
+            const uint8_t* stage = x_ring + (size_t)xs_i * VT_X_STAGE;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 t = *reinterpret_cast<const float4*>(stage + r * 128 + (((4 * half + q) ^ (r & 7)) << 4));
-            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+            for (int q = 0; q < 4; ++q) {
+              const float4 t = *reinterpret_cast<const float4*>(stage + r * 128 + (((4 * half + q) ^ (r & 7)) << 4));
+              v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+            }
+            tc::mbar_arrive(&x_empty[xs_i]);                      // the buffer may be refilled
+            tc::mbar_wait(&a_empty[slot], ((ga / VT_STAGES) & 1u) ^ 1u);
+          } else {
+            // coalesced load of the chunk (a warp reads 4 rows x 128 B per instruction), issued BEFORE the slot is claimed.
+            // (Keeping the group's next chunk in registers across the drain was measured slower: 9.6 -> 11.4 ms at
+            // K = 1024, the extra live registers spill inside the arg-min loop.)
+            float4 ldv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int f = tg + 256 * i, rr = f >> 3, ch = f & 7;
+              const long long prow = tile * VT_M + rr;
+              ldv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (prow < p.n) ldv[i] = __ldg(reinterpret_cast<const float4*>(p.x + prow * VQ_Z + c * 32 + 4 * ch));
+            }
+            tc::mbar_wait(&a_empty[slot], ((ga / VT_STAGES) & 1u) ^ 1u);
+            uint8_t* stage = dst + VT_A_PLANE;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int f = tg + 256 * i, rr = f >> 3, ch = f & 7;
+              *reinterpret_cast<float4*>(stage + rr * 128 + ((ch ^ (rr & 7)) << 4)) = ldv[i];
+            }
+            vt_group_bar(grp);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 t = *reinterpret_cast<const float4*>(stage + r * 128 + (((4 * half + q) ^ (r & 7)) << 4));
+              v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+            }
+            vt_group_bar(grp);                                   // every row has been read before plane C is overwritten
           }
-          vt_group_bar(grp);                                     // every row has been read before plane C is overwritten
           if (b == 0) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) xs = fmaf(v[j], v[j], xs);
@@ -299,11 +344,12 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
           uint32_t acc = 0;
           for (int c = 0; c < VT_KCHUNKS; ++c, ++ga) {
             const int s_ = (int)(ga % VT_STAGES);
+            const int ws = (int)(ga % NWS);
             tc::mbar_wait(&a_full[s_], (ga / VT_STAGES) & 1u);
-            tc::mbar_wait(&w_full[s_], (ga / VT_STAGES) & 1u);
+            tc::mbar_wait(&w_full[ws], (ga / NWS) & 1u);
             tc::fence_after_sync();
             const uint32_t a_addr = tc::smem_u32(a_ring + (size_t)s_ * VT_A_SLOT);
-            const uint32_t w_addr = tc::smem_u32(w_ring + (size_t)s_ * VT_W_SLOT);
+            const uint32_t w_addr = tc::smem_u32(w_ring + (size_t)ws * W_SLOT);
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
               tc::mma_ss<true>(d_tmem, tc::make_desc_sw128(a_addr + 32 * s), tc::make_desc_sw128(w_addr + 32 * s), idesc, acc);
@@ -312,7 +358,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
                                 tc::make_desc_sw128(w_addr + w_plane + 32 * s), idesc_c, 1);
             }
             tc::mma_commit(&a_empty[s_]);
-            tc::mma_commit(&w_empty[s_]);
+            tc::mma_commit(&w_empty[ws]);
           }
           tc::mma_commit(&acc_full[region]);
         }
@@ -328,11 +374,25 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
           const uint32_t bytes = (uint32_t)npad * 128 * 2;
           const uint8_t* wb = p.wpack + (size_t)b * VT_KCHUNKS * VT_W_SLOT;
           for (int c = 0; c < VT_KCHUNKS; ++c, ++gw) {
-            const int s_ = (int)(gw % VT_STAGES);
-            tc::mbar_wait(&w_empty[s_], ((gw / VT_STAGES) & 1u) ^ 1u);
+            const int s_ = (int)(gw % NWS);
+            tc::mbar_wait(&w_empty[s_], ((gw / NWS) & 1u) ^ 1u);
             tc::mbar_expect_tx(&w_full[s_], bytes);
-            tc::bulk_g2s(w_ring + (size_t)s_ * VT_W_SLOT, wb + (size_t)c * bytes, bytes, &w_full[s_]);
+            tc::bulk_g2s(w_ring + (size_t)s_ * W_SLOT, wb + (size_t)c * bytes, bytes, &w_full[s_]);
           }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (SMALLK && warp == X_WARP) {
+    // =========================== latent chunks through the TMA engine (one thread) ===========================
+    if (lane == 0) {
+      uint32_t gx = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int c = 0; c < VT_KCHUNKS; ++c, ++gx) {              // nb == 1
+          const int xs_i = (int)(gx % VT_XSTAGES);
+          tc::mbar_wait(&x_empty[xs_i], ((gx / VT_XSTAGES) & 1u) ^ 1u);
+          tc::mbar_expect_tx(&x_full[xs_i], VT_X_STAGE);
+          vt_tma_load_2d(x_ring + (size_t)xs_i * VT_X_STAGE, &xmap, &x_full[xs_i], c * 32, (int)(tile * VT_M));
         }
       }
     }
@@ -347,7 +407,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
 
 int vq_tc_min_k() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("VQN_VQ_TC_MIN_K"); v = e ? atoi(e) : 65; if (v < 16) v = 16; }
+  if (v < 0) { const char* e = getenv("VQN_VQ_TC_MIN_K"); v = e ? atoi(e) : 33; if (v < 16) v = 16; }
   return v;
 }
 
@@ -363,8 +423,25 @@ int vq_tc_assign_launch(vqn_ctx* ctx, const VqParams& q, cudaStream_t s) {
   VQN_LAUNCHED(ctx);
   const long long tiles = (q.n + VT_M - 1) / VT_M;
   const int blocks = (int)(tiles < (long long)ctx->sm_count ? tiles : (long long)ctx->sm_count);
-  VQN_CUDA(cudaFuncSetAttribute(vq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VT_SMEM));
-  vq_tc_kernel<<<blocks, VT_THREADS, VT_SMEM, s>>>(p);
+  CUtensorMap xmap;
+  memset(&xmap, 0, sizeof(xmap));
+  const bool smallk = q.K <= 128 && (reinterpret_cast<uintptr_t>(q.x) & 15) == 0 && q.n < (1ll << 31);
+  if (smallk) {
+    // latents [n, 256] fp32 row-major; box = 32 values x 128 rows = one K-chunk of a tile; rows past n read as zero
+    const cuuint64_t gdim[2] = {(cuuint64_t)VQ_Z, (cuuint64_t)q.n};
+    const cuuint64_t gstr[1] = {(cuuint64_t)VQ_Z * sizeof(float)};
+    const cuuint32_t box[2] = {32, VT_M};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult cr = cuTensorMapEncodeTiled(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(q.x), gdim, gstr,
+                                               box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { vqn_set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return VQN_ERR_CUDA; }
+    VQN_CUDA(cudaFuncSetAttribute(vq_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VT_SMEM));
+    vq_tc_kernel<true><<<blocks, VT_THREADS, VT_SMEM, s>>>(p, xmap);
+  } else {
+    VQN_CUDA(cudaFuncSetAttribute(vq_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VT_SMEM));
+    vq_tc_kernel<false><<<blocks, VT_THREADS, VT_SMEM, s>>>(p, xmap);
+  }
   VQN_LAUNCHED(ctx);
   return VQN_OK;
 }
