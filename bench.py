@@ -285,8 +285,9 @@ def bench_train_step(dev, rank, world, args):
     return {'rays_per_s': n * world / (ms * 1e-3), 'ms_per_step': ms, 'rays_per_gpu': n, 'global_rays': n * world,
             'allreduce_ms': ar_ms, 'allreduce_bytes': int(st.gflat.numel() * 4), 'kernel_launches_per_step': int(launches),
             'mlp_tflops': TRAIN_FLOP_PER_RAY * n / (ms * 1e-3) / 1e12, 'loss': float(loss), 'eager_ms_per_step': eager_ms,
-            'note': 'whole step (fwd, loss, bwd, all-reduce, EMA, Adam) replayed from one CUDA graph; 3xTF32 dense '
-                    'kernels; eager_ms_per_step = the same kernels launched one by one from Python'}
+            'note': 'whole step (fwd, loss, bwd, all-reduce, EMA, Adam) replayed from one CUDA graph; forward = one fused '
+                    'tcgen05 launch per network with saved activations, backward = 3xTF32 dense kernels; '
+                    'eager_ms_per_step = the same kernels launched one by one from Python'}
 
 
 def bench_neus_scan(dev, hbm_peak):

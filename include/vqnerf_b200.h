@@ -248,6 +248,13 @@ int vqn_scatter_rows(vqn_ctx* ctx, const float* compact, const int32_t* row_idx,
 int vqn_dense_forward(vqn_ctx* ctx, const float* x, int64_t ldx, const float* w, const float* b, float* y,
                       int64_t ldy, int64_t m, int k, int n, int act, float out_scale, float out_bias,
                       vqn_stream stream);
+/* The same forward for a WHOLE network in one launch of the fused tensor-core kernel (precision tf32x3 / bf16): x [n, ldx]
+ * (ldx % 4 == 0, columns >= in_dim zero), y[i] / ldy[i] = output buffer and leading dimension of layer i (the concat
+ * buffers of mlp.py:47-48; the caller copies the x half of a concat).  vqn_net_repack_tc refreshes the pre-split weight
+ * images of one precision from the caller's current weights (after every optimizer step). */
+int vqn_net_forward_train(vqn_ctx* ctx, vqn_net* net, const float* x, int64_t ldx, int64_t n, float* const* y,
+                          const int64_t* ldy, float out_scale, float out_bias, int precision, vqn_stream stream);
+int vqn_net_repack_tc(vqn_net* net, int precision, vqn_stream stream);
 /* dX[m,k] (+)= (dZ[m,n] . W[k,n]^T) * act_prev'(Yprev[m,k]); act_prev' is taken from the stored activation
  * (relu: y > 0, sigmoid: y (1 - y)); accumulate != 0 adds into dX (several consumers of one tensor). */
 int vqn_dense_backward_data(vqn_ctx* ctx, const float* dz, int64_t lddz, const float* w, float* dx, int64_t lddx,

@@ -101,6 +101,8 @@ SIGNATURES = {
     'vqn_neus_light_rays': (_I, [_P, _P, _P, _P, _L, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
     'vqn_neus_lvis_scatter': (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _P, _P]),
     'vqn_dense_forward': (_I, [_P, _P, _L, _P, _P, _P, _L, _L, _I, _I, _I, _F, _F, _P]),
+    'vqn_net_forward_train': (_I, [_P, _P, _P, _L, _L, C.POINTER(_P), C.POINTER(_L), _F, _F, _I, _P]),
+    'vqn_net_repack_tc': (_I, [_P, _I, _P]),
     'vqn_dense_backward_data': (_I, [_P, _P, _L, _P, _P, _L, _P, _L, _I, _I, _L, _I, _I, _P]),
     'vqn_dense_backward_weights': (_I, [_P, _P, _L, _P, _L, _P, _P, _L, _I, _I, _P]),
     'vqn_act_backward': (_I, [_P, _P, _L, _P, _L, _L, _I, _I, _F, _F, _F, _P, _L, _P]),

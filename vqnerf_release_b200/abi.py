@@ -77,6 +77,23 @@ class PackedNet:
         d = self._desc()
         L.check(self.ctx.lib.vqn_net_repack(self.handle, C.byref(d), L.stream_ptr(self.weights[0].device)))
 
+    def repack_tc(self, precision='tf32x3'):
+        """Refresh only the tensor-core weight images of `precision` (after an optimizer step)."""
+        L.check(self.ctx.lib.vqn_net_repack_tc(self.handle, L.precision_code(precision),
+                                               L.stream_ptr(self.weights[0].device)))
+
+    def forward_train(self, x: torch.Tensor, ldx: int, n: int, ys: Sequence[torch.Tensor], lds: Sequence[int],
+                      out_scale: float = 1.0, out_bias: float = 0.0, precision='tf32x3') -> None:
+        """vqn_net_forward_train: the whole network in one launch, every layer's output stored into ys[i] (ld lds[i])."""
+        nl = len(self.weights)
+        if len(ys) != nl or len(lds) != nl:
+            raise ValueError('one activation buffer per layer')
+        yp = (C.c_void_p * nl)(*[y.data_ptr() for y in ys])
+        lp = (C.c_int64 * nl)(*[int(v) for v in lds])
+        L.check(self.ctx.lib.vqn_net_forward_train(self.ctx.handle, self.handle, L.ptr(x, F32), int(ldx), int(n), yp, lp,
+                                                   float(out_scale), float(out_bias), L.precision_code(precision),
+                                                   L.stream_ptr(x.device)))
+
     def forward(self, x: torch.Tensor, precision='fp32') -> torch.Tensor:
         x = _f(x)
         if x.dim() != 2 or x.shape[1] != self.in_dim:

@@ -66,6 +66,10 @@ struct TcLayer {
   // and are contracted with the embedding Jacobian (the skip half of the skip_in layer, and the whole last layer);
   // grad_final: this is the last backward layer -- combine the partial gradients and store d out / d x.
   int stash_w, grad_stash, grad_tail_woff, egrad_col0, grad_final;
+  // Training forward (MODE 3, vqn_net_forward_train): whoever applies this layer's activation also stores the activated
+  // values into save[row * save_ld + col] -- the layer outputs the backward pass needs (mlp.py under GradientTape)
+  float* save;
+  int save_ld;
 };
 
 struct TcProgram {
@@ -95,6 +99,7 @@ struct TcProgram {
   // embedding and a contraction with the embedding's Jacobian: 2 row-passes per point instead of the 4 of the jets.
   int reverse;
   float* stash;            // sm_count x TC_STASH_FLOATS
+  int train;               // MODE 3
   int* nonfinite;
   long long* trace;        // diagnostic (vqn_debug_tc_trace): clock64 stamps of CTA 0's MMA thread, 4 per layer
   TcLayer layers[TC_MAX_LAYERS];
@@ -499,7 +504,8 @@ __device__ __forceinline__ void embed_chunk(uint8_t* slot, int r, const float (&
 // named barrier of one 256-thread epilogue group (ids 1, 2; id 0 is __syncthreads)
 __device__ __forceinline__ void group_bar(int grp) { asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory"); }
 
-// MODE 0: plain chain (decomposition stage, SDF value-only); 1: jets (4 rows per point); 2: reverse-mode gradient
+// MODE 0: plain chain (decomposition stage, SDF value-only); 1: jets (4 rows per point); 2: reverse-mode gradient;
+// 3: plain chain that also stores every hidden layer's output (training forward)
 template <bool BF16, int MODE>
 __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcProgram pg) {
   using C = TcCfg<BF16>;
@@ -546,6 +552,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
   if (n > pg.n) n = pg.n;
   constexpr bool jet = MODE == 1;                        // compile-time: the decomposition-stage kernels carry no jet code
   constexpr bool rev = MODE == 2;
+  constexpr bool trn = MODE == 3;
   constexpr int tile_pts = jet ? TC_M / 4 : TC_M;        // points per tile
   const long long n_tiles = (n + tile_pts - 1) / tile_pts;
   const int L = pg.n_layers;
@@ -677,6 +684,18 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                                      pg.stash + (size_t)blockIdx.x * TC_STASH_FLOATS +
                                          ((size_t)(pg.layers[l - 1].stash_w * 16 + (col0 >> 4)) * TC_M + r) * 16);
                   else bias_act32_dyn(v, pbias + col0, pact);
+                  if (trn && pg.layers[l - 1].save && valid) {      // the previous layer's output, kept for the backward pass
+                    const TcLayer& pl = pg.layers[l - 1];
+                    float* sv = pl.save + (size_t)pi * pl.save_ld + col0;
+                    if (col0 + 16 <= pl.N) {
+#pragma unroll
+                      for (int q = 0; q < 4; ++q)
+                        reinterpret_cast<float4*>(sv)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    } else {
+#pragma unroll
+                      for (int j = 0; j < 16; ++j) if (col0 + j < pl.N) sv[j] = v[j];
+                    }
+                  }
                 } else if (rev && (st == SRC_GRAD || st == SRC_GRADINIT)) {
                   float dv[16];
                   stash_load16(pg.stash + (size_t)blockIdx.x * TC_STASH_FLOATS +
@@ -748,6 +767,12 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                 bias_act32_stash(v, lb + c16, ly.act, pg.stash + (size_t)blockIdx.x * TC_STASH_FLOATS +
                                                           ((size_t)(ly.stash_w * 16 + (c16 >> 4)) * TC_M + r) * 16);
               else bias_act32_dyn(v, lb + c16, ly.act);
+              if (trn && ly.save && valid) {
+                float* sv = ly.save + (size_t)pi * ly.save_ld + c16;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  reinterpret_cast<float4*>(sv)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              }
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const float4 w4 = tw[c16 + j];
@@ -1017,6 +1042,7 @@ static bool tc_append_net(TcBuilder& B, vqn_net* net, TcPack* tp, int first_src,
     ly.tmem_col = (B.pg.n_layers & 1) * 256; ly.skip_w = nullptr; ly.skip_n = 0;
     ly.tail_w = nullptr; ly.tail_b = nullptr; ly.tail_n = 0; ly.tail_out_slot = -1; ly.tail_add_skip = 0;
     ly.stash_w = -1; ly.grad_stash = -1; ly.grad_tail_woff = 0; ly.egrad_col0 = -1; ly.grad_final = 0;
+    ly.save = nullptr; ly.save_ld = 0;
     const bool after_skip = (d.skip_at >= 0 && i == d.skip_at + 1);
     const int seg0_rows = (i == 0) ? d.in_dim : d.widths[i - 1];
     ly.nseg = 1;
@@ -1091,11 +1117,11 @@ static int tc_launch(vqn_ctx* ctx, TcProgram& pg, int precision, cudaStream_t s)
     VQN_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<BF, JT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
     mlp_tc_kernel<BF, JT><<<blocks, TcCfg<BF>::THREADS, smem, s>>>(pg);                                                \
   } while (0)
-  const int mode = pg.jet ? 1 : (pg.reverse ? 2 : 0);
+  const int mode = pg.jet ? 1 : (pg.reverse ? 2 : (pg.train ? 3 : 0));
   if (precision == VQN_PREC_BF16) {
-    if (mode == 1) TC_LAUNCH(true, 1); else if (mode == 2) TC_LAUNCH(true, 2); else TC_LAUNCH(true, 0);
+    if (mode == 1) TC_LAUNCH(true, 1); else if (mode == 2) TC_LAUNCH(true, 2); else if (mode == 3) TC_LAUNCH(true, 3); else TC_LAUNCH(true, 0);
   } else {
-    if (mode == 1) TC_LAUNCH(false, 1); else if (mode == 2) TC_LAUNCH(false, 2); else TC_LAUNCH(false, 0);
+    if (mode == 1) TC_LAUNCH(false, 1); else if (mode == 2) TC_LAUNCH(false, 2); else if (mode == 3) TC_LAUNCH(false, 3); else TC_LAUNCH(false, 0);
   }
 #undef TC_LAUNCH
   VQN_LAUNCHED(ctx);
@@ -1273,4 +1299,43 @@ extern "C" int vqn_sdf_forward(vqn_ctx* ctx, vqn_net* trunk, const float* w_sdf,
     }
   }
   return tc_launch(ctx, B.pg, precision, s);
+}
+
+// Training forward of ONE mlp.Network (networks/mlp.py:39-50 under tf.GradientTape, train_nfr.py:562-576) as a single
+// launch of the fused kernel: every layer's output is stored (y[i], leading dimension ldy[i]: the concat buffers of the
+// skip connections) because the backward pass needs them; x [n, ldx] is the network input (ldx % 4 == 0, columns beyond
+// in_dim zero).  The weight images are refreshed with vqn_net_repack_tc after every optimizer step.
+extern "C" int vqn_net_forward_train(vqn_ctx* ctx, vqn_net* net, const float* x, int64_t ldx, int64_t n, float* const* y,
+                                     const int64_t* ldy, float out_scale, float out_bias, int precision,
+                                     vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && net && x && y && ldy && n >= 0, "net_forward_train: null argument");
+  VQN_CHECK_ARG(precision == VQN_PREC_TF32X3 || precision == VQN_PREC_BF16, "net_forward_train: tensor-core precisions only");
+  VQN_CHECK_ARG(ldx % 4 == 0 && ldx >= net->in_dim && ldx < (1 << 20), "net_forward_train: ldx must be a multiple of 4 >= in_dim");
+  const int L = net->n_layers;
+  for (int i = 0; i < L; ++i)
+    VQN_CHECK_ARG(y[i] && ldy[i] >= net->desc.widths[i] && ldy[i] % 4 == 0 && ldy[i] < (1 << 20) &&
+                      (reinterpret_cast<uintptr_t>(y[i]) & 15) == 0, "net_forward_train: bad activation buffer");
+  if (n == 0) return VQN_OK;
+  cudaStream_t s = vqn_cs(stream);
+  TcPack* tp;
+  int rc = tc_pack_get(net, precision, s, &tp);
+  if (rc != VQN_OK) return rc;
+  TcBuilder B(precision);
+  B.pg.gsrc = x; B.pg.g_dim = (int)ldx; B.pg.n = n; B.pg.train = 1;
+  B.pg.outs[0] = y[L - 1]; B.pg.out_stride[0] = (int)ldy[L - 1];
+  if (!tc_append_net(B, net, tp, SRC_GLOBAL, 0, out_scale, out_bias, true))
+    TC_UNSUPPORTED("net_forward_train: network does not fit the tensor-core kernel");
+  for (int j = 0; j < B.pg.n_layers; ++j) {
+    const bool is_output = (j == L - 1);                     // (absent when the narrow last layer runs as a tail)
+    if (!is_output) { B.pg.layers[j].save = y[j]; B.pg.layers[j].save_ld = (int)ldy[j]; }
+  }
+  return tc_launch(ctx, B.pg, precision, s);
+}
+
+// refresh (or build) only the tensor-core weight images of `precision` from the caller's current weights
+extern "C" int vqn_net_repack_tc(vqn_net* net, int precision, vqn_stream stream) {
+  VQN_CHECK_ARG(net && (precision == VQN_PREC_TF32X3 || precision == VQN_PREC_BF16), "net_repack_tc args");
+  const int p = precision == VQN_PREC_BF16 ? 1 : 0;
+  if (!net->tc_pack[p]) { TcPack* tp; return tc_pack_get(net, precision, vqn_cs(stream), &tp); }   // builds and fills
+  return tc_pack_fill(net, p, vqn_cs(stream));
 }

@@ -15,6 +15,8 @@ gradients, so the collective and the optimizer are each a single launch.
 """
 from __future__ import annotations
 
+import os
+
 import math
 from typing import Dict, List, Optional
 
@@ -69,6 +71,11 @@ class Adam:
         return {'iterations': self.iterations, 'm': self.m, 'v': self.v, 'vhat': self.vhat}
 
 
+# Training forward: one fused tensor-core launch per network (default) or one Dense kernel per layer
+# (VQN_TRAIN_FUSED_FORWARD=0; the per-layer kernels remain the backward path either way)
+FUSED_FORWARD = os.environ.get('VQN_TRAIN_FUSED_FORWARD', '1') != '0'
+
+
 class _NetTrain:
     """Activations and gradient scratch of one mlp.Network for a fixed row count (networks/mlp.py:39-50)."""
 
@@ -97,6 +104,16 @@ class _NetTrain:
 
     def forward(self, x: torch.Tensor, ldx: int) -> torch.Tensor:
         self.x, self.ldx = x, ldx
+        if FUSED_FORWARD and ldx % 4 == 0:
+            # the whole network in ONE launch of the fused tcgen05 kernel (every layer's output stored for the backward
+            # pass); the pre-split weight images are refreshed first because the optimizer has moved the weights
+            packed = self.net.packed
+            packed.repack_tc('tf32x3')
+            packed.forward_train(x, ldx, self.n, self.y, self.ld, self.out_scale, self.out_bias, 'tf32x3')
+            if self.skip is not None:                                     # concat(y, x) (mlp.py:47-48)
+                abi.copy_cols(x, ldx, self.y[self.skip], self.ld[self.skip], self.n, self.in_dim,
+                              dst_off=self.widths[self.skip])
+            return self.y[-1]
         cur, ld = x, ldx
         n_layers = len(self.widths)
         for i, w in enumerate(self.widths):
