@@ -432,9 +432,22 @@ int vq_tc_assign_launch(vqn_ctx* ctx, const VqParams& q, cudaStream_t s) {
     const cuuint64_t gstr[1] = {(cuuint64_t)VQ_Z * sizeof(float)};
     const cuuint32_t box[2] = {32, VT_M};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult cr = cuTensorMapEncodeTiled(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(q.x), gdim, gstr,
-                                               box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    // the driver entry point is resolved through the runtime, so the library has no link-time dependency on libcuda.so
+    // (it must load on machines without a driver: build checks, symbol tests)
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      VQN_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+      if (!fn || qres != cudaDriverEntryPointSuccess) { vqn_set_error("cuTensorMapEncodeTiled is not available"); return VQN_ERR_UNSUPPORTED; }
+      encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    const CUresult cr = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(q.x), gdim, gstr,
+                               box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { vqn_set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return VQN_ERR_CUDA; }
     VQN_CUDA(cudaFuncSetAttribute(vq_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VT_SMEM));
     vq_tc_kernel<true><<<blocks, VT_THREADS, VT_SMEM, s>>>(p, xmap);
