@@ -33,7 +33,8 @@
 
 #define VT_M 128
 #define VT_G 2                               // producer groups of 8 warps
-#define VT_THREADS (32 * (8 * VT_G + 3))      // + MMA warp, codebook-stream warp, latent-TMA warp (SMALLK)
+#define VT_THREADS_BIG (32 * (8 * VT_G + 3))  // K > 128 kernel: + MMA warp, codebook-stream warp, (idle) TMA warp
+#define VT_THREADS (32 * (8 * VT_G + 7))      // + MMA warp, codebook-stream warp, latent-TMA warp (SMALLK), 4 drain warps
 #define VT_A_PLANE (VT_M * 128u)             // 16 KB
 #define VT_A_SLOT (2u * VT_A_PLANE)          // tf32 plane + bf16 correction plane
 #define VT_W_SLOT (256u * 128u * 2u)         // 64 KB
@@ -45,6 +46,7 @@
 // ring that the TMA engine fills with [128 rows x 128 B] boxes of the latents (tensor map, SWIZZLE_128B)
 #define VT_W_SLOT_SMALL (128u * 128u * 2u)   // 32 KB
 #define VT_XSTAGES 4
+#define VT_XSTAGES_MAX 7
 #define VT_WSTAGES_MAX 8                     // SMALLK: the 64 KB codebook ring holds 2 (K <= 128), 4 (K <= 64) or 8 (K <= 32) chunks
 #define VT_X_STAGE (VT_M * 128u)             // 16 KB
 
@@ -154,6 +156,250 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[VT_STAGES], a_empty[VT_STAGES], w_full[VT_WSTAGES_MAX], w_empty[VT_WSTAGES_MAX];
   __shared__ __align__(8) uint64_t acc_full[2], drain_done[2];
+  __shared__ __align__(8) uint64_t x_full[VT_XSTAGES_MAX], x_empty[VT_XSTAGES_MAX];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float c2_s[VT_MAXK];
+  __shared__ float xs_s[2][VT_M * 4];                        // partial ||x||^2 of the 4 producer threads of a row, per tile parity
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_ring = smem;
+  uint8_t* w_ring = smem + (size_t)VT_STAGES * VT_A_SLOT;
+  // codebook ring: two 64 KB slots; SMALLK: 64 KB in total, cut into as many chunk-sized slots as fit (the stream of a
+  // small codebook is latency-bound with two slots: every copy waits for the MMAs two chunks back)
+  const uint32_t npad0 = (uint32_t)((min(256, p.K) + 15) / 16 * 16);
+  const uint32_t W_SLOT = SMALLK ? npad0 * 256u : VT_W_SLOT;
+  const uint32_t NWS = (uint32_t)VT_STAGES;
+  // SMALLK: whatever the two codebook slots leave of the 128 KB goes to the TMA staging ring of the latents (4 boxes of
+  // 16 KB at K = 128, 6 at K <= 64, 7 at K <= 32): the depth of that ring is what bounds the small-K case
+  uint8_t* x_ring = w_ring + (size_t)NWS * W_SLOT;
+  const uint32_t NXS = SMALLK ? min((uint32_t)VT_XSTAGES_MAX, (2u * VT_W_SLOT - NWS * W_SLOT) / VT_X_STAGE) : 1u;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int MMA_WARP = 8 * VT_G, W_WARP = 8 * VT_G + 1, X_WARP = 8 * VT_G + 2, D_WARP0 = 8 * VT_G + 3;
+
+  if (warp == MMA_WARP) tc::tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) {
+    for (int i = 0; i < VT_STAGES; ++i) { tc::mbar_init(&a_full[i], 256); tc::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < VT_WSTAGES_MAX; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&drain_done[i], 128); }
+    for (int i = 0; i < VT_XSTAGES_MAX; ++i) { tc::mbar_init(&x_full[i], 1); tc::mbar_init(&x_empty[i], 256); }
+    tc::mbar_fence_init();
+  }
+  for (int i = tid; i < p.nb * 256; i += VT_THREADS) c2_s[i] = p.c2[i];
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+  const long long n_tiles = (p.n + VT_M - 1) / VT_M;
+  const int nb = p.nb;
+
+  if (warp < 8 * VT_G) {
+    // ===================== producers: A chunks (split into the tf32 + bf16-correction planes), ||x||^2 =====================
+    const int grp = warp >> 3, half = (warp >> 2) & 1, tg = tid & 255;
+    const int r = 32 * (warp & 3) + lane;                          // latent row of the tile
+    uint32_t ga = 0;                                               // global chunk counter
+    uint32_t tile_i = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_i) {
+      float xs = 0.f;
+      for (int b = 0; b < nb; ++b) {
+        for (int c = 0; c < VT_KCHUNKS; ++c, ++ga) {
+          if ((int)(ga % VT_G) != grp) continue;
+          const int slot = (int)(ga % VT_STAGES);
+          uint8_t* dst = a_ring + (size_t)slot * VT_A_SLOT;
+          float v[16];
+          if (SMALLK) {
+            // the chunk was put into staging buffer ga % VT_XSTAGES by the TMA engine (swizzled like the A planes)
+            const int xs_i = (int)(ga % NXS);
+            tc::mbar_wait(&x_full[xs_i], (ga / NXS) & 1u);
+            const uint8_t* stage = x_ring + (size_t)xs_i * VT_X_STAGE;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 t = *reinterpret_cast<const float4*>(stage + r * 128 + (((4 * half + q) ^ (r & 7)) << 4));
+              v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+            }
+            tc::mbar_arrive(&x_empty[xs_i]);                      // the buffer may be refilled
+            tc::mbar_wait(&a_empty[slot], ((ga / VT_STAGES) & 1u) ^ 1u);
+          } else {
+            // coalesced load of the chunk (a warp reads 4 rows x 128 B per instruction), issued BEFORE the slot is claimed
+            float4 ldv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int f = tg + 256 * i, rr = f >> 3, ch = f & 7;
+              const long long prow = tile * VT_M + rr;
+              ldv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (prow < p.n) ldv[i] = __ldg(reinterpret_cast<const float4*>(p.x + prow * VQ_Z + c * 32 + 4 * ch));
+            }
+            tc::mbar_wait(&a_empty[slot], ((ga / VT_STAGES) & 1u) ^ 1u);
+            uint8_t* stage = dst + VT_A_PLANE;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int f = tg + 256 * i, rr = f >> 3, ch = f & 7;
+              *reinterpret_cast<float4*>(stage + rr * 128 + ((ch ^ (rr & 7)) << 4)) = ldv[i];
+            }
+            vt_group_bar(grp);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 t = *reinterpret_cast<const float4*>(stage + r * 128 + (((4 * half + q) ^ (r & 7)) << 4));
+              v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+            }
+            vt_group_bar(grp);                                   // every row has been read before plane C is overwritten
+          }
+          if (b == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) xs = fmaf(v[j], v[j], xs);
+            // the group's last chunk of the tile's first block: publish this thread's share of ||x||^2 for the drain
+            // warps BEFORE the chunk is handed over (they read it after the block's accumulator is complete)
+            if (c + VT_G >= VT_KCHUNKS) xs_s[tile_i & 1u][r * 4 + grp * 2 + half] = xs;
+          }
+          vt_store16(dst, r, 16 * half, v);
+          tc::fence_proxy_async();
+          tc::fence_before_sync();
+          tc::mbar_arrive(&a_full[slot]);
+        }
+      }
+    }
+  } else if (warp >= D_WARP0) {
+    // ===================== drain warps: a thread owns a latent row, arg-min over every codeword block =====================
+    const int q4 = warp & 3;                                       // a warp reaches the TMEM lanes 32 (warp id % 4) ..; the four
+                                                                   // drain warps cover the four quarters
+    const int r = 32 * q4 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q4) << 16);
+    uint32_t gk = 0, tile_i = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_i) {
+      Top2 m = {3.0e38f, 3.0e38f, 0x7fffffff, 0x7fffffff};
+      for (int b = 0; b < nb; ++b, ++gk) {
+        const int region = (int)(gk & 1u);
+        tc::mbar_wait(&acc_full[region], (gk >> 1) & 1u);
+        tc::fence_after_sync();
+        const int nblk = min(256, p.K - 256 * b), npad = (nblk + 15) / 16 * 16;
+        const float* c2b = c2_s + 256 * b;
+        for (int c16 = 0; c16 < npad; c16 += 16) {
+          float v[16];
+          tc::tmem_ld16(lane_addr + (uint32_t)(region * 256 + c16), v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) top2_push(m, fmaf(-2.0f, v[j], c2b[c16 + j]), 256 * b + c16 + j);
+        }
+        tc::fence_before_sync();
+        tc::mbar_arrive(&drain_done[region]);                     // the tensor cores may refill this TMEM region
+      }
+      // ---- the tile's arg-min: near-ties re-scored in fp64, index written ----
+      float xsum = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) xsum += xs_s[tile_i & 1u][r * 4 + q];
+      const long long row = tile * VT_M + r;
+      const bool ok = row < p.n;
+      int best = m.bi;
+      const float full = m.b + xsum;                              // the reference's distance of the winner
+      const bool near = ok && p.K > 1 && (m.s - m.b) <= 4e-5f * fmaxf(fabsf(full), 1e-3f);
+      unsigned need = __ballot_sync(0xffffffffu, near);
+      while (need) {                                              // warp-uniform: fp64 re-score of the two candidates
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const long long rrow = tile * VT_M + 32 * q4 + src;
+        const int i1 = __shfl_sync(0xffffffffu, m.bi, src), i2 = __shfl_sync(0xffffffffu, m.si, src);
+        double d1 = 0.0, d2 = 0.0;
+#pragma unroll
+        for (int mm = 0; mm < 8; ++mm) {
+          const int z = lane + 32 * mm;
+          const double xv = (double)p.x[rrow * VQ_Z + z];
+          const double c1 = (double)p.cb[(size_t)z * p.K + i1], c2v = (double)p.cb[(size_t)z * p.K + i2];
+          d1 += c1 * c1 - 2.0 * xv * c1;
+          d2 += c2v * c2v - 2.0 * xv * c2v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+          d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+        }
+        const bool swap = (d2 < d1) || (d2 == d1 && i2 < i1);
+        if (swap && lane == src) best = i2;
+      }
+      if (ok) p.idx_out[row] = (long long)best;
+    }
+  } else if (warp == MMA_WARP) {
+    if (lane == 0) {
+      uint32_t ga = 0, gk = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int b = 0; b < nb; ++b, ++gk) {
+          const int region = (int)(gk & 1u);
+          const int nblk = min(256, p.K - 256 * b), npad = (nblk + 15) / 16 * 16;
+          const uint32_t idesc = tc::make_idesc(tc::FMT_TF32, VT_M, npad);
+          const uint32_t idesc_c = tc::make_idesc(tc::FMT_BF16, VT_M, npad);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(region * 256);
+          const uint32_t w_plane = (uint32_t)npad * 128;
+          if (gk >= 2) {                                          // the drain of the layer that used this region
+            tc::mbar_wait(&drain_done[region], ((gk - 2) >> 1) & 1u);
+            tc::fence_after_sync();
+          }
+          uint32_t acc = 0;
+          for (int c = 0; c < VT_KCHUNKS; ++c, ++ga) {
+            const int s_ = (int)(ga % VT_STAGES);
+            const int ws = (int)(ga % NWS);
+            tc::mbar_wait(&a_full[s_], (ga / VT_STAGES) & 1u);
+            tc::mbar_wait(&w_full[ws], (ga / NWS) & 1u);
+            tc::fence_after_sync();
+            const uint32_t a_addr = tc::smem_u32(a_ring + (size_t)s_ * VT_A_SLOT);
+            const uint32_t w_addr = tc::smem_u32(w_ring + (size_t)ws * W_SLOT);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+              tc::mma_ss<true>(d_tmem, tc::make_desc_sw128(a_addr + 32 * s), tc::make_desc_sw128(w_addr + 32 * s), idesc, acc);
+              acc = 1;
+              tc::mma_ss<false>(d_tmem, tc::make_desc_sw128(a_addr + VT_A_PLANE + 32 * s),
+                                tc::make_desc_sw128(w_addr + w_plane + 32 * s), idesc_c, 1);
+            }
+            tc::mma_commit(&a_empty[s_]);
+            tc::mma_commit(&w_empty[ws]);
+          }
+          tc::mma_commit(&acc_full[region]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == W_WARP) {
+    if (lane == 0) {
+      uint32_t gw = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int b = 0; b < nb; ++b) {
+          const int nblk = min(256, p.K - 256 * b), npad = (nblk + 15) / 16 * 16;
+          const uint32_t bytes = (uint32_t)npad * 128 * 2;
+          const uint8_t* wb = p.wpack + (size_t)b * VT_KCHUNKS * VT_W_SLOT;
+          for (int c = 0; c < VT_KCHUNKS; ++c, ++gw) {
+            const int s_ = (int)(gw % NWS);
+            tc::mbar_wait(&w_empty[s_], ((gw / NWS) & 1u) ^ 1u);
+            tc::mbar_expect_tx(&w_full[s_], bytes);
+            tc::bulk_g2s(w_ring + (size_t)s_ * W_SLOT, wb + (size_t)c * bytes, bytes, &w_full[s_]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (SMALLK && warp == X_WARP) {
+    // =========================== latent chunks through the TMA engine (one thread) ===========================
+    if (lane == 0) {
+      uint32_t gx = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int c = 0; c < VT_KCHUNKS; ++c, ++gx) {              // nb == 1
+          const int xs_i = (int)(gx % NXS);
+          tc::mbar_wait(&x_empty[xs_i], ((gx / NXS) & 1u) ^ 1u);
+          tc::mbar_expect_tx(&x_full[xs_i], VT_X_STAGE);
+          vt_tma_load_2d(x_ring + (size_t)xs_i * VT_X_STAGE, &xmap, &x_full[xs_i], c * 32, (int)(tile * VT_M));
+        }
+      }
+    }
+    __syncwarp();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == MMA_WARP) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// K > 128 (several codeword blocks): the 16 producer warps also drain the accumulators -- at these sizes the A-chunk
+// production has slack and the extra drain throughput matters (four dedicated drain warps were measured 10 % slower at
+// K = 1024: 9.4 -> 10.4 ms).  Instantiated with SMALLK = false only.
+template <bool SMALLK>
+__global__ void __launch_bounds__(VT_THREADS_BIG, 1) vq_tc_big_kernel(const __grid_constant__ VtParams p,
+                                                              const __grid_constant__ CUtensorMap xmap) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[VT_STAGES], a_empty[VT_STAGES], w_full[VT_WSTAGES_MAX], w_empty[VT_WSTAGES_MAX];
+  __shared__ __align__(8) uint64_t acc_full[2], drain_done[2];
   __shared__ __align__(8) uint64_t x_full[VT_XSTAGES], x_empty[VT_XSTAGES];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float c2_s[VT_MAXK];
@@ -179,7 +425,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
     for (int i = 0; i < VT_XSTAGES; ++i) { tc::mbar_init(&x_full[i], 1); tc::mbar_init(&x_empty[i], 256); }
     tc::mbar_fence_init();
   }
-  for (int i = tid; i < p.nb * 256; i += VT_THREADS) c2_s[i] = p.c2[i];
+  for (int i = tid; i < p.nb * 256; i += VT_THREADS_BIG) c2_s[i] = p.c2[i];
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -447,13 +693,13 @@ int vq_tc_assign_launch(vqn_ctx* ctx, const VqParams& q, cudaStream_t s) {
     }
     const CUresult cr = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(q.x), gdim, gstr,
                                box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { vqn_set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return VQN_ERR_CUDA; }
     VQN_CUDA(cudaFuncSetAttribute(vq_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VT_SMEM));
     vq_tc_kernel<true><<<blocks, VT_THREADS, VT_SMEM, s>>>(p, xmap);
   } else {
-    VQN_CUDA(cudaFuncSetAttribute(vq_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VT_SMEM));
-    vq_tc_kernel<false><<<blocks, VT_THREADS, VT_SMEM, s>>>(p, xmap);
+    VQN_CUDA(cudaFuncSetAttribute(vq_tc_big_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VT_SMEM));
+    vq_tc_big_kernel<false><<<blocks, VT_THREADS_BIG, VT_SMEM, s>>>(p, xmap);
   }
   VQN_LAUNCHED(ctx);
   return VQN_OK;
