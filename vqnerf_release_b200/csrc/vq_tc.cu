@@ -18,10 +18,11 @@
 //     rows whose two best distances are closer than 4e-5 relative are re-scored in fp64 (warp-cooperative), so the
 //     index is exact whenever the true top-2 gap exceeds the 1e-6 tolerance of BASELINE.json.
 //
-// K <= 128 (one codeword block, SMALLK): the latent chunks come through the TMA engine -- a tensor map with the 128-byte
-// swizzle, four [128 x 32] boxes in flight per SM -- and the 64 KB codebook ring is cut into 2 / 4 / 8 chunk-sized slots.
-// Measured (4 M latents): K = 64 1.62 ms (warp-level kernel: 2.13 ms, it pads K = 33..64 to 8 n-tiles), K = 128 1.84 ms
-// (register loads instead of TMA: 2.49 ms), K = 32 1.49 ms (warp-level kernel: 1.23 ms -> routing starts at K = 33).
+// K <= 128 (one codeword block, vq_tc_kernel<true>): the latent chunks come through the TMA engine -- a tensor map with the
+// 128-byte swizzle, 4..7 [128 x 32] boxes in flight per SM -- and four dedicated drain warps (a thread owns a row) take the
+// arg-min off the producers.  K > 128: vq_tc_big_kernel (producers drain, four partial results per row merged in smem).
+// Measured (4 M latents): K = 64 1.36 ms (warp-level kernel: 2.13 ms, it pads K = 33..64 to 8 n-tiles), K = 128 1.64 ms
+// (register loads, producers draining: 2.49 ms), K = 32 1.32 ms (warp-level kernel: 1.24 ms -> routing starts at K = 33).
 //
 // Indices only (no thres mask, no l2-normalise, no statistics): every other variant stays on vq_mma.cu.
 #include <cuda.h>
