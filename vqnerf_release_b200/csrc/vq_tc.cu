@@ -90,7 +90,7 @@ __global__ void vt_pack_kernel(const float* __restrict__ cb, int K, int nb, uint
     const int nrow = (int)((i / 32) % 256);
     const int c = (int)((i / (32 * 256)) % VT_KCHUNKS);
     const int b = (int)(i / (32 * 256 * VT_KCHUNKS));
-    const int nblk = min(256, K - 256 * b), npad = (nblk + 15) / 16 * 16;
+    const int nblk = min(256, K - 256 * b), npad = nblk <= 0 ? 16 : (nblk + 15) / 16 * 16;   // nblk <= 0: padding block
     if (nrow >= npad) continue;
     const int z = c * 32 + kk, col = 256 * b + nrow;
     const float v = nrow < nblk ? cb[(size_t)z * K + col] : 0.f;
@@ -392,16 +392,18 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
   if (warp == MMA_WARP) tc::tmem_dealloc(tmem_base, 512);
 }
 
-// K > 128 (several codeword blocks): the 16 producer warps also drain the accumulators -- at these sizes the A-chunk
-// production has slack and the extra drain throughput matters (four dedicated drain warps were measured 10 % slower at
-// K = 1024: 9.4 -> 10.4 ms).  Instantiated with SMALLK = false only.
-template <bool SMALLK>
-__global__ void __launch_bounds__(VT_THREADS_BIG, 1) vq_tc_big_kernel(const __grid_constant__ VtParams p,
-                                                              const __grid_constant__ CUtensorMap xmap) {
+// K > 128: the 16 producer warps also drain the accumulators (at these sizes the A-chunk production has slack and the
+// extra drain throughput matters: four dedicated drain warps were measured 10 % slower at K = 1024, 9.4 -> 10.4 ms).
+//   PAIR = false (one codeword block, 128 < K <= 256): a "layer" is one block; TMEM regions ping-pong between tiles.
+//   PAIR = true  (K > 256): a layer is a PAIR of blocks -- every A chunk feeds two MMAs, block 2j into TMEM region 0 and
+//   block 2j+1 into region 1 -- because re-producing the A chunks per block (load, split, 32 KB of smem stores) was what
+//   bounded the large-K case; the block count is padded to an even number (an all-padding block never wins).  Both
+//   regions are busy during a layer, so its drain runs between layers instead of under the next layer's MMAs.
+template <bool PAIR>
+__global__ void __launch_bounds__(VT_THREADS_BIG, 1) vq_tc_big_kernel(const __grid_constant__ VtParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t a_full[VT_STAGES], a_empty[VT_STAGES], w_full[VT_WSTAGES_MAX], w_empty[VT_WSTAGES_MAX];
+  __shared__ __align__(8) uint64_t a_full[VT_STAGES], a_empty[VT_STAGES], w_full[VT_STAGES], w_empty[VT_STAGES];
   __shared__ __align__(8) uint64_t acc_full[2], drain_done[2];
-  __shared__ __align__(8) uint64_t x_full[VT_XSTAGES], x_empty[VT_XSTAGES];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float c2_s[VT_MAXK];
   __shared__ __align__(16) float4 merge_s[2][VT_M * 4];      // Top2 of the 4 threads of a row, double-buffered by tile
@@ -409,21 +411,17 @@ __global__ void __launch_bounds__(VT_THREADS_BIG, 1) vq_tc_big_kernel(const __gr
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_ring = smem;
   uint8_t* w_ring = smem + (size_t)VT_STAGES * VT_A_SLOT;
-  // codebook ring: two 64 KB slots; SMALLK: 64 KB in total, cut into as many chunk-sized slots as fit (the stream of a
-  // small codebook is latency-bound with two slots: every copy waits for the MMAs two chunks back)
-  const uint32_t npad0 = (uint32_t)((min(256, p.K) + 15) / 16 * 16);
-  const uint32_t W_SLOT = SMALLK ? npad0 * 256u : VT_W_SLOT;
-  const uint32_t NWS = SMALLK ? (npad0 <= 32 ? 8u : npad0 <= 64 ? 4u : 2u) : (uint32_t)VT_STAGES;
-  uint8_t* x_ring = w_ring + (size_t)VT_STAGES * VT_W_SLOT_SMALL;       // SMALLK only: the upper half of the W ring
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int MMA_WARP = 8 * VT_G, W_WARP = 8 * VT_G + 1, X_WARP = 8 * VT_G + 2;
+  constexpr int MMA_WARP = 8 * VT_G, W_WARP = 8 * VT_G + 1;
+  constexpr int BPL = PAIR ? 2 : 1;                                // codeword blocks per layer
 
   if (warp == MMA_WARP) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
-    for (int i = 0; i < VT_STAGES; ++i) { tc::mbar_init(&a_full[i], 256); tc::mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < VT_WSTAGES_MAX; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < VT_STAGES; ++i) {
+      tc::mbar_init(&a_full[i], 256); tc::mbar_init(&a_empty[i], 1);
+      tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1);
+    }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&drain_done[i], 256 * VT_G); }
-    for (int i = 0; i < VT_XSTAGES; ++i) { tc::mbar_init(&x_full[i], 1); tc::mbar_init(&x_empty[i], 256); }
     tc::mbar_fence_init();
   }
   for (int i = tid; i < p.nb * 256; i += VT_THREADS_BIG) c2_s[i] = p.c2[i];
@@ -432,7 +430,9 @@ __global__ void __launch_bounds__(VT_THREADS_BIG, 1) vq_tc_big_kernel(const __gr
   tc::fence_after_sync();
   const uint32_t tmem_base = tmem_base_s;
   const long long n_tiles = (p.n + VT_M - 1) / VT_M;
-  const int nb = p.nb;
+  const int nl = p.nb / BPL;                                       // layers per tile (p.nb is even in PAIR mode)
+  // columns of codeword block b (a padding block of PAIR mode has 16 all-padding columns)
+  auto npad_of = [&](int b) { const int nblk = min(256, p.K - 256 * b); return nblk <= 0 ? 16 : (nblk + 15) / 16 * 16; };
 
   if (warp < 8 * VT_G) {
     // ===================== producers: A chunks, accumulator drain, arg-min =====================
@@ -442,27 +442,31 @@ __global__ void __launch_bounds__(VT_THREADS_BIG, 1) vq_tc_big_kernel(const __gr
     uint32_t ga = 0, gk = 0;                                       // global chunk / layer counters
     Top2 t2 = {3.0e38f, 3.0e38f, 0, 0};
     float xs = 0.f, xs_fin = 0.f;
-    long long pend_tile = -1; int pend_b = 0; uint32_t pend_k = 0; uint32_t tiles_done = 0;
+    long long pend_tile = -1; int pend_l = 0; uint32_t pend_k = 0; uint32_t tiles_done = 0;
 
-    auto drain = [&](long long tile, int b, uint32_t k) {
-      const int region = (int)(k & 1u);
-      tc::mbar_wait(&acc_full[region], (k >> 1) & 1u);
-      tc::fence_after_sync();
-      const int nblk = min(256, p.K - 256 * b), npad = (nblk + 15) / 16 * 16;
-      const float* c2b = c2_s + 256 * b;
-      for (int cbk = grp; cbk * 32 < npad; cbk += VT_G) {
-        const int c16 = cbk * 32 + 16 * half;
-        if (c16 < npad) {
-          float v[16];
-          tc::tmem_ld16(lane_addr + (uint32_t)(region * 256 + c16), v);
+    auto drain = [&](long long tile, int l, uint32_t k) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) top2_push(t2, fmaf(-2.0f, v[j], c2b[c16 + j]), 256 * b + c16 + j);
+      for (int h2 = 0; h2 < BPL; ++h2) {
+        const int region = PAIR ? h2 : (int)(k & 1u);
+        const int b = PAIR ? 2 * l + h2 : l;
+        tc::mbar_wait(&acc_full[region], PAIR ? (k & 1u) : ((k >> 1) & 1u));
+        tc::fence_after_sync();
+        const int npad = npad_of(b);
+        const float* c2b = c2_s + 256 * b;
+        for (int cbk = grp; cbk * 32 < npad; cbk += VT_G) {
+          const int c16 = cbk * 32 + 16 * half;
+          if (c16 < npad) {
+            float v[16];
+            tc::tmem_ld16(lane_addr + (uint32_t)(region * 256 + c16), v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) top2_push(t2, fmaf(-2.0f, v[j], c2b[c16 + j]), 256 * b + c16 + j);
+          }
         }
+        tc::fence_before_sync();
+        tc::mbar_arrive(&drain_done[region]);
       }
-      tc::fence_before_sync();
-      tc::mbar_arrive(&drain_done[region]);
-      if (b + 1 < nb) return;
-      // ---- last block of the tile: merge the 4 partial results of each row, re-score near-ties, write the index ----
+      if (l + 1 < nl) return;
+      // ---- last layer of the tile: merge the 4 partial results of each row, re-score near-ties, write the index ----
       const int buf = (int)(tiles_done & 1u);
       ++tiles_done;
       merge_s[buf][r * 4 + grp * 2 + half] = make_float4(t2.b, t2.s, __int_as_float(t2.bi), __int_as_float(t2.si));
@@ -511,52 +515,38 @@ __global__ void __launch_bounds__(VT_THREADS_BIG, 1) vq_tc_big_kernel(const __gr
     };
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      for (int b = 0; b < nb; ++b, ++gk) {
+      for (int l = 0; l < nl; ++l, ++gk) {
         for (int c = 0; c < VT_KCHUNKS; ++c, ++ga) {
           if ((int)(ga % VT_G) != grp) continue;
           const int slot = (int)(ga % VT_STAGES);
           uint8_t* dst = a_ring + (size_t)slot * VT_A_SLOT;
-          float v[16];
-          if (SMALLK) {
-            // the chunk was put into staging buffer ga % VT_XSTAGES by the TMA engine (swizzled like the A planes)
-            const int xs_i = (int)(ga % VT_XSTAGES);
-            tc::mbar_wait(&x_full[xs_i], (ga / VT_XSTAGES) & 1u);
-            const uint8_t* stage = x_ring + (size_t)xs_i * VT_X_STAGE;
+          // coalesced load of the chunk (a warp reads 4 rows x 128 B per instruction), issued BEFORE the slot is claimed.
+          // (Keeping the group's next chunk in registers across the drain was measured slower: 9.6 -> 11.4 ms at
+          // K = 1024, the extra live registers spill inside the arg-min loop.)
+          float4 ldv[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 t = *reinterpret_cast<const float4*>(stage + r * 128 + (((4 * half + q) ^ (r & 7)) << 4));
-              v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-            }
-            tc::mbar_arrive(&x_empty[xs_i]);                      // the buffer may be refilled
-            tc::mbar_wait(&a_empty[slot], ((ga / VT_STAGES) & 1u) ^ 1u);
-          } else {
-            // coalesced load of the chunk (a warp reads 4 rows x 128 B per instruction), issued BEFORE the slot is claimed.
-            // (Keeping the group's next chunk in registers across the drain was measured slower: 9.6 -> 11.4 ms at
-            // K = 1024, the extra live registers spill inside the arg-min loop.)
-            float4 ldv[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int f = tg + 256 * i, rr = f >> 3, ch = f & 7;
-              const long long prow = tile * VT_M + rr;
-              ldv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (prow < p.n) ldv[i] = __ldg(reinterpret_cast<const float4*>(p.x + prow * VQ_Z + c * 32 + 4 * ch));
-            }
-            tc::mbar_wait(&a_empty[slot], ((ga / VT_STAGES) & 1u) ^ 1u);
-            uint8_t* stage = dst + VT_A_PLANE;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int f = tg + 256 * i, rr = f >> 3, ch = f & 7;
-              *reinterpret_cast<float4*>(stage + rr * 128 + ((ch ^ (rr & 7)) << 4)) = ldv[i];
-            }
-            vt_group_bar(grp);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 t = *reinterpret_cast<const float4*>(stage + r * 128 + (((4 * half + q) ^ (r & 7)) << 4));
-              v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-            }
-            vt_group_bar(grp);                                   // every row has been read before plane C is overwritten
+          for (int i = 0; i < 4; ++i) {
+            const int f = tg + 256 * i, rr = f >> 3, ch = f & 7;
+            const long long prow = tile * VT_M + rr;
+            ldv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (prow < p.n) ldv[i] = __ldg(reinterpret_cast<const float4*>(p.x + prow * VQ_Z + c * 32 + 4 * ch));
           }
-          if (b == 0) {
+          tc::mbar_wait(&a_empty[slot], ((ga / VT_STAGES) & 1u) ^ 1u);
+          uint8_t* stage = dst + VT_A_PLANE;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int f = tg + 256 * i, rr = f >> 3, ch = f & 7;
+            *reinterpret_cast<float4*>(stage + rr * 128 + ((ch ^ (rr & 7)) << 4)) = ldv[i];
+          }
+          vt_group_bar(grp);
+          float v[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 t = *reinterpret_cast<const float4*>(stage + r * 128 + (((4 * half + q) ^ (r & 7)) << 4));
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+          }
+          vt_group_bar(grp);                                     // every row has been read before plane C is overwritten
+          if (l == 0) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) xs = fmaf(v[j], v[j], xs);
           }
@@ -565,49 +555,66 @@ __global__ void __launch_bounds__(VT_THREADS_BIG, 1) vq_tc_big_kernel(const __gr
           tc::fence_before_sync();
           tc::mbar_arrive(&a_full[slot]);
         }
-        // the previous layer is drained while the tensor cores work on this one
-        if (pend_tile >= 0) drain(pend_tile, pend_b, pend_k);
-        pend_tile = tile; pend_b = b; pend_k = gk;
-        if (b == nb - 1) { xs_fin = xs; xs = 0.f; }
-        else if (b == 0 && nb > 1) { /* xs complete after block 0; kept until the tile's last drain */ }
+        if (PAIR) {
+          if (l == nl - 1) { xs_fin = xs; xs = 0.f; }
+          drain(tile, l, gk);                                    // both regions are busy: the next layer waits for this drain
+        } else {
+          // the previous layer (of the previous tile: xs_fin still holds ITS ||x||^2) is drained while the tensor cores
+          // work on this one
+          if (pend_tile >= 0) drain(pend_tile, pend_l, pend_k);
+          pend_tile = tile; pend_l = l; pend_k = gk;
+          if (l == nl - 1) { xs_fin = xs; xs = 0.f; }
+        }
       }
     }
-    if (pend_tile >= 0) drain(pend_tile, pend_b, pend_k);
+    if (!PAIR && pend_tile >= 0) drain(pend_tile, pend_l, pend_k);
   } else if (warp == MMA_WARP) {
     if (lane == 0) {
-      uint32_t ga = 0, gk = 0;
+      uint32_t ga = 0, gk = 0, gw = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int b = 0; b < nb; ++b, ++gk) {
-          const int region = (int)(gk & 1u);
-          const int nblk = min(256, p.K - 256 * b), npad = (nblk + 15) / 16 * 16;
-          const uint32_t idesc = tc::make_idesc(tc::FMT_TF32, VT_M, npad);
-          const uint32_t idesc_c = tc::make_idesc(tc::FMT_BF16, VT_M, npad);
-          const uint32_t d_tmem = tmem_base + (uint32_t)(region * 256);
-          const uint32_t w_plane = (uint32_t)npad * 128;
-          if (gk >= 2) {                                          // the drain of the layer that used this region
-            tc::mbar_wait(&drain_done[region], ((gk - 2) >> 1) & 1u);
+        for (int l = 0; l < nl; ++l, ++gk) {
+          if (PAIR) {
+            if (gk >= 1) {                                        // both regions: the drain of the previous layer
+              tc::mbar_wait(&drain_done[0], (gk - 1) & 1u);
+              tc::mbar_wait(&drain_done[1], (gk - 1) & 1u);
+              tc::fence_after_sync();
+            }
+          } else if (gk >= 2) {                                   // the drain of the layer that used this region
+            tc::mbar_wait(&drain_done[gk & 1u], ((gk - 2) >> 1) & 1u);
             tc::fence_after_sync();
           }
           uint32_t acc = 0;
           for (int c = 0; c < VT_KCHUNKS; ++c, ++ga) {
             const int s_ = (int)(ga % VT_STAGES);
-            const int ws = (int)(ga % NWS);
             tc::mbar_wait(&a_full[s_], (ga / VT_STAGES) & 1u);
-            tc::mbar_wait(&w_full[ws], (ga / NWS) & 1u);
-            tc::fence_after_sync();
             const uint32_t a_addr = tc::smem_u32(a_ring + (size_t)s_ * VT_A_SLOT);
-            const uint32_t w_addr = tc::smem_u32(w_ring + (size_t)ws * W_SLOT);
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-              tc::mma_ss<true>(d_tmem, tc::make_desc_sw128(a_addr + 32 * s), tc::make_desc_sw128(w_addr + 32 * s), idesc, acc);
-              acc = 1;
-              tc::mma_ss<false>(d_tmem, tc::make_desc_sw128(a_addr + VT_A_PLANE + 32 * s),
-                                tc::make_desc_sw128(w_addr + w_plane + 32 * s), idesc_c, 1);
+            for (int h2 = 0; h2 < BPL; ++h2, ++gw) {
+              const int region = PAIR ? h2 : (int)(gk & 1u);
+              const int npad = npad_of(PAIR ? 2 * l + h2 : l);
+              const uint32_t idesc = tc::make_idesc(tc::FMT_TF32, VT_M, npad);
+              const uint32_t idesc_c = tc::make_idesc(tc::FMT_BF16, VT_M, npad);
+              const uint32_t d_tmem = tmem_base + (uint32_t)(region * 256);
+              const uint32_t w_plane = (uint32_t)npad * 128;
+              const int ws = (int)(gw % VT_STAGES);
+              tc::mbar_wait(&w_full[ws], (gw / VT_STAGES) & 1u);
+              tc::fence_after_sync();
+              const uint32_t w_addr = tc::smem_u32(w_ring + (size_t)ws * VT_W_SLOT);
+              uint32_t first = acc;                               // 0 only for the first K-step of the layer's first chunk
+#pragma unroll
+              for (int s = 0; s < 4; ++s) {
+                tc::mma_ss<true>(d_tmem, tc::make_desc_sw128(a_addr + 32 * s), tc::make_desc_sw128(w_addr + 32 * s), idesc, first);
+                first = 1;
+                tc::mma_ss<false>(d_tmem, tc::make_desc_sw128(a_addr + VT_A_PLANE + 32 * s),
+                                  tc::make_desc_sw128(w_addr + w_plane + 32 * s), idesc_c, 1);
+              }
+              tc::mma_commit(&w_empty[ws]);
             }
+            acc = 1;
             tc::mma_commit(&a_empty[s_]);
-            tc::mma_commit(&w_empty[ws]);
           }
-          tc::mma_commit(&acc_full[region]);
+          if (PAIR) { tc::mma_commit(&acc_full[0]); tc::mma_commit(&acc_full[1]); }
+          else tc::mma_commit(&acc_full[gk & 1u]);
         }
       }
     }
@@ -616,30 +623,19 @@ __global__ void __launch_bounds__(VT_THREADS_BIG, 1) vq_tc_big_kernel(const __gr
     if (lane == 0) {
       uint32_t gw = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int b = 0; b < nb; ++b) {
-          const int nblk = min(256, p.K - 256 * b), npad = (nblk + 15) / 16 * 16;
-          const uint32_t bytes = (uint32_t)npad * 128 * 2;
-          const uint8_t* wb = p.wpack + (size_t)b * VT_KCHUNKS * VT_W_SLOT;
-          for (int c = 0; c < VT_KCHUNKS; ++c, ++gw) {
-            const int s_ = (int)(gw % NWS);
-            tc::mbar_wait(&w_empty[s_], ((gw / NWS) & 1u) ^ 1u);
-            tc::mbar_expect_tx(&w_full[s_], bytes);
-            tc::bulk_g2s(w_ring + (size_t)s_ * W_SLOT, wb + (size_t)c * bytes, bytes, &w_full[s_]);
+        for (int l = 0; l < nl; ++l) {
+          for (int c = 0; c < VT_KCHUNKS; ++c) {
+#pragma unroll
+            for (int h2 = 0; h2 < BPL; ++h2, ++gw) {
+              const int b = PAIR ? 2 * l + h2 : l;
+              const uint32_t bytes = (uint32_t)npad_of(b) * 128 * 2;
+              const uint8_t* wb = p.wpack + (size_t)b * VT_KCHUNKS * VT_W_SLOT;
+              const int s_ = (int)(gw % VT_STAGES);
+              tc::mbar_wait(&w_empty[s_], ((gw / VT_STAGES) & 1u) ^ 1u);
+              tc::mbar_expect_tx(&w_full[s_], bytes);
+              tc::bulk_g2s(w_ring + (size_t)s_ * VT_W_SLOT, wb + (size_t)c * bytes, bytes, &w_full[s_]);
+            }
           }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (SMALLK && warp == X_WARP) {
-    // =========================== latent chunks through the TMA engine (one thread) ===========================
-    if (lane == 0) {
-      uint32_t gx = 0;
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int c = 0; c < VT_KCHUNKS; ++c, ++gx) {              // nb == 1
-          const int xs_i = (int)(gx % VT_XSTAGES);
-          tc::mbar_wait(&x_empty[xs_i], ((gx / VT_XSTAGES) & 1u) ^ 1u);
-          tc::mbar_expect_tx(&x_full[xs_i], VT_X_STAGE);
-          vt_tma_load_2d(x_ring + (size_t)xs_i * VT_X_STAGE, &xmap, &x_full[xs_i], c * 32, (int)(tile * VT_M));
         }
       }
     }
@@ -665,6 +661,7 @@ int vq_tc_assign_launch(vqn_ctx* ctx, const VqParams& q, cudaStream_t s) {
   if (!wpack || !c2) return VQN_ERR_CUDA;
   VtParams p;
   p.x = q.x; p.n = q.n; p.cb = q.cb; p.K = q.K; p.nb = (q.K + 255) / 256;
+  if (p.nb > 1 && (p.nb & 1)) p.nb += 1;        // K > 256: blocks are processed in pairs (an all-padding block never wins)
   p.wpack = wpack; p.c2 = c2; p.idx_out = q.idx_out;
   vt_pack_kernel<<<256, 256, 0, s>>>(q.cb, q.K, p.nb, wpack, c2);
   VQN_LAUNCHED(ctx);
@@ -698,9 +695,12 @@ int vq_tc_assign_launch(vqn_ctx* ctx, const VqParams& q, cudaStream_t s) {
     if (cr != CUDA_SUCCESS) { vqn_set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return VQN_ERR_CUDA; }
     VQN_CUDA(cudaFuncSetAttribute(vq_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VT_SMEM));
     vq_tc_kernel<true><<<blocks, VT_THREADS, VT_SMEM, s>>>(p, xmap);
+  } else if (p.nb > 1) {
+    VQN_CUDA(cudaFuncSetAttribute(vq_tc_big_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VT_SMEM));
+    vq_tc_big_kernel<true><<<blocks, VT_THREADS_BIG, VT_SMEM, s>>>(p);
   } else {
     VQN_CUDA(cudaFuncSetAttribute(vq_tc_big_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VT_SMEM));
-    vq_tc_big_kernel<false><<<blocks, VT_THREADS_BIG, VT_SMEM, s>>>(p, xmap);
+    vq_tc_big_kernel<false><<<blocks, VT_THREADS_BIG, VT_SMEM, s>>>(p);
   }
   VQN_LAUNCHED(ctx);
   return VQN_OK;
