@@ -28,7 +28,7 @@ def main():
     n = args.points
     xyz = torch.rand((n, 3), device=dev) * 2 - 1
     nf = m.embedder['xyz'].n_freqs
-    buf = torch.zeros((256 + 8 * 96,), dtype=torch.int64, device=dev)
+    buf = torch.zeros((320 + 8 * 96,), dtype=torch.int64, device=dev)      # 4 tiles x TC_MAX_LAYERS (20) x 4 stamps, then the producer trace
     ctx.lib.vqn_debug_tc_trace.argtypes = [C.c_void_p]
     for which in ('encoder', 'heads'):
         z = abi.pred_enc_at(m.net['fine_enc'].packed, m.net['bottleneck'].packed, nf, xyz, precision=args.precision)
@@ -43,8 +43,8 @@ def main():
         torch.cuda.synchronize()
         ctx.lib.vqn_debug_tc_trace(None)
         raw = buf.cpu().numpy()
-        t = raw[:256].reshape(4, 16, 4)
-        pt = raw[256:].reshape(96, 8)
+        t = raw[:320].reshape(4, 20, 4)
+        pt = raw[320:].reshape(96, 8)
         print('==', which, args.precision)
         for tile in (1, 2):
             base = t[tile, 0, 0]

@@ -617,7 +617,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
             const int sc = first + c;                     // chunk index inside the source
             long long* ptr_ = nullptr;                    // diagnostic stamps of one producer thread (tile 1 of CTA 0)
             if (pg.trace && blockIdx.x == 0 && tid == 0 && tile == (long long)gridDim.x && ptrace_n < 96)
-              ptr_ = pg.trace + 256 + 8 * (ptrace_n++);
+              ptr_ = pg.trace + 4 * TC_MAX_LAYERS * 4 + 8 * (ptrace_n++);
             if (ptr_) { ptr_[0] = clock64(); ptr_[6] = l * 1000 + sg * 100 + c; }
 #ifdef TC_EXP_NO_PROD
             if (sc >= 0) {
@@ -1078,7 +1078,7 @@ static bool tc_append_net(TcBuilder& B, vqn_net* net, TcPack* tp, int first_src,
   return true;
 }
 
-// diagnostic knob (not part of include/vqnerf_b200.h): device buffer of >= 256 + 8 * 96 int64 that receives the
+// diagnostic knob (not part of include/vqnerf_b200.h): device buffer of >= 4 * TC_MAX_LAYERS * 4 + 8 * 96 int64 (= 1088) that receives the
 // MMA-thread time stamps of the next launches (NULL: off)
 static long long* g_tc_trace = nullptr;
 extern "C" void vqn_debug_tc_trace(long long* dev_buf) { g_tc_trace = dev_buf; }
