@@ -181,9 +181,10 @@ def cpu_baseline(probes, chunk=CPU_SAMPLE_POINTS, budget_s=CPU_BUDGET_S):
         if dt >= budget_s or done >= N_POINTS:
             break
     return {'value': done / dt, 'unit': 'points/s', 'cores': cores, 'kind': 'port',
-            'sample': '%d of %d points of the 800x800 view in chunks of %d, %d relight probes, fp32 torch-CPU '
-                      'restatement of vq_nfr.fast_render incl. [N,512,3] intermediates; %.1f s of CPU time'
-                      % (done, N_POINTS, chunk, probes, dt)}, dt, done
+            'sample': '%s in chunks of %d, %d relight probes, fp32 torch-CPU restatement of vq_nfr.fast_render incl. '
+                      '[N,512,3] intermediates; %.1f s of CPU time'
+                      % ('one whole 800x800 view (%d chunks = %d points)' % (done // chunk, done) if done >= N_POINTS
+                         else '%d of %d points of the 800x800 view' % (done, N_POINTS), chunk, probes, dt)}, dt, done
 
 
 def run_reference(args):
