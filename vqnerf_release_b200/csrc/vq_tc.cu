@@ -18,7 +18,7 @@
 //     rows whose two best distances are closer than 4e-5 relative are re-scored in fp64 (warp-cooperative), so the
 //     index is exact whenever the true top-2 gap exceeds the 1e-6 tolerance of BASELINE.json.
 //
-// K <= 128 (one codeword block, vq_tc_kernel<true>): the latent chunks come through the TMA engine -- a tensor map with the
+// K <= 128 (one codeword block, vq_tc_kernel): the latent chunks come through the TMA engine -- a tensor map with the
 // 128-byte swizzle, 4..7 [128 x 32] boxes in flight per SM -- and four dedicated drain warps (a thread owns a row) take the
 // arg-min off the producers.  K > 128: vq_tc_big_kernel (producers drain, four partial results per row merged in smem).
 // Measured (4 M latents): K = 64 1.36 ms (warp-level kernel: 2.13 ms, it pads K = 33..64 to 8 n-tiles), K = 128 1.64 ms
@@ -35,7 +35,7 @@
 #define VT_M 128
 #define VT_G 2                               // producer groups of 8 warps
 #define VT_THREADS_BIG (32 * (8 * VT_G + 3))  // K > 128 kernel: + MMA warp, codebook-stream warp, (idle) TMA warp
-#define VT_THREADS (32 * (8 * VT_G + 7))      // + MMA warp, codebook-stream warp, latent-TMA warp (SMALLK), 4 drain warps
+#define VT_THREADS (32 * (8 * VT_G + 7))      // + MMA warp, codebook-stream warp, latent-TMA warp, 4 drain warps
 #define VT_A_PLANE (VT_M * 128u)             // 16 KB
 #define VT_A_SLOT (2u * VT_A_PLANE)          // tf32 plane + bf16 correction plane
 #define VT_W_SLOT (256u * 128u * 2u)         // 64 KB
@@ -43,12 +43,12 @@
 #define VT_KCHUNKS (VQ_Z / 32)               // 8 K-chunks of 32 values
 #define VT_MAXK 1024
 #define VT_SMEM (VT_STAGES * VT_A_SLOT + VT_STAGES * VT_W_SLOT + 1024)
-// SMALLK (K <= 128, one codeword block): the codebook chunk is <= 32 KB, so half of the W ring holds a 4-stage staging
+// vq_tc_kernel (K <= 128, one codeword block): the codebook chunk is <= 32 KB, so half of the W ring holds a 4-stage staging
 // ring that the TMA engine fills with [128 rows x 128 B] boxes of the latents (tensor map, SWIZZLE_128B)
 #define VT_W_SLOT_SMALL (128u * 128u * 2u)   // 32 KB
 #define VT_XSTAGES 4
 #define VT_XSTAGES_MAX 7
-#define VT_WSTAGES_MAX 8                     // SMALLK: the 64 KB codebook ring holds 2 (K <= 128), 4 (K <= 64) or 8 (K <= 32) chunks
+#define VT_WSTAGES_MAX 8                     // barrier array size of the codebook ring (two slots are used)
 #define VT_X_STAGE (VT_M * 128u)             // 16 KB
 
 namespace {
@@ -148,10 +148,9 @@ __device__ __forceinline__ void vt_tma_load_2d(void* smem_dst, const CUtensorMap
                "r"(crd1) : "memory");
 }
 
-// SMALLK: K <= 128 (one codeword block).  There the kernel is bound by the latency of the latent loads, so they go
+// K <= 128 (one codeword block).  There the kernel is bound by the latency of the latent loads, so they go
 // through the TMA engine: one thread keeps VT_XSTAGES boxes of [128 latents x 32 values] in flight (tensor map with the
 // 128-byte swizzle = the layout the producers read conflict-free), the producer groups only split and store.
-template <bool SMALLK>
 __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_constant__ VtParams p,
                                                               const __grid_constant__ CUtensorMap xmap) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -164,15 +163,14 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_ring = smem;
   uint8_t* w_ring = smem + (size_t)VT_STAGES * VT_A_SLOT;
-  // codebook ring: two 64 KB slots; SMALLK: 64 KB in total, cut into as many chunk-sized slots as fit (the stream of a
-  // small codebook is latency-bound with two slots: every copy waits for the MMAs two chunks back)
+  // codebook ring: two chunk-sized slots (more were measured: no gain)
   const uint32_t npad0 = (uint32_t)((min(256, p.K) + 15) / 16 * 16);
-  const uint32_t W_SLOT = SMALLK ? npad0 * 256u : VT_W_SLOT;
+  const uint32_t W_SLOT = npad0 * 256u;
   const uint32_t NWS = (uint32_t)VT_STAGES;
-  // SMALLK: whatever the two codebook slots leave of the 128 KB goes to the TMA staging ring of the latents (4 boxes of
+  // whatever the two codebook slots leave of the 128 KB goes to the TMA staging ring of the latents (4 boxes of
   // 16 KB at K = 128, 6 at K <= 64, 7 at K <= 32): the depth of that ring is what bounds the small-K case
   uint8_t* x_ring = w_ring + (size_t)NWS * W_SLOT;
-  const uint32_t NXS = SMALLK ? min((uint32_t)VT_XSTAGES_MAX, (2u * VT_W_SLOT - NWS * W_SLOT) / VT_X_STAGE) : 1u;
+  const uint32_t NXS = min((uint32_t)VT_XSTAGES_MAX, (2u * VT_W_SLOT - NWS * W_SLOT) / VT_X_STAGE);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int MMA_WARP = 8 * VT_G, W_WARP = 8 * VT_G + 1, X_WARP = 8 * VT_G + 2, D_WARP0 = 8 * VT_G + 3;
 
@@ -194,7 +192,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
 
   if (warp < 8 * VT_G) {
     // ===================== producers: A chunks (split into the tf32 + bf16-correction planes), ||x||^2 =====================
-    const int grp = warp >> 3, half = (warp >> 2) & 1, tg = tid & 255;
+    const int grp = warp >> 3, half = (warp >> 2) & 1;
     const int r = 32 * (warp & 3) + lane;                          // latent row of the tile
     uint32_t ga = 0;                                               // global chunk counter
     uint32_t tile_i = 0;
@@ -206,43 +204,17 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
           const int slot = (int)(ga % VT_STAGES);
           uint8_t* dst = a_ring + (size_t)slot * VT_A_SLOT;
           float v[16];
-          if (SMALLK) {
-            // the chunk was put into staging buffer ga % VT_XSTAGES by the TMA engine (swizzled like the A planes)
-            const int xs_i = (int)(ga % NXS);
-            tc::mbar_wait(&x_full[xs_i], (ga / NXS) & 1u);
-            const uint8_t* stage = x_ring + (size_t)xs_i * VT_X_STAGE;
+          // the chunk was put into staging buffer ga % VT_XSTAGES by the TMA engine (swizzled like the A planes)
+          const int xs_i = (int)(ga % NXS);
+          tc::mbar_wait(&x_full[xs_i], (ga / NXS) & 1u);
+          const uint8_t* stage = x_ring + (size_t)xs_i * VT_X_STAGE;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 t = *reinterpret_cast<const float4*>(stage + r * 128 + (((4 * half + q) ^ (r & 7)) << 4));
-              v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-            }
-            tc::mbar_arrive(&x_empty[xs_i]);                      // the buffer may be refilled
-            tc::mbar_wait(&a_empty[slot], ((ga / VT_STAGES) & 1u) ^ 1u);
-          } else {
-            // coalesced load of the chunk (a warp reads 4 rows x 128 B per instruction), issued BEFORE the slot is claimed
-            float4 ldv[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int f = tg + 256 * i, rr = f >> 3, ch = f & 7;
-              const long long prow = tile * VT_M + rr;
-              ldv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (prow < p.n) ldv[i] = __ldg(reinterpret_cast<const float4*>(p.x + prow * VQ_Z + c * 32 + 4 * ch));
-            }
-            tc::mbar_wait(&a_empty[slot], ((ga / VT_STAGES) & 1u) ^ 1u);
-            uint8_t* stage = dst + VT_A_PLANE;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int f = tg + 256 * i, rr = f >> 3, ch = f & 7;
-              *reinterpret_cast<float4*>(stage + rr * 128 + ((ch ^ (rr & 7)) << 4)) = ldv[i];
-            }
-            vt_group_bar(grp);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 t = *reinterpret_cast<const float4*>(stage + r * 128 + (((4 * half + q) ^ (r & 7)) << 4));
-              v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-            }
-            vt_group_bar(grp);                                   // every row has been read before plane C is overwritten
+          for (int q = 0; q < 4; ++q) {
+            const float4 t = *reinterpret_cast<const float4*>(stage + r * 128 + (((4 * half + q) ^ (r & 7)) << 4));
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
           }
+          tc::mbar_arrive(&x_empty[xs_i]);                      // the buffer may be refilled
+          tc::mbar_wait(&a_empty[slot], ((ga / VT_STAGES) & 1u) ^ 1u);
           if (b == 0) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) xs = fmaf(v[j], v[j], xs);
@@ -372,7 +344,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
       }
     }
     __syncwarp();
-  } else if (SMALLK && warp == X_WARP) {
+  } else if (warp == X_WARP) {
     // =========================== latent chunks through the TMA engine (one thread) ===========================
     if (lane == 0) {
       uint32_t gx = 0;
@@ -693,8 +665,8 @@ int vq_tc_assign_launch(vqn_ctx* ctx, const VqParams& q, cudaStream_t s) {
                                box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { vqn_set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return VQN_ERR_CUDA; }
-    VQN_CUDA(cudaFuncSetAttribute(vq_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VT_SMEM));
-    vq_tc_kernel<true><<<blocks, VT_THREADS, VT_SMEM, s>>>(p, xmap);
+    VQN_CUDA(cudaFuncSetAttribute(vq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VT_SMEM));
+    vq_tc_kernel<<<blocks, VT_THREADS, VT_SMEM, s>>>(p, xmap);
   } else if (p.nb > 1) {
     VQN_CUDA(cudaFuncSetAttribute(vq_tc_big_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VT_SMEM));
     vq_tc_big_kernel<true><<<blocks, VT_THREADS_BIG, VT_SMEM, s>>>(p);
