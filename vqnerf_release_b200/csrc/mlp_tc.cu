@@ -397,7 +397,7 @@ __device__ __forceinline__ float act1_dyn(float t, int act) {
 
 // store 16 consecutive K values (columns j0 .. j0+15 of the chunk, j0 % 16 == 0) of row r into the chunk slot
 template <bool BF16>
-__device__ __forceinline__ void store_chunk32(uint8_t* slot, int r, int j0, const float (&v)[16]) {
+__device__ __forceinline__ void store_chunk32(uint32_t slot, int r, int j0, const float (&v)[16]) {
   if (BF16) {
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -408,11 +408,11 @@ __device__ __forceinline__ void store_chunk32(uint8_t* slot, int r, int j0, cons
       uint4 u;
       u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
       u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
-      *reinterpret_cast<uint4*>(slot + tc::sw128_off(r, j0 / 8 + q)) = u;
+      tc::sts128(slot + tc::sw128_off(r, j0 / 8 + q), u);
     }
   } else {
     // plane H (tf32 hi) at slot, plane C at slot + 16 KB: [bf16(a_lo) x 32 | bf16(a_hi) x 32] per row.
-    uint8_t* row = slot + r * 128;
+    const uint32_t row = slot + (uint32_t)r * 128u;
     const uint32_t rx = (uint32_t)(r & 7);
 #pragma unroll
     for (int qq = 0; qq < 2; ++qq) {            // 8 K values per step
@@ -420,8 +420,8 @@ __device__ __forceinline__ void store_chunk32(uint8_t* slot, int r, int j0, cons
 #pragma unroll
       for (int i = 0; i < 8; ++i) { h[i] = tc::tf32_rna(v[8 * qq + i]); l[i] = v[8 * qq + i] - h[i]; }
       const uint32_t c0 = (uint32_t)(j0 / 4 + 2 * qq);
-      *reinterpret_cast<float4*>(row + (((c0) ^ rx) << 4)) = make_float4(h[0], h[1], h[2], h[3]);
-      *reinterpret_cast<float4*>(row + (((c0 + 1) ^ rx) << 4)) = make_float4(h[4], h[5], h[6], h[7]);
+      tc::sts128(row + (((c0) ^ rx) << 4), make_float4(h[0], h[1], h[2], h[3]));
+      tc::sts128(row + (((c0 + 1) ^ rx) << 4), make_float4(h[4], h[5], h[6], h[7]));
       uint4 ul, uh;
       __nv_bfloat162 t0 = __floats2bfloat162_rn(l[0], l[1]), t1 = __floats2bfloat162_rn(l[2], l[3]);
       __nv_bfloat162 t2 = __floats2bfloat162_rn(l[4], l[5]), t3 = __floats2bfloat162_rn(l[6], l[7]);
@@ -432,24 +432,23 @@ __device__ __forceinline__ void store_chunk32(uint8_t* slot, int r, int j0, cons
       uh.x = *reinterpret_cast<uint32_t*>(&t0); uh.y = *reinterpret_cast<uint32_t*>(&t1);
       uh.z = *reinterpret_cast<uint32_t*>(&t2); uh.w = *reinterpret_cast<uint32_t*>(&t3);
       const uint32_t cc = (uint32_t)(j0 / 8 + qq);                 // bf16 16-byte chunk of the lo half
-      *reinterpret_cast<uint4*>(row + TC_M * 128 + ((cc ^ rx) << 4)) = ul;
-      *reinterpret_cast<uint4*>(row + TC_M * 128 + (((cc + 4) ^ rx) << 4)) = uh;
+      tc::sts128(row + TC_M * 128 + ((cc ^ rx) << 4), ul);
+      tc::sts128(row + TC_M * 128 + (((cc + 4) ^ rx) << 4), uh);
     }
   }
 }
 
 // one scalar K value (column `col` of the chunk) of row r
 template <bool BF16>
-__device__ __forceinline__ void store_chunk1(uint8_t* slot, int r, int col, float v) {
+__device__ __forceinline__ void store_chunk1(uint32_t slot, int r, int col, float v) {
   if (BF16) {
-    *reinterpret_cast<__nv_bfloat16*>(slot + tc::sw128_off(r, col / 8) + (col % 8) * 2) = __float2bfloat16_rn(v);
+    tc::sts16(slot + tc::sw128_off(r, col / 8) + (col % 8) * 2, __float2bfloat16_rn(v));
   } else {
-    const uint32_t off = tc::sw128_off(r, col / 4) + (col % 4) * 4;
     const float h = tc::tf32_rna(v);
-    *reinterpret_cast<float*>(slot + off) = h;
-    uint8_t* pc = slot + TC_M * 128;
-    *reinterpret_cast<__nv_bfloat16*>(pc + tc::sw128_off(r, col / 8) + (col % 8) * 2) = __float2bfloat16_rn(v - h);
-    *reinterpret_cast<__nv_bfloat16*>(pc + tc::sw128_off(r, 4 + col / 8) + (col % 8) * 2) = __float2bfloat16_rn(h);
+    tc::sts32(slot + tc::sw128_off(r, col / 4) + (col % 4) * 4, h);
+    const uint32_t pc = slot + TC_M * 128;
+    tc::sts16(pc + tc::sw128_off(r, col / 8) + (col % 8) * 2, __float2bfloat16_rn(v - h));
+    tc::sts16(pc + tc::sw128_off(r, 4 + col / 8) + (col % 8) * 2, __float2bfloat16_rn(h));
   }
 }
 
@@ -458,7 +457,7 @@ __device__ __forceinline__ void store_chunk1(uint8_t* slot, int r, int col, floa
 // jc = 0: the embedding itself; jc = 1..3 (tangent rows of a jet tile): its derivative with respect to x[jc-1], i.e.
 // [e_m, f cos(x_m f) e_m, -f sin(x_m f) e_m, ...] with m = jc - 1.
 template <bool BF16>
-__device__ __forceinline__ void embed_chunk(uint8_t* slot, int r, const float (&x)[3], int col0, int n_freqs, int jc) {
+__device__ __forceinline__ void embed_chunk(uint32_t slot, int r, const float (&x)[3], int col0, int n_freqs, int jc) {
   constexpr int E = BF16 ? 64 : 32;
   const int d = 3 + 6 * n_freqs;
   if (col0 == 0) {
@@ -516,6 +515,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_ring = smem;
   uint8_t* w_ring = smem + (size_t)C::SA * C::A_SLOT;
+  const uint32_t a_ring_s = tc::smem_u32(a_ring);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int MMA_WARP = 8 * C::G, W_WARP = 8 * C::G + 1;
 
@@ -613,7 +613,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
               acc_ready = true;
             }
             const int slot = ga % C::SA;
-            uint8_t* dst = a_ring + (size_t)slot * C::A_SLOT;
+            const uint32_t dst = a_ring_s + (uint32_t)slot * C::A_SLOT;          // shared-space address of the slot
             const int sc = first + c;                     // chunk index inside the source
             long long* ptr_ = nullptr;                    // diagnostic stamps of one producer thread (tile 1 of CTA 0)
             if (pg.trace && blockIdx.x == 0 && tid == 0 && tile == (long long)gridDim.x && ptrace_n < 96)
@@ -648,17 +648,17 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
               if (ptr_) ptr_[1] = clock64();
               tc::mbar_wait(&a_empty[slot], ((ga / C::SA) & 1) ^ 1);
               if (ptr_) ptr_[2] = clock64();
-              uint8_t* stage = dst + C::A_PLANE;
+              const uint32_t stage = dst + C::A_PLANE;
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int f = tg + 256 * i, rr = f >> 3, ch = f & 7;
-                *reinterpret_cast<float4*>(stage + rr * 128 + ((ch ^ (rr & 7)) << 4)) = ldv[i];
+                tc::sts128(stage + rr * 128 + ((ch ^ (rr & 7)) << 4), ldv[i]);
               }
               group_bar(grp);
               float v[16];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const float4 t = *reinterpret_cast<const float4*>(stage + r * 128 + (((4 * half + q) ^ (r & 7)) << 4));
+                const float4 t = tc::lds128(stage + r * 128 + (((4 * half + q) ^ (r & 7)) << 4));
                 v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
               }
               group_bar(grp);                    // every row has been read before plane C is overwritten
@@ -879,11 +879,11 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
               if (wide) {
                 // stage the 32-column block in the group's own (free) A slot, swizzled, then store it coalesced:
                 // a warp writes 4 rows x 128 B per instruction instead of 16 B into each of 32 rows
-                uint8_t* stage = a_ring + (size_t)grp * C::A_SLOT;
+                const uint32_t stage = a_ring_s + (uint32_t)grp * C::A_SLOT;
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
-                  *reinterpret_cast<float4*>(stage + r * 128 + (((4 * half + q) ^ (r & 7)) << 4)) =
-                      make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                  tc::sts128(stage + r * 128 + (((4 * half + q) ^ (r & 7)) << 4),
+                             make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
               } else if (valid_out) {
                 if (c16 + 16 <= ly.N && (gs & 3) == 0) {
                   float4* o = reinterpret_cast<float4*>(go + pi * gs + c16);
@@ -897,14 +897,14 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
               }
             }
             if (wide) {
-              const uint8_t* stage = a_ring + (size_t)grp * C::A_SLOT;
+              const uint32_t stage = a_ring_s + (uint32_t)grp * C::A_SLOT;
               group_bar(grp);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int f = tg + 256 * i, rr = f >> 3, ch = f & 7;
                 const long long prow = tile * tile_pts + (jet ? (rr >> 2) : rr);
                 if (prow < n && (!jet || (rr & 3) == 0)) {
-                  const float4 val = *reinterpret_cast<const float4*>(stage + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                  const float4 val = tc::lds128(stage + rr * 128 + ((ch ^ (rr & 7)) << 4));
                   if (local) {
                     *reinterpret_cast<float4*>(go + ((size_t)blockIdx.x * TC_M + rr) * gs + cb * 32 + 4 * ch) = val;
                     if (pg.out_dup) *reinterpret_cast<float4*>(pg.out_dup + (size_t)prow * gs + cb * 32 + 4 * ch) = val;

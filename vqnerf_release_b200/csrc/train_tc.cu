@@ -46,8 +46,8 @@ struct DtParams {
 // 16 consecutive K values of row r -> tf32 hi plane + bf16 correction plane (layout of mlp_tc.cu).  The correction MMA
 // evaluates a_lo.b_hi + a_hi.b_lo in ONE product of K = 64, so the A operand stores [bf16(lo) x 32 | bf16(hi) x 32] and
 // the B operand the opposite order [bf16(hi) x 32 | bf16(lo) x 32].
-__device__ __forceinline__ void dt_store16(uint8_t* op, int r, int j0, const float* v, bool b_operand) {
-  uint8_t* row = op + r * 128;
+__device__ __forceinline__ void dt_store16(uint32_t op, int r, int j0, const float* v, bool b_operand) {
+  const uint32_t row = op + (uint32_t)r * 128u;             // shared-space address: STS, not generic stores
   const uint32_t rx = (uint32_t)(r & 7);
 #pragma unroll
   for (int qq = 0; qq < 2; ++qq) {
@@ -55,8 +55,8 @@ __device__ __forceinline__ void dt_store16(uint8_t* op, int r, int j0, const flo
 #pragma unroll
     for (int i = 0; i < 8; ++i) { h[i] = tc::tf32_rna(v[8 * qq + i]); l[i] = v[8 * qq + i] - h[i]; }
     const uint32_t c0 = (uint32_t)(j0 / 4 + 2 * qq);
-    *reinterpret_cast<float4*>(row + (((c0) ^ rx) << 4)) = make_float4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<float4*>(row + (((c0 + 1) ^ rx) << 4)) = make_float4(h[4], h[5], h[6], h[7]);
+    tc::sts128(row + (((c0) ^ rx) << 4), make_float4(h[0], h[1], h[2], h[3]));
+    tc::sts128(row + (((c0 + 1) ^ rx) << 4), make_float4(h[4], h[5], h[6], h[7]));
     uint4 ul, uh;
     __nv_bfloat162 t0 = __floats2bfloat162_rn(l[0], l[1]), t1 = __floats2bfloat162_rn(l[2], l[3]);
     __nv_bfloat162 t2 = __floats2bfloat162_rn(l[4], l[5]), t3 = __floats2bfloat162_rn(l[6], l[7]);
@@ -67,8 +67,8 @@ __device__ __forceinline__ void dt_store16(uint8_t* op, int r, int j0, const flo
     uh.x = *reinterpret_cast<uint32_t*>(&t0); uh.y = *reinterpret_cast<uint32_t*>(&t1);
     uh.z = *reinterpret_cast<uint32_t*>(&t2); uh.w = *reinterpret_cast<uint32_t*>(&t3);
     const uint32_t cc = (uint32_t)(j0 / 8 + qq);
-    *reinterpret_cast<uint4*>(row + DT_PLANE + ((cc ^ rx) << 4)) = b_operand ? uh : ul;
-    *reinterpret_cast<uint4*>(row + DT_PLANE + (((cc + 4) ^ rx) << 4)) = b_operand ? ul : uh;
+    tc::sts128(row + DT_PLANE + ((cc ^ rx) << 4), b_operand ? uh : ul);
+    tc::sts128(row + DT_PLANE + (((cc + 4) ^ rx) << 4), b_operand ? ul : uh);
   }
 }
 
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(const __grid_co
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
       tc::mbar_wait(&empty[slot], (((uint32_t)c / DT_STAGES) & 1u) ^ 1u);
-      uint8_t* op = smem + (size_t)slot * DT_SLOT + (a_role ? 0 : DT_OPERAND);
+      const uint32_t op = tc::smem_u32(smem) + (uint32_t)slot * DT_SLOT + (a_role ? 0u : DT_OPERAND);
       dt_store16(op, r, 0, v, !a_role);
       dt_store16(op, r, 16, v + 16, !a_role);
       tc::fence_proxy_async();

@@ -113,8 +113,8 @@ __global__ void vt_pack_kernel(const float* __restrict__ cb, int K, int nb, uint
 }
 
 // 16 consecutive K values of row r into the A slot (tf32 hi plane + [bf16(lo) | bf16(hi)] plane), as mlp_tc.cu
-__device__ __forceinline__ void vt_store16(uint8_t* slot, int r, int j0, const float (&v)[16]) {
-  uint8_t* row = slot + r * 128;
+__device__ __forceinline__ void vt_store16(uint32_t slot, int r, int j0, const float (&v)[16]) {
+  const uint32_t row = slot + (uint32_t)r * 128u;           // shared-space address: STS, not generic stores
   const uint32_t rx = (uint32_t)(r & 7);
 #pragma unroll
   for (int qq = 0; qq < 2; ++qq) {
@@ -122,8 +122,8 @@ __device__ __forceinline__ void vt_store16(uint8_t* slot, int r, int j0, const f
 #pragma unroll
     for (int i = 0; i < 8; ++i) { h[i] = tc::tf32_rna(v[8 * qq + i]); l[i] = v[8 * qq + i] - h[i]; }
     const uint32_t c0 = (uint32_t)(j0 / 4 + 2 * qq);
-    *reinterpret_cast<float4*>(row + (((c0) ^ rx) << 4)) = make_float4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<float4*>(row + (((c0 + 1) ^ rx) << 4)) = make_float4(h[4], h[5], h[6], h[7]);
+    tc::sts128(row + (((c0) ^ rx) << 4), make_float4(h[0], h[1], h[2], h[3]));
+    tc::sts128(row + (((c0 + 1) ^ rx) << 4), make_float4(h[4], h[5], h[6], h[7]));
     uint4 ul, uh;
     __nv_bfloat162 t0 = __floats2bfloat162_rn(l[0], l[1]), t1 = __floats2bfloat162_rn(l[2], l[3]);
     __nv_bfloat162 t2 = __floats2bfloat162_rn(l[4], l[5]), t3 = __floats2bfloat162_rn(l[6], l[7]);
@@ -134,8 +134,8 @@ __device__ __forceinline__ void vt_store16(uint8_t* slot, int r, int j0, const f
     uh.x = *reinterpret_cast<uint32_t*>(&t0); uh.y = *reinterpret_cast<uint32_t*>(&t1);
     uh.z = *reinterpret_cast<uint32_t*>(&t2); uh.w = *reinterpret_cast<uint32_t*>(&t3);
     const uint32_t cc = (uint32_t)(j0 / 8 + qq);
-    *reinterpret_cast<uint4*>(row + VT_A_PLANE + ((cc ^ rx) << 4)) = ul;
-    *reinterpret_cast<uint4*>(row + VT_A_PLANE + (((cc + 4) ^ rx) << 4)) = uh;
+    tc::sts128(row + VT_A_PLANE + ((cc ^ rx) << 4), ul);
+    tc::sts128(row + VT_A_PLANE + (((cc + 4) ^ rx) << 4), uh);
   }
 }
 
@@ -202,15 +202,15 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
         for (int c = 0; c < VT_KCHUNKS; ++c, ++ga) {
           if ((int)(ga % VT_G) != grp) continue;
           const int slot = (int)(ga % VT_STAGES);
-          uint8_t* dst = a_ring + (size_t)slot * VT_A_SLOT;
+          const uint32_t dst = tc::smem_u32(a_ring) + (uint32_t)slot * VT_A_SLOT;
           float v[16];
           // the chunk was put into staging buffer ga % VT_XSTAGES by the TMA engine (swizzled like the A planes)
           const int xs_i = (int)(ga % NXS);
           tc::mbar_wait(&x_full[xs_i], (ga / NXS) & 1u);
-          const uint8_t* stage = x_ring + (size_t)xs_i * VT_X_STAGE;
+          const uint32_t stage = tc::smem_u32(x_ring) + (uint32_t)xs_i * VT_X_STAGE;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float4 t = *reinterpret_cast<const float4*>(stage + r * 128 + (((4 * half + q) ^ (r & 7)) << 4));
+            const float4 t = tc::lds128(stage + r * 128 + (((4 * half + q) ^ (r & 7)) << 4));
             v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
           }
           tc::mbar_arrive(&x_empty[xs_i]);                      // the buffer may be refilled
@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(VT_THREADS_BIG, 1) vq_tc_big_kernel(const __gr
         for (int c = 0; c < VT_KCHUNKS; ++c, ++ga) {
           if ((int)(ga % VT_G) != grp) continue;
           const int slot = (int)(ga % VT_STAGES);
-          uint8_t* dst = a_ring + (size_t)slot * VT_A_SLOT;
+          const uint32_t dst = tc::smem_u32(a_ring) + (uint32_t)slot * VT_A_SLOT;
           // coalesced load of the chunk (a warp reads 4 rows x 128 B per instruction), issued BEFORE the slot is claimed.
           // (Keeping the group's next chunk in registers across the drain was measured slower: 9.6 -> 11.4 ms at
           // K = 1024, the extra live registers spill inside the arg-min loop.)
@@ -504,17 +504,17 @@ __global__ void __launch_bounds__(VT_THREADS_BIG, 1) vq_tc_big_kernel(const __gr
             if (prow < p.n) ldv[i] = __ldg(reinterpret_cast<const float4*>(p.x + prow * VQ_Z + c * 32 + 4 * ch));
           }
           tc::mbar_wait(&a_empty[slot], ((ga / VT_STAGES) & 1u) ^ 1u);
-          uint8_t* stage = dst + VT_A_PLANE;
+          const uint32_t stage = dst + VT_A_PLANE;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int f = tg + 256 * i, rr = f >> 3, ch = f & 7;
-            *reinterpret_cast<float4*>(stage + rr * 128 + ((ch ^ (rr & 7)) << 4)) = ldv[i];
+            tc::sts128(stage + rr * 128 + ((ch ^ (rr & 7)) << 4), ldv[i]);
           }
           vt_group_bar(grp);
           float v[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float4 t = *reinterpret_cast<const float4*>(stage + r * 128 + (((4 * half + q) ^ (r & 7)) << 4));
+            const float4 t = tc::lds128(stage + r * 128 + (((4 * half + q) ^ (r & 7)) << 4));
             v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
           }
           vt_group_bar(grp);                                     // every row has been read before plane C is overwritten
