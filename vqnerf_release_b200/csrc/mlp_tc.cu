@@ -781,8 +781,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
             }
           }
           // the four partial sums of a row (2 groups x 2 column halves) meet in the (free) first A slot
-          float4* part = reinterpret_cast<float4*>(a_ring);
-          part[r * 4 + grp * 2 + half] = make_float4(p0, p1, p2, p3);
+          tc::sts128(a_ring_s + (uint32_t)(r * 4 + grp * 2 + half) * 16u, make_float4(p0, p1, p2, p3));
           tc::fence_before_sync();
           if (rev) __threadfence_block();      // the stash written above (and by the forward drains) is read by other threads
           asm volatile("bar.sync 3, %0;" ::"r"(256 * C::G) : "memory");
@@ -790,7 +789,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
             float o[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int q = 0; q < 2 * C::G; ++q) {
-              const float4 t4 = part[r * 4 + q];
+              const float4 t4 = tc::lds128(a_ring_s + (uint32_t)(r * 4 + q) * 16u);
               o[0] += t4.x; o[1] += t4.y; o[2] += t4.z; o[3] += t4.w;
             }
             float* go = pg.outs[ly.tail_out_slot];
@@ -829,15 +828,14 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
             tc::tmem_ld16(lane_addr + (uint32_t)(ly.tmem_col + c16), v);
             embed_jac_contract(v, c16 - ly.egrad_col0, pg.n_freqs, x, sp0, sp1, sp2);
           }
-          float4* part = reinterpret_cast<float4*>(a_ring);
-          part[r * 4 + t4] = make_float4(sp0, sp1, sp2, 0.f);
+          tc::sts128(a_ring_s + (uint32_t)(r * 4 + t4) * 16u, make_float4(sp0, sp1, sp2, 0.f));
           sp0 = sp1 = sp2 = 0.f;
           tc::fence_before_sync();
           asm volatile("bar.sync 3, %0;" ::"r"(256 * C::G) : "memory");
           if (t4 == 0) {
             float g0 = 0.f, g1 = 0.f, g2 = 0.f;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { const float4 t = part[r * 4 + q]; g0 += t.x; g1 += t.y; g2 += t.z; }
+            for (int q = 0; q < 4; ++q) { const float4 t = tc::lds128(a_ring_s + (uint32_t)(r * 4 + q) * 16u); g0 += t.x; g1 += t.y; g2 += t.z; }
             if (valid) {
               if (!isfinite(g0) || !isfinite(g1) || !isfinite(g2)) atomicOr(pg.nonfinite, 1);
               pg.jet_grad[pi * 3] = g0; pg.jet_grad[pi * 3 + 1] = g1; pg.jet_grad[pi * 3 + 2] = g2;
