@@ -1,5 +1,6 @@
 """Per-layer time stamps of the tcgen05 MLP kernel's MMA thread (CTA 0, first 4 tiles) -- diagnostic.
 
+    VQN_EXTRA_NVCC_FLAGS=-DVQN_TC_TRACE python -m vqnerf_release_b200.build --force    # the stamps are compiled out by default
     python benchmarks/tc_trace.py [--precision tf32x3]
 Prints, per layer: wait for the previous drain, wait for the first A/W chunk, time to issue all chunks (which
 includes waiting for A slots to be refilled), in SM clock cycles."""

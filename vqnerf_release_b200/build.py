@@ -21,7 +21,7 @@ LIB = os.path.join(HERE, 'libvqnerf_b200.so')
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
     '-Xcompiler', '-fPIC', '-Xptxas', '-v', '--expt-relaxed-constexpr',
-]
+] + os.environ.get('VQN_EXTRA_NVCC_FLAGS', '').split()      # e.g. -DVQN_TC_TRACE for benchmarks/tc_trace.py
 
 
 def _nvcc() -> str:

@@ -30,6 +30,13 @@
 #include "tc_common.cuh"
 
 #define TC_M 128               // points per tile (= TMEM lanes)
+// clock64 stamps for benchmarks/tc_trace.py: compiled in only with -DVQN_TC_TRACE (VQN_EXTRA_NVCC_FLAGS=-DVQN_TC_TRACE
+// python -m vqnerf_release_b200.build --force); in the product build the hot loops carry no predicated CS2R / stores
+#ifdef VQN_TC_TRACE
+#define TC_STAMP(p, i) do { if (p) (p)[i] = clock64(); } while (0)
+#else
+#define TC_STAMP(p, i) do { } while (0)
+#endif
 #define TC_MAX_LAYERS 20
 #define TC_NPAD_MAX 256
 
@@ -569,7 +576,9 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
     uint32_t ga = 0;                                     // global A-chunk counter
     uint32_t gl = 0;                                     // global layer counter (acc_full phase)
+#ifdef VQN_TC_TRACE
     int ptrace_n = 0;
+#endif
     float sp0 = 0.f, sp1 = 0.f, sp2 = 0.f, sp3 = 0.f;   // folded-skip partial sums of this thread (see TcLayer::skip_w)
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long pi = tile * tile_pts + (jet ? (r >> 2) : r);   // compact point index
@@ -615,10 +624,12 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
             const int slot = ga % C::SA;
             const uint32_t dst = a_ring_s + (uint32_t)slot * C::A_SLOT;          // shared-space address of the slot
             const int sc = first + c;                     // chunk index inside the source
+#ifdef VQN_TC_TRACE
             long long* ptr_ = nullptr;                    // diagnostic stamps of one producer thread (tile 1 of CTA 0)
             if (pg.trace && blockIdx.x == 0 && tid == 0 && tile == (long long)gridDim.x && ptrace_n < 96)
               ptr_ = pg.trace + 4 * TC_MAX_LAYERS * 4 + 8 * (ptrace_n++);
             if (ptr_) { ptr_[0] = clock64(); ptr_[6] = l * 1000 + sg * 100 + c; }
+#endif
 #ifdef TC_EXP_NO_PROD
             if (sc >= 0) {
               tc::mbar_wait(&a_empty[slot], ((ga / C::SA) & 1) ^ 1);
@@ -645,9 +656,9 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                   else ldv[i] = __ldg(reinterpret_cast<const float4*>(pg.gsrc + prow * pg.g_dim + col_base + 4 * ch));
                 }
               }
-              if (ptr_) ptr_[1] = clock64();
+              TC_STAMP(ptr_, 1);
               tc::mbar_wait(&a_empty[slot], ((ga / C::SA) & 1) ^ 1);
-              if (ptr_) ptr_[2] = clock64();
+              TC_STAMP(ptr_, 2);
               const uint32_t stage = dst + C::A_PLANE;
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -733,18 +744,18 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                 }
                 // the values are ready in registers BEFORE the slot is claimed: the TMEM / global load latency
                 // and the activation math overlap the MMAs that are still reading the slot's previous chunk
-                if (ptr_ && h == 0) ptr_[1] = clock64();
+                if (h == 0) TC_STAMP(ptr_, 1);
                 if (h == 0) tc::mbar_wait(&a_empty[slot], ((ga / C::SA) & 1) ^ 1);
-                if (ptr_ && h == 0) ptr_[2] = clock64();
+                if (h == 0) TC_STAMP(ptr_, 2);
                 store_chunk32<BF16>(dst, r, 32 * h + 16 * half, v);
               }
             }
-            if (ptr_) ptr_[3] = clock64();
+            TC_STAMP(ptr_, 3);
             tc::fence_proxy_async();       // generic-proxy stores -> visible to the UMMA (async proxy)
             tc::fence_before_sync();       // order the tcgen05.ld's above before the hand-off
-            if (ptr_) ptr_[4] = clock64();
+            TC_STAMP(ptr_, 4);
             tc::mbar_arrive(&a_full[slot]);
-            if (ptr_) ptr_[5] = clock64();
+            TC_STAMP(ptr_, 5);
           }
         }
         ++gl;                               // layer l's chunks are all queued
@@ -938,9 +949,11 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
           const uint32_t d_tmem = tmem_base + (uint32_t)ly.tmem_col;
           const int nch = ly.seg_chunks[0] + (ly.nseg > 1 ? ly.seg_chunks[1] : 0);
           const uint32_t w_plane = (uint32_t)ly.Npad * 128;
+#ifdef VQN_TC_TRACE
           long long* tr = (pg.trace && blockIdx.x == 0 && tile < 4 * (long long)gridDim.x)
                               ? pg.trace + ((tile / gridDim.x) * TC_MAX_LAYERS + l) * 4 : nullptr;
-          if (tr) tr[0] = clock64();
+#endif
+          TC_STAMP(tr, 0);
           if (pending_drain) {
             // a final layer is being drained to global: wait before overwriting ITS columns (other columns may go on)
             const bool hit = (ly.tmem_col < pend_hi && ly.tmem_col + ly.Npad > pend_lo) || ly.out_slot >= 0;
@@ -953,11 +966,11 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
           uint32_t acc = 0;
           for (int c = 0; c < nch; ++c, ++ga, ++gw) {
             const int sa = ga % C::SA, sw = gw % C::SW;
-            if (tr && c == 0) tr[1] = clock64();
+            if (c == 0) TC_STAMP(tr, 1);
             tc::mbar_wait(&a_full[sa], (ga / C::SA) & 1);
             tc::mbar_wait(&w_full[sw], (gw / C::SW) & 1);
             tc::fence_after_sync();
-            if (tr && c == 0) tr[2] = clock64();
+            if (c == 0) TC_STAMP(tr, 2);
             const uint32_t a_addr = tc::smem_u32(a_ring + (size_t)sa * C::A_SLOT);
             const uint32_t w_addr = tc::smem_u32(w_ring + (size_t)sw * C::W_SLOT);
 #ifdef TC_EXP_NO_MMA
@@ -980,7 +993,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
             tc::mma_commit(&w_empty[sw]);
           }
           tc::mma_commit(&acc_full);            // layer complete -> epilogue warps may drain it
-          if (tr) tr[3] = clock64();
+          TC_STAMP(tr, 3);
           if (ly.out_slot >= 0) { pending_drain = true; pend_lo = ly.tmem_col; pend_hi = ly.tmem_col + ly.Npad; }
         }
       }
