@@ -388,9 +388,13 @@ def _t(a, dt):
 
 def fast_render(scene: Scene, batch: Dict[str, np.ndarray], dtype=torch.float64,
                 relight_probes: bool = False, opt_scale=None, gen_embed: bool = False,
-                return_brdf: bool = False) -> Dict[str, torch.Tensor]:
+                return_brdf: bool = False, dst_env: Optional[int] = None, edit_mask=None,
+                edit_material=None) -> Dict[str, torch.Tensor]:
     """models/vq_nfr.py:262-398.  Returns the `pred` dict entries (full length, zeros at
-    background rows) plus the compacted intermediates under '_'-prefixed keys."""
+    background rows) plus the compacted intermediates under '_'-prefixed keys.
+    `dst_env` = index into scene.probes of the light the main render uses (`self.novel_probes[dst_env]`, :699-700;
+    None = the learned `_light`); `edit_mask [N,>=1]` / `edit_material {'diff','spec','rough'}` = the material edit
+    of :293-295, 324-330 (`_update_material`: src * (1 - mask) + mask * update, skipped when update[0] < 0)."""
     dt = dtype
     alpha = _t(batch['alpha'], dt)
     mask = alpha[:, 0] > 0
@@ -413,6 +417,15 @@ def fast_render(scene: Scene, batch: Dict[str, np.ndarray], dtype=torch.float64,
     ks = pred_head(scene.nets, 'spec_main', z_enc)
     spec = ks * basecolor
     albedo = (1 - ks) * basecolor
+    if edit_mask is not None:
+        em = (_t(edit_mask, dt)[mask][..., 0:1] > 0).to(dt)                          # :293-295
+        upd = lambda src, u: src * (1.0 - em) + em * _t(np.asarray([u], np.float32), dt)   # :258-260
+        if not edit_material['diff'][0] < 0:
+            albedo = upd(albedo, edit_material['diff'])
+        if not edit_material['spec'][0] < 0:
+            spec = upd(spec, edit_material['spec'])
+        if not edit_material['rough'][0] < 0:
+            rough = upd(rough, edit_material['rough'])
     if opt_scale is not None:
         s = _t(opt_scale, dt)
         s_albedo, s_spec = albedo * s, spec * s
@@ -420,6 +433,8 @@ def fast_render(scene: Scene, batch: Dict[str, np.ndarray], dtype=torch.float64,
         s_albedo, s_spec = albedo, spec
     brdf, _, _ = get_brdf(surf2l, surf2c, normal_pred, s_albedo, rough, s_spec)
     light = torch.clamp(_t(scene.light, dt), min=0.0)
+    if dst_env is not None:
+        light = _t(scene.probes[dst_env], dt)                                        # :699-700 (not clipped)
     probes = _t(scene.probes, dt) if (relight_probes and scene.probes is not None) else None
     gamma = None if scene.data_type == 'nerf' else scene.gamma
     rgb_pred, rgb_probes = render(brdf, surf2l, normal_pred, lareas, light, lvis, probes, gamma)

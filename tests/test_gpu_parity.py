@@ -153,6 +153,69 @@ def test_vq_large_codebook_tensor_core_path(cuda_dev, n, k):
     assert out['indices'].dtype == torch.int64
 
 
+def _fp64_argmin_gpu(xt, ct, chunk=262144):
+    """The reference's distances (vq_layers.py:279-282) in float64 on the device, first arg-min + relative top-2 gap."""
+    c64 = ct.double()
+    c2 = (c64 * c64).sum(0, keepdim=True)
+    idx, gap = [], []
+    for i in range(0, xt.shape[0], chunk):
+        x = xt[i:i + chunk].double()
+        d = (x * x).sum(1, keepdim=True) - 2 * x @ c64 + c2
+        t = torch.topk(d, min(2, d.shape[1]), dim=1, largest=False)
+        # torch.topk does not promise first-index ties: take the first arg-min explicitly
+        idx.append(torch.argmax((d == t.values[:, :1]).to(torch.int8), dim=1))
+        gap.append((t.values[:, -1] - t.values[:, 0]) / t.values[:, 0].abs().clamp_min(1e-30))
+    return torch.cat(idx), torch.cat(gap)
+
+
+@pytest.mark.parametrize('k', [33, 64, 100, 128, 256, 1024])
+def test_vq_tensor_core_path_many_tiles_per_cta_deterministic(cuda_dev, k):
+    """Indices-only tcgen05 path with >= 8 tiles per CTA (the TMEM ping-pong, the TMA staging ring wrap, drain_done and the
+    xs_s parity reuse only exist across tiles) on ill-separated data (normalised U(0,1) latents AND codewords: every
+    distance within a few percent of every other), EVERY row against the float64 arg-min, three runs bit-identical.
+    Round 1 shipped a kernel whose staging-buffer release overtook its own shared-memory loads: ~1e-3 of the rows wrong,
+    differently on every run -- invisible at one tile per CTA."""
+    from vqnerf_release_b200 import abi
+    n = 148 * 128 * 8 + 77
+    g = torch.Generator(device=cuda_dev).manual_seed(1000 + k)
+    xt = abi.l2_normalize_rows(torch.rand((n, 256), generator=g, device=cuda_dev))
+    ct = abi.get_codebook(torch.rand((256, k), generator=g, device=cuda_dev))
+    ref, gap = _fp64_argmin_gpu(xt, ct)
+    outs = [abi.vq_assign(xt, ct, want_quantize=False)['indices'].clone() for _ in range(3)]
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0]), 'K=%d: the kernel is not deterministic' % k
+    mism = outs[0] != ref
+    bad = int((mism & (gap >= 1e-6)).sum())
+    assert bad == 0, 'K=%d: %d of %d rows outside the 1e-6 tie tolerance' % (k, bad, n)
+    # and the warp-level kernel (other outputs requested) agrees wherever the gap is meaningful
+    other = abi.vq_assign(xt[:300000], ct, want_quantize=True)['indices']
+    assert int(((other != ref[:300000]) & (gap[:300000] >= 1e-6)).sum()) == 0
+
+
+@pytest.mark.parametrize('k', [15, 40, 128, 300])
+def test_vq_three_way_near_ties_resolved_exactly(cuda_dev, k):
+    """Three (or more) codewords within ~1e-6 of each other: the tensor-core distances cannot even name the two
+    candidates, so a top-2 re-score is not enough (1 row in 4 M went wrong at K = 128 in the round-2 sweep).  Rows whose
+    third-best distance is within tolerance are re-scored in float64 against every codeword: the result must equal the
+    float64 arg-min wherever the float64 gap is not itself rounding noise."""
+    from vqnerf_release_b200 import abi
+    n = 40000
+    rng = np.random.RandomState(k)
+    x, cb = _latents(n, k, 500 + k)
+    base = cb[:, 2].copy()
+    for j, col in enumerate((2, k // 2, k - 1, 5)):                 # four clones of one codeword, ~3e-7 apart
+        cb[:, col] = base + (rng.standard_normal(256) * 2e-8 * j).astype(np.float32)
+    xt, ct = torch.as_tensor(x).to(cuda_dev), torch.as_tensor(cb).to(cuda_dev)
+    ref, gap = _fp64_argmin_gpu(xt, ct)
+    hit = torch.isin(ref, torch.tensor([2, k // 2, k - 1, 5], device=cuda_dev))
+    assert int(hit.sum()) > 20                                      # the clones do win rows
+    for kw in (dict(want_quantize=False), dict(want_quantize=True)):   # tcgen05 (K > 32) and warp-level kernels
+        idx = abi.vq_assign(xt, ct, **kw)['indices']
+        bad = (idx != ref) & (gap >= 1e-12)
+        assert int(bad.sum()) == 0, 'K=%d %s: %d rows wrong (of them among the clones: %d)' % (
+            k, kw, int(bad.sum()), int((bad & hit).sum()))
+
+
 def test_vq_duplicate_codewords_pick_first(cuda_dev):
     from vqnerf_release_b200 import abi
     x, cb = _latents(512, 15, 3)

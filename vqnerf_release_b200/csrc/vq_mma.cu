@@ -66,22 +66,40 @@ __device__ __forceinline__ float4 ldg_f4(const float* p) {
 }
 
 struct Top2 {
-  float b, s;
+  float b, s, t;       // best, runner-up, THIRD-best value (a three-way near-tie sends the row to the full fp64 re-score)
   int bi, si;
 };
 __device__ __forceinline__ void top2_push(Top2& t, float d, int k) {   // k arrives in increasing order
-  if (d < t.b) { t.s = t.b; t.si = t.bi; t.b = d; t.bi = k; }
-  else if (d < t.s) { t.s = d; t.si = k; }
+  if (d < t.b) { t.t = t.s; t.s = t.b; t.si = t.bi; t.b = d; t.bi = k; }
+  else if (d < t.s) { t.t = t.s; t.s = d; t.si = k; }
+  else if (d < t.t) t.t = d;
 }
-// merge with another (best, runner-up) pair; equal distances -> lower index first
-__device__ __forceinline__ void top2_merge(Top2& t, float ob, int obi, float os, int osi) {
+// merge with another (best, runner-up, third) triple; equal distances -> lower index first
+__device__ __forceinline__ void top2_merge(Top2& t, float ob, int obi, float os, int osi, float ot) {
+  // third smallest of the union = min(third of each side, third smallest of the four indexed values)
+  const float t3 = fminf(fminf(t.t, ot), fmaxf(fminf(t.s, os), fmaxf(t.b, ob)));
   const bool ow = (ob < t.b) || (ob == t.b && obi < t.bi);
   const float lose = ow ? t.b : ob;  const int losei = ow ? t.bi : obi;
   const float w2 = ow ? os : t.s;    const int w2i = ow ? osi : t.si;
   if (ow) { t.b = ob; t.bi = obi; }
   const bool l = (lose < w2) || (lose == w2 && losei < w2i);
   t.s = l ? lose : w2;  t.si = l ? losei : w2i;
+  t.t = t3;
 }
+
+// Hot-loop form of the same triple: PACKED keys, the distance with its low 6 mantissa bits replaced by the chunk-local
+// codeword index (< 64): five FMNMX per value, three shuffles per merge step, no index bookkeeping.  The truncation
+// (2^-17 relative) is covered by the fp64 re-score thresholds below.
+struct Top3 { float b, s, t; };
+__device__ __forceinline__ void top3_push(Top3& m, float dp) {
+  m.t = fminf(m.t, fmaxf(dp, m.s));
+  m.s = fminf(m.s, fmaxf(dp, m.b));
+  m.b = fminf(m.b, dp);
+}
+#define VQM_KMASK 0xffffffc0u
+__device__ __forceinline__ float vqm_pack(float d, int kk) { return __uint_as_float((__float_as_uint(d) & VQM_KMASK) + (unsigned)kk); }
+__device__ __forceinline__ float vqm_val(float p) { return __uint_as_float(__float_as_uint(p) & VQM_KMASK); }
+__device__ __forceinline__ int vqm_idx(float p) { return (int)(__float_as_uint(p) & ~VQM_KMASK); }
 
 // one pipeline phase: 4 column groups c0..c0+3 of rows g (vg) and g+8 (vh) = 8 k-steps
 template <int NT>
@@ -136,10 +154,11 @@ __global__ void __launch_bounds__(VqmCfg<NT>::WARPS * 32, VqmCfg<NT>::BLOCKS) vq
   // smem: B fragments [32 k-steps][NT][32 lanes] float4 | cnorm[KCH] | top-2 state (chunked) | stats
   float4* bsm = reinterpret_cast<float4*>(smem_raw);
   float* cnorm = reinterpret_cast<float*>(bsm + 32 * NT * 32);
-  float* st_b = cnorm + KCH;                     // chunked: [8 warps * TPW * 16 rows] x {b, s, bi, si}
+  float* st_b = cnorm + KCH;                     // chunked: [8 warps * TPW * 16 rows] x {b, s, t, bi, si}
   constexpr int ST_ROWS = CHUNKED ? VQM_WARPS * VQM_TPW * 16 : 0;
   float* st_s = st_b + ST_ROWS;
-  int* st_bi = reinterpret_cast<int*>(st_s + ST_ROWS);
+  float* st_t = st_s + ST_ROWS;
+  int* st_bi = reinterpret_cast<int*>(st_t + ST_ROWS);
   int* st_si = st_bi + ST_ROWS;
   float* cnt_s = reinterpret_cast<float*>(st_si + ST_ROWS);   // stats: cnt_s[K] | elat_s[4] | dw_s[K*256]
   const int K = p.K;
@@ -150,7 +169,7 @@ __global__ void __launch_bounds__(VqmCfg<NT>::WARPS * 32, VqmCfg<NT>::BLOCKS) vq
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int nchunks = (K + KCH - 1) / KCH;
-  const float INF = __int_as_float(0x7f800000);
+  const float INF = 3.0e38f;                     // finite: a packed key must not become a NaN pattern
 
   if (p.stats) {
     for (int i = tid; i < K + 4 + (smem_dw ? K * VQ_Z : 0); i += VQM_THREADS) cnt_s[i] = 0.f;
@@ -198,7 +217,7 @@ __global__ void __launch_bounds__(VqmCfg<NT>::WARPS * 32, VqmCfg<NT>::BLOCKS) vq
       inv_g = rsqrtf(fmaxf(xs_g, 1e-6f)); inv_h = rsqrtf(fmaxf(xs_h, 1e-6f));
       xs_g = xs_g * inv_g * inv_g; xs_h = xs_h * inv_h * inv_h;
     }
-    Top2 tg = {INF, INF, 0, 0}, th = {INF, INF, 0, 0};
+    Top3 pg = {INF, INF, INF}, ph = {INF, INF, INF};
     float mv = 0.f;
     if (MODE == 0 && p.sel_mask) mv = ord2f(*p.maxdist);
 #pragma unroll
@@ -225,49 +244,66 @@ __global__ void __launch_bounds__(VqmCfg<NT>::WARPS * 32, VqmCfg<NT>::BLOCKS) vq
           if (ok_g) p.dist_out[row_g * K + k] = dg;
           if (ok_h) p.dist_out[row_h * K + k] = dh;
         }
-        top2_push(tg, dg, k);
-        top2_push(th, dh, k);
+        top3_push(pg, vqm_pack(dg, kk));
+        top3_push(ph, vqm_pack(dh, kk));
       }
     }
     if (MODE == 1) return;
 #pragma unroll
     for (int o = 1; o <= 2; o <<= 1) {
-      float ob = __shfl_xor_sync(0xffffffffu, tg.b, o), os = __shfl_xor_sync(0xffffffffu, tg.s, o);
-      int obi = __shfl_xor_sync(0xffffffffu, tg.bi, o), osi = __shfl_xor_sync(0xffffffffu, tg.si, o);
-      top2_merge(tg, ob, obi, os, osi);
-      ob = __shfl_xor_sync(0xffffffffu, th.b, o); os = __shfl_xor_sync(0xffffffffu, th.s, o);
-      obi = __shfl_xor_sync(0xffffffffu, th.bi, o); osi = __shfl_xor_sync(0xffffffffu, th.si, o);
-      top2_merge(th, ob, obi, os, osi);
+      float ob = __shfl_xor_sync(0xffffffffu, pg.b, o), os = __shfl_xor_sync(0xffffffffu, pg.s, o);
+      float ot = __shfl_xor_sync(0xffffffffu, pg.t, o);
+      top3_push(pg, ob); top3_push(pg, os); top3_push(pg, ot);
+      ob = __shfl_xor_sync(0xffffffffu, ph.b, o); os = __shfl_xor_sync(0xffffffffu, ph.s, o);
+      ot = __shfl_xor_sync(0xffffffffu, ph.t, o);
+      top3_push(ph, ob); top3_push(ph, os); top3_push(ph, ot);
     }
+    Top2 tg = {vqm_val(pg.b), vqm_val(pg.s), vqm_val(pg.t), ch * KCH + vqm_idx(pg.b), ch * KCH + vqm_idx(pg.s)};
+    Top2 th = {vqm_val(ph.b), vqm_val(ph.s), vqm_val(ph.t), ch * KCH + vqm_idx(ph.b), ch * KCH + vqm_idx(ph.s)};
     if (CHUNKED) {
       // running state across codeword chunks (earlier chunk = lower indices, merged first)
       const int sg = slot * 16 + g, sh = sg + 8;
       if (ch > 0) {
-        Top2 rg = {st_b[sg], st_s[sg], st_bi[sg], st_si[sg]}, rh = {st_b[sh], st_s[sh], st_bi[sh], st_si[sh]};
-        top2_merge(rg, tg.b, tg.bi, tg.s, tg.si); tg = rg;
-        top2_merge(rh, th.b, th.bi, th.s, th.si); th = rh;
+        Top2 rg = {st_b[sg], st_s[sg], st_t[sg], st_bi[sg], st_si[sg]};
+        Top2 rh = {st_b[sh], st_s[sh], st_t[sh], st_bi[sh], st_si[sh]};
+        top2_merge(rg, tg.b, tg.bi, tg.s, tg.si, tg.t); tg = rg;
+        top2_merge(rh, th.b, th.bi, th.s, th.si, th.t); th = rh;
       }
       if (ch + 1 < nchunks) {
         __syncwarp();
         if (t == 0) {
-          st_b[sg] = tg.b; st_s[sg] = tg.s; st_bi[sg] = tg.bi; st_si[sg] = tg.si;
-          st_b[sh] = th.b; st_s[sh] = th.s; st_bi[sh] = th.bi; st_si[sh] = th.si;
+          st_b[sg] = tg.b; st_s[sg] = tg.s; st_t[sg] = tg.t; st_bi[sg] = tg.bi; st_si[sg] = tg.si;
+          st_b[sh] = th.b; st_s[sh] = th.s; st_t[sh] = th.t; st_bi[sh] = th.bi; st_si[sh] = th.si;
         }
         __syncwarp();
         return;
       }
     }
-    // fp64 re-score of near-ties (top-2 gap below 4e-5 relative): exact ordering of the two candidates
+    // fp64 re-score of near-ties.  The tensor-core distance carries the split error (~2^-20 |x||c|) and the fp32
+    // accumulation error, both proportional to |x||c| <= SCALE = |d| + 2 ||x||^2: runner-up within 1.1e-5 SCALE of the best ->
+    // exact ordering of the two candidates; THIRD-best within 4e-6 SCALE -> the approximate values cannot name the
+    // candidates (three-way near-tie, a few rows per million): every codeword is re-scored in fp64.
     int best_g = tg.bi, best_h = th.bi;
     {
-      bool near_g = ok_g && K > 1 && (tg.s - tg.b) <= 4e-5f * fmaxf(fabsf(tg.b), 1e-3f);
-      bool near_h = ok_h && K > 1 && (th.s - th.b) <= 4e-5f * fmaxf(fabsf(th.b), 1e-3f);
+      // |d| + 2 ||x||^2 bounds 2 |x||c| from above up to a small factor without keeping ||c_best||^2 across chunks
+      const float sc_g = fmaxf(fabsf(tg.b) + 2.f * xs_g, 1e-3f), sc_h = fmaxf(fabsf(th.b) + 2.f * xs_h, 1e-3f);
+      // + 2 * 2^-17 |d|: the packed keys of the hot loop are truncated to 17 mantissa bits
+      bool near3_g = ok_g && K > 2 && (tg.t - tg.b) <= 4.0e-6f * sc_g + 1.6e-5f * fmaxf(fabsf(tg.b), fabsf(tg.t));
+      bool near3_h = ok_h && K > 2 && (th.t - th.b) <= 4.0e-6f * sc_h + 1.6e-5f * fmaxf(fabsf(th.b), fabsf(th.t));
+      bool near_g = ok_g && K > 1 && !near3_g && (tg.s - tg.b) <= 1.1e-5f * sc_g + 1.6e-5f * fmaxf(fabsf(tg.b), fabsf(tg.s));
+      bool near_h = ok_h && K > 1 && !near3_h && (th.s - th.b) <= 1.1e-5f * sc_h + 1.6e-5f * fmaxf(fabsf(th.b), fabsf(th.s));
       if (p.sel_mask) {
+        // dropped codewords all sit at the mask value (vq_layers.py:290): ties among them keep the first index, which
+        // the scan order already delivers; a re-score in exact arithmetic would not reproduce the masked values
         if (near_g && (p.sel_mask[tg.bi] == 0.f || p.sel_mask[tg.si] == 0.f)) near_g = false;
         if (near_h && (p.sel_mask[th.bi] == 0.f || p.sel_mask[th.si] == 0.f)) near_h = false;
+        if (near3_g && p.sel_mask[tg.bi] == 0.f) near3_g = false;
+        if (near3_h && p.sel_mask[th.bi] == 0.f) near3_h = false;
       }
       unsigned need_g = __ballot_sync(0xffffffffu, near_g && t == 0);
       unsigned need_h = __ballot_sync(0xffffffffu, near_h && t == 0);
+      unsigned need3_g = __ballot_sync(0xffffffffu, near3_g && t == 0);
+      unsigned need3_h = __ballot_sync(0xffffffffu, near3_h && t == 0);
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         unsigned need = half ? need_h : need_g;
@@ -294,6 +330,34 @@ __global__ void __launch_bounds__(VqmCfg<NT>::WARPS * 32, VqmCfg<NT>::BLOCKS) vq
           }
           const bool swap = (d2 < d1) || (d2 == d1 && i2 < i1);
           if (swap && (lane >> 2) == (src >> 2)) { if (half) best_h = i2; else best_g = i2; }
+        }
+        need = half ? need3_h : need3_g;
+#pragma unroll 1
+        while (need) {                                           // warp-uniform: every (not dropped) codeword in fp64
+          const int src = __ffs(need) - 1;
+          need &= need - 1;
+          const long long row = tile * 16 + (src >> 2) + 8 * half;
+          const float inv = __shfl_sync(0xffffffffu, half ? inv_h : inv_g, src);
+          double bestd = 1.0e300;
+          int besti = 0x7fffffff;
+#pragma unroll 1
+          for (int k = lane; k < K; k += 32) {
+            if (p.sel_mask && p.sel_mask[k] == 0.f) continue;    // sits at the mask value, cannot beat a kept codeword
+            double d = 0.0;
+#pragma unroll 4
+            for (int z = 0; z < VQ_Z; ++z) {
+              const double xv = (double)(p.x[row * VQ_Z + z] * inv), c = (double)p.cb[(size_t)z * K + k];
+              d += c * c - 2.0 * xv * c;
+            }
+            if (d < bestd) { bestd = d; besti = k; }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, bestd, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (od < bestd || (od == bestd && oi < besti)) { bestd = od; besti = oi; }
+          }
+          if ((lane >> 2) == (src >> 2)) { if (half) best_h = besti; else best_g = besti; }
         }
       }
     }
@@ -438,7 +502,7 @@ static int launch_nt(vqn_ctx* ctx, VqParams p, cudaStream_t s) {
   const int K = p.K;
   const bool smem_dw = p.stats && p.want_dw && K <= 32;
   size_t smem = sizeof(float4) * 32 * NT * 32 + sizeof(float) * 8 * NT +
-                (CHUNKED ? sizeof(float) * 4 * VQM_WARPS * VQM_TPW * 16 : 0) +
+                (CHUNKED ? sizeof(float) * 5 * VQM_WARPS * VQM_TPW * 16 : 0) +
                 sizeof(float) * (p.stats ? K + 4 + (smem_dw ? (size_t)K * VQ_Z : 0) : 0);
   const long long ntiles = (p.n + 15) / 16;
   long long want = CHUNKED ? (ntiles + VQM_WARPS * VQM_TPW - 1) / (VQM_WARPS * VQM_TPW)

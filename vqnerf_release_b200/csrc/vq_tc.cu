@@ -63,20 +63,118 @@ struct VtParams {
   long long* idx_out;
 };
 
-struct Top2 { float b, s; int bi, si; };
+// Running (best, runner-up, third) of a row as PACKED keys: the distance with its low `ibits` mantissa bits replaced by
+// the codeword index (ibits = log2 of the padded codeword count, <= 10).  The arg-min scan is then five FMNMX per
+// codeword and no index bookkeeping (round 1 tracked two indices with predicated selects: 8 ALU-pipe operations per
+// codeword, and the accumulator drain is what bounds K >= 128); the truncation (2^(ibits-23) relative) is far above the
+// arithmetic error, so it is covered by the same exactness net: every near-tie is re-scored in fp64 below.
+struct Top3 { float b, s, t; };
 
-__device__ __forceinline__ void top2_push(Top2& t, float d, int i) {
-  if (d < t.b) { t.s = t.b; t.si = t.bi; t.b = d; t.bi = i; }
-  else if (d < t.s) { t.s = d; t.si = i; }
+__device__ __forceinline__ void top3_push(Top3& m, float dp) {
+  m.t = fminf(m.t, fmaxf(dp, m.s));
+  m.s = fminf(m.s, fmaxf(dp, m.b));
+  m.b = fminf(m.b, dp);
 }
-// merge (ob, obi, os, osi) into t; ties go to the lower index (first minimum, tf.argmax(-d))
-__device__ __forceinline__ void top2_merge(Top2& t, float ob, int obi, float os, int osi) {
-  const bool other_first = (ob < t.b) || (ob == t.b && obi < t.bi);
-  float b, s, c1, c2_; int bi, si, i1, i2;
-  if (other_first) { b = ob; bi = obi; c1 = t.b; i1 = t.bi; c2_ = os; i2 = osi; }
-  else { b = t.b; bi = t.bi; c1 = ob; i1 = obi; c2_ = t.s; i2 = t.si; }
-  if ((c1 < c2_) || (c1 == c2_ && i1 < i2)) { s = c1; si = i1; } else { s = c2_; si = i2; }
-  t.b = b; t.bi = bi; t.s = s; t.si = si;
+// running result across codeword blocks: the keys keep their BLOCK-LOCAL 8-bit index (so the truncation stays at
+// 2^-15 for any K); the blocks of the best and of the runner-up are tracked here, once per block instead of per codeword
+struct Run3 { float b, s, t; int bb, sb; };
+__device__ __forceinline__ void run3_push(Run3& m, float k, int blk) {
+  const bool p1 = k < m.b, p2 = k < m.s;
+  m.t = fminf(m.t, fmaxf(k, m.s));
+  m.s = fminf(m.s, fmaxf(k, m.b));
+  m.sb = p1 ? m.bb : (p2 ? blk : m.sb);
+  m.b = fminf(m.b, k);
+  m.bb = p1 ? blk : m.bb;
+}
+__device__ __forceinline__ float vt_pack(float d, uint32_t kmask, int idx) {
+  return __int_as_float((int)((__float_as_uint(d) & kmask) + (uint32_t)idx));
+}
+
+// Tolerances of the exactness net.  The tensor-core value of c^2 - 2 x.c carries the 3-term split error (~2^-20 of |x||c|)
+// and the accumulator's truncation (48 accumulation steps of < 1 ulp each; measured on unit vectors: a common bias of
+// ~3.5e-6 and a spread of +-5e-7), all proportional to SCALE = ||x||^2 + ||c||^2 >= 2 |x.c|; on top of that the packed
+// keys are truncated by up to TRUNC = 2^(ibits-23) |d| each:
+//   runner-up within VT_TOL2 * SCALE + 2 TRUNC of the best  -> the two candidates are re-scored in fp64;
+//   THIRD-best within VT_TOL3 * SCALE + 2 TRUNC of the best -> three-way near-tie, the approximate values cannot even name
+//   the candidates (round 2 sweep: 1 row of 4 M at K = 128 had the true winner ranked third): the row is re-scored in
+//   fp64 against EVERY codeword.  Exact duplicates land in one of the two and resolve to the first index.
+#define VT_TOL2 1.1e-5f
+#define VT_TOL3 4.0e-6f
+
+// fp64 distances (minus the row constant ||x||^2) of one latent row to every codeword, warp-cooperative: lane owns the
+// codewords k = lane + 32 i, four at a time for ILP; returns the first arg-min (networks/vq_layers.py:279-292 in
+// exact arithmetic)
+__device__ __forceinline__ int vt_full_rescore(const float* __restrict__ xrow, const float* __restrict__ cb, int K, int lane) {
+  double bestd = 1.0e300;
+  int besti = 0x7fffffff;
+  for (int k0 = lane; k0 < K; k0 += 128) {
+    const int k1 = min(k0 + 32, K - 1), k2 = min(k0 + 64, K - 1), k3 = min(k0 + 96, K - 1);
+    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+#pragma unroll 2
+    for (int z = 0; z < VQ_Z; ++z) {
+      const double x2 = 2.0 * (double)xrow[z];
+      const float* cr = cb + (size_t)z * K;
+      const double c0 = (double)cr[k0], c1 = (double)cr[k1], c2 = (double)cr[k2], c3 = (double)cr[k3];
+      d0 += c0 * (c0 - x2); d1 += c1 * (c1 - x2); d2 += c2 * (c2 - x2); d3 += c3 * (c3 - x2);
+    }
+    if (d0 < bestd) { bestd = d0; besti = k0; }                  // increasing k: strict < keeps the first minimum
+    if (k0 + 32 < K && d1 < bestd) { bestd = d1; besti = k0 + 32; }
+    if (k0 + 64 < K && d2 < bestd) { bestd = d2; besti = k0 + 64; }
+    if (k0 + 96 < K && d3 < bestd) { bestd = d3; besti = k0 + 96; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double od = __shfl_xor_sync(0xffffffffu, bestd, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (od < bestd || (od == bestd && oi < besti)) { bestd = od; besti = oi; }
+  }
+  return besti;
+}
+
+// The tile's final decision for the 32 rows a warp owns (one row per lane): m = the row's packed (best, runner-up,
+// third), xsum = ||x||^2.  Near-ties are resolved in fp64, warp-cooperatively; returns the row's index.
+__device__ __forceinline__ int vt_resolve(float mb, float ms, float mt, int bblk, int sblk, uint32_t kmask, float xsum,
+                                          const float* c2_s, bool ok, const float* __restrict__ x, long long row0,
+                                          const float* __restrict__ cb, int K, int lane) {
+  const int bi = 256 * bblk + (int)(__float_as_uint(mb) & ~kmask), si = 256 * sblk + (int)(__float_as_uint(ms) & ~kmask);
+  const float bv = __uint_as_float(__float_as_uint(mb) & kmask), sv = __uint_as_float(__float_as_uint(ms) & kmask);
+  const float tv = __uint_as_float(__float_as_uint(mt) & kmask);
+  int best = bi;
+  const float scale = fmaxf(xsum + c2_s[min(bi, VT_MAXK - 1)], 1e-3f);
+  const float trunc2 = 2.0f * __uint_as_float(0x34000000u) * (float)(~kmask + 1u);   // 2 * 2^-23 * 2^ibits
+  const bool near3 = ok && K > 2 && (tv - bv) <= VT_TOL3 * scale + trunc2 * fmaxf(fabsf(bv), fabsf(tv));
+  const bool near2 = ok && K > 1 && !near3 && (sv - bv) <= VT_TOL2 * scale + trunc2 * fmaxf(fabsf(bv), fabsf(sv));
+  unsigned need = __ballot_sync(0xffffffffu, near2);
+  while (need) {                                                // warp-uniform: fp64 re-score of the two candidates
+    const int src = __ffs(need) - 1;
+    need &= need - 1;
+    const float* xr = x + (row0 + src) * VQ_Z;
+    const int i1 = __shfl_sync(0xffffffffu, bi, src), i2 = __shfl_sync(0xffffffffu, si, src);
+    double d1 = 0.0, d2 = 0.0;
+#pragma unroll
+    for (int mm = 0; mm < 8; ++mm) {
+      const int z = lane + 32 * mm;
+      const double xv = (double)xr[z];
+      const double c1 = (double)cb[(size_t)z * K + i1], c2v = (double)cb[(size_t)z * K + i2];
+      d1 += c1 * c1 - 2.0 * xv * c1;
+      d2 += c2v * c2v - 2.0 * xv * c2v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+      d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+    }
+    const bool first2 = (d2 < d1) || (d2 == d1 && i2 < i1);
+    if (lane == src) best = first2 ? i2 : i1;
+  }
+  need = __ballot_sync(0xffffffffu, near3);
+  while (need) {                                                // three-way near-tie: every codeword, in fp64
+    const int src = __ffs(need) - 1;
+    need &= need - 1;
+    const int fi = vt_full_rescore(x + (row0 + src) * VQ_Z, cb, K, lane);
+    if (lane == src) best = fi;
+  }
+  return best;
 }
 
 // codebook block -> per K-chunk swizzled images: plane H = tf32 hi [Npad x 32 fp32], plane C = [bf16(hi) x 32 | bf16(lo) x 32]
@@ -189,6 +287,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
   const uint32_t tmem_base = tmem_base_s;
   const long long n_tiles = (p.n + VT_M - 1) / VT_M;
   const int nb = p.nb;
+  const uint32_t kmask = ~((p.K <= 64 ? 64u : 128u) - 1u);         // packed-key index bits (one codeword block, K <= 128)
 
   if (warp < 8 * VT_G) {
     // ===================== producers: A chunks (split into the tf32 + bf16-correction planes), ||x||^2 =====================
@@ -196,6 +295,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
     const int r = 32 * (warp & 3) + lane;                          // latent row of the tile
     uint32_t ga = 0;                                               // global chunk counter
     uint32_t tile_i = 0;
+    const uint32_t rt_zero = (uint32_t)p.K & 0x40000000u;          // 0 (K <= 1024), not foldable at compile time
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_i) {
       float xs = 0.f;
       for (int b = 0; b < nb; ++b) {
@@ -213,7 +313,19 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
             const float4 t = tc::lds128(stage + r * 128 + (((4 * half + q) ^ (r & 7)) << 4));
             v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
           }
-          tc::mbar_arrive(&x_empty[xs_i]);                      // the buffer may be refilled
+          // The staging buffer may be refilled -- but only once the LDS results above have RETURNED: an
+          // mbarrier.arrive issued right behind the loads is not ordered behind them by the hardware (it overtakes
+          // them when the shared-memory pipe is busy with the UMMA operand reads, and the TMA engine then overwrites
+          // rows that have not been read yet: ~1e-3 of the rows got another tile's values, non-deterministically).
+          // The arrive therefore takes a register dependency on the last word of every load (an address offset that
+          // is zero at run time but unknown to the compiler).
+          {
+            uint32_t dep;
+            asm volatile("{\n\t.reg .b32 t0, t1;\n\tor.b32 t0, %1, %2;\n\tor.b32 t1, %3, %4;\n\tor.b32 t0, t0, t1;\n\t"
+                         "and.b32 %0, t0, %5;\n\t}"
+                         : "=r"(dep) : "f"(v[3]), "f"(v[7]), "f"(v[11]), "f"(v[15]), "r"(rt_zero));
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&x_empty[xs_i]) + dep) : "memory");
+          }
           tc::mbar_wait(&a_empty[slot], ((ga / VT_STAGES) & 1u) ^ 1u);
           if (b == 0) {
 #pragma unroll
@@ -237,7 +349,8 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q4) << 16);
     uint32_t gk = 0, tile_i = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_i) {
-      Top2 m = {3.0e38f, 3.0e38f, 0x7fffffff, 0x7fffffff};
+      Top3 m = {3.0e38f, 3.0e38f, 3.0e38f};
+      float xsum = 0.f;
       for (int b = 0; b < nb; ++b, ++gk) {
         const int region = (int)(gk & 1u);
         tc::mbar_wait(&acc_full[region], (gk >> 1) & 1u);
@@ -248,43 +361,19 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
           float v[16];
           tc::tmem_ld16(lane_addr + (uint32_t)(region * 256 + c16), v);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) top2_push(m, fmaf(-2.0f, v[j], c2b[c16 + j]), 256 * b + c16 + j);
+          for (int j = 0; j < 16; ++j) top3_push(m, vt_pack(fmaf(-2.0f, v[j], c2b[c16 + j]), kmask, 256 * b + c16 + j));
+        }
+        if (b == nb - 1) {                                        // before the hand-over: the producers reuse xs_s two tiles on
+#pragma unroll
+          for (int q = 0; q < 4; ++q) xsum += xs_s[tile_i & 1u][r * 4 + q];
         }
         tc::fence_before_sync();
         tc::mbar_arrive(&drain_done[region]);                     // the tensor cores may refill this TMEM region
       }
       // ---- the tile's arg-min: near-ties re-scored in fp64, index written ----
-      float xsum = 0.f;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) xsum += xs_s[tile_i & 1u][r * 4 + q];
       const long long row = tile * VT_M + r;
       const bool ok = row < p.n;
-      int best = m.bi;
-      const float full = m.b + xsum;                              // the reference's distance of the winner
-      const bool near = ok && p.K > 1 && (m.s - m.b) <= 4e-5f * fmaxf(fabsf(full), 1e-3f);
-      unsigned need = __ballot_sync(0xffffffffu, near);
-      while (need) {                                              // warp-uniform: fp64 re-score of the two candidates
-        const int src = __ffs(need) - 1;
-        need &= need - 1;
-        const long long rrow = tile * VT_M + 32 * q4 + src;
-        const int i1 = __shfl_sync(0xffffffffu, m.bi, src), i2 = __shfl_sync(0xffffffffu, m.si, src);
-        double d1 = 0.0, d2 = 0.0;
-#pragma unroll
-        for (int mm = 0; mm < 8; ++mm) {
-          const int z = lane + 32 * mm;
-          const double xv = (double)p.x[rrow * VQ_Z + z];
-          const double c1 = (double)p.cb[(size_t)z * p.K + i1], c2v = (double)p.cb[(size_t)z * p.K + i2];
-          d1 += c1 * c1 - 2.0 * xv * c1;
-          d2 += c2v * c2v - 2.0 * xv * c2v;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          d1 += __shfl_xor_sync(0xffffffffu, d1, o);
-          d2 += __shfl_xor_sync(0xffffffffu, d2, o);
-        }
-        const bool swap = (d2 < d1) || (d2 == d1 && i2 < i1);
-        if (swap && lane == src) best = i2;
-      }
+      const int best = vt_resolve(m.b, m.s, m.t, 0, 0, kmask, xsum, c2_s, ok, p.x, tile * VT_M + 32 * q4, p.cb, p.K, lane);
       if (ok) p.idx_out[row] = (long long)best;
     }
   } else if (warp == MMA_WARP) {
@@ -378,8 +467,8 @@ __global__ void __launch_bounds__(VT_THREADS_BIG, 1) vq_tc_big_kernel(const __gr
   __shared__ __align__(8) uint64_t acc_full[2], drain_done[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float c2_s[VT_MAXK];
-  __shared__ __align__(16) float4 merge_s[2][VT_M * 4];      // Top2 of the 4 threads of a row, double-buffered by tile
-  __shared__ float xs_s[2][VT_M * 4];
+  __shared__ __align__(16) float4 merge_s[2][VT_M * 4];      // packed Top3 + ||x||^2 share of the 4 threads of a row, double-buffered by tile
+  __shared__ int mergeb_s[2][VT_M * 4];                      // codeword block of their best | runner-up << 8
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_ring = smem;
   uint8_t* w_ring = smem + (size_t)VT_STAGES * VT_A_SLOT;
@@ -403,6 +492,7 @@ __global__ void __launch_bounds__(VT_THREADS_BIG, 1) vq_tc_big_kernel(const __gr
   const uint32_t tmem_base = tmem_base_s;
   const long long n_tiles = (p.n + VT_M - 1) / VT_M;
   const int nl = p.nb / BPL;                                       // layers per tile (p.nb is even in PAIR mode)
+  const uint32_t kmask = ~255u;                                    // packed keys carry the index inside the 256-codeword block
   // columns of codeword block b (a padding block of PAIR mode has 16 all-padding columns)
   auto npad_of = [&](int b) { const int nblk = min(256, p.K - 256 * b); return nblk <= 0 ? 16 : (nblk + 15) / 16 * 16; };
 
@@ -412,7 +502,7 @@ __global__ void __launch_bounds__(VT_THREADS_BIG, 1) vq_tc_big_kernel(const __gr
     const int r = 32 * (warp & 3) + lane;                          // TMEM lane == latent row of the tile
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
     uint32_t ga = 0, gk = 0;                                       // global chunk / layer counters
-    Top2 t2 = {3.0e38f, 3.0e38f, 0, 0};
+    Run3 t2 = {3.0e38f, 3.0e38f, 3.0e38f, 0, 0};
     float xs = 0.f, xs_fin = 0.f;
     long long pend_tile = -1; int pend_l = 0; uint32_t pend_k = 0; uint32_t tiles_done = 0;
 
@@ -425,63 +515,43 @@ __global__ void __launch_bounds__(VT_THREADS_BIG, 1) vq_tc_big_kernel(const __gr
         tc::fence_after_sync();
         const int npad = npad_of(b);
         const float* c2b = c2_s + 256 * b;
+        Top3 blk = {3.0e38f, 3.0e38f, 3.0e38f};
         for (int cbk = grp; cbk * 32 < npad; cbk += VT_G) {
           const int c16 = cbk * 32 + 16 * half;
           if (c16 < npad) {
             float v[16];
             tc::tmem_ld16(lane_addr + (uint32_t)(region * 256 + c16), v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) top2_push(t2, fmaf(-2.0f, v[j], c2b[c16 + j]), 256 * b + c16 + j);
+            for (int j = 0; j < 16; ++j) top3_push(blk, vt_pack(fmaf(-2.0f, v[j], c2b[c16 + j]), kmask, c16 + j));
           }
         }
         tc::fence_before_sync();
         tc::mbar_arrive(&drain_done[region]);
+        run3_push(t2, blk.b, b); run3_push(t2, blk.s, b); run3_push(t2, blk.t, b);
       }
       if (l + 1 < nl) return;
       // ---- last layer of the tile: merge the 4 partial results of each row, re-score near-ties, write the index ----
       const int buf = (int)(tiles_done & 1u);
       ++tiles_done;
-      merge_s[buf][r * 4 + grp * 2 + half] = make_float4(t2.b, t2.s, __int_as_float(t2.bi), __int_as_float(t2.si));
-      xs_s[buf][r * 4 + grp * 2 + half] = xs_fin;
-      t2.b = 3.0e38f; t2.s = 3.0e38f; t2.bi = 0; t2.si = 0;
+      merge_s[buf][r * 4 + grp * 2 + half] = make_float4(t2.b, t2.s, t2.t, xs_fin);
+      mergeb_s[buf][r * 4 + grp * 2 + half] = t2.bb | (t2.sb << 8);
+      t2.b = 3.0e38f; t2.s = 3.0e38f; t2.t = 3.0e38f; t2.bb = 0; t2.sb = 0;
       asm volatile("bar.sync 3, %0;" ::"r"(256 * VT_G) : "memory");
       if (grp == 0 && half == 0) {
-        Top2 m = {3.0e38f, 3.0e38f, 0x7fffffff, 0x7fffffff};
+        Run3 m = {3.0e38f, 3.0e38f, 3.0e38f, 0, 0};
         float xsum = 0.f;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 e = merge_s[buf][r * 4 + q];
-          top2_merge(m, e.x, __float_as_int(e.z), e.y, __float_as_int(e.w));
-          xsum += xs_s[buf][r * 4 + q];
+          const int eb = mergeb_s[buf][r * 4 + q];
+          // a partial's third can only enter the merged top two through a tie, and ties go to the full re-score
+          run3_push(m, e.x, eb & 255); run3_push(m, e.y, eb >> 8); run3_push(m, e.z, eb >> 8);
+          xsum += e.w;
         }
         const long long row = tile * VT_M + r;
         const bool ok = row < p.n;
-        int best = m.bi;
-        const float full = m.b + xsum;                            // the reference's distance of the winner
-        const bool near = ok && p.K > 1 && (m.s - m.b) <= 4e-5f * fmaxf(fabsf(full), 1e-3f);
-        unsigned need = __ballot_sync(0xffffffffu, near);
-        while (need) {                                            // warp-uniform: fp64 re-score of the two candidates
-          const int src = __ffs(need) - 1;
-          need &= need - 1;
-          const long long rrow = tile * VT_M + 32 * (warp & 3) + src;
-          const int i1 = __shfl_sync(0xffffffffu, m.bi, src), i2 = __shfl_sync(0xffffffffu, m.si, src);
-          double d1 = 0.0, d2 = 0.0;
-#pragma unroll
-          for (int mm = 0; mm < 8; ++mm) {
-            const int z = lane + 32 * mm;
-            const double xv = (double)p.x[rrow * VQ_Z + z];
-            const double c1 = (double)p.cb[(size_t)z * p.K + i1], c2v = (double)p.cb[(size_t)z * p.K + i2];
-            d1 += c1 * c1 - 2.0 * xv * c1;
-            d2 += c2v * c2v - 2.0 * xv * c2v;
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            d1 += __shfl_xor_sync(0xffffffffu, d1, o);
-            d2 += __shfl_xor_sync(0xffffffffu, d2, o);
-          }
-          const bool swap = (d2 < d1) || (d2 == d1 && i2 < i1);
-          if (swap && lane == src) best = i2;
-        }
+        const int best = vt_resolve(m.b, m.s, m.t, m.bb, m.sb, kmask, xsum, c2_s, ok, p.x, tile * VT_M + 32 * (warp & 3),
+                                    p.cb, p.K, lane);
         if (ok) p.idx_out[row] = (long long)best;
       }
     };
