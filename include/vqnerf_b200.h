@@ -226,6 +226,15 @@ int vqn_material_combine(vqn_ctx* ctx, const float* basecolor, const float* ks, 
                          const int32_t* n_dev, int64_t n, float* albedo, float* spec, float* albedo_scaled,
                          float* spec_scaled, vqn_stream stream);
 
+/* fast_render(edit_mask=, edit_material=) (models/vq_nfr.py:258-260 `_update_material`, :293-295, :324-330): compact rows
+ * whose edit_mask[row_idx[i] * mask_stride] > 0 get albedo := diff3, spec := spec3, rough := rough1 (HOST pointers; NULL =
+ * the reference's "update[0] < 0: leave alone"), in place; the opt_scale'd copies the shading kernel reads are refreshed
+ * (:333-336).  edit_mask is the full-length [n_total, mask_stride] tensor of the reference's signature. */
+int vqn_material_edit(vqn_ctx* ctx, const float* edit_mask, int mask_stride, const int32_t* row_idx,
+                      const int32_t* n_dev, int64_t n, const float* diff3, const float* spec3, const float* rough1,
+                      const float* opt_scale, float* albedo, float* spec, float* rough, float* albedo_scaled,
+                      float* spec_scaled, vqn_stream stream);
+
 /* util/img.py:142-186 */
 int vqn_linear2srgb(vqn_ctx* ctx, const float* x, int64_t count, float* out, vqn_stream stream);
 int vqn_srgb2linear(vqn_ctx* ctx, const float* x, int64_t count, float* out, vqn_stream stream);

@@ -88,6 +88,7 @@ SIGNATURES = {
     'vqn_eval_brdf': (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P]),
     'vqn_render': (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _F, _P, _P]),
     'vqn_material_combine': (_I, [_P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P]),
+    'vqn_material_edit': (_I, [_P, _P, _I, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'vqn_linear2srgb': (_I, [_P, _P, _L, _P, _P]),
     'vqn_srgb2linear': (_I, [_P, _P, _L, _P, _P]),
     'vqn_compact_mask': (_I, [_P, _P, _L, _P, _P, _P, _P]),

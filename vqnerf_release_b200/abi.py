@@ -338,6 +338,35 @@ def material_combine(basecolor, ks, opt_scale=None, n_dev=None, want_scaled=True
     return albedo, spec, (a_s if a_s is not None else albedo), (s_s if s_s is not None else spec)
 
 
+def material_edit(edit_mask, edit_material, row_idx, n_dev, albedo, spec, rough, opt_scale=None, albedo_s=None,
+                  spec_s=None):
+    """fast_render's `_update_material` (models/vq_nfr.py:258-260, 324-330), in place on the compact tensors.  A channel
+    list whose first entry is negative is left alone, as in the reference."""
+    import ctypes as C
+    edit_mask = _f(edit_mask)
+    if edit_mask.dim() == 1:
+        edit_mask = edit_mask[:, None]
+    stride = edit_mask.shape[1]
+
+    def host(vals, k):
+        vals = list(vals)
+        if vals[0] < 0:
+            return None
+        if len(vals) != k:
+            raise ValueError('edit_material: expected %d values, got %d' % (k, len(vals)))
+        return (C.c_float * k)(*[float(v) for v in vals])
+    d3, s3, r1 = host(edit_material['diff'], 3), host(edit_material['spec'], 3), host(edit_material['rough'], 1)
+    cptr = lambda a: C.cast(a, C.c_void_p) if a is not None else None
+    if opt_scale is not None:
+        opt_scale = _f(opt_scale).reshape(-1)
+    c = _ctx(albedo)
+    L.check(c.lib.vqn_material_edit(c.handle, L.ptr(edit_mask), stride, L.ptr(row_idx, torch.int32),
+                                    L.ptr(n_dev, torch.int32), albedo.shape[0], cptr(d3), cptr(s3), cptr(r1),
+                                    L.ptr(opt_scale), L.ptr(albedo), L.ptr(spec), L.ptr(rough),
+                                    L.ptr(albedo_s if albedo_s is not albedo else None),
+                                    L.ptr(spec_s if spec_s is not spec else None), L.stream_ptr(albedo.device)))
+
+
 def linear2srgb(x):
     x = _f(x)
     out = torch.empty_like(x)

@@ -409,3 +409,51 @@ extern "C" int vqn_material_combine(vqn_ctx* ctx, const float* basecolor, const 
   VQN_LAUNCHED(ctx);
   return VQN_OK;
 }
+
+// fast_render's material edit (models/vq_nfr.py:258-260, 293-295, 324-330): rows whose edit_mask[..., 0] > 0 get
+// src * (1 - m) + m * update with m = 1, i.e. the update; the scaled copies the shading kernel reads follow (:333-336)
+__global__ void material_edit_kernel(const float* __restrict__ edit_mask, int mask_stride, const int* __restrict__ row_idx,
+                                     const int* __restrict__ n_dev, long long n_max, float3 diff, int has_diff, float3 spc,
+                                     int has_spec, float rgh, int has_rough, const float* __restrict__ opt_scale,
+                                     float* __restrict__ albedo, float* __restrict__ spec, float* __restrict__ rough,
+                                     float* __restrict__ albedo_s, float* __restrict__ spec_s) {
+  long long n = n_dev ? (long long)*n_dev : n_max;
+  if (n > n_max) n = n_max;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = row_idx ? (long long)row_idx[i] : i;
+    const float m = edit_mask[row * mask_stride] > 0.f ? 1.f : 0.f;
+    const float sc[3] = {opt_scale ? opt_scale[0] : 1.f, opt_scale ? opt_scale[1] : 1.f, opt_scale ? opt_scale[2] : 1.f};
+    const float dv[3] = {diff.x, diff.y, diff.z}, sv[3] = {spc.x, spc.y, spc.z};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (has_diff) {
+        const float v = albedo[i * 3 + c] * (1.f - m) + m * dv[c];
+        albedo[i * 3 + c] = v;
+        if (albedo_s) albedo_s[i * 3 + c] = opt_scale ? v * sc[c] : v;
+      }
+      if (has_spec) {
+        const float v = spec[i * 3 + c] * (1.f - m) + m * sv[c];
+        spec[i * 3 + c] = v;
+        if (spec_s) spec_s[i * 3 + c] = opt_scale ? v * sc[c] : v;
+      }
+    }
+    if (has_rough) rough[i] = rough[i] * (1.f - m) + m * rgh;
+  }
+}
+
+extern "C" int vqn_material_edit(vqn_ctx* ctx, const float* edit_mask, int mask_stride, const int32_t* row_idx,
+                                 const int32_t* n_dev, int64_t n, const float* diff3, const float* spec3,
+                                 const float* rough1, const float* opt_scale, float* albedo, float* spec, float* rough,
+                                 float* albedo_scaled, float* spec_scaled, vqn_stream s) {
+  VQN_CHECK_ARG(ctx && edit_mask && mask_stride >= 1 && albedo && spec && rough && n >= 0, "material_edit args");
+  if (n == 0 || (!diff3 && !spec3 && !rough1)) return VQN_OK;
+  const float3 d = diff3 ? make_float3(diff3[0], diff3[1], diff3[2]) : make_float3(0.f, 0.f, 0.f);
+  const float3 sp = spec3 ? make_float3(spec3[0], spec3[1], spec3[2]) : make_float3(0.f, 0.f, 0.f);
+  long long want = (n + 255) / 256;
+  int blocks = (int)(want < (long long)ctx->sm_count * 8 ? want : (long long)ctx->sm_count * 8);
+  material_edit_kernel<<<blocks, 256, 0, vqn_cs(s)>>>(edit_mask, mask_stride, row_idx, n_dev, n, d, diff3 != nullptr, sp,
+                                                      spec3 != nullptr, rough1 ? rough1[0] : 0.f, rough1 != nullptr,
+                                                      opt_scale, albedo, spec, rough, albedo_scaled, spec_scaled);
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}

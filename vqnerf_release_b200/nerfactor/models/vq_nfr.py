@@ -310,8 +310,6 @@ class Model:
         stored into every rank's image buffer from inside the shading kernel (fused gather); call
         `peer_image.barrier()` afterwards."""
         self._validate_mode(mode)
-        if edit_mask is not None:
-            raise NotImplementedError('material editing (edit.py) is outside the hot path (SURVEY 2.1)')
         id_, hw, rayo, rayd, rgb, alpha, pred_alpha, xyz, normal, lvis = self._unpack(batch, ref_batch)
         n_total = alpha.shape[0]
         dev = xyz.device
@@ -338,6 +336,8 @@ class Model:
         if (opt_scale is not None) and (not vis_scale):
             scale_t = torch.as_tensor(np.asarray(opt_scale), dtype=torch.float32).reshape(-1).to(dev)
         albedo, spec, s_albedo, s_spec = abi.material_combine(basecolor, ks, scale_t, n_dev=n_act)
+        if edit_mask is not None:                                              # :293-295, 324-330 (edit.py:219,226)
+            abi.material_edit(edit_mask, edit_material, row_idx, n_act, albedo, spec, rough, scale_t, s_albedo, s_spec)
         gamma = None if self.data_type == 'nerf' else self.gamma
         lights = self._lights(relight_probes, dst_env)
         self._mark('combine', dev)
