@@ -167,6 +167,7 @@ int vqn_vq_ema_update(vqn_ctx* ctx, const double* stats, int z_dim, int k, const
                       vqn_stream stream);
 
 /* ---- shading ---------------------------------------------------------------------------------- */
+enum { VQN_LVIS_F32 = 0, VQN_LVIS_F16 = 1, VQN_LVIS_U8 = 2 };
 typedef struct vqn_shade_args {
   /* per point, compacted rows i in [0,n); when row_idx != NULL the geometry inputs and outputs are
    * full-length arrays addressed through row_idx[i] (mask compaction/expansion, vq_nfr.py:283-291,
@@ -174,7 +175,7 @@ typedef struct vqn_shade_args {
   const float* xyz;     /* [*,3] surface points                                   */
   const float* rayo;    /* [*,3] camera locations (_calc_vdir, shape.py:112-119)  */
   const float* normal;  /* [*,3] (un-corrected; _normal_correct is fused)         */
-  const float* lvis;    /* [*,512] or NULL (non-'nerf' data, vq_nfr.py:707)       */
+  const float* lvis;    /* [*,512] or NULL (non-'nerf' data, vq_nfr.py:707); element type: lvis_format */
   const float* albedo;  /* [n,3] */
   const float* spec;    /* [n,3] (f0) */
   const float* rough;   /* [n,1] */
@@ -202,7 +203,9 @@ typedef struct vqn_shade_args {
    * The caller synchronises the ranks afterwards (a barrier on the stream).  Large un-split batches only. */
   float* peer_rgb[8];
   int32_t n_peers;
-  int32_t reserved_peers;
+  /* element type of lvis: VQN_LVIS_F32 (0, the reference's lvis.npy), VQN_LVIS_F16 or VQN_LVIS_U8 (v = q / 255) -- compact
+   * opt-in formats of the host-buffer path (the fp32 rows are 98 % of a view's H2D bytes); large un-split batches only */
+  int32_t lvis_format;
   int64_t peer_row0;
 } vqn_shade_args;
 
@@ -225,6 +228,13 @@ int vqn_render(vqn_ctx* ctx, const float* brdf, const float* l, const float* nor
 int vqn_material_combine(vqn_ctx* ctx, const float* basecolor, const float* ks, const float* opt_scale,
                          const int32_t* n_dev, int64_t n, float* albedo, float* spec, float* albedo_scaled,
                          float* spec_scaled, vqn_stream stream);
+
+/* Fused image gather, background rows: vqn_shade stores only the live rows of a shard into the peers' image buffers
+ * (vqn_shade_args.peer_rgb); this stores zeros for the shard's rows with alpha[row * alpha_stride] <= 0 at global row
+ * peer_row0 + row ([.., width] floats per row) in each of the n_peers buffers (HOST array of P2P-mapped device
+ * pointers), as scatter_nd leaves them (models/vq_nfr.py:347-370). */
+int vqn_peer_clear_background(vqn_ctx* ctx, const float* alpha, int alpha_stride, int64_t n_local, int64_t peer_row0,
+                              int width, float* const* peer_ptrs, int n_peers, vqn_stream stream);
 
 /* fast_render(edit_mask=, edit_material=) (models/vq_nfr.py:258-260 `_update_material`, :293-295, :324-330): compact rows
  * whose edit_mask[row_idx[i] * mask_stride] > 0 get albedo := diff3, spec := spec3, rough := rough1 (HOST pointers; NULL =

@@ -351,7 +351,7 @@ def _l2_normalize(x, axis=None, epsilon=1e-12):
 
 
 linalg.l2_normalize = _l2_normalize
-linalg.norm = lambda x, axis=None: _torch.linalg.vector_norm(x, dim=axis)
+linalg.norm = lambda x, axis=None: _torch.linalg.vector_norm(x if isinstance(x, _torch.Tensor) else _torch.as_tensor(_np.asarray(x)), dim=axis)
 nn = _types.ModuleType('tensorflow.nn')
 nn.embedding_lookup = lambda params, ids: params[ids]
 nn.l2_normalize = _l2_normalize

@@ -64,6 +64,7 @@ def main():
     assert torch.equal(img1, img2), 'sharded render + all-gather differs from the single-device image'
     # fused gather: the shading kernel stores its rows into every rank's symmetric-memory image (P2P over NVLink)
     peer = vdist.PeerImage(n, (3, 3), dev)
+    peer.begin_frame()
     pred_p = m2.fast_render(batch_tuple(batch, dev, lo, hi), mode='test', relight_probes=True, peer_image=peer)[0]
     peer.barrier()
     torch.cuda.synchronize()
@@ -74,18 +75,53 @@ def main():
     assert torch.allclose(peer.tensor[:, 1:, :], ref_all, rtol=5e-5, atol=2e-6), 'fused P2P gather differs from the single-device image'
     assert torch.equal(pred_p['rgb_probes'], peer.tensor[lo:hi, 1:, :]), 'local rows differ from the rows stored into the image'
     print('rank %d: fused P2P gather OK (max |diff| vs single device %.2e)' % (rank, (peer.tensor[:, 1:, :] - ref_all).abs().max().item()), flush=True)
+    img_full = peer.tensor.clone()
     # gather semantics: only rank 0's buffer receives the rows
     peer0 = vdist.PeerImage(n, (3, 3), dev, dst=0)
-    peer0.tensor.zero_()
-    dist.barrier()
+    peer0.begin_frame()
     m2.fast_render(batch_tuple(batch, dev, lo, hi), mode='test', relight_probes=True, peer_image=peer0)
     peer0.barrier()
     torch.cuda.synchronize()
     if rank == 0:
-        assert torch.equal(peer0.tensor, peer.tensor), 'gather-to-rank-0 image differs from the all-gather image'
+        assert torch.equal(peer0.tensor, img_full), 'gather-to-rank-0 image differs from the all-gather image'
     else:
         assert float(peer0.tensor.abs().max()) == 0.0, 'a non-destination rank received rows'
     print('rank %d: fused gather to rank 0 OK' % rank, flush=True)
+    # frames with a CHANGING foreground mask: background rows must read zero in every frame (no stale pixels of the frame
+    # two buffers ago), and five back-to-back frames without host synchronisation must each equal the single-device image
+    rng = np.random.RandomState(11)
+    ref_frames, frames = [], []
+    for f in range(5):
+        bf = dict(batch)
+        bf['alpha'] = (rng.uniform(0, 1, size=(n, 1)) < 0.6).astype(np.float32)
+        bf['pred_alpha'] = bf['alpha']
+        m3.assume_all_foreground = False
+        ref_frames.append(m3.fast_render(batch_tuple(bf, dev, 0, n), mode='test', relight_probes=True)[0]['rgb_probes'].clone())
+        frames.append(batch_tuple(bf, dev, lo, hi))
+    m2.assume_all_foreground = False
+    got = []
+    for f in range(5):
+        peer0.begin_frame()
+        m2.fast_render(frames[f], mode='test', relight_probes=True, peer_image=peer0)
+        peer0.barrier()
+        if rank == 0:
+            got.append(peer0.tensor[:, 1:, :].clone())       # stream-ordered read of frame f before frame f+1 begins
+    torch.cuda.synchronize()
+    if rank == 0:
+        for f in range(5):
+            assert torch.allclose(got[f], ref_frames[f], rtol=5e-5, atol=2e-6), 'frame %d differs (stale background rows?)' % f
+            bgrows = (frames[f][5] <= 0) if world == 1 else None
+        print('rank 0: 5 frames with changing masks, background rows zero in every frame: OK', flush=True)
+    # the same through the captured graphs (GraphedFastRender: two graphs, one per frame buffer)
+    from vqnerf_release_b200.nerfactor.models.vq_nfr import GraphedFastRender
+    gr = GraphedFastRender(m2, frames[0], peer_image=peer0, mode='test', relight_probes=True)
+    for f in range(5):
+        pred_g, img_g = gr(frames[f])
+        if rank == 0:
+            assert torch.allclose(img_g[:, 1:, :], ref_frames[f], rtol=5e-5, atol=2e-6), 'graphed frame %d differs' % f
+    torch.cuda.synchronize()
+    print('rank %d: graph-replayed fused gather OK' % rank, flush=True)
+    m2.assume_all_foreground = True
     losses2 = []
     for it in range(2):
         roll = np.random.RandomState(it).uniform(0, 1, size=(1, k))

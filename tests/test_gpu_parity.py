@@ -507,6 +507,44 @@ def test_shade_thread_per_point_kernel(cuda_dev, n_probes, with_lvis):
     _close(big[:m], ref, 'thread-per-point vs oracle', rtol=1e-4, atol=5e-6)
 
 
+@pytest.mark.parametrize('fmt,tol_vs_f32', [('f16', 1e-4), ('u8', 5e-3)])
+def test_compact_light_visibility_formats(cuda_dev, fmt, tol_vs_f32):
+    """Opt-in float16 / uint8 `lvis` (abi.compress_lvis): the kernel must (1) equal the float64 oracle evaluated on the
+    DEQUANTISED visibility to the usual 1e-4 (same inputs -> same arithmetic) and (2) stay within the stated bound of the
+    float32-visibility result (f16: ~1e-5, inside the parity budget; u8: a few 1e-4, outside it -- documented)."""
+    from vqnerf_release_b200 import abi
+    n, n_probes = 40000, 8
+    scene = O.synth_scene(4, n_probes=n_probes, bias_scale=0.05)
+    batch = O.synth_batch(n, 4, fg_frac=0.9)
+    m = _model_from_scene(scene, cuda_dev)
+    bt = list(_batch_tuple(batch, cuda_dev))
+    ref32 = m.fast_render(tuple(bt), mode='test', relight_probes=True)[0]['rgb_probes'].clone()
+    packed = abi.compress_lvis(bt[-1], fmt)
+    assert packed.dtype == (torch.float16 if fmt == 'f16' else torch.uint8)
+    bt[-1] = packed
+    got = m.fast_render(tuple(bt), mode='test', relight_probes=True)[0]['rgb_probes']
+    deq = packed.float() if fmt == 'f16' else packed.float() / 255.0
+    b2 = dict(batch)
+    b2['lvis'] = deq.cpu().numpy()
+    sub = slice(0, 3000)                                         # the oracle materialises [N,512,3]
+    o = O.fast_render(scene, {k: v[sub] for k, v in b2.items()}, torch.float64, relight_probes=True)
+    _close(got[sub], o['rgb_probes'], 'rgb_probes (%s lvis) vs oracle on the dequantised visibility' % fmt, rtol=RTOL, atol=5e-6)
+    err = float((got - ref32).abs().max())
+    print('%s lvis: max |sRGB - sRGB(float32 lvis)| = %.2e, mean %.2e' % (fmt, err, float((got - ref32).abs().mean())))
+    assert err <= tol_vs_f32, '%s lvis: max |rgb - rgb(float32 lvis)| = %.2e' % (fmt, err)
+    # small batches and the host-buffer path take the same kernel
+    small = tuple(t[:777] if torch.is_tensor(t) else t for t in bt)
+    got_s = m.fast_render(small, mode='test', relight_probes=True)[0]['rgb_probes']
+    assert torch.allclose(got_s, got[:777], rtol=1e-6, atol=1e-7)
+    host = tuple(t.cpu().pin_memory() if torch.is_tensor(t) else t for t in bt)
+    got_h = m.fast_render_host(host, n_chunks=3, mode='test', relight_probes=True)['rgb_probes']
+    torch.cuda.synchronize()
+    assert torch.allclose(got_h.to(cuda_dev), got, rtol=1e-6, atol=1e-7)
+    # the diffuse / specular split of call(mode='vali') keeps float32 visibility: loud failure, no silent conversion
+    with pytest.raises(Exception):
+        m.call(tuple(bt), mode='vali')
+
+
 def test_shade_grazing_opposite_light(cuda_dev):
     """View nearly tangent AND a light nearly opposite to it (l ~ -v): |l + v| -> 0.  The shortcut
     |l + v|^2 = 2 + 2 l.v cancels there; the kernels must form the half vector componentwise like the reference

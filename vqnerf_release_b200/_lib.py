@@ -40,7 +40,7 @@ class ShadeArgs(C.Structure):
                 ('n_probes', C.c_int32), ('clip_light0', C.c_int32), ('to_srgb', C.c_int32), ('use_gamma', C.c_int32),
                 ('gamma_bias', C.c_float), ('gamma_index', C.c_float),
                 ('rgb', C.c_void_p), ('rgb_diff', C.c_void_p), ('rgb_spec', C.c_void_p), ('normal_out', C.c_void_p),
-                ('peer_rgb', C.c_void_p * 8), ('n_peers', C.c_int32), ('reserved_peers', C.c_int32),
+                ('peer_rgb', C.c_void_p * 8), ('n_peers', C.c_int32), ('lvis_format', C.c_int32),
                 ('peer_row0', C.c_int64)]
 
 
@@ -88,6 +88,7 @@ SIGNATURES = {
     'vqn_eval_brdf': (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P]),
     'vqn_render': (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _F, _P, _P]),
     'vqn_material_combine': (_I, [_P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P]),
+    'vqn_peer_clear_background': (_I, [_P, _P, _I, _L, _L, _I, _P, _I, _P]),
     'vqn_material_edit': (_I, [_P, _P, _I, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'vqn_linear2srgb': (_I, [_P, _P, _L, _P, _P]),
     'vqn_srgb2linear': (_I, [_P, _P, _L, _P, _P]),

@@ -247,6 +247,23 @@ def vq_ema_update(stats: torch.Tensor, codebook: torch.Tensor, decay: float, eps
     return update, loss, perp
 
 
+LVIS_FORMATS = {torch.float32: 0, torch.float16: 1, torch.uint8: 2}
+
+
+def compress_lvis(lvis: torch.Tensor, fmt: str) -> torch.Tensor:
+    """Compact light-visibility formats of the host-buffer path (explicit opt-in; the reference stores float32):
+    'f16' = IEEE half (relative error 2^-11 per light: ~1e-5 on a shaded radiance), 'u8' = round(255 v) (absolute error
+    <= 1/510 per light: ~5e-5 typical, up to ~4e-4 on a radiance dominated by a few lights).  Works on host or device
+    tensors; `Model.fast_render` / `fast_render_host` accept the result in place of the float32 tensor."""
+    if fmt in ('f32', None):
+        return lvis.to(F32)
+    if fmt == 'f16':
+        return lvis.to(torch.float16)
+    if fmt == 'u8':
+        return (lvis.to(F32).clamp(0, 1) * 255.0 + 0.5).to(torch.uint8)
+    raise ValueError("lvis format must be 'f32', 'f16' or 'u8'")
+
+
 def shade(xyz, rayo, normal, lvis, albedo, spec, rough, lxyz, lareas, lights, *, row_idx=None, n_dev=None,
           n: Optional[int] = None, n_total: Optional[int] = None, to_srgb=False, gamma=None, clip_light0=True,
           want_split=False, want_normal=False, out_rgb: Optional[torch.Tensor] = None,
@@ -267,8 +284,13 @@ def shade(xyz, rayo, normal, lvis, albedo, spec, rough, lxyz, lareas, lights, *,
     a = L.ShadeArgs()
     a.xyz, a.rayo, a.normal = xyz.data_ptr(), rayo.data_ptr(), normal.data_ptr()
     if lvis is not None:
-        lvis = _f(lvis)
+        # float32 = the reference's lvis.npy; float16 / uint8 (v = q / 255) = the compact opt-in formats (LVIS_FORMATS)
+        if lvis.dtype not in LVIS_FORMATS:
+            lvis = lvis.to(F32)
+        if not lvis.is_cuda or not lvis.is_contiguous():
+            raise ValueError('lvis must be a contiguous CUDA tensor')
         a.lvis = lvis.data_ptr()
+        a.lvis_format = LVIS_FORMATS[lvis.dtype]
     a.albedo, a.spec, a.rough = albedo.data_ptr(), spec.data_ptr(), rough.data_ptr()
     if row_idx is not None:
         a.row_idx = L.ptr(row_idx, torch.int32).value
@@ -336,6 +358,19 @@ def material_combine(basecolor, ks, opt_scale=None, n_dev=None, want_scaled=True
                                        L.ptr(n_dev, torch.int32), n, L.ptr(albedo), L.ptr(spec), L.ptr(a_s),
                                        L.ptr(s_s), L.stream_ptr(basecolor.device)))
     return albedo, spec, (a_s if a_s is not None else albedo), (s_s if s_s is not None else spec)
+
+
+def peer_clear_background(alpha, peer_ptrs, peer_row0, width):
+    """Zeros for the background rows of this rank's shard in the peers' image buffers (fused gather, dist.PeerImage)."""
+    import ctypes as C
+    alpha = _f(alpha)
+    if alpha.dim() == 1:
+        alpha = alpha[:, None]
+    arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+    c = _ctx(alpha)
+    L.check(c.lib.vqn_peer_clear_background(c.handle, L.ptr(alpha), alpha.shape[1], alpha.shape[0], int(peer_row0),
+                                            int(width), C.cast(arr, C.c_void_p), len(peer_ptrs),
+                                            L.stream_ptr(alpha.device)))
 
 
 def material_edit(edit_mask, edit_material, row_idx, n_dev, albedo, spec, rough, opt_scale=None, albedo_s=None,

@@ -37,24 +37,39 @@ extern "C" const char* vqn_status_str(int s) {
 
 namespace {
 struct ScratchEntry { int kind; cudaStream_t stream; void* ptr; size_t bytes; };
-struct ScratchPool { std::mutex mu; std::vector<ScratchEntry> entries; };
+// `retired`: blocks replaced by a larger one.  They are NOT freed before the context is destroyed: a captured CUDA graph
+// may have their address baked into its kernel nodes, and a replay after a free would be a use-after-free.
+struct ScratchPool { std::mutex mu; std::vector<ScratchEntry> entries; std::vector<void*> retired; };
+
+// cudaMalloc is not allowed while the calling thread captures a stream (thread-local / global capture modes): the first
+// use of a scratch kind on a stream must happen in the warm-up run on that SAME stream (torch.cuda.graph(stream=...)).
+bool stream_is_capturing(cudaStream_t stream) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess) { cudaGetLastError(); return false; }
+  return st != cudaStreamCaptureStatusNone;
+}
 }  // namespace
 
 void* vqn_stream_scratch(vqn_ctx* ctx, int kind, cudaStream_t stream, size_t bytes) {
   ScratchPool* pool = static_cast<ScratchPool*>(ctx->pool);
   std::lock_guard<std::mutex> lock(pool->mu);
+  ScratchEntry* hit = nullptr;
   for (ScratchEntry& e : pool->entries)
-    if (e.kind == kind && e.stream == stream) {
-      if (e.bytes >= bytes) return e.ptr;
-      cudaFree(e.ptr);                                   // grow (cudaFree synchronises: no kernel still uses it)
-      e.ptr = nullptr; e.bytes = 0;
-      if (cudaMalloc(&e.ptr, bytes) != cudaSuccess) { vqn_set_error("scratch allocation of %zu bytes failed", bytes); return nullptr; }
-      e.bytes = bytes;
-      return e.ptr;
-    }
+    if (e.kind == kind && e.stream == stream) { hit = &e; break; }
+  if (hit && hit->bytes >= bytes) return hit->ptr;
+  if (stream_is_capturing(stream)) {
+    vqn_set_error("work buffer %d (%zu bytes) would have to be allocated during stream capture: run the call once on "
+                  "this stream before capturing it", kind, bytes);
+    return nullptr;
+  }
   void* p = nullptr;
   if (cudaMalloc(&p, bytes) != cudaSuccess) { vqn_set_error("scratch allocation of %zu bytes failed", bytes); return nullptr; }
-  pool->entries.push_back({kind, stream, p, bytes});
+  if (hit) {
+    pool->retired.push_back(hit->ptr);                   // grown: the old block stays alive (see ScratchPool)
+    hit->ptr = p; hit->bytes = bytes;
+  } else {
+    pool->entries.push_back({kind, stream, p, bytes});
+  }
   return p;
 }
 
@@ -98,6 +113,7 @@ extern "C" int vqn_ctx_destroy(vqn_ctx* ctx) {
   if (ctx->pool) {
     ScratchPool* pool = static_cast<ScratchPool*>(ctx->pool);
     for (ScratchEntry& e : pool->entries) cudaFree(e.ptr);
+    for (void* r : pool->retired) cudaFree(r);
     delete pool;
   }
   delete ctx;

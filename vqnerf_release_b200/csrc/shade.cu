@@ -15,6 +15,7 @@
 // and keeps it in registers (48 per lane).  Phase 2 is then 3 FFMA per (light, probe):
 //     rgb[p][ch] += e_ch * L[p][l][ch]
 // followed by a halving-butterfly reduction of the 3 values per probe across the warp.  Algorithmic HBM bytes per point: 2048 (lvis) + 36 + 28 + 12 (1 + P).
+struct vqn_peer_ptrs { float* p[8]; int n; };
 #include "common.cuh"
 
 #define SH_L 512
@@ -303,8 +304,11 @@ extern "C" int vqn_shade(vqn_ctx* ctx, const vqn_shade_args* args, vqn_stream st
   // large un-split batches: thread-per-point kernel with the light tables in the constant bank (shade_pt.cu);
   // small batches (training, 8192 rays) keep the warp-per-point kernel, which exposes 32x more parallelism
   VQN_CHECK_ARG(a.n_peers >= 0 && a.n_peers <= 8, "shade: 0 <= n_peers <= 8");
-  if (!split && a.n_probes <= 9 && (a.n >= 32768 || a.n_peers > 0)) return vqn_shade_pt_launch(ctx, a, vqn_cs(stream));
+  VQN_CHECK_ARG(a.lvis_format >= VQN_LVIS_F32 && a.lvis_format <= VQN_LVIS_U8, "shade: unknown lvis_format");
+  const bool compact_lvis = a.lvis && a.lvis_format != VQN_LVIS_F32;
+  if (!split && a.n_probes <= 9 && (a.n >= 32768 || a.n_peers > 0 || compact_lvis)) return vqn_shade_pt_launch(ctx, a, vqn_cs(stream));
   VQN_CHECK_ARG(a.n_peers == 0, "shade: the fused peer gather needs an un-split batch with at most 9 probes");
+  if (compact_lvis) { vqn_set_error("shade: float16 / uint8 light visibility needs an un-split batch with at most 9 probes"); return VQN_ERR_UNSUPPORTED; }
   auto kern = a.lvis ? (split ? shade_kernel<true, true> : shade_kernel<true, false>)
                      : (split ? shade_kernel<false, true> : shade_kernel<false, false>);
   VQN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -421,6 +425,36 @@ extern "C" int vqn_render(vqn_ctx* ctx, const float* brdf, const float* l, const
   int blocks = (int)(want < (long long)ctx->sm_count * 8 ? want : (long long)ctx->sm_count * 8);
   render_kernel<<<blocks, 256, 0, vqn_cs(stream)>>>(brdf, l, normal, lvis, lareas, light, n, use_gamma,
                                                     gamma_bias, gamma_index, rgb, ctx->nonfinite_flag);
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}
+
+// Background rows of a fused image gather.  shade_pt_kernel stores only the live (alpha > 0) rows of a shard into the
+// peers' image buffers; this writes zeros for the shard's OTHER rows (models/vq_nfr.py:347-370: scatter_nd leaves zeros
+// at background rows), so that a gathered frame never shows pixels of the previous one.  Traffic: dead rows only.
+__global__ void peer_clear_background_kernel(const float* __restrict__ alpha, int alpha_stride, long long n_local,
+                                             long long peer_row0, int width, vqn_peer_ptrs pp) {
+  const long long total = n_local * width;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / width;
+    if (alpha[row * alpha_stride] > 0.f) continue;
+    const long long off = (peer_row0 + row) * width + (i - row * width);
+    for (int q = 0; q < pp.n; ++q) pp.p[q][off] = 0.f;
+  }
+}
+
+extern "C" int vqn_peer_clear_background(vqn_ctx* ctx, const float* alpha, int alpha_stride, int64_t n_local,
+                                         int64_t peer_row0, int width, float* const* peer_ptrs, int n_peers,
+                                         vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && alpha && alpha_stride >= 1 && n_local >= 0 && width >= 1, "peer_clear_background args");
+  VQN_CHECK_ARG(peer_ptrs && n_peers >= 1 && n_peers <= 8, "peer_clear_background: 1 <= n_peers <= 8");
+  if (n_local == 0) return VQN_OK;
+  vqn_peer_ptrs pp;
+  pp.n = n_peers;
+  for (int q = 0; q < 8; ++q) pp.p[q] = q < n_peers ? peer_ptrs[q] : nullptr;
+  const long long want = (n_local * width + 255) / 256;
+  const int blocks = (int)(want < (long long)ctx->sm_count * 8 ? want : (long long)ctx->sm_count * 8);
+  peer_clear_background_kernel<<<blocks, 256, 0, vqn_cs(stream)>>>(alpha, alpha_stride, n_local, peer_row0, width, pp);
   VQN_LAUNCHED(ctx);
   return VQN_OK;
 }

@@ -19,6 +19,7 @@
 // accumulation (27 -> 14 per light for 9 probes); the per-light factor is (e0, e1) or (e2, e2); an LDS.128 delivers
 // two radiance pairs already in aligned 64-bit registers.  One persistent
 // 512-thread block per SM copies the image into shared memory once and walks 32-point tiles, warp-strided.
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 #define SP_L 512
@@ -72,7 +73,9 @@ __global__ void shade_pt_prep_kernel(const float* __restrict__ lxyz, const float
   img[i] = make_float4(v[0], v[1], v[2], v[3]);
 }
 
-template <int NPC, bool HAS_LVIS>
+// LV: light-visibility format -- 0 none, 1 float32 (the reference's lvis.npy), 2 float16, 3 uint8 (v = q / 255): the
+// compact formats are an opt-in of the host-buffer path (the fp32 rows are 98 % of a view's H2D bytes)
+template <int NPC, int LV>
 __global__ void __launch_bounds__(SP_THREADS, 1) shade_pt_kernel(vqn_shade_args a, const float4* __restrict__ img,
                                                                  int* nonfinite) {
   extern __shared__ __align__(16) float4 s_img[];
@@ -120,14 +123,34 @@ __global__ void __launch_bounds__(SP_THREADS, 1) shade_pt_kernel(vqn_shade_args 
   u64 acc[NPAIR];                                               // (out[2m], out[2m+1]) pairs, fp32 x 2
 #pragma unroll
   for (int m = 0; m < NPAIR; ++m) acc[m] = 0ull;
-  const float4* lv = reinterpret_cast<const float4*>(a.lvis + (HAS_LVIS ? row * SP_L : 0));
+  constexpr bool HAS_LVIS = LV != 0;
+  // one group = 4 lights = 16 / 8 / 4 bytes of the point's visibility row
+  const unsigned char* lvb = reinterpret_cast<const unsigned char*>(a.lvis) +
+                             (HAS_LVIS ? (size_t)row * SP_L * (LV == 1 ? 4 : LV == 2 ? 2 : 1) : 0);
+  auto lv_load = [&](int g) -> float4 {
+    if (LV == 1) return __ldg(reinterpret_cast<const float4*>(lvb) + g);
+    if (LV == 2) {
+      const uint2 raw = __ldg(reinterpret_cast<const uint2*>(lvb) + g);
+      const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+      const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+      return make_float4(lo.x, lo.y, hi.x, hi.y);
+    }
+    // uint8: byte b -> the float 2^23 + b by a byte permute into the mantissa; the subtraction of 2^23 is exact, then one
+    // multiply (an FMA with the pre-scaled offset -2^23/255 would round that offset to 0.002 -- half a quantisation step)
+    const unsigned raw = __ldg(reinterpret_cast<const unsigned*>(lvb) + g);
+    const float k = 1.0f / 255.0f, o = 8388608.0f;
+    return make_float4((__uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7650)) - o) * k,
+                       (__uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7651)) - o) * k,
+                       (__uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7652)) - o) * k,
+                       (__uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7653)) - o) * k);
+  };
   float4 lv_cur = make_float4(1.f, 1.f, 1.f, 1.f);
-  if (HAS_LVIS) lv_cur = __ldg(lv);
+  if (HAS_LVIS) lv_cur = lv_load(0);
 
 #pragma unroll 1
   for (int grp = 0; grp < SP_GROUPS; ++grp) {
     float4 lv_nxt = lv_cur;
-    if (HAS_LVIS && grp + 1 < SP_GROUPS) lv_nxt = __ldg(lv + grp + 1);
+    if (HAS_LVIS && grp + 1 < SP_GROUPS) lv_nxt = lv_load(grp + 1);
     const float4* cg = s_img + grp * PER_GROUP;                // warp-uniform address: broadcast reads
     const float4 X = cg[0], Y = cg[1], Z = cg[2];
     const float xs4[4] = {X.x, X.y, X.z, X.w}, ys4[4] = {Y.x, Y.y, Y.z, Y.w}, zs4[4] = {Z.x, Z.y, Z.z, Z.w};
@@ -223,13 +246,17 @@ int launch_pt(vqn_ctx* ctx, const vqn_shade_args& a, const float4* img, cudaStre
   const size_t smem = sizeof(float4) * SP_GROUPS * SP_F4_PER_GROUP(NPC) + sizeof(float) * (SP_THREADS / 32) * 32 * (3 * NPC + 1);
   long long want = (a.n + SP_THREADS - 1) / SP_THREADS;
   const unsigned blocks = (unsigned)(want < (long long)ctx->sm_count ? want : (long long)ctx->sm_count);
-  if (a.lvis) {
-    VQN_CUDA(cudaFuncSetAttribute(shade_pt_kernel<NPC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    shade_pt_kernel<NPC, true><<<blocks, SP_THREADS, smem, s>>>(a, img, ctx->nonfinite_flag);
-  } else {
-    VQN_CUDA(cudaFuncSetAttribute(shade_pt_kernel<NPC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    shade_pt_kernel<NPC, false><<<blocks, SP_THREADS, smem, s>>>(a, img, ctx->nonfinite_flag);
-  }
+  const int lv = !a.lvis ? 0 : a.lvis_format == VQN_LVIS_F16 ? 2 : a.lvis_format == VQN_LVIS_U8 ? 3 : 1;
+#define SP_LAUNCH(LVV)                                                                                                  \
+  do {                                                                                                                  \
+    VQN_CUDA(cudaFuncSetAttribute(shade_pt_kernel<NPC, LVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+    shade_pt_kernel<NPC, LVV><<<blocks, SP_THREADS, smem, s>>>(a, img, ctx->nonfinite_flag);                           \
+  } while (0)
+  if (lv == 0) SP_LAUNCH(0);
+  else if (lv == 1) SP_LAUNCH(1);
+  else if (lv == 2) SP_LAUNCH(2);
+  else SP_LAUNCH(3);
+#undef SP_LAUNCH
   VQN_LAUNCHED(ctx);
   return VQN_OK;
 }

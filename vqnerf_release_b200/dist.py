@@ -86,11 +86,22 @@ def make_stats_allreduce(group=None):
 
 
 class PeerImage:
-    """Fused gather of a pixel-sharded render: every rank owns an image buffer [n_total, c...] in torch symmetric
-    memory (P2P-mapped over NVLink / NVSwitch); the shading kernel of rank r stores its rows straight into ALL
+    """Fused gather of a pixel-sharded render: every rank owns image buffers [n_total, c...] in torch symmetric memory
+    (P2P-mapped over NVLink / NVSwitch); the shading kernel of rank r stores its rows straight into the destination
     ranks' buffers (vqn_shade_args.peer_rgb), so the "single gather" of SURVEY 8e overlaps the light integral tile by
-    tile instead of running as a separate NCCL collective.  `barrier()` (device-side, on the current stream) makes the
-    peers' rows visible; afterwards `tensor` holds the complete image on every rank."""
+    tile instead of running as a separate NCCL collective.
+
+    Frame protocol (every rank, on its current stream, per frame):
+
+        img.begin_frame()                      # flips to the other of TWO buffers
+        model.fast_render(..., peer_image=img) # live rows -> peers' buffers; background rows of the shard -> zeros
+        img.barrier()                          # device-side: all peers' stores have landed
+        ... img.tensor is the complete frame on the destination rank(s) until the frame after next begins ...
+
+    Two buffers + one barrier per frame are enough: a peer starts writing frame t+2 into the buffer of frame t only
+    after it passed barrier(t+1), which the destination joined -- in stream order -- after its reads of frame t.
+    Background (alpha <= 0) rows are written as zeros by their owner (vqn_peer_clear_background), as the reference's
+    scatter_nd leaves them, so a frame never shows pixels of an earlier one; both buffers start zero-filled."""
 
     def __init__(self, n_total: int, tail, device, group=None, dst: Optional[int] = None):
         """dst=None: every rank ends up with the full image (all-gather semantics, world x the NVLink traffic);
@@ -101,14 +112,47 @@ class PeerImage:
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         self.n_total = int(n_total)
-        self.tensor = symm_mem.empty((self.n_total,) + tuple(tail), dtype=torch.float32, device=device)
-        self.handle = symm_mem.rendezvous(self.tensor, self.group)
-        ptrs = [int(p) for p in self.handle.buffer_ptrs]
-        if len(ptrs) != self.world:
-            raise RuntimeError('symmetric memory rendezvous returned %d peers for world %d' % (len(ptrs), self.world))
+        self.tail = tuple(tail)
+        self.width = 1
+        for t in self.tail:
+            self.width *= int(t)
         self.dst = dst
-        self.peer_ptrs = ptrs if dst is None else [ptrs[int(dst)]]
-        self.row0 = shard_rows(self.n_total, self.rank, self.world)[0]
+        self._bufs, self._handles, self._ptrs = [], [], []
+        for _ in range(2):
+            t = symm_mem.empty((self.n_total,) + self.tail, dtype=torch.float32, device=device)
+            t.zero_()
+            h = symm_mem.rendezvous(t, self.group)
+            ptrs = [int(p) for p in h.buffer_ptrs]
+            if len(ptrs) != self.world:
+                raise RuntimeError('symmetric memory rendezvous returned %d peers for world %d' % (len(ptrs), self.world))
+            self._bufs.append(t); self._handles.append(h)
+            self._ptrs.append(ptrs if dst is None else [ptrs[int(dst)]])
+        self.row0, self.row1 = shard_rows(self.n_total, self.rank, self.world)
+        self._frame = 0
+        torch.cuda.synchronize(device)
+        self._handles[0].barrier()                       # every rank's zero-fill is done before anyone stores
+
+    # -- current frame
+    @property
+    def tensor(self) -> torch.Tensor:
+        return self._bufs[self._frame & 1]
+
+    @property
+    def handle(self):
+        return self._handles[self._frame & 1]
+
+    @property
+    def peer_ptrs(self):
+        return self._ptrs[self._frame & 1]
+
+    def begin_frame(self) -> None:
+        self._frame += 1
+
+    def clear_background(self, alpha_local: torch.Tensor, row_off: int = 0) -> None:
+        """Zeros for this shard's background rows in the destination buffers (called by fast_render; `row_off` = first
+        row of `alpha_local` inside the shard, for chunked calls)."""
+        from . import abi
+        abi.peer_clear_background(alpha_local, self.peer_ptrs, self.row0 + int(row_off), self.width)
 
     def barrier(self) -> None:
         self.handle.barrier()

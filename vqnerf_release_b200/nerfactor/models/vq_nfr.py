@@ -305,10 +305,11 @@ class Model:
     # ------------------------------------------------------------------ fast_render (vq_nfr.py:262-398)
     def fast_render(self, batch, mode='train', relight_olat=False, relight_probes=False, opt_scale=None,
                     edit_mask=None, edit_material=None, ref_batch=False, dst_env=None, gen_embed=False, thres=None,
-                    vis_scale=False, roll=None, peer_image=None):
+                    vis_scale=False, roll=None, peer_image=None, _peer_row_off=0):
         """`peer_image` (vqnerf_release_b200.dist.PeerImage, multi-GPU only): the shaded rows [.., 1+P, 3] are also
-        stored into every rank's image buffer from inside the shading kernel (fused gather); call
-        `peer_image.barrier()` afterwards."""
+        stored into the destination ranks' image buffers from inside the shading kernel (fused gather) and the shard's
+        background rows are zero-filled there; frame protocol: `peer_image.begin_frame()` before, `peer_image.barrier()`
+        after (see dist.PeerImage)."""
         self._validate_mode(mode)
         id_, hw, rayo, rayd, rgb, alpha, pred_alpha, xyz, normal, lvis = self._unpack(batch, ref_batch)
         n_total = alpha.shape[0]
@@ -346,7 +347,9 @@ class Model:
                        n_total=n_total, to_srgb=(self.data_type == 'nerf'), gamma=gamma,
                        clip_light0=(dst_env is None),
                        peer_ptrs=None if peer_image is None else peer_image.peer_ptrs,
-                       peer_row0=0 if peer_image is None else peer_image.row0)
+                       peer_row0=0 if peer_image is None else peer_image.row0 + _peer_row_off)
+        if peer_image is not None:
+            peer_image.clear_background(alpha, _peer_row_off)
         self._mark('shade', dev)
         self._check_numerics(dev)
         loss_kwargs = {'mode': mode, 'gtc': rgb}
@@ -411,7 +414,8 @@ class Model:
                     sub.append(dummy3)
                 if self.data_type == 'nerf':
                     sub.append(d_lvis)
-                pred, _, _, _ = self.fast_render(tuple(sub), **kw)
+                pred, _, _, _ = self.fast_render(tuple(sub), _peer_row_off=a, **kw) if kw.get('peer_image') is not None \
+                    else self.fast_render(tuple(sub), **kw)
                 for k, v in pred.items():
                     if k == 'alpha' or not torch.is_tensor(v):
                         continue
@@ -543,3 +547,56 @@ class Model:
         return pred, gt, loss_kwargs, to_vis
 
     __call__ = call
+
+
+class GraphedFastRender:
+    """`Model.fast_render` (+ the device-side barrier of a fused multi-GPU gather) captured ONCE into a CUDA graph and
+    replayed.  A pixel shard of a view at 8 GPUs is ~0.6 ms of kernels: launched one by one from Python the ~15 launches
+    of a call cost more than they run; as one graph launch the step is GPU-bound again.  Inputs are copied into static
+    buffers (or updated in place by the caller through `static`); the returned dict holds the same static output
+    tensors on every call.  With `peer_image`, TWO graphs are captured (one per frame buffer of dist.PeerImage) and
+    replayed alternately."""
+
+    def __init__(self, model: Model, example_batch, peer_image=None, **kw):
+        self.model, self.peer_image = model, peer_image
+        dev = model.device
+        self.static = tuple(t.clone() if torch.is_tensor(t) else t for t in example_batch)
+        self.kw = kw
+        self.stream = torch.cuda.Stream(device=dev)
+        self.stream.wait_stream(torch.cuda.current_stream(dev))
+        n_graphs = 2 if peer_image is not None else 1
+        with torch.cuda.stream(self.stream):              # warm-up on the capture stream: the library's per-stream work
+            for _ in range(2 * n_graphs):                 # buffers must exist before the capture (no cudaMalloc inside)
+                self._run()
+        torch.cuda.current_stream(dev).wait_stream(self.stream)
+        torch.cuda.synchronize(dev)
+        self.graphs, self.outs = [], []
+        for _ in range(n_graphs):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.stream, capture_error_mode='thread_local'):
+                out = self._run()
+            self.graphs.append(g)
+            self.outs.append(out)
+        self._i = 0
+
+    def _run(self):
+        if self.peer_image is not None:
+            self.peer_image.begin_frame()
+        pred, gt, lk, vis = self.model.fast_render(self.static, peer_image=self.peer_image, **self.kw)
+        img = None
+        if self.peer_image is not None:
+            self.peer_image.barrier()
+            img = self.peer_image.tensor
+        return pred, img
+
+    def __call__(self, batch=None):
+        """Returns (pred, gathered_image_or_None).  `batch`: tensors to copy into the static inputs (None: the caller
+        has already updated `self.static` in place)."""
+        if batch is not None:
+            for dst, src in zip(self.static, batch):
+                if torch.is_tensor(dst) and src is not dst:
+                    dst.copy_(src, non_blocking=True)
+        i = self._i
+        self._i = (i + 1) % len(self.graphs)
+        self.graphs[i].replay()
+        return self.outs[i]
