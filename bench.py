@@ -752,7 +752,7 @@ def run_ours(args):
             'other_ms': {k: v for k, v in stage_ms.items() if k not in ('mlp_main', 'shade')},
         }
         cb = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only
             cb, _, _ = cpu_baseline(P)
         line = {
             'metric': 'shaded surface points/sec', 'value': value, 'unit': 'points/s', 'n_gpus': world,

@@ -508,6 +508,116 @@ def call_forward(scene: Scene, batch: Dict[str, np.ndarray], vq: VectorQuantizer
 
 
 # ----------------------------------------------------------------------------
+# ref_nfr.Model (models/ref_nfr.py): the residual model test.py renders before the VQ model
+# ----------------------------------------------------------------------------
+def make_ref_nfr_nets(seed: int = 0, bias_scale: float = 0.0) -> Dict[str, Net]:
+    """models/ref_nfr.py:137-160: fine_enc / bottleneck / spec_out come from the VQ-stage model (:141-146),
+    rgb_enc = [z, z, z] (none, relu, sigmoid) on the 3-d reference RGB (:148), diff_out / rough_out = [z, z/2, out]
+    with skip_at=[1] on the 512-d concat [z_xyz, z_ref] (:149-152)."""
+    base = make_vq_nfr_nets(seed, bias_scale)
+    rng = np.random.RandomState(seed + 77)
+    R, S, N_ = ACT_RELU, ACT_SIGMOID, ACT_NONE
+    nets = {'fine_enc': base['fine_enc'], 'bottleneck': base['bottleneck'], 'spec_out': base['spec_main']}
+    nets['rgb_enc'] = make_net(rng, 3, [Z_DIM, Z_DIM, Z_DIM], [N_, R, S], bias_scale=bias_scale)
+    nets['diff_out'] = make_net(rng, 2 * Z_DIM, [Z_DIM, Z_DIM // 2, 3], [R, R, S], skip_at=1, bias_scale=bias_scale)
+    nets['rough_out'] = make_net(rng, 2 * Z_DIM, [Z_DIM, Z_DIM // 2, 1], [R, R, S], skip_at=1, bias_scale=bias_scale)
+    return nets
+
+
+def _ref_materials(scene: Scene, xyz, ref):
+    """ref_nfr.py:196-208: z_xyz -> ks; z_bias = concat(z_xyz, rgb_enc(ref)) -> basecolor, rough."""
+    nets = scene.nets
+    z_xyz = nets['bottleneck'](nets['fine_enc'](embed(xyz)))
+    ks = nets['spec_out'](z_xyz)
+    z_bias = torch.cat([z_xyz, nets['rgb_enc'](ref)], dim=-1)
+    basecolor = scene.albedo_slope * nets['diff_out'](z_bias) + scene.albedo_bias
+    rough = nets['rough_out'](z_bias)
+    return ks, basecolor, rough, ks * basecolor, (1 - ks) * basecolor
+
+
+def ref_fast_render(scene: Scene, batch: Dict[str, np.ndarray], dtype=torch.float64, relight_probes: bool = False,
+                    opt_scale=None, edit_mask=None, edit_material=None) -> Dict[str, torch.Tensor]:
+    """models/ref_nfr.py:306-417: rgb = the RAW BRDF under the model light; rgb_probes = the opt_scale'd BRDF under the
+    novel probes; batch['ref'] = the reference RGB."""
+    dt = dtype
+    alpha = _t(batch['alpha'], dt)
+    mask = alpha[:, 0] > 0
+    rayo, xyz, normal, ref = (_t(batch[k], dt)[mask] for k in ('rayo', 'xyz', 'normal', 'ref'))
+    lvis = _t(batch['lvis'], dt)[mask] if batch.get('lvis') is not None else None
+    lxyz, lareas = _t(scene.lxyz, torch.float32).to(dt), _t(scene.lareas, torch.float32).to(dt)
+    surf2l, surf2c = calc_ldir(lxyz, xyz), calc_vdir(rayo, xyz)
+    normal_pred = normal_correct(normal, surf2c)
+    ks, basecolor, rough, spec, albedo = _ref_materials(scene, xyz, ref)
+    if edit_mask is not None:
+        em = (_t(edit_mask, dt)[mask][..., 0:1] > 0).to(dt)
+        upd = lambda src, u: src * (1.0 - em) + em * _t(np.asarray([u], np.float32), dt)
+        if not edit_material['diff'][0] < 0:
+            albedo = upd(albedo, edit_material['diff'])
+        if not edit_material['spec'][0] < 0:
+            spec = upd(spec, edit_material['spec'])
+        if not edit_material['rough'][0] < 0:
+            rough = upd(rough, edit_material['rough'])
+    raw_brdf, _, _ = get_brdf(surf2l, surf2c, normal_pred, albedo, rough, spec)
+    if opt_scale is not None:
+        s = _t(opt_scale, dt)
+        albedo, spec = albedo * s, spec * s
+    brdf, _, _ = get_brdf(surf2l, surf2c, normal_pred, albedo, rough, spec)
+    light = _t(scene.light, dt)                       # ref_nfr.py:88,424: np_light.npy as loaded, not clipped
+    gamma = None if scene.data_type == 'nerf' else scene.gamma
+    rgb_pred, _ = render(raw_brdf, surf2l, normal_pred, lareas, light, lvis, None, gamma)
+    n = alpha.shape[0]
+
+    def scatter(v):
+        full = torch.zeros((n,) + tuple(v.shape[1:]), dtype=v.dtype)
+        full[mask] = v
+        return full
+    to_s = linear2srgb if scene.data_type == 'nerf' else (lambda v: v)
+    out = {'rgb': scatter(to_s(rgb_pred))}
+    if relight_probes and scene.probes is not None:
+        _, rgb_probes = render(brdf, surf2l, normal_pred, lareas, light, lvis, _t(scene.probes, dt), gamma)
+        out['rgb_probes'] = scatter(to_s(rgb_probes))
+    return out
+
+
+def ref_call(scene: Scene, batch: Dict[str, np.ndarray], mode: str = 'vali', dtype=torch.float64,
+             relight_probes: bool = False, opt_scale=None) -> Dict[str, torch.Tensor]:
+    """models/ref_nfr.py:176-300 forward: full-length pred dict entries."""
+    dt = dtype
+    alpha = _t(batch['alpha'], dt)
+    mask = alpha[:, 0] > 0
+    rayo, xyz, normal, ref = (_t(batch[k], dt)[mask] for k in ('rayo', 'xyz', 'normal', 'ref'))
+    lvis = _t(batch['lvis'], dt)[mask] if batch.get('lvis') is not None else None
+    lxyz, lareas = _t(scene.lxyz, torch.float32).to(dt), _t(scene.lareas, torch.float32).to(dt)
+    surf2l, surf2c = calc_ldir(lxyz, xyz), calc_vdir(rayo, xyz)
+    normal_pred = normal_correct(normal, surf2c)
+    ks, basecolor, rough, spec, albedo = _ref_materials(scene, xyz, ref)
+    if opt_scale is not None and mode == 'test':
+        s = _t(opt_scale, dt)
+        albedo, spec = albedo * s, spec * s
+    brdf, brdf_spec, brdf_diff = get_brdf(surf2l, surf2c, normal_pred, albedo, rough, spec)
+    light = _t(scene.light, dt)                       # ref_nfr.py:88,424: np_light.npy as loaded, not clipped
+    gamma = None if scene.data_type == 'nerf' else scene.gamma
+    probes = _t(scene.probes, dt) if (relight_probes and scene.probes is not None) else None
+    rgb_pred, rgb_probes = render(brdf, surf2l, normal_pred, lareas, light, lvis, probes, gamma)
+    n = alpha.shape[0]
+
+    def scatter(v):
+        full = torch.zeros((n,) + tuple(v.shape[1:]), dtype=v.dtype)
+        full[mask] = v
+        return full
+    to_s = linear2srgb if scene.data_type == 'nerf' else (lambda v: v)
+    out = {'rgb': scatter(to_s(rgb_pred)), 'normal': scatter(normal_pred), 'albedo': scatter(albedo),
+           'spec': scatter(spec), 'rough': scatter(rough), 'ks': scatter(ks), 'basecolor': scatter(basecolor),
+           '_rgb_linear': rgb_pred}
+    if mode != 'train':
+        out['rgb_diff'] = scatter(render(brdf_diff, surf2l, normal_pred, lareas, light, lvis, None, gamma)[0])
+        out['rgb_spec'] = scatter(render(brdf_spec, surf2l, normal_pred, lareas, light, lvis, None, gamma)[0])
+    if rgb_probes is not None:
+        out['rgb_probes'] = scatter(to_s(rgb_probes))
+    return out
+
+
+# ----------------------------------------------------------------------------
 # training step: compute_loss (models/vq_nfr.py:876-986) + train_iter (train_nfr.py:562-576)
 # ----------------------------------------------------------------------------
 @dataclass

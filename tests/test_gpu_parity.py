@@ -545,6 +545,43 @@ def test_compact_light_visibility_formats(cuda_dev, fmt, tol_vs_f32):
         m.call(tuple(bt), mode='vali')
 
 
+@pytest.mark.parametrize('rem_tiles', [100, 200, 400, 900, 1500])
+def test_shade_split_last_round_equals_whole_tiles(cuda_dev, rem_tiles):
+    """The partial last round of the thread-per-point kernel is cut into S = 16 / 8 / 4 / 2 / 1 light ranges per tile (here:
+    100 / 200 / 400 / 900 / 1500 remainder tiles on 148 x 16 warps); the S partial sums are added in a fixed order.  The
+    same rows shaded as WHOLE tiles (a batch of exactly 148 x 16 tiles that ends with them) must agree to fp32
+    summation-order noise, rows that are whole tiles in both launches bit for bit, and two runs must be bit-identical."""
+    from vqnerf_release_b200 import abi
+    w_tiles = 148 * 16
+    n = (w_tiles + rem_tiles) * 32
+    g = torch.Generator(device=cuda_dev).manual_seed(rem_tiles)
+    r = lambda *s: torch.rand(s, generator=g, device=cuda_dev)
+    xyz = r(n, 3) * 2 - 1
+    rayo = torch.nn.functional.normalize(torch.randn((n, 3), generator=g, device=cuda_dev), dim=1) * 4
+    normal = torch.nn.functional.normalize(torch.randn((n, 3), generator=g, device=cuda_dev), dim=1)
+    lvis, albedo, spec, rough = r(n, 512), r(n, 3), r(n, 3) * 0.2, 0.2 + 0.7 * r(n, 1)
+    lx, la = abi.gen_light_xyz(16, 32)
+    lxyz, lareas = torch.as_tensor(lx, dtype=torch.float32).to(cuda_dev), torch.as_tensor(la, dtype=torch.float32).to(cuda_dev)
+    lights = r(9, 512, 3)
+
+    def shade(sl):
+        c = lambda t: t[sl].contiguous()
+        return abi.shade(c(xyz), c(rayo), c(normal), c(lvis), c(albedo), c(spec), c(rough), lxyz, lareas, lights,
+                         to_srgb=True)['rgb']
+    full = shade(slice(0, n))
+    assert torch.equal(full, shade(slice(0, n)))
+    lo = w_tiles * 32                                           # first row of the split round of `full`
+    tail = shade(slice(n - lo, n))                              # exactly 148 x 16 whole tiles ending with the same rows
+    k = lo - (n - lo)                                           # rows [n - lo, lo) are whole tiles in both launches
+    assert torch.equal(full[n - lo:lo], tail[:k])
+    err = float((full[lo:] - tail[k:]).abs().max())
+    assert err <= 2e-6, 'split round vs whole tiles: max abs diff %.2e' % err
+    # one ragged tile at the end
+    n2 = n - 7
+    a, b2 = shade(slice(0, n2)), shade(slice(n2 - lo, n2))
+    assert float((a[lo:] - b2[lo - (n2 - lo):]).abs().max()) <= 2e-6
+
+
 def test_shade_grazing_opposite_light(cuda_dev):
     """View nearly tangent AND a light nearly opposite to it (l ~ -v): |l + v| -> 0.  The shortcut
     |l + v|^2 = 2 + 2 l.v cancels there; the kernels must form the half vector componentwise like the reference

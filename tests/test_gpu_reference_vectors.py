@@ -95,4 +95,5 @@ def test_two_training_steps_vs_reference_code(ref, setup, cuda_dev):
             for i, gb in enumerate(st.dB[name]):
                 want = ref['%sd_%s_b%d' % (p, name, i)]
                 err = np.abs(gb.cpu().double().numpy() - want).max()
-                assert err <= 2e-4 * max(np.abs(want).max(), 1e-30), 'd %s.bias[%d]: %.3e' % (name, i, err)
+                # + 1e-7: a 1-wide layer's bias gradient is ONE number, a sum over the rows with cancellation (fp32 noise)
+                assert err <= 2e-4 * np.abs(want).max() + 1e-7, 'd %s.bias[%d]: %.3e' % (name, i, err)

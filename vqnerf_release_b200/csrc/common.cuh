@@ -22,7 +22,7 @@ struct vqn_ctx {
 
 // Library-owned work buffers that must not be shared between streams (latent scratch of mlp_main, act' stash of the SDF
 // gradient, codebook images of vq_tc): one buffer per (kind, stream), allocated on first use, freed with the context.
-enum { VQN_SCRATCH_Z = 0, VQN_SCRATCH_STASH = 1, VQN_SCRATCH_VQ_W = 2, VQN_SCRATCH_VQ_C2 = 3 };
+enum { VQN_SCRATCH_Z = 0, VQN_SCRATCH_STASH = 1, VQN_SCRATCH_VQ_W = 2, VQN_SCRATCH_VQ_C2 = 3, VQN_SCRATCH_SHADE = 4 };
 void* vqn_stream_scratch(vqn_ctx* ctx, int kind, cudaStream_t stream, size_t bytes);   // nullptr: allocation failed
 #define VQN_SCRATCH_INTS (1 << 16)
 

@@ -75,9 +75,10 @@ __global__ void shade_pt_prep_kernel(const float* __restrict__ lxyz, const float
 
 // LV: light-visibility format -- 0 none, 1 float32 (the reference's lvis.npy), 2 float16, 3 uint8 (v = q / 255): the
 // compact formats are an opt-in of the host-buffer path (the fp32 rows are 98 % of a view's H2D bytes)
-template <int NPC, int LV>
+template <int NPC, int LV, bool SPLIT>
 __global__ void __launch_bounds__(SP_THREADS, 1) shade_pt_kernel(vqn_shade_args a, const float4* __restrict__ img,
-                                                                 int* nonfinite) {
+                                                                 int* nonfinite, float* __restrict__ part_buf,
+                                                                 unsigned* __restrict__ part_cnt) {
   extern __shared__ __align__(16) float4 s_img[];
   constexpr int NF4 = SP_NF4(NPC), PER_GROUP = SP_F4_PER_GROUP(NPC), NPAIR = 2 * NF4;   // NPAIR includes the padding pair
   for (int k = threadIdx.x; k < SP_GROUPS * PER_GROUP; k += SP_THREADS) s_img[k] = img[k];
@@ -89,7 +90,28 @@ __global__ void __launch_bounds__(SP_THREADS, 1) shade_pt_kernel(vqn_shade_args 
   const int lane = threadIdx.x & 31;
   const long long warps_total = (long long)gridDim.x * (SP_THREADS / 32);
   const long long warp0 = (long long)blockIdx.x * (SP_THREADS / 32) + (threadIdx.x >> 5);
-  for (long long tile = warp0; tile * 32 < n; tile += warps_total) {
+  // Work units.  T tiles of 32 points over W persistent warps: the first F = T / W rounds are whole tiles; the R = T - F W
+  // tiles of the last, partial round are cut into S light ranges each (S = the largest power of two <= 16 with
+  // R S <= W), so that the tail costs 1/S of a round instead of a whole one -- at 80 000 points per GPU (an 800x800 view
+  // over 8 GPUs) that is 2500 tiles on 2368 warps: 1.06 rounds of work used to take 2.  The S partial sums of a tile meet
+  // in global scratch; the LAST warp to arrive adds them in a fixed order (deterministic) and runs the epilogue.
+  // (SPLIT is chosen by the host from the row count it knows: only when the last round would fill less than a quarter of
+  // the warps -- a fuller tail round already runs at the issue rate, and the instantiation without the split keeps the
+  // constant loop bounds.)
+  const long long T = (n + 31) / 32, F = SPLIT ? T / warps_total : T, R = T - F * warps_total;
+  int S = 1;
+  if (SPLIT && R > 0) { const long long q = warps_total / R; S = q >= 16 ? 16 : q >= 8 ? 8 : q >= 4 ? 4 : 1; }
+  const long long whole = SPLIT ? F * warps_total : T;          // tiles processed whole
+  for (long long u = warp0; u < whole + R * S; u += warps_total) {
+  long long tile = u;
+  int g0 = 0, g1 = SP_GROUPS, part = 0;
+  const bool split = SPLIT && u >= whole && S > 1;
+  if (SPLIT && u >= whole) {
+    const long long ru = u - whole;
+    tile = whole + ru / S;
+    part = (int)(ru % S);
+    g0 = part * (SP_GROUPS / S); g1 = g0 + SP_GROUPS / S;
+  }
   const long long i_raw = tile * 32 + lane;
   const bool live = i_raw < n;
   const long long i = live ? i_raw : n - 1;                     // dead lanes of the last tile recompute row n-1
@@ -145,12 +167,12 @@ __global__ void __launch_bounds__(SP_THREADS, 1) shade_pt_kernel(vqn_shade_args 
                        (__uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7653)) - o) * k);
   };
   float4 lv_cur = make_float4(1.f, 1.f, 1.f, 1.f);
-  if (HAS_LVIS) lv_cur = lv_load(0);
+  if (HAS_LVIS) lv_cur = lv_load(g0);
 
 #pragma unroll 1
-  for (int grp = 0; grp < SP_GROUPS; ++grp) {
+  for (int grp = g0; grp < g1; ++grp) {
     float4 lv_nxt = lv_cur;
-    if (HAS_LVIS && grp + 1 < SP_GROUPS) lv_nxt = lv_load(grp + 1);
+    if (HAS_LVIS && grp + 1 < g1) lv_nxt = lv_load(grp + 1);
     const float4* cg = s_img + grp * PER_GROUP;                // warp-uniform address: broadcast reads
     const float4 X = cg[0], Y = cg[1], Z = cg[2];
     const float xs4[4] = {X.x, X.y, X.z, X.w}, ys4[4] = {Y.x, Y.y, Y.z, Y.w}, zs4[4] = {Z.x, Z.y, Z.z, Z.w};
@@ -205,6 +227,27 @@ __global__ void __launch_bounds__(SP_THREADS, 1) shade_pt_kernel(vqn_shade_args 
     unpack2(acc[NPC + p / 2], lo, hi);
     out[3 * p + 2] = (p & 1) ? hi : lo;
   }
+  if (split) {
+    // this warp's light range of the tile -> scratch [remainder tile][part][k][lane]; the last of the S warps finishes the tile
+    const long long rt = tile - whole;
+    float* pb = part_buf + ((size_t)rt * 16 + part) * (32 * 3 * SP_MAXP);
+#pragma unroll
+    for (int k = 0; k < 3 * NPC; ++k) pb[k * 32 + lane] = out[k];
+    __threadfence();
+    unsigned old = 0;
+    if (lane == 0) old = atomicAdd(&part_cnt[rt], 1u);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old != (unsigned)(S - 1)) continue;                            // warp-uniform: not the last one
+    __threadfence();
+    if (lane == 0) part_cnt[rt] = 0;                                   // ready for the next launch
+    const float* p0 = part_buf + (size_t)rt * 16 * (32 * 3 * SP_MAXP);
+#pragma unroll
+    for (int k = 0; k < 3 * NPC; ++k) {
+      float sum = 0.f;
+      for (int q = 0; q < S; ++q) sum += __ldcg(p0 + (size_t)q * (32 * 3 * SP_MAXP) + k * 32 + lane);
+      out[k] = sum;
+    }
+  }
 #pragma unroll
   for (int p = 0; p < NPC; ++p) {
 #pragma unroll
@@ -238,7 +281,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) shade_pt_kernel(vqn_shade_args 
       }
     }
   }
-  }   // tile loop
+  }   // work-unit loop
 }
 
 template <int NPC>
@@ -247,15 +290,29 @@ int launch_pt(vqn_ctx* ctx, const vqn_shade_args& a, const float4* img, cudaStre
   long long want = (a.n + SP_THREADS - 1) / SP_THREADS;
   const unsigned blocks = (unsigned)(want < (long long)ctx->sm_count ? want : (long long)ctx->sm_count);
   const int lv = !a.lvis ? 0 : a.lvis_format == VQN_LVIS_F16 ? 2 : a.lvis_format == VQN_LVIS_U8 ? 3 : 1;
-#define SP_LAUNCH(LVV)                                                                                                  \
+  // scratch of the split last round: <= W / S tiles x 16 parts x [27][32] partial sums, + one arrival counter per tile
+  const size_t warps = (size_t)blocks * (SP_THREADS / 32);
+  const size_t cnt_bytes = (warps * sizeof(unsigned) + 255) / 256 * 256;
+  const size_t part_bytes = warps / 2 * 16 * (32 * 3 * SP_MAXP) * sizeof(float);
+  unsigned char* sc = static_cast<unsigned char*>(vqn_stream_scratch(ctx, VQN_SCRATCH_SHADE, s, cnt_bytes + part_bytes));
+  if (!sc) return VQN_ERR_CUDA;
+  unsigned* part_cnt = reinterpret_cast<unsigned*>(sc);
+  float* part_buf = reinterpret_cast<float*>(sc + cnt_bytes);
+  // split the last round only when it would be poorly occupied (see the kernel)
+  const long long T_host = (a.n + 31) / 32, R_host = T_host % (long long)warps;
+  const bool do_split = R_host > 0 && (long long)warps / R_host >= 4;
+  if (do_split) VQN_CUDA(cudaMemsetAsync(part_cnt, 0, cnt_bytes, s));
+#define SP_LAUNCH2(LVV, SPL)                                                                                            \
   do {                                                                                                                  \
-    VQN_CUDA(cudaFuncSetAttribute(shade_pt_kernel<NPC, LVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-    shade_pt_kernel<NPC, LVV><<<blocks, SP_THREADS, smem, s>>>(a, img, ctx->nonfinite_flag);                           \
+    VQN_CUDA(cudaFuncSetAttribute(shade_pt_kernel<NPC, LVV, SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    shade_pt_kernel<NPC, LVV, SPL><<<blocks, SP_THREADS, smem, s>>>(a, img, ctx->nonfinite_flag, part_buf, part_cnt);   \
   } while (0)
+#define SP_LAUNCH(LVV) do { if (do_split) SP_LAUNCH2(LVV, true); else SP_LAUNCH2(LVV, false); } while (0)
   if (lv == 0) SP_LAUNCH(0);
   else if (lv == 1) SP_LAUNCH(1);
   else if (lv == 2) SP_LAUNCH(2);
   else SP_LAUNCH(3);
+#undef SP_LAUNCH2
 #undef SP_LAUNCH
   VQN_LAUNCHED(ctx);
   return VQN_OK;

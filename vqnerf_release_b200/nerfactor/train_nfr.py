@@ -398,8 +398,12 @@ class GraphedTrainIter:
         self.K = model.num_embed
         self.sel_mask = torch.ones((self.K,), dtype=F32, device=dev) if use_thres else None
         self.lr_t = torch.zeros((1,), dtype=F32, device=dev)
-        self._lr_host = torch.zeros((1,), dtype=F32).pin_memory()
-        self._mask_host = torch.ones((self.K,), dtype=F32).pin_memory()
+        # per-step host values (Adam's rate, the dropout mask) go through a RING of pinned staging slots, each guarded by
+        # an event recorded after its H2D copy: the host may run several replays ahead of the GPU, and rewriting a pinned
+        # buffer whose copy is still queued would hand a step the NEXT step's rate / a torn mask
+        self._ring = [(torch.zeros((1,), dtype=F32).pin_memory(), torch.ones((self.K,), dtype=F32).pin_memory(),
+                       torch.cuda.Event()) for _ in range(4)]
+        self._ring_i = 0
         # warm-up on a side stream (allocates the activation set, Adam state, NCCL buffers), then capture; the
         # learned state touched by the warm-up steps is snapshotted and restored so that construction has no effect
         st = _train_state(model)
@@ -429,17 +433,21 @@ class GraphedTrainIter:
 
     def _refresh(self, thres, roll):
         self.opt.iterations += 1
-        self._lr_host[0] = self.opt.lr_t()
-        self.lr_t.copy_(self._lr_host, non_blocking=True)
+        lr_host, mask_host, ev = self._ring[self._ring_i]
+        self._ring_i = (self._ring_i + 1) % len(self._ring)
+        ev.synchronize()                                  # the copy that last read this slot has completed (no-op if unused)
+        lr_host[0] = self.opt.lr_t()
+        self.lr_t.copy_(lr_host, non_blocking=True)
         if self.sel_mask is not None:
             if thres is None:
-                self._mask_host.fill_(1.0)
+                mask_host.fill_(1.0)
             else:
                 th = torch.as_tensor(thres, dtype=F32).reshape(-1)
                 if roll is None:
                     roll = torch.rand((1, self.K), generator=self.model.vq_layer._gen, dtype=F32)
-                self._mask_host.copy_((torch.as_tensor(roll, dtype=F32).reshape(-1) >= th).to(F32))
-            self.sel_mask.copy_(self._mask_host, non_blocking=True)
+                mask_host.copy_((torch.as_tensor(roll, dtype=F32).reshape(-1) >= th).to(F32))
+            self.sel_mask.copy_(mask_host, non_blocking=True)
+        ev.record(torch.cuda.current_stream(self.model.device))
 
     def __call__(self, batch, thres=None, roll=None):
         for dst, src in zip(self.static, batch):

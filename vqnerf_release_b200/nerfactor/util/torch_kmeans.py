@@ -43,17 +43,26 @@ def _prep(X, distance, device):
 
 
 def kmeans(X, num_clusters, distance='euclidean', tol=1e-4, device=torch.device('cuda'), seed=1, max_iter=10000):
-    """torch_kmeans.py:23-94.  Returns (cluster ids [N] int64 on the CPU, cluster centres [K,Z] on the CPU)."""
+    """torch_kmeans.py:23-94.  Returns (cluster ids [N] int64 on the CPU, cluster centres [K,Z] on the CPU).
+
+    'cosine' (pairwise_cosine, :147-166) normalises both operands INSIDE the distance only: the centres are the means of
+    the RAW member rows and are never re-normalised, exactly as in the reference -- the arg-min runs on the unit rows /
+    unit centres (1 - cos = |a/|a| - b/|b||^2 / 2), the member sums on the raw rows."""
+    raw = X.float().to(device).contiguous() if distance == 'cosine' else None
     X = _prep(X, distance, device)
-    centers = initialize(X, num_clusters, seed)
+    centers = initialize(raw if raw is not None else X, num_clusters, seed)
     z, k = X.shape[1], num_clusters
     for _ in range(max_iter):
         if distance == 'cosine':
-            centers = abi.l2_normalize_rows(centers)
-        idx, stats = _assign(X, centers, True)
-        counts = stats[:k]
-        dw = stats[k + 2:].reshape(z, k)
-        new = (dw / counts.clamp_min(1.0)[None, :]).t().to(torch.float32)
+            idx, stats = _assign(X, abi.l2_normalize_rows(centers), True)
+            counts = stats[:k]
+            sums = torch.zeros((k, z), dtype=torch.float64, device=X.device).index_add_(0, idx, raw.double())
+            new = (sums / counts.clamp_min(1.0)[:, None]).to(torch.float32)
+        else:
+            idx, stats = _assign(X, centers, True)
+            counts = stats[:k]
+            dw = stats[k + 2:].reshape(z, k)
+            new = (dw / counts.clamp_min(1.0)[None, :]).t().to(torch.float32)
         new = torch.where((counts > 0)[:, None], new, centers)           # empty cluster: keep the centre
         center_shift = torch.sum(torch.sqrt(torch.sum((new - centers) ** 2, dim=1)))   # :72-75
         centers = new

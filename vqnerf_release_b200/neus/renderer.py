@@ -93,7 +93,8 @@ class NeuSRenderer:
     def render(self, rays_o, rays_d, near, far, radius, perturb_overwrite=-1, background_rgb=None,
                cos_anneal_ratio=0.0, to_light=False, need_color=True):
         if to_light:
-            raise NotImplementedError('to_light marching (gen_geo.compute_vis) is a "next" row (SURVEY 8f N1)')
+            raise NotImplementedError('to_light marching (a per-ray sample_dist, renderer.py:211,302) has no caller in the '
+                                      'reference -- gen_geo.compute_vis renders with the default -- and is not built')
         batch_size = len(rays_o)
         dev = rays_o.device
         sample_dist = 2 * radius / self.n_samples
