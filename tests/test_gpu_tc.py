@@ -15,7 +15,8 @@ def _tf32(x):
 
 
 @pytest.mark.parametrize('mode,n,k', [(0, 16, 32), (0, 128, 64), (0, 256, 128), (1, 16, 64), (1, 256, 128),
-                                     (1, 128, 256), (2, 16, 32), (2, 256, 64), (2, 128, 64)])
+                                     (1, 128, 256), (2, 16, 32), (2, 256, 64), (2, 128, 64),
+                                     (3, 16, 32), (3, 128, 64), (3, 256, 64), (3, 128, 128)])    # 3: A operand from tensor memory
 def test_tc_selftest_gemm(cuda_dev, mode, n, k):
     from vqnerf_release_b200 import abi
     rng = np.random.RandomState(mode * 1000 + n + k)
@@ -32,7 +33,7 @@ def test_tc_selftest_gemm(cuda_dev, mode, n, k):
         tol = 2e-5
     else:
         ref = a.astype(np.float64) @ b.astype(np.float64).T
-        tol = 3e-6            # 3xTF32 with round-to-nearest hi/lo: fp32-level accuracy (plain tf32: ~5e-4)
+        tol = 3e-6 if mode == 2 else 8e-6   # 3xTF32 with round-to-nearest hi/lo: fp32-level accuracy (plain tf32: ~5e-4)
     scale = np.sqrt(k)
     err = np.abs(d - ref).max() / scale
     print('tc_selftest mode %d N=%d K=%d err/sqrt(K)=%.3e' % (mode, n, k, err))

@@ -592,7 +592,7 @@ def neus_lvis_scatter(weight_sum, row_idx, n: int, l0: int, n_chunk: int, lvis: 
 
 # ---- tensor-core primitive self-test ------------------------------------------------------------
 def tc_selftest(a: torch.Tensor, b: torch.Tensor, mode: int) -> torch.Tensor:
-    """d[128,n] = a[128,k] @ b[n,k]^T on tcgen05 (mode 0 tf32, 1 bf16, 2 3xTF32)."""
+    """d[128,n] = a[128,k] @ b[n,k]^T on tcgen05 (mode 0 tf32, 1 bf16, 2 3xTF32, 3 shipped tf32+bf16 scheme with A in TMEM)."""
     a, b = _f(a), _f(b)
     if a.shape[0] != 128 or a.shape[1] != b.shape[1]:
         raise ValueError('a must be [128,k], b [n,k]')

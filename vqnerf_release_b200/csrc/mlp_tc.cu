@@ -275,13 +275,19 @@ template <bool BF16>
 struct TcCfg {
   static constexpr int E = BF16 ? 64 : 32;                 // K elements per chunk
   static constexpr int PLANES = BF16 ? 1 : 2;
-  static constexpr int SA = BF16 ? 4 : 2;                  // A ring stages
-  static constexpr int SW = BF16 ? 4 : 2;                  // W ring stages
+  // Ring depths.  A slot = one 32-K chunk of the 128-row tile (tf32x3: tf32 plane + correction plane = 32 KB).  A slot is
+  // busy from the producers' first store until the MMAs reading it complete, so a ring of S slots sustains one chunk per
+  // (store time + MMA time + hand-off latency) / S: with S = 2 that was ~1250 cycles against 745 cycles of tensor time on
+  // the N = 128 layers.  The third A slot is paid for by the WEIGHT ring: its entries are 32 KB -- both planes of a chunk
+  // of a layer with Npad <= 128, ONE plane of a wider layer (the tf32 MMAs of a chunk need only plane H, the correction
+  // MMAs only plane C; each entry is released by its own tcgen05.commit) -- instead of two 64 KB slots.
+  static constexpr int SA = BF16 ? 4 : 3;                  // A ring stages
+  static constexpr int SW = BF16 ? 4 : 3;                  // W ring entries
   static constexpr int G = 2;                              // epilogue warp-groups (8 warps each: a thread owns 16 columns of a row)
   static constexpr int THREADS = 32 * (8 * G + 2);         // + MMA warp + weight-producer warp
   static constexpr uint32_t A_PLANE = TC_M * 128;          // 16 KB
   static constexpr uint32_t A_SLOT = A_PLANE * PLANES;
-  static constexpr uint32_t W_SLOT = (uint32_t)TC_NPAD_MAX * 128 * PLANES;
+  static constexpr uint32_t W_SLOT = (uint32_t)TC_NPAD_MAX * 128;    // 32 KB
   static constexpr size_t SMEM = (size_t)SA * A_SLOT + (size_t)SW * W_SLOT + 1024;
 };
 #define TC_BIAS_FLOATS 7168
@@ -651,7 +657,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
             if (st == SRC_EMBED) {
               tc::mbar_wait(&a_empty[slot], ((ga / C::SA) & 1) ^ 1);
               if (half == 0) embed_chunk<BF16>(dst, r, x, sc * C::E, pg.n_freqs, jc);
-            } else if (!BF16 && st == SRC_GLOBAL) {
+            } else if (!BF16 && st == SRC_GLOBAL && !pg.g_local) {
               // Latent chunk [128 rows x 32 columns] of the row-major source: loaded COALESCED (a warp reads 4 rows x
               // 128 B per instruction; a thread-per-row load touches 32 lines per instruction and costs 8x the L1/smem
               // data-pipe wavefronts, which is the port this kernel is bound by), staged through the plane-C half of the
@@ -665,8 +671,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                 ldv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (prow < n && col_base + 4 * ch < pg.g_dim) {
                   // per-CTA scratch: written earlier in this kernel by other threads -> L2-coherent load, no L1 line
-                  if (pg.g_local) ldv[i] = __ldcg(reinterpret_cast<const float4*>(pg.gsrc + ((size_t)blockIdx.x * TC_M + rr) * pg.g_dim + col_base + 4 * ch));
-                  else ldv[i] = __ldg(reinterpret_cast<const float4*>(pg.gsrc + prow * pg.g_dim + col_base + 4 * ch));
+                  ldv[i] = __ldg(reinterpret_cast<const float4*>(pg.gsrc + prow * pg.g_dim + col_base + 4 * ch));
                 }
               }
               TC_STAMP(ptr_, 1);
@@ -733,13 +738,23 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = dv[j] * tw[j].x;
                   }
-                } else {                                  // SRC_GLOBAL (bf16 mode): this thread's own latent row
-                  if (valid && col0 < pg.g_dim) {
-                    const float4* src = reinterpret_cast<const float4*>(
-                        pg.gsrc + (pg.g_local ? (size_t)blockIdx.x * TC_M + r : (size_t)pi) * pg.g_dim + col0);
+                } else {                                  // SRC_GLOBAL: this thread's own 16 values of its latent row
+                  if (pg.g_local && col0 < pg.g_dim) {
+                    // per-CTA scratch tile, ROW-INTERLEAVED ([col / 4][row][4]): a warp reads 32 rows x 16 B = 512 contiguous
+                    // bytes per instruction -- coalesced without staging; written earlier in this kernel by other threads of
+                    // the CTA -> L2-coherent loads, no L1 line
+                    const float4* src = reinterpret_cast<const float4*>(pg.gsrc + (size_t)blockIdx.x * TC_M * pg.g_dim) +
+                                        (size_t)(col0 >> 2) * TC_M + r;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                      float4 t = pg.g_local ? __ldcg(src + j) : src[j];
+                      const float4 t = __ldcg(src + (size_t)j * TC_M);
+                      v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+                    }
+                  } else if (valid && col0 < pg.g_dim) {
+                    const float4* src = reinterpret_cast<const float4*>(pg.gsrc + (size_t)pi * pg.g_dim + col0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      float4 t = src[j];
                       v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
                     }
                   } else {
@@ -898,7 +913,17 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                 bad |= (c16 + j < ly.N) && !isfinite(v[j]);
               }
               if (valid_out && bad) atomicOr(pg.nonfinite, 1);
-              if (wide) {
+              if (local) {
+                // per-CTA latent scratch, row-interleaved (see the SRC_GLOBAL producers): 512 contiguous bytes per warp store;
+                // every row is written (rows beyond n carry the finite values of x = 0), so no stale data is ever re-read
+                float4* dstz = reinterpret_cast<float4*>(go + (size_t)blockIdx.x * TC_M * gs) + (size_t)(c16 >> 2) * TC_M + r;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  __stcg(dstz + (size_t)q * TC_M, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+              }
+              if (local && !pg.out_dup) {
+                // nothing else to store
+              } else if (wide) {
                 // stage the 32-column block in the group's own (free) A slot, swizzled, then store it coalesced:
                 // a warp writes 4 rows x 128 B per instruction instead of 16 B into each of 32 rows
                 const uint32_t stage = a_ring_s + (uint32_t)grp * C::A_SLOT;
@@ -918,8 +943,9 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                 }
               }
             }
-            if (wide) {
+            if (wide && (!local || pg.out_dup)) {
               const uint32_t stage = a_ring_s + (uint32_t)grp * C::A_SLOT;
+              float* gout = local ? pg.out_dup : go;        // (the caller's row-major copy of the latent / the output)
               group_bar(grp);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -927,12 +953,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                 const long long prow = tile * tile_pts + (jet ? (rr >> 2) : rr);
                 if (prow < n && (!jet || (rr & 3) == 0)) {
                   const float4 val = tc::lds128(stage + rr * 128 + ((ch ^ (rr & 7)) << 4));
-                  if (local) {
-                    *reinterpret_cast<float4*>(go + ((size_t)blockIdx.x * TC_M + rr) * gs + cb * 32 + 4 * ch) = val;
-                    if (pg.out_dup) *reinterpret_cast<float4*>(pg.out_dup + (size_t)prow * gs + cb * 32 + 4 * ch) = val;
-                  } else {
-                    *reinterpret_cast<float4*>(go + (size_t)prow * gs + cb * 32 + 4 * ch) = val;
-                  }
+                  *reinterpret_cast<float4*>(gout + (size_t)prow * gs + cb * 32 + 4 * ch) = val;
                 }
               }
               group_bar(grp);
@@ -943,6 +964,9 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
           if (local) {
             // the heads' producers (all 512 threads) re-read this tile from the scratch: CTA-wide visibility
             __threadfence_block();
+            asm volatile("bar.sync 3, %0;" ::"r"(256 * C::G) : "memory");
+          } else if (wide && C::SA % C::G != 0) {
+            // slots are not owned by one group: the other group's next chunk could land in this group's staging slot
             asm volatile("bar.sync 3, %0;" ::"r"(256 * C::G) : "memory");
           }
         }
@@ -977,6 +1001,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
             }
           }
           uint32_t acc = 0;
+          const bool wsplit = !BF16 && ly.Npad > 128;     // the two planes of a chunk are separate ring entries
           for (int c = 0; c < nch; ++c, ++ga, ++gw) {
             const int sa = ga % C::SA, sw = gw % C::SW;
             if (c == 0) TC_STAMP(tr, 1);
@@ -989,6 +1014,27 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
 #ifdef TC_EXP_NO_MMA
             if (tile >= 0) { tc::mma_commit(&a_empty[sa]); tc::mma_commit(&w_empty[sw]); continue; }
 #endif
+            if (wsplit) {
+              // wide layer: the four tf32 MMAs (plane H entry), release it, then the four correction MMAs (plane C entry)
+#pragma unroll
+              for (int s = 0; s < 4; ++s) {
+                tc::mma_ss<true>(d_tmem, tc::make_desc_sw128(a_addr + 32 * s), tc::make_desc_sw128(w_addr + 32 * s), idesc, acc);
+                acc = 1;
+              }
+              tc::mma_commit(&w_empty[sw]);
+              ++gw;
+              const int sc = gw % C::SW;
+              tc::mbar_wait(&w_full[sc], (gw / C::SW) & 1);
+              tc::fence_after_sync();
+              const uint32_t c_addr = tc::smem_u32(w_ring + (size_t)sc * C::W_SLOT);
+#pragma unroll
+              for (int s = 0; s < 4; ++s)
+                tc::mma_ss<false>(d_tmem, tc::make_desc_sw128(a_addr + C::A_PLANE + 32 * s),
+                                  tc::make_desc_sw128(c_addr + 32 * s), idesc_c, 1);
+              tc::mma_commit(&a_empty[sa]);
+              tc::mma_commit(&w_empty[sc]);
+              continue;
+            }
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
               const uint64_t a_hi = tc::make_desc_sw128(a_addr + 32 * s);
@@ -1020,15 +1066,20 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
         for (int l = 0; l < L; ++l) {
           const TcLayer& ly = pg.layers[l];
           const int nch = ly.seg_chunks[0] + (ly.nseg > 1 ? ly.seg_chunks[1] : 0);
-          const uint32_t bytes = (uint32_t)ly.Npad * 128 * C::PLANES;
-          for (int c = 0; c < nch; ++c, ++gw) {
-            const int sw = gw % C::SW;
-            tc::mbar_wait(&w_empty[sw], ((gw / C::SW) & 1) ^ 1);
+          const uint32_t bytes = (uint32_t)ly.Npad * 128 * C::PLANES;        // chunk image: plane H, then plane C
+          const int parts = (!BF16 && ly.Npad > 128) ? 2 : 1;                  // wide layer: one ring entry per plane
+          const uint32_t part_bytes = bytes / parts;
+          for (int c = 0; c < nch; ++c) {
+            for (int pt = 0; pt < parts; ++pt, ++gw) {
+              const int sw = gw % C::SW;
+              tc::mbar_wait(&w_empty[sw], ((gw / C::SW) & 1) ^ 1);
 #ifdef TC_EXPERIMENT_NO_W
-            if (gw >= (uint32_t)C::SW) { tc::mbar_arrive(&w_full[sw]); continue; }
+              if (gw >= (uint32_t)C::SW) { tc::mbar_arrive(&w_full[sw]); continue; }
 #endif
-            tc::mbar_expect_tx(&w_full[sw], bytes);
-            tc::bulk_g2s(w_ring + (size_t)sw * C::W_SLOT, ly.w + (size_t)c * bytes, bytes, &w_full[sw]);
+              tc::mbar_expect_tx(&w_full[sw], part_bytes);
+              tc::bulk_g2s(w_ring + (size_t)sw * C::W_SLOT, ly.w + (size_t)c * bytes + (size_t)pt * part_bytes, part_bytes,
+                           &w_full[sw]);
+            }
           }
         }
       }

@@ -98,10 +98,11 @@ __global__ void __launch_bounds__(SP_THREADS, 1) shade_pt_kernel(vqn_shade_args 
   // (SPLIT is chosen by the host from the row count it knows: only when the last round would fill less than a quarter of
   // the warps -- a fuller tail round already runs at the issue rate, and the instantiation without the split keeps the
   // constant loop bounds.)
-  const long long T = (n + 31) / 32, F = SPLIT ? T / warps_total : T, R = T - F * warps_total;
+  const long long T = (n + 31) / 32;
+  const long long whole = SPLIT ? (T / warps_total) * warps_total : T;      // tiles processed whole
+  const long long R = T - whole;
   int S = 1;
   if (SPLIT && R > 0) { const long long q = warps_total / R; S = q >= 16 ? 16 : q >= 8 ? 8 : q >= 4 ? 4 : 1; }
-  const long long whole = SPLIT ? F * warps_total : T;          // tiles processed whole
   for (long long u = warp0; u < whole + R * S; u += warps_total) {
   long long tile = u;
   int g0 = 0, g1 = SP_GROUPS, part = 0;
