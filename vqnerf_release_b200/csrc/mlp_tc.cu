@@ -49,6 +49,7 @@ struct TcLayer {
   const float* bias;      // [Npad]
   int N, Npad, act;
   int nseg, seg_type[2], seg_chunks[2], seg_first_chunk[2];   // seg_first_chunk: index inside the source
+  int seg_ts[2];          // 1: the chunks of this segment are handed over in TENSOR MEMORY (TS-mode MMAs), see TC_TS_COL
   int out_slot;           // >= 0: accumulator is written to global outs[out_slot] (row-major [point][N])
   int bias_off;           // offset of this layer's bias inside the shared-memory bias table
   float post_scale, post_bias;
@@ -290,6 +291,14 @@ struct TcCfg {
   static constexpr uint32_t W_SLOT = (uint32_t)TC_NPAD_MAX * 128;    // 32 KB
   static constexpr size_t SMEM = (size_t)SA * A_SLOT + (size_t)SW * W_SLOT + 1024;
 };
+// A operand from tensor memory (tf32x3 plain chain): two A slots of 64 columns at the top of TMEM -- per 32-K chunk
+// [tf32 hi x 32 | bf16 pairs of a_lo x 16 | bf16 pairs of a_hi x 16], written by the producers with tcgen05.st and read by
+// TS-mode MMAs.  The kernel is bound by the 128 B/clk shared-memory port (UMMA operand reads + A-chunk stores + weight
+// copies: 128 KB per chunk of an N = 128 layer = 1024 cycles against 512 cycles of tensor time); a chunk that goes through
+// TMEM takes its 32 KB of stores and 32 KB of operand reads off that port.  The host planner (tc_plan_ts) enables it per
+// segment where the accumulators leave columns [TC_TS_COL, 512) free.
+#define TC_TS_COL 384
+#define TC_TS_SLOTS 2
 #define TC_BIAS_FLOATS 7168
 #define TC_STASH_SLOTS 8
 // act' of the reverse-mode gradient is stashed as 16-bit fixed point (act' of relu / softplus / sigmoid lies in [0, 1]: step
@@ -531,11 +540,12 @@ __device__ __forceinline__ void group_bar(int grp) { asm volatile("bar.sync %0, 
 
 // MODE 0: plain chain (decomposition stage, SDF value-only); 1: jets (4 rows per point); 2: reverse-mode gradient;
 // 3: plain chain that also stores every hidden layer's output (training forward)
-template <bool BF16, int MODE>
+template <bool BF16, int MODE, bool TS>
 __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcProgram pg) {
   using C = TcCfg<BF16>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[4], a_empty[4], w_full[4], w_empty[4], acc_full, drain_done;
+  __shared__ __align__(8) uint64_t t_full[TC_TS_SLOTS], t_empty[TC_TS_SLOTS];       // TMEM A slots (TS)
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[TC_BIAS_FLOATS];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -551,6 +561,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
       tc::mbar_init(&a_full[i], 256); tc::mbar_init(&a_empty[i], 1);
       tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1);
     }
+    for (int i = 0; i < TC_TS_SLOTS; ++i) { tc::mbar_init(&t_full[i], 256); tc::mbar_init(&t_empty[i], 1); }
     tc::mbar_init(&acc_full, 1);
     tc::mbar_init(&drain_done, 256 * C::G);
     tc::mbar_fence_init();
@@ -593,7 +604,8 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
     const int tg = tid & 255;                            // thread index inside the group
     const int r = 32 * (warp & 3) + lane;                // TMEM lane == point row of the tile
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
-    uint32_t ga = 0;                                     // global A-chunk counter
+    uint32_t ga = 0;                                     // global A-chunk counter (chunk -> group)
+    uint32_t gs = 0, gt = 0;                             // chunks handed over in shared memory / in tensor memory so far
     uint32_t gl = 0;                                     // global layer counter (acc_full phase)
 #ifdef VQN_TC_TRACE
     int ptrace_n = 0;
@@ -633,14 +645,22 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
           const float* pbias = bias_s + (l > 0 ? pg.layers[l - 1].bias_off : 0);
           const uint32_t pacc = lane_addr + (uint32_t)(l > 0 ? pg.layers[l - 1].tmem_col : 0);
           bool acc_ready = false;
+#ifdef TC_TS_NO_PROD
+          const bool ts = false;
+#else
+          const bool ts = TS && pg.layers[l].seg_ts[sg];
+#endif
           for (int c = 0; c < nch; ++c, ++ga) {
+            const uint32_t gsm = ts ? 0u : gs, gtm = gt;  // this chunk's position in its ring
+            if (ts) ++gt; else ++gs;
             if ((int)(ga % C::G) != grp) continue;
             if ((st == SRC_DRAIN || st == SRC_GRAD) && !acc_ready) {
               tc::mbar_wait(&acc_full, (gl - 1) & 1);    // previous layer's accumulator is complete
               tc::fence_after_sync();
               acc_ready = true;
             }
-            const int slot = ga % C::SA;
+            const int slot = gsm % C::SA;
+            const uint32_t a_par = ((gsm / C::SA) & 1) ^ 1;                     // parity of the slot's "empty" phase
             const uint32_t dst = a_ring_s + (uint32_t)slot * C::A_SLOT;          // shared-space address of the slot
             const int sc = first + c;                     // chunk index inside the source
 #ifdef VQN_TC_TRACE
@@ -651,11 +671,11 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
 #endif
 #ifdef TC_EXP_NO_PROD
             if (sc >= 0) {
-              tc::mbar_wait(&a_empty[slot], ((ga / C::SA) & 1) ^ 1);
+              tc::mbar_wait(&a_empty[slot], a_par);
             } else
 #endif
             if (st == SRC_EMBED) {
-              tc::mbar_wait(&a_empty[slot], ((ga / C::SA) & 1) ^ 1);
+              tc::mbar_wait(&a_empty[slot], a_par);
               if (half == 0) embed_chunk<BF16>(dst, r, x, sc * C::E, pg.n_freqs, jc);
             } else if (!BF16 && st == SRC_GLOBAL && !pg.g_local) {
               // Latent chunk [128 rows x 32 columns] of the row-major source: loaded COALESCED (a warp reads 4 rows x
@@ -675,7 +695,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                 }
               }
               TC_STAMP(ptr_, 1);
-              tc::mbar_wait(&a_empty[slot], ((ga / C::SA) & 1) ^ 1);
+              tc::mbar_wait(&a_empty[slot], a_par);
               TC_STAMP(ptr_, 2);
               const uint32_t stage = dst + C::A_PLANE;
 #pragma unroll
@@ -773,10 +793,41 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                 // the values are ready in registers BEFORE the slot is claimed: the TMEM / global load latency
                 // and the activation math overlap the MMAs that are still reading the slot's previous chunk
                 if (h == 0) TC_STAMP(ptr_, 1);
-                if (h == 0) tc::mbar_wait(&a_empty[slot], ((ga / C::SA) & 1) ^ 1);
+                if (TS && ts) {
+                  // hand-over in tensor memory: this thread's 16 K-values of its row -> 16 + 8 + 8 columns of the slot
+                  const int tslot = gtm % TC_TS_SLOTS;
+                  tc::mbar_wait(&t_empty[tslot], ((gtm / TC_TS_SLOTS) & 1) ^ 1);
+                  tc::fence_after_sync();
+                  TC_STAMP(ptr_, 2);
+                  const uint32_t tdst = lane_addr + (uint32_t)(TC_TS_COL + 64 * tslot);
+#pragma unroll
+                  for (int qq = 0; qq < 2; ++qq) {
+                    uint32_t hw[8], lw[4], cw[4];
+#pragma unroll
+                    for (int i = 0; i < 8; i += 2) {
+                      const float h0 = tc::tf32_rna(v[8 * qq + i]), h1 = tc::tf32_rna(v[8 * qq + i + 1]);
+                      hw[i] = __float_as_uint(h0); hw[i + 1] = __float_as_uint(h1);
+                      __nv_bfloat162 pl = __floats2bfloat162_rn(v[8 * qq + i] - h0, v[8 * qq + i + 1] - h1);
+                      __nv_bfloat162 ph = __floats2bfloat162_rn(h0, h1);
+                      lw[i >> 1] = *reinterpret_cast<uint32_t*>(&pl); cw[i >> 1] = *reinterpret_cast<uint32_t*>(&ph);
+                    }
+                    tc::tmem_st8(tdst + (uint32_t)(16 * half + 8 * qq), hw);
+                    tc::tmem_st4(tdst + (uint32_t)(32 + 8 * half + 4 * qq), lw);
+                    tc::tmem_st4(tdst + (uint32_t)(48 + 8 * half + 4 * qq), cw);
+                  }
+                  tc::tmem_st_wait();
+                  TC_STAMP(ptr_, 3);
+                  tc::fence_before_sync();
+                  TC_STAMP(ptr_, 4);
+                  tc::mbar_arrive(&t_full[tslot]);
+                  TC_STAMP(ptr_, 5);
+                  continue;
+                }
+                if (h == 0) tc::mbar_wait(&a_empty[slot], a_par);
                 if (h == 0) TC_STAMP(ptr_, 2);
                 store_chunk32<BF16>(dst, r, 32 * h + 16 * half, v);
               }
+              if (TS && ts) continue;
             }
             TC_STAMP(ptr_, 3);
             tc::fence_proxy_async();       // generic-proxy stores -> visible to the UMMA (async proxy)
@@ -973,9 +1024,18 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
       }
     }
   } else if (warp == MMA_WARP) {
-    // =========================== MMA issuer (one thread) ===========================
-    if (lane == 0) {
-      uint32_t ga = 0, gw = 0, gd = 0;
+    // =========================== MMA issuer (whole warp walks the loop, one elected lane issues) ===========================
+    // Every operand below derives from kernel parameters, blockIdx and loop counters, so it lives in UNIFORM registers
+    // and a UTCHMMA / UTCBAR is issued straight from them (see tc::mma_ss_e); the only per-thread input, the TMEM base
+    // read from shared memory, is made uniform by a broadcast.
+    {
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t a_ring_u = __shfl_sync(0xffffffffu, a_ring_s, 0);
+      const uint32_t w_ring_u = a_ring_u + (uint32_t)C::SA * C::A_SLOT;
+      const uint32_t bar_a_full = tc::smem_u32(&a_full[0]), bar_a_empty = tc::smem_u32(&a_empty[0]);
+      const uint32_t bar_w_full = tc::smem_u32(&w_full[0]), bar_w_empty = tc::smem_u32(&w_empty[0]);
+      const uint32_t bar_t_full = tc::smem_u32(&t_full[0]), bar_t_empty = tc::smem_u32(&t_empty[0]);
+      uint32_t ga = 0, gs = 0, gt = 0, gw = 0, gd = 0;
       bool pending_drain = false;
       int pend_lo = 0, pend_hi = 0;         // TMEM columns of the accumulator still being drained to global
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -983,11 +1043,11 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
           const TcLayer& ly = pg.layers[l];
           const uint32_t idesc = tc::make_idesc(BF16 ? tc::FMT_BF16 : tc::FMT_TF32, TC_M, ly.Npad);
           const uint32_t idesc_c = tc::make_idesc(tc::FMT_BF16, TC_M, ly.Npad);        // correction plane (kind::f16)
-          const uint32_t d_tmem = tmem_base + (uint32_t)ly.tmem_col;
+          const uint32_t d_tmem = tmem_u + (uint32_t)ly.tmem_col;
           const int nch = ly.seg_chunks[0] + (ly.nseg > 1 ? ly.seg_chunks[1] : 0);
           const uint32_t w_plane = (uint32_t)ly.Npad * 128;
 #ifdef VQN_TC_TRACE
-          long long* tr = (pg.trace && blockIdx.x == 0 && tile < 4 * (long long)gridDim.x)
+          long long* tr = (pg.trace && blockIdx.x == 0 && lane == 0 && tile < 4 * (long long)gridDim.x)
                               ? pg.trace + ((tile / gridDim.x) * TC_MAX_LAYERS + l) * 4 : nullptr;
 #endif
           TC_STAMP(tr, 0);
@@ -995,63 +1055,74 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
             // a final layer is being drained to global: wait before overwriting ITS columns (other columns may go on)
             const bool hit = (ly.tmem_col < pend_hi && ly.tmem_col + ly.Npad > pend_lo) || ly.out_slot >= 0;
             if (hit) {
-              tc::mbar_wait(&drain_done, gd & 1);
-              tc::fence_after_sync();
+              tc::mbar_wait_u(tc::smem_u32(&drain_done), gd & 1);
               ++gd; pending_drain = false;
             }
           }
           uint32_t acc = 0;
           const bool wsplit = !BF16 && ly.Npad > 128;     // the two planes of a chunk are separate ring entries
-          for (int c = 0; c < nch; ++c, ++ga, ++gw) {
-            const int sa = ga % C::SA, sw = gw % C::SW;
+          for (int c = 0; c < nch; ++c, ++ga) {
+            // A side: a shared-memory slot (descriptors) or, TS, a tensor-memory slot (column addresses)
+            const bool ts = TS && ly.seg_ts[c < ly.seg_chunks[0] ? 0 : 1];
+            uint32_t a_rel;                               // barrier that hands the slot back to the producers
+            uint32_t a_addr;                              // smem address / TMEM column address of the slot
             if (c == 0) TC_STAMP(tr, 1);
-            tc::mbar_wait(&a_full[sa], (ga / C::SA) & 1);
-            tc::mbar_wait(&w_full[sw], (gw / C::SW) & 1);
+            if (ts) {
+              const uint32_t st_ = gt % TC_TS_SLOTS;
+              tc::mbar_wait_u(bar_t_full + 8u * st_, (gt / TC_TS_SLOTS) & 1);
+              a_rel = bar_t_empty + 8u * st_; a_addr = tmem_u + (uint32_t)TC_TS_COL + 64u * st_;
+              ++gt;
+            } else {
+              const uint32_t sa = gs % C::SA;
+              tc::mbar_wait_u(bar_a_full + 8u * sa, (gs / C::SA) & 1);
+              a_rel = bar_a_empty + 8u * sa; a_addr = a_ring_u + sa * C::A_SLOT;
+              ++gs;
+            }
+            uint32_t sw = gw % C::SW;
+            tc::mbar_wait_u(bar_w_full + 8u * sw, (gw / C::SW) & 1);
             tc::fence_after_sync();
             if (c == 0) TC_STAMP(tr, 2);
-            const uint32_t a_addr = tc::smem_u32(a_ring + (size_t)sa * C::A_SLOT);
-            const uint32_t w_addr = tc::smem_u32(w_ring + (size_t)sw * C::W_SLOT);
-#ifdef TC_EXP_NO_MMA
-            if (tile >= 0) { tc::mma_commit(&a_empty[sa]); tc::mma_commit(&w_empty[sw]); continue; }
-#endif
-            if (wsplit) {
-              // wide layer: the four tf32 MMAs (plane H entry), release it, then the four correction MMAs (plane C entry)
+            uint32_t w_addr = w_ring_u + sw * C::W_SLOT;
+            if (BF16) {
 #pragma unroll
               for (int s = 0; s < 4; ++s) {
-                tc::mma_ss<true>(d_tmem, tc::make_desc_sw128(a_addr + 32 * s), tc::make_desc_sw128(w_addr + 32 * s), idesc, acc);
+                tc::mma_ss_e<false>(d_tmem, tc::make_desc_sw128(a_addr + 32 * s), tc::make_desc_sw128(w_addr + 32 * s), idesc, acc);
                 acc = 1;
               }
-              tc::mma_commit(&w_empty[sw]);
-              ++gw;
-              const int sc = gw % C::SW;
-              tc::mbar_wait(&w_full[sc], (gw / C::SW) & 1);
-              tc::fence_after_sync();
-              const uint32_t c_addr = tc::smem_u32(w_ring + (size_t)sc * C::W_SLOT);
+            } else {
+              // leading products: four kind::tf32 MMAs on plane H
+              if (ts) {
 #pragma unroll
-              for (int s = 0; s < 4; ++s)
-                tc::mma_ss<false>(d_tmem, tc::make_desc_sw128(a_addr + C::A_PLANE + 32 * s),
-                                  tc::make_desc_sw128(c_addr + 32 * s), idesc_c, 1);
-              tc::mma_commit(&a_empty[sa]);
-              tc::mma_commit(&w_empty[sc]);
-              continue;
-            }
+                for (int s = 0; s < 4; ++s) { tc::mma_ts_e<true>(d_tmem, a_addr + 8u * s, tc::make_desc_sw128(w_addr + 32 * s), idesc, acc); acc = 1; }
+              } else {
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-              const uint64_t a_hi = tc::make_desc_sw128(a_addr + 32 * s);
-              const uint64_t b_hi = tc::make_desc_sw128(w_addr + 32 * s);
-              tc::mma_ss<!BF16>(d_tmem, a_hi, b_hi, idesc, acc);
-              acc = 1;
-              if (!BF16) {
-                // both correction products in ONE bf16 MMA of K = 16: [a_lo | a_hi] . [w_hi ; w_lo] (plane C)
-                const uint64_t a_c = tc::make_desc_sw128(a_addr + C::A_PLANE + 32 * s);
-                const uint64_t b_c = tc::make_desc_sw128(w_addr + w_plane + 32 * s);
-                tc::mma_ss<false>(d_tmem, a_c, b_c, idesc_c, 1);
+                for (int s = 0; s < 4; ++s) { tc::mma_ss_e<true>(d_tmem, tc::make_desc_sw128(a_addr + 32 * s), tc::make_desc_sw128(w_addr + 32 * s), idesc, acc); acc = 1; }
+              }
+              if (wsplit) {
+                // wide layer: plane C is the next ring entry; plane H's entry is released by its own commit
+                tc::mma_commit_e(bar_w_empty + 8u * sw);
+                ++gw;
+                sw = gw % C::SW;
+                tc::mbar_wait_u(bar_w_full + 8u * sw, (gw / C::SW) & 1);
+                tc::fence_after_sync();
+                w_addr = w_ring_u + sw * C::W_SLOT;
+              } else {
+                w_addr += w_plane;
+              }
+              // both correction products in ONE bf16 MMA of K = 16 per step: [a_lo | a_hi] . [w_hi ; w_lo] (plane C)
+              if (ts) {
+#pragma unroll
+                for (int s = 0; s < 4; ++s) tc::mma_ts_e<false>(d_tmem, a_addr + 32u + 8u * s, tc::make_desc_sw128(w_addr + 32 * s), idesc_c, 1);
+              } else {
+#pragma unroll
+                for (int s = 0; s < 4; ++s) tc::mma_ss_e<false>(d_tmem, tc::make_desc_sw128(a_addr + C::A_PLANE + 32 * s), tc::make_desc_sw128(w_addr + 32 * s), idesc_c, 1);
               }
             }
-            tc::mma_commit(&a_empty[sa]);       // slots are free once these MMAs have read them
-            tc::mma_commit(&w_empty[sw]);
+            tc::mma_commit_e(a_rel);              // slots are free once these MMAs have read them
+            tc::mma_commit_e(bar_w_empty + 8u * sw);
+            ++gw;
           }
-          tc::mma_commit(&acc_full);            // layer complete -> epilogue warps may drain it
+          tc::mma_commit_e(tc::smem_u32(&acc_full));   // layer complete -> epilogue warps may drain it
           TC_STAMP(tr, 3);
           if (ly.out_slot >= 0) { pending_drain = true; pend_lo = ly.tmem_col; pend_hi = ly.tmem_col + ly.Npad; }
         }
@@ -1153,10 +1224,80 @@ static bool tc_append_net(TcBuilder& B, vqn_net* net, TcPack* tp, int first_src,
   return true;
 }
 
+// Accumulator columns of a chain of layers (each draining the previous one) chosen so that as many layers as possible
+// stay below TC_TS_COL: walk BACKWARDS from the last layer (a wide final layer may take the top of TMEM), giving every
+// layer the lowest 128-aligned region that is disjoint from its consumer's.  Falls back to the ping-pong default.
+static void tc_plan_columns(TcProgram& pg) {
+  const int L = pg.n_layers;
+  int col[TC_MAX_LAYERS];
+  int next_lo = -1, next_hi = -1;
+  for (int l = L - 1; l >= 0; --l) {
+    const int N = pg.layers[l].Npad;
+    int pick = -1;
+    for (int c = 0; c + N <= 512 && pick < 0; c += 128) {
+      if (l < L - 1 && c + N > TC_TS_COL) break;                        // only the last layer may reach into the slots
+      if (next_lo >= 0 && c < next_hi && c + N > next_lo) continue;     // overlaps its consumer's accumulator
+      pick = c;
+    }
+    if (l == L - 1 && N > 128) pick = 512 - N >= 0 && (512 - N) % 128 == 0 ? 512 - N : pick;   // keep [0, 384) for the others
+    if (pick < 0) return;                                               // no plan: keep the defaults
+    col[l] = pick; next_lo = pick; next_hi = pick + N;
+  }
+  for (int l = 0; l < L; ++l) pg.layers[l].tmem_col = col[l];
+}
+
 // diagnostic knob (not part of include/vqnerf_b200.h): device buffer of >= 4 * TC_MAX_LAYERS * 4 + 8 * 96 int64 (= 1088) that receives the
 // MMA-thread time stamps of the next launches (NULL: off)
 static long long* g_tc_trace = nullptr;
 extern "C" void vqn_debug_tc_trace(long long* dev_buf) { g_tc_trace = dev_buf; }
+
+// Which segments hand their A chunks over in tensor memory (TC_TS_COL).  A DRAIN segment, or a GLOBAL segment reading the
+// per-CTA latent scratch, of a layer whose accumulator AND whose source accumulator lie below TC_TS_COL.  A layer whose
+// accumulator reaches into the slot columns must (a) start with a DRAIN segment -- its first MMA is then issued after every
+// earlier MMA (TS reads included) has completed -- and (b) be a final layer drained behind a CTA-wide barrier (the latent
+// scratch, or a wide output: see the end of the final drain), so that no producer writes a slot while another group still
+// reads those columns.  Anything else: no TS in this program.
+static bool tc_plan_ts(TcProgram& pg) {
+  static int env = -1;
+  if (env < 0) { const char* e = getenv("VQN_TC_TS"); env = e ? atoi(e) : 1; }
+  for (int l = 0; l < pg.n_layers; ++l) pg.layers[l].seg_ts[0] = pg.layers[l].seg_ts[1] = 0;
+  if (!env) return false;
+  for (int l = 0; l < pg.n_layers; ++l) {
+    const TcLayer& ly = pg.layers[l];
+    if (ly.tmem_col + ly.Npad <= TC_TS_COL) continue;
+    const bool wide_out = ly.out_slot >= 0 && (ly.N % 32 == 0) && (pg.out_stride[ly.out_slot] % 4 == 0);
+    if (!(ly.seg_type[0] == SRC_DRAIN && wide_out)) return false;
+  }
+  bool any = false;
+  for (int l = 0; l < pg.n_layers; ++l) {
+    TcLayer& ly = pg.layers[l];
+    if (ly.tmem_col + ly.Npad > TC_TS_COL) continue;
+    for (int sg = 0; sg < ly.nseg; ++sg) {
+      const int st = ly.seg_type[sg];
+      if (st == SRC_DRAIN) {
+        if (l == 0) continue;
+        const TcLayer& pl = pg.layers[l - 1];
+        if (pl.tmem_col + pl.Npad > TC_TS_COL) continue;
+        ly.seg_ts[sg] = 1; any = true;
+      } else if (st == SRC_GLOBAL && pg.g_local && env != 3) {
+        ly.seg_ts[sg] = 1; any = true;
+      }
+    }
+  }
+  if (env == 2) {            // experiment: the TS instantiation with every chunk in shared memory
+    for (int l = 0; l < pg.n_layers; ++l) pg.layers[l].seg_ts[0] = pg.layers[l].seg_ts[1] = 0;
+    return true;
+  }
+  if (env >= 4) {            // experiment: TS only for layers of width <= 128 (4) / only for wider layers (5)
+    any = false;
+    for (int l = 0; l < pg.n_layers; ++l)
+      for (int sg = 0; sg < 2; ++sg) {
+        if ((env == 4) != (pg.layers[l].Npad <= 128)) pg.layers[l].seg_ts[sg] = 0;
+        any = any || pg.layers[l].seg_ts[sg];
+      }
+  }
+  return any;
+}
 
 static int tc_launch(vqn_ctx* ctx, TcProgram& pg, int precision, cudaStream_t s) {
   pg.nonfinite = ctx->nonfinite_flag;
@@ -1186,17 +1327,22 @@ static int tc_launch(vqn_ctx* ctx, TcProgram& pg, int precision, cudaStream_t s)
   const int tile_pts = pg.jet ? TC_M / 4 : TC_M;
   long long tiles = (pg.n + tile_pts - 1) / tile_pts;
   int blocks = (int)(tiles < (long long)ctx->sm_count ? tiles : (long long)ctx->sm_count);
-#define TC_LAUNCH(BF, JT)                                                                                              \
+#define TC_LAUNCH(BF, JT, TSV)                                                                                         \
   do {                                                                                                                 \
     size_t smem = TcCfg<BF>::SMEM;                                                                                     \
-    VQN_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<BF, JT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    mlp_tc_kernel<BF, JT><<<blocks, TcCfg<BF>::THREADS, smem, s>>>(pg);                                                \
+    VQN_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<BF, JT, TSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    mlp_tc_kernel<BF, JT, TSV><<<blocks, TcCfg<BF>::THREADS, smem, s>>>(pg);                                           \
   } while (0)
   const int mode = pg.jet ? 1 : (pg.reverse ? 2 : (pg.train ? 3 : 0));
+  if (mode == 0 && precision != VQN_PREC_BF16 && tc_plan_ts(pg)) {
+    TC_LAUNCH(false, 0, true);
+    VQN_LAUNCHED(ctx);
+    return VQN_OK;
+  }
   if (precision == VQN_PREC_BF16) {
-    if (mode == 1) TC_LAUNCH(true, 1); else if (mode == 2) TC_LAUNCH(true, 2); else if (mode == 3) TC_LAUNCH(true, 3); else TC_LAUNCH(true, 0);
+    if (mode == 1) TC_LAUNCH(true, 1, false); else if (mode == 2) TC_LAUNCH(true, 2, false); else if (mode == 3) TC_LAUNCH(true, 3, false); else TC_LAUNCH(true, 0, false);
   } else {
-    if (mode == 1) TC_LAUNCH(false, 1); else if (mode == 2) TC_LAUNCH(false, 2); else if (mode == 3) TC_LAUNCH(false, 3); else TC_LAUNCH(false, 0);
+    if (mode == 1) TC_LAUNCH(false, 1, false); else if (mode == 2) TC_LAUNCH(false, 2, false); else if (mode == 3) TC_LAUNCH(false, 3, false); else TC_LAUNCH(false, 0, false);
   }
 #undef TC_LAUNCH
   VQN_LAUNCHED(ctx);
@@ -1229,6 +1375,7 @@ int vqn_tc_pred_enc_at(vqn_ctx* ctx, vqn_net* fe, vqn_net* bn, int n_freqs, cons
   B.pg.outs[0] = z; B.pg.out_stride[0] = bn->desc.widths[bn->n_layers - 1];
   bool ok = tc_append_net(B, fe, t0, SRC_EMBED, -1, 1.f, 0.f) && tc_append_net(B, bn, t1, SRC_DRAIN, 0, 1.f, 0.f);
   if (!ok) TC_UNSUPPORTED("pred_enc_at: program does not fit the tensor-core kernel");
+  tc_plan_columns(B.pg);
   return tc_launch(ctx, B.pg, precision, s);
 }
 
@@ -1296,6 +1443,7 @@ int vqn_tc_mlp_main(vqn_ctx* ctx, vqn_net* fe, vqn_net* bn, vqn_net* diff, vqn_n
   B.pg.gsrc = zscratch; B.pg.g_dim = z_dim; B.pg.g_local = 1; B.pg.local_slot = 3; B.pg.out_dup = z_out;
   B.pg.outs[3] = zscratch; B.pg.out_stride[3] = z_dim;
   bool ok = tc_append_net(B, fe, t0, SRC_EMBED, -1, 1.f, 0.f) && tc_append_net(B, bn, t1, SRC_DRAIN, 3, 1.f, 0.f);
+  if (ok) tc_plan_columns(B.pg);
   for (int h = 0; ok && h < 3; ++h) {
     TcPack* tp;
     rc = tc_pack_get(nets[h], precision, s, &tp);

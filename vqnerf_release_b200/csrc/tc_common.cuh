@@ -68,6 +68,48 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
   }
 }
 
+// ---- warp-uniform issue: the WHOLE warp walks the issue loop and one elected lane issues.  With the loop inside
+// `if (lane == 0)` every operand lives in a per-thread register and the compiler wraps each UTCHMMA / UTCBAR in an election
+// loop (ELECT, seven R2UR.BROADCAST, BRA.U.ANY: ~100 cycles per instruction -- more than the 64 tensor cycles of an
+// M = 128, N = 128 MMA); with uniform control flow the descriptors are computed in uniform registers and an MMA is a
+// handful of uniform-datapath instructions.  elect.sync with a full mask always names the same lane, so the commits
+// below track the MMAs issued here. ----
+template <bool TF32>
+__device__ __forceinline__ void mma_ss_e(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  if (TF32) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  }
+}
+template <bool TF32>
+__device__ __forceinline__ void mma_ts_e(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  if (TF32) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  }
+}
+__device__ __forceinline__ void mma_commit_e(uint32_t bar_smem_addr) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar_smem_addr) : "memory");
+}
+
 // all previously issued MMAs of this thread -> one arrival on the mbarrier when they complete
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -135,6 +177,10 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- mbarrier ----
@@ -160,6 +206,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
     if (spins > (1u << 26)) { asm volatile("trap;"); }
   }
+}
+
+// whole-warp wait on a barrier given by its 32-bit shared address (uniform operands, see mma_ss_e); ends with the
+// tcgen05 fence every consumer of tensor-core results needs
+__device__ __forceinline__ void mbar_wait_u(uint32_t bar_smem_addr, uint32_t parity) {
+  for (uint32_t spins = 0;; ++spins) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar_smem_addr), "r"(parity) : "memory");
+    if (__all_sync(0xffffffffu, ok != 0)) break;
+    if (spins > (1u << 26)) { asm volatile("trap;"); }
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
 // 1-D bulk copy global -> shared (TMA engine, no tensor map), completion counted on `bar` in bytes
