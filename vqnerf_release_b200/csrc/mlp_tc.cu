@@ -453,7 +453,7 @@ __device__ __forceinline__ void store_chunk32(uint32_t slot, int r, int j0, cons
     for (int qq = 0; qq < 2; ++qq) {            // 8 K values per step
       float h[8], l[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { h[i] = tc::tf32_rna(v[8 * qq + i]); l[i] = v[8 * qq + i] - h[i]; }
+      for (int i = 0; i < 8; ++i) { h[i] = tc::tf32_rna_fast(v[8 * qq + i]); l[i] = v[8 * qq + i] - h[i]; }
       const uint32_t c0 = (uint32_t)(j0 / 4 + 2 * qq);
       tc::sts128(row + (((c0) ^ rx) << 4), make_float4(h[0], h[1], h[2], h[3]));
       tc::sts128(row + (((c0 + 1) ^ rx) << 4), make_float4(h[4], h[5], h[6], h[7]));
@@ -805,7 +805,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                     uint32_t hw[8], lw[4], cw[4];
 #pragma unroll
                     for (int i = 0; i < 8; i += 2) {
-                      const float h0 = tc::tf32_rna(v[8 * qq + i]), h1 = tc::tf32_rna(v[8 * qq + i + 1]);
+                      const float h0 = tc::tf32_rna_fast(v[8 * qq + i]), h1 = tc::tf32_rna_fast(v[8 * qq + i + 1]);
                       hw[i] = __float_as_uint(h0); hw[i + 1] = __float_as_uint(h1);
                       __nv_bfloat162 pl = __floats2bfloat162_rn(v[8 * qq + i] - h0, v[8 * qq + i + 1] - h1);
                       __nv_bfloat162 ph = __floats2bfloat162_rn(h0, h1);
@@ -1259,7 +1259,10 @@ extern "C" void vqn_debug_tc_trace(long long* dev_buf) { g_tc_trace = dev_buf; }
 // reads those columns.  Anything else: no TS in this program.
 static bool tc_plan_ts(TcProgram& pg) {
   static int env = -1;
-  if (env < 0) { const char* e = getenv("VQN_TC_TS"); env = e ? atoi(e) : 1; }
+  // opt-in (VQN_TC_TS=1): measured 2.72 ms against 2.63 ms for the shared-memory hand-over on mlp_main -- once the MMA
+  // issue path was fixed the kernel turned out to be bound by the producers' instruction count, not by the smem port,
+  // and two TMEM slots are a shallower ring than three shared-memory slots
+  if (env < 0) { const char* e = getenv("VQN_TC_TS"); env = e ? atoi(e) : 0; }
   for (int l = 0; l < pg.n_layers; ++l) pg.layers[l].seg_ts[0] = pg.layers[l].seg_ts[1] = 0;
   if (!env) return false;
   for (int l = 0; l < pg.n_layers; ++l) {

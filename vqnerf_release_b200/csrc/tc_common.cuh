@@ -194,11 +194,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// The suspend-time hint lets the hardware park the warp until the phase completes (or the hint expires) instead of
+// returning at once: without it the waiting warps of mlp_tc_kernel spent 29 % of the kernel's issue slots on
+// try_wait / branch / counter instructions (ncu source page, profiles/r2c_*), slots the working warps were waiting for.
+#define TC_MBAR_SUSPEND_NS 0x989680
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(TC_MBAR_SUSPEND_NS) : "memory");
   return ok != 0;
 }
 // Bounded wait: a barrier that never completes (a protocol bug) traps instead of hanging the GPU.
@@ -214,8 +218,8 @@ __device__ __forceinline__ void mbar_wait_u(uint32_t bar_smem_addr, uint32_t par
   for (uint32_t spins = 0;; ++spins) {
     uint32_t ok;
     asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar_smem_addr), "r"(parity) : "memory");
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar_smem_addr), "r"(parity), "r"(TC_MBAR_SUSPEND_NS) : "memory");
     if (__all_sync(0xffffffffu, ok != 0)) break;
     if (spins > (1u << 26)) { asm volatile("trap;"); }
   }
@@ -252,6 +256,13 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 // byte offset of 16-byte chunk `c16` of row `r` inside a swizzled [rows x 128 B] tile
 __device__ __host__ __forceinline__ uint32_t sw128_off(uint32_t r, uint32_t c16) {
   return r * 128u + ((c16 ^ (r & 7u)) << 4);
+}
+
+// the same rounding for finite values in two integer instructions (add half an ulp of the 10-bit mantissa to the
+// magnitude, clear the low 13 bits: ties away from zero like cvt.rna); cvt.rna.tf32 itself compiles to four (it also
+// special-cases Inf / NaN), and the producers of the tensor-core kernels split 4096 values per chunk
+__device__ __forceinline__ float tf32_rna_fast(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
 // round-to-nearest tf32 (low 13 mantissa bits zero afterwards); hi = rna(x), lo = rna(x - hi) is the 3xTF32 split
