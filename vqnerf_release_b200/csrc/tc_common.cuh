@@ -226,6 +226,9 @@ __device__ __forceinline__ void mbar_wait_u(uint32_t bar_smem_addr, uint32_t par
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
+__device__ __forceinline__ void mbar_wait_u(uint64_t* bar, uint32_t parity) { mbar_wait_u(smem_u32(bar), parity); }
+__device__ __forceinline__ void mma_commit_e(uint64_t* bar) { mma_commit_e(smem_u32(bar)); }
+
 // 1-D bulk copy global -> shared (TMA engine, no tensor map), completion counted on `bar` in bytes
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

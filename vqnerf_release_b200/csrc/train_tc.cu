@@ -191,26 +191,27 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(const __grid_co
     }
     tc::fence_before_sync();
   } else {
-    if (lane == 0) {
+    {   // whole warp walks the loop, one elected lane issues (uniform operands: see tc::mma_ss_e)
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc = tc::make_idesc(tc::FMT_TF32, DT_M, npad);
       const uint32_t idesc_c = tc::make_idesc(tc::FMT_BF16, DT_M, npad);
       uint32_t acc = 0;
       for (int c = 0; c < nch; ++c) {
         const int slot = c & 1;
-        tc::mbar_wait(&full[slot], ((uint32_t)c / DT_STAGES) & 1u);
+        tc::mbar_wait_u(&full[slot], ((uint32_t)c / DT_STAGES) & 1u);
         tc::fence_after_sync();
         const uint32_t a_addr = tc::smem_u32(smem + (size_t)slot * DT_SLOT);
         const uint32_t b_addr = a_addr + DT_OPERAND;
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-          tc::mma_ss<true>(tmem_base, tc::make_desc_sw128(a_addr + 32 * s), tc::make_desc_sw128(b_addr + 32 * s), idesc, acc);
+          tc::mma_ss_e<true>(tmem_u, tc::make_desc_sw128(a_addr + 32 * s), tc::make_desc_sw128(b_addr + 32 * s), idesc, acc);
           acc = 1;
-          tc::mma_ss<false>(tmem_base, tc::make_desc_sw128(a_addr + DT_PLANE + 32 * s),
+          tc::mma_ss_e<false>(tmem_u, tc::make_desc_sw128(a_addr + DT_PLANE + 32 * s),
                             tc::make_desc_sw128(b_addr + DT_PLANE + 32 * s), idesc_c, 1);
         }
-        tc::mma_commit(&empty[slot]);
+        tc::mma_commit_e(&empty[slot]);
       }
-      tc::mma_commit(&acc_full);
+      tc::mma_commit_e(&acc_full);
     }
     __syncwarp();
   }

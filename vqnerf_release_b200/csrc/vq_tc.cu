@@ -377,7 +377,8 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
       if (ok) p.idx_out[row] = (long long)best;
     }
   } else if (warp == MMA_WARP) {
-    if (lane == 0) {
+    {   // whole warp walks the loop, one elected lane issues (uniform operands: see tc::mma_ss_e)
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       uint32_t ga = 0, gk = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int b = 0; b < nb; ++b, ++gk) {
@@ -385,32 +386,32 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vq_tc_kernel(const __grid_const
           const int nblk = min(256, p.K - 256 * b), npad = (nblk + 15) / 16 * 16;
           const uint32_t idesc = tc::make_idesc(tc::FMT_TF32, VT_M, npad);
           const uint32_t idesc_c = tc::make_idesc(tc::FMT_BF16, VT_M, npad);
-          const uint32_t d_tmem = tmem_base + (uint32_t)(region * 256);
+          const uint32_t d_tmem = tmem_u + (uint32_t)(region * 256);
           const uint32_t w_plane = (uint32_t)npad * 128;
           if (gk >= 2) {                                          // the drain of the layer that used this region
-            tc::mbar_wait(&drain_done[region], ((gk - 2) >> 1) & 1u);
+            tc::mbar_wait_u(&drain_done[region], ((gk - 2) >> 1) & 1u);
             tc::fence_after_sync();
           }
           uint32_t acc = 0;
           for (int c = 0; c < VT_KCHUNKS; ++c, ++ga) {
             const int s_ = (int)(ga % VT_STAGES);
             const int ws = (int)(ga % NWS);
-            tc::mbar_wait(&a_full[s_], (ga / VT_STAGES) & 1u);
-            tc::mbar_wait(&w_full[ws], (ga / NWS) & 1u);
+            tc::mbar_wait_u(&a_full[s_], (ga / VT_STAGES) & 1u);
+            tc::mbar_wait_u(&w_full[ws], (ga / NWS) & 1u);
             tc::fence_after_sync();
             const uint32_t a_addr = tc::smem_u32(a_ring + (size_t)s_ * VT_A_SLOT);
             const uint32_t w_addr = tc::smem_u32(w_ring + (size_t)ws * W_SLOT);
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
-              tc::mma_ss<true>(d_tmem, tc::make_desc_sw128(a_addr + 32 * s), tc::make_desc_sw128(w_addr + 32 * s), idesc, acc);
+              tc::mma_ss_e<true>(d_tmem, tc::make_desc_sw128(a_addr + 32 * s), tc::make_desc_sw128(w_addr + 32 * s), idesc, acc);
               acc = 1;
-              tc::mma_ss<false>(d_tmem, tc::make_desc_sw128(a_addr + VT_A_PLANE + 32 * s),
+              tc::mma_ss_e<false>(d_tmem, tc::make_desc_sw128(a_addr + VT_A_PLANE + 32 * s),
                                 tc::make_desc_sw128(w_addr + w_plane + 32 * s), idesc_c, 1);
             }
-            tc::mma_commit(&a_empty[s_]);
-            tc::mma_commit(&w_empty[ws]);
+            tc::mma_commit_e(&a_empty[s_]);
+            tc::mma_commit_e(&w_empty[ws]);
           }
-          tc::mma_commit(&acc_full[region]);
+          tc::mma_commit_e(&acc_full[region]);
         }
       }
     }
@@ -611,24 +612,25 @@ __global__ void __launch_bounds__(VT_THREADS_BIG, 1) vq_tc_big_kernel(const __gr
     }
     if (!PAIR && pend_tile >= 0) drain(pend_tile, pend_l, pend_k);
   } else if (warp == MMA_WARP) {
-    if (lane == 0) {
+    {   // whole warp walks the loop, one elected lane issues (uniform operands: see tc::mma_ss_e)
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       uint32_t ga = 0, gk = 0, gw = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int l = 0; l < nl; ++l, ++gk) {
           if (PAIR) {
             if (gk >= 1) {                                        // both regions: the drain of the previous layer
-              tc::mbar_wait(&drain_done[0], (gk - 1) & 1u);
-              tc::mbar_wait(&drain_done[1], (gk - 1) & 1u);
+              tc::mbar_wait_u(&drain_done[0], (gk - 1) & 1u);
+              tc::mbar_wait_u(&drain_done[1], (gk - 1) & 1u);
               tc::fence_after_sync();
             }
           } else if (gk >= 2) {                                   // the drain of the layer that used this region
-            tc::mbar_wait(&drain_done[gk & 1u], ((gk - 2) >> 1) & 1u);
+            tc::mbar_wait_u(&drain_done[gk & 1u], ((gk - 2) >> 1) & 1u);
             tc::fence_after_sync();
           }
           uint32_t acc = 0;
           for (int c = 0; c < VT_KCHUNKS; ++c, ++ga) {
             const int s_ = (int)(ga % VT_STAGES);
-            tc::mbar_wait(&a_full[s_], (ga / VT_STAGES) & 1u);
+            tc::mbar_wait_u(&a_full[s_], (ga / VT_STAGES) & 1u);
             const uint32_t a_addr = tc::smem_u32(a_ring + (size_t)s_ * VT_A_SLOT);
 #pragma unroll
             for (int h2 = 0; h2 < BPL; ++h2, ++gw) {
@@ -636,27 +638,27 @@ __global__ void __launch_bounds__(VT_THREADS_BIG, 1) vq_tc_big_kernel(const __gr
               const int npad = npad_of(PAIR ? 2 * l + h2 : l);
               const uint32_t idesc = tc::make_idesc(tc::FMT_TF32, VT_M, npad);
               const uint32_t idesc_c = tc::make_idesc(tc::FMT_BF16, VT_M, npad);
-              const uint32_t d_tmem = tmem_base + (uint32_t)(region * 256);
+              const uint32_t d_tmem = tmem_u + (uint32_t)(region * 256);
               const uint32_t w_plane = (uint32_t)npad * 128;
               const int ws = (int)(gw % VT_STAGES);
-              tc::mbar_wait(&w_full[ws], (gw / VT_STAGES) & 1u);
+              tc::mbar_wait_u(&w_full[ws], (gw / VT_STAGES) & 1u);
               tc::fence_after_sync();
               const uint32_t w_addr = tc::smem_u32(w_ring + (size_t)ws * VT_W_SLOT);
               uint32_t first = acc;                               // 0 only for the first K-step of the layer's first chunk
 #pragma unroll
               for (int s = 0; s < 4; ++s) {
-                tc::mma_ss<true>(d_tmem, tc::make_desc_sw128(a_addr + 32 * s), tc::make_desc_sw128(w_addr + 32 * s), idesc, first);
+                tc::mma_ss_e<true>(d_tmem, tc::make_desc_sw128(a_addr + 32 * s), tc::make_desc_sw128(w_addr + 32 * s), idesc, first);
                 first = 1;
-                tc::mma_ss<false>(d_tmem, tc::make_desc_sw128(a_addr + VT_A_PLANE + 32 * s),
+                tc::mma_ss_e<false>(d_tmem, tc::make_desc_sw128(a_addr + VT_A_PLANE + 32 * s),
                                   tc::make_desc_sw128(w_addr + w_plane + 32 * s), idesc_c, 1);
               }
-              tc::mma_commit(&w_empty[ws]);
+              tc::mma_commit_e(&w_empty[ws]);
             }
             acc = 1;
-            tc::mma_commit(&a_empty[s_]);
+            tc::mma_commit_e(&a_empty[s_]);
           }
-          if (PAIR) { tc::mma_commit(&acc_full[0]); tc::mma_commit(&acc_full[1]); }
-          else tc::mma_commit(&acc_full[gk & 1u]);
+          if (PAIR) { tc::mma_commit_e(&acc_full[0]); tc::mma_commit_e(&acc_full[1]); }
+          else tc::mma_commit_e(&acc_full[gk & 1u]);
         }
       }
     }
