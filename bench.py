@@ -340,11 +340,21 @@ def bench_neus_scan(dev, hbm_peak):
         sdf_f = torch.rand((b, 128), generator=g, device=dev) - 0.5
 
         def run():
+            # the launch sequence of NeuSRenderer.render (neus/renderer.py): up_sample, three fused steps (cat_z_vals +
+            # up_sample; the last one + the final cat_z_vals + mid points), compositing
             z, sdf = z0, sdf0
-            for i in range(4):
-                nz = abi.neus_up_sample(rays_o, rays_d, z, sdf, 1.0, 16, 64 * 2 ** i)
-                z, sdf = abi.neus_cat_z_vals(z, nz, sdf, new_sdf[i])
-            return abi.neus_composite(rays_o, rays_d, z, sdf_f, grads, cols, 300.0, 1.0, 2.0 / 64, 1.0)
+            nz, _ = abi.neus_up_sample_pts(rays_o, rays_d, z, sdf, 1.0, 16, 64)
+            for i in range(3):
+                o = abi.neus_scan_step(rays_o, rays_d, z, nz, sdf, new_sdf[i], 1.0, 16, 64 * 2 ** (i + 1),
+                                       final_merge=(i == 2), sample_dist=2.0 / 64, want_merged=(i < 2))
+                if i < 2:
+                    z, sdf, nz = o['z'], o['sdf'], o['new_z']
+            return abi.neus_composite(rays_o, rays_d, o['z_final'], sdf_f, grads, cols, 300.0, 1.0, 2.0 / 64, 1.0)
+
+        ctx = abi._ctx(rays_o)
+        l0 = ctx.launch_count()
+        run()
+        n_launch = ctx.launch_count() - l0
 
         for _ in range(3):
             run()
@@ -357,12 +367,15 @@ def bench_neus_scan(dev, hbm_peak):
         e1.record()
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1) / reps
-        # algorithmic bytes: composite B*S*(4+4+12+12) in + B*(3+3+1+S)*4 out; up-sample steps read z,sdf and write z,sdf
+        # algorithmic bytes: composite B*S*(4+4+12+12) in + B*(3+3+1+S)*4 out; every sampling step reads z, sdf
+        # (+ the 16 new z / sdf) and writes the merged z, sdf, 16 new z and their 48 B positions; the last one writes the
+        # final z and the 2 x 12 B mid points / directions per sample instead of a merged row
         comp = b * 128 * 32 + b * (7 + 128) * 4
-        ups = sum(b * (s * 8 + 16 * 4 + (s + 16) * 8 + 16 * 4) for s in (64, 80, 96, 112))
+        ups = b * (64 * 8 + 16 * 16) + sum(b * ((s + 16) * 8 + (s + 32) * 8 + 16 * 16) for s in (64, 80)) + \
+            b * ((96 + 16) * 8 + 128 * 4 + 128 * 24)
         out['rays_%d' % b] = {'ms': ms, 'rays_per_s': b / (ms * 1e-3), 'samples_per_s': b * 128 / (ms * 1e-3),
                               'gbs': (comp + ups) / (ms * 1e-3) / 1e9, 'hbm_frac': (comp + ups) / (ms * 1e-3) / 1e9 / hbm_peak,
-                              'launches': 9}
+                              'launches': int(n_launch)}
     return out
 
 

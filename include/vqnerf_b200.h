@@ -356,6 +356,26 @@ int vqn_neus_cat_z_vals(vqn_ctx* ctx, const float* z_vals, const float* new_z, c
                         const float* new_sdf, int64_t n_rays, int n_samples, int n_importance,
                         float* z_out, float* sdf_out, vqn_stream stream);
 
+/* vqn_neus_up_sample that also writes the positions of the new samples, pts_out[B,n_importance,3] = o + d * z_sample
+ * (renderer.py:184, the input of the next SDF call); pts_out may be NULL. */
+int vqn_neus_up_sample_pts(vqn_ctx* ctx, const float* rays_o, const float* rays_d, const float* z_vals,
+                           const float* sdf, int64_t n_rays, int n_samples, float r_limit,
+                           int n_importance, float inv_s, float* z_samples, float* pts_out, vqn_stream stream);
+
+/* One hierarchical-sampling step of NeuSRenderer.render (renderer.py:343-366) in ONE launch: cat_z_vals of step i
+ * (z_vals[B,S] + new_z[B,I] with sdf[B,S] + new_sdf[B,I] -> z_out / sdf_out [B,S+I], may both be NULL), then up_sample of
+ * step i+1 on the merged row (n_importance new samples at inv_s -> new_z_out[B,n_importance] and their positions
+ * pts_out[B,n_importance,3], either may be NULL), and with final_merge != 0 the last cat_z_vals (last=True: no SDF) and
+ * render_core's mid points: z_final[B,S+I+n_importance], mid_pts / mid_dirs [B,S+I+n_importance,3] (:203-216).
+ * Bit-identical to vqn_neus_cat_z_vals + vqn_neus_up_sample (+ vqn_neus_cat_z_vals + vqn_neus_mid_points). */
+typedef struct vqn_neus_step_args {
+  const float* rays_o; const float* rays_d; const float* z_vals; const float* new_z; const float* sdf; const float* new_sdf;
+  int64_t n_rays; int32_t n_samples; int32_t n_new; int32_t n_importance; int32_t final_merge;
+  float r_limit, inv_s, sample_dist, reserved;
+  float* z_out; float* sdf_out; float* new_z_out; float* pts_out; float* z_final; float* mid_pts; float* mid_dirs;
+} vqn_neus_step_args;
+int vqn_neus_scan_step(vqn_ctx* ctx, const vqn_neus_step_args* args, vqn_stream stream);
+
 /* NeuSRenderer.render_core compositing half (:229-282), n_outside == 0:
  *   inputs per sample: sdf[B,S], gradients[B,S,3], sampled_color[B,S,3], z_vals[B,S]; per ray rays_o,
  *   rays_d; scalars inv_s (already clipped to [1e-6,1e6]), cos_anneal_ratio, sample_dist, radius,

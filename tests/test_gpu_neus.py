@@ -131,3 +131,36 @@ def test_renderer_mirror_runs_end_to_end(cuda_dev):
     assert float((surf_r - 0.5).abs().max()) < 0.02         # rays that hit the sphere land on its surface
     with pytest.raises(NotImplementedError):
         NeuSRenderer(None, Sdf(), dev_net, col_net, 64, 64, 32, 4, 0.0)
+
+
+@pytest.mark.parametrize('n_rays,s,i,i2', [(1, 2, 1, 1), (7, 64, 16, 16), (513, 80, 16, 16), (300, 96, 16, 16), (33, 37, 5, 9)])
+def test_fused_scan_steps_equal_separate_kernels(cuda_dev, n_rays, s, i, i2):
+    """neus_scan_step (cat_z_vals + up_sample [+ last cat_z_vals + mid points] in one launch) == the separate kernels, bit
+    for bit -- the separate kernels are the ones pinned against the reference's vectors above."""
+    from vqnerf_release_b200 import abi
+    g = torch.Generator(device='cpu').manual_seed(n_rays * 1000 + s)
+    r = lambda *sh: torch.rand(sh, generator=g)
+    rays_o = (r(n_rays, 3) - 0.5).to(cuda_dev)
+    rays_d = torch.nn.functional.normalize(r(n_rays, 3) - 0.5, dim=1).to(cuda_dev)
+    z = torch.sort(r(n_rays, s) * 2 + 0.5, dim=1)[0]
+    z[:, 1::7] = z[:, 0::7][:, :z[:, 1::7].shape[1]]              # exact ties: the stable order matters
+    z = torch.sort(z, dim=1)[0].to(cuda_dev)
+    new_z = (r(n_rays, i) * 2 + 0.5).to(cuda_dev)
+    new_z[:, 0] = z[:, 0]                                          # a tie between the two lists
+    sdf, new_sdf = (r(n_rays, s) - 0.4).to(cuda_dev), (r(n_rays, i) - 0.4).to(cuda_dev)
+    radius, inv_s, sd = 1.0, 128.0, 0.03
+    z_ref, sdf_ref = abi.neus_cat_z_vals(z, new_z, sdf, new_sdf)
+    nz_ref = abi.neus_up_sample(rays_o, rays_d, z_ref, sdf_ref, radius, i2, inv_s)
+    o = abi.neus_scan_step(rays_o, rays_d, z, new_z, sdf, new_sdf, radius, i2, inv_s)
+    assert torch.equal(o['z'], z_ref) and torch.equal(o['sdf'], sdf_ref) and torch.equal(o['new_z'], nz_ref)
+    pts_ref = rays_o[:, None, :] + rays_d[:, None, :] * nz_ref[..., None]
+    assert float((o['pts'] - pts_ref).abs().max()) < 1e-6           # (fma contraction differs from torch's mul + add)
+    nz2, pts2 = abi.neus_up_sample_pts(rays_o, rays_d, z_ref, sdf_ref, radius, i2, inv_s)
+    assert torch.equal(nz2, nz_ref) and torch.equal(pts2, o['pts'])
+    # last step: + cat_z_vals(last=True) + mid points
+    zf_ref, _ = abi.neus_cat_z_vals(z_ref, nz_ref)
+    pm_ref, dm_ref = abi.neus_mid_points(rays_o, rays_d, zf_ref, sd)
+    f = abi.neus_scan_step(rays_o, rays_d, z, new_z, sdf, new_sdf, radius, i2, inv_s, final_merge=True, sample_dist=sd,
+                           want_merged=False)
+    assert torch.equal(f['z_final'], zf_ref)
+    assert torch.equal(f['mid_pts'], pm_ref) and torch.equal(f['mid_dirs'], dm_ref)

@@ -56,6 +56,16 @@ class NeusCompositeArgs(C.Structure):
                 ('grad_err_sums', C.c_void_p)]
 
 
+class NeusStepArgs(C.Structure):
+    _fields_ = [('rays_o', C.c_void_p), ('rays_d', C.c_void_p), ('z_vals', C.c_void_p), ('new_z', C.c_void_p),
+                ('sdf', C.c_void_p), ('new_sdf', C.c_void_p),
+                ('n_rays', C.c_int64), ('n_samples', C.c_int32), ('n_new', C.c_int32), ('n_importance', C.c_int32),
+                ('final_merge', C.c_int32),
+                ('r_limit', C.c_float), ('inv_s', C.c_float), ('sample_dist', C.c_float), ('reserved', C.c_float),
+                ('z_out', C.c_void_p), ('sdf_out', C.c_void_p), ('new_z_out', C.c_void_p), ('pts_out', C.c_void_p),
+                ('z_final', C.c_void_p), ('mid_pts', C.c_void_p), ('mid_dirs', C.c_void_p)]
+
+
 _P, _I, _L, _F, _D = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 
 # name -> (restype, argtypes); every symbol declared in include/vqnerf_b200.h
@@ -95,6 +105,8 @@ SIGNATURES = {
     'vqn_compact_mask': (_I, [_P, _P, _L, _P, _P, _P, _P]),
     'vqn_scatter_rows': (_I, [_P, _P, _P, _P, _L, _I, _P, _P]),
     'vqn_neus_up_sample': (_I, [_P, _P, _P, _P, _P, _L, _I, _F, _I, _F, _P, _P]),
+    'vqn_neus_up_sample_pts': (_I, [_P, _P, _P, _P, _P, _L, _I, _F, _I, _F, _P, _P, _P]),
+    'vqn_neus_scan_step': (_I, [_P, C.POINTER(NeusStepArgs), _P]),
     'vqn_neus_cat_z_vals': (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _P, _P, _P]),
     'vqn_neus_composite': (_I, [_P, C.POINTER(NeusCompositeArgs), _P]),
     'vqn_neus_mid_points': (_I, [_P, _P, _P, _P, _L, _I, _F, _P, _P, _P]),

@@ -456,6 +456,55 @@ def neus_up_sample(rays_o, rays_d, z_vals, sdf, r_limit, n_importance, inv_s):
     return out
 
 
+def neus_up_sample_pts(rays_o, rays_d, z_vals, sdf, r_limit, n_importance, inv_s):
+    """up_sample + the positions o + d z of the new samples (the next SDF call's input): (new_z [B,I], pts [B,I,3])."""
+    rays_o, rays_d, z_vals, sdf = map(_f, (rays_o, rays_d, z_vals, sdf))
+    b, s = z_vals.shape
+    sdf = sdf.reshape(b, s)
+    out = torch.empty((b, n_importance), dtype=F32, device=z_vals.device)
+    pts = torch.empty((b, n_importance, 3), dtype=F32, device=z_vals.device)
+    c = _ctx(z_vals)
+    L.check(c.lib.vqn_neus_up_sample_pts(c.handle, L.ptr(rays_o), L.ptr(rays_d), L.ptr(z_vals), L.ptr(sdf), b, s,
+                                         float(r_limit), int(n_importance), float(inv_s), L.ptr(out), L.ptr(pts),
+                                         L.stream_ptr(z_vals.device)))
+    return out, pts
+
+
+def neus_scan_step(rays_o, rays_d, z_vals, new_z, sdf, new_sdf, r_limit, n_importance, inv_s, final_merge=False,
+                   sample_dist=0.0, want_merged=True, want_dirs=True):
+    """One hierarchical-sampling step in one launch: cat_z_vals(z_vals, new_z, sdf, new_sdf) -> up_sample of the next
+    step on the merged row [-> the last cat_z_vals and render_core's mid points when final_merge].  Returns a dict with
+    'z', 'sdf' (merged, when want_merged), 'new_z', 'pts' (not final) or 'z_final', 'mid_pts', 'mid_dirs' (final)."""
+    rays_o, rays_d, z_vals, new_z = map(_f, (rays_o, rays_d, z_vals, new_z))
+    b, s = z_vals.shape
+    i = new_z.shape[1]
+    dev = z_vals.device
+    sdf, new_sdf = _f(sdf).reshape(b, s), _f(new_sdf).reshape(b, i)
+    a = L.NeusStepArgs()
+    a.rays_o, a.rays_d, a.z_vals, a.new_z = rays_o.data_ptr(), rays_d.data_ptr(), z_vals.data_ptr(), new_z.data_ptr()
+    a.sdf, a.new_sdf = sdf.data_ptr(), new_sdf.data_ptr()
+    a.n_rays, a.n_samples, a.n_new, a.n_importance, a.final_merge = b, s, i, int(n_importance), int(bool(final_merge))
+    a.r_limit, a.inv_s, a.sample_dist = float(r_limit), float(inv_s), float(sample_dist)
+    out = {}
+    e = lambda *shape: torch.empty(shape, dtype=F32, device=dev)
+    if want_merged:
+        out['z'], out['sdf'] = e(b, s + i), e(b, s + i)
+        a.z_out, a.sdf_out = out['z'].data_ptr(), out['sdf'].data_ptr()
+    if final_merge:
+        t = s + i + int(n_importance)
+        out['z_final'], out['mid_pts'] = e(b, t), e(b, t, 3)
+        a.z_final, a.mid_pts = out['z_final'].data_ptr(), out['mid_pts'].data_ptr()
+        if want_dirs:
+            out['mid_dirs'] = e(b, t, 3)
+            a.mid_dirs = out['mid_dirs'].data_ptr()
+    else:
+        out['new_z'], out['pts'] = e(b, int(n_importance)), e(b, int(n_importance), 3)
+        a.new_z_out, a.pts_out = out['new_z'].data_ptr(), out['pts'].data_ptr()
+    c = _ctx(z_vals)
+    L.check(c.lib.vqn_neus_scan_step(c.handle, C.byref(a), L.stream_ptr(dev)))
+    return out
+
+
 def neus_cat_z_vals(z_vals, new_z, sdf=None, new_sdf=None):
     z_vals, new_z = _f(z_vals), _f(new_z)
     b, s = z_vals.shape

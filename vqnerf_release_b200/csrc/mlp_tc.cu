@@ -371,8 +371,12 @@ __device__ __forceinline__ void bias_act32_stash(float (&v)[16], const float* __
     const uint32_t hi = __float_as_uint(fmaf(d[2 * j + 1], 65535.0f, 8388608.0f));
     w[j] = __byte_perm(lo, hi, 0x5410);
   }
-  __stcg(reinterpret_cast<uint4*>(stash16), make_uint4(w[0], w[1], w[2], w[3]));
-  __stcg(reinterpret_cast<uint4*>(stash16) + 1, make_uint4(w[4], w[5], w[6], w[7]));
+  // L2 evict_last: the 74 MB of stash of the 148 CTAs are re-read within the same tile and rewritten by the next one; the
+  // output streams (1 KB of feature per point) must not push them out to HBM
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(stash16), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "l"(pol) : "memory");
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(stash16 + 4), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void stash_load16(const float* __restrict__ stash16, float (&d)[16]) {
   const uint4 a = __ldcg(reinterpret_cast<const uint4*>(stash16)), b = __ldcg(reinterpret_cast<const uint4*>(stash16) + 1);

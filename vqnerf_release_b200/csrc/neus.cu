@@ -50,10 +50,98 @@ __device__ __forceinline__ void warp_incl_cumsum4(float (&v)[NS_PER], int lane) 
 // ---------------------------------------------------------------------------------------------
 // up_sample + sample_pdf(det=True)
 // ---------------------------------------------------------------------------------------------
+// One ray's up_sample (renderer.py:131-175 + sample_pdf det=True :39-69) by one warp.  zsrc / sdsrc: the ray's S sorted depths
+// and SDF values (global or shared memory); s_cdf / s_z: the warp's scratch rows.  Lane q writes sample q + 32 k to
+// z_samples (global, may be NULL), s_new (shared, may be NULL) and its position o + d z to pts_out (global, may be NULL).
+__device__ __forceinline__ void up_sample_ray(const float* zsrc, const float* sdsrc, int S, float ox, float oy, float oz,
+                                              float dx, float dy, float dz, float r_limit, int n_imp, float inv_s,
+                                              float* s_cdf, float* s_z, float* z_samples, float* s_new, float* pts_out,
+                                              int lane) {
+  float z[NS_PER + 1], sd[NS_PER + 1], rad[NS_PER + 1];
+#pragma unroll
+  for (int j = 0; j < NS_PER; ++j) {
+    int i = NS_PER * lane + j;
+    z[j] = i < S ? zsrc[i] : 0.f;
+    sd[j] = i < S ? sdsrc[i] : 0.f;
+    float px = ox + dx * z[j], py = oy + dy * z[j], pz = oz + dz * z[j];
+    rad[j] = sqrtf(px * px + py * py + pz * pz);     // torch.linalg.norm(pts, ord=2)
+  }
+  // element NS_PER = first element of the next lane
+  z[NS_PER] = __shfl_down_sync(0xffffffffu, z[0], 1);
+  sd[NS_PER] = __shfl_down_sync(0xffffffffu, sd[0], 1);
+  rad[NS_PER] = __shfl_down_sync(0xffffffffu, rad[0], 1);
+  // cos_val per interval i (valid for i < S-1)
+  float cosv[NS_PER];
+#pragma unroll
+  for (int j = 0; j < NS_PER; ++j) cosv[j] = (sd[j + 1] - sd[j]) / (z[j + 1] - z[j] + 1e-5f);
+  float prev_last = __shfl_up_sync(0xffffffffu, cosv[NS_PER - 1], 1);
+  if (lane == 0) prev_last = 0.f;                     // prev_cos_val[:,0] = 0
+  float om[NS_PER], alpha[NS_PER];
+#pragma unroll
+  for (int j = 0; j < NS_PER; ++j) {
+    int i = NS_PER * lane + j;
+    float pc = j == 0 ? prev_last : cosv[j - 1];
+    float c = fminf(pc, cosv[j]);
+    c = fminf(fmaxf(c, -1e3f), 0.f);
+    bool inside = (rad[j] < r_limit) || (rad[j + 1] < r_limit);
+    c = inside ? c : 0.f;
+    float mid = (sd[j] + sd[j + 1]) * 0.5f;
+    float dist = z[j + 1] - z[j];
+    float pe = mid - c * dist * 0.5f, ne = mid + c * dist * 0.5f;
+    float pcdf = sigmoidf_(pe * inv_s), ncdf = sigmoidf_(ne * inv_s);
+    float a = (pcdf - ncdf + 1e-5f) / (pcdf + 1e-5f);
+    bool valid = i < S - 1;
+    alpha[j] = valid ? a : 0.f;
+    om[j] = valid ? (1.f - a + 1e-7f) : 1.f;
+  }
+  warp_excl_cumprod4(om, lane);                        // transmittance
+  float w[NS_PER];
+  float wsum = 0.f;
+#pragma unroll
+  for (int j = 0; j < NS_PER; ++j) {
+    int i = NS_PER * lane + j;
+    w[j] = i < S - 1 ? alpha[j] * om[j] + 1e-5f : 0.f;  // sample_pdf: weights + 1e-5
+    wsum += w[j];
+  }
+  wsum = warp_sum(wsum);
+#pragma unroll
+  for (int j = 0; j < NS_PER; ++j) w[j] = w[j] / wsum;  // pdf
+  warp_incl_cumsum4(w, lane);                          // cdf[1..S-1]
+  __syncwarp();
+  if (lane == 0) s_cdf[0] = 0.f;
+#pragma unroll
+  for (int j = 0; j < NS_PER; ++j) {
+    int i = NS_PER * lane + j;
+    if (i < S - 1) s_cdf[i + 1] = w[j];
+    if (i < S) s_z[i] = z[j];
+  }
+  __syncwarp();
+  // inverse CDF at u = linspace(0.5/n, 1-0.5/n, n)
+  for (int q = lane; q < n_imp; q += 32) {
+    float lo = 0.5f / n_imp, hi = 1.0f - 0.5f / n_imp;
+    float u = n_imp > 1 ? lo + (hi - lo) * ((float)q / (float)(n_imp - 1)) : lo;
+    if (q == n_imp - 1 && n_imp > 1) u = hi;
+    // searchsorted(cdf, u, right=True): first idx with cdf[idx] > u, in [0, S]
+    int a0 = 0, b0 = S;
+    while (a0 < b0) { int m = (a0 + b0) >> 1; if (s_cdf[m] > u) b0 = m; else a0 = m + 1; }
+    int below = max(0, a0 - 1), above = min(S - 1, a0);
+    float cb = s_cdf[below], ca = s_cdf[above];
+    float bb = s_z[below], ba = s_z[above];
+    float den = ca - cb;
+    if (den < 1e-5f) den = 1.f;
+    float t = (u - cb) / den;
+    const float zs = bb + t * (ba - bb);
+    if (z_samples) z_samples[q] = zs;
+    if (s_new) s_new[q] = zs;
+    if (pts_out) { pts_out[q * 3] = ox + dx * zs; pts_out[q * 3 + 1] = oy + dy * zs; pts_out[q * 3 + 2] = oz + dz * zs; }
+  }
+  __syncwarp();
+}
+
 __global__ void neus_up_sample_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                       const float* __restrict__ z_vals, const float* __restrict__ sdf,
                                       long long n_rays, int S, float r_limit, int n_imp, float inv_s,
-                                      float* __restrict__ z_samples) {
+                                      float* __restrict__ z_samples, float* __restrict__ pts_out) {
   __shared__ float s_cdf[8][NS_MAXS + 1];
   __shared__ float s_z[8][NS_MAXS];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -62,88 +150,21 @@ __global__ void neus_up_sample_kernel(const float* __restrict__ rays_o, const fl
   for (long long ray = warp; ray < n_rays; ray += nw) {
     const float ox = rays_o[ray * 3], oy = rays_o[ray * 3 + 1], oz = rays_o[ray * 3 + 2];
     const float dx = rays_d[ray * 3], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
-    float z[NS_PER + 1], sd[NS_PER + 1], rad[NS_PER + 1];
-#pragma unroll
-    for (int j = 0; j < NS_PER; ++j) {
-      int i = NS_PER * lane + j;
-      z[j] = i < S ? z_vals[ray * S + i] : 0.f;
-      sd[j] = i < S ? sdf[ray * S + i] : 0.f;
-      float px = ox + dx * z[j], py = oy + dy * z[j], pz = oz + dz * z[j];
-      rad[j] = sqrtf(px * px + py * py + pz * pz);     // torch.linalg.norm(pts, ord=2)
-    }
-    // element NS_PER = first element of the next lane
-    z[NS_PER] = __shfl_down_sync(0xffffffffu, z[0], 1);
-    sd[NS_PER] = __shfl_down_sync(0xffffffffu, sd[0], 1);
-    rad[NS_PER] = __shfl_down_sync(0xffffffffu, rad[0], 1);
-    // cos_val per interval i (valid for i < S-1)
-    float cosv[NS_PER];
-#pragma unroll
-    for (int j = 0; j < NS_PER; ++j) cosv[j] = (sd[j + 1] - sd[j]) / (z[j + 1] - z[j] + 1e-5f);
-    float prev_last = __shfl_up_sync(0xffffffffu, cosv[NS_PER - 1], 1);
-    if (lane == 0) prev_last = 0.f;                     // prev_cos_val[:,0] = 0
-    float om[NS_PER], alpha[NS_PER];
-#pragma unroll
-    for (int j = 0; j < NS_PER; ++j) {
-      int i = NS_PER * lane + j;
-      float pc = j == 0 ? prev_last : cosv[j - 1];
-      float c = fminf(pc, cosv[j]);
-      c = fminf(fmaxf(c, -1e3f), 0.f);
-      bool inside = (rad[j] < r_limit) || (rad[j + 1] < r_limit);
-      c = inside ? c : 0.f;
-      float mid = (sd[j] + sd[j + 1]) * 0.5f;
-      float dist = z[j + 1] - z[j];
-      float pe = mid - c * dist * 0.5f, ne = mid + c * dist * 0.5f;
-      float pcdf = sigmoidf_(pe * inv_s), ncdf = sigmoidf_(ne * inv_s);
-      float a = (pcdf - ncdf + 1e-5f) / (pcdf + 1e-5f);
-      bool valid = i < S - 1;
-      alpha[j] = valid ? a : 0.f;
-      om[j] = valid ? (1.f - a + 1e-7f) : 1.f;
-    }
-    warp_excl_cumprod4(om, lane);                        // transmittance
-    float w[NS_PER];
-    float wsum = 0.f;
-#pragma unroll
-    for (int j = 0; j < NS_PER; ++j) {
-      int i = NS_PER * lane + j;
-      w[j] = i < S - 1 ? alpha[j] * om[j] + 1e-5f : 0.f;  // sample_pdf: weights + 1e-5
-      wsum += w[j];
-    }
-    wsum = warp_sum(wsum);
-#pragma unroll
-    for (int j = 0; j < NS_PER; ++j) w[j] = w[j] / wsum;  // pdf
-    warp_incl_cumsum4(w, lane);                          // cdf[1..S-1]
-    __syncwarp();
-    if (lane == 0) s_cdf[wib][0] = 0.f;
-#pragma unroll
-    for (int j = 0; j < NS_PER; ++j) {
-      int i = NS_PER * lane + j;
-      if (i < S - 1) s_cdf[wib][i + 1] = w[j];
-      if (i < S) s_z[wib][i] = z[j];
-    }
-    __syncwarp();
-    // inverse CDF at u = linspace(0.5/n, 1-0.5/n, n)
-    for (int q = lane; q < n_imp; q += 32) {
-      float lo = 0.5f / n_imp, hi = 1.0f - 0.5f / n_imp;
-      float u = n_imp > 1 ? lo + (hi - lo) * ((float)q / (float)(n_imp - 1)) : lo;
-      if (q == n_imp - 1 && n_imp > 1) u = hi;
-      // searchsorted(cdf, u, right=True): first idx with cdf[idx] > u, in [0, S]
-      int a0 = 0, b0 = S;
-      while (a0 < b0) { int m = (a0 + b0) >> 1; if (s_cdf[wib][m] > u) b0 = m; else a0 = m + 1; }
-      int below = max(0, a0 - 1), above = min(S - 1, a0);
-      float cb = s_cdf[wib][below], ca = s_cdf[wib][above];
-      float bb = s_z[wib][below], ba = s_z[wib][above];
-      float den = ca - cb;
-      if (den < 1e-5f) den = 1.f;
-      float t = (u - cb) / den;
-      z_samples[ray * n_imp + q] = bb + t * (ba - bb);
-    }
-    __syncwarp();
+    up_sample_ray(z_vals + ray * S, sdf + ray * S, S, ox, oy, oz, dx, dy, dz, r_limit, n_imp, inv_s, s_cdf[wib], s_z[wib],
+                  z_samples + ray * n_imp, nullptr, pts_out ? pts_out + ray * n_imp * 3 : nullptr, lane);
   }
 }
 
 extern "C" int vqn_neus_up_sample(vqn_ctx* ctx, const float* rays_o, const float* rays_d, const float* z_vals,
                                   const float* sdf, int64_t n_rays, int n_samples, float r_limit, int n_importance,
                                   float inv_s, float* z_samples, vqn_stream stream) {
+  return vqn_neus_up_sample_pts(ctx, rays_o, rays_d, z_vals, sdf, n_rays, n_samples, r_limit, n_importance, inv_s, z_samples,
+                                nullptr, stream);
+}
+
+extern "C" int vqn_neus_up_sample_pts(vqn_ctx* ctx, const float* rays_o, const float* rays_d, const float* z_vals,
+                                      const float* sdf, int64_t n_rays, int n_samples, float r_limit, int n_importance,
+                                      float inv_s, float* z_samples, float* pts_out, vqn_stream stream) {
   VQN_CHECK_ARG(ctx && rays_o && rays_d && z_vals && sdf && z_samples, "up_sample: null");
   VQN_CHECK_ARG(n_samples >= 2 && n_samples <= NS_MAXS, "up_sample: 2 <= n_samples <= 128");
   VQN_CHECK_ARG(n_importance >= 1 && n_rays >= 0, "up_sample: n_importance >= 1");
@@ -151,7 +172,7 @@ extern "C" int vqn_neus_up_sample(vqn_ctx* ctx, const float* rays_o, const float
   long long want = (n_rays + 7) / 8;
   int blocks = (int)(want < (long long)ctx->sm_count * 8 ? want : (long long)ctx->sm_count * 8);
   neus_up_sample_kernel<<<blocks, 256, 0, vqn_cs(stream)>>>(rays_o, rays_d, z_vals, sdf, n_rays, n_samples,
-                                                            r_limit, n_importance, inv_s, z_samples);
+                                                            r_limit, n_importance, inv_s, z_samples, pts_out);
   VQN_LAUNCHED(ctx);
   return VQN_OK;
 }
@@ -161,31 +182,7 @@ extern "C" int vqn_neus_up_sample(vqn_ctx* ctx, const float* rays_o, const float
 // ---------------------------------------------------------------------------------------------
 __global__ void neus_cat_kernel(const float* __restrict__ z_vals, const float* __restrict__ new_z,
                                 const float* __restrict__ sdf, const float* __restrict__ new_sdf, long long n_rays,
-                                int S, int I, float* __restrict__ z_out, float* __restrict__ sdf_out) {
-  __shared__ float s_z[8][2 * NS_MAXS];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int T = S + I;
-  long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long ray = warp; ray < n_rays; ray += nw) {
-    for (int i = lane; i < T; i += 32) s_z[wib][i] = i < S ? z_vals[ray * S + i] : new_z[ray * I + (i - S)];
-    __syncwarp();
-    for (int i = lane; i < T; i += 32) {
-      float v = s_z[wib][i];
-      int rank = 0;
-      for (int k = 0; k < T; ++k) {
-        float u = s_z[wib][k];
-        rank += (u < v) || (u == v && k < i);
-      }
-      z_out[ray * T + rank] = v;
-      if (sdf_out) {
-        float sv = i < S ? sdf[ray * S + i] : (new_sdf ? new_sdf[ray * I + (i - S)] : 0.f);
-        sdf_out[ray * T + rank] = sv;
-      }
-    }
-    __syncwarp();
-  }
-}
+                                int S, int I, float* __restrict__ z_out, float* __restrict__ sdf_out);   // (below rank_merge)
 
 extern "C" int vqn_neus_cat_z_vals(vqn_ctx* ctx, const float* z_vals, const float* new_z, const float* sdf,
                                    const float* new_sdf, int64_t n_rays, int n_samples, int n_importance,
@@ -199,6 +196,129 @@ extern "C" int vqn_neus_cat_z_vals(vqn_ctx* ctx, const float* z_vals, const floa
   int blocks = (int)(want < (long long)ctx->sm_count * 8 ? want : (long long)ctx->sm_count * 8);
   neus_cat_kernel<<<blocks, 256, 0, vqn_cs(stream)>>>(z_vals, new_z, sdf, new_sdf, n_rays, n_samples,
                                                       n_importance, z_out, sdf_out);
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One hierarchical-sampling step in ONE launch (NeuSRenderer.render, renderer.py:343-366): cat_z_vals of step i (the SDF
+// of the new samples has just been evaluated), up_sample of step i + 1 on the merged row while it is still in shared
+// memory -- including the positions o + d z of the new samples, the next SDF call's input -- and, for the last step
+// (whose cat_z_vals needs no SDF), the final merge and the mid-point positions / directions render_core asks for.
+// 4 + 4 + 1 launches per render become 4; the same arithmetic as the separate kernels, bit for bit.
+// ---------------------------------------------------------------------------------------------
+// Stable sort of s_in[0..T) = [list A (S elements) ; list B (T - S elements)] -- the order torch.sort gives the reference
+// (cat_z_vals, renderer.py:181-182): element i goes to position #{k : in[k] < in[i] or (in[k] == in[i] and k < i)}.
+// Both lists are normally sorted already (A is a previous merge, B an inverse CDF at increasing u), and then the position is
+// i + #{b < A_i} resp. j + #{a <= B_j}: two binary searches instead of T comparisons per element (T^2 = 16 k per ray was a
+// quarter of the scan kernels' time).  An unsorted input (possible through the public cat_z_vals) takes the rank sort.
+__device__ __forceinline__ void rank_merge(const float* s_in, int S, int T, float* z_dst, const float* sd_in, float* sd_dst,
+                                           int lane) {
+  bool sorted = true;
+  for (int i = lane; i + 1 < T; i += 32) sorted = sorted && (i + 1 == S || s_in[i] <= s_in[i + 1]);
+  sorted = __all_sync(0xffffffffu, sorted);
+  for (int i = lane; i < T; i += 32) {
+    const float v = s_in[i];
+    int rank;
+    if (sorted) {
+      int lo, hi;
+      if (i < S) {                    // #{b in B : b < v}
+        lo = S; hi = T;
+        while (lo < hi) { const int m = (lo + hi) >> 1; if (s_in[m] < v) lo = m + 1; else hi = m; }
+        rank = i + (lo - S);
+      } else {                        // #{a in A : a <= v}
+        lo = 0; hi = S;
+        while (lo < hi) { const int m = (lo + hi) >> 1; if (s_in[m] <= v) lo = m + 1; else hi = m; }
+        rank = (i - S) + lo;
+      }
+    } else {
+      rank = 0;
+      for (int k = 0; k < T; ++k) {
+        const float u = s_in[k];
+        rank += (u < v) || (u == v && k < i);
+      }
+    }
+    z_dst[rank] = v;
+    if (sd_dst) sd_dst[rank] = sd_in[i];
+  }
+}
+
+__global__ void neus_cat_kernel(const float* __restrict__ z_vals, const float* __restrict__ new_z,
+                                const float* __restrict__ sdf, const float* __restrict__ new_sdf, long long n_rays,
+                                int S, int I, float* __restrict__ z_out, float* __restrict__ sdf_out) {
+  __shared__ float s_z[8][2 * NS_MAXS], s_sd[8][2 * NS_MAXS];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int T = S + I;
+  long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long ray = warp; ray < n_rays; ray += nw) {
+    for (int i = lane; i < T; i += 32) {
+      s_z[wib][i] = i < S ? z_vals[ray * S + i] : new_z[ray * I + (i - S)];
+      if (sdf_out) s_sd[wib][i] = i < S ? sdf[ray * S + i] : (new_sdf ? new_sdf[ray * I + (i - S)] : 0.f);
+    }
+    __syncwarp();
+    rank_merge(s_z[wib], S, T, z_out + ray * T, s_sd[wib], sdf_out ? sdf_out + ray * T : nullptr, lane);
+    __syncwarp();
+  }
+}
+
+__global__ void neus_scan_step_kernel(vqn_neus_step_args a) {
+  __shared__ float s_in[8][2 * NS_MAXS], s_sdin[8][2 * NS_MAXS];      // unsorted [z_vals ; new_z] and their SDF values
+  __shared__ float s_zm[8][NS_MAXS], s_sdm[8][NS_MAXS];               // merged row (T <= 128 when it is up-sampled)
+  __shared__ float s_cdf[8][NS_MAXS + 1], s_z[8][NS_MAXS];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int S = a.n_samples, I = a.n_new, T = S + I, I2 = a.n_importance, F = T + I2;
+  long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long ray = warp; ray < a.n_rays; ray += nw) {
+    const float ox = a.rays_o[ray * 3], oy = a.rays_o[ray * 3 + 1], oz = a.rays_o[ray * 3 + 2];
+    const float dx = a.rays_d[ray * 3], dy = a.rays_d[ray * 3 + 1], dz = a.rays_d[ray * 3 + 2];
+    for (int i = lane; i < T; i += 32) {
+      s_in[wib][i] = i < S ? a.z_vals[ray * S + i] : a.new_z[ray * I + (i - S)];
+      s_sdin[wib][i] = i < S ? a.sdf[ray * S + i] : a.new_sdf[ray * I + (i - S)];
+    }
+    __syncwarp();
+    rank_merge(s_in[wib], S, T, s_zm[wib], s_sdin[wib], s_sdm[wib], lane);
+    __syncwarp();
+    if (a.z_out) for (int i = lane; i < T; i += 32) { a.z_out[ray * T + i] = s_zm[wib][i]; a.sdf_out[ray * T + i] = s_sdm[wib][i]; }
+    // up_sample of the next step on the merged row; the new samples land behind it in s_in for the final merge
+    if (a.final_merge) for (int i = lane; i < T; i += 32) s_in[wib][i] = s_zm[wib][i];
+    up_sample_ray(s_zm[wib], s_sdm[wib], T, ox, oy, oz, dx, dy, dz, a.r_limit, I2, a.inv_s, s_cdf[wib], s_z[wib],
+                  a.new_z_out ? a.new_z_out + ray * I2 : nullptr, a.final_merge ? s_in[wib] + T : nullptr,
+                  a.pts_out ? a.pts_out + ray * I2 * 3 : nullptr, lane);
+    if (a.final_merge) {
+      // last step: cat_z_vals(last=True) needs no SDF; then render_core's mid-point positions (:203-209)
+      __syncwarp();
+      rank_merge(s_in[wib], T, F, s_sdin[wib], nullptr, nullptr, lane);    // sorted depths -> s_sdin (free by now)
+      __syncwarp();
+      for (int i = lane; i < F; i += 32) {
+        const float z = s_sdin[wib][i];
+        const float dist = i + 1 < F ? s_sdin[wib][i + 1] - z : a.sample_dist;
+        const float mz = z + dist * 0.5f;
+        const long long idx = ray * F + i;
+        a.z_final[idx] = z;
+        a.mid_pts[idx * 3] = ox + dx * mz; a.mid_pts[idx * 3 + 1] = oy + dy * mz; a.mid_pts[idx * 3 + 2] = oz + dz * mz;
+        if (a.mid_dirs) { a.mid_dirs[idx * 3] = dx; a.mid_dirs[idx * 3 + 1] = dy; a.mid_dirs[idx * 3 + 2] = dz; }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+extern "C" int vqn_neus_scan_step(vqn_ctx* ctx, const vqn_neus_step_args* args, vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && args, "scan_step: null");
+  const vqn_neus_step_args& a = *args;
+  VQN_CHECK_ARG(a.rays_o && a.rays_d && a.z_vals && a.new_z && a.sdf && a.new_sdf, "scan_step: null input");
+  VQN_CHECK_ARG(a.n_samples >= 1 && a.n_new >= 1 && a.n_samples + a.n_new >= 2 && a.n_samples + a.n_new <= NS_MAXS,
+                "scan_step: 2 <= n_samples + n_new <= 128");
+  VQN_CHECK_ARG(a.n_importance >= 1 && a.n_samples + a.n_new + a.n_importance <= 2 * NS_MAXS, "scan_step: n_importance");
+  VQN_CHECK_ARG((a.z_out == nullptr) == (a.sdf_out == nullptr), "scan_step: z_out and sdf_out go together");
+  VQN_CHECK_ARG(!a.final_merge || (a.z_final && a.mid_pts), "scan_step: final_merge needs z_final and mid_pts");
+  VQN_CHECK_ARG(a.final_merge || a.new_z_out, "scan_step: new_z_out missing");
+  if (a.n_rays == 0) return VQN_OK;
+  long long want = (a.n_rays + 7) / 8;
+  int blocks = (int)(want < (long long)ctx->sm_count * 8 ? want : (long long)ctx->sm_count * 8);
+  neus_scan_step_kernel<<<blocks, 256, 0, vqn_cs(stream)>>>(a);
   VQN_LAUNCHED(ctx);
   return VQN_OK;
 }

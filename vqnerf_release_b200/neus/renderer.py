@@ -48,13 +48,15 @@ class NeuSRenderer:
     # renderer.py:193-297
     def render_core(self, rays_o, rays_d, z_vals, sample_dist, radius, sdf_network, deviation_network,
                     color_network, background_alpha=None, background_sampled_color=None, background_rgb=None,
-                    cos_anneal_ratio=0.0, to_light=False, need_color=True):
+                    cos_anneal_ratio=0.0, to_light=False, need_color=True, _mid=None):
         # need_color=False (not a reference argument): callers that only read the weights (compute_vis) skip the
         # colour network; every other output is unchanged and 'color' is the composited background only
         if background_alpha is not None or to_light:
             raise NotImplementedError('background model / to_light marching are outside the path (n_outside = 0)')
         batch_size, n_samples = z_vals.shape
-        pts, dirs = abi.neus_mid_points(rays_o, rays_d, z_vals, float(sample_dist))
+        # _mid (not a reference argument): the mid-point positions / directions already produced by the last fused
+        # sampling step of render()
+        pts, dirs = _mid if _mid is not None else abi.neus_mid_points(rays_o, rays_d, z_vals, float(sample_dist))
         pts = pts.reshape(-1, 3)
         dirs = dirs.reshape(-1, 3)
         if not need_color and hasattr(sdf_network, 'forward_with_gradient'):
@@ -107,7 +109,30 @@ class NeuSRenderer:
         if perturb > 0:
             t_rand = torch.rand([batch_size, 1], device=dev) - 0.5
             z_vals = z_vals + t_rand * 2. * radius / self.n_samples
-        if self.n_importance > 0:
+        mid = None
+        steps = self.up_sample_steps
+        n_imp = self.n_importance // steps if steps > 0 else 0
+        if (self.n_importance > 0 and steps >= 2 and self.n_samples + steps * n_imp <= 128 and
+                type(self).up_sample is NeuSRenderer.up_sample and type(self).cat_z_vals is NeuSRenderer.cat_z_vals):
+            # Fused sampling (csrc/neus.cu::neus_scan_step_kernel): one launch per step does cat_z_vals of step i,
+            # up_sample of step i + 1 and the positions of its new samples; the last launch also does the final
+            # cat_z_vals(last=True) and render_core's mid points.  4 launches instead of 4 + 4 + 1, same values bit for
+            # bit (tests/test_gpu_neus.py::test_fused_scan_steps_equal_separate_kernels).
+            with torch.no_grad():
+                pts = rays_o[:, None, :] + rays_d[:, None, :] * z_vals[..., :, None]
+                sdf = self.sdf_network.sdf(pts.reshape(-1, 3)).reshape(batch_size, self.n_samples)
+                new_z, pts = abi.neus_up_sample_pts(rays_o, rays_d, z_vals, sdf, radius, n_imp, 64)
+                for i in range(steps - 1):
+                    new_sdf = self.sdf_network.sdf(pts.reshape(-1, 3)).reshape(batch_size, n_imp)
+                    last = (i + 2 == steps)
+                    o = abi.neus_scan_step(rays_o, rays_d, z_vals, new_z, sdf, new_sdf, radius, n_imp, 64 * 2 ** (i + 1),
+                                           final_merge=last, sample_dist=sample_dist, want_merged=not last)
+                    if last:
+                        z_vals, mid = o['z_final'], (o['mid_pts'], o['mid_dirs'])
+                    else:
+                        z_vals, sdf, new_z, pts = o['z'], o['sdf'], o['new_z'], o['pts']
+            n_samples = self.n_samples + self.n_importance
+        elif self.n_importance > 0:
             with torch.no_grad():
                 pts = rays_o[:, None, :] + rays_d[:, None, :] * z_vals[..., :, None]
                 sdf = self.sdf_network.sdf(pts.reshape(-1, 3)).reshape(batch_size, self.n_samples)
@@ -119,7 +144,7 @@ class NeuSRenderer:
             n_samples = self.n_samples + self.n_importance
         ret_fine = self.render_core(rays_o, rays_d, z_vals, sample_dist, radius, self.sdf_network,
                                     self.deviation_network, self.color_network, background_rgb=background_rgb,
-                                    cos_anneal_ratio=cos_anneal_ratio, need_color=need_color)
+                                    cos_anneal_ratio=cos_anneal_ratio, need_color=need_color, _mid=mid)
         s_val = ret_fine['s_val'].reshape(batch_size, n_samples).mean(dim=-1, keepdim=True)
         return {
             'color_fine': ret_fine['color'], 's_val': s_val, 'cdf_fine': ret_fine['cdf'],
