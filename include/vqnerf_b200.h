@@ -274,6 +274,8 @@ int vqn_dense_forward(vqn_ctx* ctx, const float* x, int64_t ldx, const float* w,
 int vqn_net_forward_train(vqn_ctx* ctx, vqn_net* net, const float* x, int64_t ldx, int64_t n, float* const* y,
                           const int64_t* ldy, float out_scale, float out_bias, int precision, vqn_stream stream);
 int vqn_net_repack_tc(vqn_net* net, int precision, vqn_stream stream);
+/* the same for `count` networks in ONE launch (the training step refreshes all of its networks after the optimizer step) */
+int vqn_nets_repack_tc(vqn_net* const* nets, int count, int precision, vqn_stream stream);
 /* dX[m,k] (+)= (dZ[m,n] . W[k,n]^T) * act_prev'(Yprev[m,k]); act_prev' is taken from the stored activation
  * (relu: y > 0, sigmoid: y (1 - y)); accumulate != 0 adds into dX (several consumers of one tensor). */
 int vqn_dense_backward_data(vqn_ctx* ctx, const float* dz, int64_t lddz, const float* w, float* dx, int64_t lddx,
@@ -282,6 +284,22 @@ int vqn_dense_backward_data(vqn_ctx* ctx, const float* dz, int64_t lddz, const f
 /* dW[k,n] += X[m,k]^T . dZ[m,n];  db[n] += colsum(dZ)  (gradient buffers are accumulated: zero them per step) */
 int vqn_dense_backward_weights(vqn_ctx* ctx, const float* x, int64_t ldx, const float* dz, int64_t lddz, float* dw,
                                float* db, int64_t m, int k, int n, vqn_stream stream);
+/* Batched backward GEMMs: up to 32 INDEPENDENT problems of one kind in ONE launch (the same-level layers of the head
+ * networks; every weight-gradient GEMM of the step).  Fields per problem:
+ *   backward-data:    a = dZ [m,n] (ld lda), w = W [k,n] row-major, out = dX [m,k] (ld ldo), yprev/ldy/act_prev as in
+ *                     vqn_dense_backward_data, accumulate 0 = store, 1 = add, 2 = add atomically (shared target);
+ *   backward-weights: a = X [m,k] (ld lda), w = dZ [m,n] (ld ldw), out = dW [k,n] (+=, atomics), colsum = db [n] or NULL. */
+typedef struct vqn_dense_problem {
+  const float* a; int64_t lda;
+  const float* w; int64_t ldw;
+  float* out; int64_t ldo;
+  const float* yprev; int64_t ldy;
+  float* colsum;
+  int64_t m; int32_t k, n, act_prev, accumulate;
+} vqn_dense_problem;
+int vqn_dense_backward_data_batched(vqn_ctx* ctx, const vqn_dense_problem* problems, int count, vqn_stream stream);
+int vqn_dense_backward_weights_batched(vqn_ctx* ctx, const vqn_dense_problem* problems, int count, vqn_stream stream);
+
 /* dZ = scale * dY * act'(Y) through a net's LAST activation; Y is stored as out_scale * act(.) + out_bias */
 int vqn_act_backward(vqn_ctx* ctx, const float* dy, int64_t lddy, const float* y, int64_t ldy, int64_t m, int n,
                      int act, float scale, float out_scale, float out_bias, float* dz, int64_t lddz,
@@ -289,6 +307,9 @@ int vqn_act_backward(vqn_ctx* ctx, const float* dy, int64_t lddy, const float* y
 /* dst[:, 0:w] (leading dim ldd) = src[:, 0:w] (leading dim lds): the x half of concat(y, x) (mlp.py:47-48) */
 int vqn_copy_cols(vqn_ctx* ctx, const float* src, int64_t lds, float* dst, int64_t ldd, int64_t m, int w,
                   vqn_stream stream);
+/* up to 16 column-block copies (vqn_copy_cols) in ONE launch */
+typedef struct vqn_copy_job { const float* src; float* dst; int64_t lds, ldd, m; int32_t w, reserved; } vqn_copy_job;
+int vqn_copy_cols_batched(vqn_ctx* ctx, const vqn_copy_job* jobs, int count, vqn_stream stream);
 /* Backward of vqn_shade for probe 0 (linear rgb; clip_by_value_preserve_gradient has identity gradient,
  * vq_nfr.py:718,759): d_rgb [n,3] compact -> d_albedo [n,3], d_spec [n,3], d_rough [n,1] compact and
  * d_light [512,3] (ACCUMULATED over points and calls; gradient w.r.t. the raw _light variable). */

@@ -66,6 +66,18 @@ class NeusStepArgs(C.Structure):
                 ('z_final', C.c_void_p), ('mid_pts', C.c_void_p), ('mid_dirs', C.c_void_p)]
 
 
+class CopyJob(C.Structure):
+    _fields_ = [('src', C.c_void_p), ('dst', C.c_void_p), ('lds', C.c_int64), ('ldd', C.c_int64), ('m', C.c_int64),
+                ('w', C.c_int32), ('reserved', C.c_int32)]
+
+
+class DenseProblem(C.Structure):
+    _fields_ = [('a', C.c_void_p), ('lda', C.c_int64), ('w', C.c_void_p), ('ldw', C.c_int64),
+                ('out', C.c_void_p), ('ldo', C.c_int64), ('yprev', C.c_void_p), ('ldy', C.c_int64),
+                ('colsum', C.c_void_p), ('m', C.c_int64), ('k', C.c_int32), ('n', C.c_int32),
+                ('act_prev', C.c_int32), ('accumulate', C.c_int32)]
+
+
 _P, _I, _L, _F, _D = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 
 # name -> (restype, argtypes); every symbol declared in include/vqnerf_b200.h
@@ -117,8 +129,12 @@ SIGNATURES = {
     'vqn_dense_forward': (_I, [_P, _P, _L, _P, _P, _P, _L, _L, _I, _I, _I, _F, _F, _P]),
     'vqn_net_forward_train': (_I, [_P, _P, _P, _L, _L, C.POINTER(_P), C.POINTER(_L), _F, _F, _I, _P]),
     'vqn_net_repack_tc': (_I, [_P, _I, _P]),
+    'vqn_nets_repack_tc': (_I, [C.POINTER(_P), _I, _I, _P]),
+    'vqn_copy_cols_batched': (_I, [_P, C.POINTER(CopyJob), _I, _P]),
     'vqn_dense_backward_data': (_I, [_P, _P, _L, _P, _P, _L, _P, _L, _I, _I, _L, _I, _I, _P]),
     'vqn_dense_backward_weights': (_I, [_P, _P, _L, _P, _L, _P, _P, _L, _I, _I, _P]),
+    'vqn_dense_backward_data_batched': (_I, [_P, C.POINTER(DenseProblem), _I, _P]),
+    'vqn_dense_backward_weights_batched': (_I, [_P, C.POINTER(DenseProblem), _I, _P]),
     'vqn_act_backward': (_I, [_P, _P, _L, _P, _L, _L, _I, _I, _F, _F, _F, _P, _L, _P]),
     'vqn_copy_cols': (_I, [_P, _P, _L, _P, _L, _L, _I, _P]),
     'vqn_shade_backward': (_I, [_P] * 6 + [_L] + [_P] * 6 + [_I] + [_P] * 6),

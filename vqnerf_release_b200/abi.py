@@ -684,6 +684,46 @@ def dense_backward_weights(x, ldx, dz, lddz, dw, db, m, k, n, x_off=0):
                                              L.stream_ptr(dw.device)))
 
 
+def _ptr_int(t, off_elems=0):
+    return None if t is None else t.data_ptr() + 4 * int(off_elems)
+
+
+def bwd_data_problem(dz, lddz, w, dx, lddx, yprev, ldyp, act_prev, accumulate, m, k, n, w_row0=0, dx_off=0):
+    """One problem of dense_backward_data_batched (same meaning as dense_backward_data; accumulate 2 = atomic add)."""
+    q = L.DenseProblem()
+    q.a, q.lda, q.w, q.ldw = _ptr_int(dz), lddz, _ptr_int(w, w_row0 * n), n
+    q.out, q.ldo, q.yprev, q.ldy = _ptr_int(dx, dx_off), lddx, _ptr_int(yprev), ldyp
+    q.m, q.k, q.n, q.act_prev, q.accumulate = m, k, n, act_prev, int(accumulate)
+    return q
+
+
+def bwd_weights_problem(x, ldx, dz, lddz, dw, db, m, k, n):
+    q = L.DenseProblem()
+    q.a, q.lda, q.w, q.ldw = _ptr_int(x), ldx, _ptr_int(dz), lddz
+    q.out, q.ldo, q.colsum = _ptr_int(dw), n, _ptr_int(db)
+    q.m, q.k, q.n = m, k, n
+    return q
+
+
+def _dense_batched(fn_name, problems, dev):
+    c = L.Context.get(dev)
+    fn = getattr(c.lib, fn_name)
+    for i in range(0, len(problems), 32):
+        chunk = problems[i:i + 32]
+        arr = (L.DenseProblem * len(chunk))(*chunk)
+        L.check(fn(c.handle, arr, len(chunk), L.stream_ptr(dev)))
+
+
+def dense_backward_data_batched(problems, dev):
+    """Independent backward-data GEMMs (bwd_data_problem) in ONE launch per 32 problems."""
+    _dense_batched('vqn_dense_backward_data_batched', problems, dev)
+
+
+def dense_backward_weights_batched(problems, dev):
+    """Every weight-gradient GEMM of a step (bwd_weights_problem) in ONE launch per 32 problems."""
+    _dense_batched('vqn_dense_backward_weights_batched', problems, dev)
+
+
 def act_backward(dy, lddy, y, ldy, m, n, act, scale, out_scale, out_bias, dz, lddz):
     c = _ctx(dy)
     L.check(c.lib.vqn_act_backward(c.handle, _p(dy), lddy, _p(y), ldy, m, n, act, float(scale), float(out_scale),
@@ -693,6 +733,27 @@ def act_backward(dy, lddy, y, ldy, m, n, act, scale, out_scale, out_bias, dz, ld
 def copy_cols(src, lds, dst, ldd, m, w, dst_off=0):
     c = _ctx(src)
     L.check(c.lib.vqn_copy_cols(c.handle, _p(src), lds, _p(dst, dst_off), ldd, m, w, L.stream_ptr(src.device)))
+
+
+def copy_cols_batched(jobs, dev):
+    """jobs: list of (src, lds, dst, ldd, m, w, dst_off) -- the arguments of copy_cols -- in ONE launch per 16 jobs."""
+    c = L.Context.get(dev)
+    for i in range(0, len(jobs), 16):
+        chunk = jobs[i:i + 16]
+        arr = (L.CopyJob * len(chunk))()
+        for q, (src, lds, dst, ldd, m, w, dst_off) in zip(arr, chunk):
+            q.src, q.dst, q.lds, q.ldd, q.m, q.w = _ptr_int(src), _ptr_int(dst, dst_off), lds, ldd, m, w
+        L.check(c.lib.vqn_copy_cols_batched(c.handle, arr, len(chunk), L.stream_ptr(dev)))
+
+
+def nets_repack_tc(packed_nets, precision='tf32x3'):
+    """Refresh the pre-split tensor-core weight images of several PackedNets in ONE launch (after an optimizer step)."""
+    if not packed_nets:
+        return
+    arr = (C.c_void_p * len(packed_nets))(*[p.handle.value for p in packed_nets])
+    c = packed_nets[0].ctx
+    L.check(c.lib.vqn_nets_repack_tc(arr, len(packed_nets), L.precision_code(precision),
+                                     L.stream_ptr(packed_nets[0].weights[0].device)))
 
 
 def shade_backward(xyz, rayo, normal, lvis, albedo, spec, rough, lxyz, lareas, light, d_rgb, d_albedo, d_spec,

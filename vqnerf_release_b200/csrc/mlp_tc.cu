@@ -133,9 +133,10 @@ struct TcPack {
 // K order = Keras row order (after a skip: y rows, then the x rows), each segment padded to whole chunks.
 // ---------------------------------------------------------------------------------------------
 template <bool BF16>
-__global__ void tc_pack_kernel(const float* __restrict__ w, const float* __restrict__ b, int n_out, int Npad,
-                               int seg0_rows, int seg0_chunks, int seg1_rows, int seg1_chunks,
-                               uint8_t* __restrict__ pw, float* __restrict__ pb, int transpose_ld) {
+__device__ __forceinline__ void tc_pack_body(const float* __restrict__ w, const float* __restrict__ b, int n_out, int Npad,
+                                             int seg0_rows, int seg0_chunks, int seg1_rows, int seg1_chunks,
+                                             uint8_t* __restrict__ pw, float* __restrict__ pb, int transpose_ld,
+                                             const int block, const int n_blocks) {
   // transpose_ld > 0: the GEMM's N index runs over the Keras kernel's ROWS (n_out of them) and its K index over the
   // kernel's columns (seg0_rows of them, row length transpose_ld): the image of W^T for the backward pass
   constexpr int E = BF16 ? 64 : 32;
@@ -143,8 +144,8 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, const float* __restr
   const size_t plane = (size_t)Npad * 128;
   const size_t chunk_bytes = BF16 ? plane : 2 * plane;
   const long long total = (long long)n_chunks * Npad * E;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  for (long long i = block * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)n_blocks * blockDim.x) {
     int kk = (int)(i % E);
     int n = (int)((i / E) % Npad);
     int c = (int)(i / ((long long)E * Npad));
@@ -167,8 +168,29 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, const float* __restr
       *reinterpret_cast<__nv_bfloat16*>(pc + tc::sw128_off(n, 4 + kk / 8) + (kk % 8) * 2) = __float2bfloat16_rn(v - hi);
     }
   }
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < Npad; c += gridDim.x * blockDim.x)
+  for (int c = block * blockDim.x + threadIdx.x; c < Npad; c += n_blocks * blockDim.x)
     pb[c] = (b && c < n_out) ? b[c] : 0.f;
+}
+
+template <bool BF16>
+__global__ void tc_pack_kernel(const float* __restrict__ w, const float* __restrict__ b, int n_out, int Npad,
+                               int seg0_rows, int seg0_chunks, int seg1_rows, int seg1_chunks,
+                               uint8_t* __restrict__ pw, float* __restrict__ pb, int transpose_ld) {
+  tc_pack_body<BF16>(w, b, n_out, Npad, seg0_rows, seg0_chunks, seg1_rows, seg1_chunks, pw, pb, transpose_ld,
+                     (int)blockIdx.x, (int)gridDim.x);
+}
+
+// every layer of several networks in ONE launch (the training step refreshes the images of its eight networks after each
+// optimizer step: 25 launches of ~4 us each otherwise); TC_PACK_BLOCKS blocks per layer
+#define TC_PACK_JOBS 48
+#define TC_PACK_BLOCKS 16
+struct TcPackJob { const float* w; const float* b; uint8_t* pw; float* pb; int n_out, Npad, seg0_rows, seg0_chunks, seg1_rows, seg1_chunks, transpose_ld, pad_; };
+struct TcPackBatch { int count; TcPackJob j[TC_PACK_JOBS]; };
+template <bool BF16>
+__global__ void tc_pack_batched_kernel(const __grid_constant__ TcPackBatch pb) {
+  const TcPackJob& j = pb.j[blockIdx.x / TC_PACK_BLOCKS];
+  tc_pack_body<BF16>(j.w, j.b, j.n_out, j.Npad, j.seg0_rows, j.seg0_chunks, j.seg1_rows, j.seg1_chunks, j.pw, j.pb,
+                     j.transpose_ld, (int)(blockIdx.x % TC_PACK_BLOCKS), TC_PACK_BLOCKS);
 }
 
 static int tc_pack_fill(vqn_net* net, int p, cudaStream_t s) {
@@ -1560,6 +1582,51 @@ extern "C" int vqn_net_forward_train(vqn_ctx* ctx, vqn_net* net, const float* x,
     if (!is_output) { B.pg.layers[j].save = y[j]; B.pg.layers[j].save_ld = (int)ldy[j]; }
   }
   return tc_launch(ctx, B.pg, precision, s);
+}
+
+// vqn_net_repack_tc for several networks in ONE launch (packs that do not exist yet are built first, the usual way)
+extern "C" int vqn_nets_repack_tc(vqn_net* const* nets, int count, int precision, vqn_stream stream) {
+  VQN_CHECK_ARG(nets && count >= 1 && (precision == VQN_PREC_TF32X3 || precision == VQN_PREC_BF16), "nets_repack_tc args");
+  const int p = precision == VQN_PREC_BF16 ? 1 : 0;
+  const int E = p == 1 ? 64 : 32;
+  cudaStream_t s = vqn_cs(stream);
+  TcPackBatch batch;
+  batch.count = 0;
+  vqn_ctx* ctx = nullptr;
+  auto flush = [&]() -> int {
+    if (batch.count == 0) return VQN_OK;
+    if (p == 1) tc_pack_batched_kernel<true><<<batch.count * TC_PACK_BLOCKS, 256, 0, s>>>(batch);
+    else tc_pack_batched_kernel<false><<<batch.count * TC_PACK_BLOCKS, 256, 0, s>>>(batch);
+    VQN_CUDA(cudaGetLastError());
+    ctx->launches.fetch_add(1);
+    batch.count = 0;
+    return VQN_OK;
+  };
+  for (int q = 0; q < count; ++q) {
+    vqn_net* net = nets[q];
+    VQN_CHECK_ARG(net, "nets_repack_tc: null network");
+    ctx = net->ctx;
+    if (!net->tc_pack[p]) { TcPack* tp; int rc = tc_pack_get(net, precision, s, &tp); if (rc != VQN_OK) return rc; continue; }
+    TcPack* tp = net->tc_pack[p];
+    const vqn_net_desc& d = net->desc;
+    for (int i = 0; i < d.n_layers; ++i) {
+      const bool after_skip = (d.skip_at >= 0 && i == d.skip_at + 1);
+      const int seg0_rows = (i == 0) ? d.in_dim : d.widths[i - 1];
+      const int seg1_rows = after_skip ? d.in_dim : 0;
+      for (int t = 0; t < (tp->has_T ? 2 : 1); ++t) {
+        if (batch.count == TC_PACK_JOBS) { int rc = flush(); if (rc != VQN_OK) return rc; }
+        TcPackJob& j = batch.j[batch.count++];
+        if (t == 0) {
+          j = {d.w[i], d.b[i], tp->w[i], tp->bias[i], d.widths[i], tp->Npad[i], seg0_rows, vqn_round_up(seg0_rows, E) / E,
+               seg1_rows, vqn_round_up(seg1_rows, E) / E, 0, 0};
+        } else {
+          j = {d.w[i], nullptr, tp->wT[i], tp->biasT[i], seg0_rows + seg1_rows, tp->NpadT[i], d.widths[i],
+               vqn_round_up(d.widths[i], E) / E, 0, 0, d.widths[i], 0};
+        }
+      }
+    }
+  }
+  return flush();
 }
 
 // refresh (or build) only the tensor-core weight images of `precision` from the caller's current weights

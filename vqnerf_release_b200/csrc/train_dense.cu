@@ -80,17 +80,17 @@ __device__ __forceinline__ float4 load4(const float* base, long long ld, int out
 }
 
 template <bool A_TRANS, bool B_TRANS, int EPI>
-__global__ void __launch_bounds__(THREADS) dense_gemm_kernel(GemmParams p) {
+__device__ __forceinline__ void gemm_tile(const GemmParams& p, const int bx, const int by, const int bz) {
   // A tile: !A_TRANS -> As[m][k] (stride LDK), A_TRANS -> As[k][m] (stride LDR); same for B with n
   __shared__ __align__(16) float As[A_TRANS ? BK * LDR : BM * LDK];
   __shared__ __align__(16) float Bs[B_TRANS ? BN * LDK : BK * LDR];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int m0 = bx * BM, n0 = by * BN;
   int k_begin = 0, k_end = p.K;
   if (EPI == EPI_ATOMIC) {
-    k_begin = blockIdx.z * p.k_split;
+    k_begin = bz * p.k_split;
     k_end = min(p.K, k_begin + p.k_split);
   }
   float acc_m[2][4][4], acc_c[2][4][4];
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(THREADS) dense_gemm_kernel(GemmParams p) {
 
   // bias gradient fused into the weight-gradient GEMM: the CTAs of the first row-tile also sum the columns of
   // every dZ tile they stage (thread t < 64 owns column n0 + t)
-  const bool do_colsum = EPI == EPI_ATOMIC && p.colsum != nullptr && blockIdx.x == 0 && tid < BN;
+  const bool do_colsum = EPI == EPI_ATOMIC && p.colsum != nullptr && bx == 0 && tid < BN;
   float csum = 0.f;
   if (k_begin < k_end) gload(k_begin);
   for (int k0 = k_begin; k0 < k_end; k0 += BK) {
@@ -207,12 +207,37 @@ __global__ void __launch_bounds__(THREADS) dense_gemm_kernel(GemmParams p) {
             const float y = p.yprev[(long long)m * p.ldy + n];
             v *= (p.act_prev == VQN_ACT_RELU) ? (y > 0.f ? 1.f : 0.f) : y * (1.f - y);
           }
-          if (p.accumulate) v += *dst;
-          *dst = v;
+          if (p.accumulate == 2) atomicAdd(dst, v);        // several problems of a batch add into the same buffer
+          else { if (p.accumulate) v += *dst; *dst = v; }
         } else {
           atomicAdd(dst, v);
         }
       }
+}
+
+template <bool A_TRANS, bool B_TRANS, int EPI>
+__global__ void __launch_bounds__(THREADS) dense_gemm_kernel(GemmParams p) {
+  gemm_tile<A_TRANS, B_TRANS, EPI>(p, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// Batched form: up to GB_MAX independent GEMMs of one kind in ONE launch (the same-level layers of the six head networks,
+// or every weight-gradient GEMM of the step).  The training batch is 8192 rows, a single layer is 20 us of latency on a
+// fraction of the SMs, and a step had ~57 of them in a row; a CTA finds its problem in the prefix table of tile counts.
+constexpr int GB_MAX = 32;
+struct GemmBatch {
+  int count;
+  int tile_start[GB_MAX + 1];         // first linear tile of problem i; tile_start[count] = grid size
+  int tiles_x[GB_MAX], tiles_y[GB_MAX];
+  GemmParams p[GB_MAX];
+};
+
+template <bool A_TRANS, bool B_TRANS, int EPI>
+__global__ void __launch_bounds__(THREADS) dense_gemm_batched_kernel(const __grid_constant__ GemmBatch b) {
+  int i = 0;
+  while (i + 1 < b.count && (int)blockIdx.x >= b.tile_start[i + 1]) ++i;
+  const int t = (int)blockIdx.x - b.tile_start[i];
+  const int bx = t % b.tiles_x[i], by = (t / b.tiles_x[i]) % b.tiles_y[i], bz = t / (b.tiles_x[i] * b.tiles_y[i]);
+  gemm_tile<A_TRANS, B_TRANS, EPI>(b.p[i], bx, by, bz);
 }
 
 // dZ = dY * act'(Y) for the LAST layer of a net (no following GEMM epilogue to fuse into);
@@ -317,6 +342,68 @@ extern "C" int vqn_act_backward(vqn_ctx* ctx, const float* dy, int64_t lddy, con
   const long long total = (long long)m * n;
   act_grad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, vqn_cs(stream)>>>(dy, lddy, y, ldy, (int)m, n, act, scale,
                                                                               out_scale, out_bias, dz, lddz);
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}
+
+/* Batched forms of vqn_dense_backward_data / vqn_dense_backward_weights: `count` <= 32 independent problems in ONE launch.
+ * backward-data problems with accumulate == 2 ADD atomically (several problems may target the same dx). */
+extern "C" int vqn_dense_backward_data_batched(vqn_ctx* ctx, const vqn_dense_problem* pr, int count, vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && pr && count >= 1 && count <= GB_MAX, "dense_backward_data_batched: 1 <= count <= 32");
+  GemmBatch b = {};
+  int tiles = 0;
+  for (int i = 0; i < count; ++i) {
+    const vqn_dense_problem& q = pr[i];
+    VQN_CHECK_ARG(q.a && q.w && q.out && q.m >= 0 && q.k > 0 && q.n > 0 && q.lda >= q.n && q.ldo >= q.k,
+                  "dense_backward_data_batched: bad problem");
+    VQN_CHECK_ARG(q.act_prev == VQN_ACT_NONE || q.yprev, "dense_backward_data_batched: act_prev needs yprev");
+    GemmParams& p = b.p[b.count];
+    if (q.m == 0) continue;
+    p.A = q.a; p.lda = q.lda; p.B = q.w; p.ldb = q.n; p.C = q.out; p.ldc = q.ldo; p.M = (int)q.m; p.N = q.k; p.K = q.n;
+    p.yprev = q.yprev; p.ldy = q.ldy; p.act_prev = q.act_prev; p.accumulate = q.accumulate;
+    b.tiles_x[b.count] = (int)((q.m + BM - 1) / BM); b.tiles_y[b.count] = (q.k + BN - 1) / BN;
+    b.tile_start[b.count] = tiles;
+    tiles += b.tiles_x[b.count] * b.tiles_y[b.count];
+    ++b.count;
+  }
+  if (b.count == 0) return VQN_OK;
+  b.tile_start[b.count] = tiles;
+  dense_gemm_batched_kernel<false, true, EPI_BWD><<<tiles, THREADS, 0, vqn_cs(stream)>>>(b);
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}
+
+extern "C" int vqn_dense_backward_weights_batched(vqn_ctx* ctx, const vqn_dense_problem* pr, int count, vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && pr && count >= 1 && count <= GB_MAX, "dense_backward_weights_batched: 1 <= count <= 32");
+  GemmBatch b = {};
+  // row splits: ~4 waves of CTAs over the whole batch, shared out in proportion to the tiles of each problem
+  long long base_tiles = 0;
+  for (int i = 0; i < count; ++i) base_tiles += (long long)((pr[i].k + BM - 1) / BM) * ((pr[i].n + BN - 1) / BN);
+  if (base_tiles == 0) return VQN_OK;
+  int splits_target = (int)((4LL * ctx->sm_count + base_tiles - 1) / base_tiles);
+  if (splits_target < 1) splits_target = 1;
+  int tiles = 0;
+  for (int i = 0; i < count; ++i) {
+    const vqn_dense_problem& q = pr[i];
+    VQN_CHECK_ARG(q.a && q.w && q.out && q.m >= 0 && q.k > 0 && q.n > 0 && q.lda >= q.k && q.ldw >= q.n,
+                  "dense_backward_weights_batched: bad problem");
+    if (q.m == 0) continue;
+    GemmParams& p = b.p[b.count];
+    // a = x [m, k] (ld lda), w = dz [m, n] (ld ldw), out = dW [k, n], colsum = db
+    p.A = q.a; p.lda = q.lda; p.B = q.w; p.ldb = q.ldw; p.C = q.out; p.ldc = q.n; p.M = q.k; p.N = q.n; p.K = (int)q.m;
+    int per = (int)((q.m + splits_target - 1) / splits_target);
+    per = ((per + BK - 1) / BK) * BK;
+    if (per < 4 * BK) per = 4 * BK;
+    const int splits = (int)((q.m + per - 1) / per);
+    p.k_split = per; p.colsum = q.colsum;
+    b.tiles_x[b.count] = (q.k + BM - 1) / BM; b.tiles_y[b.count] = (q.n + BN - 1) / BN;
+    b.tile_start[b.count] = tiles;
+    tiles += b.tiles_x[b.count] * b.tiles_y[b.count] * splits;
+    ++b.count;
+  }
+  if (b.count == 0) return VQN_OK;
+  b.tile_start[b.count] = tiles;
+  dense_gemm_batched_kernel<true, false, EPI_ATOMIC><<<tiles, THREADS, 0, vqn_cs(stream)>>>(b);
   VQN_LAUNCHED(ctx);
   return VQN_OK;
 }

@@ -448,6 +448,19 @@ __global__ void copy_cols_kernel(const float* __restrict__ src, long long lds, f
   const long long r = i / w; const int c = (int)(i % w);
   dst[r * ldd + c] = src[r * lds + c];
 }
+// several column-block copies in ONE launch (the skip-concat halves and output compactions of the training step)
+#define COPY_JOBS 16
+struct CopyJob { const float* src; float* dst; long long lds, ldd, m; int w, pad_; };
+struct CopyBatch { int count; int block_start[COPY_JOBS + 1]; CopyJob j[COPY_JOBS]; };
+__global__ void copy_cols_batched_kernel(const __grid_constant__ CopyBatch b) {
+  int q = 0;
+  while (q + 1 < b.count && (int)blockIdx.x >= b.block_start[q + 1]) ++q;
+  const CopyJob& j = b.j[q];
+  const long long i = (long long)((int)blockIdx.x - b.block_start[q]) * blockDim.x + threadIdx.x;
+  if (i >= j.m * j.w) return;
+  const long long r = i / j.w; const int c = (int)(i % j.w);
+  j.dst[r * j.ldd + c] = j.src[r * j.lds + c];
+}
 __global__ void cast_f64_f32_kernel(const double* __restrict__ s, float* __restrict__ d, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) d[i] = (float)s[i];
@@ -546,6 +559,27 @@ extern "C" int vqn_copy_cols(vqn_ctx* ctx, const float* src, int64_t lds, float*
   if (m == 0) return VQN_OK;
   const long long total = (long long)m * w;
   copy_cols_kernel<<<(unsigned)((total + 255) / 256), 256, 0, vqn_cs(stream)>>>(src, lds, dst, ldd, (long long)m, w);
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}
+
+extern "C" int vqn_copy_cols_batched(vqn_ctx* ctx, const vqn_copy_job* jobs, int count, vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && jobs && count >= 1 && count <= COPY_JOBS, "copy_cols_batched: 1 <= count <= 16");
+  CopyBatch b;
+  b.count = 0;
+  int blocks = 0;
+  for (int q = 0; q < count; ++q) {
+    const vqn_copy_job& c = jobs[q];
+    VQN_CHECK_ARG(c.src && c.dst && c.m >= 0 && c.w > 0 && c.lds >= c.w && c.ldd >= c.w, "copy_cols_batched: bad job");
+    if (c.m == 0) continue;
+    b.j[b.count] = {c.src, c.dst, (long long)c.lds, (long long)c.ldd, (long long)c.m, c.w, 0};
+    b.block_start[b.count] = blocks;
+    blocks += (int)(((long long)c.m * c.w + 255) / 256);
+    ++b.count;
+  }
+  if (b.count == 0) return VQN_OK;
+  b.block_start[b.count] = blocks;
+  copy_cols_batched_kernel<<<blocks, 256, 0, vqn_cs(stream)>>>(b);
   VQN_LAUNCHED(ctx);
   return VQN_OK;
 }

@@ -74,6 +74,10 @@ class Adam:
 # Training forward: one fused tensor-core launch per network (default) or one Dense kernel per layer
 # (VQN_TRAIN_FUSED_FORWARD=0; the per-layer kernels remain the backward path either way)
 FUSED_FORWARD = os.environ.get('VQN_TRAIN_FUSED_FORWARD', '1') != '0'
+# backward GEMMs batched: the six heads level by level and all weight gradients in one launch (VQN_TRAIN_BATCHED_BACKWARD=0:
+# one launch per layer, the per-network order of round 1)
+BATCHED_BACKWARD = os.environ.get('VQN_TRAIN_BATCHED_BACKWARD', '1') != '0'
+CONCURRENT_HEADS = os.environ.get('VQN_TRAIN_CONCURRENT_HEADS', '1') != '0'
 
 
 class _NetTrain:
@@ -102,15 +106,24 @@ class _NetTrain:
     def out(self) -> torch.Tensor:
         return self.y[-1]
 
-    def forward(self, x: torch.Tensor, ldx: int) -> torch.Tensor:
+    def concat_job(self, x: torch.Tensor, ldx: int):
+        """The x half of concat(y, x) (mlp.py:47-48) as a job of abi.copy_cols_batched (None without a skip connection)."""
+        if self.skip is None:
+            return None
+        return (x, ldx, self.y[self.skip], self.ld[self.skip], self.n, self.in_dim, self.widths[self.skip])
+
+    def forward(self, x: torch.Tensor, ldx: int, prepared: bool = False) -> torch.Tensor:
+        """prepared: the caller has already refreshed the weight images (abi.nets_repack_tc) and copied the x half of the
+        skip concat (concat_job) for several networks in single launches."""
         self.x, self.ldx = x, ldx
         if FUSED_FORWARD and ldx % 4 == 0:
             # the whole network in ONE launch of the fused tcgen05 kernel (every layer's output stored for the backward
             # pass); the pre-split weight images are refreshed first because the optimizer has moved the weights
             packed = self.net.packed
-            packed.repack_tc('tf32x3')
+            if not prepared:
+                packed.repack_tc('tf32x3')
             packed.forward_train(x, ldx, self.n, self.y, self.ld, self.out_scale, self.out_bias, 'tf32x3')
-            if self.skip is not None:                                     # concat(y, x) (mlp.py:47-48)
+            if self.skip is not None and not prepared:                    # concat(y, x) (mlp.py:47-48)
                 abi.copy_cols(x, ldx, self.y[self.skip], self.ld[self.skip], self.n, self.in_dim,
                               dst_off=self.widths[self.skip])
             return self.y[-1]
@@ -126,19 +139,56 @@ class _NetTrain:
             cur, ld = self.y[i], self.ld[i]
         return self.y[-1]
 
-    def backward(self, dy: torch.Tensor, lddy: int, dW: List[torch.Tensor], dB: List[torch.Tensor],
-                 d_input: Optional[torch.Tensor] = None, ld_din: int = 0) -> None:
-        """dy: gradient w.r.t. the net output [n, out].  Adds weight gradients into dW/dB and (optionally)
-        ACCUMULATES the gradient w.r.t. the net input into d_input."""
-        nl = len(self.widths)
-        last = nl - 1
+    def weight_problems(self, dW: List[torch.Tensor], dB: List[torch.Tensor]) -> list:
+        """The weight-gradient GEMMs of every layer (dW_i += x_i^T dz_i, dB_i += colsum dz_i) as problems of ONE batched
+        launch; valid once the backward-data chain has filled every dz."""
+        out = []
+        for i, w in enumerate(self.widths):
+            xin, ldin = (self.x, self.ldx) if i == 0 else (self.y[i - 1], self.ld[i - 1])
+            out.append(abi.bwd_weights_problem(xin, ldin, self.dz[i], self.dz[i].shape[1], dW[i], dB[i], self.n,
+                                               self.k_in[i], w))
+        return out
+
+    def data_problems(self, i: int, d_input: Optional[torch.Tensor], ld_din: int, atomic: bool) -> list:
+        """Backward-data GEMMs out of layer i's dz (dz[i] must be complete): into dz[i-1] through the previous activation,
+        and the x part of a skip concat / the network input into d_input (added; atomically when `atomic`)."""
+        w = self.widths[i]
+        dz, lddz = self.dz[i], self.dz[i].shape[1]
+        acc = 2 if atomic else 1
+        out = []
+        if i > 0:
+            wp = self.widths[i - 1]
+            out.append(abi.bwd_data_problem(dz, lddz, self.net.kernels[i], self.dz[i - 1], self.dz[i - 1].shape[1],
+                                            self.y[i - 1], self.ld[i - 1], self.acts[i - 1], 0, self.n, wp, w))
+            if self.skip == i - 1 and d_input is not None:
+                out.append(abi.bwd_data_problem(dz, lddz, self.net.kernels[i], d_input, ld_din, None, 0, L.ACT_NONE, acc,
+                                                self.n, self.in_dim, w, w_row0=wp))
+        elif d_input is not None:
+            out.append(abi.bwd_data_problem(dz, lddz, self.net.kernels[0], d_input, ld_din, None, 0, L.ACT_NONE, acc,
+                                            self.n, self.in_dim, w))
+        return out
+
+    def act_backward_last(self, dy: torch.Tensor, lddy: int) -> None:
+        last = len(self.widths) - 1
         abi.act_backward(dy, lddy, self.y[last], self.ld[last], self.n, self.widths[last], self.acts[last],
                          self.out_scale, self.out_scale, self.out_bias, self.dz[last], self.dz[last].shape[1])
+
+    def backward(self, dy: torch.Tensor, lddy: int, dW: List[torch.Tensor], dB: List[torch.Tensor],
+                 d_input: Optional[torch.Tensor] = None, ld_din: int = 0, weight_list: Optional[list] = None) -> None:
+        """dy: gradient w.r.t. the net output [n, out].  Adds weight gradients into dW/dB and (optionally)
+        ACCUMULATES the gradient w.r.t. the net input into d_input.  weight_list: defer the weight-gradient GEMMs --
+        their problems are appended to the list and the caller launches them in one batch."""
+        nl = len(self.widths)
+        last = nl - 1
+        self.act_backward_last(dy, lddy)
+        if weight_list is not None:
+            weight_list += self.weight_problems(dW, dB)
         for i in range(last, -1, -1):
             w = self.widths[i]
             dz, lddz = self.dz[i], self.dz[i].shape[1]
             xin, ldin = (self.x, self.ldx) if i == 0 else (self.y[i - 1], self.ld[i - 1])
-            abi.dense_backward_weights(xin, ldin, dz, lddz, dW[i], dB[i], self.n, self.k_in[i], w)
+            if weight_list is None:
+                abi.dense_backward_weights(xin, ldin, dz, lddz, dW[i], dB[i], self.n, self.k_in[i], w)
             if i > 0:
                 wp = self.widths[i - 1]
                 # y part of the input: through the previous layer's activation -> dz[i-1]
@@ -203,6 +253,7 @@ class TrainState:
         self.sim_loss = torch.zeros((1,), dtype=F32, device=dev)
         self.acts: Dict[int, dict] = {}
         self.dirty = False
+        self.side_streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]   # forked head forwards
 
     def buffers(self, n: int) -> dict:
         if n in self.acts:
@@ -288,9 +339,17 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
     c = L.Context.get(m.device)
     xyz_c = xyz.contiguous()
     e_tmp = abi.embed(xyz_c, emb.n_freqs)
-    abi.copy_cols(e_tmp, emb.out_dims, E, E.shape[1], n, emb.out_dims)
-    h = nets['fine_enc'].forward(E, E.shape[1])
-    z_enc = nets['bottleneck'].forward(h, nets['fine_enc'].ld[-1])
+    # launches shared by several networks (the step is launch-latency-bound at 8192 rows): ONE refresh of all weight images,
+    # the x halves of the skip concats of the networks fed from the same input in one copy launch
+    prep = FUSED_FORWARD and BATCHED_BACKWARD
+    if prep:
+        abi.nets_repack_tc([nets[name].net.packed for name in NET_ORDER], 'tf32x3')
+        abi.copy_cols_batched([(e_tmp, emb.out_dims, E, E.shape[1], n, emb.out_dims, 0),
+                               (e_tmp, emb.out_dims) + nets['fine_enc'].concat_job(E, E.shape[1])[2:]], m.device)
+    else:
+        abi.copy_cols(e_tmp, emb.out_dims, E, E.shape[1], n, emb.out_dims)
+    h = nets['fine_enc'].forward(E, E.shape[1], prepared=prep)
+    z_enc = nets['bottleneck'].forward(h, nets['fine_enc'].ld[-1], prepared=prep)
     codebook = m.get_codebook()                                                   # :576, before the EMA assign
     sel_mask = _sel_mask_dev           # graph replay: a static device mask refreshed by the caller
     th = m._thres_mask(thres) if _sel_mask_dev is None else None
@@ -303,22 +362,62 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
     vq_out = abi.vq_assign(z_enc, codebook, sel_mask=sel_mask, normalize_inputs=True, want_quantize=True,
                            stats=st.stats64, want_dw=True)                        # :575-577 (l2_normalize fused)
     z_vq, idx = vq_out['quantize'], vq_out['indices']
-    base = nets['diff_main'].forward(z_enc, z)
-    ks = nets['spec_main'].forward(z_enc, z)
-    rough = nets['rough_main'].forward(z_enc, z)
-    base_c = _compact_col(base, nets['diff_main'].ld[-1], 3, B['base_c'])
-    ks_c = _compact_col(ks, nets['spec_main'].ld[-1], 1, B['ks_c'])
-    rough_c = _compact_col(rough, nets['rough_main'].ld[-1], 1, B['rough_c'])
+    if prep:
+        abi.copy_cols_batched([nets[k].concat_job(z_enc, z) for k in ('diff_main', 'spec_main', 'rough_main')] +
+                              [nets[k].concat_job(z_vq, z) for k in ('diff_vq', 'spec_vq', 'rough_vq')], m.device)
+    if prep and CONCURRENT_HEADS:
+        # The six head networks are independent given z_enc / z_vq, and one fused forward launch occupies only 64 of the 148
+        # SMs at 8192 rows (one 128-row tile per CTA): fork them over three streams (the fork / join events become edges of
+        # the captured graph).  Nothing is allocated on the side streams -- every buffer is a preallocated one.
+        cur = torch.cuda.current_stream(m.device)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        outs = {}
+        groups = (('diff_main', 'rough_vq'), ('spec_main', 'diff_vq'), ('rough_main', 'spec_vq'))
+        for si, names in enumerate(groups):
+            side = cur if si == 0 else st.side_streams[si - 1]
+            if si > 0:
+                side.wait_event(ev)
+            with torch.cuda.stream(side):
+                for k in names:
+                    outs[k] = nets[k].forward(z_vq if k.endswith('_vq') else z_enc, z, prepared=True)
+            if si > 0:
+                done = torch.cuda.Event()
+                done.record(side)
+                cur.wait_event(done)
+        base, ks, rough = outs['diff_main'], outs['spec_main'], outs['rough_main']
+    else:
+        base = nets['diff_main'].forward(z_enc, z, prepared=prep)
+        ks = nets['spec_main'].forward(z_enc, z, prepared=prep)
+        rough = nets['rough_main'].forward(z_enc, z, prepared=prep)
+    if prep:
+        base_c, ks_c, rough_c = B['base_c'], B['ks_c'], B['rough_c']
+        abi.copy_cols_batched([(base, nets['diff_main'].ld[-1], base_c, 3, n, 3, 0),
+                               (ks, nets['spec_main'].ld[-1], ks_c, 1, n, 1, 0),
+                               (rough, nets['rough_main'].ld[-1], rough_c, 1, n, 1, 0)], m.device)
+    else:
+        base_c = _compact_col(base, nets['diff_main'].ld[-1], 3, B['base_c'])
+        ks_c = _compact_col(ks, nets['spec_main'].ld[-1], 1, B['ks_c'])
+        rough_c = _compact_col(rough, nets['rough_main'].ld[-1], 1, B['rough_c'])
     albedo, spec, _, _ = abi.material_combine(base_c, ks_c, want_scaled=False)    # :590-591
     lights = m._light.reshape(1, 512, 3)
     sh = abi.shade(xyz, rayo, normal, lvis, albedo, spec, rough_c, m.lxyz, m.lareas, lights, n=n, n_total=n)
     rgb_pred = sh['rgb'].reshape(n, 3)
-    va = nets['diff_vq'].forward(z_vq, z)
-    vs = nets['spec_vq'].forward(z_vq, z)
-    vr = nets['rough_vq'].forward(z_vq, z)
-    va_c = _compact_col(va, nets['diff_vq'].ld[-1], 3, B['vq_albedo_c'])
-    vs_c = _compact_col(vs, nets['spec_vq'].ld[-1], 3, B['vq_spec_c'])
-    vr_c = _compact_col(vr, nets['rough_vq'].ld[-1], 1, B['vq_rough_c'])
+    if prep and CONCURRENT_HEADS:
+        va, vs, vr = outs['diff_vq'], outs['spec_vq'], outs['rough_vq']
+    else:
+        va = nets['diff_vq'].forward(z_vq, z, prepared=prep)
+        vs = nets['spec_vq'].forward(z_vq, z, prepared=prep)
+        vr = nets['rough_vq'].forward(z_vq, z, prepared=prep)
+    if prep:
+        va_c, vs_c, vr_c = B['vq_albedo_c'], B['vq_spec_c'], B['vq_rough_c']
+        abi.copy_cols_batched([(va, nets['diff_vq'].ld[-1], va_c, 3, n, 3, 0),
+                               (vs, nets['spec_vq'].ld[-1], vs_c, 3, n, 3, 0),
+                               (vr, nets['rough_vq'].ld[-1], vr_c, 1, n, 1, 0)], m.device)
+    else:
+        va_c = _compact_col(va, nets['diff_vq'].ld[-1], 3, B['vq_albedo_c'])
+        vs_c = _compact_col(vs, nets['spec_vq'].ld[-1], 3, B['vq_spec_c'])
+        vr_c = _compact_col(vr, nets['rough_vq'].ld[-1], 1, B['vq_rough_c'])
     sh_vq = abi.shade(xyz, rayo, normal, lvis, va_c, vs_c, vr_c, m.lxyz, m.lareas, lights, n=n, n_total=n)
     vq_rgb = sh_vq['rgb'].reshape(n, 3)
 
@@ -333,22 +432,38 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
     abi.material_combine_backward(base_c, ks_c, B['d_albedo'], B['d_spec'], B['d_spec_l'], B['d_base'], B['d_ks'])
     d_zenc = B['d_zenc']
     d_zenc.zero_()
-    nets['diff_main'].backward(B['d_base'], 3, st.dW['diff_main'], st.dB['diff_main'], d_zenc, z)
-    nets['spec_main'].backward(B['d_ks'], 1, st.dW['spec_main'], st.dB['spec_main'], d_zenc, z)
-    nets['rough_main'].backward(B['d_rough'], 1, st.dW['rough_main'], st.dB['rough_main'], d_zenc, z)
     # VQ branch (d_zvq already holds the pair-smoothness gradient)
     abi.shade_backward(xyz, rayo, normal, lvis, va_c, vs_c, vr_c, m.lxyz, m.lareas, m._light, B['d_vqrgb'],
                        B['d_vq_albedo'], B['d_vq_spec'], B['d_vq_rough'], st.d_light)
     d_zvq = B['d_zvq']
-    nets['diff_vq'].backward(B['d_vq_albedo'], 3, st.dW['diff_vq'], st.dB['diff_vq'], d_zvq, z)
-    nets['spec_vq'].backward(B['d_vq_spec'], 3, st.dW['spec_vq'], st.dB['spec_vq'], d_zvq, z)
-    nets['rough_vq'].backward(B['d_vq_rough'], 1, st.dW['rough_vq'], st.dB['rough_vq'], d_zvq, z)
+    heads = [('diff_main', B['d_base'], 3, d_zenc), ('spec_main', B['d_ks'], 1, d_zenc),
+             ('rough_main', B['d_rough'], 1, d_zenc), ('diff_vq', B['d_vq_albedo'], 3, d_zvq),
+             ('spec_vq', B['d_vq_spec'], 3, d_zvq), ('rough_vq', B['d_vq_rough'], 1, d_zvq)]
+    wlist: list = []                       # every weight-gradient GEMM of the step: ONE batched launch at the end
+    if BATCHED_BACKWARD:
+        # the six heads level by level: the same-level backward-data GEMMs of all heads are independent -> one launch per
+        # level (3 launches instead of 24); the three heads of a branch add into the same d_z atomically
+        for name, dy, lddy, _ in heads:
+            nets[name].act_backward_last(dy, lddy)
+        for level in (2, 1, 0):
+            probs = []
+            for name, _, _, dzin in heads:
+                probs += nets[name].data_problems(level, dzin, z, atomic=True)
+            abi.dense_backward_data_batched(probs, m.device)
+        for name, _, _, _ in heads:
+            wlist += nets[name].weight_problems(st.dW[name], st.dB[name])
+    else:
+        for name, dy, lddy, dzin in heads:
+            nets[name].backward(dy, lddy, st.dW[name], st.dB[name], dzin, z)
     commit_coef = lw['vq_loss_weight'] * m.vq_layer.commitment_cost * 2.0 * inv_gbs / z
     abi.vq_backward(z_enc, idx, codebook, d_zvq, commit_coef, d_zenc, accumulate=True)
     d_h = B['d_h']
     d_h.zero_()
-    nets['bottleneck'].backward(d_zenc, z, st.dW['bottleneck'], st.dB['bottleneck'], d_h, d_h.shape[1])
-    nets['fine_enc'].backward(d_h, d_h.shape[1], st.dW['fine_enc'], st.dB['fine_enc'])
+    wl = wlist if BATCHED_BACKWARD else None
+    nets['bottleneck'].backward(d_zenc, z, st.dW['bottleneck'], st.dB['bottleneck'], d_h, d_h.shape[1], weight_list=wl)
+    nets['fine_enc'].backward(d_h, d_h.shape[1], st.dW['fine_enc'], st.dB['fine_enc'], weight_list=wl)
+    if wlist:
+        abi.dense_backward_weights_batched(wlist, m.device)
 
     # ---- the single collective: [gradients | VQ statistics | loss sums] --------------------------------------
     abi.cast_f64_f32(st.stats64, st.stats32)
