@@ -617,6 +617,43 @@ def ref_call(scene: Scene, batch: Dict[str, np.ndarray], mode: str = 'vali', dty
     return out
 
 
+def unit_call(scene: Scene, batch: Dict[str, np.ndarray], mode: str = 'vali', dtype=torch.float64) -> Dict[str, torch.Tensor]:
+    """models/nfr_unit.py:182-271 forward (the warm-up model: the main branch without a VQ layer; scene.nets carries
+    diff_main / spec_main / rough_main as its diff_out / spec_out / rough_out): full-length pred dict entries."""
+    dt = dtype
+    alpha = _t(batch['alpha'], dt)
+    mask = alpha[:, 0] > 0
+    rayo, xyz, normal = (_t(batch[k], dt)[mask] for k in ('rayo', 'xyz', 'normal'))
+    lvis = _t(batch['lvis'], dt)[mask] if batch.get('lvis') is not None else None
+    lxyz, lareas = _t(scene.lxyz, torch.float32).to(dt), _t(scene.lareas, torch.float32).to(dt)
+    surf2l, surf2c = calc_ldir(lxyz, xyz), calc_vdir(rayo, xyz)
+    normal_pred = normal_correct(normal, surf2c)
+    nets = scene.nets
+    z_bias = pred_enc_at(nets, xyz)                                                # :208 _pred_bias_at
+    basecolor = pred_head(nets, 'diff_main', z_bias, scene.albedo_slope, scene.albedo_bias)
+    rough = pred_head(nets, 'rough_main', z_bias)
+    ks = pred_head(nets, 'spec_main', z_bias)
+    spec, albedo = ks * basecolor, (1 - ks) * basecolor                            # :213-214
+    brdf, brdf_spec, brdf_diff = get_brdf(surf2l, surf2c, normal_pred, albedo, rough, spec)
+    light = torch.clamp(_t(scene.light, dt), min=0.0)                              # :321-327 the light property clips at 0
+    gamma = None if scene.data_type == 'nerf' else scene.gamma
+    rgb_pred, _ = render(brdf, surf2l, normal_pred, lareas, light, lvis, None, gamma)
+    n = alpha.shape[0]
+
+    def scatter(v):
+        full = torch.zeros((n,) + tuple(v.shape[1:]), dtype=v.dtype)
+        full[mask] = v
+        return full
+    to_s = linear2srgb if scene.data_type == 'nerf' else (lambda v: v)
+    out = {'rgb': scatter(to_s(rgb_pred)), 'normal': scatter(normal_pred), 'albedo': scatter(albedo),
+           'spec': scatter(spec), 'rough': scatter(rough), 'ks': scatter(ks), 'basecolor': scatter(basecolor),
+           'xyz': scatter(xyz), 'z_bias': scatter(z_bias), '_rgb_linear': rgb_pred}
+    if mode != 'train':
+        out['rgb_diff'] = scatter(render(brdf_diff, surf2l, normal_pred, lareas, light, lvis, None, gamma)[0])
+        out['rgb_spec'] = scatter(render(brdf_spec, surf2l, normal_pred, lareas, light, lvis, None, gamma)[0])
+    return out
+
+
 # ----------------------------------------------------------------------------
 # training step: compute_loss (models/vq_nfr.py:876-986) + train_iter (train_nfr.py:562-576)
 # ----------------------------------------------------------------------------

@@ -272,7 +272,7 @@ class Model:
         else:
             id_, hw, _, _, _, alpha, pred_alpha, xyz, _ = batch
         row_idx, n_act = abi.compact_mask(alpha)
-        n = int(n_act.item())
+        n = int(n_act.item())             # z_pred [n_active, z] is the return value: its SHAPE is the count (as boolean_mask)
         z_pred = abi.pred_enc_at(self.net['fine_enc'].packed, self.net['bottleneck'].packed,
                                  self.embedder['xyz'].n_freqs, xyz, row_idx=row_idx, n=n, precision=self.precision)
         return {'id': id_, 'hw': hw, 'z_pred': z_pred}
@@ -283,9 +283,13 @@ class Model:
         id_, hw, rayo, rayd, rgb, alpha, pred_alpha, xyz, normal, lvis = self._unpack(batch, ref_batch)
         n_total = alpha.shape[0]
         row_idx, n_act = abi.compact_mask(alpha)
-        n = int(n_act.item())
+        # Outside training no output shape depends on the foreground count, so there is no host round trip: the compact
+        # rows are computed for row_idx[0 .. n_act) with the count read on the device, rows beyond it are never scattered
+        # (the reference syncs in tf.boolean_mask).  The EMA statistics of mode == 'train' need the exact row count.
+        n, n_dev = (int(n_act.item()), None) if mode == 'train' else (n_total, n_act)
         z_enc = abi.pred_enc_at(self.net['fine_enc'].packed, self.net['bottleneck'].packed,
-                                self.embedder['xyz'].n_freqs, xyz, row_idx=row_idx, n=n, precision=self.precision)
+                                self.embedder['xyz'].n_freqs, xyz, row_idx=row_idx, n=n, n_dev=n_dev,
+                                precision=self.precision)
         z_norm = abi.l2_normalize_rows(z_enc)
         codebook = self.get_codebook()
         vq_outs = self.vq_layer(z_norm, codebook, is_training=(mode == 'train'), thres=self._thres_mask(thres),
@@ -293,8 +297,8 @@ class Model:
         embed_ind = (vq_outs['encoding_indices'] + 1).to(torch.float32)
         pred, gt = {'alpha': pred_alpha}, {'alpha': alpha}
         loss_kwargs = {'mode': mode}
-        embed = abi.scatter_rows(embed_ind[:, None], row_idx, n_total, n=n)
-        xyz_s = abi.scatter_rows(torch.index_select(xyz, 0, row_idx[:n].long()), row_idx, n_total, n=n)
+        embed = abi.scatter_rows(embed_ind[:, None], row_idx, n_total, n_dev=n_dev, n=n)
+        xyz_s = xyz * (alpha[:, :1] > 0).to(xyz.dtype)           # scatter_nd(ind, boolean_mask(xyz)) without the gather
         to_vis = {'id': id_, 'hw': hw, 'embed': embed, 'xyz': xyz_s}
         for k, v in pred.items():
             to_vis['pred_' + k] = v
@@ -433,9 +437,10 @@ class Model:
         id_, hw, rayo, rayd, rgb, alpha, pred_alpha, xyz, normal, lvis = self._unpack(batch, ref_batch)
         n_total = alpha.shape[0]
         row_idx, n_act = abi.compact_mask(alpha)
-        n = int(n_act.item())
+        n, n_dev = (int(n_act.item()), None) if mode == 'train' else (n_total, n_act)      # (see fast_embed)
         z_enc = abi.pred_enc_at(self.net['fine_enc'].packed, self.net['bottleneck'].packed,
-                                self.embedder['xyz'].n_freqs, xyz, row_idx=row_idx, n=n, precision=self.precision)
+                                self.embedder['xyz'].n_freqs, xyz, row_idx=row_idx, n=n, n_dev=n_dev,
+                                precision=self.precision)
         codebook = self.get_codebook()
         vq_outs = self.vq_layer(abi.l2_normalize_rows(z_enc), codebook, is_training=(mode == 'train'),
                                 thres=self._thres_mask(thres), roll=roll, return_encodings=False,
@@ -443,9 +448,9 @@ class Model:
         embed_ind = (vq_outs['encoding_indices'] + 1).to(torch.float32)
         basecolor, ks, rough = abi.pred_heads(self.net['diff_main'].packed, self.net['spec_main'].packed,
                                               self.net['rough_main'].packed, z_enc, self.albedo_slope,
-                                              self.albedo_bias, self.precision)
-        albedo, spec, _, _ = abi.material_combine(basecolor, ks)
-        sc = lambda v: abi.scatter_rows(v, row_idx, n_total, n=n)
+                                              self.albedo_bias, self.precision, n_dev=n_dev)
+        albedo, spec, _, _ = abi.material_combine(basecolor, ks, n_dev=n_dev)
+        sc = lambda v: abi.scatter_rows(v, row_idx, n_total, n_dev=n_dev, n=n)
         pred = {'alpha': pred_alpha, 'albedo': sc(albedo), 'spec': sc(spec), 'rough': sc(rough),
                 'embed': sc(embed_ind[:, None])}
         gt = {'alpha': alpha}
