@@ -138,21 +138,19 @@ class ClockSampler:
 
 def ncu_traffic(n, probes, precision):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r1e_ncu_traffic.json) -- only valid for the workload it was captured on, else None."""
-    p = os.path.join(ROOT, 'profiles', 'r1e_ncu_traffic.json')
+    (profiles/r2c_ncu_traffic.json) -- only valid for the workload it was captured on, else None."""
+    p = os.path.join(ROOT, 'profiles', 'r2c_ncu_traffic.json')
     try:
         d = json.load(open(p))
         w = d['workload']
         if (w['points'], w['probes'], w['precision']) != (n, probes, precision):
             return None
-        k = d['per_launch_dram_bytes']
-        f = k['mlp_tc_kernel<tf32x3> encoder+heads, ONE launch (r1f, per-CTA L2-resident latent scratch)']
-        return {'bytes': f['read'] + f['write'],
+        f = d['per_launch_dram_bytes']['mlp_tc_kernel<tf32x3> encoder+heads, ONE launch (640000 points)']
+        return {'bytes': f['read'] + f['write'], 'tensor_pct': f['sm__pipe_tensor_cycles_active_pct'],
                 'note': 'dram__bytes_read.sum + dram__bytes_write.sum of the single encoder+heads launch: the latent z '
-                        '[128,256] tile of a CTA goes through a per-CTA scratch that stays in L2 (the two-launch form '
-                        'moved 1.28 GB per view); reads = xyz + weights, the 17.9 MB of outputs were still in L2 when '
-                        'the kernel ended; algorithmic bytes: 40 B/point = 25.6 MB',
-                'source': 'profiles/r1e_ncu_traffic.json'}
+                        '[128,256] tile of a CTA goes through a per-CTA scratch that stays in L2; reads = xyz + weights, the '
+                        '17.9 MB of outputs were still in L2 when the kernel ended; algorithmic bytes: 40 B/point = 25.6 MB',
+                'source': 'profiles/r2c_ncu_traffic.json, profiles/r2c_ncu_full_mlp_tc_main.txt'}
     except Exception:
         return None
 
@@ -313,7 +311,9 @@ def bench_train_step(dev, rank, world, args):
             'allreduce_ms': ar_ms, 'allreduce_bytes': int(st.gflat.numel() * 4), 'kernel_launches_per_step': int(launches),
             'mlp_tflops': TRAIN_FLOP_PER_RAY * n / (ms * 1e-3) / 1e12, 'loss': float(loss), 'eager_ms_per_step': eager_ms,
             'note': 'whole step (fwd, loss, bwd, all-reduce, EMA, Adam) replayed from one CUDA graph; forward = one fused '
-                    'tcgen05 launch per network with saved activations, backward = 3xTF32 dense kernels; '
+                    'tcgen05 launch per network with saved activations (the six heads forked over three streams inside the '
+                    'graph), backward = 3xTF32 mma.sync GEMMs batched per level (six heads: 3 launches; all weight gradients: '
+                    '1 launch); '
                     'eager_ms_per_step = the same kernels launched one by one from Python'}
 
 
@@ -743,9 +743,11 @@ def run_ours(args):
             if tr is not None:
                 roof['traffic'] = tr['bytes']
                 roof['traffic_note'] = tr['note'] + ' [' + tr['source'] + ']'
-            roof['binding_resource'] = ('shared-memory port (128 B/clk/SM): UMMA operand reads + A-chunk stores + weight '
-                                        'copies, and on the N = 128 layers the producers\' chunk rate; see DESIGN.md 4.1 '
-                                        'and benchmarks/tc_trace.py')
+            roof['binding_resource'] = ('the producer warps (drain -> bias / activation -> hi/lo split -> swizzled store -> fence -> '
+                                        'arrive): a dependent chain of ~2000 cycles per 32-K chunk and group at 96 registers / 16 '
+                                        'warps; issue slots 44 %, tensor pipe 41 % (profiles/r2c_ncu_source_mlp_tc_main.txt); the '
+                                        'MMA issue path (per-instruction election loops) was the bound until round 2 -- see '
+                                        'DESIGN.md 4.1')
             if args.precision == 'tf32x3':
                 # the kernel evaluates the two correction products as ONE bf16 MMA of twice the K, i.e. 4 instead of 6
                 # bf16-equivalent MMA units per fp32-equivalent product: its own instruction stream has a higher ceiling
@@ -753,8 +755,8 @@ def run_ours(args):
                 roof['executed_scheme_note'] = ('peak above = three kind::tf32 MMAs per product (the plain 3xTF32 split); the '
                                                 'kernel issues 1 tf32 + 1 bf16(K=16) MMA per 8 K-values = bf16 peak / 4 = '
                                                 '%.0f TFLOP/s fp32-equivalent; ncu sm__pipe_tensor_cycles_active of the fused '
-                                                'launch: 31 %% (profiles/r1f_ncu_full_mlp_tc_fused.txt)'
-                                                % (bf16_peak / 4))
+                                                'launch: %s %% (profiles/r2c_ncu_full_mlp_tc_main.txt)'
+                                                % (bf16_peak / 4, ('%.0f' % tr['tensor_pct']) if tr is not None else '41'))
         shade_bytes = n * (2048 + 36 + 28 + 12 * (1 + P))
         kernels = {
             'mlp_main': {'ms': mlp_ms, 'tflops': MLP_FLOP * n / (mlp_ms * 1e-3) / 1e12},
