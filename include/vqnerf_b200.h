@@ -236,6 +236,13 @@ int vqn_material_combine(vqn_ctx* ctx, const float* basecolor, const float* ks, 
 int vqn_peer_clear_background(vqn_ctx* ctx, const float* alpha, int alpha_stride, int64_t n_local, int64_t peer_row0,
                               int width, float* const* peer_ptrs, int n_peers, vqn_stream stream);
 
+/* Frame hand-shake of the fused gather on ONE destination rank (instead of a barrier over all ranks): a sender publishes
+ * "frame f finished" into the destination's flags and waits until frame f-1 was consumed; the destination acknowledges
+ * frame f-1 and waits for every sender's frame f.  counter: this rank's frame count (device int32, starts at 0);
+ * local_flags / peer_flags[r]: world+1 int32 of symmetric memory on this rank / on rank r (HOST array of P2P pointers). */
+int vqn_peer_frame_sync(vqn_ctx* ctx, int32_t* counter, const int32_t* local_flags, int32_t* const* peer_flags, int world,
+                        int rank, int dst, vqn_stream stream);
+
 /* fast_render(edit_mask=, edit_material=) (models/vq_nfr.py:258-260 `_update_material`, :293-295, :324-330): compact rows
  * whose edit_mask[row_idx[i] * mask_stride] > 0 get albedo := diff3, spec := spec3, rough := rough1 (HOST pointers; NULL =
  * the reference's "update[0] < 0: leave alone"), in place; the opt_scale'd copies the shading kernel reads are refreshed

@@ -111,6 +111,7 @@ SIGNATURES = {
     'vqn_render': (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _F, _P, _P]),
     'vqn_material_combine': (_I, [_P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P]),
     'vqn_peer_clear_background': (_I, [_P, _P, _I, _L, _L, _I, _P, _I, _P]),
+    'vqn_peer_frame_sync': (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     'vqn_material_edit': (_I, [_P, _P, _I, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'vqn_linear2srgb': (_I, [_P, _P, _L, _P, _P]),
     'vqn_srgb2linear': (_I, [_P, _P, _L, _P, _P]),

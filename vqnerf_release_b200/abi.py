@@ -373,6 +373,15 @@ def peer_clear_background(alpha, peer_ptrs, peer_row0, width):
                                             L.stream_ptr(alpha.device)))
 
 
+def peer_frame_sync(counter, local_flags, peer_flag_ptrs, world, rank, dst):
+    """Frame hand-shake of the fused gather on one destination rank (vqn_peer_frame_sync; dist.PeerImage.barrier)."""
+    import ctypes as C
+    arr = (C.c_void_p * len(peer_flag_ptrs))(*[int(p) for p in peer_flag_ptrs])
+    c = _ctx(counter)
+    L.check(c.lib.vqn_peer_frame_sync(c.handle, counter.data_ptr(), local_flags.data_ptr(), C.cast(arr, C.c_void_p),
+                                      int(world), int(rank), int(dst), L.stream_ptr(counter.device)))
+
+
 def material_edit(edit_mask, edit_material, row_idx, n_dev, albedo, spec, rough, opt_scale=None, albedo_s=None,
                   spec_s=None):
     """fast_render's `_update_material` (models/vq_nfr.py:258-260, 324-330), in place on the compact tensors.  A channel

@@ -10,6 +10,8 @@ processes (geo/NeuS-ours2/gen_geo.py:141-146).
 """
 from __future__ import annotations
 
+import os
+
 from typing import List, Optional, Tuple
 
 import torch
@@ -129,6 +131,15 @@ class PeerImage:
             self._ptrs.append(ptrs if dst is None else [ptrs[int(dst)]])
         self.row0, self.row1 = shard_rows(self.n_total, self.rank, self.world)
         self._frame = 0
+        # gather on one rank: per-frame flag hand-shake instead of a barrier over all ranks (vqn_peer_frame_sync)
+        self._flags = None
+        if dst is not None and self.world > 1 and os.environ.get('VQN_PEER_FLAG_SYNC', '1') != '0':
+            self._flags = symm_mem.empty((self.world + 1,), dtype=torch.int32, device=device)
+            self._flags.zero_()
+            fh = symm_mem.rendezvous(self._flags, self.group)
+            self._flag_ptrs = [int(p) for p in fh.buffer_ptrs]
+            self._flag_handle = fh
+            self._counter = torch.zeros((1,), dtype=torch.int32, device=device)
         torch.cuda.synchronize(device)
         self._handles[0].barrier()                       # every rank's zero-fill is done before anyone stores
 
@@ -155,4 +166,8 @@ class PeerImage:
         abi.peer_clear_background(alpha_local, self.peer_ptrs, self.row0 + int(row_off), self.width)
 
     def barrier(self) -> None:
-        self.handle.barrier()
+        if self._flags is not None:
+            from . import abi
+            abi.peer_frame_sync(self._counter, self._flags, self._flag_ptrs, self.world, self.rank, int(self.dst))
+        else:
+            self.handle.barrier()
