@@ -5,14 +5,20 @@ import this module; only `tests/`, `__graft_entry__.smoke()` and the
 `cpu_baseline` / `--impl reference` legs of `bench.py` do, and only as the
 checker / the CPU baseline.
 
-PARITY UNPINNED: the reference's decomp stage is TensorFlow 2.4.1 + dm-sonnet
-2.0.0 + tensorflow-probability 0.12.1, none of which is installed in this image
-(no network), and the reference ships no tests, fixtures or golden vectors for
-this path.  This file is therefore an op-for-op restatement
-of the reference's arithmetic in PyTorch-CPU (float64 = "truth", float32 =
-emulation of the TF fp32 op sequence, including the [N,512,3] intermediates the
-reference materialises).  Each function cites the reference file:line it follows
-(paths relative to /root/reference/decomp/nerfvq_nfr3/).
+PARITY PINNED against the reference's own code, executed here: the reference's decomp stage is TensorFlow 2.4.1 +
+dm-sonnet 2.0.0 + tensorflow-probability 0.12.1, none of which is installable in this image (no network), and the
+reference ships no tests, fixtures or golden vectors for this path -- but its model code
+is pure `tf.*` calls, so `oracle/gen_golden_decomp_ref.py` (and `gen_golden_ref_nfr.py`, `gen_golden_nfr_unit.py`,
+`gen_golden_shape_unit.py`) import the UNMODIFIED reference modules with the `oracle/tf_shim` stand-in for
+tensorflow / tensorflow_probability / sonnet first on sys.path, execute `Model.fast_render`, `Model.call`,
+`Model.vq_test`, `Model.compute_loss`, `VectorQuantizerEMA.__call__`, `microfacet.get_brdf`, ... on torch-CPU and record
+`tests/golden/{decomp_ref,ref_nfr_ref,nfr_unit_ref,shape_unit_ref}.npz`.  This file (an op-for-op restatement of the
+reference's arithmetic in PyTorch-CPU: float64 = "truth", float32 = emulation of the TF fp32 op sequence, including
+the [N,512,3] intermediates the reference materialises) is compared with those vectors to 1e-9 in
+tests/test_oracle_vs_reference_cpu.py, test_ref_nfr_cpu.py, test_nfr_unit_cpu.py; the CUDA kernels are compared with
+the same vectors in the `-m gpu` tests.  What remains a restatement is the semantics of the individual `tf.*` ops
+inside the shim (oracle/tf_shim/README.md).  Each function cites the reference file:line it follows (paths relative
+to /root/reference/decomp/nerfvq_nfr3/).
 
 Third-party arithmetic restated from published sources (not vendored in the
 reference): dm-sonnet 2.0.0 `moving_averages.ExponentialMovingAverage`
