@@ -207,6 +207,11 @@ typedef struct vqn_shade_args {
    * opt-in formats of the host-buffer path (the fp32 rows are 98 % of a view's H2D bytes); large un-split batches only */
   int32_t lvis_format;
   int64_t peer_row0;
+  /* 1: rgb is the raw, un-clipped integral (no gamma, no clip, no sRGB): the training step of non-'nerf' data applies
+   * gamma with device-resident parameters (vqn_gamma_forward) so that a captured graph follows them; warp-per-point
+   * kernel only (small batches) */
+  int32_t no_clip;
+  int32_t reserved0;
 } vqn_shade_args;
 
 /* _calc_ldir + _calc_vdir + _normal_correct + _eval_brdf_at (util/microfacet.py:9-89) + _render
@@ -291,6 +296,14 @@ int vqn_dense_backward_data(vqn_ctx* ctx, const float* dz, int64_t lddz, const f
 /* dW[k,n] += X[m,k]^T . dZ[m,n];  db[n] += colsum(dZ)  (gradient buffers are accumulated: zero them per step) */
 int vqn_dense_backward_weights(vqn_ctx* ctx, const float* x, int64_t ldx, const float* dz, int64_t lddz, float* dw,
                                float* db, int64_t m, int k, int n, vqn_stream stream);
+/* Learnable tone scaling of non-'nerf' data in the TRAINING step (models/vq_nfr.py:715-718, 736-745):
+ *   out = clip((lin * gpar[0]) ^ clip(gpar[1], 0, 5), 0, 1),  gpar = [_gamma_bias, _gamma_index] in DEVICE memory;
+ * backward: d_lin = d_out * d out / d lin (both clips pass the gradient: clip_by_value_preserve_gradient) and
+ * d_gpar[0..1] += the sums over all `count` elements (atomic).  lin >= 0 (a light integral). */
+int vqn_gamma_forward(vqn_ctx* ctx, const float* lin, const float* gpar, float* out, int64_t count, vqn_stream stream);
+int vqn_gamma_backward(vqn_ctx* ctx, const float* lin, const float* gpar, const float* d_out, float* d_lin, float* d_gpar,
+                       int64_t count, vqn_stream stream);
+
 /* Batched backward GEMMs: up to 32 INDEPENDENT problems of one kind in ONE launch (the same-level layers of the head
  * networks; every weight-gradient GEMM of the step).  Fields per problem:
  *   backward-data:    a = dZ [m,n] (ld lda), w = W [k,n] row-major, out = dX [m,k] (ld ldo), yprev/ldy/act_prev as in

@@ -760,9 +760,12 @@ def train_step(scene: Scene, batch: Dict[str, np.ndarray], vq: VectorQuantizerEM
     nets_t = {k: Net([leaf(w) for w in n.weights], [leaf(b) for b in n.biases], n.acts, n.skip_at)
               for k, n in scene.nets.items()}
     light_t = leaf(scene.light)
+    # non-'nerf' data: the tone parameters are trainable too (vq_nfr.py:736-745: [_gamma_bias, clip_preserve(_gamma_index, 0, 5)])
+    g_bias, g_index = leaf(np.asarray(scene.gamma[0], np.float64)), leaf(np.asarray(scene.gamma[1], np.float64))
+    gamma_t = (g_bias, clip_preserve_grad(g_index, 0.0, 5.0)) if scene.data_type != 'nerf' else scene.gamma
     sc = Scene(nets=nets_t, light=light_t, codebook=scene.codebook, probes=None,
                albedo_slope=scene.albedo_slope, albedo_bias=scene.albedo_bias, data_type=scene.data_type,
-               gamma=scene.gamma, lxyz=scene.lxyz, lareas=scene.lareas)
+               gamma=gamma_t, lxyz=scene.lxyz, lareas=scene.lareas)
     out = call_forward(sc, batch, vq, 'train', thres, roll, dt)
     cb_after = leaf(out['update'].detach().numpy())                 # _codebook.assign(update) (:582-583)
     mask = out['mask']
@@ -776,6 +779,7 @@ def train_step(scene: Scene, batch: Dict[str, np.ndarray], vq: VectorQuantizerEM
     grads = {k: ([w.grad for w in n.weights], [b.grad for b in n.biases]) for k, n in nets_t.items()}
     return {'loss': weighted.detach(), 'per_example': loss.detach(), 'loss_dict': {k: v.detach() for k, v in ld.items()},
             'grads': grads, 'dlight': light_t.grad, 'dcodebook': cb_after.grad, 'update': out['update'].detach(),
+            'dgamma': (g_bias.grad, g_index.grad),
             'out': {k: (v.detach() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}}
 
 

@@ -97,3 +97,40 @@ def test_two_training_steps_vs_reference_code(ref, setup, cuda_dev):
                 err = np.abs(gb.cpu().double().numpy() - want).max()
                 # + 1e-7: a 1-wide layer's bias gradient is ONE number, a sum over the rows with cancellation (fp32 noise)
                 assert err <= 2e-4 * np.abs(want).max() + 1e-7, 'd %s.bias[%d]: %.3e' % (name, i, err)
+
+
+def test_training_step_non_nerf_data_vs_reference_code(cuda_dev):
+    """train_iter on data_type != 'nerf' (no light visibility; rgb = clip((rgb * gamma_bias) ^ clip(gamma_index, 0, 5)) with
+    TRAINABLE gamma): loss, rendered colours and the gradients of light / gamma / every bias against one step of the
+    reference's own code (tests/golden/decomp_real_ref.npz), eager and graph-replayed."""
+    from vqnerf_release_b200.nerfactor import train_nfr as T
+    g = np.load(os.path.join(os.path.dirname(GOLD), 'decomp_real_ref.npz'))
+    scene = O.synth_scene(int(g['seed']), bias_scale=float(g['bias_scale']), data_type='real')
+    scene.gamma = tuple(float(np.float32(v)) for v in g['gamma'])      # float32 variables in the reference
+    batch = O.synth_batch(int(g['n']), int(g['seed']), fg_frac=float(g['fg_frac']), with_lvis=False)
+    m = _model_from_scene(scene, cuda_dev)
+    bt = _batch_tuple(batch, cuda_dev, data_type='real')
+    loss, vis, ld = T.train_iter(m, bt, T.Adam(learning_rate=5e-4), int(g['global_bs']), thres=g['thres'], roll=g['roll'],
+                                 apply=False)
+    st = m._train_state
+    assert st.has_gamma
+    _close(loss, g['train_loss'], 'weighted loss', rtol=1e-4, atol=1e-7)
+    mask = batch['alpha'][:, 0] > 0
+    _close(vis['pred_rgb_linear'], g['train_rgb'][mask], 'rgb', rtol=1e-4, atol=5e-6)
+    _close(vis['pred_vq_rgb_linear'], g['train_vqrgb'], 'vq_rgb', rtol=1e-4, atol=5e-6)
+    dg = st.d_gamma.cpu().double().numpy()
+    want = np.array([float(g['train_d_gamma_bias'][0]), float(g['train_d_gamma_index'][0])])
+    assert np.abs(dg - want).max() <= 2e-4 * np.abs(want).max(), 'gamma gradient %s vs %s' % (dg, want)
+    d_light = g['train_d_light']
+    err = np.abs(st.d_light.cpu().double().numpy().reshape(d_light.shape) - d_light).max()
+    assert err <= 2e-4 * np.abs(d_light).max(), 'light gradient: %.3e' % err
+    for name in T.NET_ORDER:
+        for i, gb in enumerate(st.dB[name]):
+            want = g['train_d_%s_b%d' % (name, i)]
+            err = np.abs(gb.cpu().double().numpy() - want).max()
+            assert err <= 2e-4 * np.abs(want).max() + 1e-7, 'd %s.bias[%d]: %.3e' % (name, i, err)
+    # the optimizer moves the two tone parameters (they are views of the flat parameter buffer)
+    before = st.gamma_par.clone()
+    T.train_iter(m, bt, T.Adam(learning_rate=5e-4), int(g['global_bs']), thres=g['thres'], roll=g['roll'])
+    assert float((st.gamma_par - before).abs().min()) > 0
+    assert abs(m.gamma[0] - float(st.gamma_par[0])) < 1e-7

@@ -316,10 +316,7 @@ def test_training_abi_edge_cases(cuda_dev):
     scene, batch, m, _ = _train_pair(cuda_dev, 7)
     with pytest.raises(ValueError):
         T.train_iter(m, _batch_tuple(batch, cuda_dev), T.Adam(), 4)
-    # non-nerf data is refused (no gamma variables in the training kernels)
-    m.data_type = 'dtu'
-    with pytest.raises(NotImplementedError):
-        T.train_iter(m, _batch_tuple(batch, cuda_dev), T.Adam(), 4)
+    # (non-'nerf' data trains too: test_gpu_reference_vectors.py::test_training_step_non_nerf_data_vs_reference_code)
     # sampler argument checks
     with pytest.raises(ValueError):
         abi.sample_pairs(torch.ones((4,), device=cuda_dev), 2, 2, 4, 0)

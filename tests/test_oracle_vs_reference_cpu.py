@@ -186,3 +186,29 @@ def test_float32_emulation_close_to_reference_float32(ref, setup):
     for k in ('albedo', 'spec', 'rough', 'rgb_probes'):
         np.testing.assert_allclose(o[k].numpy(), ref['f32_fr_' + k], rtol=1e-5, atol=2e-6, err_msg=k)
     np.testing.assert_array_equal(o['embed'].numpy().astype(np.int64), ref['f32_fr_embed'])
+
+
+def test_training_step_non_nerf_data_matches_reference():
+    """data_type != 'nerf' (no light visibility, trainable tone scaling, vq_nfr.py:707, 715-718, 736-745): one training step
+    of the reference's own code (oracle/gen_golden_decomp_real.py) against oracle.train_step, including the gradients of
+    _gamma_bias / _gamma_index."""
+    g = np.load(os.path.join(os.path.dirname(GOLD), 'decomp_real_ref.npz'))
+    scene = O.synth_scene(int(g['seed']), bias_scale=float(g['bias_scale']), data_type='real')
+    scene.gamma = tuple(float(np.float32(v)) for v in g['gamma'])      # float32 variables in the reference
+    batch = O.synth_batch(int(g['n']), int(g['seed']), fg_frac=float(g['fg_frac']), with_lvis=False)
+    vq = O.VectorQuantizerEMA(O.Z_DIM, O.NUM_EMBED, O.COMMITMENT_COST, dtype=torch.float64)
+    r = O.train_step(scene, batch, vq, thres=g['thres'], roll=g['roll'], global_bs=int(g['global_bs']), dtype=torch.float64)
+    mask = batch['alpha'][:, 0] > 0
+    rgb_full = np.zeros((mask.shape[0], 3))
+    rgb_full[mask] = r['out']['rgb_linear'].numpy()              # no sRGB transform for this data type (:350-356)
+    np.testing.assert_allclose(rgb_full, g['train_rgb'], **TOL)
+    np.testing.assert_allclose(r['out']['vq_rgb_linear'].numpy(), g['train_vqrgb'], **TOL)
+    np.testing.assert_allclose(r['per_example'].numpy(), g['train_per_example'], **TOL)
+    np.testing.assert_allclose(r['loss'].numpy(), g['train_loss'], **TOL)
+    gtol = dict(rtol=1e-7, atol=1e-12)
+    np.testing.assert_allclose(r['dgamma'][0].numpy().reshape(-1), g['train_d_gamma_bias'], **gtol)
+    np.testing.assert_allclose(r['dgamma'][1].numpy().reshape(-1), g['train_d_gamma_index'], **gtol)
+    np.testing.assert_allclose(r['dlight'].numpy(), g['train_d_light'], **gtol)
+    for name, (gw, gb) in r['grads'].items():
+        for li, b in enumerate(gb):
+            np.testing.assert_allclose(b.numpy(), g['train_d_%s_b%d' % (name, li)], err_msg=name, **gtol)

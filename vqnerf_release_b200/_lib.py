@@ -41,7 +41,7 @@ class ShadeArgs(C.Structure):
                 ('gamma_bias', C.c_float), ('gamma_index', C.c_float),
                 ('rgb', C.c_void_p), ('rgb_diff', C.c_void_p), ('rgb_spec', C.c_void_p), ('normal_out', C.c_void_p),
                 ('peer_rgb', C.c_void_p * 8), ('n_peers', C.c_int32), ('lvis_format', C.c_int32),
-                ('peer_row0', C.c_int64)]
+                ('peer_row0', C.c_int64), ('no_clip', C.c_int32), ('reserved0', C.c_int32)]
 
 
 class NeusCompositeArgs(C.Structure):
@@ -134,6 +134,8 @@ SIGNATURES = {
     'vqn_copy_cols_batched': (_I, [_P, C.POINTER(CopyJob), _I, _P]),
     'vqn_dense_backward_data': (_I, [_P, _P, _L, _P, _P, _L, _P, _L, _I, _I, _L, _I, _I, _P]),
     'vqn_dense_backward_weights': (_I, [_P, _P, _L, _P, _L, _P, _P, _L, _I, _I, _P]),
+    'vqn_gamma_forward': (_I, [_P, _P, _P, _P, _L, _P]),
+    'vqn_gamma_backward': (_I, [_P, _P, _P, _P, _P, _P, _L, _P]),
     'vqn_dense_backward_data_batched': (_I, [_P, C.POINTER(DenseProblem), _I, _P]),
     'vqn_dense_backward_weights_batched': (_I, [_P, C.POINTER(DenseProblem), _I, _P]),
     'vqn_act_backward': (_I, [_P, _P, _L, _P, _L, _L, _I, _I, _F, _F, _F, _P, _L, _P]),

@@ -267,8 +267,9 @@ def compress_lvis(lvis: torch.Tensor, fmt: str) -> torch.Tensor:
 def shade(xyz, rayo, normal, lvis, albedo, spec, rough, lxyz, lareas, lights, *, row_idx=None, n_dev=None,
           n: Optional[int] = None, n_total: Optional[int] = None, to_srgb=False, gamma=None, clip_light0=True,
           want_split=False, want_normal=False, out_rgb: Optional[torch.Tensor] = None,
-          peer_ptrs: Optional[Sequence[int]] = None, peer_row0: int = 0):
+          peer_ptrs: Optional[Sequence[int]] = None, peer_row0: int = 0, no_clip: bool = False):
     """Fused _calc_ldir/_calc_vdir/_normal_correct/_eval_brdf_at/_render.  lights [1+P,512,3].
+    no_clip: the raw, un-clipped integral (training of non-'nerf' data applies gamma afterwards: gamma_forward).
     Returns dict(rgb [n_total,1+P,3], rgb_diff, rgb_spec, normal) (full-length when row_idx is given)."""
     xyz, rayo, normal = _f(xyz), _f(rayo), _f(normal)
     albedo, spec, rough = _f(albedo), _f(spec), _f(rough)
@@ -303,6 +304,7 @@ def shade(xyz, rayo, normal, lvis, albedo, spec, rough, lxyz, lareas, lights, *,
     if gamma is not None:
         a.use_gamma, a.gamma_bias, a.gamma_index = 1, float(gamma[0]), float(gamma[1])
     a.rgb = rgb.data_ptr()
+    a.no_clip = int(bool(no_clip))
     if peer_ptrs:
         if len(peer_ptrs) > 8:
             raise ValueError('at most 8 peers (one NVSwitch box)')
@@ -742,6 +744,22 @@ def act_backward(dy, lddy, y, ldy, m, n, act, scale, out_scale, out_bias, dz, ld
 def copy_cols(src, lds, dst, ldd, m, w, dst_off=0):
     c = _ctx(src)
     L.check(c.lib.vqn_copy_cols(c.handle, _p(src), lds, _p(dst, dst_off), ldd, m, w, L.stream_ptr(src.device)))
+
+
+def gamma_forward(lin, gpar, out=None):
+    """out = clip((lin * gpar[0]) ^ clip(gpar[1], 0, 5), 0, 1) with gpar = [_gamma_bias, _gamma_index] on the device."""
+    lin = _f(lin)
+    out = torch.empty_like(lin) if out is None else out
+    c = _ctx(lin)
+    L.check(c.lib.vqn_gamma_forward(c.handle, _p(lin), _p(gpar), _p(out), lin.numel(), L.stream_ptr(lin.device)))
+    return out
+
+
+def gamma_backward(lin, gpar, d_out, d_lin, d_gpar):
+    """d_lin = d_out * d out / d lin;  d_gpar[0..1] += gradients of the two tone parameters (see gamma_forward)."""
+    c = _ctx(lin)
+    L.check(c.lib.vqn_gamma_backward(c.handle, _p(lin), _p(gpar), _p(d_out), _p(d_lin), _p(d_gpar), lin.numel(),
+                                     L.stream_ptr(lin.device)))
 
 
 def copy_cols_batched(jobs, dev):

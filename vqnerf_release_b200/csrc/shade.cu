@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(SH_THREADS, 2) shade_kernel(ShadeParams P) {
             float v = out[k];
             if (a.use_gamma) v = powf(v * a.gamma_bias, a.gamma_index);    // vq_nfr.py:715-716
             if (!isfinite(v)) atomicOr(P.nonfinite, 2);                    // check_numerics (:731)
-            v = fminf(fmaxf(v, 0.f), 1.f);                                 // clip_by_value (:718)
+            if (!a.no_clip) v = fminf(fmaxf(v, 0.f), 1.f);                 // clip_by_value (:718)
             if (a.to_srgb) v = vqn_linear2srgb(v);
             a.rgb[(row * NP + p0 + p) * 3 + ch] = v;
           }
@@ -306,7 +306,9 @@ extern "C" int vqn_shade(vqn_ctx* ctx, const vqn_shade_args* args, vqn_stream st
   VQN_CHECK_ARG(a.n_peers >= 0 && a.n_peers <= 8, "shade: 0 <= n_peers <= 8");
   VQN_CHECK_ARG(a.lvis_format >= VQN_LVIS_F32 && a.lvis_format <= VQN_LVIS_U8, "shade: unknown lvis_format");
   const bool compact_lvis = a.lvis && a.lvis_format != VQN_LVIS_F32;
-  if (!split && a.n_probes <= 9 && (a.n >= 32768 || a.n_peers > 0 || compact_lvis)) return vqn_shade_pt_launch(ctx, a, vqn_cs(stream));
+  VQN_CHECK_ARG(!a.no_clip || (!a.use_gamma && !a.to_srgb && a.n_peers == 0 && !compact_lvis),
+                "shade: no_clip returns the raw integral (no gamma / sRGB / gather / compact visibility)");
+  if (!split && !a.no_clip && a.n_probes <= 9 && (a.n >= 32768 || a.n_peers > 0 || compact_lvis)) return vqn_shade_pt_launch(ctx, a, vqn_cs(stream));
   VQN_CHECK_ARG(a.n_peers == 0, "shade: the fused peer gather needs an un-split batch with at most 9 probes");
   if (compact_lvis) { vqn_set_error("shade: float16 / uint8 light visibility needs an un-split batch with at most 9 probes"); return VQN_ERR_UNSUPPORTED; }
   auto kern = a.lvis ? (split ? shade_kernel<true, true> : shade_kernel<true, false>)

@@ -380,7 +380,18 @@ extern "C" int vqn_dense_backward_weights_batched(vqn_ctx* ctx, const vqn_dense_
   long long base_tiles = 0;
   for (int i = 0; i < count; ++i) base_tiles += (long long)((pr[i].k + BM - 1) / BM) * ((pr[i].n + BN - 1) / BN);
   if (base_tiles == 0) return VQN_OK;
-  int splits_target = (int)((4LL * ctx->sm_count + base_tiles - 1) / base_tiles);
+  // every CTA of the batch does the same work (`per` rows of one 64 x 64 tile), so the launch costs whole waves: pick the
+  // split that fills ONE wave of resident CTAs (672 CTAs on 592 slots were two waves: 384 us; 588 on 592: one)
+  static int ctas_per_sm = 0;
+  if (ctas_per_sm == 0) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dense_gemm_batched_kernel<true, false, EPI_ATOMIC>, THREADS, 0) !=
+            cudaSuccess || occ < 1)
+      occ = 4;
+    ctas_per_sm = occ;
+  }
+  const long long slots = (long long)ctx->sm_count * ctas_per_sm;
+  int splits_target = (int)(slots / base_tiles);
   if (splits_target < 1) splits_target = 1;
   int tiles = 0;
   for (int i = 0; i < count; ++i) {

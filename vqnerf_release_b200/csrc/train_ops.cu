@@ -461,6 +461,28 @@ __global__ void copy_cols_batched_kernel(const __grid_constant__ CopyBatch b) {
   const long long r = i / j.w; const int c = (int)(i % j.w);
   j.dst[r * j.ldd + c] = j.src[r * j.lds + c];
 }
+// learnable tone scaling of non-'nerf' data (vq_nfr.py:715-718, 736-745); gpar = [_gamma_bias, _gamma_index] on the device
+__global__ void gamma_fwd_kernel(const float* __restrict__ lin, const float* __restrict__ gpar, float* __restrict__ out,
+                                 long long n) {
+  const float g0 = gpar[0], g1 = fminf(fmaxf(gpar[1], 0.f), 5.f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = fminf(fmaxf(powf(lin[i] * g0, g1), 0.f), 1.f);
+}
+__global__ void gamma_bwd_kernel(const float* __restrict__ lin, const float* __restrict__ gpar,
+                                 const float* __restrict__ d_out, float* __restrict__ d_lin, float* __restrict__ d_gpar,
+                                 long long n) {
+  const float g0 = gpar[0], g1 = fminf(fmaxf(gpar[1], 0.f), 5.f);
+  float s0 = 0.f, s1 = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = lin[i], u = x * g0, g = d_out[i];
+    const float um1 = powf(u, g1 - 1.0f);            // d u^g1 / d u = g1 u^(g1 - 1)
+    d_lin[i] = g * g1 * g0 * um1;
+    s0 += g * g1 * x * um1;
+    s1 += u > 0.f ? g * powf(u, g1) * logf(u) : 0.f; // TF's pow gradient uses log(x) where x > 0, else 0
+  }
+  s0 = warp_sum(s0); s1 = warp_sum(s1);
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&d_gpar[0], s0); atomicAdd(&d_gpar[1], s1); }
+}
 __global__ void cast_f64_f32_kernel(const double* __restrict__ s, float* __restrict__ d, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) d[i] = (float)s[i];
@@ -559,6 +581,26 @@ extern "C" int vqn_copy_cols(vqn_ctx* ctx, const float* src, int64_t lds, float*
   if (m == 0) return VQN_OK;
   const long long total = (long long)m * w;
   copy_cols_kernel<<<(unsigned)((total + 255) / 256), 256, 0, vqn_cs(stream)>>>(src, lds, dst, ldd, (long long)m, w);
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}
+
+extern "C" int vqn_gamma_forward(vqn_ctx* ctx, const float* lin, const float* gpar, float* out, int64_t count,
+                                 vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && lin && gpar && out && count >= 0, "gamma_forward args");
+  if (count == 0) return VQN_OK;
+  long long want = (count + 255) / 256;
+  gamma_fwd_kernel<<<(unsigned)(want < 1184 ? want : 1184), 256, 0, vqn_cs(stream)>>>(lin, gpar, out, (long long)count);
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}
+extern "C" int vqn_gamma_backward(vqn_ctx* ctx, const float* lin, const float* gpar, const float* d_out, float* d_lin,
+                                  float* d_gpar, int64_t count, vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && lin && gpar && d_out && d_lin && d_gpar && count >= 0, "gamma_backward args");
+  if (count == 0) return VQN_OK;
+  long long want = (count + 255) / 256;
+  gamma_bwd_kernel<<<(unsigned)(want < 592 ? want : 592), 256, 0, vqn_cs(stream)>>>(lin, gpar, d_out, d_lin, d_gpar,
+                                                                                   (long long)count);
   VQN_LAUNCHED(ctx);
   return VQN_OK;
 }

@@ -214,6 +214,9 @@ class TrainState:
             for k, b in zip(net.kernels, net.biases):
                 tensors += [k, b]
         tensors += [model._light, model._codebook]
+        self.has_gamma = model.data_type != 'nerf'               # learnable tone scaling [_gamma_bias, _gamma_index] (:736-745)
+        if self.has_gamma:
+            tensors += [torch.cat([model._gamma_bias.reshape(1), model._gamma_index.reshape(1)]).to(dev)]
         sizes = [_pad4(t.numel()) for t in tensors]              # 16-byte aligned views
         self.n_param = sum(sizes)
         z, k = model.z_dim, model.num_embed
@@ -250,6 +253,10 @@ class TrainState:
         model._codebook = next(it)
         self.d_light = next(git)
         self.d_codebook = next(git)
+        if self.has_gamma:
+            self.gamma_par = next(it)                             # device copy the kernels read; the model's views follow
+            self.d_gamma = next(git)
+            model._gamma_bias, model._gamma_index = self.gamma_par[0:1], self.gamma_par[1:2]
         self.sim_loss = torch.zeros((1,), dtype=F32, device=dev)
         self.acts: Dict[int, dict] = {}
         self.dirty = False
@@ -281,6 +288,7 @@ class TrainState:
             'd_albedo': e(n, 3), 'd_spec': e(n, 3), 'd_rough': e(n, 1), 'd_base': e(n, 3), 'd_ks': e(n, 1),
             'd_vq_albedo': e(n, 3), 'd_vq_spec': e(n, 3), 'd_vq_rough': e(n, 1),
             'd_zenc': e(n, z), 'd_h': e(n, m.net['fine_enc'].widths[-1]),
+            'rgb_g': e(n, 3), 'vqrgb_g': e(n, 3), 'd_rgb_lin': e(n, 3), 'd_vqrgb_lin': e(n, 3),   # non-'nerf' data: gamma
         }
         self.acts[n] = b
         return b
@@ -309,8 +317,6 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
     batch means).  `group`: torch.distributed process group for the data-parallel all-reduce (None: default
     group when initialised, else single GPU).  Rows must be (pixel, neighbour) pairs (train_nfr.py:447-448)."""
     m = model
-    if m.data_type != 'nerf':
-        raise NotImplementedError('training kernels are built for data_type == nerf (no gamma variables)')
     st = _train_state(m)
     cfg = m.config
     lw = {k: (cfg.getfloat(k, fallback=v) if hasattr(cfg, 'getfloat') else v) for k, v in LOSS_DEFAULTS.items()}
@@ -401,8 +407,13 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
         rough_c = _compact_col(rough, nets['rough_main'].ld[-1], 1, B['rough_c'])
     albedo, spec, _, _ = abi.material_combine(base_c, ks_c, want_scaled=False)    # :590-591
     lights = m._light.reshape(1, 512, 3)
-    sh = abi.shade(xyz, rayo, normal, lvis, albedo, spec, rough_c, m.lxyz, m.lareas, lights, n=n, n_total=n)
-    rgb_pred = sh['rgb'].reshape(n, 3)
+    is_nerf = m.data_type == 'nerf'
+    # non-'nerf' data: rgb = clip((rgb * gamma_bias) ^ gamma_index) with TRAINABLE gamma (:715-718): the integral comes out
+    # raw and the tone scaling is its own pair of kernels reading the parameters from the flat device buffer
+    sh = abi.shade(xyz, rayo, normal, lvis, albedo, spec, rough_c, m.lxyz, m.lareas, lights, n=n, n_total=n,
+                   no_clip=not is_nerf)
+    rgb_lin = sh['rgb'].reshape(n, 3)
+    rgb_pred = rgb_lin if is_nerf else abi.gamma_forward(rgb_lin, st.gamma_par, B['rgb_g'])
     if prep and CONCURRENT_HEADS:
         va, vs, vr = outs['diff_vq'], outs['spec_vq'], outs['rough_vq']
     else:
@@ -418,22 +429,29 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
         va_c = _compact_col(va, nets['diff_vq'].ld[-1], 3, B['vq_albedo_c'])
         vs_c = _compact_col(vs, nets['spec_vq'].ld[-1], 3, B['vq_spec_c'])
         vr_c = _compact_col(vr, nets['rough_vq'].ld[-1], 1, B['vq_rough_c'])
-    sh_vq = abi.shade(xyz, rayo, normal, lvis, va_c, vs_c, vr_c, m.lxyz, m.lareas, lights, n=n, n_total=n)
-    vq_rgb = sh_vq['rgb'].reshape(n, 3)
+    sh_vq = abi.shade(xyz, rayo, normal, lvis, va_c, vs_c, vr_c, m.lxyz, m.lareas, lights, n=n, n_total=n,
+                      no_clip=not is_nerf)
+    vq_rgb_lin = sh_vq['rgb'].reshape(n, 3)
+    vq_rgb = vq_rgb_lin if is_nerf else abi.gamma_forward(vq_rgb_lin, st.gamma_par, B['vqrgb_g'])
 
     # ---- loss + backward ----------------------------------------------------------------------------------
-    abi.loss_train(rgb.contiguous(), rgb_pred, vq_rgb, z_vq, spec, rough_c, True, lw['combine_weight'],
+    abi.loss_train(rgb.contiguous(), rgb_pred, vq_rgb, z_vq, spec, rough_c, is_nerf, lw['combine_weight'],
                    lw['chromaticity_loss_weight'], lw['mat_sloss_weight'], lw['lambert_weight'], lw['chr_alpha'],
                    lw['chr_thres'], inv_gbs, B['loss_rows'], B['d_rgb'], B['d_vqrgb'], B['d_zvq'], B['d_spec_l'],
                    st.sums)
+    d_rgb, d_vqrgb = B['d_rgb'], B['d_vqrgb']
+    if not is_nerf:                      # back through the tone scaling: d rgb_lin, and the gradients of the two parameters
+        abi.gamma_backward(rgb_lin, st.gamma_par, B['d_rgb'], B['d_rgb_lin'], st.d_gamma)
+        abi.gamma_backward(vq_rgb_lin, st.gamma_par, B['d_vqrgb'], B['d_vqrgb_lin'], st.d_gamma)
+        d_rgb, d_vqrgb = B['d_rgb_lin'], B['d_vqrgb_lin']
     # main branch
-    abi.shade_backward(xyz, rayo, normal, lvis, albedo, spec, rough_c, m.lxyz, m.lareas, m._light, B['d_rgb'],
+    abi.shade_backward(xyz, rayo, normal, lvis, albedo, spec, rough_c, m.lxyz, m.lareas, m._light, d_rgb,
                        B['d_albedo'], B['d_spec'], B['d_rough'], st.d_light)
     abi.material_combine_backward(base_c, ks_c, B['d_albedo'], B['d_spec'], B['d_spec_l'], B['d_base'], B['d_ks'])
     d_zenc = B['d_zenc']
     d_zenc.zero_()
     # VQ branch (d_zvq already holds the pair-smoothness gradient)
-    abi.shade_backward(xyz, rayo, normal, lvis, va_c, vs_c, vr_c, m.lxyz, m.lareas, m._light, B['d_vqrgb'],
+    abi.shade_backward(xyz, rayo, normal, lvis, va_c, vs_c, vr_c, m.lxyz, m.lareas, m._light, d_vqrgb,
                        B['d_vq_albedo'], B['d_vq_spec'], B['d_vq_rough'], st.d_light)
     d_zvq = B['d_zvq']
     heads = [('diff_main', B['d_base'], 3, d_zenc), ('spec_main', B['d_ks'], 1, d_zenc),
@@ -450,9 +468,26 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
             for name, _, _, dzin in heads:
                 probs += nets[name].data_problems(level, dzin, z, atomic=True)
             abi.dense_backward_data_batched(probs, m.device)
+        head_w = []
         for name, _, _, _ in heads:
-            wlist += nets[name].weight_problems(st.dW[name], st.dB[name])
+            head_w += nets[name].weight_problems(st.dW[name], st.dB[name])
+        if CONCURRENT_HEADS and prep:
+            # the heads' 18 weight-gradient GEMMs (one full wave of CTAs) run on a side stream UNDER the encoder's backward
+            # chain, whose per-layer launches fill less than half of the SMs
+            cur = torch.cuda.current_stream(m.device)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            side = st.side_streams[0]
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                abi.dense_backward_weights_batched(head_w, m.device)
+                heads_w_done = torch.cuda.Event()
+                heads_w_done.record(side)
+        else:
+            wlist += head_w
+            heads_w_done = None
     else:
+        heads_w_done = None
         for name, dy, lddy, dzin in heads:
             nets[name].backward(dy, lddy, st.dW[name], st.dB[name], dzin, z)
     commit_coef = lw['vq_loss_weight'] * m.vq_layer.commitment_cost * 2.0 * inv_gbs / z
@@ -464,6 +499,8 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
     nets['fine_enc'].backward(d_h, d_h.shape[1], st.dW['fine_enc'], st.dB['fine_enc'], weight_list=wl)
     if wlist:
         abi.dense_backward_weights_batched(wlist, m.device)
+    if heads_w_done is not None:
+        torch.cuda.current_stream(m.device).wait_event(heads_w_done)
 
     # ---- the single collective: [gradients | VQ statistics | loss sums] --------------------------------------
     abi.cast_f64_f32(st.stats64, st.stats32)
