@@ -473,16 +473,19 @@ __device__ __forceinline__ void store_chunk32(uint32_t slot, int r, int j0, cons
     }
   } else {
     // plane H (tf32 hi) at slot, plane C at slot + 16 KB: [bf16(a_lo) x 32 | bf16(a_hi) x 32] per row.
+    // j0 is 0 or 16, so the eight 16-byte chunks of this thread are two swizzled bases XOR small constants
+    // ((c + k) ^ rx == (c ^ rx) ^ k for k below c's alignment): one LOP3 per store instead of xor + shift + add
     const uint32_t row = slot + (uint32_t)r * 128u;
     const uint32_t rx = (uint32_t)(r & 7);
+    const uint32_t th = row + ((((uint32_t)j0 >> 2) ^ rx) << 4);                    // tf32 chunk j0 / 4
+    const uint32_t tb = row + TC_M * 128 + ((((uint32_t)j0 >> 3) ^ rx) << 4);       // bf16 chunk j0 / 8 of the lo half
 #pragma unroll
     for (int qq = 0; qq < 2; ++qq) {            // 8 K values per step
       float h[8], l[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) { h[i] = tc::tf32_rna_fast(v[8 * qq + i]); l[i] = v[8 * qq + i] - h[i]; }
-      const uint32_t c0 = (uint32_t)(j0 / 4 + 2 * qq);
-      tc::sts128(row + (((c0) ^ rx) << 4), make_float4(h[0], h[1], h[2], h[3]));
-      tc::sts128(row + (((c0 + 1) ^ rx) << 4), make_float4(h[4], h[5], h[6], h[7]));
+      tc::sts128(th ^ (uint32_t)(32 * qq), make_float4(h[0], h[1], h[2], h[3]));
+      tc::sts128(th ^ (uint32_t)(32 * qq + 16), make_float4(h[4], h[5], h[6], h[7]));
       uint4 ul, uh;
       __nv_bfloat162 t0 = __floats2bfloat162_rn(l[0], l[1]), t1 = __floats2bfloat162_rn(l[2], l[3]);
       __nv_bfloat162 t2 = __floats2bfloat162_rn(l[4], l[5]), t3 = __floats2bfloat162_rn(l[6], l[7]);
@@ -492,9 +495,8 @@ __device__ __forceinline__ void store_chunk32(uint32_t slot, int r, int j0, cons
       t2 = __floats2bfloat162_rn(h[4], h[5]); t3 = __floats2bfloat162_rn(h[6], h[7]);
       uh.x = *reinterpret_cast<uint32_t*>(&t0); uh.y = *reinterpret_cast<uint32_t*>(&t1);
       uh.z = *reinterpret_cast<uint32_t*>(&t2); uh.w = *reinterpret_cast<uint32_t*>(&t3);
-      const uint32_t cc = (uint32_t)(j0 / 8 + qq);                 // bf16 16-byte chunk of the lo half
-      tc::sts128(row + TC_M * 128 + ((cc ^ rx) << 4), ul);
-      tc::sts128(row + TC_M * 128 + (((cc + 4) ^ rx) << 4), uh);
+      tc::sts128(tb ^ (uint32_t)(16 * qq), ul);                      // bf16 chunk j0 / 8 + qq of the lo half
+      tc::sts128(tb ^ (uint32_t)(16 * qq + 64), uh);                 // ... and of the hi half (chunk + 4)
     }
   }
 }
@@ -676,10 +678,12 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
 #else
           const bool ts = TS && pg.layers[l].seg_ts[sg];
 #endif
-          for (int c = 0; c < nch; ++c, ++ga) {
-            const uint32_t gsm = ts ? 0u : gs, gtm = gt;  // this chunk's position in its ring
-            if (ts) ++gt; else ++gs;
-            if ((int)(ga % C::G) != grp) continue;
+          // this group's chunks of the segment: c = first, first + G, ... (chunk ga0 + c belongs to group (ga0 + c) % G)
+          const uint32_t ga0 = ga, gs0 = gs, gt0 = gt;
+          ga += (uint32_t)nch;
+          if (ts) gt += (uint32_t)nch; else gs += (uint32_t)nch;
+          for (int c = (int)(((uint32_t)grp + C::G - ga0 % C::G) % C::G); c < nch; c += C::G) {
+            const uint32_t gsm = gs0 + (uint32_t)c, gtm = gt0 + (uint32_t)c;  // this chunk's position in its ring
             if ((st == SRC_DRAIN || st == SRC_GRAD) && !acc_ready) {
               tc::mbar_wait(&acc_full, (gl - 1) & 1);    // previous layer's accumulator is complete
               tc::fence_after_sync();
