@@ -242,11 +242,14 @@ __global__ void __launch_bounds__(SP_THREADS, 1) shade_pt_kernel(vqn_shade_args 
     __threadfence();
     if (lane == 0) part_cnt[rt] = 0;                                   // ready for the next launch
     const float* p0 = part_buf + (size_t)rt * 16 * (32 * 3 * SP_MAXP);
+    // q outer, k inner: the 3 NPC loads of a part are independent and in flight together (one L2 latency per part; with
+    // k outer the 16 x 27 loads ran back to back -- 50 us for the tail of ONE tile); the order of the sum over q is fixed
 #pragma unroll
-    for (int k = 0; k < 3 * NPC; ++k) {
-      float sum = 0.f;
-      for (int q = 0; q < S; ++q) sum += __ldcg(p0 + (size_t)q * (32 * 3 * SP_MAXP) + k * 32 + lane);
-      out[k] = sum;
+    for (int k = 0; k < 3 * NPC; ++k) out[k] = 0.f;
+    for (int q = 0; q < S; ++q) {
+      const float* pq = p0 + (size_t)q * (32 * 3 * SP_MAXP) + lane;
+#pragma unroll
+      for (int k = 0; k < 3 * NPC; ++k) out[k] += __ldcg(pq + k * 32);
     }
   }
 #pragma unroll
