@@ -270,6 +270,9 @@ int vqn_compact_mask(vqn_ctx* ctx, const float* alpha, int64_t n_total, int32_t*
 /* scatter_nd(ind, value, (n_total,c)) (vq_nfr.py:347-370): out must be pre-zeroed full length */
 int vqn_scatter_rows(vqn_ctx* ctx, const float* compact, const int32_t* row_idx, const int32_t* n_dev,
                      int64_t n_max, int c, float* out, vqn_stream stream);
+/* up to 4 scatters that share row_idx / n_dev in ONE launch: outs[q][row_idx[r], :widths[q]] = compact[q][r, :] (HOST arrays) */
+int vqn_scatter_rows_multi(vqn_ctx* ctx, const float* const* compact, const int32_t* widths, int count,
+                           const int32_t* row_idx, const int32_t* n_dev, int64_t n_max, float* const* outs, vqn_stream s);
 
 /* ---- training step (BASELINE config #4): Model.call(mode='train') + compute_loss under tf.GradientTape and
  * the Adam(amsgrad) update (models/vq_nfr.py:534-692, 876-986; train_nfr.py:121-139, 562-576) -------------- */

@@ -117,6 +117,7 @@ SIGNATURES = {
     'vqn_srgb2linear': (_I, [_P, _P, _L, _P, _P]),
     'vqn_compact_mask': (_I, [_P, _P, _L, _P, _P, _P, _P]),
     'vqn_scatter_rows': (_I, [_P, _P, _P, _P, _L, _I, _P, _P]),
+    'vqn_scatter_rows_multi': (_I, [_P, _P, _P, _I, _P, _P, _L, _P, _P]),
     'vqn_neus_up_sample': (_I, [_P, _P, _P, _P, _P, _L, _I, _F, _I, _F, _P, _P]),
     'vqn_neus_up_sample_pts': (_I, [_P, _P, _P, _P, _P, _L, _I, _F, _I, _F, _P, _P, _P]),
     'vqn_neus_scan_step': (_I, [_P, C.POINTER(NeusStepArgs), _P]),

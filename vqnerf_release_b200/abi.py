@@ -454,6 +454,27 @@ def scatter_rows(compact: torch.Tensor, row_idx: torch.Tensor, n_total: int, n_d
     return out
 
 
+def scatter_rows_multi(compacts, row_idx: torch.Tensor, n_total: int, n_dev=None, n: Optional[int] = None):
+    """scatter_rows for up to 4 compact [n, c_q] tensors that share the row list: ONE zero fill + ONE launch."""
+    compacts = [_f(c) for c in compacts]
+    widths = [int(np.prod(c.shape[1:])) if c.dim() > 1 else 1 for c in compacts]
+    n = compacts[0].shape[0] if n is None else n
+    dev = compacts[0].device
+    flat = torch.zeros((n_total * sum(widths),), dtype=F32, device=dev)
+    outs, off = [], 0
+    for c, w in zip(compacts, widths):
+        outs.append(flat[off:off + n_total * w].view((n_total,) + tuple(c.shape[1:])))
+        off += n_total * w
+    k = len(compacts)
+    src = (C.c_void_p * k)(*[c.data_ptr() for c in compacts])
+    dst = (C.c_void_p * k)(*[o.data_ptr() for o in outs])
+    wid = (C.c_int32 * k)(*widths)
+    ctx = _ctx(compacts[0])
+    L.check(ctx.lib.vqn_scatter_rows_multi(ctx.handle, src, wid, k, L.ptr(row_idx, torch.int32), L.ptr(n_dev, torch.int32),
+                                           n, dst, L.stream_ptr(dev)))
+    return outs
+
+
 # ---- NeuS -------------------------------------------------------------------------------------
 def neus_up_sample(rays_o, rays_d, z_vals, sdf, r_limit, n_importance, inv_s):
     rays_o, rays_d, z_vals, sdf = map(_f, (rays_o, rays_d, z_vals, sdf))

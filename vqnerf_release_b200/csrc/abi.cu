@@ -389,6 +389,42 @@ extern "C" int vqn_scatter_rows(vqn_ctx* ctx, const float* compact, const int32_
   return VQN_OK;
 }
 
+// up to 4 scatter_nd's that share the row list in ONE launch (fast_render scatters four material maps per view)
+struct ScatterMulti { const float* src[4]; float* out[4]; int c[4]; int count; };
+__global__ void scatter_rows_multi_kernel(ScatterMulti m, const int* __restrict__ row_idx, const int* __restrict__ n_dev,
+                                          long long n_max) {
+  long long n = n_dev ? (long long)*n_dev : n_max;
+  if (n > n_max) n = n_max;
+  int ctot = 0;
+  for (int q = 0; q < m.count; ++q) ctot += m.c[q];
+  const long long total = n * ctot;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / ctot;
+    int k = (int)(i - r * ctot), q = 0;
+    while (k >= m.c[q]) { k -= m.c[q]; ++q; }
+    m.out[q][(long long)row_idx[r] * m.c[q] + k] = m.src[q][r * m.c[q] + k];
+  }
+}
+extern "C" int vqn_scatter_rows_multi(vqn_ctx* ctx, const float* const* compact, const int32_t* widths, int count,
+                                      const int32_t* row_idx, const int32_t* n_dev, int64_t n_max, float* const* outs,
+                                      vqn_stream s) {
+  VQN_CHECK_ARG(ctx && compact && widths && outs && count >= 1 && count <= 4 && n_max >= 0, "scatter_rows_multi args");
+  if (n_max == 0) return VQN_OK;
+  VQN_CHECK_ARG(row_idx, "scatter_rows_multi: null row_idx");
+  ScatterMulti m = {};
+  m.count = count;
+  int ctot = 0;
+  for (int q = 0; q < count; ++q) {
+    VQN_CHECK_ARG(compact[q] && outs[q] && widths[q] > 0, "scatter_rows_multi: bad entry");
+    m.src[q] = compact[q]; m.out[q] = outs[q]; m.c[q] = widths[q]; ctot += widths[q];
+  }
+  long long want = (n_max * ctot + 255) / 256;
+  int blocks = (int)(want < (long long)ctx->sm_count * 16 ? want : (long long)ctx->sm_count * 16);
+  scatter_rows_multi_kernel<<<blocks, 256, 0, vqn_cs(s)>>>(m, row_idx, n_dev, n_max);
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // material combine: spec = ks * basecolor; albedo = (1 - ks) * basecolor (vq_nfr.py:330-331,590-591)
 // and the optional opt_scale of fast_render (:333-336); compact [n,*] in and out.

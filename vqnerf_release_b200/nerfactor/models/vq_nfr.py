@@ -364,8 +364,10 @@ class Model:
             spec_v = abi.linear2srgb(spec) * s
         else:
             basecolor_v, spec_v = basecolor, spec
-        pred = {'alpha': pred_alpha, 'basecolor': sc(basecolor_v), 'albedo': sc(albedo), 'spec': sc(spec_v),
-                'rough': sc(rough)}
+        # the four material maps share the row list: one zero fill + one scatter launch instead of four of each
+        m_base, m_alb, m_spec, m_rough = abi.scatter_rows_multi([basecolor_v, albedo, spec_v, rough], row_idx, n_total,
+                                                                n_dev=n_act, n=n_total)
+        pred = {'alpha': pred_alpha, 'basecolor': m_base, 'albedo': m_alb, 'spec': m_spec, 'rough': m_rough}
         if gen_embed:
             pred['embed'] = abi.scatter_rows(embed_ind[:, None], row_idx, n_total, n=embed_ind.shape[0])
         rgb_all = sh['rgb']                                       # [n_total, 1+P, 3]
