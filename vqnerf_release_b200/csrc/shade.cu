@@ -482,13 +482,15 @@ __global__ void peer_frame_sync_kernel(int* counter, const int* local_flags, Pee
     for (int r = 0; r < world; ++r) if (r != rank) st_release_sys(peers.p[r] + world, f - 1);
     for (int r = 0; r < world; ++r) {
       if (r == rank) continue;
-      for (unsigned spins = 0; ld_acquire_sys(local_flags + r) < f; ++spins)
-        if (spins > (1u << 28)) { asm volatile("trap;"); }          // a protocol bug traps instead of hanging the GPU
+      const long long t0 = clock64();
+      for (unsigned spins = 0; ld_acquire_sys(local_flags + r) < f; ++spins)   // a protocol bug traps (after ~60 s) instead of hanging
+        if ((spins & 4095u) == 4095u && clock64() - t0 > 120000000000LL) { asm volatile("trap;"); }
     }
   } else {
     st_release_sys(peers.p[dst] + rank, f);
+    const long long t0 = clock64();
     for (unsigned spins = 0; ld_acquire_sys(local_flags + world) < f - 1; ++spins)
-      if (spins > (1u << 28)) { asm volatile("trap;"); }
+      if ((spins & 4095u) == 4095u && clock64() - t0 > 120000000000LL) { asm volatile("trap;"); }
   }
   __threadfence_system();
 }

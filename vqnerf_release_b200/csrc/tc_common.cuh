@@ -197,7 +197,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 // The suspend-time hint lets the hardware park the warp until the phase completes (or the hint expires) instead of
 // returning at once: without it the waiting warps of mlp_tc_kernel spent 29 % of the kernel's issue slots on
 // try_wait / branch / counter instructions (ncu source page, profiles/r2c_*), slots the working warps were waiting for.
-#define TC_MBAR_SUSPEND_NS 0x989680
+// (20 us: with the spin bound of 2^24 below a barrier that never completes -- a protocol bug -- traps after at most ~5 min
+// instead of hanging the GPU for days; a clock-based bound in the wait loops cost mlp_tc 2 %)
+#define TC_MBAR_SUSPEND_NS 20000
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -208,7 +210,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded wait: a barrier that never completes (a protocol bug) traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
-    if (spins > (1u << 26)) { asm volatile("trap;"); }
+    if (spins > (1u << 24)) { asm volatile("trap;"); }
   }
 }
 
@@ -221,7 +223,7 @@ __device__ __forceinline__ void mbar_wait_u(uint32_t bar_smem_addr, uint32_t par
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(bar_smem_addr), "r"(parity), "r"(TC_MBAR_SUSPEND_NS) : "memory");
     if (__all_sync(0xffffffffu, ok != 0)) break;
-    if (spins > (1u << 26)) { asm volatile("trap;"); }
+    if (spins > (1u << 24)) { asm volatile("trap;"); }
   }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
