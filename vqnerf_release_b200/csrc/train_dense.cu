@@ -13,6 +13,8 @@
 //   forward   (mlp.py:44-46)   Y  = act(X . W + b)                 A = X,    B = W
 //   bwd data                   dX = (dZ . W^T) * act'(Y_prev)      A = dZ,   B = W^T (read in place)
 //   bwd weight                 dW += X^T . dZ  (split over rows, fp32 atomics),  db += colsum(dZ) (fused)
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -373,8 +375,24 @@ extern "C" int vqn_dense_backward_data_batched(vqn_ctx* ctx, const vqn_dense_pro
   return VQN_OK;
 }
 
+int vqn_dense_tc_wgrad_batched(vqn_ctx* ctx, const vqn_dense_problem* pr, int count, cudaStream_t s);   // train_tc.cu
+
 extern "C" int vqn_dense_backward_weights_batched(vqn_ctx* ctx, const vqn_dense_problem* pr, int count, vqn_stream stream) {
   VQN_CHECK_ARG(ctx && pr && count >= 1 && count <= GB_MAX, "dense_backward_weights_batched: 1 <= count <= 32");
+  {
+    // tcgen05 form (train_tc.cu) from 1024 rows upwards; VQN_WGRAD_TC=0 keeps the warp-level kernel
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("VQN_WGRAD_TC"); env = e ? atoi(e) : 1; }
+    long long rows_min = 1LL << 62;
+    for (int i = 0; i < count; ++i) {
+      const vqn_dense_problem& q = pr[i];
+      VQN_CHECK_ARG(q.a && q.w && q.out && q.m >= 0 && q.k > 0 && q.n > 0 && q.lda >= q.k && q.ldw >= q.n,
+                    "dense_backward_weights_batched: bad problem");
+      if (q.m > 0 && q.m < rows_min) rows_min = q.m;
+    }
+    if (env && (rows_min >= 1024 || env == 2) && rows_min < (1LL << 62))       // (2: any row count -- the parity tests)
+      return vqn_dense_tc_wgrad_batched(ctx, pr, count, vqn_cs(stream));
+  }
   GemmBatch b = {};
   // row splits: ~4 waves of CTAs over the whole batch, shared out in proportion to the tiles of each problem
   long long base_tiles = 0;

@@ -233,6 +233,178 @@ int dt_launch(vqn_ctx* ctx, const DtParams& p, cudaStream_t s) {
   return VQN_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Weight gradients on tcgen05, batched:  dW[k_in, n_out] += X[rows, k_in]^T . dZ[rows, n_out],  db[n_out] += colsum(dZ)
+// for up to WG_MAX layers in ONE launch.  The reduction runs over the ROWS, so both operands are read transposed: the
+// producer thread that owns operand row m (a column of X, resp. of dZ) loads X[k0 + j][m] for the 32 rows of the chunk --
+// for a fixed j the 32 threads of a warp read 128 contiguous bytes -- splits them and stores its row of the K-major slot,
+// exactly as dense_tc_kernel does.  A CTA owns (layer, 128 x 128 output tile, row range); its accumulator is added into
+// dW with fp32 atomics (as the warp-level kernel does); the B-role threads of the first row-tile also sum their column
+// of dZ (the bias gradient).
+// ---------------------------------------------------------------------------------------------
+#define WG_MAX 32
+struct WgProblem { const float* X; long long ldx; const float* dZ; long long lddz; float* dW; float* db; int M, N; long long rows; };
+struct WgBatch { int count; int cta_start[WG_MAX + 1]; int tiles_m[WG_MAX], tiles_n[WG_MAX], per[WG_MAX]; WgProblem p[WG_MAX]; };
+
+__global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_wgrad_kernel(const __grid_constant__ WgBatch b) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full[DT_STAGES], empty[DT_STAGES], acc_full;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int MMA_WARP = 16;
+  int pi = 0;
+  while (pi + 1 < b.count && (int)blockIdx.x >= b.cta_start[pi + 1]) ++pi;
+  const WgProblem& p = b.p[pi];
+  const int t = (int)blockIdx.x - b.cta_start[pi];
+  const int mt = t % b.tiles_m[pi], nt = (t / b.tiles_m[pi]) % b.tiles_n[pi], sp = t / (b.tiles_m[pi] * b.tiles_n[pi]);
+  const int m0 = mt * DT_M, n0 = nt * DT_N;
+  const int nvalid = min(DT_N, p.N - n0), npad = (nvalid + 15) / 16 * 16;
+  const long long k_begin = (long long)sp * b.per[pi];
+  const long long k_end = min(p.rows, k_begin + (long long)b.per[pi]);
+  const int nch = (int)((k_end - k_begin + 31) / 32);
+
+  if (warp == MMA_WARP) tc::tmem_alloc(&tmem_base_s, 128);
+  if (tid == 0) {
+    for (int i = 0; i < DT_STAGES; ++i) { tc::mbar_init(&full[i], 256); tc::mbar_init(&empty[i], 1); }
+    tc::mbar_init(&acc_full, 1);
+    tc::mbar_fence_init();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < 16) {
+    const int grp = warp >> 3, i = tid & 255;
+    const bool a_role = i < 128;
+    const int r = a_role ? i : i - 128;                       // operand row: column m0 + r of X / column n0 + r of dZ
+    const bool live = a_role ? (m0 + r < p.M) : (r < nvalid);
+    const float* src = a_role ? p.X + m0 + r : p.dZ + n0 + r;
+    const long long ld = a_role ? p.ldx : p.lddz;
+    float csum = 0.f;
+    for (int c = grp; c < nch; c += 2) {
+      const int slot = c & 1;
+      const long long k0 = k_begin + 32LL * c;
+      float v[32];
+      if (live) {
+        if (k0 + 32 <= k_end) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __ldg(src + (k0 + j) * ld);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = k0 + j < k_end ? __ldg(src + (k0 + j) * ld) : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      if (!a_role) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) csum += v[j];
+      }
+      tc::mbar_wait(&empty[slot], (((uint32_t)c / DT_STAGES) & 1u) ^ 1u);
+      const uint32_t op = tc::smem_u32(smem) + (uint32_t)slot * DT_SLOT + (a_role ? 0u : DT_OPERAND);
+      dt_store16(op, r, 0, v, !a_role);
+      dt_store16(op, r, 16, v + 16, !a_role);
+      tc::fence_proxy_async();
+      tc::mbar_arrive(&full[slot]);
+    }
+    if (!a_role && live && mt == 0 && p.db && csum != 0.f) atomicAdd(p.db + n0 + r, csum);
+    if (nch > 0) {
+      // ---- epilogue: the accumulator tile is ADDED into dW (other row ranges add theirs) ----
+      tc::mbar_wait(&acc_full, 0);
+      tc::fence_after_sync();
+      const int row = 32 * (warp & 3) + lane, m = m0 + row;
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+      const int piece0 = warp >> 2;                             // 0..3
+#pragma unroll 1
+      for (int tt = 0; tt < 2; ++tt) {
+        const int c16 = 16 * (piece0 + 4 * tt);
+        if (c16 >= npad) continue;                              // warp-uniform
+        float v[16];
+        tc::tmem_ld16(lane_addr + (uint32_t)c16, v);
+        if (m < p.M) {
+          float* dst = p.dW + (long long)m * p.N + n0 + c16;
+          const int cnt = min(16, nvalid - c16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (j < cnt) atomicAdd(dst + j, v[j]);
+        }
+        __syncwarp();
+      }
+      tc::fence_before_sync();
+    }
+  } else {
+    {   // whole warp walks the loop, one elected lane issues (uniform operands: see tc::mma_ss_e)
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t idesc = tc::make_idesc(tc::FMT_TF32, DT_M, npad);
+      const uint32_t idesc_c = tc::make_idesc(tc::FMT_BF16, DT_M, npad);
+      uint32_t acc = 0;
+      for (int c = 0; c < nch; ++c) {
+        const int slot = c & 1;
+        tc::mbar_wait_u(&full[slot], ((uint32_t)c / DT_STAGES) & 1u);
+        tc::fence_after_sync();
+        const uint32_t a_addr = tc::smem_u32(smem + (size_t)slot * DT_SLOT);
+        const uint32_t b_addr = a_addr + DT_OPERAND;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          tc::mma_ss_e<true>(tmem_u, tc::make_desc_sw128(a_addr + 32 * s), tc::make_desc_sw128(b_addr + 32 * s), idesc, acc);
+          acc = 1;
+          tc::mma_ss_e<false>(tmem_u, tc::make_desc_sw128(a_addr + DT_PLANE + 32 * s),
+                            tc::make_desc_sw128(b_addr + DT_PLANE + 32 * s), idesc_c, 1);
+        }
+        tc::mma_commit_e(&empty[slot]);
+      }
+      if (nch > 0) tc::mma_commit_e(&acc_full);
+    }
+    __syncwarp();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == MMA_WARP) tc::tmem_dealloc(tmem_base, 128);
+}
+
+}  // namespace
+
+// every weight-gradient GEMM of a training step on tcgen05 (called by vqn_dense_backward_weights_batched)
+int vqn_dense_tc_wgrad_batched(vqn_ctx* ctx, const vqn_dense_problem* pr, int count, cudaStream_t s) {
+  static bool attr_set[16] = {false};
+  const int dev = ctx->device & 15;
+  if (!attr_set[dev]) {
+    VQN_CUDA(cudaFuncSetAttribute(dense_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DT_SMEM));
+    attr_set[dev] = true;
+  }
+  WgBatch b = {};
+  long long base_tiles = 0;
+  for (int i = 0; i < count; ++i)
+    if (pr[i].m > 0) base_tiles += (long long)((pr[i].k + DT_M - 1) / DT_M) * ((pr[i].n + DT_N - 1) / DT_N);
+  if (base_tiles == 0) return VQN_OK;
+  // one CTA per SM (129 KB of shared memory): the row split fills whole waves of sm_count CTAs
+  int splits_target = (int)((long long)ctx->sm_count / base_tiles);
+  if (splits_target < 1) splits_target = 1;
+  int ctas = 0;
+  for (int i = 0; i < count; ++i) {
+    const vqn_dense_problem& q = pr[i];
+    if (q.m == 0) continue;
+    WgProblem& p = b.p[b.count];
+    p.X = q.a; p.ldx = q.lda; p.dZ = q.w; p.lddz = q.ldw; p.dW = q.out; p.db = q.colsum; p.M = q.k; p.N = q.n; p.rows = q.m;
+    long long per = (q.m + splits_target - 1) / splits_target;
+    per = (per + 31) / 32 * 32;
+    if (per < 128) per = 128;
+    const int splits = (int)((q.m + per - 1) / per);
+    b.per[b.count] = (int)per;
+    b.tiles_m[b.count] = (q.k + DT_M - 1) / DT_M; b.tiles_n[b.count] = (q.n + DT_N - 1) / DT_N;
+    b.cta_start[b.count] = ctas;
+    ctas += b.tiles_m[b.count] * b.tiles_n[b.count] * splits;
+    ++b.count;
+  }
+  b.cta_start[b.count] = ctas;
+  dense_tc_wgrad_kernel<<<ctas, DT_THREADS, DT_SMEM, s>>>(b);
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}
+
+namespace {
 }  // namespace
 
 // rows from which the tcgen05 forward is taken for the WIDE layers (k, n >= 192); VQN_DENSE_TC_MIN_M overrides: 1 = every
