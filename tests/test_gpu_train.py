@@ -80,7 +80,9 @@ def test_dense_tc_forced():
     import sys
     if os.environ.get('VQN_DENSE_TC_MIN_M') == '1':
         pytest.skip('already running with the tcgen05 kernels forced')
-    env = dict(os.environ, VQN_DENSE_TC_MIN_M='1')
+    # ... and the batched weight-gradient / backward-data GEMMs of train_iter on their tcgen05 forms at ANY row count
+    # (dense_tc_wgrad_kernel is the default from 1024 rows upwards, which the small test batches never reach)
+    env = dict(os.environ, VQN_DENSE_TC_MIN_M='1', VQN_WGRAD_TC='2', VQN_BWD_TC='2')
     r = subprocess.run([sys.executable, '-m', 'pytest', os.path.abspath(__file__), '-q', '-x', '-m', 'gpu', '-k',
                         'dense_kernels or gradients_match or graphed'], env=env, capture_output=True, text=True,
                        timeout=600)

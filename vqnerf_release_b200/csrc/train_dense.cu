@@ -350,8 +350,27 @@ extern "C" int vqn_act_backward(vqn_ctx* ctx, const float* dy, int64_t lddy, con
 
 /* Batched forms of vqn_dense_backward_data / vqn_dense_backward_weights: `count` <= 32 independent problems in ONE launch.
  * backward-data problems with accumulate == 2 ADD atomically (several problems may target the same dx). */
+int vqn_dense_tc_backward_data_batched(vqn_ctx* ctx, const vqn_dense_problem* pr, int count, cudaStream_t s);   // train_tc.cu
+
 extern "C" int vqn_dense_backward_data_batched(vqn_ctx* ctx, const vqn_dense_problem* pr, int count, vqn_stream stream) {
   VQN_CHECK_ARG(ctx && pr && count >= 1 && count <= GB_MAX, "dense_backward_data_batched: 1 <= count <= 32");
+  {
+    // tcgen05 form (train_tc.cu): opt-in (VQN_BWD_TC=1 from 1024 rows upwards, 2 always -- the parity tests).  Measured at
+    // 8192 rows: 1.315 ms per step against 1.272 ms with the warp-level kernel (one CTA per SM, ~8 waves of CTAs that each
+    // pay TMEM allocation + barrier set-up for 1 - 8 chunks of work; routing only the long reductions to it: 1.265 vs 1.269)
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("VQN_BWD_TC"); env = e ? atoi(e) : 0; }
+    long long rows_min = 1LL << 62;
+    for (int i = 0; i < count; ++i) {
+      const vqn_dense_problem& q = pr[i];
+      VQN_CHECK_ARG(q.a && q.w && q.out && q.m >= 0 && q.k > 0 && q.n > 0 && q.lda >= q.n && q.ldo >= q.k,
+                    "dense_backward_data_batched: bad problem");
+      VQN_CHECK_ARG(q.act_prev == VQN_ACT_NONE || q.yprev, "dense_backward_data_batched: act_prev needs yprev");
+      if (q.m > 0 && q.m < rows_min) rows_min = q.m;
+    }
+    if (env && (rows_min >= 1024 || env == 2) && rows_min < (1LL << 62))
+      return vqn_dense_tc_backward_data_batched(ctx, pr, count, vqn_cs(stream));
+  }
   GemmBatch b = {};
   int tiles = 0;
   for (int i = 0; i < count; ++i) {

@@ -86,14 +86,14 @@ __device__ __forceinline__ void dt_load_row32(const float* p, int n_valid, float
   }
 }
 
-__global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(const __grid_constant__ DtParams p) {
+__device__ __forceinline__ void dense_tc_body(const DtParams& p, const int bx, const int by) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full[DT_STAGES], empty[DT_STAGES], acc_full;
   __shared__ uint32_t tmem_base_s;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int MMA_WARP = 16;
-  const int m0 = blockIdx.x * DT_M, n0 = blockIdx.y * DT_N;
+  const int m0 = bx * DT_M, n0 = by * DT_N;
   const int nvalid = min(DT_N, p.N - n0), npad = (nvalid + 15) / 16 * 16;
   const int nch = (p.K + 31) / 32;
 
@@ -173,12 +173,15 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(const __grid_co
               }
             }
           }
-          if (p.accumulate) {
+          if (p.accumulate == 1) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) if (j < cnt) v[j] += dst[j];
           }
         }
-        if (cnt == 16 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        if (p.bwd && p.accumulate == 2) {                       // several problems of a batch add into the same buffer
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (j < cnt) atomicAdd(dst + j, v[j]);
+        } else if (cnt == 16 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
           for (int q = 0; q < 4; ++q)
             reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -218,6 +221,20 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(const __grid_co
   tc::fence_before_sync();
   __syncthreads();
   if (warp == MMA_WARP) tc::tmem_dealloc(tmem_base, 128);
+}
+
+__global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(const __grid_constant__ DtParams p) {
+  dense_tc_body(p, (int)blockIdx.x, (int)blockIdx.y);
+}
+
+// up to DTB_MAX independent problems (the same-level backward-data GEMMs of the six head networks) in ONE launch
+#define DTB_MAX 24
+struct DtBatch { int count; int cta_start[DTB_MAX + 1]; int tiles_x[DTB_MAX]; DtParams p[DTB_MAX]; };
+__global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_batched_kernel(const __grid_constant__ DtBatch b) {
+  int i = 0;
+  while (i + 1 < b.count && (int)blockIdx.x >= b.cta_start[i + 1]) ++i;
+  const int t = (int)blockIdx.x - b.cta_start[i];
+  dense_tc_body(b.p[i], t % b.tiles_x[i], t / b.tiles_x[i]);
 }
 
 int dt_launch(vqn_ctx* ctx, const DtParams& p, cudaStream_t s) {
@@ -365,6 +382,36 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_wgrad_kernel(const __g
 }
 
 }  // namespace
+
+// the backward-data GEMMs of one level of the head networks on tcgen05, one launch
+int vqn_dense_tc_backward_data_batched(vqn_ctx* ctx, const vqn_dense_problem* pr, int count, cudaStream_t s) {
+  static bool attr_set[16] = {false};
+  const int dev = ctx->device & 15;
+  if (!attr_set[dev]) {
+    VQN_CUDA(cudaFuncSetAttribute(dense_tc_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DT_SMEM));
+    attr_set[dev] = true;
+  }
+  for (int i0 = 0; i0 < count; i0 += DTB_MAX) {
+    DtBatch b = {};
+    int ctas = 0;
+    for (int i = i0; i < count && i < i0 + DTB_MAX; ++i) {
+      const vqn_dense_problem& q = pr[i];
+      if (q.m == 0) continue;
+      DtParams& p = b.p[b.count];
+      p.A = q.a; p.lda = q.lda; p.W = q.w; p.ldw = q.n; p.C = q.out; p.ldc = q.ldo; p.M = (int)q.m; p.N = q.k; p.K = q.n; p.bwd = 1;
+      p.yprev = q.yprev; p.ldy = q.ldy; p.act_prev = q.act_prev; p.accumulate = q.accumulate;
+      b.tiles_x[b.count] = (int)((q.m + DT_M - 1) / DT_M);
+      b.cta_start[b.count] = ctas;
+      ctas += b.tiles_x[b.count] * ((q.k + DT_N - 1) / DT_N);
+      ++b.count;
+    }
+    if (b.count == 0) continue;
+    b.cta_start[b.count] = ctas;
+    dense_tc_batched_kernel<<<ctas, DT_THREADS, DT_SMEM, s>>>(b);
+    VQN_LAUNCHED(ctx);
+  }
+  return VQN_OK;
+}
 
 // every weight-gradient GEMM of a training step on tcgen05 (called by vqn_dense_backward_weights_batched)
 int vqn_dense_tc_wgrad_batched(vqn_ctx* ctx, const vqn_dense_problem* pr, int count, cudaStream_t s) {
