@@ -289,6 +289,15 @@ int vqn_dense_forward(vqn_ctx* ctx, const float* x, int64_t ldx, const float* w,
 int vqn_net_forward_train(vqn_ctx* ctx, vqn_net* net, const float* x, int64_t ldx, int64_t n, float* const* y,
                           const int64_t* ldy, float out_scale, float out_bias, int precision, vqn_stream stream);
 int vqn_net_repack_tc(vqn_net* net, int precision, vqn_stream stream);
+/* Backward-data of ONE network as a single launch of the fused tensor-core kernel (tf32x3): dz_last = d loss / d
+ * (pre-activation of the last layer) [n, lddz_last]; y[i] / ldy[i] = the outputs saved by vqn_net_forward_train; every
+ * dz_i = (dz_{i+1} . W_{i+1}^T) * act'(y_i) is stored to dz[i] (ld lddz[i]) for the weight gradients; the gradient w.r.t. the
+ * network input goes to d_input (ld ld_din; din_mode 0 store / 1 add / 2 atomic add) or, with d_input == NULL, the chain
+ * ends in dz[0].  Shapes: plain chains; a skip concat whose x half needs no gradient; the head shape [w0, w1, out <= 3] with
+ * skip_at == 1 (d_input required).  Weight images are refreshed by vqn_net_repack_tc / vqn_nets_repack_tc. */
+int vqn_net_backward_train(vqn_ctx* ctx, vqn_net* net, const float* dz_last, int64_t lddz_last, int64_t n,
+                           const float* const* y, const int64_t* ldy, float* const* dz, const int64_t* lddz,
+                           float* d_input, int64_t ld_din, int din_mode, vqn_stream stream);
 /* the same for `count` networks in ONE launch (the training step refreshes all of its networks after the optimizer step) */
 int vqn_nets_repack_tc(vqn_net* const* nets, int count, int precision, vqn_stream stream);
 /* dX[m,k] (+)= (dZ[m,n] . W[k,n]^T) * act_prev'(Yprev[m,k]); act_prev' is taken from the stored activation

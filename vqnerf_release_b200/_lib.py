@@ -131,6 +131,8 @@ SIGNATURES = {
     'vqn_dense_forward': (_I, [_P, _P, _L, _P, _P, _P, _L, _L, _I, _I, _I, _F, _F, _P]),
     'vqn_net_forward_train': (_I, [_P, _P, _P, _L, _L, C.POINTER(_P), C.POINTER(_L), _F, _F, _I, _P]),
     'vqn_net_repack_tc': (_I, [_P, _I, _P]),
+    'vqn_net_backward_train': (_I, [_P, _P, _P, _L, _L, C.POINTER(_P), C.POINTER(_L), C.POINTER(_P), C.POINTER(_L), _P, _L,
+                                    _I, _P]),
     'vqn_nets_repack_tc': (_I, [C.POINTER(_P), _I, _I, _P]),
     'vqn_copy_cols_batched': (_I, [_P, C.POINTER(CopyJob), _I, _P]),
     'vqn_dense_backward_data': (_I, [_P, _P, _L, _P, _P, _L, _P, _L, _I, _I, _L, _I, _I, _P]),

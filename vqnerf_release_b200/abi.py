@@ -82,6 +82,19 @@ class PackedNet:
         L.check(self.ctx.lib.vqn_net_repack_tc(self.handle, L.precision_code(precision),
                                                L.stream_ptr(self.weights[0].device)))
 
+    def backward_train(self, dz_last: torch.Tensor, lddz_last: int, n: int, ys: Sequence[torch.Tensor],
+                       ldys: Sequence[int], dzs: Sequence[torch.Tensor], lddzs: Sequence[int],
+                       d_input: Optional[torch.Tensor] = None, ld_din: int = 0, din_mode: int = 0) -> None:
+        """vqn_net_backward_train: the backward-data chain of the whole network in one launch (tf32x3)."""
+        nl = len(self.weights)
+        yp = (C.c_void_p * nl)(*[y.data_ptr() for y in ys])
+        lp = (C.c_int64 * nl)(*[int(v) for v in ldys])
+        zp = (C.c_void_p * nl)(*[z.data_ptr() for z in dzs])
+        zl = (C.c_int64 * nl)(*[int(v) for v in lddzs])
+        L.check(self.ctx.lib.vqn_net_backward_train(self.ctx.handle, self.handle, dz_last.data_ptr(), int(lddz_last), int(n),
+                                                    yp, lp, zp, zl, None if d_input is None else d_input.data_ptr(),
+                                                    int(ld_din), int(din_mode), L.stream_ptr(dz_last.device)))
+
     def forward_train(self, x: torch.Tensor, ldx: int, n: int, ys: Sequence[torch.Tensor], lds: Sequence[int],
                       out_scale: float = 1.0, out_bias: float = 0.0, precision='tf32x3') -> None:
         """vqn_net_forward_train: the whole network in one launch, every layer's output stored into ys[i] (ld lds[i])."""

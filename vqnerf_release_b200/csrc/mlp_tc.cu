@@ -42,7 +42,9 @@
 
 enum { SRC_DRAIN = 0, SRC_EMBED = 1, SRC_GLOBAL = 2,
        SRC_GRADINIT = 3,      // reverse mode: A = w_tail (x) act'(stash)            (d out / d pre of the last hidden layer)
-       SRC_GRAD = 4 };        // reverse mode: A = drain(previous accumulator) * act'(stash)
+       SRC_GRAD = 4,          // reverse mode: A = drain(previous accumulator) * act'(stash)
+       SRC_BWD = 5,           // training backward (MODE 4): A = dz = drain(previous accumulator) * act'(saved forward output), dz also stored
+       SRC_TAILGRAD = 6 };    // training backward: A = dz of the layer below a NARROW last layer, formed on the CUDA cores
 
 struct TcLayer {
   const uint8_t* w;       // packed chunk images, chunk c at w + c * chunk_bytes
@@ -78,6 +80,16 @@ struct TcLayer {
   // values into save[row * save_ld + col] -- the layer outputs the backward pass needs (mlp.py under GradientTape)
   float* save;
   int save_ld;
+  // Training backward (MODE 4, vqn_net_backward_train): this layer is the GEMM  d_in = dz_i . W_i^T  of forward layer i, its A
+  // chunks are dz_i:  SRC_BWD: drain(previous accumulator) * act'(bw_y) (bw_y = the forward layer's saved output, bw_act its
+  // activation); SRC_TAILGRAD: (sum_o tg_dz[row][o] W_last[c][o]) * act'(bw_y) -- the narrow last forward layer evaluated
+  // backwards on the CUDA cores (tg_w = its Keras kernel [rows, tg_n], tg_n <= 3).  Either way dz_i is also STORED to bw_dz
+  // (the weight gradients read it).  Final drain of the chain (out_slot >= 0): fin_mode 0 store / 1 add / 2 atomic add;
+  // fin_y: multiply by act'(fin_y) first (the chain ends in a dz, not in an input gradient); fin_skip_n > 0: add the x half of
+  // the folded skip concat, sum_o tg_dz[row][o] W_last[K_y + c][o].
+  const float* bw_y; float* bw_dz; const float* tg_dz; const float* tg_w; const float* fin_y;
+  int bw_y_ld, bw_act, bw_dz_ld, bw_n, tg_dz_ld, tg_n, tg_woff, tg_rows, fin_mode, fin_y_ld, fin_act, fin_skip_n, fin_skip_woff,
+      fin_skip_row0;
 };
 
 struct TcProgram {
@@ -108,6 +120,7 @@ struct TcProgram {
   int reverse;
   float* stash;            // sm_count x TC_STASH_FLOATS
   int train;               // MODE 3
+  int train_bwd;           // MODE 4
   int* nonfinite;
   long long* trace;        // diagnostic (vqn_debug_tc_trace): clock64 stamps of CTA 0's MMA thread, 4 per layer
   TcLayer layers[TC_MAX_LAYERS];
@@ -209,7 +222,7 @@ static int tc_pack_fill(vqn_net* net, int p, cudaStream_t s) {
                                                    seg1_rows, c1, tp->w[i], tp->bias[i], 0);
     net->ctx->launches.fetch_add(1);
     VQN_CUDA(cudaGetLastError());
-    if (tp->has_T) {
+    if (tp->has_T && tp->wT[i]) {
       const int in_rows = seg0_rows + seg1_rows;             // Keras kernel rows (y rows, then the x rows after a skip)
       const int kc = vqn_round_up(d.widths[i], E) / E;
       if (bf16) tc_pack_kernel<true><<<128, 256, 0, s>>>(d.w[i], nullptr, in_rows, tp->NpadT[i], d.widths[i], kc, 0, 0,
@@ -235,7 +248,11 @@ static int tc_packT_ensure(vqn_net* net, int precision, cudaStream_t s) {
     const int in_rows = ((i == 0) ? d.in_dim : d.widths[i - 1]) + (after_skip ? d.in_dim : 0);
     tp->NpadT[i] = vqn_round_up(in_rows, i > 0 ? E : 16);   // layer 0's input gradient is only contracted, not chained
     tp->n_chunksT[i] = vqn_round_up(d.widths[i], E) / E;
-    if (tp->NpadT[i] > TC_NPAD_MAX) { vqn_set_error("reverse-mode gradient: layer %d has more than 256 inputs", i); return VQN_ERR_UNSUPPORTED; }
+    if (tp->NpadT[i] > TC_NPAD_MAX) {                       // no transposed image: such a layer cannot be an MMA layer of a
+      tp->NpadT[i] = 0; tp->n_chunksT[i] = 0;               // backward chain (vqn_sdf_forward / vqn_net_backward_train check)
+      tp->wT[i] = nullptr; tp->biasT[i] = nullptr;
+      continue;
+    }
     const size_t chunk_bytes = (size_t)tp->NpadT[i] * 128 * (p == 1 ? 1 : 2);
     VQN_CUDA(cudaMalloc(&tp->wT[i], chunk_bytes * tp->n_chunksT[i]));
     VQN_CUDA(cudaMalloc(&tp->biasT[i], sizeof(float) * tp->NpadT[i]));
@@ -602,6 +619,12 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
         const int k = i >> 2, o = i & 3;
         bias_s[pg.layers[l].skip_woff + i] = o < pg.layers[l].skip_n ? pg.layers[l].skip_w[k * pg.layers[l].skip_n + o] : 0.f;
       }
+    if (pg.layers[l].tg_w)            // training backward: rows of the narrow last layer as float4 {w[c][0..2]} (y part, x part)
+      for (int i = tid; i < (pg.layers[l].tg_rows + pg.layers[l].fin_skip_n) * 4; i += C::THREADS) {
+        const int k = i >> 2, o = i & 3;
+        const int row = k < pg.layers[l].tg_rows ? k : pg.layers[l].fin_skip_row0 + (k - pg.layers[l].tg_rows);
+        bias_s[pg.layers[l].tg_woff + i] = o < pg.layers[l].tg_n ? pg.layers[l].tg_w[row * pg.layers[l].tg_n + o] : 0.f;
+      }
     if (pg.layers[l].tail_w)          // tail kernel rows as float4 {w[k][0..3]} (zero padded)
       for (int i = tid; i < pg.layers[l].N * 4; i += C::THREADS) {
         const int k = i >> 2, o = i & 3;
@@ -618,6 +641,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
   constexpr bool jet = MODE == 1;                        // compile-time: the decomposition-stage kernels carry no jet code
   constexpr bool rev = MODE == 2;
   constexpr bool trn = MODE == 3;
+  constexpr bool bwd = MODE == 4;
   constexpr int tile_pts = jet ? TC_M / 4 : TC_M;        // points per tile
   const long long n_tiles = (n + tile_pts - 1) / tile_pts;
   const int L = pg.n_layers;
@@ -684,7 +708,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
           if (ts) gt += (uint32_t)nch; else gs += (uint32_t)nch;
           for (int c = (int)(((uint32_t)grp + C::G - ga0 % C::G) % C::G); c < nch; c += C::G) {
             const uint32_t gsm = gs0 + (uint32_t)c, gtm = gt0 + (uint32_t)c;  // this chunk's position in its ring
-            if ((st == SRC_DRAIN || st == SRC_GRAD) && !acc_ready) {
+            if ((st == SRC_DRAIN || st == SRC_GRAD || st == SRC_BWD) && !acc_ready) {
               tc::mbar_wait(&acc_full, (gl - 1) & 1);    // previous layer's accumulator is complete
               tc::fence_after_sync();
               acc_ready = true;
@@ -774,6 +798,52 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
 #pragma unroll
                       for (int j = 0; j < 16; ++j) if (col0 + j < pl.N) sv[j] = v[j];
                     }
+                  }
+                } else if (bwd && (st == SRC_BWD || st == SRC_TAILGRAD)) {
+                  // dz of forward layer i = (gradient w.r.t. its output) * act'(its saved output); stored for the weight gradients
+                  const TcLayer& ly = pg.layers[l];
+                  if (st == SRC_BWD) tc::tmem_ld16(pacc + (uint32_t)col0, v);
+                  else {
+                    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+                    if (valid) {
+                      const float* dzr = ly.tg_dz + (size_t)pi * ly.tg_dz_ld;
+                      d0 = dzr[0]; d1 = ly.tg_n > 1 ? dzr[1] : 0.f; d2 = ly.tg_n > 2 ? dzr[2] : 0.f;
+                    }
+                    const float4* tw = reinterpret_cast<const float4*>(bias_s + ly.tg_woff) + col0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { const float4 w4 = tw[j]; v[j] = fmaf(d0, w4.x, fmaf(d1, w4.y, d2 * w4.z)); }
+                  }
+                  if (valid && col0 < ly.bw_n) {
+                    float y[16];
+                    const float* yr = ly.bw_y + (size_t)pi * ly.bw_y_ld + col0;
+                    float* dr = ly.bw_dz + (size_t)pi * ly.bw_dz_ld + col0;
+                    if (col0 + 16 <= ly.bw_n) {
+#pragma unroll
+                      for (int q = 0; q < 4; ++q) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(yr) + q);
+                        y[4 * q] = t.x; y[4 * q + 1] = t.y; y[4 * q + 2] = t.z; y[4 * q + 3] = t.w;
+                      }
+                    } else {
+#pragma unroll
+                      for (int j = 0; j < 16; ++j) y[j] = col0 + j < ly.bw_n ? __ldg(yr + j) : 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                      const float dact = ly.bw_act == VQN_ACT_RELU ? (y[j] > 0.f ? 1.f : 0.f)
+                                       : ly.bw_act == VQN_ACT_SIGMOID ? y[j] * (1.f - y[j]) : 1.f;
+                      v[j] = col0 + j < ly.bw_n ? v[j] * dact : 0.f;
+                    }
+                    if (col0 + 16 <= ly.bw_n) {
+#pragma unroll
+                      for (int q = 0; q < 4; ++q)
+                        reinterpret_cast<float4*>(dr)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    } else {
+#pragma unroll
+                      for (int j = 0; j < 16; ++j) if (col0 + j < ly.bw_n) dr[j] = v[j];
+                    }
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = 0.f;
                   }
                 } else if (rev && (st == SRC_GRAD || st == SRC_GRADINIT)) {
                   float dv[16];
@@ -964,6 +1034,58 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
           tc::fence_before_sync();
           asm volatile("bar.sync 3, %0;" ::"r"(256 * C::G) : "memory");   // scratch is free again
         }
+        if (bwd && pg.layers[l].out_slot >= 0) {
+          // end of a backward chain: the accumulator is the gradient w.r.t. the chain's input (or, with fin_y, a last dz)
+          const TcLayer& ly = pg.layers[l];
+          tc::mbar_wait(&acc_full, (gl - 1) & 1);
+          tc::fence_after_sync();
+          float* go = pg.outs[ly.out_slot];
+          const int gs = pg.out_stride[ly.out_slot];
+          float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+          if (ly.fin_skip_n > 0 && valid) {
+            const float* dzr = ly.tg_dz + (size_t)pi * ly.tg_dz_ld;
+            d0 = dzr[0]; d1 = ly.tg_n > 1 ? dzr[1] : 0.f; d2 = ly.tg_n > 2 ? dzr[2] : 0.f;
+          }
+          for (int cb = grp; cb * 32 < ly.N; cb += C::G) {
+            const int c16 = cb * 32 + 16 * half;
+            if (c16 < ly.N) {                                   // warp-uniform
+              float v[16];
+              tc::tmem_ld16(lane_addr + (uint32_t)(ly.tmem_col + c16), v);
+              if (valid) {
+                if (ly.fin_skip_n > 0) {
+                  const float4* sw = reinterpret_cast<const float4*>(bias_s + ly.tg_woff) + ly.tg_rows + c16;
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    if (c16 + j < ly.fin_skip_n) { const float4 w4 = sw[j]; v[j] += fmaf(d0, w4.x, fmaf(d1, w4.y, d2 * w4.z)); }
+                }
+                if (ly.fin_y) {
+                  const float* yr = ly.fin_y + (size_t)pi * ly.fin_y_ld + c16;
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    if (c16 + j < ly.N) {
+                      const float y = __ldg(yr + j);
+                      v[j] *= ly.fin_act == VQN_ACT_RELU ? (y > 0.f ? 1.f : 0.f) : ly.fin_act == VQN_ACT_SIGMOID ? y * (1.f - y) : 1.f;
+                    }
+                  }
+                }
+                float* dst = go + (size_t)pi * gs + c16;
+                bool bad = false;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  if (c16 + j < ly.N) {
+                    bad |= !isfinite(v[j]);
+                    if (ly.fin_mode == 2) atomicAdd(dst + j, v[j]);
+                    else if (ly.fin_mode == 1) dst[j] += v[j];
+                    else dst[j] = v[j];
+                  }
+                }
+                if (bad) atomicOr(pg.nonfinite, 1);
+              }
+            }
+          }
+          tc::fence_before_sync();
+          tc::mbar_arrive(&drain_done);     // the MMA thread may now reuse this TMEM region
+        } else
         if (pg.layers[l].out_slot >= 0) {
           // final layer of a network: drain its accumulator to global memory (column blocks split over groups)
           const TcLayer& ly = pg.layers[l];
@@ -1340,6 +1462,7 @@ static int tc_launch(vqn_ctx* ctx, TcProgram& pg, int precision, cudaStream_t s)
   for (int l = 0; l < pg.n_layers; ++l) {
     if (pg.layers[l].tail_w) { pg.layers[l].tail_woff = boff; boff += 4 * pg.layers[l].N; }
     if (pg.layers[l].skip_w) { pg.layers[l].skip_woff = boff; boff += 4 * pg.g_dim; }
+    if (pg.layers[l].tg_w) { pg.layers[l].tg_woff = boff; boff += 4 * (pg.layers[l].tg_rows + pg.layers[l].fin_skip_n); }
   }
   if (boff > TC_BIAS_FLOATS) { vqn_set_error("tensor-core MLP: bias table exceeds %d floats", TC_BIAS_FLOATS); return VQN_ERR_UNSUPPORTED; }
   if (pg.reverse) {
@@ -1366,16 +1489,18 @@ static int tc_launch(vqn_ctx* ctx, TcProgram& pg, int precision, cudaStream_t s)
     VQN_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<BF, JT, TSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     mlp_tc_kernel<BF, JT, TSV><<<blocks, TcCfg<BF>::THREADS, smem, s>>>(pg);                                           \
   } while (0)
-  const int mode = pg.jet ? 1 : (pg.reverse ? 2 : (pg.train ? 3 : 0));
+  const int mode = pg.jet ? 1 : (pg.reverse ? 2 : (pg.train ? 3 : (pg.train_bwd ? 4 : 0)));
   if (mode == 0 && precision != VQN_PREC_BF16 && tc_plan_ts(pg)) {
     TC_LAUNCH(false, 0, true);
     VQN_LAUNCHED(ctx);
     return VQN_OK;
   }
+  if (precision == VQN_PREC_BF16 && mode == 4) { vqn_set_error("training backward chain: tf32x3 only"); return VQN_ERR_UNSUPPORTED; }
   if (precision == VQN_PREC_BF16) {
     if (mode == 1) TC_LAUNCH(true, 1, false); else if (mode == 2) TC_LAUNCH(true, 2, false); else if (mode == 3) TC_LAUNCH(true, 3, false); else TC_LAUNCH(true, 0, false);
   } else {
-    if (mode == 1) TC_LAUNCH(false, 1, false); else if (mode == 2) TC_LAUNCH(false, 2, false); else if (mode == 3) TC_LAUNCH(false, 3, false); else TC_LAUNCH(false, 0, false);
+    if (mode == 1) TC_LAUNCH(false, 1, false); else if (mode == 2) TC_LAUNCH(false, 2, false); else if (mode == 3) TC_LAUNCH(false, 3, false);
+    else if (mode == 4) TC_LAUNCH(false, 4, false); else TC_LAUNCH(false, 0, false);
   }
 #undef TC_LAUNCH
   VQN_LAUNCHED(ctx);
@@ -1530,6 +1655,7 @@ extern "C" int vqn_sdf_forward(vqn_ctx* ctx, vqn_net* trunk, const float* w_sdf,
     if (nt > TC_STASH_SLOTS || B.pg.n_layers + nt > TC_MAX_LAYERS) TC_UNSUPPORTED("sdf_forward: too many layers for the reverse-mode gradient");
     rc = tc_packT_ensure(trunk, precision, s);
     if (rc != VQN_OK) return rc;
+    for (int i = 0; i < nt; ++i) if (!t0->wT[i]) TC_UNSUPPORTED("sdf_forward: reverse-mode gradient needs layers with at most 256 inputs");
     float* stash = static_cast<float*>(
         vqn_stream_scratch(ctx, VQN_SCRATCH_STASH, s, sizeof(float) * (size_t)ctx->sm_count * TC_STASH_FLOATS));
     if (!stash) return VQN_ERR_CUDA;
@@ -1617,7 +1743,7 @@ extern "C" int vqn_nets_repack_tc(vqn_net* const* nets, int count, int precision
       const bool after_skip = (d.skip_at >= 0 && i == d.skip_at + 1);
       const int seg0_rows = (i == 0) ? d.in_dim : d.widths[i - 1];
       const int seg1_rows = after_skip ? d.in_dim : 0;
-      for (int t = 0; t < (tp->has_T ? 2 : 1); ++t) {
+      for (int t = 0; t < ((tp->has_T && tp->wT[i]) ? 2 : 1); ++t) {
         if (batch.count == TC_PACK_JOBS) { int rc = flush(); if (rc != VQN_OK) return rc; }
         TcPackJob& j = batch.j[batch.count++];
         if (t == 0) {
@@ -1639,4 +1765,79 @@ extern "C" int vqn_net_repack_tc(vqn_net* net, int precision, vqn_stream stream)
   const int p = precision == VQN_PREC_BF16 ? 1 : 0;
   if (!net->tc_pack[p]) { TcPack* tp; return tc_pack_get(net, precision, vqn_cs(stream), &tp); }   // builds and fills
   return tc_pack_fill(net, p, vqn_cs(stream));
+}
+
+// Training backward of ONE mlp.Network as a single launch (the backward-data half of tf.GradientTape over networks/mlp.py:39-50):
+// given dz_last = d loss / d (pre-activation of the last layer) [n, lddz_last] (vqn_act_backward) and the outputs y[i] saved by
+// vqn_net_forward_train, the chain  dz_{i-1} = (dz_i . W_i^T) * act'(y_{i-1})  runs through the transposed weight images of the
+// fused kernel; every dz_i is stored to dz[i] (ld lddz[i]; the weight gradients read them) and the gradient w.r.t. the network
+// input is written to d_input (ld ld_din; din_mode 0 store, 1 add, 2 atomic add; NULL: not needed -- then the chain stops at
+// dz[0]).  Supported shapes: plain chains, a skip concat whose x half needs no gradient (d_input == NULL), and the head shape
+// [w0, w1, out <= 3] with skip_at == 1, whose narrow last layer is evaluated backwards on the CUDA cores (its y half feeds dz[1],
+// its x half is added to d_input in the final drain).
+extern "C" int vqn_net_backward_train(vqn_ctx* ctx, vqn_net* net, const float* dz_last, int64_t lddz_last, int64_t n,
+                                      const float* const* y, const int64_t* ldy, float* const* dz, const int64_t* lddz,
+                                      float* d_input, int64_t ld_din, int din_mode, vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && net && dz_last && y && ldy && dz && lddz && n >= 0, "net_backward_train: null argument");
+  VQN_CHECK_ARG(lddz_last % 4 == 0 && lddz_last < (1 << 20), "net_backward_train: lddz_last must be a multiple of 4");
+  VQN_CHECK_ARG(din_mode >= 0 && din_mode <= 2, "net_backward_train: din_mode");
+  if (n == 0) return VQN_OK;
+  cudaStream_t s = vqn_cs(stream);
+  const vqn_net_desc& d = net->desc;
+  const int L = d.n_layers;
+  TcPack* tp;
+  int rc = tc_pack_get(net, VQN_PREC_TF32X3, s, &tp);
+  if (rc != VQN_OK) return rc;
+  rc = tc_packT_ensure(net, VQN_PREC_TF32X3, s);
+  if (rc != VQN_OK) return rc;
+  const bool head = L == 3 && d.skip_at == 1 && d.widths[2] <= 3;
+  if (d.skip_at >= 0 && !head && d_input) TC_UNSUPPORTED("net_backward_train: input gradient through a skip concat (general shape)");
+  if (head && !d_input) TC_UNSUPPORTED("net_backward_train: the head shape needs d_input");
+  TcBuilder B(VQN_PREC_TF32X3);
+  B.pg.n = n; B.pg.train_bwd = 1;
+  // MMA layers: forward layer i backwards, i = top .. bottom, where bottom = 1 when no input gradient is needed
+  const int top = head ? 1 : L - 1, bottom = d_input ? 0 : 1;
+  if (top < bottom) TC_UNSUPPORTED("net_backward_train: nothing to do on the tensor cores for this shape");
+  if (!head) { B.pg.gsrc = dz_last; B.pg.g_dim = (int)lddz_last; }
+  for (int i = top; i >= bottom; --i) {
+    if (B.pg.n_layers >= TC_MAX_LAYERS || !tp->wT[i]) TC_UNSUPPORTED("net_backward_train: layer does not fit the tensor-core kernel");
+    TcLayer& ly = B.pg.layers[B.pg.n_layers];
+    memset(&ly, 0, sizeof(ly));
+    const bool after_skip = (d.skip_at >= 0 && i == d.skip_at + 1);
+    ly.w = tp->wT[i]; ly.bias = tp->biasT[i];
+    ly.N = ((i == 0) ? d.in_dim : d.widths[i - 1]) + (after_skip ? d.in_dim : 0);
+    ly.Npad = tp->NpadT[i]; ly.act = VQN_ACT_NONE;
+    ly.nseg = 1; ly.seg_chunks[0] = tp->n_chunksT[i]; ly.seg_first_chunk[0] = 0;
+    ly.out_slot = -1; ly.post_scale = 1.f; ly.post_bias = 0.f;
+    ly.tmem_col = (B.pg.n_layers & 1) * 256;
+    ly.tail_out_slot = -1; ly.stash_w = -1; ly.grad_stash = -1; ly.egrad_col0 = -1;
+    if (i == top && !head) ly.seg_type[0] = SRC_GLOBAL;          // dz of the last layer: the caller's buffer
+    else {
+      ly.seg_type[0] = (i == top && head) ? SRC_TAILGRAD : SRC_BWD;
+      ly.bw_y = y[i]; ly.bw_y_ld = (int)ldy[i]; ly.bw_act = d.acts[i];
+      ly.bw_dz = dz[i]; ly.bw_dz_ld = (int)lddz[i]; ly.bw_n = d.widths[i];
+      VQN_CHECK_ARG(y[i] && dz[i] && ldy[i] % 4 == 0 && lddz[i] % 4 == 0 && ldy[i] >= d.widths[i] && lddz[i] >= d.widths[i],
+                    "net_backward_train: activation / dz buffer");
+    }
+    if (head) {                                                 // both MMA layers may need the narrow layer's table / dz
+      ly.tg_dz = dz_last; ly.tg_dz_ld = (int)lddz_last; ly.tg_n = d.widths[2]; ly.tg_w = d.w[2];
+      ly.tg_rows = d.widths[1]; ly.fin_skip_row0 = d.widths[1];
+      if (i != top) { ly.tg_rows = 0; ly.fin_skip_n = d.in_dim; }    // the last MMA layer: only the x half, for the final drain
+    }
+    B.pg.n_layers++;
+  }
+  TcLayer& last = B.pg.layers[B.pg.n_layers - 1];
+  last.out_slot = 0;
+  if (d_input) {
+    VQN_CHECK_ARG(ld_din >= d.in_dim && ld_din < (1 << 20), "net_backward_train: ld_din");
+    B.pg.outs[0] = d_input; B.pg.out_stride[0] = (int)ld_din; last.fin_mode = din_mode;
+    last.N = d.in_dim;
+  } else {
+    // the chain ends in dz[0] = (gradient w.r.t. y[0]) * act'(y[0])
+    VQN_CHECK_ARG(y[0] && dz[0], "net_backward_train: y[0] / dz[0]");
+    B.pg.outs[0] = dz[0]; B.pg.out_stride[0] = (int)lddz[0]; last.fin_mode = 0;
+    last.fin_y = y[0]; last.fin_y_ld = (int)ldy[0]; last.fin_act = d.acts[0];
+    last.N = d.widths[0];
+  }
+  return tc_launch(ctx, B.pg, VQN_PREC_TF32X3, s);
 }

@@ -78,6 +78,8 @@ FUSED_FORWARD = os.environ.get('VQN_TRAIN_FUSED_FORWARD', '1') != '0'
 # one launch per layer, the per-network order of round 1)
 BATCHED_BACKWARD = os.environ.get('VQN_TRAIN_BATCHED_BACKWARD', '1') != '0'
 CONCURRENT_HEADS = os.environ.get('VQN_TRAIN_CONCURRENT_HEADS', '1') != '0'
+# backward-data chain of a network as ONE launch of the fused tcgen05 kernel (vqn_net_backward_train); 0: batched per-level GEMMs
+FUSED_BACKWARD = os.environ.get('VQN_TRAIN_FUSED_BACKWARD', '1') != '0'
 
 
 class _NetTrain:
@@ -172,6 +174,14 @@ class _NetTrain:
         last = len(self.widths) - 1
         abi.act_backward(dy, lddy, self.y[last], self.ld[last], self.n, self.widths[last], self.acts[last],
                          self.out_scale, self.out_scale, self.out_bias, self.dz[last], self.dz[last].shape[1])
+
+    def backward_fused(self, dy: torch.Tensor, lddy: int, d_input: Optional[torch.Tensor], ld_din: int, din_mode: int) -> None:
+        """The backward-DATA chain of the network as ONE launch of the fused tcgen05 kernel (vqn_net_backward_train): fills
+        every dz[i]; the caller batches the weight-gradient GEMMs (weight_problems)."""
+        last = len(self.widths) - 1
+        self.act_backward_last(dy, lddy)
+        self.net.packed.backward_train(self.dz[last], self.dz[last].shape[1], self.n, self.y, self.ld, self.dz,
+                                       [t.shape[1] for t in self.dz], d_input, ld_din, din_mode)
 
     def backward(self, dy: torch.Tensor, lddy: int, dW: List[torch.Tensor], dB: List[torch.Tensor],
                  d_input: Optional[torch.Tensor] = None, ld_din: int = 0, weight_list: Optional[list] = None) -> None:
@@ -458,7 +468,26 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
              ('rough_main', B['d_rough'], 1, d_zenc), ('diff_vq', B['d_vq_albedo'], 3, d_zvq),
              ('spec_vq', B['d_vq_spec'], 3, d_zvq), ('rough_vq', B['d_vq_rough'], 1, d_zvq)]
     wlist: list = []                       # every weight-gradient GEMM of the step: ONE batched launch at the end
-    if BATCHED_BACKWARD:
+    if BATCHED_BACKWARD and FUSED_BACKWARD and prep:
+        # every head's backward-data chain is ONE launch of the fused tcgen05 kernel (transposed weight images, dz_i stored for
+        # the weight gradients, the narrow last layer backwards on the CUDA cores); the six launches are forked over three
+        # streams like the forwards; the three heads of a branch add into the same d_z atomically
+        cur = torch.cuda.current_stream(m.device)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        groups = (heads[0::3], heads[1::3], heads[2::3])
+        for si, grp_ in enumerate(groups):
+            side = cur if si == 0 else st.side_streams[si - 1]
+            if si > 0:
+                side.wait_event(ev)
+            with torch.cuda.stream(side):
+                for name, dy, lddy, dzin in grp_:
+                    nets[name].backward_fused(dy, lddy, dzin, z, 2)
+            if si > 0:
+                done = torch.cuda.Event()
+                done.record(side)
+                cur.wait_event(done)
+    elif BATCHED_BACKWARD:
         # the six heads level by level: the same-level backward-data GEMMs of all heads are independent -> one launch per
         # level (3 launches instead of 24); the three heads of a branch add into the same d_z atomically
         for name, dy, lddy, _ in heads:
@@ -468,6 +497,7 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
             for name, _, _, dzin in heads:
                 probs += nets[name].data_problems(level, dzin, z, atomic=True)
             abi.dense_backward_data_batched(probs, m.device)
+    if BATCHED_BACKWARD:
         head_w = []
         for name, _, _, _ in heads:
             head_w += nets[name].weight_problems(st.dW[name], st.dB[name])
@@ -495,8 +525,14 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
     d_h = B['d_h']
     d_h.zero_()
     wl = wlist if BATCHED_BACKWARD else None
-    nets['bottleneck'].backward(d_zenc, z, st.dW['bottleneck'], st.dB['bottleneck'], d_h, d_h.shape[1], weight_list=wl)
-    nets['fine_enc'].backward(d_h, d_h.shape[1], st.dW['fine_enc'], st.dB['fine_enc'], weight_list=wl)
+    if BATCHED_BACKWARD and FUSED_BACKWARD and prep:
+        nets['bottleneck'].backward_fused(d_zenc, z, d_h, d_h.shape[1], 0)          # d_h is stored (no zero fill needed)
+        nets['fine_enc'].backward_fused(d_h, d_h.shape[1], None, 0, 0)
+        wlist += nets['bottleneck'].weight_problems(st.dW['bottleneck'], st.dB['bottleneck'])
+        wlist += nets['fine_enc'].weight_problems(st.dW['fine_enc'], st.dB['fine_enc'])
+    else:
+        nets['bottleneck'].backward(d_zenc, z, st.dW['bottleneck'], st.dB['bottleneck'], d_h, d_h.shape[1], weight_list=wl)
+        nets['fine_enc'].backward(d_h, d_h.shape[1], st.dW['fine_enc'], st.dB['fine_enc'], weight_list=wl)
     if wlist:
         abi.dense_backward_weights_batched(wlist, m.device)
     if heads_w_done is not None:
