@@ -82,7 +82,8 @@ def test_dense_tc_forced():
         pytest.skip('already running with the tcgen05 kernels forced')
     # ... and the batched weight-gradient / backward-data GEMMs of train_iter on their tcgen05 forms at ANY row count
     # (dense_tc_wgrad_kernel is the default from 1024 rows upwards, which the small test batches never reach)
-    env = dict(os.environ, VQN_DENSE_TC_MIN_M='1', VQN_WGRAD_TC='2', VQN_BWD_TC='2')
+    # (VQN_TRAIN_FUSED_BACKWARD=0: the per-level batched backward-data GEMMs instead of the fused chain the default runs)
+    env = dict(os.environ, VQN_DENSE_TC_MIN_M='1', VQN_WGRAD_TC='2', VQN_BWD_TC='2', VQN_TRAIN_FUSED_BACKWARD='0')
     r = subprocess.run([sys.executable, '-m', 'pytest', os.path.abspath(__file__), '-q', '-x', '-m', 'gpu', '-k',
                         'dense_kernels or gradients_match or graphed'], env=env, capture_output=True, text=True,
                        timeout=600)
