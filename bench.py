@@ -312,8 +312,9 @@ def bench_train_step(dev, rank, world, args):
             'mlp_tflops': TRAIN_FLOP_PER_RAY * n / (ms * 1e-3) / 1e12, 'loss': float(loss), 'eager_ms_per_step': eager_ms,
             'note': 'whole step (fwd, loss, bwd, all-reduce, EMA, Adam) replayed from one CUDA graph; forward = one fused '
                     'tcgen05 launch per network with saved activations (the six heads forked over three streams inside the '
-                    'graph), backward = 3xTF32 mma.sync GEMMs batched per level (six heads: 3 launches; all weight gradients: '
-                    '1 launch); '
+                    'graph), backward = one fused tcgen05 launch per network for the backward-data chain (transposed weight '
+                    'images + the saved activations; head chains forked over the same streams) and ONE tcgen05 launch for all '
+                    'weight gradients; '
                     'eager_ms_per_step = the same kernels launched one by one from Python'}
 
 
