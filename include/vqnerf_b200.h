@@ -294,10 +294,13 @@ int vqn_net_repack_tc(vqn_net* net, int precision, vqn_stream stream);
  * dz_i = (dz_{i+1} . W_{i+1}^T) * act'(y_i) is stored to dz[i] (ld lddz[i]) for the weight gradients; the gradient w.r.t. the
  * network input goes to d_input (ld ld_din; din_mode 0 store / 1 add / 2 atomic add) or, with d_input == NULL, the chain
  * ends in dz[0].  Shapes: plain chains; a skip concat whose x half needs no gradient; the head shape [w0, w1, out <= 3] with
- * skip_at == 1 (d_input required).  Weight images are refreshed by vqn_net_repack_tc / vqn_nets_repack_tc. */
+ * skip_at == 1 (d_input required).  din_y (optional; plain chains): the network's input is the activated output din_y
+ * [n, ld_din_y] of another layer (activation din_act) -- d_input is multiplied by act'(din_y) and is then that layer's dz.
+ * Weight images are refreshed by vqn_net_repack_tc / vqn_nets_repack_tc. */
 int vqn_net_backward_train(vqn_ctx* ctx, vqn_net* net, const float* dz_last, int64_t lddz_last, int64_t n,
                            const float* const* y, const int64_t* ldy, float* const* dz, const int64_t* lddz,
-                           float* d_input, int64_t ld_din, int din_mode, vqn_stream stream);
+                           float* d_input, int64_t ld_din, int din_mode, const float* din_y, int64_t ld_din_y,
+                           int din_act, vqn_stream stream);
 /* the same for `count` networks in ONE launch (the training step refreshes all of its networks after the optimizer step) */
 int vqn_nets_repack_tc(vqn_net* const* nets, int count, int precision, vqn_stream stream);
 /* dX[m,k] (+)= (dZ[m,n] . W[k,n]^T) * act_prev'(Yprev[m,k]); act_prev' is taken from the stored activation
@@ -336,6 +339,14 @@ int vqn_dense_backward_weights_batched(vqn_ctx* ctx, const vqn_dense_problem* pr
 int vqn_act_backward(vqn_ctx* ctx, const float* dy, int64_t lddy, const float* y, int64_t ldy, int64_t m, int n,
                      int act, float scale, float out_scale, float out_bias, float* dz, int64_t lddz,
                      vqn_stream stream);
+/* vqn_act_backward for up to 8 networks (the six heads of a training step) in ONE launch */
+typedef struct vqn_act_job {
+  const float* dy; const float* y; float* dz;
+  int64_t lddy, ldy, lddz, m;
+  int32_t n, act;
+  float scale, out_scale, out_bias, reserved;
+} vqn_act_job;
+int vqn_act_backward_batched(vqn_ctx* ctx, const vqn_act_job* jobs, int count, vqn_stream stream);
 /* dst[:, 0:w] (leading dim ldd) = src[:, 0:w] (leading dim lds): the x half of concat(y, x) (mlp.py:47-48) */
 int vqn_copy_cols(vqn_ctx* ctx, const float* src, int64_t lds, float* dst, int64_t ldd, int64_t m, int w,
                   vqn_stream stream);
@@ -365,6 +376,17 @@ int vqn_loss_train(vqn_ctx* ctx, const float* gtc, const float* rgb, const float
 int vqn_vq_backward(vqn_ctx* ctx, const float* z_enc, const int64_t* indices, const float* codebook, int k,
                     const float* d_zvq, float commit_coef, int64_t n, int accumulate, float* d_zenc,
                     vqn_stream stream);
+/* vqn_vq_backward that also forms the dz of the layer that produced z_enc (its activated output):
+ * dz_out[n, lddz] = d_zenc * act'(z_enc)  (nfr_unit.py:122: the bottleneck ends in a sigmoid); dz_out may be NULL. */
+int vqn_vq_backward_act(vqn_ctx* ctx, const float* z_enc, const int64_t* indices, const float* codebook, int k,
+                        const float* d_zvq, float commit_coef, int64_t n, int accumulate, float* d_zenc, int act,
+                        float* dz_out, int64_t lddz, vqn_stream stream);
+/* memset(ptrs[i], 0, bytes[i]) for up to 8 device buffers in ONE launch (4-byte aligned, sizes multiples of 4):
+ * the accumulators of a training step (gradients, VQ statistics, d_z) */
+int vqn_zero_batched(vqn_ctx* ctx, void* const* ptrs, const int64_t* bytes, int count, vqn_stream stream);
+/* stats32 = (float) stats64 (the VQ statistics' slot of the all-reduce buffer) and rows_slot[0] += rows (optional) */
+int vqn_train_pack_stats(vqn_ctx* ctx, const double* stats64, float* stats32, int64_t count, float* rows_slot, float rows,
+                         vqn_stream stream);
 /* spec = ks*basecolor, albedo = (1-ks)*basecolor backward (vq_nfr.py:590-591); d_spec_extra (optional) is added
  * to d_spec (the lambert term). */
 int vqn_material_combine_backward(vqn_ctx* ctx, const float* basecolor, const float* ks, const float* d_albedo,
@@ -382,6 +404,11 @@ int vqn_adam_amsgrad(vqn_ctx* ctx, float* param, const float* grad, float* m, fl
 /* VQ statistics (float64) <-> the fp32 tail of the flat all-reduce buffer */
 int vqn_cast_f64_f32(vqn_ctx* ctx, const double* src, float* dst, int64_t count, vqn_stream stream);
 int vqn_cast_f32_f64(vqn_ctx* ctx, const float* src, double* dst, int64_t count, vqn_stream stream);
+/* The scalar tail of a training step (train_nfr.py:571; vq_nfr.py:971-986) in one launch:
+ * out[4] = { sums[5]*inv_gbs + r*(vq_w*vq_loss[0] + sim_w*sim_loss[0]), vq_w*vq_loss[0], sim_w*sim_loss[0], r },
+ * r = sums[6]*inv_gbs (share of active rows: weight of the two broadcast scalars).  sim_loss may be NULL. */
+int vqn_train_scalars(vqn_ctx* ctx, const float* sums, const float* vq_loss, const float* sim_loss, float inv_gbs,
+                      float vq_w, float sim_w, float* out, vqn_stream stream);
 
 /* ---- training-batch assembler: outer_sample, nerfactor/train_nfr.py:380-467 ------------------- */
 /* Index half (:401-448): one random 8-neighbour per interior pixel, pairs whose alphas both exceed alpha_thres,

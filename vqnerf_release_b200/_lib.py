@@ -71,6 +71,12 @@ class CopyJob(C.Structure):
                 ('w', C.c_int32), ('reserved', C.c_int32)]
 
 
+class ActJob(C.Structure):
+    _fields_ = [('dy', C.c_void_p), ('y', C.c_void_p), ('dz', C.c_void_p), ('lddy', C.c_int64), ('ldy', C.c_int64),
+                ('lddz', C.c_int64), ('m', C.c_int64), ('n', C.c_int32), ('act', C.c_int32), ('scale', C.c_float),
+                ('out_scale', C.c_float), ('out_bias', C.c_float), ('reserved', C.c_float)]
+
+
 class DenseProblem(C.Structure):
     _fields_ = [('a', C.c_void_p), ('lda', C.c_int64), ('w', C.c_void_p), ('ldw', C.c_int64),
                 ('out', C.c_void_p), ('ldo', C.c_int64), ('yprev', C.c_void_p), ('ldy', C.c_int64),
@@ -132,7 +138,7 @@ SIGNATURES = {
     'vqn_net_forward_train': (_I, [_P, _P, _P, _L, _L, C.POINTER(_P), C.POINTER(_L), _F, _F, _I, _P]),
     'vqn_net_repack_tc': (_I, [_P, _I, _P]),
     'vqn_net_backward_train': (_I, [_P, _P, _P, _L, _L, C.POINTER(_P), C.POINTER(_L), C.POINTER(_P), C.POINTER(_L), _P, _L,
-                                    _I, _P]),
+                                    _I, _P, _L, _I, _P]),
     'vqn_nets_repack_tc': (_I, [C.POINTER(_P), _I, _I, _P]),
     'vqn_copy_cols_batched': (_I, [_P, C.POINTER(CopyJob), _I, _P]),
     'vqn_dense_backward_data': (_I, [_P, _P, _L, _P, _P, _L, _P, _L, _I, _I, _L, _I, _I, _P]),
@@ -151,6 +157,11 @@ SIGNATURES = {
     'vqn_adam_amsgrad': (_I, [_P, _P, _P, _P, _P, _P, _L, _F, _P, _F, _F, _F, _P]),
     'vqn_cast_f64_f32': (_I, [_P, _P, _P, _L, _P]),
     'vqn_cast_f32_f64': (_I, [_P, _P, _P, _L, _P]),
+    'vqn_zero_batched': (_I, [_P, C.POINTER(_P), C.POINTER(_L), _I, _P]),
+    'vqn_train_pack_stats': (_I, [_P, _P, _P, _L, _P, _F, _P]),
+    'vqn_vq_backward_act': (_I, [_P, _P, _P, _P, _I, _P, _F, _L, _I, _P, _I, _P, _L, _P]),
+    'vqn_train_scalars': (_I, [_P, _P, _P, _P, _F, _F, _F, _P, _P]),
+    'vqn_act_backward_batched': (_I, [_P, _P, _I, _P]),
     'vqn_sample_pairs': (_I, [_P, _P, _I, _I, _I, _F, _I, C.c_uint64, _P, _P, _P, _P, _P, _P, _P]),
     'vqn_gather_rows': (_I, [_P, _P, _P, _L, _I, _P, _P]),
     'vqn_microbench_fma': (_I, [_P, _I, _I, C.POINTER(_D)]),

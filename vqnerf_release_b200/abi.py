@@ -84,8 +84,10 @@ class PackedNet:
 
     def backward_train(self, dz_last: torch.Tensor, lddz_last: int, n: int, ys: Sequence[torch.Tensor],
                        ldys: Sequence[int], dzs: Sequence[torch.Tensor], lddzs: Sequence[int],
-                       d_input: Optional[torch.Tensor] = None, ld_din: int = 0, din_mode: int = 0) -> None:
-        """vqn_net_backward_train: the backward-data chain of the whole network in one launch (tf32x3)."""
+                       d_input: Optional[torch.Tensor] = None, ld_din: int = 0, din_mode: int = 0,
+                       din_y: Optional[torch.Tensor] = None, ld_din_y: int = 0, din_act: int = 0) -> None:
+        """vqn_net_backward_train: the backward-data chain of the whole network in one launch (tf32x3).  din_y: the
+        network's input is the activated output of another layer -- d_input becomes that layer's dz (times act'(din_y))."""
         nl = len(self.weights)
         yp = (C.c_void_p * nl)(*[y.data_ptr() for y in ys])
         lp = (C.c_int64 * nl)(*[int(v) for v in ldys])
@@ -93,7 +95,9 @@ class PackedNet:
         zl = (C.c_int64 * nl)(*[int(v) for v in lddzs])
         L.check(self.ctx.lib.vqn_net_backward_train(self.ctx.handle, self.handle, dz_last.data_ptr(), int(lddz_last), int(n),
                                                     yp, lp, zp, zl, None if d_input is None else d_input.data_ptr(),
-                                                    int(ld_din), int(din_mode), L.stream_ptr(dz_last.device)))
+                                                    int(ld_din), int(din_mode),
+                                                    None if din_y is None else din_y.data_ptr(), int(ld_din_y), int(din_act),
+                                                    L.stream_ptr(dz_last.device)))
 
     def forward_train(self, x: torch.Tensor, ldx: int, n: int, ys: Sequence[torch.Tensor], lds: Sequence[int],
                       out_scale: float = 1.0, out_bias: float = 0.0, precision='tf32x3') -> None:
@@ -775,6 +779,27 @@ def act_backward(dy, lddy, y, ldy, m, n, act, scale, out_scale, out_bias, dz, ld
                                    float(out_bias), _p(dz), lddz, L.stream_ptr(dy.device)))
 
 
+def act_backward_batched(jobs, dev):
+    """jobs: list of the argument tuples of act_backward (<= 8) -- ONE launch."""
+    if not jobs:
+        return
+    c = L.Context.get(dev)
+    arr = (L.ActJob * len(jobs))()
+    for q, (dy, lddy, y, ldy, m, n, act, scale, out_scale, out_bias, dz, lddz) in zip(arr, jobs):
+        q.dy, q.y, q.dz = _ptr_int(dy), (_ptr_int(y) if y is not None else None), _ptr_int(dz)
+        q.lddy, q.ldy, q.lddz, q.m, q.n, q.act = lddy, ldy, lddz, m, n, act
+        q.scale, q.out_scale, q.out_bias = float(scale), float(out_scale), float(out_bias)
+    L.check(c.lib.vqn_act_backward_batched(c.handle, arr, len(jobs), L.stream_ptr(dev)))
+
+
+def train_scalars(sums, vq_loss, sim_loss, inv_gbs, vq_w, sim_w, out):
+    """out[4] = [weighted loss, vq_w*vq_loss, sim_w*sim_loss, rows/global_bs] on the device (train_nfr.py:571)."""
+    c = _ctx(sums)
+    L.check(c.lib.vqn_train_scalars(c.handle, _p(sums), _p(vq_loss), _p(sim_loss) if sim_loss is not None else None,
+                                    float(inv_gbs), float(vq_w), float(sim_w), _p(out), L.stream_ptr(sums.device)))
+    return out
+
+
 def copy_cols(src, lds, dst, ldd, m, w, dst_off=0):
     c = _ctx(src)
     L.check(c.lib.vqn_copy_cols(c.handle, _p(src), lds, _p(dst, dst_off), ldd, m, w, L.stream_ptr(src.device)))
@@ -839,11 +864,30 @@ def loss_train(gtc, rgb, vqrgb, z_vq, spec, rough, data_is_nerf, combine_weight,
                                  _p(sums), L.stream_ptr(gtc.device)))
 
 
-def vq_backward(z_enc, indices, codebook, d_zvq, commit_coef, d_zenc, accumulate=True):
+def vq_backward(z_enc, indices, codebook, d_zvq, commit_coef, d_zenc, accumulate=True, act=0, dz_out=None):
+    """dz_out (optional, [n, ld]): also d_zenc * act'(z_enc) -- the dz of the layer whose activated output z_enc is."""
     c = _ctx(z_enc)
-    L.check(c.lib.vqn_vq_backward(c.handle, _p(z_enc), _p(indices), _p(codebook), codebook.shape[1], _p(d_zvq),
-                                  float(commit_coef), z_enc.shape[0], int(accumulate), _p(d_zenc),
-                                  L.stream_ptr(z_enc.device)))
+    L.check(c.lib.vqn_vq_backward_act(c.handle, _p(z_enc), _p(indices), _p(codebook), codebook.shape[1], _p(d_zvq),
+                                      float(commit_coef), z_enc.shape[0], int(accumulate), _p(d_zenc), int(act),
+                                      None if dz_out is None else _p(dz_out), 0 if dz_out is None else dz_out.shape[1],
+                                      L.stream_ptr(z_enc.device)))
+
+
+def zero_batched(tensors, dev):
+    """Clear up to 8 contiguous device tensors in ONE launch."""
+    c = L.Context.get(dev)
+    for i in range(0, len(tensors), 8):
+        chunk = tensors[i:i + 8]
+        ptrs = (C.c_void_p * len(chunk))(*[t.data_ptr() for t in chunk])
+        sizes = (C.c_int64 * len(chunk))(*[t.numel() * t.element_size() for t in chunk])
+        L.check(c.lib.vqn_zero_batched(c.handle, ptrs, sizes, len(chunk), L.stream_ptr(dev)))
+
+
+def train_pack_stats(stats64, stats32, rows_slot, rows):
+    """stats32 = float(stats64); rows_slot[0] += rows (this rank's active-row count, part of the all-reduce buffer)."""
+    c = _ctx(stats64)
+    L.check(c.lib.vqn_train_pack_stats(c.handle, _p(stats64), _p(stats32), stats64.numel(), _p(rows_slot), float(rows),
+                                       L.stream_ptr(stats64.device)))
 
 
 def material_combine_backward(basecolor, ks, d_albedo, d_spec, d_spec_extra, d_basecolor, d_ks):

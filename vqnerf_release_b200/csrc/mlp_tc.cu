@@ -1777,7 +1777,8 @@ extern "C" int vqn_net_repack_tc(vqn_net* net, int precision, vqn_stream stream)
 // its x half is added to d_input in the final drain).
 extern "C" int vqn_net_backward_train(vqn_ctx* ctx, vqn_net* net, const float* dz_last, int64_t lddz_last, int64_t n,
                                       const float* const* y, const int64_t* ldy, float* const* dz, const int64_t* lddz,
-                                      float* d_input, int64_t ld_din, int din_mode, vqn_stream stream) {
+                                      float* d_input, int64_t ld_din, int din_mode, const float* din_y,
+                                      int64_t ld_din_y, int din_act, vqn_stream stream) {
   VQN_CHECK_ARG(ctx && net && dz_last && y && ldy && dz && lddz && n >= 0, "net_backward_train: null argument");
   VQN_CHECK_ARG(lddz_last % 4 == 0 && lddz_last < (1 << 20), "net_backward_train: lddz_last must be a multiple of 4");
   VQN_CHECK_ARG(din_mode >= 0 && din_mode <= 2, "net_backward_train: din_mode");
@@ -1832,6 +1833,11 @@ extern "C" int vqn_net_backward_train(vqn_ctx* ctx, vqn_net* net, const float* d
     VQN_CHECK_ARG(ld_din >= d.in_dim && ld_din < (1 << 20), "net_backward_train: ld_din");
     B.pg.outs[0] = d_input; B.pg.out_stride[0] = (int)ld_din; last.fin_mode = din_mode;
     last.N = d.in_dim;
+    if (din_y) {                     // the input is another layer's activated output: end in that layer's dz
+      if (head || d.skip_at >= 0) TC_UNSUPPORTED("net_backward_train: din_y with a skip concat");
+      VQN_CHECK_ARG(ld_din_y >= d.in_dim && ld_din_y % 4 == 0 && ld_din_y < (1 << 20), "net_backward_train: ld_din_y");
+      last.fin_y = din_y; last.fin_y_ld = (int)ld_din_y; last.fin_act = din_act;
+    }
   } else {
     // the chain ends in dz[0] = (gradient w.r.t. y[0]) * act'(y[0])
     VQN_CHECK_ARG(y[0] && dz[0], "net_backward_train: y[0] / dz[0]");

@@ -13,6 +13,7 @@
 //   forward   (mlp.py:44-46)   Y  = act(X . W + b)                 A = X,    B = W
 //   bwd data                   dX = (dZ . W^T) * act'(Y_prev)      A = dZ,   B = W^T (read in place)
 //   bwd weight                 dW += X^T . dZ  (split over rows, fp32 atomics),  db += colsum(dZ) (fused)
+#include <algorithm>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -259,6 +260,24 @@ __global__ void act_grad_kernel(const float* __restrict__ dy, long long lddy, co
   dz[(long long)m * lddz + n] = v;
 }
 
+// the last-layer activation gradients of several networks (the six heads of a training step) in ONE launch: blockIdx.y = job
+constexpr int ACT_JOBS_MAX = 8;
+struct ActJobs { vqn_act_job j[ACT_JOBS_MAX]; };
+__global__ void act_grad_batched_kernel(const __grid_constant__ ActJobs jobs) {
+  const vqn_act_job& q = jobs.j[blockIdx.y];
+  const long long total = (long long)q.m * q.n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / q.n;
+    const int n = (int)(i % q.n);
+    float v = q.dy[m * q.lddy + n] * q.scale;
+    if (q.act != VQN_ACT_NONE) {
+      const float a = (q.y[m * q.ldy + n] - q.out_bias) / q.out_scale;
+      v *= (q.act == VQN_ACT_RELU) ? (a > 0.f ? 1.f : 0.f) : a * (1.f - a);
+    }
+    q.dz[m * q.lddz + n] = v;
+  }
+}
+
 }  // namespace
 
 // train_tc.cu: the same two contracts on tcgen05/TMEM (taken from vqn_dense_tc_min_m() rows upwards)
@@ -344,6 +363,26 @@ extern "C" int vqn_act_backward(vqn_ctx* ctx, const float* dy, int64_t lddy, con
   const long long total = (long long)m * n;
   act_grad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, vqn_cs(stream)>>>(dy, lddy, y, ldy, (int)m, n, act, scale,
                                                                               out_scale, out_bias, dz, lddz);
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}
+
+/* vqn_act_backward for up to 8 networks in ONE launch */
+extern "C" int vqn_act_backward_batched(vqn_ctx* ctx, const vqn_act_job* jobs, int count, vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && jobs && count >= 0 && count <= ACT_JOBS_MAX, "act_backward_batched: 0..8 jobs");
+  if (count == 0) return VQN_OK;
+  ActJobs a;
+  long long most = 0;
+  for (int i = 0; i < count; ++i) {
+    const vqn_act_job& q = jobs[i];
+    VQN_CHECK_ARG(q.dy && q.dz && (q.act == VQN_ACT_NONE || q.y) && q.m >= 0 && q.n > 0, "act_backward_batched: null pointer");
+    VQN_CHECK_ARG(q.out_scale != 0.f, "act_backward_batched: out_scale == 0");
+    a.j[i] = q;
+    most = std::max(most, (long long)q.m * q.n);
+  }
+  if (most == 0) return VQN_OK;
+  dim3 grid((unsigned)std::min<long long>((most + 255) / 256, 1024), (unsigned)count);
+  act_grad_batched_kernel<<<grid, 256, 0, vqn_cs(stream)>>>(a);
   VQN_LAUNCHED(ctx);
   return VQN_OK;
 }

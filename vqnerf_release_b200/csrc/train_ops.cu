@@ -10,6 +10,7 @@
 //  sim_loss_kernel       codebook separation loss and its gradient through get_codebook()
 //  adam_kernel           tf.keras.optimizers.Adam(amsgrad=True) dense update
 #include "common.cuh"
+#include <cstdlib>
 
 #define TL 512
 
@@ -36,134 +37,158 @@ struct ShadeBwdParams {
 //   d f0_ch   = g_ch * sum_l (1 - p5) S w R_ch
 //   d rough   = 4 rough^3 * sum_l S w (sum_ch g_ch F_ch R_ch) * [1/A + T_v - 2 hn^2/q - (1 - cl^2)/(2 sqrt(u_l) den_l)]
 //   d light_l,ch += g_ch (F_ch S + alb_ch/pi) w area_l         (clip_by_value_preserve_gradient: identity, :759)
-__global__ void __launch_bounds__(256, 1) shade_bwd_kernel(ShadeBwdParams a) {
+// Work split: SB_LW warps share a point, each owning 4 / SB_LW blocks of 128 lights (lane l: 4 consecutive lights of a
+// block, the float4 the forward kernel reads).  With all 512 lights in one warp the 48 per-lane light gradients pushed the
+// kernel to 161 registers = 8..12 warps per SM, and at 8192 points (55 per SM) it was latency-bound at 4x its issue bound.
+// The partial sums of a point meet in shared memory in a fixed order (deterministic); the loop trip count is uniform per
+// CTA.  Per-light divisions are the forward kernel's __fdividef (shade.cu); sqrt is sqrt.approx (1 ulp).
+constexpr int SB_THREADS = 256, SB_WARPS = SB_THREADS / 32;
+__device__ __forceinline__ float fast_sqrt_(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+template <int SB_LW, int MIN_CTAS>
+__global__ void __launch_bounds__(SB_THREADS, MIN_CTAS) shade_bwd_kernel(ShadeBwdParams a) {
+  constexpr int SB_PPI = SB_WARPS / SB_LW, SB_LB = 4 / SB_LW;
   __shared__ __align__(16) float lx[TL], ly[TL], lz[TL], rad[3 * TL], dls[3 * TL];
+  __shared__ float part[2][SB_PPI][SB_LW][8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < TL; i += 256) {
-    lx[i] = a.lxyz[3 * i]; ly[i] = a.lxyz[3 * i + 1]; lz[i] = a.lxyz[3 * i + 2];
+  const int ps = warp / SB_LW, lq = warp % SB_LW;
+  // light tables permuted so that lane l of a warp finds light 4 l + q of a 128-block at [32 q + l]: the per-light scalar
+  // reads in the loop are bank-conflict-free and nothing loop-invariant has to be held in registers
+  for (int i = tid; i < TL; i += SB_THREADS) {
+    const int pos = (i & ~127) + 32 * (i & 3) + ((i & 127) >> 2);
+    lx[pos] = a.lxyz[3 * i]; ly[pos] = a.lxyz[3 * i + 1]; lz[pos] = a.lxyz[3 * i + 2];
   }
-  for (int i = tid; i < 3 * TL; i += 256) {
+  for (int i = tid; i < 3 * TL; i += SB_THREADS) {
     const int ch = i / TL, l = i % TL;
+    const int pos = (l & ~127) + 32 * (l & 3) + ((l & 127) >> 2);
     float v = a.light[l * 3 + ch];
     if (a.clip_light0) v = fmaxf(v, 0.f);
-    rad[i] = v * a.lareas[l];
+    rad[ch * TL + pos] = v * a.lareas[l];
     dls[i] = 0.f;
   }
   __syncthreads();
   const float INV_PI = 0.318309886183790671538f;
-  float dl[16][3];
+  float dl[4 * SB_LB][3];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) { dl[k][0] = 0.f; dl[k][1] = 0.f; dl[k][2] = 0.f; }
-  const long long warps_total = (long long)gridDim.x * 8;
-  for (long long i = (long long)blockIdx.x * 8 + warp; i < a.n; i += warps_total) {
-    const long long row = a.row_idx ? (long long)a.row_idx[i] : i;
-    const float px = a.xyz[row * 3], py = a.xyz[row * 3 + 1], pz = a.xyz[row * 3 + 2];
-    float vx = a.rayo[row * 3] - px, vy = a.rayo[row * 3 + 1] - py, vz = a.rayo[row * 3 + 2] - pz;
-    {
-      float inv = rsqrtf(fmaxf(vx * vx + vy * vy + vz * vz, 1e-6f));
-      vx *= inv; vy *= inv; vz *= inv;
-    }
-    float nx = a.normal[row * 3], ny = a.normal[row * 3 + 1], nz = a.normal[row * 3 + 2];
-    {
-      float c = nx * vx + ny * vy + nz * vz;
-      if (!(c >= 0.f)) { nx = -nx; ny = -ny; nz = -nz; }
-    }
-    const float inv_n = rsqrtf(fmaxf(nx * nx + ny * ny + nz * nz, 1e-6f));
-    const float vn = (nx * vx + ny * vy + nz * vz) * inv_n;
-    const float alb[3] = {a.albedo[i * 3] * INV_PI, a.albedo[i * 3 + 1] * INV_PI, a.albedo[i * 3 + 2] * INV_PI};
-    const float f0[3] = {a.spec[i * 3], a.spec[i * 3 + 1], a.spec[i * 3 + 2]};
-    const float g[3] = {a.d_rgb[i * 3], a.d_rgb[i * 3 + 1], a.d_rgb[i * 3 + 2]};
-    const float rough = a.rough[i];
-    const float alpha = rough * rough, a2 = alpha * alpha;
-    const float oma2 = 1.0f - a2, a2m1 = a2 - 1.0f;
-    const float cv = fminf(fmaxf(vn, 0.f), 1.f);
-    const float su_v = sqrtf(fabsf(a2 + oma2 * cv * cv));
-    const float den_v = cv + su_v;
-    const float g_v = den_v == 0.f ? 0.f : 2.0f * cv / den_v;
-    const float avn = fabsf(vn);
-    const float a_pt = avn == 0.f ? 0.f : a2 * g_v * (0.5f * INV_PI) / avn;
-    // point-level part of d ln(S)/dA: 1/A + (d g_v/dA)/g_v
-    const float t_pt = (a2 > 0.f ? 1.0f / a2 : 0.f) -
-                       ((su_v * den_v) > 0.f ? (1.0f - cv * cv) / (2.0f * su_v * den_v) : 0.f);
+  for (int k = 0; k < 4 * SB_LB; ++k) { dl[k][0] = 0.f; dl[k][1] = 0.f; dl[k][2] = 0.f; }
+  int it = 0;
+  for (long long base = (long long)blockIdx.x * SB_PPI; base < a.n; base += (long long)gridDim.x * SB_PPI, ++it) {
+    const long long i = base + ps;
+    const bool valid = i < a.n;                  // warp-uniform
+    float g[3] = {0.f, 0.f, 0.f}, rough = 0.f;
     float s_alb[3] = {0.f, 0.f, 0.f}, s_f0[3] = {0.f, 0.f, 0.f}, s_rough = 0.f;
+    if (valid) {
+      const long long row = a.row_idx ? (long long)a.row_idx[i] : i;
+      const float px = a.xyz[row * 3], py = a.xyz[row * 3 + 1], pz = a.xyz[row * 3 + 2];
+      float vx = a.rayo[row * 3] - px, vy = a.rayo[row * 3 + 1] - py, vz = a.rayo[row * 3 + 2] - pz;
+      {
+        float inv = rsqrtf(fmaxf(vx * vx + vy * vy + vz * vz, 1e-6f));
+        vx *= inv; vy *= inv; vz *= inv;
+      }
+      float nx = a.normal[row * 3], ny = a.normal[row * 3 + 1], nz = a.normal[row * 3 + 2];
+      {
+        float c = nx * vx + ny * vy + nz * vz;
+        if (!(c >= 0.f)) { nx = -nx; ny = -ny; nz = -nz; }
+      }
+      const float inv_n = rsqrtf(fmaxf(nx * nx + ny * ny + nz * nz, 1e-6f));
+      const float vn = (nx * vx + ny * vy + nz * vz) * inv_n;
+      const float alb[3] = {a.albedo[i * 3] * INV_PI, a.albedo[i * 3 + 1] * INV_PI, a.albedo[i * 3 + 2] * INV_PI};
+      const float f0[3] = {a.spec[i * 3], a.spec[i * 3 + 1], a.spec[i * 3 + 2]};
+      g[0] = a.d_rgb[i * 3]; g[1] = a.d_rgb[i * 3 + 1]; g[2] = a.d_rgb[i * 3 + 2];
+      rough = a.rough[i];
+      const float alpha = rough * rough, a2 = alpha * alpha;
+      const float oma2 = 1.0f - a2, a2m1 = a2 - 1.0f;
+      const float cv = fminf(fmaxf(vn, 0.f), 1.f);
+      const float su_v = sqrtf(fabsf(a2 + oma2 * cv * cv));
+      const float den_v = cv + su_v;
+      const float g_v = den_v == 0.f ? 0.f : 2.0f * cv / den_v;
+      const float avn = fabsf(vn);
+      const float a_pt = avn == 0.f ? 0.f : a2 * g_v * (0.5f * INV_PI) / avn;
+      // point-level part of d ln(S)/dA: 1/A + (d g_v/dA)/g_v
+      const float t_pt = (a2 > 0.f ? 1.0f / a2 : 0.f) -
+                         ((su_v * den_v) > 0.f ? (1.0f - cv * cv) / (2.0f * su_v * den_v) : 0.f);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int lb = 128 * j + 4 * lane;
-      const float4 X = *reinterpret_cast<const float4*>(lx + lb);
-      const float4 Y = *reinterpret_cast<const float4*>(ly + lb);
-      const float4 Z = *reinterpret_cast<const float4*>(lz + lb);
-      const float4 R0 = *reinterpret_cast<const float4*>(rad + lb);
-      const float4 R1 = *reinterpret_cast<const float4*>(rad + TL + lb);
-      const float4 R2 = *reinterpret_cast<const float4*>(rad + 2 * TL + lb);
-      float4 LV = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (a.lvis) LV = ldg_stream_f4(a.lvis + row * TL + lb);
-      const float xs4[4] = {X.x, X.y, X.z, X.w}, ys4[4] = {Y.x, Y.y, Y.z, Y.w}, zs4[4] = {Z.x, Z.y, Z.z, Z.w};
-      const float r0[4] = {R0.x, R0.y, R0.z, R0.w}, r1[4] = {R1.x, R1.y, R1.z, R1.w}, r2[4] = {R2.x, R2.y, R2.z, R2.w};
-      const float lv4[4] = {LV.x, LV.y, LV.z, LV.w};
+      for (int j = 0; j < SB_LB; ++j) {
+        const int blk = lq * SB_LB + j;
+        const int pb = 128 * blk + lane;         // the lane's constants in the permuted tables: [pb + 32 q]
+        float4 LV = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (a.lvis) LV = ldg_stream_f4(a.lvis + row * TL + 128 * blk + 4 * lane);
+        const float lv4[4] = {LV.x, LV.y, LV.z, LV.w};
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int li = 4 * j + q;
-        float dx = xs4[q] - px, dy = ys4[q] - py, dz = zs4[q] - pz;
-        const float inv = fast_rsqrt_(fmaxf(dx * dx + dy * dy + dz * dz, 1e-6f));
-        dx *= inv; dy *= inv; dz *= inv;
-        const float cos_r = dx * nx + dy * ny + dz * nz;
-        const float ln = cos_r * inv_n;
-        const float lv = dx * vx + dy * vy + dz * vz;
-        // h = normalize(l + v), formed componentwise as the reference does (microfacet.py:21-22).  The shortcut
-        // |l + v|^2 = 2 + 2 l.v is cheaper but its rounding error is amplified by 2/q in q = 1 - (h.n)^2 (1 - a^2)
-        // near the highlight (h ~ n, small roughness): 2e-4 relative on the specular lobe, outside the parity budget.
-        const float hx = dx + vx, hy = dy + vy, hz = dz + vz;
-        const float hi_ = fast_rsqrt_(fmaxf(hx * hx + hy * hy + hz * hz, 1e-6f));
-        const float hvr = (hx * vx + hy * vy + hz * vz) * hi_;
-        const float hnr = (hx * nx + hy * ny + hz * nz) * inv_n * hi_;
-        const float hv = fminf(fmaxf(hvr, 0.f), 1.f);                     // h . v
-        const float hn = fminf(fmaxf(hnr, 0.f), 1.f);                     // h . n
-        const float om = 1.0f - hv, om2 = om * om;
-        const float p5 = om2 * om2 * om;
-        const float q_ = fmaf(hn * hn, a2m1, 1.0f);
-        const float cl = fminf(fmaxf(ln, 0.f), 1.f);
-        const float su_l = sqrtf(fabsf(fmaf(oma2, cl * cl, a2)));
-        const float den_l = cl + su_l;
-        const float den = q_ * q_ * den_l * fabsf(ln);
-        const float S = den == 0.f ? 0.f : a_pt * cl / den;
-        const float wv = (cos_r > 0.f ? cos_r : 0.f) * lv4[q];
-        const float sw = S * wv;
-        const float R[3] = {r0[q], r1[q], r2[q]};
-        float gFR = 0.f;
+        for (int q = 0; q < 4; ++q) {
+          const int li = 4 * j + q;
+          float dx = lx[pb + 32 * q] - px, dy = ly[pb + 32 * q] - py, dz = lz[pb + 32 * q] - pz;
+          const float inv = fast_rsqrt_(fmaxf(dx * dx + dy * dy + dz * dz, 1e-6f));
+          dx *= inv; dy *= inv; dz *= inv;
+          const float cos_r = dx * nx + dy * ny + dz * nz;
+          const float ln = cos_r * inv_n;
+          // h = normalize(l + v), formed componentwise as the reference does (microfacet.py:21-22).  The shortcut
+          // |l + v|^2 = 2 + 2 l.v is cheaper but its rounding error is amplified by 2/q in q = 1 - (h.n)^2 (1 - a^2)
+          // near the highlight (h ~ n, small roughness): 2e-4 relative on the specular lobe, outside the parity budget.
+          const float hx = dx + vx, hy = dy + vy, hz = dz + vz;
+          const float hi_ = fast_rsqrt_(fmaxf(hx * hx + hy * hy + hz * hz, 1e-6f));
+          const float hvr = (hx * vx + hy * vy + hz * vz) * hi_;
+          const float hnr = (hx * nx + hy * ny + hz * nz) * inv_n * hi_;
+          const float hv = fminf(fmaxf(hvr, 0.f), 1.f);                     // h . v
+          const float hn = fminf(fmaxf(hnr, 0.f), 1.f);                     // h . n
+          const float om = 1.0f - hv, om2 = om * om;
+          const float p5 = om2 * om2 * om;
+          const float q_ = fmaf(hn * hn, a2m1, 1.0f);
+          const float cl = fminf(fmaxf(ln, 0.f), 1.f);
+          const float su_l = fast_sqrt_(fabsf(fmaf(oma2, cl * cl, a2)));
+          const float den_l = cl + su_l;
+          const float den = q_ * q_ * den_l * fabsf(ln);
+          const float S = den == 0.f ? 0.f : __fdividef(a_pt * cl, den);
+          const float wv = (cos_r > 0.f ? cos_r : 0.f) * lv4[q];
+          const float sw = S * wv;
+          const float R[3] = {rad[pb + 32 * q], rad[TL + pb + 32 * q], rad[2 * TL + pb + 32 * q]};
+          float gFR = 0.f;
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          const float F = fmaf(f0[ch], 1.0f - p5, p5);
-          s_alb[ch] = fmaf(wv, R[ch], s_alb[ch]);
-          s_f0[ch] = fmaf((1.0f - p5) * sw, R[ch], s_f0[ch]);
-          gFR = fmaf(g[ch] * F, R[ch], gFR);
-          dl[li][ch] = fmaf(g[ch], fmaf(F, sw, alb[ch] * wv), dl[li][ch]);
+          for (int ch = 0; ch < 3; ++ch) {
+            const float F = fmaf(f0[ch], 1.0f - p5, p5);
+            s_alb[ch] = fmaf(wv, R[ch], s_alb[ch]);
+            s_f0[ch] = fmaf((1.0f - p5) * sw, R[ch], s_f0[ch]);
+            gFR = fmaf(g[ch] * F, R[ch], gFR);
+            dl[li][ch] = fmaf(g[ch], fmaf(F, sw, alb[ch] * wv), dl[li][ch]);
+          }
+          const float sd = su_l * den_l;
+          const float bk = t_pt - (q_ != 0.f ? __fdividef(2.0f * hn * hn, q_) : 0.f) -
+                           (sd > 0.f ? __fdividef(1.0f - cl * cl, 2.0f * sd) : 0.f);
+          s_rough = fmaf(sw * bk, gFR, s_rough);
         }
-        const float bk = t_pt - (q_ != 0.f ? 2.0f * hn * hn / q_ : 0.f) -
-                         ((su_l * den_l) > 0.f ? (1.0f - cl * cl) / (2.0f * su_l * den_l) : 0.f);
-        s_rough = fmaf(sw * bk, gFR, s_rough);
       }
     }
+    // (outside the branch: `valid` is warp-uniform, but the compiler cannot know, and shuffles under a divergent-looking
+    // branch cost a WARPSYNC + collective prologue each)
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) { s_alb[ch] = warp_sum(s_alb[ch]); s_f0[ch] = warp_sum(s_f0[ch]); }
     s_rough = warp_sum(s_rough);
     if (lane == 0) {
+      float* pp = part[it & 1][ps][lq];
+      pp[0] = s_alb[0]; pp[1] = s_alb[1]; pp[2] = s_alb[2];
+      pp[3] = s_f0[0]; pp[4] = s_f0[1]; pp[5] = s_f0[2]; pp[6] = s_rough;
+    }
+    __syncthreads();                   // buffer (it & 1) is rewritten two iterations later, after the next barrier
+    if (lq == 0 && valid && lane < 7) {
+      float sum = 0.f;
 #pragma unroll
-      for (int ch = 0; ch < 3; ++ch) {
-        a.d_albedo[i * 3 + ch] = g[ch] * INV_PI * s_alb[ch];
-        a.d_spec[i * 3 + ch] = g[ch] * s_f0[ch];
-      }
-      a.d_rough[i] = 4.0f * rough * rough * rough * s_rough;
+      for (int w = 0; w < SB_LW; ++w) sum += part[it & 1][ps][w][lane];
+      const int ch = lane < 3 ? lane : lane - 3;
+      const float gc = ch == 0 ? g[0] : ch == 1 ? g[1] : g[2];
+      if (lane < 3) a.d_albedo[i * 3 + lane] = gc * INV_PI * sum;
+      else if (lane < 6) a.d_spec[i * 3 + lane - 3] = gc * sum;
+      else a.d_rough[i] = 4.0f * rough * rough * rough * sum;
     }
   }
   // flush the per-lane light gradients: smem per block, then one global atomic per (light, channel)
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
+  for (int j = 0; j < SB_LB; ++j)
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
-      for (int ch = 0; ch < 3; ++ch) atomicAdd(&dls[ch * TL + 128 * j + 4 * lane + q], dl[4 * j + q][ch]);
+      for (int ch = 0; ch < 3; ++ch)
+        atomicAdd(&dls[ch * TL + 128 * (lq * SB_LB + j) + 4 * lane + q], dl[4 * j + q][ch]);
   __syncthreads();
-  for (int i = tid; i < 3 * TL; i += 256) {
+  for (int i = tid; i < 3 * TL; i += SB_THREADS) {
     const int ch = i / TL, l = i % TL;
     const float v = dls[i] * a.lareas[l];
     if (v != 0.f) atomicAdd(&a.d_light[l * 3 + ch], v);
@@ -192,7 +217,10 @@ __global__ void __launch_bounds__(256) loss_train_kernel(LossParams p) {
   const int lane = threadIdx.x & 31;
   const long long pair = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long npairs = p.n >> 1;
-  if (pair >= npairs) return;
+  __shared__ float bsum[6];
+  if (threadIdx.x < 6) bsum[threadIdx.x] = 0.f;
+  __syncthreads();
+  if (pair < npairs) {
   float terms[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   float schr[3] = {0.f, 0.f, 0.f};
   if (lane < 2) {
@@ -284,10 +312,14 @@ __global__ void __launch_bounds__(256) loss_train_kernel(LossParams p) {
   t0 += __shfl_xor_sync(0xffffffffu, t0, 1); t1 += __shfl_xor_sync(0xffffffffu, t1, 1);
   t2 += __shfl_xor_sync(0xffffffffu, t2, 1); t3 += __shfl_xor_sync(0xffffffffu, t3, 1);
   t4 += __shfl_xor_sync(0xffffffffu, t4, 1);
+  // per block in shared memory first: 4096 warps adding to the same six addresses serialise in L2 (35 us of an 8192-row step)
   if (lane == 0 && p.sums) {
-    atomicAdd(&p.sums[0], t0); atomicAdd(&p.sums[1], t1); atomicAdd(&p.sums[2], t2); atomicAdd(&p.sums[3], t3);
-    atomicAdd(&p.sums[4], t4); atomicAdd(&p.sums[5], t0 + t1 + t2 + t3 + t4);
+    atomicAdd(&bsum[0], t0); atomicAdd(&bsum[1], t1); atomicAdd(&bsum[2], t2); atomicAdd(&bsum[3], t3);
+    atomicAdd(&bsum[4], t4); atomicAdd(&bsum[5], t0 + t1 + t2 + t3 + t4);
   }
+  }
+  __syncthreads();
+  if (threadIdx.x < 6 && p.sums) atomicAdd(&p.sums[threadIdx.x], bsum[threadIdx.x]);
 }
 
 // z_vq = z_norm + sg(q - z_norm) (vq_layers.py:327) => d z_norm = d z_vq; commitment term
@@ -295,7 +327,8 @@ __global__ void __launch_bounds__(256) loss_train_kernel(LossParams p) {
 // z_norm = z * rsqrt(max(sum z^2, 1e-6)) (util/math.py:63-64) => d z = inv (g - z_norm (g . z_norm)) (or inv g below eps)
 __global__ void __launch_bounds__(256) vq_bwd_kernel(const float* __restrict__ z_enc, const long long* __restrict__ idx,
                                                      const float* __restrict__ cb, int K, const float* __restrict__ d_zvq,
-                                                     float coef, long long n, int accumulate, float* __restrict__ d_zenc) {
+                                                     float coef, long long n, int accumulate, float* __restrict__ d_zenc,
+                                                     int act, float* __restrict__ dz_out, long long lddz) {
   const int lane = threadIdx.x & 31;
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n) return;
@@ -324,7 +357,12 @@ __global__ void __launch_bounds__(256) vq_bwd_kernel(const float* __restrict__ z
     const int zi = lane + 32 * i;
     const float v = inv * (gq[i] - z[i] * dot);
     float* dst = d_zenc + row * 256 + zi;
-    *dst = accumulate ? *dst + v : v;
+    const float tot = accumulate ? *dst + v : v;
+    *dst = tot;
+    if (dz_out) {                    // z_enc is the producing layer's activated output: also form that layer's dz
+      const float y = pz[zi];
+      dz_out[row * lddz + zi] = tot * (act == VQN_ACT_RELU ? (y > 0.f ? 1.f : 0.f) : act == VQN_ACT_SIGMOID ? y * (1.f - y) : 1.f);
+    }
   }
 }
 
@@ -457,6 +495,13 @@ __global__ void copy_cols_batched_kernel(const __grid_constant__ CopyBatch b) {
   while (q + 1 < b.count && (int)blockIdx.x >= b.block_start[q + 1]) ++q;
   const CopyJob& j = b.j[q];
   const long long i = (long long)((int)blockIdx.x - b.block_start[q]) * blockDim.x + threadIdx.x;
+  if (j.pad_) {                       // 16-byte form: width, leading dimensions and both bases are multiples of 4 floats
+    const int w4 = j.w >> 2;
+    if (i >= j.m * w4) return;
+    const long long r = i / w4; const int c = (int)(i % w4) * 4;
+    *reinterpret_cast<float4*>(j.dst + r * j.ldd + c) = *reinterpret_cast<const float4*>(j.src + r * j.lds + c);
+    return;
+  }
   if (i >= j.m * j.w) return;
   const long long r = i / j.w; const int c = (int)(i % j.w);
   j.dst[r * j.ldd + c] = j.src[r * j.lds + c];
@@ -487,9 +532,46 @@ __global__ void cast_f64_f32_kernel(const double* __restrict__ s, float* __restr
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) d[i] = (float)s[i];
 }
+// the buffers a training step accumulates into (gradients, VQ statistics, d_z) cleared in ONE launch; sizes in 4-byte words
+#define ZERO_JOBS 8
+struct ZeroBatch { int count; uint32_t* p[ZERO_JOBS]; long long words[ZERO_JOBS]; };
+__global__ void zero_batched_kernel(const __grid_constant__ ZeroBatch b) {
+  for (int q = 0; q < b.count; ++q) {
+    uint32_t* p = b.p[q];
+    const long long n = b.words[q];
+    const long long stride = (long long)gridDim.x * blockDim.x, t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (((uintptr_t)p & 15) == 0) {
+      const long long n4 = n >> 2;
+      for (long long i = t; i < n4; i += stride) reinterpret_cast<uint4*>(p)[i] = make_uint4(0, 0, 0, 0);
+      for (long long i = (n4 << 2) + t; i < n; i += stride) p[i] = 0;
+    } else {
+      for (long long i = t; i < n; i += stride) p[i] = 0;
+    }
+  }
+}
+__global__ void pack_stats_kernel(const double* __restrict__ s, float* __restrict__ d, long long n,
+                                  float* __restrict__ rows_slot, float rows) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = (float)s[i];
+  if (i == 0 && rows_slot) rows_slot[0] += rows;
+}
 __global__ void cast_f32_f64_kernel(const float* __restrict__ s, double* __restrict__ d, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) d[i] = (double)s[i];
+}
+
+// the scalar tail of a training step (train_nfr.py:571, vq_nfr.py:971-986) in one thread instead of ~10 elementwise launches
+__global__ void train_scalars_kernel(const float* __restrict__ sums, const float* __restrict__ vq_loss,
+                                     const float* __restrict__ sim_loss, float inv_gbs, float vq_w, float sim_w,
+                                     float* __restrict__ out) {
+  if (blockIdx.x || threadIdx.x) return;
+  const float rows_scale = sums[6] * inv_gbs;
+  const float vq = vq_w * vq_loss[0];
+  const float sim = sim_loss ? sim_w * sim_loss[0] : 0.f;
+  out[0] = sums[5] * inv_gbs + rows_scale * (vq + sim);
+  out[1] = vq;
+  out[2] = sim;
+  out[3] = rows_scale;
 }
 
 }  // namespace
@@ -505,9 +587,10 @@ extern "C" int vqn_shade_backward(vqn_ctx* ctx, const float* xyz, const float* r
   if (n == 0) return VQN_OK;
   ShadeBwdParams a = {xyz, rayo, normal, lvis, row_idx, (long long)n, albedo, spec, rough, lxyz, lareas, light,
                       clip_light0, d_rgb, d_albedo, d_spec, d_rough, d_light};
-  long long want = (n + 7) / 8;
-  int blocks = (int)(want < (long long)ctx->sm_count ? want : (long long)ctx->sm_count);
-  shade_bwd_kernel<<<blocks, 256, 0, vqn_cs(stream)>>>(a);
+  // two warps per point, two CTAs (16 warps, 128 registers) per SM: 40 us per 8192 points; four warps per point at three
+  // CTAs per SM measured 58 us (the per-point set-up and reduction are repeated by every warp of a point), one warp 68-82 us
+  const long long want = (n + 3) / 4, cap = (long long)ctx->sm_count * 2;
+  shade_bwd_kernel<2, 2><<<(unsigned)(want < cap ? want : cap), SB_THREADS, 0, vqn_cs(stream)>>>(a);
   VQN_LAUNCHED(ctx);
   return VQN_OK;
 }
@@ -531,13 +614,52 @@ extern "C" int vqn_loss_train(vqn_ctx* ctx, const float* gtc, const float* rgb, 
   return VQN_OK;
 }
 
+extern "C" int vqn_vq_backward_act(vqn_ctx* ctx, const float* z_enc, const int64_t* indices, const float* codebook, int k,
+                                   const float* d_zvq, float commit_coef, int64_t n, int accumulate, float* d_zenc,
+                                   int act, float* dz_out, int64_t lddz, vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && z_enc && indices && codebook && d_zvq && d_zenc && k > 0 && n >= 0, "vq_backward args");
+  VQN_CHECK_ARG(!dz_out || lddz >= 256, "vq_backward_act: lddz");
+  if (n == 0) return VQN_OK;
+  vq_bwd_kernel<<<(unsigned)((n + 7) / 8), 256, 0, vqn_cs(stream)>>>(z_enc, (const long long*)indices, codebook, k,
+                                                                    d_zvq, commit_coef, (long long)n, accumulate, d_zenc,
+                                                                    act, dz_out, (long long)lddz);
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}
 extern "C" int vqn_vq_backward(vqn_ctx* ctx, const float* z_enc, const int64_t* indices, const float* codebook, int k,
                                const float* d_zvq, float commit_coef, int64_t n, int accumulate, float* d_zenc,
                                vqn_stream stream) {
-  VQN_CHECK_ARG(ctx && z_enc && indices && codebook && d_zvq && d_zenc && k > 0 && n >= 0, "vq_backward args");
-  if (n == 0) return VQN_OK;
-  vq_bwd_kernel<<<(unsigned)((n + 7) / 8), 256, 0, vqn_cs(stream)>>>(z_enc, (const long long*)indices, codebook, k,
-                                                                    d_zvq, commit_coef, (long long)n, accumulate, d_zenc);
+  return vqn_vq_backward_act(ctx, z_enc, indices, codebook, k, d_zvq, commit_coef, n, accumulate, d_zenc, VQN_ACT_NONE,
+                             nullptr, 0, stream);
+}
+
+/* memset(ptrs[i], 0, bytes[i]) for up to 8 device buffers (4-byte aligned, sizes multiples of 4) in ONE launch */
+extern "C" int vqn_zero_batched(vqn_ctx* ctx, void* const* ptrs, const int64_t* bytes, int count, vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && ptrs && bytes && count >= 0 && count <= ZERO_JOBS, "zero_batched: 0..8 buffers");
+  ZeroBatch b;
+  b.count = 0;
+  long long most = 0;
+  for (int i = 0; i < count; ++i) {
+    VQN_CHECK_ARG(bytes[i] >= 0 && bytes[i] % 4 == 0 && (bytes[i] == 0 || (ptrs[i] && (uintptr_t)ptrs[i] % 4 == 0)),
+                  "zero_batched: buffers must be 4-byte aligned with sizes in multiples of 4");
+    if (bytes[i] == 0) continue;
+    b.p[b.count] = (uint32_t*)ptrs[i]; b.words[b.count] = bytes[i] / 4; ++b.count;
+    most = most > bytes[i] / 16 ? most : bytes[i] / 16;
+  }
+  if (b.count == 0) return VQN_OK;
+  long long blocks = (most + 255) / 256;
+  blocks = blocks < 1 ? 1 : blocks > 4 * (long long)ctx->sm_count ? 4 * (long long)ctx->sm_count : blocks;
+  zero_batched_kernel<<<(unsigned)blocks, 256, 0, vqn_cs(stream)>>>(b);
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}
+
+/* stats32 = (float) stats64 for the gradient all-reduce buffer, and rows_slot[0] += rows (this rank's active rows) */
+extern "C" int vqn_train_pack_stats(vqn_ctx* ctx, const double* stats64, float* stats32, int64_t count, float* rows_slot,
+                                    float rows, vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && stats64 && stats32 && count > 0, "train_pack_stats args");
+  pack_stats_kernel<<<(unsigned)((count + 255) / 256), 256, 0, vqn_cs(stream)>>>(stats64, stats32, (long long)count,
+                                                                                rows_slot, rows);
   VQN_LAUNCHED(ctx);
   return VQN_OK;
 }
@@ -614,9 +736,11 @@ extern "C" int vqn_copy_cols_batched(vqn_ctx* ctx, const vqn_copy_job* jobs, int
     const vqn_copy_job& c = jobs[q];
     VQN_CHECK_ARG(c.src && c.dst && c.m >= 0 && c.w > 0 && c.lds >= c.w && c.ldd >= c.w, "copy_cols_batched: bad job");
     if (c.m == 0) continue;
-    b.j[b.count] = {c.src, c.dst, (long long)c.lds, (long long)c.ldd, (long long)c.m, c.w, 0};
+    const int vec = (c.w % 4 == 0 && c.lds % 4 == 0 && c.ldd % 4 == 0 &&
+                     ((uintptr_t)c.src | (uintptr_t)c.dst) % 16 == 0) ? 1 : 0;
+    b.j[b.count] = {c.src, c.dst, (long long)c.lds, (long long)c.ldd, (long long)c.m, c.w, vec};
     b.block_start[b.count] = blocks;
-    blocks += (int)(((long long)c.m * c.w + 255) / 256);
+    blocks += (int)(((long long)c.m * (vec ? c.w / 4 : c.w) + 255) / 256);
     ++b.count;
   }
   if (b.count == 0) return VQN_OK;
@@ -630,6 +754,15 @@ extern "C" int vqn_cast_f64_f32(vqn_ctx* ctx, const double* src, float* dst, int
   VQN_CHECK_ARG(ctx && src && dst && count >= 0, "cast args");
   if (count == 0) return VQN_OK;
   cast_f64_f32_kernel<<<(unsigned)((count + 255) / 256), 256, 0, vqn_cs(stream)>>>(src, dst, (long long)count);
+  VQN_LAUNCHED(ctx);
+  return VQN_OK;
+}
+/* out[4] = { weighted loss, vq_w * vq_loss, sim_w * sim_loss, rows / global_bs } from the reduced sums
+ * (sums[5] = total of the per-example terms, sums[6] = active rows); sim_loss may be NULL (weight 0). */
+extern "C" int vqn_train_scalars(vqn_ctx* ctx, const float* sums, const float* vq_loss, const float* sim_loss,
+                                 float inv_gbs, float vq_w, float sim_w, float* out, vqn_stream stream) {
+  VQN_CHECK_ARG(ctx && sums && vq_loss && out, "train_scalars: null pointer");
+  train_scalars_kernel<<<1, 32, 0, vqn_cs(stream)>>>(sums, vq_loss, sim_loss, inv_gbs, vq_w, sim_w, out);
   VQN_LAUNCHED(ctx);
   return VQN_OK;
 }

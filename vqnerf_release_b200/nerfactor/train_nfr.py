@@ -170,18 +170,26 @@ class _NetTrain:
                                             self.n, self.in_dim, w))
         return out
 
-    def act_backward_last(self, dy: torch.Tensor, lddy: int) -> None:
+    def act_job(self, dy: torch.Tensor, lddy: int) -> tuple:
+        """The arguments of abi.act_backward for the last layer (dz[last] = dy * act'(y[last]) * albedo_slope)."""
         last = len(self.widths) - 1
-        abi.act_backward(dy, lddy, self.y[last], self.ld[last], self.n, self.widths[last], self.acts[last],
-                         self.out_scale, self.out_scale, self.out_bias, self.dz[last], self.dz[last].shape[1])
+        return (dy, lddy, self.y[last], self.ld[last], self.n, self.widths[last], self.acts[last],
+                self.out_scale, self.out_scale, self.out_bias, self.dz[last], self.dz[last].shape[1])
 
-    def backward_fused(self, dy: torch.Tensor, lddy: int, d_input: Optional[torch.Tensor], ld_din: int, din_mode: int) -> None:
+    def act_backward_last(self, dy: torch.Tensor, lddy: int) -> None:
+        abi.act_backward(*self.act_job(dy, lddy))
+
+    def backward_fused(self, dy: torch.Tensor, lddy: int, d_input: Optional[torch.Tensor], ld_din: int, din_mode: int,
+                       act_done: bool = False, din_y: Optional[torch.Tensor] = None, ld_din_y: int = 0,
+                       din_act: int = 0) -> None:
         """The backward-DATA chain of the network as ONE launch of the fused tcgen05 kernel (vqn_net_backward_train): fills
-        every dz[i]; the caller batches the weight-gradient GEMMs (weight_problems)."""
+        every dz[i]; the caller batches the weight-gradient GEMMs (weight_problems).  act_done: dz[last] was already formed
+        (the heads' last-layer activation gradients share one launch)."""
         last = len(self.widths) - 1
-        self.act_backward_last(dy, lddy)
+        if not act_done:
+            self.act_backward_last(dy, lddy)
         self.net.packed.backward_train(self.dz[last], self.dz[last].shape[1], self.n, self.y, self.ld, self.dz,
-                                       [t.shape[1] for t in self.dz], d_input, ld_din, din_mode)
+                                       [t.shape[1] for t in self.dz], d_input, ld_din, din_mode, din_y, ld_din_y, din_act)
 
     def backward(self, dy: torch.Tensor, lddy: int, dW: List[torch.Tensor], dB: List[torch.Tensor],
                  d_input: Optional[torch.Tensor] = None, ld_din: int = 0, weight_list: Optional[list] = None) -> None:
@@ -268,6 +276,7 @@ class TrainState:
             self.d_gamma = next(git)
             model._gamma_bias, model._gamma_index = self.gamma_par[0:1], self.gamma_par[1:2]
         self.sim_loss = torch.zeros((1,), dtype=F32, device=dev)
+        self.scalars = torch.zeros((4,), dtype=F32, device=dev)
         self.acts: Dict[int, dict] = {}
         self.dirty = False
         self.side_streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]   # forked head forwards
@@ -332,9 +341,12 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
     lw = {k: (cfg.getfloat(k, fallback=v) if hasattr(cfg, 'getfloat') else v) for k, v in LOSS_DEFAULTS.items()}
     id_, hw, rayo, rayd, rgb, alpha, pred_alpha, xyz, normal, lvis = m._unpack(batch, False)
     n_total = alpha.shape[0]
-    row_idx, n_act = abi.compact_mask(alpha)
     full = getattr(m, 'assume_all_foreground', False)
-    n = n_total if full else int(n_act.item())
+    if full:
+        n = n_total
+    else:
+        row_idx, n_act = abi.compact_mask(alpha)
+        n = int(n_act.item())
     if n != n_total:                     # the sampler only draws foreground pixels (train_nfr.py:380-467); rare path
         idx = row_idx[:n].long()
         rayo, rgb, xyz, normal = (t.index_select(0, idx) for t in (rayo, rgb, xyz, normal))
@@ -346,8 +358,9 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
     z = m.z_dim
     K = m.num_embed
     inv_gbs = 1.0 / float(global_bs)
-    st.gflat.zero_()
-    st.stats64.zero_()
+    fused_bwd = FUSED_FORWARD and BATCHED_BACKWARD and FUSED_BACKWARD
+    # everything the step accumulates into, cleared in one launch (d_h is stored, not accumulated, by the fused backward)
+    abi.zero_batched([st.gflat, st.stats64, B['d_zenc']] + ([] if fused_bwd else [B['d_h']]), m.device)
 
     # ---- forward ------------------------------------------------------------------------------------------
     emb = m.embedder['xyz']
@@ -406,11 +419,17 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
         base = nets['diff_main'].forward(z_enc, z, prepared=prep)
         ks = nets['spec_main'].forward(z_enc, z, prepared=prep)
         rough = nets['rough_main'].forward(z_enc, z, prepared=prep)
+    all_heads_done = prep and CONCURRENT_HEADS
     if prep:
         base_c, ks_c, rough_c = B['base_c'], B['ks_c'], B['rough_c']
-        abi.copy_cols_batched([(base, nets['diff_main'].ld[-1], base_c, 3, n, 3, 0),
-                               (ks, nets['spec_main'].ld[-1], ks_c, 1, n, 1, 0),
-                               (rough, nets['rough_main'].ld[-1], rough_c, 1, n, 1, 0)], m.device)
+        jobs = [(base, nets['diff_main'].ld[-1], base_c, 3, n, 3, 0), (ks, nets['spec_main'].ld[-1], ks_c, 1, n, 1, 0),
+                (rough, nets['rough_main'].ld[-1], rough_c, 1, n, 1, 0)]
+        if all_heads_done:               # the VQ branch's outputs exist already: compact all six in this launch
+            va, vs, vr = outs['diff_vq'], outs['spec_vq'], outs['rough_vq']
+            va_c, vs_c, vr_c = B['vq_albedo_c'], B['vq_spec_c'], B['vq_rough_c']
+            jobs += [(va, nets['diff_vq'].ld[-1], va_c, 3, n, 3, 0), (vs, nets['spec_vq'].ld[-1], vs_c, 3, n, 3, 0),
+                     (vr, nets['rough_vq'].ld[-1], vr_c, 1, n, 1, 0)]
+        abi.copy_cols_batched(jobs, m.device)
     else:
         base_c = _compact_col(base, nets['diff_main'].ld[-1], 3, B['base_c'])
         ks_c = _compact_col(ks, nets['spec_main'].ld[-1], 1, B['ks_c'])
@@ -424,13 +443,13 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
                    no_clip=not is_nerf)
     rgb_lin = sh['rgb'].reshape(n, 3)
     rgb_pred = rgb_lin if is_nerf else abi.gamma_forward(rgb_lin, st.gamma_par, B['rgb_g'])
-    if prep and CONCURRENT_HEADS:
-        va, vs, vr = outs['diff_vq'], outs['spec_vq'], outs['rough_vq']
-    else:
+    if not all_heads_done:
         va = nets['diff_vq'].forward(z_vq, z, prepared=prep)
         vs = nets['spec_vq'].forward(z_vq, z, prepared=prep)
         vr = nets['rough_vq'].forward(z_vq, z, prepared=prep)
-    if prep:
+    if all_heads_done:
+        pass
+    elif prep:
         va_c, vs_c, vr_c = B['vq_albedo_c'], B['vq_spec_c'], B['vq_rough_c']
         abi.copy_cols_batched([(va, nets['diff_vq'].ld[-1], va_c, 3, n, 3, 0),
                                (vs, nets['spec_vq'].ld[-1], vs_c, 3, n, 3, 0),
@@ -459,7 +478,6 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
                        B['d_albedo'], B['d_spec'], B['d_rough'], st.d_light)
     abi.material_combine_backward(base_c, ks_c, B['d_albedo'], B['d_spec'], B['d_spec_l'], B['d_base'], B['d_ks'])
     d_zenc = B['d_zenc']
-    d_zenc.zero_()
     # VQ branch (d_zvq already holds the pair-smoothness gradient)
     abi.shade_backward(xyz, rayo, normal, lvis, va_c, vs_c, vr_c, m.lxyz, m.lareas, m._light, d_vqrgb,
                        B['d_vq_albedo'], B['d_vq_spec'], B['d_vq_rough'], st.d_light)
@@ -472,6 +490,7 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
         # every head's backward-data chain is ONE launch of the fused tcgen05 kernel (transposed weight images, dz_i stored for
         # the weight gradients, the narrow last layer backwards on the CUDA cores); the six launches are forked over three
         # streams like the forwards; the three heads of a branch add into the same d_z atomically
+        abi.act_backward_batched([nets[name].act_job(dy, lddy) for name, dy, lddy, _ in heads], m.device)
         cur = torch.cuda.current_stream(m.device)
         ev = torch.cuda.Event()
         ev.record(cur)
@@ -482,7 +501,7 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
                 side.wait_event(ev)
             with torch.cuda.stream(side):
                 for name, dy, lddy, dzin in grp_:
-                    nets[name].backward_fused(dy, lddy, dzin, z, 2)
+                    nets[name].backward_fused(dy, lddy, dzin, z, 2, act_done=True)
             if si > 0:
                 done = torch.cuda.Event()
                 done.record(side)
@@ -521,26 +540,31 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
         for name, dy, lddy, dzin in heads:
             nets[name].backward(dy, lddy, st.dW[name], st.dB[name], dzin, z)
     commit_coef = lw['vq_loss_weight'] * m.vq_layer.commitment_cost * 2.0 * inv_gbs / z
-    abi.vq_backward(z_enc, idx, codebook, d_zvq, commit_coef, d_zenc, accumulate=True)
-    d_h = B['d_h']
-    d_h.zero_()
-    wl = wlist if BATCHED_BACKWARD else None
-    if BATCHED_BACKWARD and FUSED_BACKWARD and prep:
-        nets['bottleneck'].backward_fused(d_zenc, z, d_h, d_h.shape[1], 0)          # d_h is stored (no zero fill needed)
-        nets['fine_enc'].backward_fused(d_h, d_h.shape[1], None, 0, 0)
-        wlist += nets['bottleneck'].weight_problems(st.dW['bottleneck'], st.dB['bottleneck'])
-        wlist += nets['fine_enc'].weight_problems(st.dW['fine_enc'], st.dB['fine_enc'])
+    bn, fe = nets['bottleneck'], nets['fine_enc']
+    if fused_bwd:
+        # ... and, z_enc being the bottleneck's activated output, the dz of its last layer in the same pass
+        abi.vq_backward(z_enc, idx, codebook, d_zvq, commit_coef, d_zenc, accumulate=True, act=bn.acts[-1], dz_out=bn.dz[-1])
     else:
-        nets['bottleneck'].backward(d_zenc, z, st.dW['bottleneck'], st.dB['bottleneck'], d_h, d_h.shape[1], weight_list=wl)
-        nets['fine_enc'].backward(d_h, d_h.shape[1], st.dW['fine_enc'], st.dB['fine_enc'], weight_list=wl)
+        abi.vq_backward(z_enc, idx, codebook, d_zvq, commit_coef, d_zenc, accumulate=True)
+    d_h = B['d_h']
+    wl = wlist if BATCHED_BACKWARD else None
+    if fused_bwd:
+        # the bottleneck's chain ends in fine_enc's last dz (its input IS fine_enc's activated output): no d_h round trip
+        bn.backward_fused(d_zenc, z, fe.dz[-1], fe.dz[-1].shape[1], 0, act_done=True, din_y=fe.y[-1], ld_din_y=fe.ld[-1],
+                          din_act=fe.acts[-1])
+        fe.backward_fused(None, 0, None, 0, 0, act_done=True)
+        wlist += bn.weight_problems(st.dW['bottleneck'], st.dB['bottleneck'])
+        wlist += fe.weight_problems(st.dW['fine_enc'], st.dB['fine_enc'])
+    else:
+        bn.backward(d_zenc, z, st.dW['bottleneck'], st.dB['bottleneck'], d_h, d_h.shape[1], weight_list=wl)
+        fe.backward(d_h, d_h.shape[1], st.dW['fine_enc'], st.dB['fine_enc'], weight_list=wl)
     if wlist:
         abi.dense_backward_weights_batched(wlist, m.device)
     if heads_w_done is not None:
         torch.cuda.current_stream(m.device).wait_event(heads_w_done)
 
     # ---- the single collective: [gradients | VQ statistics | loss sums] --------------------------------------
-    abi.cast_f64_f32(st.stats64, st.stats32)
-    st.sums[6:7] += float(n)
+    abi.train_pack_stats(st.stats64, st.stats32, st.sums[6:7], float(n))
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(st.gflat, op=dist.ReduceOp.SUM, group=group)
     abi.cast_f32_f64(st.stats32, st.stats64)
@@ -550,18 +574,20 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
     update, vq_loss, _ = abi.vq_ema_update(st.stats64, codebook, vq.decay, vq.epsilon, vq.commitment_cost, True,
                                            vq.state)
     m._codebook.copy_(update)
-    rows_scale = st.sums[6] * inv_gbs             # (global active rows) / global_bs: weight of broadcast scalars
     sim_w = lw['sim_loss_weight']
     if sim_w > 0:
         # gradient scale = sim_w * rows / gbs (scalar broadcast to every row, vq_nfr.py:971-972); rows == known
         n_glob = n * (dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1) \
             if full else None
-        scale = sim_w * (float(n_glob) * inv_gbs if n_glob is not None else float(rows_scale.item()))
+        scale = sim_w * (float(n_glob) * inv_gbs if n_glob is not None else float((st.sums[6] * inv_gbs).item()))
         abi.codebook_sim_loss(m._codebook, scale, st.sim_loss, st.d_codebook, accumulate=False)
-    weighted = st.sums[5] * inv_gbs + rows_scale * (lw['vq_loss_weight'] * vq_loss[0] + sim_w * st.sim_loss[0])
+    # weighted = sums[5]/gbs + (rows/gbs) * (vq_w * vq_loss + sim_w * sim_loss): the two broadcast scalars weigh by the share
+    # of active rows; one launch for the scalar arithmetic
+    sc = abi.train_scalars(st.sums, vq_loss, st.sim_loss if sim_w > 0 else None, inv_gbs, lw['vq_loss_weight'], sim_w,
+                           st.scalars)
+    weighted = sc[0]
     loss_dict = {'rgb': st.sums[0], 'vqrgb': st.sums[1], 'chromaticity': st.sums[2], 'chr_smooth': st.sums[3],
-                 'lambert': st.sums[4], 'vqloss': lw['vq_loss_weight'] * vq_loss[0],
-                 'sim_smooth': sim_w * st.sim_loss[0], 'rows': st.sums[6]}
+                 'lambert': st.sums[4], 'vqloss': sc[1], 'sim_smooth': sc[2], 'rows': st.sums[6]}
     if apply:
         optimizer.apply_gradients(st.params, st.grads, lr_t_dev=_lr_t_dev)
         st.dirty = True
