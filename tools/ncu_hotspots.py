@@ -1,7 +1,7 @@
 """Stall-reason totals, instruction mix and the most-stalled SASS lines of one kernel from an .ncu-rep that was captured with
 `--set full --import-source on` (ncu -i ... --page source --csv).
 
-    python tools/ncu_hotspots.py gpurun_out/prof.ncu-rep [units_per_launch]      # e.g. 5000 tiles -> per-tile counts
+    python tools/ncu_hotspots.py gpurun_out/prof.ncu-rep [units_per_launch] [launch_index]   # e.g. 5000 tiles -> per-tile counts
 """
 import collections
 import csv
@@ -13,10 +13,12 @@ import sys
 def main():
     rep = sys.argv[1]
     units = float(sys.argv[2]) if len(sys.argv) > 2 else None
-    out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+    sel = ['--launch-skip', sys.argv[3], '--launch-count', '1'] if len(sys.argv) > 3 else []
+    out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'] + sel, capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     print('kernel:', rows[0][1])
-    hdr, data = rows[1], rows[2:]
+    hdr = rows[1]
+    data = [r for r in rows[2:] if len(r) >= len(hdr) - 1 and r[0].startswith('0x')]
     ix = {h: i for i, h in enumerate(hdr)}
     samples = sum(int(r[ix['# Samples']]) for r in data)
     instr = sum(int(r[ix['Instructions Executed']]) for r in data)
