@@ -18,7 +18,11 @@ def main():
     rows = list(csv.reader(out.splitlines()))
     print('kernel:', rows[0][1])
     hdr = rows[1]
-    data = [r for r in rows[2:] if len(r) >= len(hdr) - 1 and r[0].startswith('0x')]
+    seen, data = set(), []
+    for r in rows[2:]:            # (a report with both SASS and source views lists every address twice)
+        if len(r) >= len(hdr) - 1 and r[0].startswith('0x') and r[0] not in seen:
+            seen.add(r[0])
+            data.append(r)
     ix = {h: i for i, h in enumerate(hdr)}
     samples = sum(int(r[ix['# Samples']]) for r in data)
     instr = sum(int(r[ix['Instructions Executed']]) for r in data)
