@@ -335,3 +335,130 @@ def test_training_abi_edge_cases(cuda_dev):
     loss, vis, _ = T.train_iter(m, _batch_tuple(batch, cuda_dev), T.Adam(), 64, apply=False)
     _close(loss, ref['loss'], 'loss with background rows', rtol=1e-4, atol=1e-7)
     _tensor_close(m._train_state.dW['fine_enc'][0], ref['grads']['fine_enc'][0][0], 'd fine_enc.kernel[0] (masked batch)')
+
+
+def _ref_chain(x, Ws, bs, acts, skip, dy, out_scale=1.0):
+    """float64 autograd restatement of mlp.Network (mlp.py:39-50): outputs y_i, dz_i = d/d(pre-activation_i), d/dx."""
+    x = x.double().requires_grad_(True)
+    pres, ys = [], []
+    cur = x
+    for i, (W, b, a) in enumerate(zip(Ws, bs, acts)):
+        pre = cur @ W.double() + b.double()
+        pre.retain_grad()
+        y = torch.relu(pre) if a == 'relu' else torch.sigmoid(pre) if a == 'sigmoid' else pre
+        if i == len(Ws) - 1:
+            y = y * out_scale
+        pres.append(pre)
+        ys.append(y)
+        cur = torch.cat([y, x], 1) if skip == i else y
+    (ys[-1] * dy.double()).sum().backward()
+    return [y.detach() for y in ys], [p.grad for p in pres], x.grad
+
+
+@pytest.mark.parametrize('shape', ['bottleneck', 'fine_enc', 'head3', 'head1'])
+@pytest.mark.parametrize('n', [200, 1000])
+def test_fused_forward_backward_chain_vs_float64(cuda_dev, shape, n):
+    """vqn_net_forward_train + vqn_net_backward_train (one launch each) against float64 autograd: the saved activations,
+    every dz_i and the input gradient, for the three network shapes of the training step (nfr_unit.py:115-122)."""
+    from vqnerf_release_b200 import abi
+    from vqnerf_release_b200 import _lib as L
+    g = torch.Generator(device='cpu').manual_seed(11 + n)
+    if shape == 'bottleneck':
+        in_dim, widths, acts, skip = 128, [128, 256, 256], [None, 'relu', 'sigmoid'], None
+    elif shape == 'fine_enc':
+        in_dim, widths, acts, skip = 64, [128, 128, 128, 128], ['relu'] * 4, 2
+    else:
+        in_dim, widths, acts, skip = 256, [256, 128, 3 if shape == 'head3' else 1], ['relu', 'relu', 'sigmoid'], 1
+    Ws, bs, d = [], [], in_dim
+    for i, w in enumerate(widths):
+        Ws.append(torch.randn((d, w), generator=g) * (1.5 / np.sqrt(d)))
+        bs.append(torch.randn((w,), generator=g) * 0.1)
+        d = w + (in_dim if skip == i else 0)
+    x = torch.randn((n, in_dim), generator=g)
+    dy = torch.randn((n, widths[-1]), generator=g)
+    ys_ref, dz_ref, dx_ref = _ref_chain(x, Ws, bs, acts, skip, dy)
+    Wd, bd = [w.to(cuda_dev) for w in Ws], [b.to(cuda_dev) for b in bs]
+    net = abi.PackedNet(Wd, bd, acts, skip_at=skip)
+    pad4 = lambda v: (v + 3) // 4 * 4
+    ld = [pad4(w + (in_dim if skip == i else 0)) for i, w in enumerate(widths)]
+    y = [torch.zeros((n, l), device=cuda_dev) for l in ld]
+    dz = [torch.full((n, pad4(w)), 7.0, device=cuda_dev) for w in widths]
+    xd = x.to(cuda_dev)
+    net.repack_tc('tf32x3')
+    net.forward_train(xd, in_dim, n, y, ld)
+    if skip is not None:
+        abi.copy_cols(xd, in_dim, y[skip], ld[skip], n, in_dim, dst_off=widths[skip])
+    for i, w in enumerate(widths):
+        _tensor_close(y[i][:, :w], ys_ref[i], '%s y[%d]' % (shape, i), rel=2e-5)
+    # last-layer activation gradient, then the chain
+    abi.act_backward_batched([(dy.to(cuda_dev), widths[-1], y[-1], ld[-1], n, widths[-1], L.act_code(acts[-1]), 1.0, 1.0, 0.0,
+                               dz[-1], dz[-1].shape[1])], cuda_dev)
+    _tensor_close(dz[-1][:, :widths[-1]], dz_ref[-1], '%s dz[last]' % shape, rel=2e-5)
+    lddz = [t.shape[1] for t in dz]
+    if shape == 'fine_enc':                      # x half of the skip needs no gradient: the chain ends in dz[0]
+        net.backward_train(dz[-1], lddz[-1], n, y, ld, dz, lddz)
+    elif shape == 'bottleneck':
+        # (a) plain input gradient, stored; (b) input = relu output of a producer: d_input * act'(din_y)
+        d_in = torch.full((n, in_dim), 3.0, device=cuda_dev)
+        net.backward_train(dz[-1], lddz[-1], n, y, ld, dz, lddz, d_in, in_dim, 0)
+        _tensor_close(d_in, dx_ref, 'bottleneck d_input', rel=5e-5)
+        prod = torch.randn((n, in_dim), generator=g).to(cuda_dev)
+        net.backward_train(dz[-1], lddz[-1], n, y, ld, dz, lddz, d_in, in_dim, 0, din_y=prod, ld_din_y=in_dim,
+                           din_act=L.act_code('relu'))
+        _tensor_close(d_in, dx_ref * (prod.cpu().double() > 0), 'bottleneck d_input * relu\'(din_y)', rel=5e-5)
+    else:
+        # heads ADD into a shared d_z (atomic mode): start from a known value
+        d_in = torch.full((n, in_dim), 0.25, device=cuda_dev)
+        net.backward_train(dz[-1], lddz[-1], n, y, ld, dz, lddz, d_in, in_dim, 2)
+        _tensor_close(d_in - 0.25, dx_ref, '%s d_input (atomic add)' % shape, rel=5e-5)
+    first = 1 if shape == 'fine_enc' else 0
+    for i in range(len(widths) - 1):
+        if i >= first or shape == 'fine_enc':
+            _tensor_close(dz[i][:, :widths[i]], dz_ref[i], '%s dz[%d]' % (shape, i), rel=5e-5)
+
+
+def test_training_small_kernels(cuda_dev):
+    """vqn_zero_batched, vqn_train_pack_stats, vqn_train_scalars, vqn_vq_backward_act, 16-byte vqn_copy_cols_batched."""
+    from vqnerf_release_b200 import abi
+    from vqnerf_release_b200 import _lib as L
+    g = torch.Generator(device='cpu').manual_seed(3)
+    # zero fill: aligned / unaligned bases, sizes that are not multiples of 16 bytes, a float64 buffer
+    base = torch.ones((4099,), device=cuda_dev)
+    bufs = [base[:1000], base[1001:2006], base[2048:4099], torch.ones((7,), dtype=torch.float64, device=cuda_dev)]
+    abi.zero_batched(bufs, cuda_dev)
+    assert float(base[:1000].abs().sum()) == 0 and float(base[1001:2006].abs().sum()) == 0
+    assert float(base[2048:].abs().sum()) == 0 and float(bufs[3].abs().sum()) == 0
+    assert float(base[1000]) == 1.0 and float(base[2006:2048].sum()) == 42.0      # neighbours untouched
+    # statistics pack
+    s64 = torch.randn((333,), generator=g, dtype=torch.float64).to(cuda_dev) * 1e3
+    s32 = torch.zeros((333,), device=cuda_dev)
+    rows = torch.full((1,), 5.0, device=cuda_dev)
+    abi.train_pack_stats(s64, s32, rows, 8192.0)
+    assert torch.equal(s32, s64.float()) and float(rows) == 8197.0
+    # loss scalars
+    sums = torch.tensor([1., 2., 3., 4., 5., 15.5, 4096., 0.], device=cuda_dev)
+    vq, sim, out = torch.tensor([0.3], device=cuda_dev), torch.tensor([-2.5], device=cuda_dev), torch.zeros(4, device=cuda_dev)
+    abi.train_scalars(sums, vq, sim, 1.0 / 2048, 1.0, 1e-4, out)
+    r = 4096.0 / 2048
+    np.testing.assert_allclose(out.cpu().numpy(), [15.5 / 2048 + r * (0.3 + 1e-4 * -2.5), 0.3, 1e-4 * -2.5, r], rtol=1e-6)
+    abi.train_scalars(sums, vq, None, 1.0 / 2048, 2.0, 0.0, out)
+    np.testing.assert_allclose(out.cpu().numpy(), [15.5 / 2048 + r * 0.6, 0.6, 0.0, r], rtol=1e-6)
+    # VQ backward with the producing layer's activation gradient folded in
+    n, K = 300, 15
+    z = torch.rand((n, 256), generator=g).to(cuda_dev)
+    cb = torch.rand((256, K), generator=g).to(cuda_dev)
+    idx = torch.randint(0, K, (n,), generator=g).to(cuda_dev)
+    dq = torch.randn((n, 256), generator=g).to(cuda_dev)
+    d0 = torch.randn((n, 256), generator=g).to(cuda_dev)
+    da, db = d0.clone(), d0.clone()
+    dz = torch.zeros((n, 260), device=cuda_dev)
+    abi.vq_backward(z, idx, cb, dq, 0.01, da, accumulate=True)
+    abi.vq_backward(z, idx, cb, dq, 0.01, db, accumulate=True, act=L.act_code('sigmoid'), dz_out=dz)
+    assert torch.equal(da, db)
+    assert torch.allclose(dz[:, :256], da * z * (1 - z), rtol=1e-6, atol=1e-9) and float(dz[:, 256:].abs().sum()) == 0
+    # batched column copies: the 16-byte form and the scalar form in the same launch
+    src = torch.randn((500, 264), generator=g).to(cuda_dev)
+    d1, d2 = torch.zeros((500, 520), device=cuda_dev), torch.zeros((500, 7), device=cuda_dev)
+    abi.copy_cols_batched([(src, 264, d1, 520, 500, 256, 256), (src, 264, d2, 7, 500, 3, 2)], cuda_dev)
+    assert torch.equal(d1[:, 256:512], src[:, :256]) and float(d1[:, :256].abs().sum()) == 0
+    assert torch.equal(d2[:, 2:5], src[:, :3]) and float(d2[:, :2].abs().sum()) == 0
