@@ -199,7 +199,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 // try_wait / branch / counter instructions (ncu source page, profiles/r2c_*), slots the working warps were waiting for.
 // (20 us: with the spin bound of 2^24 below a barrier that never completes -- a protocol bug -- traps after at most ~5 min
 // instead of hanging the GPU for days; a clock-based bound in the wait loops cost mlp_tc 2 %)
+#ifndef TC_MBAR_SUSPEND_NS
 #define TC_MBAR_SUSPEND_NS 20000
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
