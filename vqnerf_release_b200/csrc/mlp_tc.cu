@@ -799,9 +799,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                     const TcLayer& pl = pg.layers[l - 1];
                     float* sv = pl.save + (size_t)pi * pl.save_ld + col0;
                     if (col0 + 16 <= pl.N) {
-#pragma unroll
-                      for (int q = 0; q < 4; ++q)
-                        reinterpret_cast<float4*>(sv)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                      tc::stg_row16(sv, v);
                     } else {
 #pragma unroll
                       for (int j = 0; j < 16; ++j) if (col0 + j < pl.N) sv[j] = v[j];
@@ -826,11 +824,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                     const float* yr = ly.bw_y + (size_t)pi * ly.bw_y_ld + col0;
                     float* dr = ly.bw_dz + (size_t)pi * ly.bw_dz_ld + col0;
                     if (col0 + 16 <= ly.bw_n) {
-#pragma unroll
-                      for (int q = 0; q < 4; ++q) {
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(yr) + q);
-                        y[4 * q] = t.x; y[4 * q + 1] = t.y; y[4 * q + 2] = t.z; y[4 * q + 3] = t.w;
-                      }
+                      tc::ldg_row16(yr, y);
                     } else {
 #pragma unroll
                       for (int j = 0; j < 16; ++j) y[j] = col0 + j < ly.bw_n ? __ldg(yr + j) : 0.f;
@@ -842,9 +836,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                       v[j] = col0 + j < ly.bw_n ? v[j] * dact : 0.f;
                     }
                     if (col0 + 16 <= ly.bw_n) {
-#pragma unroll
-                      for (int q = 0; q < 4; ++q)
-                        reinterpret_cast<float4*>(dr)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                      tc::stg_row16(dr, v);
                     } else {
 #pragma unroll
                       for (int j = 0; j < 16; ++j) if (col0 + j < ly.bw_n) dr[j] = v[j];
@@ -879,12 +871,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                       v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
                     }
                   } else if (valid && col0 < pg.g_dim) {
-                    const float4* src = reinterpret_cast<const float4*>(pg.gsrc + (size_t)pi * pg.g_dim + col0);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                      float4 t = src[j];
-                      v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
-                    }
+                    tc::ldg_row16(pg.gsrc + (size_t)pi * pg.g_dim + col0, v);
                   } else {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = 0.f;
@@ -966,10 +953,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                                                           ((size_t)(ly.stash_w * 16 + (c16 >> 4)) * TC_M + r) * 8);
               else bias_act32_dyn(v, lb + c16, ly.act);
               if (trn && ly.save && valid) {
-                float* sv = ly.save + (size_t)pi * ly.save_ld + c16;
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                  reinterpret_cast<float4*>(sv)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                tc::stg_row16(ly.save + (size_t)pi * ly.save_ld + c16, v);
               }
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
@@ -1074,11 +1058,7 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                   const float* yr = ly.fin_y + (size_t)pi * ly.fin_y_ld + c16;
                   float y[16];
                   if (whole && (ly.fin_y_ld & 3) == 0) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                      const float4 t = __ldg(reinterpret_cast<const float4*>(yr) + q);
-                      y[4 * q] = t.x; y[4 * q + 1] = t.y; y[4 * q + 2] = t.z; y[4 * q + 3] = t.w;
-                    }
+                    tc::ldg_row16(yr, y);
                   } else {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) y[j] = c16 + j < ly.N ? __ldg(yr + j) : 0.f;
@@ -1092,7 +1072,9 @@ __global__ void __launch_bounds__(TcCfg<BF16>::THREADS, 1) mlp_tc_kernel(const _
                 bool bad = false;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) if (c16 + j < ly.N) bad |= !isfinite(v[j]);
-                if (whole && (gs & 3) == 0 && (reinterpret_cast<uintptr_t>(go) & 15) == 0) {
+                if (whole && (gs & 3) == 0 && (reinterpret_cast<uintptr_t>(go) & 15) == 0 && ly.fin_mode == 0) {
+                  tc::stg_row16(dst, v);
+                } else if (whole && (gs & 3) == 0 && (reinterpret_cast<uintptr_t>(go) & 15) == 0) {
 #pragma unroll
                   for (int q = 0; q < 4; ++q) {
                     float4* d4 = reinterpret_cast<float4*>(dst) + q;

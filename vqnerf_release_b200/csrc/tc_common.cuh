@@ -239,6 +239,39 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// 16 consecutive floats of ONE row per thread (a thread owns a row of the tile, so a warp-level access touches 32
+// different sectors whatever its width): as two 32-byte accesses (LDG/STG.256, sm_100) when the address allows, else four
+// 16-byte ones -- half / a quarter of the L1 wavefronts of narrower accesses.  p must be 16-byte aligned.
+__device__ __forceinline__ void ldg_row16(const float* p, float (&v)[16]) {
+  if ((reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=f"(v[8 * q]), "=f"(v[8 * q + 1]), "=f"(v[8 * q + 2]), "=f"(v[8 * q + 3]), "=f"(v[8 * q + 4]),
+                     "=f"(v[8 * q + 5]), "=f"(v[8 * q + 6]), "=f"(v[8 * q + 7])
+                   : "l"(p + 8 * q));
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p) + q);
+      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+  }
+}
+__device__ __forceinline__ void stg_row16(float* p, const float (&v)[16]) {
+  if ((reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p + 8 * q), "f"(v[8 * q]), "f"(v[8 * q + 1]),
+                   "f"(v[8 * q + 2]), "f"(v[8 * q + 3]), "f"(v[8 * q + 4]), "f"(v[8 * q + 5]), "f"(v[8 * q + 6]), "f"(v[8 * q + 7])
+                   : "memory");
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      reinterpret_cast<float4*>(p)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+}
+
 // Explicit shared-memory accesses by 32-bit shared address.  The operand rings are reached through a pointer that was
 // aligned by integer arithmetic, so the compiler no longer knows its address space and emits GENERIC stores (ST.E with
 // 64-bit addresses and the generic-window check) for every A-chunk store; these keep the hot producer loops on STS / LDS.
