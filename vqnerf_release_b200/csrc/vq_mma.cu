@@ -367,6 +367,13 @@ __global__ void __launch_bounds__(VqmCfg<NT>::WARPS * 32, VqmCfg<NT>::BLOCKS) vq
     }
     // second pass (training / quantize consumers): row-wise re-read (L2 hits), lane l owns z {4l.., 128+4l..}
     if (p.quant_out || p.znorm_out || p.stats) {
+      // (the next row's latent is requested before the current row is processed: the loop is a serial chain of L2 round trips
+      // otherwise -- 16 rows x ~1 us per warp at 8192 training rows)
+      float4 a_nx = make_float4(0.f, 0.f, 0.f, 0.f), b_nx = a_nx;
+      if (tile * 16 < p.n) {
+        a_nx = __ldg(reinterpret_cast<const float4*>(p.x + tile * 16 * VQ_Z + 4 * lane));
+        b_nx = __ldg(reinterpret_cast<const float4*>(p.x + tile * 16 * VQ_Z + 128 + 4 * lane));
+      }
 #pragma unroll 1
       for (int rr = 0; rr < 16; ++rr) {
         const long long row = tile * 16 + rr;
@@ -374,9 +381,11 @@ __global__ void __launch_bounds__(VqmCfg<NT>::WARPS * 32, VqmCfg<NT>::BLOCKS) vq
         const int src = (rr & 7) * 4;
         const int idx = __shfl_sync(0xffffffffu, rr < 8 ? best_g : best_h, src);
         const float inv = __shfl_sync(0xffffffffu, rr < 8 ? inv_g : inv_h, src);
-        const float* px = p.x + row * VQ_Z;
-        const float4 a = __ldg(reinterpret_cast<const float4*>(px + 4 * lane));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(px + 128 + 4 * lane));
+        const float4 a = a_nx, b = b_nx;
+        if (rr + 1 < 16 && row + 1 < p.n) {
+          a_nx = __ldg(reinterpret_cast<const float4*>(p.x + (row + 1) * VQ_Z + 4 * lane));
+          b_nx = __ldg(reinterpret_cast<const float4*>(p.x + (row + 1) * VQ_Z + 128 + 4 * lane));
+        }
         float xv[8] = {a.x * inv, a.y * inv, a.z * inv, a.w * inv, b.x * inv, b.y * inv, b.z * inv, b.w * inv};
         float q[8];
         float e = 0.f;

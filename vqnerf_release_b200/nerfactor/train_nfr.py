@@ -359,6 +359,18 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
     K = m.num_embed
     inv_gbs = 1.0 / float(global_bs)
     fused_bwd = FUSED_FORWARD and BATCHED_BACKWARD and FUSED_BACKWARD
+    prep = FUSED_FORWARD and BATCHED_BACKWARD
+    pack_done = None
+    if prep and CONCURRENT_HEADS:
+        # ONE refresh of all weight images (17 us), on a side stream under the clears / the embedding / the input copies
+        cur = torch.cuda.current_stream(m.device)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        st.side_streams[0].wait_event(ev)
+        with torch.cuda.stream(st.side_streams[0]):
+            abi.nets_repack_tc([nets[name].net.packed for name in NET_ORDER], 'tf32x3')
+            pack_done = torch.cuda.Event()
+            pack_done.record(st.side_streams[0])
     # everything the step accumulates into, cleared in one launch (d_h is stored, not accumulated, by the fused backward)
     abi.zero_batched([st.gflat, st.stats64, B['d_zenc']] + ([] if fused_bwd else [B['d_h']]), m.device)
 
@@ -370,11 +382,13 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
     e_tmp = abi.embed(xyz_c, emb.n_freqs)
     # launches shared by several networks (the step is launch-latency-bound at 8192 rows): ONE refresh of all weight images,
     # the x halves of the skip concats of the networks fed from the same input in one copy launch
-    prep = FUSED_FORWARD and BATCHED_BACKWARD
     if prep:
-        abi.nets_repack_tc([nets[name].net.packed for name in NET_ORDER], 'tf32x3')
+        if pack_done is None:
+            abi.nets_repack_tc([nets[name].net.packed for name in NET_ORDER], 'tf32x3')
         abi.copy_cols_batched([(e_tmp, emb.out_dims, E, E.shape[1], n, emb.out_dims, 0),
                                (e_tmp, emb.out_dims) + nets['fine_enc'].concat_job(E, E.shape[1])[2:]], m.device)
+        if pack_done is not None:
+            torch.cuda.current_stream(m.device).wait_event(pack_done)
     else:
         abi.copy_cols(e_tmp, emb.out_dims, E, E.shape[1], n, emb.out_dims)
     h = nets['fine_enc'].forward(E, E.shape[1], prepared=prep)
