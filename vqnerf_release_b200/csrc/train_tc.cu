@@ -53,7 +53,7 @@ __device__ __forceinline__ void dt_store16(uint32_t op, int r, int j0, const flo
   for (int qq = 0; qq < 2; ++qq) {
     float h[8], l[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { h[i] = tc::tf32_rna(v[8 * qq + i]); l[i] = v[8 * qq + i] - h[i]; }
+    for (int i = 0; i < 8; ++i) { h[i] = tc::tf32_rna_fast(v[8 * qq + i]); l[i] = v[8 * qq + i] - h[i]; }
     const uint32_t c0 = (uint32_t)(j0 / 4 + 2 * qq);
     tc::sts128(row + (((c0) ^ rx) << 4), make_float4(h[0], h[1], h[2], h[3]));
     tc::sts128(row + (((c0 + 1) ^ rx) << 4), make_float4(h[4], h[5], h[6], h[7]));
@@ -344,8 +344,16 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_wgrad_kernel(const __g
         if (m < p.M) {
           float* dst = p.dW + (long long)m * p.N + n0 + c16;
           const int cnt = min(16, nvalid - c16);
+          if (cnt == 16 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            // a thread owns a row of the tile: 4 vector reductions instead of 16 scalar ones (a quarter of the L1 wavefronts)
 #pragma unroll
-          for (int j = 0; j < 16; ++j) if (j < cnt) atomicAdd(dst + j, v[j]);
+            for (int q = 0; q < 4; ++q)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "f"(v[4 * q]), "f"(v[4 * q + 1]),
+                           "f"(v[4 * q + 2]), "f"(v[4 * q + 3]) : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (j < cnt) atomicAdd(dst + j, v[j]);
+          }
         }
         __syncwarp();
       }
