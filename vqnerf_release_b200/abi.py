@@ -746,10 +746,11 @@ def bwd_data_problem(dz, lddz, w, dx, lddx, yprev, ldyp, act_prev, accumulate, m
     return q
 
 
-def bwd_weights_problem(x, ldx, dz, lddz, dw, db, m, k, n):
+def bwd_weights_problem(x, ldx, dz, lddz, dw, db, m, k, n, dw_off=0):
+    """dW[dw_off:][k, n] += x[m, k]^T dz[m, n]; db[n] += column sums of dz (db may be None)."""
     q = L.DenseProblem()
     q.a, q.lda, q.w, q.ldw = _ptr_int(x), ldx, _ptr_int(dz), lddz
-    q.out, q.ldo, q.colsum = _ptr_int(dw), n, _ptr_int(db)
+    q.out, q.ldo, q.colsum = _ptr_int(dw, dw_off), n, _ptr_int(db)
     q.m, q.k, q.n = m, k, n
     return q
 

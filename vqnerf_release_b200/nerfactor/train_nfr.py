@@ -141,12 +141,20 @@ class _NetTrain:
             cur, ld = self.y[i], self.ld[i]
         return self.y[-1]
 
-    def weight_problems(self, dW: List[torch.Tensor], dB: List[torch.Tensor]) -> list:
+    def weight_problems(self, dW: List[torch.Tensor], dB: List[torch.Tensor], split_skip: bool = False) -> list:
         """The weight-gradient GEMMs of every layer (dW_i += x_i^T dz_i, dB_i += colsum dz_i) as problems of ONE batched
         launch; valid once the backward-data chain has filled every dz."""
         out = []
         for i, w in enumerate(self.widths):
             xin, ldin = (self.x, self.ldx) if i == 0 else (self.y[i - 1], self.ld[i - 1])
+            if split_skip and self.skip is not None and i == self.skip + 1:
+                # the layer after the skip concat as TWO problems -- rows [0, w_prev) of dW from y, the rest from the network
+                # input itself: nobody has to copy x behind y (three heads of a branch share one x: it stays in L2)
+                wp = self.widths[i - 1]
+                out.append(abi.bwd_weights_problem(xin, ldin, self.dz[i], self.dz[i].shape[1], dW[i], dB[i], self.n, wp, w))
+                out.append(abi.bwd_weights_problem(self.x, self.ldx, self.dz[i], self.dz[i].shape[1], dW[i], None, self.n,
+                                                   self.in_dim, w, dw_off=wp * w))
+                continue
             out.append(abi.bwd_weights_problem(xin, ldin, self.dz[i], self.dz[i].shape[1], dW[i], dB[i], self.n,
                                                self.k_in[i], w))
         return out
@@ -385,8 +393,10 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
     if prep:
         if pack_done is None:
             abi.nets_repack_tc([nets[name].net.packed for name in NET_ORDER], 'tf32x3')
-        abi.copy_cols_batched([(e_tmp, emb.out_dims, E, E.shape[1], n, emb.out_dims, 0),
-                               (e_tmp, emb.out_dims) + nets['fine_enc'].concat_job(E, E.shape[1])[2:]], m.device)
+        jobs = [(e_tmp, emb.out_dims, E, E.shape[1], n, emb.out_dims, 0)]
+        if not fused_bwd:                # (the fused backward reads x itself: weight_problems(split_skip=True))
+            jobs.append((e_tmp, emb.out_dims) + nets['fine_enc'].concat_job(E, E.shape[1])[2:])
+        abi.copy_cols_batched(jobs, m.device)
         if pack_done is not None:
             torch.cuda.current_stream(m.device).wait_event(pack_done)
     else:
@@ -405,7 +415,7 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
     vq_out = abi.vq_assign(z_enc, codebook, sel_mask=sel_mask, normalize_inputs=True, want_quantize=True,
                            stats=st.stats64, want_dw=True)                        # :575-577 (l2_normalize fused)
     z_vq, idx = vq_out['quantize'], vq_out['indices']
-    if prep:
+    if prep and not fused_bwd:
         abi.copy_cols_batched([nets[k].concat_job(z_enc, z) for k in ('diff_main', 'spec_main', 'rough_main')] +
                               [nets[k].concat_job(z_vq, z) for k in ('diff_vq', 'spec_vq', 'rough_vq')], m.device)
     if prep and CONCURRENT_HEADS:
@@ -533,7 +543,7 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
     if BATCHED_BACKWARD:
         head_w = []
         for name, _, _, _ in heads:
-            head_w += nets[name].weight_problems(st.dW[name], st.dB[name])
+            head_w += nets[name].weight_problems(st.dW[name], st.dB[name], split_skip=fused_bwd)
         if CONCURRENT_HEADS and prep:
             # the heads' 18 weight-gradient GEMMs (one full wave of CTAs) run on a side stream UNDER the encoder's backward
             # chain, whose per-layer launches fill less than half of the SMs
@@ -567,8 +577,8 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
         bn.backward_fused(d_zenc, z, fe.dz[-1], fe.dz[-1].shape[1], 0, act_done=True, din_y=fe.y[-1], ld_din_y=fe.ld[-1],
                           din_act=fe.acts[-1])
         fe.backward_fused(None, 0, None, 0, 0, act_done=True)
-        wlist += bn.weight_problems(st.dW['bottleneck'], st.dB['bottleneck'])
-        wlist += fe.weight_problems(st.dW['fine_enc'], st.dB['fine_enc'])
+        wlist += bn.weight_problems(st.dW['bottleneck'], st.dB['bottleneck'], split_skip=True)
+        wlist += fe.weight_problems(st.dW['fine_enc'], st.dB['fine_enc'], split_skip=True)
     else:
         bn.backward(d_zenc, z, st.dW['bottleneck'], st.dB['bottleneck'], d_h, d_h.shape[1], weight_list=wl)
         fe.backward(d_h, d_h.shape[1], st.dW['fine_enc'], st.dB['fine_enc'], weight_list=wl)
