@@ -113,6 +113,8 @@ int vqn_net_forward(vqn_net* net, const float* x, int64_t n, float* y, int preci
 /* Embedder.__call__ (networks/embedder.py:23-47, kwargs of models/shape.py:82-89):
  * out[n, 3 + 6*n_freqs] = [x, sin(x 2^0), cos(x 2^0), ..., sin(x 2^(F-1)), cos(x 2^(F-1))] */
 int vqn_embed(vqn_ctx* ctx, const float* x, int64_t n, int n_freqs, float* out, vqn_stream stream);
+/* ... into rows of leading dimension ld_out >= 3 + 6 n_freqs (columns beyond the embedding are left untouched) */
+int vqn_embed_ld(vqn_ctx* ctx, const float* x, int64_t n, int n_freqs, float* out, int64_t ld_out, vqn_stream stream);
 
 /* Model._pred_enc_at (models/vq_nfr.py:771-784): z[n,256] = bottleneck(fine_enc(embed(pts))).
  * row_idx (optional, int32 [n]) gathers pts rows (mask compaction, vq_nfr.py:283-291); z is compact.

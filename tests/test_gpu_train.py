@@ -456,6 +456,14 @@ def test_training_small_kernels(cuda_dev):
     abi.vq_backward(z, idx, cb, dq, 0.01, db, accumulate=True, act=L.act_code('sigmoid'), dz_out=dz)
     assert torch.equal(da, db)
     assert torch.allclose(dz[:, :256], da * z * (1 - z), rtol=1e-6, atol=1e-9) and float(dz[:, 256:].abs().sum()) == 0
+    # embedding written straight into a padded buffer (vqn_embed_ld): same values, padding untouched
+    pts = (torch.rand((257, 3), generator=g) * 2 - 1).to(cuda_dev)
+    e0 = abi.embed(pts, 10)
+    e1 = torch.full((257, 64), 9.0, device=cuda_dev)
+    abi.embed(pts, 10, out=e1)
+    assert torch.equal(e1[:, :63], e0) and float((e1[:, 63] - 9.0).abs().sum()) == 0
+    with pytest.raises(ValueError):
+        abi.embed(pts, 10, out=torch.zeros((257, 60), device=cuda_dev))
     # batched column copies: the 16-byte form and the scalar form in the same launch
     src = torch.randn((500, 264), generator=g).to(cuda_dev)
     d1, d2 = torch.zeros((500, 520), device=cuda_dev), torch.zeros((500, 7), device=cuda_dev)

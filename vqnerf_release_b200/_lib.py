@@ -105,6 +105,7 @@ SIGNATURES = {
     'vqn_net_out_dim': (_I, [_P]),
     'vqn_net_forward': (_I, [_P, _P, _L, _P, _I, _P]),
     'vqn_embed': (_I, [_P, _P, _L, _I, _P, _P]),
+    'vqn_embed_ld': (_I, [_P, _P, _L, _I, _P, _L, _P]),
     'vqn_pred_enc_at': (_I, [_P, _P, _P, _I, _P, _P, _P, _L, _P, _I, _P]),
     'vqn_pred_heads': (_I, [_P, _P, _P, _P, _P, _P, _L, _F, _F, _P, _P, _P, _I, _P]),
     'vqn_mlp_main': (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _L, _F, _F, _P, _P, _P, _P, _I, _P]),

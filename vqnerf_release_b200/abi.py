@@ -129,11 +129,16 @@ class PackedNet:
             pass
 
 
-def embed(x: torch.Tensor, n_freqs: int) -> torch.Tensor:
+def embed(x: torch.Tensor, n_freqs: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Embedder.__call__ (embedder.py:23-47).  out: an existing [n, ld >= 3 + 6 n_freqs] buffer to fill in place (columns
+    beyond the embedding are left untouched)."""
     x = _f(x)
-    out = torch.empty((x.shape[0], 3 + 6 * n_freqs), dtype=F32, device=x.device)
     c = _ctx(x)
-    L.check(c.lib.vqn_embed(c.handle, L.ptr(x), x.shape[0], n_freqs, L.ptr(out), L.stream_ptr(x.device)))
+    if out is None:
+        out = torch.empty((x.shape[0], 3 + 6 * n_freqs), dtype=F32, device=x.device)
+    elif out.dtype != F32 or out.dim() != 2 or out.shape[0] != x.shape[0] or not out.is_contiguous():
+        raise ValueError('embed: out must be a contiguous float32 [n, ld] tensor')
+    L.check(c.lib.vqn_embed_ld(c.handle, L.ptr(x), x.shape[0], n_freqs, L.ptr(out), out.shape[1], L.stream_ptr(x.device)))
     return out
 
 

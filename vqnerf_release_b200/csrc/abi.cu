@@ -172,7 +172,7 @@ extern "C" int vqn_gen_light_xyz(int h, int w, double radius, double* xyz, doubl
 // ---------------------------------------------------------------------------------------------
 // small element-wise kernels
 // ---------------------------------------------------------------------------------------------
-__global__ void embed_kernel(const float* __restrict__ x, long long n, int n_freqs, float* __restrict__ out) {
+__global__ void embed_kernel(const float* __restrict__ x, long long n, int n_freqs, float* __restrict__ out, long long ld) {
   // Embedder.__call__: one thread per (row, output column); precise sinf/cosf on x * 2^k
   int d = 3 + 6 * n_freqs;
   long long total = n * d;
@@ -188,17 +188,22 @@ __global__ void embed_kernel(const float* __restrict__ x, long long n, int n_fre
       float a = x[r * 3 + (w % 3)] * exp2f((float)f);
       v = w < 3 ? sinf(a) : cosf(a);
     }
-    out[i] = v;
+    out[r * ld + c] = v;
   }
 }
 
+extern "C" int vqn_embed_ld(vqn_ctx* ctx, const float* x, int64_t n, int n_freqs, float* out, int64_t ld_out, vqn_stream s);
 extern "C" int vqn_embed(vqn_ctx* ctx, const float* x, int64_t n, int n_freqs, float* out, vqn_stream s) {
+  return vqn_embed_ld(ctx, x, n, n_freqs, out, 3 + 6 * (int64_t)n_freqs, s);
+}
+extern "C" int vqn_embed_ld(vqn_ctx* ctx, const float* x, int64_t n, int n_freqs, float* out, int64_t ld_out, vqn_stream s) {
   VQN_CHECK_ARG(ctx && x && out && n >= 0 && n_freqs >= 0 && n_freqs <= 16, "embed args");
+  VQN_CHECK_ARG(ld_out >= 3 + 6 * n_freqs, "embed: ld_out < 3 + 6 n_freqs");
   if (n == 0) return VQN_OK;
   long long total = n * (3 + 6 * n_freqs);
   int blocks = (int)((total + 255) / 256 < (long long)ctx->sm_count * 16 ? (total + 255) / 256
                                                                           : (long long)ctx->sm_count * 16);
-  embed_kernel<<<blocks, 256, 0, vqn_cs(s)>>>(x, n, n_freqs, out);
+  embed_kernel<<<blocks, 256, 0, vqn_cs(s)>>>(x, n, n_freqs, out, (long long)ld_out);
   VQN_LAUNCHED(ctx);
   return VQN_OK;
 }

@@ -387,16 +387,19 @@ def train_iter(model, batch, optimizer: Adam, global_bs: int, thres=None, roll=N
     E = B['embed']
     c = L.Context.get(m.device)
     xyz_c = xyz.contiguous()
-    e_tmp = abi.embed(xyz_c, emb.n_freqs)
+    e_tmp = None if fused_bwd else abi.embed(xyz_c, emb.n_freqs)
     # launches shared by several networks (the step is launch-latency-bound at 8192 rows): ONE refresh of all weight images,
     # the x halves of the skip concats of the networks fed from the same input in one copy launch
     if prep:
         if pack_done is None:
             abi.nets_repack_tc([nets[name].net.packed for name in NET_ORDER], 'tf32x3')
-        jobs = [(e_tmp, emb.out_dims, E, E.shape[1], n, emb.out_dims, 0)]
-        if not fused_bwd:                # (the fused backward reads x itself: weight_problems(split_skip=True))
-            jobs.append((e_tmp, emb.out_dims) + nets['fine_enc'].concat_job(E, E.shape[1])[2:])
-        abi.copy_cols_batched(jobs, m.device)
+        if fused_bwd:
+            # straight into the padded input buffer; the fused backward reads x itself (weight_problems(split_skip=True)),
+            # so nobody needs the copy of x behind fine_enc's skip layer
+            abi.embed(xyz_c, emb.n_freqs, out=E)
+        else:
+            abi.copy_cols_batched([(e_tmp, emb.out_dims, E, E.shape[1], n, emb.out_dims, 0),
+                                   (e_tmp, emb.out_dims) + nets['fine_enc'].concat_job(E, E.shape[1])[2:]], m.device)
         if pack_done is not None:
             torch.cuda.current_stream(m.device).wait_event(pack_done)
     else:
