@@ -145,7 +145,7 @@ int vqn_get_codebook(vqn_ctx* ctx, const float* raw, int z_dim, int k, float* ou
 int vqn_l2_normalize_rows(vqn_ctx* ctx, const float* x, int64_t n, int d, float* out, vqn_stream stream);
 
 /* VectorQuantizerEMA.__call__ forward half (networks/vq_layers.py:277-302,327-330).
- *   inputs   [n,Z] (Z == 256)   codebook [Z,K] (already normalised, 1 <= K <= 1024)
+ *   inputs   [n,Z] (Z == 256, base 32-byte aligned)   codebook [Z,K] (already normalised, 1 <= K <= 1024)
  *   sel_mask [K] or NULL: 1 = codeword selectable, 0 = dropped (the `roll >= thres` mask, :284-290);
  *   normalize_inputs != 0 fuses the caller's l2_normalize(z_enc, axis=1) (vq_nfr.py:575).
  * Outputs (each may be NULL): indices int64 [n] (0-based; callers add 1, vq_nfr.py:578), quantize [n,Z]

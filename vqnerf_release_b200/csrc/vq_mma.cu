@@ -135,13 +135,26 @@ __device__ __forceinline__ void compute_phase(const float4 (&vg)[4], const float
   }
 }
 
+// One phase = 64 latent columns of the two rows of a lane, as two 32-BYTE loads per row (LDG.256, sm_100): lane (g, t) owns
+// columns 32 C + 8 t + [0, 8) of every 32-column block C -- the k order inside the MMAs is free as long as the B fragments
+// (stage_chunk) use the same one.  A warp-level load touches 16 rows x 128 contiguous bytes whatever its width, so half the
+// load instructions are half the L1 wavefronts of the 16-byte form.  vg[2m], vg[2m+1] = the two halves of block c0/2 + m.
+template <bool STREAM>
+__device__ __forceinline__ void ldg_f8(const float* p, float4& lo, float4& hi) {
+  if (STREAM)
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w) : "l"(p));
+  else
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w) : "l"(p));
+}
 template <bool STREAM>
 __device__ __forceinline__ void load_phase(float4 (&vg)[4], float4 (&vh)[4], const float* pg, const float* ph,
                                            int c0) {
 #pragma unroll
-  for (int cc = 0; cc < 4; ++cc) {
-    vg[cc] = ldg_f4<STREAM>(pg + 16 * (c0 + cc));
-    vh[cc] = ldg_f4<STREAM>(ph + 16 * (c0 + cc));
+  for (int m = 0; m < 2; ++m) {
+    ldg_f8<STREAM>(pg + 32 * (c0 / 2 + m), vg[2 * m], vg[2 * m + 1]);
+    ldg_f8<STREAM>(ph + 32 * (c0 / 2 + m), vh[2 * m], vh[2 * m + 1]);
   }
 }
 
@@ -176,11 +189,11 @@ __global__ void __launch_bounds__(VqmCfg<NT>::WARPS * 32, VqmCfg<NT>::BLOCKS) vq
   }
   auto stage_chunk = [&](int ch) {
     // B fragments of chunk ch: lane (g,t) of (k-step s = 2c+u, n-tile j) holds cb[z0][k], cb[z0+1][k],
-    // z0 = 16c + 4t + 2u, k = ch*KCH + 8j + g, each split into tf32 hi / lo
+    // z0 = 32 (c / 2) + 8t + 4 (c % 2) + 2u (the column order of load_phase), k = ch*KCH + 8j + g, each split into tf32 hi / lo
     for (int i = tid; i < 32 * NT * 32; i += VQM_THREADS) {
       const int ln = i & 31, j = (i >> 5) % NT, s = i / (32 * NT);
       const int gg = ln >> 2, tt = ln & 3, c = s >> 1, u = s & 1;
-      const int z0 = 16 * c + 4 * tt + 2 * u, k = ch * KCH + 8 * j + gg;
+      const int z0 = 32 * (c >> 1) + 8 * tt + 4 * (c & 1) + 2 * u, k = ch * KCH + 8 * j + gg;
       float b0 = 0.f, b1 = 0.f;
       if (k < K) { b0 = p.cb[(size_t)z0 * K + k]; b1 = p.cb[(size_t)(z0 + 1) * K + k]; }
       // {b0.hi, b1.hi} as tf32 and the bf16 pairs {bf16(b0.hi), bf16(b1.hi)} (meets the x_lo slots) and
@@ -430,7 +443,7 @@ __global__ void __launch_bounds__(VqmCfg<NT>::WARPS * 32, VqmCfg<NT>::BLOCKS) vq
     auto rowptr = [&](long long tile, int add) {
       long long r = tile * 16 + g + add;
       if (r >= p.n) r = p.n - 1;                                 // clamp: loaded, never used
-      return p.x + r * VQ_Z + 4 * t;
+      return p.x + r * VQ_Z + 8 * t;
     };
     const float* pg = rowptr(first, 0);
     const float* ph = rowptr(first, 8);
@@ -509,6 +522,10 @@ template <int NT, bool CHUNKED>
 static int launch_nt(vqn_ctx* ctx, VqParams p, cudaStream_t s) {
   constexpr int VQM_WARPS = VqmCfg<NT>::WARPS, VQM_THREADS = VQM_WARPS * 32;
   const int K = p.K;
+  if (reinterpret_cast<uintptr_t>(p.x) & 31) {
+    vqn_set_error("vq_assign: inputs must be 32-byte aligned (32-byte row loads)");
+    return VQN_ERR_INVALID_ARG;
+  }
   const bool smem_dw = p.stats && p.want_dw && K <= 32;
   size_t smem = sizeof(float4) * 32 * NT * 32 + sizeof(float) * 8 * NT +
                 (CHUNKED ? sizeof(float) * 5 * VQM_WARPS * VQM_TPW * 16 : 0) +
