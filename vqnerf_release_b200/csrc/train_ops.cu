@@ -387,14 +387,22 @@ __global__ void combine_bwd_kernel(const float* __restrict__ base, const float* 
 // sim_smooth (:958-972): -log(min_{i != j} || cn_i - cn_j ||), cn = get_codebook(raw) columns.  One block.
 // The gradient reaches only the closest pair; the K diagonal zeros get weight 0 (TF's 0*0.5/0 there is defined
 // as 0 here).
-__global__ void __launch_bounds__(256) sim_loss_kernel(const float* __restrict__ raw, int Z, int K, float scale,
+__global__ void __launch_bounds__(256) sim_loss_kernel(const float* raw, int Z, int K, float scale,
                                                        float* __restrict__ loss_out, float* __restrict__ d_raw,
-                                                       int accumulate) {
-  extern __shared__ float sm[];      // inv[K] | best_d[8] | best_pair[8]
+                                                       int accumulate, int staged) {
+  extern __shared__ float sm[];      // inv[K] | best_d[8] | best_pair[8] | (small codebooks) clip(raw) [Z*K]
   float* inv = sm;
   float* bd = inv + K;
   int* bp = reinterpret_cast<int*>(bd + 8);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // a small codebook (the shipped K = 15: 15 KB) is staged once with coalesced loads: the column reads below have a stride of
+  // K floats, and from global memory every one of the ~14 dependent pair iterations per warp was an L2 round trip
+  if (staged) {
+    float* cs = reinterpret_cast<float*>(bp + 8);
+    for (int i = tid; i < Z * K; i += 256) cs[i] = fminf(fmaxf(raw[i], 0.f), 1.f);
+    __syncthreads();
+    raw = cs;
+  }
   for (int k = warp; k < K; k += 8) {
     float s = 0.f;
     for (int z = lane; z < Z; z += 32) { float c = fminf(fmaxf(raw[(size_t)z * K + k], 0.f), 1.f); s = fmaf(c, c, s); }
@@ -678,8 +686,9 @@ extern "C" int vqn_material_combine_backward(vqn_ctx* ctx, const float* basecolo
 extern "C" int vqn_codebook_sim_loss(vqn_ctx* ctx, const float* raw_codebook, int z_dim, int k, float grad_scale,
                                      float* loss_out, float* d_raw, int accumulate, vqn_stream stream) {
   VQN_CHECK_ARG(ctx && raw_codebook && d_raw && z_dim > 0 && z_dim <= 256 && k >= 1 && k <= 1024, "sim_loss args");
-  sim_loss_kernel<<<1, 256, sizeof(float) * (k + 16), vqn_cs(stream)>>>(raw_codebook, z_dim, k, grad_scale, loss_out,
-                                                                       d_raw, accumulate);
+  const int staged = (size_t)z_dim * k * sizeof(float) <= 40 * 1024 ? 1 : 0;
+  sim_loss_kernel<<<1, 256, sizeof(float) * (k + 16 + (staged ? (size_t)z_dim * k : 0)), vqn_cs(stream)>>>(
+      raw_codebook, z_dim, k, grad_scale, loss_out, d_raw, accumulate, staged);
   VQN_LAUNCHED(ctx);
   return VQN_OK;
 }
