@@ -8,7 +8,7 @@ import sys
 
 def main():
     rows = list(csv.reader(open(sys.argv[1])))
-    first = sys.argv[2] if len(sys.argv) > 2 else 'zero_batched'
+    first = sys.argv[2] if len(sys.argv) > 2 else 'tc_pack_batched'
     for i, r in enumerate(rows):
         if 'Kernel Name' in r:
             hdr, start = r, i
